@@ -1,0 +1,260 @@
+"""Pins the CPU oracle (oracle/) against the reference's own known-answer and behavioural tests
+(SURVEY.md §8c).  Each test cites the reference test it restates.  CPU only."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from trajopt_b200 import capi, problems, robots
+from trajopt_b200.capi import ROLE_CNT, ROLE_COST, TERM_JOINT_ACC, TERM_JOINT_POS, TERM_JOINT_VEL
+
+dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+# ---------------------------------------------------------------- trajopt_sco/test/solver-utils-unit.cpp
+def _square(o, coeffs, const, halved, force_diag):
+    n = len(coeffs)
+    Q, q, nnz = np.zeros((n, n)), np.zeros(n), C.c_int(0)
+    o.lib().oracle_square_to_dense(dp(np.array(coeffs, float)), n, C.c_double(const), int(halved), int(force_diag),
+                                   dp(Q), dp(q), C.byref(nnz))
+    return Q, q, nnz.value
+
+
+def test_expr_to_eigen_known_answers(oracle):
+    # solver-utils-unit.cpp:19-125: x_affine = [3,2].x + 1
+    row, u = np.zeros(2), C.c_double(0)
+    oracle.lib().oracle_aff_to_row(dp(np.array([3.0, 2.0])), 2, C.c_double(1.0), dp(row), C.byref(u))
+    assert row.tolist() == [3.0, 2.0] and u.value == -1.0
+    Q, q, nnz = _square(oracle, [3, 2], 1, False, False)
+    assert Q.tolist() == [[9, 6], [6, 4]] and q.tolist() == [6, 4] and nnz == 4
+    Q, q, nnz = _square(oracle, [3, 2], 1, True, False)
+    assert Q.tolist() == [[18, 12], [12, 8]] and q.tolist() == [6, 4] and nnz == 4
+    for halved, fd, scale, want_nnz in ((False, False, 1, 1), (True, False, 2, 1), (False, True, 1, 2), (True, True, 2, 2)):
+        Q, q, nnz = _square(oracle, [0, 2], 1, halved, fd)
+        assert Q.tolist() == [[0, 0], [0, 4 * scale]] and nnz == want_nnz
+
+
+def _csc(o, M, upper=False):
+    M = np.array(M, float)
+    ri, cp, d, nnz = np.zeros(M.size, np.int64), np.zeros(M.shape[1] + 1, np.int64), np.zeros(M.size), C.c_int(0)
+    o.lib().oracle_dense_to_csc(dp(M), M.shape[0], M.shape[1], int(upper), ri.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                cp.ctypes.data_as(C.POINTER(C.c_longlong)), dp(d), C.byref(nnz))
+    return d[:nnz.value].tolist(), ri[:nnz.value].tolist(), cp.tolist()
+
+
+def test_eigen_to_csc_known_answers(oracle):
+    # solver-utils-unit.cpp:144-244
+    assert _csc(oracle, [[1, 2, 3], [1, 0, 9], [1, 8, 0]]) == ([1, 1, 1, 2, 8, 3, 9], [0, 1, 2, 0, 2, 0, 1], [0, 3, 5, 7])
+    assert _csc(oracle, [[0, 2, 0], [7, 0, 0], [0, 0, 0]]) == ([7, 2], [1, 0], [0, 1, 2, 2])
+    assert _csc(oracle, [[0, 0, 0], [0, 0, 0], [0, 6, 0]]) == ([6], [2], [0, 0, 1, 1])
+    assert _csc(oracle, [[1, 2, 0], [2, 4, 0], [0, 0, 9]], upper=True) == ([1, 2, 4, 9], [0, 0, 1, 2], [0, 1, 3, 4])
+
+
+def test_quad_expr_values(oracle):
+    # solver-interface-unit.cpp:136-237: (2*x0)(x1) at (10,20) = 400; (3*x0-3)(2*x1-5) at (10,20) = 945
+    x = np.array([10.0, 20.0])
+    one = lambda aff, c, qc: oracle.lib().oracle_quad_value(dp(np.array(aff, float)), 2, C.c_double(c),
+                                                          (C.c_int * 1)(0), (C.c_int * 1)(1), dp(np.array([qc], float)), 1, dp(x))
+    assert one([0, 0], 0, 2.0) == 400.0
+    # (3x0-3)(2x1-5) = 6 x0 x1 - 15 x0 - 6 x1 + 15
+    assert one([-15, -6], 15, 6.0) == 945.0
+
+
+# ---------------------------------------------------------------- trajopt_sco/test/small-problems-unit.cpp:48-172
+@pytest.mark.parametrize("pid,expect,tol", [(0, [0, 1, 2], 1e-3), (1, [1, 7, 2], 1e-2), (2, [1, 1], 1e-2),
+                                            (3, [0, 0], 1e-2), (4, [1, 1], 1e-2), (5, [0, math.sqrt(3)], 1e-2)])
+def test_small_problems(oracle, pid, expect, tol):
+    x, status, n = np.zeros(8), C.c_int(-1), C.c_int(0)
+    assert oracle.lib().oracle_small_problem(pid, dp(x), C.byref(status), C.byref(n)) == 0
+    assert status.value == capi.OPT_CONVERGED
+    np.testing.assert_allclose(x[:n.value], expect, atol=tol)
+
+
+# ---------------------------------------------------------------- trajopt/test/joint_costs_unit.cpp
+def _joint_problem(kind, cost_targ):
+    robot = robots.pr2_arm("r", continuous_limit=4 * math.pi, with_spheres=False)
+    T, D = 10, 7
+    terms = [problems.joint_term(kind, ROLE_COST, D, 0, T - 1, coeffs=10.0, targets=cost_targ, T=T),
+             problems.joint_term(kind, ROLE_CNT, D, 0, 0, coeffs=10.0, targets=0.0, T=T)]
+    return capi.ProblemDesc(robot, T, terms, np.zeros((1, T, D)))
+
+
+def test_equality_joint_pos(oracle):  # joint_costs_unit.cpp:63-141
+    r = oracle.solve_batch(_joint_problem(TERM_JOINT_POS, -0.1))
+    x = r["x"][0]
+    np.testing.assert_allclose(x[0], 0.0, atol=1e-4)
+    np.testing.assert_allclose(x[1:], -0.1, atol=1e-2)
+
+
+def test_equality_joint_vel(oracle):  # joint_costs_unit.cpp:264-345
+    r = oracle.solve_batch(_joint_problem(TERM_JOINT_VEL, 0.1))
+    v = np.diff(r["x"][0], axis=0)
+    np.testing.assert_allclose(v[0], 0.0, atol=1e-4)
+    np.testing.assert_allclose(v[1:], 0.1, atol=1e-2)
+
+
+def test_equality_joint_acc(oracle):  # joint_costs_unit.cpp:677-760
+    r = oracle.solve_batch(_joint_problem(TERM_JOINT_ACC, 0.1))
+    a = np.diff(r["x"][0], n=2, axis=0)
+    np.testing.assert_allclose(a[0], 0.0, atol=1e-4)
+    np.testing.assert_allclose(a[1:], 0.1, atol=1e-2)
+
+
+def test_finite_difference_stencils(oracle):  # joint_costs_unit.cpp:883-937 (x = t^3): Cost::value == sum of squares
+    T, D, dt = 10, 7, 0.1
+    traj = np.repeat(((np.arange(T) * dt) ** 3)[:, None], D, axis=1)[None]
+    robot = robots.pr2_arm("r", with_spheres=False)
+    terms = [problems.joint_term(TERM_JOINT_VEL, ROLE_COST, D, 0, T - 1), problems.joint_term(TERM_JOINT_ACC, ROLE_COST, D, 0, T - 1)]
+    d = capi.ProblemDesc(robot, T, terms, traj)
+    out = oracle.convexify_batch(d, traj)
+    t = np.arange(T) * dt
+    v = (3 * t[:-1] ** 2 + 3 * t[:-1] * dt + dt * dt) * dt
+    a = (6 * t[:-2] + 6 * dt) * dt * dt
+    np.testing.assert_allclose(out["cost_vals"][0], [D * np.sum(v ** 2), D * np.sum(a ** 2)], rtol=1e-12)
+
+
+# ---------------------------------------------------------------- kinematics pins
+def test_fk_closed_form(oracle):
+    """FK of the PR2 right arm at zero is a straight arm: tool at x = -0.05+0.1+0.4+0.321+0.18 (URDF origins)."""
+    robot = robots.pr2_arm("r")
+    d = capi.ProblemDesc(robot, 1, [], np.zeros((1, 1, 7)))
+    fr = np.zeros((len(robot["segments"]), 12))
+    oracle.lib().oracle_fk(C.byref(d.c.robot), dp(np.zeros(7)), dp(fr))
+    np.testing.assert_allclose(fr[-1, 9:], [-0.05 + 0.1 + 0.4 + 0.321 + 0.18, -0.188, 0.051 + 0.739675], atol=1e-15)
+    np.testing.assert_allclose(fr[-1, :9], np.eye(3).ravel(), atol=1e-15)
+    q = np.array([0.3, -0.2, 0.5, -1.0, 0.7, -0.4, 0.9])
+    oracle.lib().oracle_fk(C.byref(d.c.robot), dp(q), dp(fr))
+    R, p = robots.fk_numpy(robot, q)[-1]
+    np.testing.assert_allclose(fr[-1, :9].reshape(3, 3), R, atol=1e-14)
+    np.testing.assert_allclose(fr[-1, 9:], p, atol=1e-14)
+
+
+def test_geometric_jacobian_vs_numeric(oracle):
+    """calcJacobian restatement vs central differences of FK (the check tesseract's numericalJacobian does)."""
+    robot = robots.pr2_arm("r")
+    d = capi.ProblemDesc(robot, 1, [], np.zeros((1, 1, 7)))
+    q = np.array([0.3, -0.2, 0.5, -1.0, 0.7, -0.4, 0.9])
+    J = np.zeros((6, 7))
+    link = robot["tool"]
+    oracle.lib().oracle_jacobian(C.byref(d.c.robot), dp(q), link, None, dp(J))
+    eps = 1e-6
+    for j in range(7):
+        qp, qm = q.copy(), q.copy()
+        qp[j] += eps
+        qm[j] -= eps
+        Rp, pp = robots.fk_numpy(robot, qp)[link]
+        Rm, pm = robots.fk_numpy(robot, qm)[link]
+        np.testing.assert_allclose(J[:3, j], (pp - pm) / (2 * eps), atol=1e-8)
+        W = (Rp - Rm) / (2 * eps) @ robots.fk_numpy(robot, q)[link][0].T  # skew(omega)
+        np.testing.assert_allclose(J[3:, j], [W[2, 1], W[0, 2], W[1, 0]], atol=1e-8)
+
+
+def test_transform_error_conventions(oracle):
+    """calcTransformError: translation of t1^-1 t2 and axis*angle with the angle in [-pi, pi]."""
+    err = np.zeros(6)
+    t1 = np.array([0.1, 0.2, 0.3, 1, 0, 0, 0.0])
+    for ang in (0.3, -0.3, 3.0, -3.0):
+        t2 = np.array([0.4, 0.2, 0.3, math.cos(ang / 2), 0, 0, math.sin(ang / 2)])
+        oracle.lib().oracle_transform_error(dp(t1), dp(t2), dp(err))
+        np.testing.assert_allclose(err, [0.3, 0, 0, 0, 0, ang], atol=1e-14)
+    # quaternion double cover: -q is the same rotation, must give the same error
+    t2 = -np.array([0, 0, 0, math.cos(0.2), math.sin(0.2), 0, 0.0])
+    t2[:3] = [0.4, 0.2, 0.3]
+    oracle.lib().oracle_transform_error(dp(t1), dp(t2), dp(err))
+    np.testing.assert_allclose(err[3:], [0.4, 0, 0], atol=1e-14)
+
+
+def test_cart_pose_fd_jacobian_matches_analytic(oracle):
+    """kinematic_costs_unit.cpp:60-97 pins the CartPose Jacobian against a numeric one to 1e-5; here the
+    restated finite-difference Jacobian is checked against the geometric Jacobian near zero error, where
+    d(err)/dq = [R_t^T J_lin ; R_t^T J_ang]."""
+    d = problems.config1(B=4, T=5)
+    x = d.init_traj.copy()
+    out = oracle.convexify_batch(d, x)
+    robot = d.robot_spec
+    for b in range(4):
+        q = x[b, -1]
+        J = np.zeros((6, 7))
+        oracle.lib().oracle_jacobian(C.byref(d.c.robot), dp(q), robot["tool"], None, dp(J))
+        Rt = robots.fk_numpy(robot, q)[robot["tool"]][0]
+        want = np.vstack([Rt.T @ J[:3], Rt.T @ J[3:]])
+        np.testing.assert_allclose(out["cart_jac"][b], want, atol=2e-5)
+        np.testing.assert_allclose(out["cart_err"][b], 0.0, atol=1e-9)
+
+
+# ---------------------------------------------------------------- trajopt/test/cart_position_optimization_unit.cpp:55-135
+def _pose_close(robot, q, link, target_R, target_p, tol_p, tol_R):
+    R, p = robots.fk_numpy(robot, q)[link]
+    assert np.linalg.norm(p - target_p) <= tol_p * min(np.linalg.norm(p), np.linalg.norm(target_p))  # Eigen isApprox
+    np.testing.assert_allclose(R, target_R, atol=tol_R)
+
+
+def test_cart_position_optimization(oracle):
+    robot = robots.pr2_arm("r", continuous_limit=4 * math.pi, with_spheres=False)
+    q_goal = np.array([0, 0, 0, -1.0, 0, -1, 0.0])
+    Rg, pg = robots.fk_numpy(robot, q_goal)[robot["tool"]]
+    tgt = np.concatenate([pg, robots.rot_to_wxyz(Rg)])
+    d = capi.ProblemDesc(robot, 1, [problems.cart_pose_term(ROLE_CNT, 0, robot["tool"], target_pose=tgt)], np.zeros((1, 1, 7)))
+    r = oracle.solve_batch(d)
+    _pose_close(robot, r["x"][0, 0], robot["tool"], Rg, pg, 1e-4, 1e-4)
+    assert r["cnt_viols"].max() < 1e-4
+
+
+def test_numerical_ik1(oracle):  # numerical_ik_unit.cpp:60-124 + data/config/numerical_ik1.json
+    robot = robots.pr2_arm("l", continuous_limit=4 * math.pi, with_spheres=False)
+    tgt = np.array([0.4, 0, 0.8, 0, 0, 1, 0.0])
+    d = capi.ProblemDesc(robot, 1, [problems.cart_pose_term(ROLE_CNT, 0, robot["tool"], target_pose=tgt)], np.zeros((1, 1, 7)))
+    r = oracle.solve_batch(d)
+    R, p = robots.fk_numpy(robot, r["x"][0, 0])[robot["tool"]]
+    np.testing.assert_allclose(p, [0.4, 0, 0.8], atol=1e-3)
+    np.testing.assert_allclose(R, [[-1, 0, 0], [0, 1, 0], [0, 0, -1]], atol=1e-3)
+
+
+# ---------------------------------------------------------------- trajopt/test/simple_collision_unit.cpp:60-123
+def _spherebot_problem():
+    robot = robots.spherebot()
+    terms = [problems.collision_term(ROLE_COST, 0, 0, margin=0.3, coeff=1.0, buffer=0.5),  # JSON route => buffer 0.5 (quirk 6)
+             problems.joint_term(TERM_JOINT_POS, ROLE_COST, 2, 0, 0, coeffs=1.0, targets=0.0),
+             problems.collision_term(ROLE_CNT, 0, 0, margin=0.2, coeff=1.0, buffer=0.5)]
+    return capi.ProblemDesc(robot, 1, terms, np.array([[[-0.75, 0.75]]]), obstacles=robots.SPHEREBOT_OBSTACLES,
+                            obstacles_per_traj=False)
+
+
+def _spherebot_dists(q):
+    c = np.array([q[0], q[1], 0.0])
+    return np.linalg.norm(robots.SPHEREBOT_OBSTACLES[:, :3] - c, axis=1) - 0.5 - 0.5
+
+
+def test_simple_collision_spherebot(oracle):
+    d = _spherebot_problem()
+    assert _spherebot_dists(d.init_traj[0, 0]).min() < 0.2  # initial trajectory in collision (w.r.t. margin 0.2)
+    r = oracle.solve_batch(d)
+    assert _spherebot_dists(r["x"][0, 0]).min() >= 0.2 - 1e-4  # final collision free
+    assert r["cnt_viols"].max() < 1e-4
+
+
+# ---------------------------------------------------------------- QP optimality (KKT) of the OSQP-equivalent solver
+def test_qp_dense_known_answer(oracle):
+    """min 1/2 x'Px + q'x, the OSQP documentation example: P=[[4,1],[1,2]], q=[1,1], A=[[1,1],[1,0],[0,1]],
+    l=[1,0,0], u=[1,0.7,0.7] -> x = (0.3, 0.7)."""
+    P = np.array([[4.0, 1], [1, 2]])
+    q = np.array([1.0, 1])
+    A = np.array([[1.0, 1], [1, 0], [0, 1]])
+    l, u = np.array([1.0, 0, 0]), np.array([1.0, 0.7, 0.7])
+    x, y = np.zeros(2), np.zeros(3)
+    st, it, pol = C.c_int(0), C.c_int(0), C.c_int(0)
+    oracle.lib().oracle_qp_dense(2, 3, dp(P), dp(q), dp(A), dp(l), dp(u), None, dp(x), dp(y), C.byref(st), C.byref(it), C.byref(pol))
+    assert st.value == 1 and pol.value == 1
+    np.testing.assert_allclose(x, [0.3, 0.7], atol=1e-9)
+    np.testing.assert_allclose(P @ x + q + A.T @ y, 0, atol=1e-8)
+
+
+def test_qp_kkt_on_trajectory_subproblems(oracle):
+    """Every QP the SQP loop would solve first (trust 0.1, mu 10) is a KKT point after polish."""
+    for d in (problems.config1(B=6, T=12), problems.config2(B=6, T=12)):
+        r = oracle.qp_solve_batch(d, d.init_traj, 0.1, 10.0)
+        assert (r["qp_status"] == capi.CVX_SOLVED).all()
+        ok = r["polish"] == 1
+        assert ok.sum() >= 4
+        assert r["kkt"][ok][:, 0].max() < 1e-6 and r["kkt"][ok][:, 1].max() < 1e-9

@@ -1,0 +1,139 @@
+"""Synthetic problem sets of BASELINE.json `configs` (definitions: SURVEY.md §8d).
+
+configs[k] uses numpy.random.default_rng(20260923 + k).  The generated arrays are the byte-identical
+inputs fed to both the CUDA path and the CPU oracle.
+"""
+import numpy as np
+
+from . import capi, robots
+from .capi import (COLL_DISCRETE, ROLE_CNT, ROLE_COST, TERM_CART_POSE, TERM_COLLISION, TERM_JOINT_ACC,
+                   TERM_JOINT_POS, TERM_JOINT_VEL, ProblemDesc, Term)
+
+SEED = 20260923
+
+
+def hatch_steps(kind, first, last, T):
+    """Step clamping of Joint{Pos,Vel,Acc}TermInfo::hatch (problem_description.cpp:1078-1106, 1197-1224,
+    1393-1421): last_step <= -1 means "to the end"; vel needs >= 2 steps, acc >= 3."""
+    if last <= -1:
+        last = T - 1
+    order = kind - TERM_JOINT_POS
+    if (T - 1 - order) <= first:
+        first = T - 1 - order
+    if (T - 1) <= last:
+        last = T - 1
+    if order > 0 and last == first:
+        last += order
+    if last < first:
+        first, last = last, first
+    return first, last
+
+
+def joint_term(kind, role, D, first, last, coeffs=1.0, targets=0.0, upper=0.0, lower=0.0, T=None):
+    if T is not None:
+        first, last = hatch_steps(kind, first, last, T)
+    t = Term()
+    t.kind, t.role, t.first_step, t.last_step = kind, role, first, last
+    for name, v in (("coeffs", coeffs), ("targets", targets), ("upper_tols", upper), ("lower_tols", lower)):
+        arr = np.broadcast_to(np.asarray(v, float), (D,))
+        getattr(t, name)[:D] = arr.tolist()
+    return t
+
+
+def cart_pose_term(role, timestep, link, target_slot=-1, target_pose=None, pos_coeffs=(1, 1, 1), rot_coeffs=(1, 1, 1),
+                   source_offset=(0, 0, 0, 1, 0, 0, 0)):
+    t = Term()
+    t.kind, t.role, t.first_step, t.last_step = TERM_CART_POSE, role, timestep, timestep
+    t.link, t.target_slot = link, target_slot
+    t.source_offset[:] = source_offset
+    t.target_pose[:] = target_pose if target_pose is not None else (0, 0, 0, 1, 0, 0, 0)
+    t.pos_coeffs[:] = pos_coeffs
+    t.rot_coeffs[:] = rot_coeffs
+    return t
+
+
+def collision_term(role, first, last, margin, coeff, buffer=0.01, fixed_steps=(), evaluator=COLL_DISCRETE, lvs=0.5):
+    t = Term()
+    t.kind, t.role, t.first_step, t.last_step = TERM_COLLISION, role, first, last
+    t.evaluator_type = evaluator
+    t.n_fixed_steps = len(fixed_steps)
+    for i, s in enumerate(fixed_steps):
+        t.fixed_steps[i] = s
+    t.margin, t.coeff, t.margin_buffer, t.longest_valid_segment_length = margin, coeff, buffer, lvs
+    return t
+
+
+def interpolate(q0, q1, T):
+    """JOINT_INTERPOLATED init (LinSpaced per joint, problem_description.cpp:351-355)."""
+    w = np.linspace(0.0, 1.0, T)[None, :, None]
+    return q0[:, None, :] * (1 - w) + q1[:, None, :] * w
+
+
+def config0():
+    """configs[0]: single PR2 arm, 10 waypoints, JointVel cost + JointPos constraint (joint_costs_unit.cpp shapes)."""
+    robot = robots.pr2_arm("r", with_spheres=False)
+    T, D = 10, 7
+    terms = [joint_term(TERM_JOINT_VEL, ROLE_COST, D, 0, T - 1, coeffs=10.0, targets=0.1),
+             joint_term(TERM_JOINT_POS, ROLE_CNT, D, 0, 0, coeffs=10.0, targets=0.0)]
+    init = np.zeros((1, T, D))
+    return ProblemDesc(robot, T, terms, init)
+
+
+def _sample_endpoints(rng, robot, B):
+    lo, hi = np.array(robot["lower"]), np.array(robot["upper"])
+    w = hi - lo
+    q0 = rng.uniform(lo + 0.1 * w, hi - 0.1 * w, size=(B, len(lo)))
+    q1 = rng.uniform(lo + 0.1 * w, hi - 0.1 * w, size=(B, len(lo)))
+    return q0, q1
+
+
+def _targets_from_goal(robot, q_goal, link):
+    out = np.zeros((len(q_goal), 1, 7))
+    for b, q in enumerate(q_goal):
+        R, p = robots.fk_numpy(robot, q)[link]
+        out[b, 0, :3] = p
+        out[b, 0, 3:] = robots.rot_to_wxyz(R)
+    return out
+
+
+def config1(B=1024, T=30, seed=SEED + 1):
+    """configs[1]: JointVel + JointAcc costs, fixed start, CartPose EQ constraint at the last waypoint
+    with target FK(q_goal) (feasible by construction)."""
+    robot = robots.pr2_arm("r", with_spheres=False)
+    rng = np.random.default_rng(seed)
+    D = 7
+    q0, q1 = _sample_endpoints(rng, robot, B)
+    init = interpolate(q0, q1, T)
+    terms = [joint_term(TERM_JOINT_VEL, ROLE_COST, D, 0, T - 1), joint_term(TERM_JOINT_ACC, ROLE_COST, D, 0, T - 1),
+             cart_pose_term(ROLE_CNT, T - 1, robot["tool"], target_slot=0)]
+    return ProblemDesc(robot, T, terms, init, fixed_timesteps=[0], cart_targets=_targets_from_goal(robot, q1, robot["tool"]))
+
+
+def config2(B=1024, T=30, seed=SEED + 2, n_obstacles=8):
+    """configs[2]: configs[1] + discrete collision CONSTRAINT (8 sphere obstacles, dist_pen 0.02, coeff 20,
+    buffer 0.01) at all non-fixed steps; per-trajectory worlds rejection-sampled for start/goal clearance 0.05."""
+    robot = robots.pr2_arm("r", with_spheres=True)
+    rng = np.random.default_rng(seed)
+    D = 7
+    q0, q1 = _sample_endpoints(rng, robot, B)
+    init = interpolate(q0, q1, T)
+    radii = np.array([s.radius for s in robot["spheres"]])
+    obstacles = np.zeros((B, n_obstacles, 4))
+    lo, hi = np.array([0.35, -0.70, 0.55]), np.array([0.95, 0.10, 1.25])
+    for b in range(B):
+        ends = np.concatenate([robots.sphere_centers(robot, q0[b]), robots.sphere_centers(robot, q1[b])])
+        rr = np.concatenate([radii, radii])
+        k = 0
+        while k < n_obstacles:
+            c = rng.uniform(lo, hi)
+            if np.min(np.linalg.norm(ends - c, axis=1) - rr - 0.10) >= 0.05:
+                obstacles[b, k] = (*c, 0.10)
+                k += 1
+    terms = [joint_term(TERM_JOINT_VEL, ROLE_COST, D, 0, T - 1), joint_term(TERM_JOINT_ACC, ROLE_COST, D, 0, T - 1),
+             cart_pose_term(ROLE_CNT, T - 1, robot["tool"], target_slot=0),
+             collision_term(ROLE_CNT, 0, T - 1, margin=0.02, coeff=20.0, buffer=0.01, fixed_steps=[0])]
+    return ProblemDesc(robot, T, terms, init, fixed_timesteps=[0],
+                       cart_targets=_targets_from_goal(robot, q1, robot["tool"]), obstacles=obstacles)
+
+
+CONFIGS = {"cfg0": config0, "cfg1": config1, "cfg2": config2}
