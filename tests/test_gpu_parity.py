@@ -1,0 +1,72 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical inputs.  -m gpu."""
+import numpy as np
+import pytest
+
+from trajopt_b200 import api, capi, problems
+
+pytestmark = pytest.mark.gpu
+
+# fp64 tolerances (north_star: final joint values and merit to a stated fp64 tolerance, final cost within 1e-6)
+ROW_RTOL = 1e-10      # convexification rows: same arithmetic, different summation order
+QP_X_ATOL = 1e-7      # one QP solve: ADMM + polish, reduced banded solve vs envelope Cholesky of the full KKT
+COST_ATOL = 1e-6      # final total cost of the SQP
+
+
+def _cfgs():
+    return {"cfg1": problems.config1(B=16, T=12), "cfg2": problems.config2(B=16, T=12),
+            "cfg1_full_T": problems.config1(B=4, T=30), "cfg2_full_T": problems.config2(B=4, T=30)}
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_full_T"])
+def test_convexify_rows_match_oracle(oracle, name):
+    d = _cfgs()[name]
+    rng = np.random.default_rng(7)
+    x = d.init_traj + 0.05 * rng.standard_normal(d.init_traj.shape)
+    p = api.Problem(d)
+    got = p.convexify(x)
+    ref = oracle.convexify_batch(d, x)
+    p.close()
+    np.testing.assert_allclose(got["cart_err"], ref["cart_err"], rtol=ROW_RTOL, atol=1e-12)
+    np.testing.assert_allclose(got["cart_jac"], ref["cart_jac"], rtol=1e-6, atol=2e-9)  # FD quotient: eps=1e-5 amplifies 1e-16 to 1e-11
+    np.testing.assert_allclose(got["cost_vals"], ref["cost_vals"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(got["cnt_viols"], ref["cnt_viols"], rtol=1e-9, atol=1e-12)
+    if got["coll_rows"].size:
+        np.testing.assert_allclose(got["coll_rows"], ref["coll_rows"], rtol=ROW_RTOL, atol=1e-12)
+        assert ((got["coll_rows"][..., -1] != 0) == (ref["coll_rows"][..., -1] != 0)).all()
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+@pytest.mark.parametrize("trust", [0.1, 0.01])
+def test_qp_solve_matches_oracle(oracle, name, trust):
+    d = _cfgs()[name]
+    x = d.init_traj.copy()
+    p = api.Problem(d)
+    got = p.qp_solve(x, trust, 10.0)
+    ref = oracle.qp_solve_batch(d, x, trust, 10.0)
+    p.close()
+    assert (got["qp_status"] == ref["qp_status"]).all()
+    assert (got["admm_iters"] == ref["admm_iters"]).all(), (got["admm_iters"], ref["admm_iters"])
+    np.testing.assert_allclose(got["new_x"], ref["new_x"], atol=QP_X_ATOL)
+    np.testing.assert_allclose(got["model_cnt_viols"], ref["model_cnt_viols"], atol=1e-6)
+    np.testing.assert_allclose(got["model_cost_vals"], ref["model_cost_vals"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg1_full_T", "cfg2_full_T"])
+def test_sqp_solve_matches_oracle(oracle, name):
+    d = _cfgs()[name]
+    got = api.solve(d)
+    ref = oracle.solve_batch(d)
+    assert (got["status"] == ref["status"]).all(), (got["status"], ref["status"])
+    assert (got["n_qp_solves"] == ref["n_qp_solves"]).all(), (got["n_qp_solves"], ref["n_qp_solves"])
+    np.testing.assert_allclose(got["total_cost"], ref["total_cost"], atol=COST_ATOL)
+    np.testing.assert_allclose(got["x"], ref["x"], atol=1e-5)
+    np.testing.assert_allclose(got["cnt_viols"], ref["cnt_viols"], atol=1e-6)
+
+
+def test_joint_terms_cfg0(oracle):
+    d = problems.config0()
+    got = api.solve(d)
+    ref = oracle.solve_batch(d)
+    assert got["status"][0] == ref["status"][0] == capi.OPT_CONVERGED
+    np.testing.assert_allclose(got["x"], ref["x"], atol=1e-6)
+    np.testing.assert_allclose(got["total_cost"], ref["total_cost"], atol=COST_ATOL)

@@ -1,0 +1,422 @@
+// Batched convexify + exact evaluation + trust-region decision kernel (one CTA per trajectory).
+//
+// For every trajectory of the batch this kernel does, at one iterate, what the reference spreads over
+//   costs[i]->convex(x) / cnts[i]->convex(x)                 trajopt_sco/src/optimizers.cpp:781-783
+//   evaluateCosts / evaluateConstraintViols at new_x         optimizers.cpp:411-412 (merit evaluation)
+//   the accept / shrink / converge / penalty decisions       optimizers.cpp:811-968
+// in a single pass (the reference's 2-entry collision cache, collision_terms.hpp:216, exists only to
+// share one FK + contact pass between value(new_x) and the next convex(new_x); here both are one pass).
+// Outputs are the fixed-layout rows of DESIGN.md §3: CartPose error/Jacobian rows and the dense
+// candidate collision rows {grad[D], dist0, margin, coeff|0}.
+#pragma once
+#include "kinematics.cuh"
+
+namespace tb200 {
+
+constexpr int kEvalThreads = 256;
+enum EvalMode { EVAL_INIT = 0, EVAL_STEP = 1, EVAL_ONLY = 2 };
+
+struct EvalSmem {
+  // offsets in doubles into the dynamic shared buffer
+  int x, sph, jax, jor, cartf, viol, mask, misc, total;
+};
+__host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_cart_objs, int n_coll_cand,
+                                                      int n_mask_words) {
+  EvalSmem s;
+  int o = 0;
+  s.x = o;      o += T * D;
+  s.sph = o;    o += T * L * 3;
+  s.jax = o;    o += T * D * 3;
+  s.jor = o;    o += T * D * 3;
+  s.cartf = o;  o += n_cart_objs * (1 + D) * 12;
+  s.viol = o;   o += n_coll_cand;
+  s.mask = o;   o += n_mask_words;
+  s.misc = o;   o += 8;
+  s.total = o;
+  return s;
+}
+
+struct EvalExtra {
+  int n_cart_objs, n_coll_objs;
+  const DevObj* cart_objs;   // pad0 = index in its own list (cost / cnt), is_cnt says which list
+  const DevObj* coll_objs;
+  int qtype[kMaxDof];                // joint type per trajectory column
+  unsigned sphere_jmask[kMaxSpheres];  // which columns move each sphere
+};
+
+// FK of one configuration; emits the per-waypoint quantities the row writers need.
+__device__ inline void fk_emit(const DevProblem& p, const double* q, double* sph, double* jax, double* jor,
+                               int link, double* link_frame) {
+  Frame fr[kMaxSeg];
+  for (int s = 0; s < p.S; ++s) {
+    const DevSegment g = p.segs[s];
+    Frame loc;
+    segment_local(g, q, loc);
+    if (g.parent < 0)
+      fr[s] = loc;
+    else
+      frame_mul(fr[g.parent], loc, fr[s]);
+    if (g.q_index >= 0 && jax) {
+      const Frame& f = fr[s];
+      for (int i = 0; i < 3; ++i) {
+        jax[g.q_index * 3 + i] = f.R[i * 3] * g.axis[0] + f.R[i * 3 + 1] * g.axis[1] + f.R[i * 3 + 2] * g.axis[2];
+        jor[g.q_index * 3 + i] = f.p[i];
+      }
+    }
+  }
+  if (sph)
+    for (int s = 0; s < p.L; ++s) {
+      const DevSphere sp = p.spheres[s];
+      const Frame& f = fr[sp.segment];
+      for (int i = 0; i < 3; ++i) sph[s * 3 + i] = f.R[i * 3] * sp.c[0] + f.R[i * 3 + 1] * sp.c[1] + f.R[i * 3 + 2] * sp.c[2] + f.p[i];
+    }
+  if (link >= 0 && link_frame) {
+    for (int i = 0; i < 9; ++i) link_frame[i] = fr[link].R[i];
+    for (int i = 0; i < 3; ++i) link_frame[9 + i] = fr[link].p[i];
+  }
+}
+
+__device__ inline double joint_err(const double* x, int D, int order, int t, int d, double target) {
+  double e;
+  if (order == 0)
+    e = x[t * D + d];
+  else if (order == 1)
+    e = x[(t + 1) * D + d] - x[t * D + d];
+  else
+    e = x[t * D + d] - 2.0 * x[(t + 1) * D + d] + x[(t + 2) * D + d];
+  return e - target;
+}
+
+// exact Cost::value / Constraint::violation of a joint-space object at x
+__device__ inline double joint_obj_value(const DevProblem& p, const DevObj& o, const double* x) {
+  const DevJointTerm& jt = p.joint_terms[o.term];
+  double s = 0.0;
+  for (int t = o.first; t < o.first + o.n_steps; ++t)
+    for (int d = 0; d < p.D; ++d) {
+      const double e = joint_err(x, p.D, o.order, t, d, jt.targets[d]);
+      if (o.kind == OBJ_JOINT_EQ_COST)
+        s += e * e * jt.coeffs[d];
+      else if (o.kind == OBJ_JOINT_EQ_CNT)
+        s += fabs(e * e * jt.coeffs[d]);  // value() is c*e^2 while the row is c*e (trajectory_costs.cpp:160 vs 173)
+      else {
+        s += fmax((e - jt.upper[d]) * jt.coeffs[d], 0.0);
+        s += fmax((jt.lower[d] - e) * jt.coeffs[d], 0.0);
+      }
+    }
+  return s;
+}
+
+__global__ void __launch_bounds__(kEvalThreads)
+eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double* x_in /*EVAL_ONLY*/) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int T = p.T, D = p.D, N = p.N, L = p.L, O = p.O;
+  if (mode != EVAL_ONLY && p.status[b] != 5 /*running == INVALID*/) return;
+  const bool qp_failed = (mode == EVAL_STEP) && (p.qp_status[b] != 0);
+  const int n_mask_words = p.n_coll_objs * p.coll_words;
+  const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_cand, n_mask_words);
+  double* xs = sm + S.x;
+  unsigned long long* mask = reinterpret_cast<unsigned long long*>(sm + S.mask);
+  int* misc = reinterpret_cast<int*>(sm + S.misc);
+
+  // destination convexification buffer: the one NOT holding the rows of the current iterate
+  const int cur = (mode == EVAL_ONLY) ? 1 : p.cur_buf[b];
+  const int dst = (mode == EVAL_STEP) ? 1 - cur : ((mode == EVAL_INIT) ? 0 : 0);
+  const size_t slot = static_cast<size_t>(dst) * p.B + b;
+
+  if (!qp_failed) {
+    // ---- load the iterate (coalesced) -------------------------------------------------------
+    const double* src = (mode == EVAL_ONLY) ? x_in + static_cast<size_t>(b) * N
+                                            : (mode == EVAL_INIT ? p.init_traj : p.new_x) + static_cast<size_t>(b) * N;
+    for (int i = tid; i < N; i += kEvalThreads) {
+      double v = src[i];
+      if (mode == EVAL_INIT) v = fmin(p.upper[i % D] - 1e-3, v);  // getClosestFeasiblePoint quirk, modeling.cpp:267-268
+      xs[i] = v;
+    }
+    for (int i = tid; i < n_mask_words; i += kEvalThreads) mask[i] = 0ull;
+    __syncthreads();
+
+    // ---- FK jobs: one per waypoint, plus D perturbed configurations per CartPose object --------
+    const int n_jobs = T + ex.n_cart_objs * D;
+    for (int job = tid; job < n_jobs; job += kEvalThreads) {
+      if (job < T) {
+        // nominal waypoint; also the nominal link frame of every CartPose object at this step
+        int link = -1;
+        double* lf = nullptr;
+        for (int c = 0; c < ex.n_cart_objs; ++c)
+          if (ex.cart_objs[c].first == job) {
+            link = ex.cart_objs[c].link;
+            lf = sm + S.cartf + c * (1 + D) * 12;
+          }
+        fk_emit(p, xs + job * D, sm + S.sph + job * L * 3, sm + S.jax + job * D * 3, sm + S.jor + job * D * 3, link, lf);
+        // (two CartPose objects on the same step with different links: handled below by a second pass)
+      } else {
+        const int c = (job - T) / D, i = (job - T) % D;
+        const DevObj& o = ex.cart_objs[c];
+        double q[kMaxDof];
+        for (int d = 0; d < D; ++d) q[d] = xs[o.first * D + d];
+        q[i] += 1e-5;  // DEFAULT_EPSILON, kinematic_terms.hpp:14
+        fk_emit(p, q, nullptr, nullptr, nullptr, o.link, sm + S.cartf + (c * (1 + D) + 1 + i) * 12);
+      }
+    }
+    __syncthreads();
+    // nominal frames for CartPose objects that share a timestep with another object
+    for (int c = tid; c < ex.n_cart_objs; c += kEvalThreads) {
+      bool shared_step = false;
+      for (int c2 = c + 1; c2 < ex.n_cart_objs; ++c2) shared_step |= (ex.cart_objs[c2].first == ex.cart_objs[c].first);
+      if (shared_step) {
+        const DevObj& o = ex.cart_objs[c];
+        fk_emit(p, xs + o.first * D, nullptr, nullptr, nullptr, o.link, sm + S.cartf + c * (1 + D) * 12);
+      }
+    }
+    __syncthreads();
+
+    // ---- CartPose rows: error + forward-difference Jacobian (kinematic_terms.cpp:250-263, 348-366) ----
+    for (int w = tid; w < ex.n_cart_objs * (1 + D); w += kEvalThreads) {
+      const int c = w / (1 + D), col = w % (1 + D);  // col 0 = error, col 1+i = Jacobian column i
+      const DevObj& o = ex.cart_objs[c];
+      const DevCartTerm& ct = p.cart_terms[o.term];
+      Frame tgt, off, lf, src, e0;
+      quat_to_frame(o.target_slot >= 0 ? p.cart_targets + (static_cast<size_t>(b) * p.n_cart_targets + o.target_slot) * 7 : ct.tgt, tgt);
+      for (int i = 0; i < 9; ++i) off.R[i] = ct.src_R[i];
+      for (int i = 0; i < 3; ++i) off.p[i] = ct.src_p[i];
+      const double* f0 = sm + S.cartf + c * (1 + D) * 12;
+      for (int i = 0; i < 9; ++i) lf.R[i] = f0[i];
+      for (int i = 0; i < 3; ++i) lf.p[i] = f0[9 + i];
+      frame_mul(lf, off, src);
+      rel_pose(tgt, src, e0);
+      double a0[3], g0;
+      rot_err_decomposed(e0.R, a0, g0);
+      double* err_out = p.cart_err + slot * p.n_cart_rows + o.src_off;
+      double* jac_out = p.cart_jac + (slot * p.n_cart_rows + o.src_off) * p.cart_stride;
+      if (col == 0) {
+        const double e[6] = {e0.p[0], e0.p[1], e0.p[2], a0[0] * g0, a0[1] * g0, a0[2] * g0};
+        for (int r = 0; r < ct.n_idx; ++r) err_out[r] = e[ct.idx[r]] * ct.coeff[r];
+      } else {
+        const double* f1 = sm + S.cartf + (c * (1 + D) + col) * 12;
+        Frame lf1, src1, e1;
+        for (int i = 0; i < 9; ++i) lf1.R[i] = f1[i];
+        for (int i = 0; i < 3; ++i) lf1.p[i] = f1[9 + i];
+        frame_mul(lf1, off, src1);
+        rel_pose(tgt, src1, e1);
+        double a1[3], g1;
+        rot_err_decomposed(e1.R, a1, g1);
+        if (a1[0] * a0[0] + a1[1] * a0[1] + a1[2] * a0[2] < 0) {
+          a1[0] = -a1[0]; a1[1] = -a1[1]; a1[2] = -a1[2];
+          g1 = -g1;
+        }
+        const double diff = g1 - g0, pi = 3.14159265358979323846;
+        if (diff > pi) g1 -= 2.0 * pi;
+        else if (diff < -pi) g1 += 2.0 * pi;
+        const double dlt[6] = {e1.p[0] - e0.p[0], e1.p[1] - e0.p[1], e1.p[2] - e0.p[2],
+                               a1[0] * g1 - a0[0] * g0, a1[1] * g1 - a0[1] * g0, a1[2] * g1 - a0[2] * g0};
+        for (int r = 0; r < ct.n_idx; ++r) jac_out[r * p.cart_stride + (col - 1)] = dlt[ct.idx[r]] / 1e-5 * ct.coeff[r];
+      }
+    }
+
+    // ---- dense candidate collision rows (collision_terms.cpp:203-250, 343-383, 540-556, 655-691) ----
+    // candidate r = (collision object k, robot sphere s, obstacle o);  row = {grad[D], dist0, margin, coeff|0}
+    const int LO = L * O;
+    const double* obst = p.obstacles + (p.obstacles_per_traj ? static_cast<size_t>(b) * O * 4 : 0);
+    double* rows_out = p.coll_rows + slot * static_cast<size_t>(p.n_coll_cand) * p.coll_stride;
+    for (int r = tid; r < p.n_coll_cand; r += kEvalThreads) {
+      const int k = r / LO, s = (r % LO) / O, o = r % O;
+      const DevObj& co = ex.coll_objs[k];
+      const int t = co.first;
+      const double* c = sm + S.sph + (t * L + s) * 3;
+      const double dx = obst[o * 4] - c[0], dy = obst[o * 4 + 1] - c[1], dz = obst[o * 4 + 2] - c[2];
+      const double len = sqrt(dx * dx + dy * dy + dz * dz);
+      const double dist = len - p.spheres[s].r - obst[o * 4 + 3];
+      const double inv = 1.0 / len;
+      const double nx = dx * inv, ny = dy * inv, nz = dz * inv;  // from the robot sphere towards the obstacle
+      double* row = rows_out + static_cast<size_t>(r) * p.coll_stride;
+      const unsigned jm = ex.sphere_jmask[s];
+      for (int j = 0; j < D; ++j) {
+        double g = 0.0;
+        if (jm & (1u << j)) {
+          const double* a = sm + S.jax + (t * D + j) * 3;
+          if (ex.qtype[j] == 1) {
+            const double* oj = sm + S.jor + (t * D + j) * 3;
+            const double rx = c[0] - oj[0], ry = c[1] - oj[1], rz = c[2] - oj[2];
+            // -n . (a x r)
+            g = -(nx * (a[1] * rz - a[2] * ry) + ny * (a[2] * rx - a[0] * rz) + nz * (a[0] * ry - a[1] * rx));
+          } else {
+            g = -(nx * a[0] + ny * a[1] + nz * a[2]);
+          }
+        }
+        row[j] = g;
+      }
+      const bool active = !(dist > co.margin + co.buffer);
+      row[D] = dist;
+      row[D + 1] = co.margin;
+      row[D + 2] = active ? co.coeff : 0.0;
+      sm[S.viol + r] = active ? fmax(co.margin - dist, 0.0) * co.coeff : 0.0;
+      if (active) atomicOr(&mask[k * p.coll_words + (r % LO) / 64], 1ull << ((r % LO) % 64));
+    }
+    __syncthreads();
+    for (int i = tid; i < n_mask_words; i += kEvalThreads) p.coll_mask[slot * n_mask_words + i] = mask[i];
+  }
+
+  if (mode == EVAL_ONLY) {
+    // tb200_convexify_batch: exact values only, no SQP state touched
+    __syncthreads();  // cart_err rows written by other threads of this CTA
+    for (int i = tid; i < p.n_costs + p.n_cnts; i += kEvalThreads) {
+      const bool is_cnt = i >= p.n_costs;
+      const DevObj& o = is_cnt ? p.cnt_objs[i - p.n_costs] : p.cost_objs[i];
+      double v = 0.0;
+      if (o.kind <= OBJ_JOINT_INEQ_CNT) v = joint_obj_value(p, o, xs);
+      else if (o.kind == OBJ_CART_POSE) {
+        const double* e = p.cart_err + slot * p.n_cart_rows + o.src_off;
+        for (int r = 0; r < o.n_rows; ++r) v += fabs(e[r]);
+      } else {
+        for (int r = 0; r < o.n_rows; ++r) v += sm[S.viol + o.src_off + r];
+      }
+      (is_cnt ? p.cnt_viols : p.cost_vals)[static_cast<size_t>(b) * (is_cnt ? p.n_cnts : p.n_costs) + (is_cnt ? i - p.n_costs : i)] = v;
+    }
+    return;
+  }
+
+  // ---- exact values at the evaluated point (Cost::value / Constraint::violation) -------------------
+  double* out_cost = (mode == EVAL_INIT ? p.cost_vals : p.new_cost_vals) + static_cast<size_t>(b) * p.n_costs;
+  double* out_viol = (mode == EVAL_INIT ? p.cnt_viols : p.new_cnt_viols) + static_cast<size_t>(b) * p.n_cnts;
+  if (!qp_failed) {
+    __syncthreads();  // cart_err written by other threads of this CTA (global) -> make visible
+    for (int i = tid; i < p.n_costs + p.n_cnts; i += kEvalThreads) {
+      const bool is_cnt = i >= p.n_costs;
+      const DevObj& o = is_cnt ? p.cnt_objs[i - p.n_costs] : p.cost_objs[i];
+      double v = 0.0;
+      if (o.kind <= OBJ_JOINT_INEQ_CNT) v = joint_obj_value(p, o, xs);
+      else if (o.kind == OBJ_CART_POSE) {
+        const double* e = p.cart_err + slot * p.n_cart_rows + o.src_off;
+        for (int r = 0; r < o.n_rows; ++r) v += fabs(e[r]);
+      } else {
+        for (int r = 0; r < o.n_rows; ++r) v += sm[S.viol + o.src_off + r];
+      }
+      if (is_cnt) out_viol[i - p.n_costs] = v;
+      else out_cost[i] = v;
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+
+  // ---- trust-region / penalty state machine (thread 0), optimizers.cpp:811-968 ----------------------
+  if (tid == 0) {
+    const SqpParams& sp = p.sqp;
+    double* mu = p.merit_coeffs + static_cast<size_t>(b) * p.n_cnts;
+    double* cv = p.cost_vals + static_cast<size_t>(b) * p.n_costs;
+    double* kv = p.cnt_viols + static_cast<size_t>(b) * p.n_cnts;
+    double trust = p.trust[b];
+    int accept = 0, finished = 0, status = 5;
+    enum { NEXT_QP = 0, AFTER_LOOP = 1, PENALTY = 2 } go = NEXT_QP;
+    if (mode == EVAL_INIT) {
+      p.n_func_evals[b] = 1;
+      accept = 2;  // rows of buffer 0 are the rows at x
+    } else {
+      p.n_qp_solves[b] += 1;
+      if (qp_failed) {  // failure ladder, optimizers.cpp:817-842
+        int f = p.qp_failures[b];
+        if (f < sp.max_qp_solver_failures - 1) {
+          trust *= sp.trust_shrink_ratio;
+          p.qp_failures[b] = f + 1;
+          go = (trust >= sp.min_trust_box_size) ? NEXT_QP : AFTER_LOOP;
+        } else if (f == sp.max_qp_solver_failures - 1) {
+          trust = sp.min_trust_box_size;
+          p.qp_failures[b] = f + 1;
+          go = (trust >= sp.min_trust_box_size) ? NEXT_QP : AFTER_LOOP;
+        } else {
+          status = 4;  // OPT_FAILED
+          finished = 1;
+        }
+      } else {
+        p.n_func_evals[b] += 1;
+        const double* mc = p.model_cost_vals + static_cast<size_t>(b) * p.n_costs;
+        const double* mk = p.model_cnt_viols + static_cast<size_t>(b) * p.n_cnts;
+        double old_merit = 0, model_merit = 0, new_merit = 0, s;
+        s = 0; for (int i = 0; i < p.n_costs; ++i) s += cv[i];
+        old_merit = s;
+        s = 0; for (int i = 0; i < p.n_cnts; ++i) s += kv[i] * mu[i];
+        old_merit += s;
+        s = 0;
+        for (int i = 0; i < p.n_costs; ++i)  // quadratic joint costs are their own convex model
+          s += (p.cost_objs[i].kind == OBJ_JOINT_EQ_COST) ? out_cost[i] : mc[i];
+        model_merit = s;
+        s = 0; for (int i = 0; i < p.n_cnts; ++i) s += mk[i] * mu[i];
+        model_merit += s;
+        s = 0; for (int i = 0; i < p.n_costs; ++i) s += out_cost[i];
+        new_merit = s;
+        s = 0; for (int i = 0; i < p.n_cnts; ++i) s += out_viol[i] * mu[i];
+        new_merit += s;
+        const double approx = old_merit - model_merit, exact = old_merit - new_merit, ratio = exact / approx;
+        if (approx < sp.min_approx_improve) go = PENALTY;
+        else if (approx / old_merit < sp.min_approx_improve_frac) go = PENALTY;
+        else if (exact < 0 || ratio < sp.improve_ratio_threshold) {
+          trust *= sp.trust_shrink_ratio;
+          go = (trust >= sp.min_trust_box_size) ? NEXT_QP : AFTER_LOOP;
+        } else {
+          accept = 1;
+          trust *= sp.trust_expand_ratio;
+          go = AFTER_LOOP;
+        }
+      }
+      if (!finished && go == AFTER_LOOP) {
+        const double* kk = accept ? out_viol : kv;
+        if (trust < sp.min_trust_box_size) go = PENALTY;
+        else if (p.sqp_iter[b] >= sp.max_iter) {
+          double mx = -1e300;
+          for (int i = 0; i < p.n_cnts; ++i) mx = fmax(mx, kk[i]);
+          status = (p.n_cnts == 0 || mx < sp.cnt_tolerance) ? 0 : 1;
+          finished = 1;
+        } else {
+          p.sqp_iter[b] += 1;
+          p.qp_failures[b] = 0;
+          go = NEXT_QP;
+        }
+      }
+      if (!finished && go == PENALTY) {  // optimizers.cpp:938-968
+        const double* kk = accept ? out_viol : kv;
+        double mx = -1e300;
+        for (int i = 0; i < p.n_cnts; ++i) mx = fmax(mx, kk[i]);
+        if (p.n_cnts == 0 || mx < sp.cnt_tolerance) {
+          status = 0;
+          finished = 1;
+        } else {
+          for (int i = 0; i < p.n_cnts; ++i)
+            if (!sp.inflate_constraints_individually || kk[i] > sp.cnt_tolerance) mu[i] *= sp.merit_coeff_increase_ratio;
+          trust = fmax(trust, sp.min_trust_box_size / sp.trust_shrink_ratio * 1.5);
+          const int round = p.merit_round[b] + 1;
+          p.merit_round[b] = round;
+          if (round >= sp.max_merit_coeff_increases) {
+            status = 2;  // OPT_PENALTY_ITERATION_LIMIT
+            finished = 1;
+          } else {
+            p.sqp_iter[b] = 1;
+            p.qp_failures[b] = 0;
+          }
+        }
+      }
+    }
+    p.trust[b] = trust;
+    misc[0] = accept;
+    if (finished) {
+      misc[1] = 1;
+      p.status[b] = status;
+      atomicSub(p.active_count, 1);
+    } else {
+      misc[1] = 0;
+    }
+  }
+  __syncthreads();
+  const int accept = misc[0];
+  if (accept) {  // results_.x = new_x, cost_vals / cnt_viols = new values (optimizers.cpp:906-909)
+    double* xd = p.x + static_cast<size_t>(b) * N;
+    for (int i = tid; i < N; i += kEvalThreads) xd[i] = xs[i];
+    if (accept == 1) {
+      for (int i = tid; i < p.n_costs; i += kEvalThreads) p.cost_vals[static_cast<size_t>(b) * p.n_costs + i] = out_cost[i];
+      for (int i = tid; i < p.n_cnts; i += kEvalThreads) p.cnt_viols[static_cast<size_t>(b) * p.n_cnts + i] = out_viol[i];
+    }
+    if (tid == 0) p.cur_buf[b] = dst;
+  }
+}
+
+}  // namespace tb200

@@ -1,0 +1,655 @@
+// Host side of the C ABI (include/trajopt_b200.h): validates and flattens the problem description the
+// way trajopt::ConstructProblem / TermInfo::hatch do (trajopt/src/problem_description.cpp:410-542,
+// 901-987, 1078-1176, 1197-1372, 1393-1493, 1714-1837), owns the device buffers, and drives the
+// batched trust-region SQP (trajopt_sco/src/optimizers.cpp:699-991) as a lock-step sequence of two
+// kernels per outer step: qp_kernel (QP subproblem per trajectory) and eval_convexify_decide_kernel
+// (exact merit evaluation + next convexification + accept/shrink/penalty decision).
+// CUDA only: every entry point fails with TB200_ERR_CUDA / TB200_ERR_NO_DEVICE when no device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/trajopt_b200.h"
+#include "eval_kernel.cuh"
+#include "qp_kernel.cuh"
+
+using namespace tb200;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return fail(TB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    n = count;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T));
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+  }
+};
+
+void quatToRot(const double* q, double* R) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double n = std::sqrt(w * w + x * x + y * y + z * z);
+  w /= n; x /= n; y /= n; z /= n;
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+}
+}  // namespace
+
+struct tb200_problem {
+  int device = 0;
+  DevProblem dp{};
+  EvalExtra ex{};
+  tb200_layout layout{};
+  int B = 0, T = 0, D = 0, N = 0;
+  size_t eval_smem = 0, qp_smem = 0;
+  cudaStream_t stream = nullptr;
+  tb200_timing timing{};
+  // host copies of the flattened description
+  std::vector<DevObj> cost_objs, cnt_objs, cart_objs, coll_objs;
+  // device storage
+  DevBuf<DevSegment> segs;
+  DevBuf<DevSphere> spheres;
+  DevBuf<double> lower, upper, Pband, qlin, init_traj, cart_targets, obstacles;
+  DevBuf<DevObj> d_cost_objs, d_cnt_objs, d_cart_objs, d_coll_objs;
+  DevBuf<DevJointTerm> joint_terms;
+  DevBuf<DevCartTerm> cart_terms;
+  DevBuf<int> fixed_vars;
+  DevBuf<double> x, new_x, trust, merit_coeffs, cost_vals, cnt_viols, new_cost_vals, new_cnt_viols, model_cost_vals,
+      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp;
+  DevBuf<unsigned long long> coll_mask;
+  DevBuf<int> status, sqp_iter, merit_round, qp_failures, qp_status, cur_buf, n_qp_solves, n_func_evals, n_admm_iters,
+      active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish;
+  std::vector<cudaEvent_t> events;
+  ~tb200_problem() {
+    for (auto e : events) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+    segs.release(); spheres.release(); lower.release(); upper.release(); Pband.release(); qlin.release();
+    init_traj.release(); cart_targets.release(); obstacles.release(); d_cost_objs.release(); d_cnt_objs.release();
+    d_cart_objs.release(); d_coll_objs.release(); joint_terms.release(); cart_terms.release(); fixed_vars.release();
+    x.release(); new_x.release(); trust.release(); merit_coeffs.release(); cost_vals.release(); cnt_viols.release();
+    new_cost_vals.release(); new_cnt_viols.release(); model_cost_vals.release(); model_cnt_viols.release();
+    cart_err.release(); cart_jac.release(); coll_rows.release(); rows.release(); ws_x.release(); ws_yb.release();
+    scratch.release(); ws_rho.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
+    sqp_iter.release(); merit_round.release(); qp_failures.release(); qp_status.release(); cur_buf.release();
+    n_qp_solves.release(); n_func_evals.release(); n_admm_iters.release(); active_count.release(); row_ints.release();
+    lists.release(); ws_meta.release(); tmp_iters.release(); tmp_polish.release();
+  }
+};
+
+extern "C" {
+
+const char* tb200_version(void) { return "trajopt_b200 0.1 (sm_100a)"; }
+const char* tb200_last_error(void) { return g_err.c_str(); }
+
+void tb200_default_sqp_params(tb200_sqp_params* p) {  // optimizers.hpp:92-135
+  p->improve_ratio_threshold = 0.25;
+  p->min_trust_box_size = 1e-4;
+  p->min_approx_improve = 1e-4;
+  p->min_approx_improve_frac = -1.7976931348623157e308;
+  p->max_iter = 50;
+  p->max_qp_solver_failures = 3;
+  p->trust_shrink_ratio = 0.1;
+  p->trust_expand_ratio = 1.5;
+  p->cnt_tolerance = 1e-4;
+  p->max_merit_coeff_increases = 5;
+  p->merit_coeff_increase_ratio = 10;
+  p->initial_merit_error_coeff = 10;
+  p->trust_box_size = 0.1;
+  p->inflate_constraints_individually = 1;
+  p->reserved = 0;
+}
+void tb200_default_qp_settings(tb200_qp_settings* s) {  // osqp_interface.cpp:78-90 over OSQP defaults
+  s->rho = 0.1; s->sigma = 1e-6; s->alpha = 1.6;
+  s->eps_abs = 1e-4; s->eps_rel = 1e-6;
+  s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4;
+  s->delta = 1e-6; s->adaptive_rho_tolerance = 5.0;
+  s->max_iter = 8192; s->scaling = 10; s->check_termination = 25;
+  s->adaptive_rho = 1; s->adaptive_rho_interval = 50;
+  s->polishing = 1; s->polish_refine_iter = 3; s->warm_starting = 1;
+}
+
+int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem** out) {
+  if (!d || !out) return fail(TB200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(TB200_ERR_NO_DEVICE, "no CUDA device: trajopt_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(TB200_ERR_INVALID, "bad device ordinal");
+  CK(cudaSetDevice(device));
+  const int T = d->n_steps, D = d->robot.n_dof, B = d->batch, N = T * D;
+  if (T < 1 || T > TB200_MAX_STEPS) return fail(TB200_ERR_INVALID, "n_steps out of range");
+  if (D < 1 || D > TB200_MAX_DOF) return fail(TB200_ERR_INVALID, "n_dof out of range");
+  if (B < 1) return fail(TB200_ERR_INVALID, "batch must be >= 1");
+  if (d->robot.n_segments < 1 || d->robot.n_segments > kMaxSeg) return fail(TB200_ERR_INVALID, "n_segments out of range");
+  if (d->robot.n_spheres > kMaxSpheres) return fail(TB200_ERR_INVALID, "too many collision spheres");
+  if (!d->init_traj) return fail(TB200_ERR_INVALID, "init_traj is required");
+
+  auto P = new tb200_problem();
+  std::unique_ptr<tb200_problem> guard(P);
+  P->device = device;
+  P->B = B; P->T = T; P->D = D; P->N = N;
+  DevProblem& dp = P->dp;
+  dp.B = B; dp.T = T; dp.D = D; dp.N = N; dp.HB = 2 * D;
+  dp.S = d->robot.n_segments; dp.L = d->robot.n_spheres; dp.O = d->n_obstacles;
+  dp.obstacles_per_traj = d->obstacles_per_traj;
+  dp.n_cart_targets = d->n_cart_targets;
+
+  // ---- robot ---------------------------------------------------------------------------------------
+  std::vector<DevSegment> segs(dp.S);
+  std::vector<int> seg_q(dp.S, -1);
+  for (int s = 0; s < dp.S; ++s) {
+    const tb200_segment& g = d->robot.segments[s];
+    if (g.parent >= s) return fail(TB200_ERR_INVALID, "segments must be topologically ordered");
+    if (g.joint_type != TB200_JOINT_FIXED && (g.q_index < 0 || g.q_index >= D)) return fail(TB200_ERR_INVALID, "bad q_index");
+    segs[s].parent = g.parent; segs[s].joint_type = g.joint_type; segs[s].q_index = g.joint_type == TB200_JOINT_FIXED ? -1 : g.q_index;
+    quatToRot(g.origin_wxyz, segs[s].R);
+    for (int i = 0; i < 3; ++i) { segs[s].p[i] = g.origin_xyz[i]; segs[s].axis[i] = g.axis[i]; }
+    if (g.joint_type != TB200_JOINT_FIXED) P->ex.qtype[g.q_index] = g.joint_type;
+  }
+  std::vector<DevSphere> sph(std::max(dp.L, 1));
+  for (int s = 0; s < dp.L; ++s) {
+    const tb200_sphere& sp = d->robot.spheres[s];
+    if (sp.segment < 0 || sp.segment >= dp.S) return fail(TB200_ERR_INVALID, "sphere attached to a bad segment");
+    sph[s].segment = sp.segment; sph[s].r = sp.radius;
+    for (int i = 0; i < 3; ++i) sph[s].c[i] = sp.center[i];
+    unsigned m = 0;
+    for (int a = sp.segment; a >= 0; a = segs[a].parent)
+      if (segs[a].q_index >= 0) m |= 1u << segs[a].q_index;
+    P->ex.sphere_jmask[s] = m;
+  }
+
+  // ---- hatch terms into cost / constraint objects (constraints: EQ first, then INEQ) ---------------------
+  std::vector<DevJointTerm> jts;
+  std::vector<DevCartTerm> cts;
+  std::vector<DevObj> costs, eqs, ineqs;
+  int n_cart_rows = 0, n_coll_cand = 0, max_rows = 0;
+  std::vector<std::pair<int, int>> cart_ref, coll_ref;  // (list id: 0 cost 1 eq 2 ineq, index)
+  for (int k = 0; k < d->n_terms; ++k) {
+    const tb200_term& tm = d->terms[k];
+    if (tm.role != TB200_ROLE_COST && tm.role != TB200_ROLE_CNT) return fail(TB200_ERR_INVALID, "term role must be COST or CNT");
+    const bool is_cnt = tm.role == TB200_ROLE_CNT;
+    DevObj o{};
+    o.is_cnt = is_cnt;
+    if (tm.kind == TB200_TERM_JOINT_POS || tm.kind == TB200_TERM_JOINT_VEL || tm.kind == TB200_TERM_JOINT_ACC) {
+      o.order = tm.kind - TB200_TERM_JOINT_POS;
+      o.first = tm.first_step;
+      o.n_steps = tm.last_step - tm.first_step + 1 - o.order;
+      if (tm.first_step < 0 || tm.last_step >= T) return fail(TB200_ERR_INVALID, "joint term steps outside the trajectory");
+      if (o.n_steps <= 0) return fail(TB200_ERR_INVALID, "joint term: trajectory is too short");
+      DevJointTerm jt{};
+      bool zero_tol = true;
+      for (int j = 0; j < D; ++j) {
+        jt.coeffs[j] = tm.coeffs[j]; jt.targets[j] = tm.targets[j]; jt.upper[j] = tm.upper_tols[j]; jt.lower[j] = tm.lower_tols[j];
+        zero_tol = zero_tol && std::fabs(tm.upper_tols[j]) < 1e-5 && std::fabs(tm.lower_tols[j]) < 1e-5;
+      }
+      o.term = static_cast<int>(jts.size());
+      jts.push_back(jt);
+      if (!is_cnt) {
+        o.kind = zero_tol ? OBJ_JOINT_EQ_COST : OBJ_JOINT_INEQ_COST;
+        o.n_rows = zero_tol ? 0 : 2 * o.n_steps * D;
+        costs.push_back(o);
+      } else {
+        o.kind = zero_tol ? OBJ_JOINT_EQ_CNT : OBJ_JOINT_INEQ_CNT;
+        o.n_rows = (zero_tol ? 1 : 2) * o.n_steps * D;
+        (zero_tol ? eqs : ineqs).push_back(o);
+      }
+      max_rows += o.n_rows;
+    } else if (tm.kind == TB200_TERM_CART_POSE) {
+      if (tm.first_step < 0 || tm.first_step >= T) return fail(TB200_ERR_INVALID, "cart_pose timestep outside the trajectory");
+      if (tm.link < 0 || tm.link >= dp.S) return fail(TB200_ERR_INVALID, "cart_pose link out of range");
+      if (tm.target_slot >= d->n_cart_targets) return fail(TB200_ERR_INVALID, "cart_pose target_slot out of range");
+      DevCartTerm ct{};
+      quatToRot(tm.source_offset + 3, ct.src_R);
+      for (int i = 0; i < 3; ++i) ct.src_p[i] = tm.source_offset[i];
+      for (int i = 0; i < 7; ++i) ct.tgt[i] = tm.target_pose[i];
+      for (int i = 0; i < 3; ++i)
+        if (std::fabs(tm.pos_coeffs[i]) > 1e-5) { ct.idx[ct.n_idx] = i; ct.coeff[ct.n_idx++] = tm.pos_coeffs[i]; }
+      for (int i = 0; i < 3; ++i)
+        if (std::fabs(tm.rot_coeffs[i]) > 1e-5) { ct.idx[ct.n_idx] = 3 + i; ct.coeff[ct.n_idx++] = tm.rot_coeffs[i]; }
+      o.kind = OBJ_CART_POSE;
+      o.first = tm.first_step;
+      o.link = tm.link;
+      o.target_slot = tm.target_slot;
+      o.term = static_cast<int>(cts.size());
+      o.src_off = n_cart_rows;
+      o.n_rows = ct.n_idx;
+      cts.push_back(ct);
+      n_cart_rows += ct.n_idx;
+      max_rows += ct.n_idx;
+      if (is_cnt) { cart_ref.push_back({1, static_cast<int>(eqs.size())}); eqs.push_back(o); }
+      else { cart_ref.push_back({0, static_cast<int>(costs.size())}); costs.push_back(o); }
+    } else if (tm.kind == TB200_TERM_COLLISION) {
+      if (tm.evaluator_type != TB200_COLL_DISCRETE)
+        return fail(TB200_ERR_UNSUPPORTED, "only the DISCRETE collision evaluator is implemented on the device so far");
+      if (dp.L == 0 || dp.O == 0) return fail(TB200_ERR_INVALID, "collision term needs robot spheres and obstacles");
+      for (int t = tm.first_step; t <= tm.last_step; ++t) {
+        bool fixed = false;
+        for (int f = 0; f < tm.n_fixed_steps; ++f) fixed |= tm.fixed_steps[f] == t;
+        if (fixed) continue;
+        if (t < 0 || t >= T) return fail(TB200_ERR_INVALID, "collision step outside the trajectory");
+        DevObj c = o;
+        c.kind = OBJ_COLL;
+        c.first = t;
+        c.src_off = n_coll_cand;
+        c.n_rows = dp.L * dp.O;
+        c.coeff = tm.coeff; c.margin = tm.margin; c.buffer = tm.margin_buffer;
+        n_coll_cand += c.n_rows;
+        max_rows += c.n_rows;
+        if (is_cnt) { coll_ref.push_back({2, static_cast<int>(ineqs.size())}); ineqs.push_back(c); }
+        else { coll_ref.push_back({0, static_cast<int>(costs.size())}); costs.push_back(c); }
+      }
+    } else if (tm.kind == TB200_TERM_CART_VEL) {
+      return fail(TB200_ERR_UNSUPPORTED, "cart_vel is not implemented on the device yet");
+    } else {
+      return fail(TB200_ERR_INVALID, "unknown term kind");
+    }
+  }
+  P->cost_objs = costs;
+  P->cnt_objs = eqs;
+  P->cnt_objs.insert(P->cnt_objs.end(), ineqs.begin(), ineqs.end());
+  const int n_eq = static_cast<int>(eqs.size());
+  for (auto& r : cart_ref) {
+    DevObj o = (r.first == 0) ? costs[r.second] : eqs[r.second];
+    o.pad0 = r.second;
+    P->cart_objs.push_back(o);
+  }
+  // collision objects in the order the QP kernel meets them: cost objects first, then constraint objects
+  for (int pass = 0; pass < 2; ++pass)
+    for (auto& r : coll_ref) {
+      if ((pass == 0) != (r.first == 0)) continue;
+      DevObj o = (r.first == 0) ? costs[r.second] : ineqs[r.second];
+      o.pad0 = (r.first == 0) ? r.second : n_eq + r.second;
+      P->coll_objs.push_back(o);
+    }
+  // candidates are laid out in P->coll_objs order (src_off) : re-number so that layout == kernel order
+  {
+    int off = 0;
+    for (auto& o : P->coll_objs) {
+      o.src_off = off;
+      off += o.n_rows;
+      (o.is_cnt ? P->cnt_objs[o.pad0] : P->cost_objs[o.pad0]).src_off = o.src_off;
+    }
+  }
+  // fixed rows
+  std::vector<int> fixed;
+  for (int k = 0; k < d->n_fixed_timesteps; ++k) {
+    const int t = d->fixed_timesteps[k];
+    if (t < 0 || t >= T) return fail(TB200_ERR_INVALID, "Fixed timestep index is outside the bounds of the initial trajectory.");
+    for (int j = 0; j < D; ++j) fixed.push_back(t * D + j);
+  }
+  for (int k = 0; k < d->n_fixed_dofs; ++k) {
+    const int j = d->fixed_dofs[k];
+    if (j < 0 || j >= D) return fail(TB200_ERR_INVALID, "DOF(aka Joint) indice is greater than the number of DOF available.");
+    for (int t = 0; t < T; ++t) {
+      bool skip = false;
+      for (int f = 0; f < d->n_fixed_timesteps; ++f) skip |= d->fixed_timesteps[f] == t;
+      if (!skip) fixed.push_back(t * D + j);
+    }
+  }
+  max_rows += static_cast<int>(fixed.size());
+  max_rows = std::max(max_rows, 1);
+
+  // ---- quadratic objective of the state-independent costs: P = M + M' (osqp_interface.cpp:170-211) ------
+  const int W = dp.HB + 1;
+  std::vector<double> Pband(static_cast<size_t>(N) * W, 0.0), qlin(N, 0.0);
+  for (const DevObj& o : costs) {
+    if (o.kind != OBJ_JOINT_EQ_COST) continue;
+    static const double wst[3][3] = {{1, 0, 0}, {-1, 1, 0}, {1, -2, 1}};
+    const DevJointTerm& jt = jts[o.term];
+    for (int t = o.first; t < o.first + o.n_steps; ++t)
+      for (int j = 0; j < D; ++j)
+        for (int a = 0; a <= o.order; ++a) {
+          const int ia = (t + a) * D + j;
+          qlin[ia] += -2.0 * jt.coeffs[j] * jt.targets[j] * wst[o.order][a];
+          for (int bb = 0; bb <= a; ++bb) {
+            const int ib = (t + bb) * D + j;
+            Pband[static_cast<size_t>(ia) * W + (ia - ib)] += 2.0 * jt.coeffs[j] * wst[o.order][a] * wst[o.order][bb];
+          }
+        }
+  }
+
+  // ---- layout ---------------------------------------------------------------------------------------
+  dp.n_costs = static_cast<int>(P->cost_objs.size());
+  dp.n_cnts = static_cast<int>(P->cnt_objs.size());
+  dp.n_cart_rows = n_cart_rows;
+  dp.cart_stride = D;
+  dp.n_coll_cand = n_coll_cand;
+  dp.coll_stride = D + 3;
+  dp.n_fixed = static_cast<int>(fixed.size());
+  dp.max_rows = max_rows;
+  dp.row_stride = std::max(D, 3) + F_NFIELDS;
+  dp.coll_words = std::max(1, (dp.L * dp.O + 63) / 64);
+  dp.n_coll_objs = static_cast<int>(P->coll_objs.size());
+  P->ex.n_cart_objs = static_cast<int>(P->cart_objs.size());
+  P->ex.n_coll_objs = dp.n_coll_objs;
+  P->layout.n_costs = dp.n_costs;
+  P->layout.n_cnts = dp.n_cnts;
+  P->layout.n_cart_rows = n_cart_rows;
+  P->layout.cart_jac_stride = D;
+  P->layout.n_coll_cand = n_coll_cand;
+  P->layout.coll_row_stride = D + 3;
+  P->layout.n_vars = N;
+
+  // ---- kernel resources --------------------------------------------------------------------------------
+  const EvalSmem es = eval_smem_layout(T, D, dp.L, P->ex.n_cart_objs, n_coll_cand, dp.n_coll_objs * dp.coll_words);
+  P->eval_smem = static_cast<size_t>(es.total) * sizeof(double);
+  const QpSmem qs = qp_smem_layout(N, dp.HB, T, D);
+  P->qp_smem = static_cast<size_t>(qs.total) * sizeof(double);
+  if (P->eval_smem > 227 * 1024 || P->qp_smem > 227 * 1024)
+    return fail(TB200_ERR_UNSUPPORTED, "problem does not fit the 227 KB shared memory of one CTA");
+  CK(cudaFuncSetAttribute(eval_convexify_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->eval_smem)));
+  CK(cudaFuncSetAttribute(qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->qp_smem)));
+  CK(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+
+  // ---- device buffers ------------------------------------------------------------------------------------
+#define ALLOC(buf, count) CK(P->buf.alloc(count))
+#define UPLOAD(buf, vec) \
+  CK(P->buf.alloc((vec).size())); \
+  if (!(vec).empty()) CK(cudaMemcpy(P->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice))
+  UPLOAD(segs, segs);
+  UPLOAD(spheres, sph);
+  std::vector<double> lo(d->robot.lower, d->robot.lower + D), up(d->robot.upper, d->robot.upper + D);
+  UPLOAD(lower, lo);
+  UPLOAD(upper, up);
+  UPLOAD(Pband, Pband);
+  UPLOAD(qlin, qlin);
+  UPLOAD(d_cost_objs, P->cost_objs);
+  UPLOAD(d_cnt_objs, P->cnt_objs);
+  UPLOAD(d_cart_objs, P->cart_objs);
+  UPLOAD(d_coll_objs, P->coll_objs);
+  UPLOAD(joint_terms, jts);
+  UPLOAD(cart_terms, cts);
+  UPLOAD(fixed_vars, fixed);
+  const size_t Bs = B;
+  ALLOC(init_traj, Bs * N);
+  ALLOC(cart_targets, Bs * std::max(1, d->n_cart_targets) * 7);
+  ALLOC(obstacles, (d->obstacles_per_traj ? Bs : 1) * std::max(1, dp.O) * 4);
+  ALLOC(x, Bs * N); ALLOC(new_x, Bs * N); ALLOC(trust, Bs); ALLOC(merit_coeffs, Bs * std::max(1, dp.n_cnts));
+  ALLOC(cost_vals, Bs * std::max(1, dp.n_costs)); ALLOC(cnt_viols, Bs * std::max(1, dp.n_cnts));
+  ALLOC(new_cost_vals, Bs * std::max(1, dp.n_costs)); ALLOC(new_cnt_viols, Bs * std::max(1, dp.n_cnts));
+  ALLOC(model_cost_vals, Bs * std::max(1, dp.n_costs)); ALLOC(model_cnt_viols, Bs * std::max(1, dp.n_cnts));
+  ALLOC(cart_err, 2 * Bs * std::max(1, n_cart_rows)); ALLOC(cart_jac, 2 * Bs * std::max(1, n_cart_rows) * D);
+  ALLOC(coll_rows, 2 * Bs * std::max(1, n_coll_cand) * (D + 3));
+  ALLOC(coll_mask, 2 * Bs * std::max(1, dp.n_coll_objs * dp.coll_words));
+  ALLOC(rows, Bs * max_rows * dp.row_stride); ALLOC(row_ints, Bs * max_rows * RI_NINTS);
+  ALLOC(lists, Bs * (2 * static_cast<size_t>(max_rows) + dp.n_costs + dp.n_cnts + 2));
+  ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 4 * N); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 4);
+  ALLOC(status, Bs); ALLOC(sqp_iter, Bs); ALLOC(merit_round, Bs); ALLOC(qp_failures, Bs); ALLOC(qp_status, Bs);
+  ALLOC(cur_buf, Bs); ALLOC(n_qp_solves, Bs); ALLOC(n_func_evals, Bs); ALLOC(n_admm_iters, Bs); ALLOC(active_count, 1);
+  ALLOC(x_tmp, Bs * N); ALLOC(trust_tmp, Bs); ALLOC(tmp_iters, Bs); ALLOC(tmp_polish, Bs);
+#undef ALLOC
+#undef UPLOAD
+  dp.segs = P->segs.p; dp.spheres = P->spheres.p; dp.lower = P->lower.p; dp.upper = P->upper.p;
+  dp.cost_objs = P->d_cost_objs.p; dp.cnt_objs = P->d_cnt_objs.p; dp.joint_terms = P->joint_terms.p;
+  dp.cart_terms = P->cart_terms.p; dp.fixed_vars = P->fixed_vars.p; dp.Pband = P->Pband.p; dp.qlin = P->qlin.p;
+  dp.init_traj = P->init_traj.p; dp.cart_targets = P->cart_targets.p; dp.obstacles = P->obstacles.p;
+  dp.x = P->x.p; dp.new_x = P->new_x.p; dp.trust = P->trust.p; dp.merit_coeffs = P->merit_coeffs.p;
+  dp.cost_vals = P->cost_vals.p; dp.cnt_viols = P->cnt_viols.p; dp.new_cost_vals = P->new_cost_vals.p;
+  dp.new_cnt_viols = P->new_cnt_viols.p; dp.model_cost_vals = P->model_cost_vals.p; dp.model_cnt_viols = P->model_cnt_viols.p;
+  dp.status = P->status.p; dp.sqp_iter = P->sqp_iter.p; dp.merit_round = P->merit_round.p; dp.qp_failures = P->qp_failures.p;
+  dp.qp_status = P->qp_status.p; dp.cur_buf = P->cur_buf.p; dp.n_qp_solves = P->n_qp_solves.p;
+  dp.n_func_evals = P->n_func_evals.p; dp.n_admm_iters = P->n_admm_iters.p; dp.active_count = P->active_count.p;
+  dp.cart_err = P->cart_err.p; dp.cart_jac = P->cart_jac.p; dp.coll_rows = P->coll_rows.p; dp.coll_mask = P->coll_mask.p;
+  dp.rows = P->rows.p; dp.row_ints = P->row_ints.p; dp.lists = P->lists.p; dp.ws_x = P->ws_x.p; dp.ws_yb = P->ws_yb.p;
+  dp.scratch = P->scratch.p; dp.ws_meta = P->ws_meta.p; dp.ws_rho = P->ws_rho.p;
+  P->ex.cart_objs = P->d_cart_objs.p;
+  P->ex.coll_objs = P->d_coll_objs.p;
+  // settings
+  const tb200_qp_settings& q = d->qp;
+  dp.qp = QpSettings{q.rho, q.sigma, q.alpha, q.eps_abs, q.eps_rel, q.eps_prim_inf, q.eps_dual_inf, q.delta,
+                     q.adaptive_rho_tolerance, q.max_iter, q.scaling, q.check_termination, q.adaptive_rho,
+                     q.adaptive_rho_interval, q.polishing, q.polish_refine_iter, q.warm_starting};
+  const tb200_sqp_params& s = d->sqp;
+  dp.sqp = SqpParams{s.improve_ratio_threshold, s.min_trust_box_size, s.min_approx_improve, s.min_approx_improve_frac,
+                     s.trust_shrink_ratio, s.trust_expand_ratio, s.cnt_tolerance, s.max_merit_coeff_increases,
+                     s.merit_coeff_increase_ratio, s.initial_merit_error_coeff, s.trust_box_size, s.max_iter,
+                     s.max_qp_solver_failures, s.inflate_constraints_individually, 0};
+  int rc = tb200_problem_set_inputs(P, d->init_traj, d->cart_targets, d->obstacles);
+  if (rc != TB200_OK) return rc;
+  *out = guard.release();
+  return TB200_OK;
+}
+
+void tb200_problem_destroy(tb200_problem* p) { delete p; }
+
+int tb200_problem_layout(const tb200_problem* p, tb200_layout* out) {
+  if (!p || !out) return fail(TB200_ERR_INVALID, "null argument");
+  *out = p->layout;
+  return TB200_OK;
+}
+
+int tb200_problem_set_inputs(tb200_problem* P, const double* init_traj, const double* cart_targets, const double* obstacles) {
+  if (!P) return fail(TB200_ERR_INVALID, "null problem");
+  CK(cudaSetDevice(P->device));
+  P->timing.h2d_bytes = 0;
+  if (init_traj) {
+    CK(cudaMemcpyAsync(P->init_traj.p, init_traj, P->init_traj.n * sizeof(double), cudaMemcpyHostToDevice, P->stream));
+    P->timing.h2d_bytes += static_cast<int64_t>(P->init_traj.n * sizeof(double));
+  }
+  if (cart_targets && P->dp.n_cart_targets > 0) {
+    CK(cudaMemcpyAsync(P->cart_targets.p, cart_targets, P->cart_targets.n * sizeof(double), cudaMemcpyHostToDevice, P->stream));
+    P->timing.h2d_bytes += static_cast<int64_t>(P->cart_targets.n * sizeof(double));
+  }
+  if (obstacles && P->dp.O > 0) {
+    CK(cudaMemcpyAsync(P->obstacles.p, obstacles, P->obstacles.n * sizeof(double), cudaMemcpyHostToDevice, P->stream));
+    P->timing.h2d_bytes += static_cast<int64_t>(P->obstacles.n * sizeof(double));
+  }
+  CK(cudaStreamSynchronize(P->stream));
+  return TB200_OK;
+}
+
+namespace {
+__global__ void reset_state_kernel(DevProblem p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *p.active_count = p.B;
+  if (b >= p.B) return;
+  p.status[b] = 5;
+  p.sqp_iter[b] = 1;
+  p.merit_round[b] = 0;
+  p.qp_failures[b] = 0;
+  p.qp_status[b] = 0;
+  p.cur_buf[b] = 0;
+  p.n_qp_solves[b] = 0;
+  p.n_func_evals[b] = 0;
+  p.n_admm_iters[b] = 0;
+  p.trust[b] = p.sqp.trust_box_size;
+  for (int c = 0; c < p.n_cnts; ++c) p.merit_coeffs[static_cast<size_t>(b) * p.n_cnts + c] = p.sqp.initial_merit_error_coeff;
+  for (int k = 0; k < 4; ++k) p.ws_meta[b * 4 + k] = 0;
+  p.ws_rho[b] = p.qp.rho;
+}
+
+cudaEvent_t getEvent(tb200_problem* P, size_t i) {
+  while (P->events.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    P->events.push_back(e);
+  }
+  return P->events[i];
+}
+}  // namespace
+
+int tb200_solve_batch_resident(tb200_problem* P) {
+  if (!P) return fail(TB200_ERR_INVALID, "null problem");
+  CK(cudaSetDevice(P->device));
+  const DevProblem& dp = P->dp;
+  cudaStream_t st = P->stream;
+  tb200_timing& tm = P->timing;
+  const int64_t h2d = tm.h2d_bytes;
+  tm = tb200_timing{};
+  tm.h2d_bytes = h2d;
+  size_t ne = 0;
+  cudaEvent_t e_begin = getEvent(P, ne++), e_end = getEvent(P, ne++);
+  std::vector<std::pair<size_t, int>> spans;  // (event index, kind 0 eval / 1 qp)
+  CK(cudaEventRecord(e_begin, st));
+  reset_state_kernel<<<(dp.B + 127) / 128, 128, 0, st>>>(dp);
+  auto launch_eval = [&](int mode) {
+    const size_t i0 = ne;
+    cudaEventRecord(getEvent(P, ne++), st);
+    eval_convexify_decide_kernel<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, mode, nullptr);
+    cudaEventRecord(getEvent(P, ne++), st);
+    spans.push_back({i0, 0});
+  };
+  auto launch_qp = [&]() {
+    const size_t i0 = ne;
+    cudaEventRecord(getEvent(P, ne++), st);
+    qp_kernel<<<dp.B, 32, P->qp_smem, st>>>(dp, nullptr, nullptr, nullptr, nullptr);
+    cudaEventRecord(getEvent(P, ne++), st);
+    spans.push_back({i0, 1});
+  };
+  launch_eval(EVAL_INIT);
+  // every trajectory needs at most this many QP solves (penalty rounds x SQP iterations x trust retries)
+  const long cap = static_cast<long>(std::ceil(dp.sqp.max_merit_coeff_increases)) * dp.sqp.max_iter * 12 + 64;
+  int active = dp.B;
+  long steps = 0;
+  while (active > 0 && steps < cap) {
+    launch_qp();
+    launch_eval(EVAL_STEP);
+    ++steps;
+    if (steps % 2 == 0 || steps < 4) {
+      CK(cudaMemcpyAsync(&active, dp.active_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  }
+  CK(cudaEventRecord(e_end, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e_begin, e_end));
+  tm.total_ms = ms;
+  tm.outer_steps = static_cast<int32_t>(steps);
+  for (auto& sp : spans) {
+    CK(cudaEventElapsedTime(&ms, P->events[sp.first], P->events[sp.first + 1]));
+    if (sp.second == 0) { tm.convexify_ms += ms; tm.convexify_launches++; }
+    else { tm.qp_ms += ms; tm.qp_launches++; }
+  }
+  // algorithmic HBM bytes of one convexify launch: read x, write cart rows, dense collision
+  // rows and the exact values, per trajectory
+  const int64_t per_traj = 8LL * (dp.N + static_cast<int64_t>(dp.n_coll_cand) * dp.coll_stride +
+                                  static_cast<int64_t>(dp.n_cart_rows) * (dp.cart_stride + 1) + dp.n_costs + dp.n_cnts);
+  tm.convexify_bytes = per_traj * dp.B;  // per launch with every trajectory active
+  if (active > 0) return fail(TB200_ERR_CUDA, "SQP driver hit its step cap with trajectories still active");
+  return TB200_OK;
+}
+
+int tb200_fetch_results(tb200_problem* P, tb200_results* out) {
+  if (!P || !out) return fail(TB200_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(P->device));
+  const DevProblem& dp = P->dp;
+  const size_t B = dp.B;
+  int64_t bytes = 0;
+  auto pull = [&](void* dst, const void* src, size_t n) {
+    if (!dst || n == 0) return cudaSuccess;
+    bytes += static_cast<int64_t>(n);
+    return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, P->stream);
+  };
+  CK(pull(out->x, dp.x, B * dp.N * sizeof(double)));
+  CK(pull(out->status, dp.status, B * sizeof(int)));
+  CK(pull(out->cost_vals, dp.cost_vals, B * dp.n_costs * sizeof(double)));
+  CK(pull(out->cnt_viols, dp.cnt_viols, B * dp.n_cnts * sizeof(double)));
+  CK(pull(out->n_qp_solves, dp.n_qp_solves, B * sizeof(int)));
+  CK(pull(out->n_func_evals, dp.n_func_evals, B * sizeof(int)));
+  CK(pull(out->n_admm_iters, dp.n_admm_iters, B * sizeof(int)));
+  std::vector<double> cv;
+  if (out->total_cost) {
+    cv.resize(B * std::max(1, dp.n_costs));
+    CK(cudaMemcpyAsync(cv.data(), dp.cost_vals, B * dp.n_costs * sizeof(double), cudaMemcpyDeviceToHost, P->stream));
+  }
+  CK(cudaStreamSynchronize(P->stream));
+  if (out->total_cost)
+    for (size_t b = 0; b < B; ++b) {
+      double s = 0;
+      for (int i = 0; i < dp.n_costs; ++i) s += cv[b * dp.n_costs + i];  // results_.total_cost = vecSum(cost_vals)
+      out->total_cost[b] = s;
+    }
+  P->timing.d2h_bytes = bytes;
+  return TB200_OK;
+}
+
+int tb200_solve_batch(tb200_problem* P, tb200_results* out) {
+  if (!P || !out) return fail(TB200_ERR_INVALID, "null argument");
+  int rc = tb200_solve_batch_resident(P);
+  if (rc != TB200_OK) return rc;
+  return tb200_fetch_results(P, out);
+}
+
+int tb200_convexify_batch(tb200_problem* P, const double* x, tb200_convexify_out* out) {
+  if (!P || !x || !out) return fail(TB200_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(P->device));
+  const DevProblem& dp = P->dp;
+  const size_t B = dp.B;
+  cudaStream_t st = P->stream;
+  CK(cudaMemcpyAsync(P->x_tmp.p, x, B * dp.N * sizeof(double), cudaMemcpyHostToDevice, st));
+  eval_convexify_decide_kernel<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
+  CK(cudaGetLastError());
+  auto pull = [&](void* dst, const void* src, size_t n) {
+    if (!dst || n == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st);
+  };
+  CK(pull(out->cart_err, dp.cart_err, B * dp.n_cart_rows * sizeof(double)));
+  CK(pull(out->cart_jac, dp.cart_jac, B * dp.n_cart_rows * dp.cart_stride * sizeof(double)));
+  CK(pull(out->coll_rows, dp.coll_rows, B * dp.n_coll_cand * dp.coll_stride * sizeof(double)));
+  CK(pull(out->cost_vals, dp.cost_vals, B * dp.n_costs * sizeof(double)));
+  CK(pull(out->cnt_viols, dp.cnt_viols, B * dp.n_cnts * sizeof(double)));
+  CK(cudaStreamSynchronize(st));
+  return TB200_OK;
+}
+
+int tb200_qp_solve_batch(tb200_problem* P, const double* x, const double* trust, const double* merit_coeffs, double* new_x,
+                         int32_t* qp_status, double* model_cost_vals, double* model_cnt_viols, int32_t* admm_iters) {
+  if (!P || !x || !trust || !merit_coeffs) return fail(TB200_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(P->device));
+  const DevProblem& dp = P->dp;
+  const size_t B = dp.B;
+  cudaStream_t st = P->stream;
+  CK(cudaMemcpyAsync(P->x_tmp.p, x, B * dp.N * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(P->trust_tmp.p, trust, B * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (dp.n_cnts > 0) CK(cudaMemcpyAsync(P->merit_coeffs.p, merit_coeffs, B * dp.n_cnts * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(P->ws_meta.p, 0, B * 4 * sizeof(int), st));
+  eval_convexify_decide_kernel<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
+  qp_kernel<<<dp.B, 32, P->qp_smem, st>>>(dp, P->x_tmp.p, P->trust_tmp.p, P->tmp_iters.p, P->tmp_polish.p);
+  CK(cudaGetLastError());
+  auto pull = [&](void* dst, const void* src, size_t n) {
+    if (!dst || n == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st);
+  };
+  CK(pull(new_x, dp.new_x, B * dp.N * sizeof(double)));
+  CK(pull(qp_status, dp.qp_status, B * sizeof(int)));
+  CK(pull(model_cost_vals, dp.model_cost_vals, B * dp.n_costs * sizeof(double)));
+  CK(pull(model_cnt_viols, dp.model_cnt_viols, B * dp.n_cnts * sizeof(double)));
+  CK(pull(admm_iters, P->tmp_iters.p, B * sizeof(int)));
+  CK(cudaStreamSynchronize(st));
+  return TB200_OK;
+}
+
+int tb200_last_timing(const tb200_problem* p, tb200_timing* out) {
+  if (!p || !out) return fail(TB200_ERR_INVALID, "null argument");
+  *out = p->timing;
+  return TB200_OK;
+}
+
+}  // extern "C"
