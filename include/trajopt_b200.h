@@ -269,6 +269,9 @@ int tb200_qp_solve_batch(tb200_problem* p, const double* x, const double* trust,
                          double* new_x, int32_t* qp_status, double* model_cost_vals, double* model_cnt_viols,
                          int32_t* admm_iters);
 
+/* Polish outcome (1 accepted, -1 rejected, 0 not attempted) of the last tb200_qp_solve_batch call, [B]. */
+int tb200_last_qp_polish(tb200_problem* p, int32_t* polish);
+
 /* Timing of the last tb200_solve_batch* call, measured with CUDA events on the solver's
  * stream: total ms, convexify-kernel ms and launches, qp-kernel ms and launches. */
 typedef struct tb200_timing {

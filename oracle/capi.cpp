@@ -69,7 +69,7 @@ int oracle_layout(const tb200_problem_desc* desc, tb200_layout* out) {
 }
 
 // BasicTrustRegionSQP::optimize() for trajectories [b0, b1) of the batch, OpenMP over trajectories.
-// trace_*: optional decision trace of trajectory `trace_b` (max trace_cap entries of 9 doubles).
+// trace_*: optional decision trace of trajectory `trace_b` (max trace_cap entries of 14 doubles).
 int oracle_solve_batch(const tb200_problem_desc* desc, int b0, int b1, int n_threads, tb200_results* out,
                        double* seconds, int trace_b, double* trace_out, int trace_cap, int* trace_len) {
   const int T = desc->n_steps, D = desc->robot.n_dof;
@@ -102,9 +102,10 @@ int oracle_solve_batch(const tb200_problem_desc* desc, int b0, int b1, int n_thr
         int n = 0;
         for (const TraceEntry& te : opt.trace) {
           if (n >= trace_cap) break;
-          double* o = trace_out + n * 9;
+          double* o = trace_out + n * 14;
           o[0] = te.merit_round; o[1] = te.iter; o[2] = te.trust; o[3] = te.old_merit; o[4] = te.model_merit;
           o[5] = te.new_merit; o[6] = te.qp_status; o[7] = te.admm_iters; o[8] = te.action;
+          o[9] = te.pri; o[10] = te.dua; o[11] = te.rho; o[12] = te.polish; o[13] = te.warm;
           ++n;
         }
         if (trace_len) *trace_len = n;

@@ -400,6 +400,11 @@ void ruizScale(Work& w, int passes) {
   }
 }
 
+void setRhoValues(Work& w, double rho) {
+  for (int r = 0; r < w.m; ++r)
+    if (w.ctype[r] == 0) w.rho_vec[r] = rho;
+    else if (w.ctype[r] == 1) w.rho_vec[r] = RHO_EQ_OVER_RHO_INEQ * rho;
+}
 void setRhoVec(Work& w, double rho) {
   w.rho_vec.resize(w.m);
   w.ctype.resize(w.m);
@@ -515,8 +520,9 @@ QPResult qp_solve(const QP& qp, const QPSettings& s, const QPWarmStart* warm) {
     return false;
   };
   // check_termination() of OSQP [EXT]; returns status or QP_UNSOLVED
+  double eps_scale = 1.0;  // tightened by the verified-polish rounds (deviation D2)
   auto checkTermination = [&](bool approximate) -> int {
-    double eps_abs = s.eps_abs, eps_rel = s.eps_rel, epi = s.eps_prim_inf, edi = s.eps_dual_inf;
+    double eps_abs = s.eps_abs * eps_scale, eps_rel = s.eps_rel * eps_scale, epi = s.eps_prim_inf, edi = s.eps_dual_inf;
     if (approximate) {
       eps_abs *= 10;
       eps_rel *= 10;
@@ -538,64 +544,147 @@ QPResult qp_solve(const QP& qp, const QPSettings& s, const QPWarmStart* warm) {
   };
 
   int status = QP_UNSOLVED, iter = 0;
-  for (iter = 1; iter <= s.max_iter; ++iter) {
-    xp = x;
-    zp = z;
-    // update_xz_tilde: (P + sigma I + A' R A) xt = sigma x_prev - q + A'(R z_prev - y);  zt = A xt
-    for (int r = 0; r < m; ++r) tmp_m[r] = w.rho_vec[r] * zp[r] - y[r];
-    matTVec(w.A, tmp_m, rhs);
-    for (int i = 0; i < n; ++i) rhs[i] += s.sigma * xp[i] - w.q[i];
-    w.K.solve(rhs, xt);
-    matVec(w.A, xt, zt);
-    for (int i = 0; i < n; ++i) {
-      x[i] = s.alpha * xt[i] + (1 - s.alpha) * xp[i];
-      dx[i] = x[i] - xp[i];
-    }
-    for (int r = 0; r < m; ++r) {
-      const double zr = s.alpha * zt[r] + (1 - s.alpha) * zp[r];
-      double v = zr + y[r] / w.rho_vec[r];
-      v = std::min(std::max(v, w.l[r]), w.u[r]);
-      z[r] = v;
-      dy[r] = w.rho_vec[r] * (zr - v);
-      y[r] += dy[r];
-    }
-    const bool can_check = s.check_termination > 0 && (iter % s.check_termination == 0);
-    if (can_check) {
-      updateInfo();
-      status = checkTermination(false);
-      if (status != QP_UNSOLVED) break;
-    }
-    if (s.adaptive_rho && s.adaptive_rho_interval > 0 && (iter % s.adaptive_rho_interval == 0)) {
-      if (!can_check) updateInfo();
-      // compute_rho_estimate (scaled quantities) [EXT]
-      double p = 0, d = 0;
-      for (int r = 0; r < m; ++r) p = std::max(p, std::fabs(Ax[r] - z[r]));
-      for (int i = 0; i < n; ++i) d = std::max(d, std::fabs(w.q[i] + Px[i] + Aty[i]));
-      p /= (std::max(normInf(z), normInf(Ax)) + 1e-10);
-      d /= (std::max(normInf(w.q), std::max(normInf(Aty), normInf(Px))) + 1e-10);
-      double rho_new = rho * std::sqrt(p / (d + 1e-10));
-      rho_new = std::min(std::max(rho_new, RHO_MIN), RHO_MAX);
-      if (rho_new > rho * s.adaptive_rho_tolerance || rho_new < rho / s.adaptive_rho_tolerance) {
-        rho = rho_new;
-        for (int r = 0; r < m; ++r)
-          if (w.ctype[r] == 0)
-            w.rho_vec[r] = rho;
-          else if (w.ctype[r] == 1)
-            w.rho_vec[r] = RHO_EQ_OVER_RHO_INEQ * rho;
-        if (!w.assemble(s.sigma, w.rho_vec)) {
-          status = QP_NON_CVX;
-          break;
+  // ADMM iterations, continuing from the current state until a termination test fires or max_iter.
+  auto runAdmm = [&]() {
+    status = QP_UNSOLVED;
+    while (iter < s.max_iter) {
+      ++iter;
+      xp = x;
+      zp = z;
+      // update_xz_tilde: (P + sigma I + A' R A) xt = sigma x_prev - q + A'(R z_prev - y);  zt = A xt
+      for (int r = 0; r < m; ++r) tmp_m[r] = w.rho_vec[r] * zp[r] - y[r];
+      matTVec(w.A, tmp_m, rhs);
+      for (int i = 0; i < n; ++i) rhs[i] += s.sigma * xp[i] - w.q[i];
+      w.K.solve(rhs, xt);
+      matVec(w.A, xt, zt);
+      for (int i = 0; i < n; ++i) {
+        x[i] = s.alpha * xt[i] + (1 - s.alpha) * xp[i];
+        dx[i] = x[i] - xp[i];
+      }
+      for (int r = 0; r < m; ++r) {
+        const double zr = s.alpha * zt[r] + (1 - s.alpha) * zp[r];
+        double v = zr + y[r] / w.rho_vec[r];
+        v = std::min(std::max(v, w.l[r]), w.u[r]);
+        z[r] = v;
+        dy[r] = w.rho_vec[r] * (zr - v);
+        y[r] += dy[r];
+      }
+      const bool can_check = s.check_termination > 0 && (iter % s.check_termination == 0);
+      if (can_check) {
+        updateInfo();
+        status = checkTermination(false);
+        if (status != QP_UNSOLVED) return;
+      }
+      if (s.adaptive_rho && s.adaptive_rho_interval > 0 && (iter % s.adaptive_rho_interval == 0)) {
+        if (!can_check) updateInfo();
+        // compute_rho_estimate (scaled quantities) [EXT]
+        double p = 0, d = 0;
+        for (int r = 0; r < m; ++r) p = std::max(p, std::fabs(Ax[r] - z[r]));
+        for (int i = 0; i < n; ++i) d = std::max(d, std::fabs(w.q[i] + Px[i] + Aty[i]));
+        p /= (std::max(normInf(z), normInf(Ax)) + 1e-10);
+        d /= (std::max(normInf(w.q), std::max(normInf(Aty), normInf(Px))) + 1e-10);
+        double rho_new = rho * std::sqrt(p / (d + 1e-10));
+        rho_new = std::min(std::max(rho_new, RHO_MIN), RHO_MAX);
+        if (rho_new > rho * s.adaptive_rho_tolerance || rho_new < rho / s.adaptive_rho_tolerance) {
+          rho = rho_new;
+          setRhoValues(w, rho);
+          if (!w.assemble(s.sigma, w.rho_vec)) {
+            status = QP_NON_CVX;
+            return;
+          }
+          ++res.rho_updates;
         }
-        ++res.rho_updates;
       }
     }
-  }
-  if (iter > s.max_iter) {
-    iter = s.max_iter;
-    if (status == QP_UNSOLVED) {
-      if (!(s.check_termination > 0 && (iter % s.check_termination == 0))) updateInfo();
-      status = checkTermination(true);
-      if (status == QP_UNSOLVED) status = QP_MAX_ITER_REACHED;
+    // max_iter reached without a verdict: approximate test, then MAX_ITER_REACHED
+    if (!(s.check_termination > 0 && (iter % s.check_termination == 0))) updateInfo();
+    status = checkTermination(true);
+    if (status == QP_UNSOLVED) status = QP_MAX_ITER_REACHED;
+  };
+
+  // ---- polish (OSQP polish.c [EXT]): equality-constrained QP on the guessed active set, solved as the
+  // delta-regularised KKT system + iterative refinement, written in its reduced (proximal method of
+  // multipliers) form  K_p = P + delta I + (1/delta) A_act' A_act.
+  // DEVIATION D2: OSQP polishes once and keeps the result whenever its residuals beat ADMM's, even
+  // when the guessed active set was wrong (the point is then NOT the QP minimiser and depends on the ADMM
+  // path).  Here a polished point is accepted at once only when it is VERIFIED: primal feasible to verify_tol
+  // and with correctly signed multipliers on its active inequality rows, i.e. a KKT point = the unique
+  // minimiser, independent of how the guess was produced.  Otherwise ADMM continues from where it stopped
+  // with 10x tighter tolerances and the polish is retried (verify_rounds times); only then OSQP's own
+  // acceptance rule is used.  verify_rounds = 0 is plain OSQP behaviour.
+  Vec wact(m), b(m), xq(n), yq(m), rd(n), step(n);
+  double pp = 0, pdres = 0;
+  auto polishOnce = [&](bool& verified) -> bool {
+    verified = false;
+    for (int r = 0; r < m; ++r) {
+      int a = 0;
+      if (z[r] - w.l[r] < -y[r]) a = -1;
+      else if (w.u[r] - z[r] < y[r]) a = 1;
+      wact[r] = a ? 1.0 / s.delta : 0.0;
+      b[r] = a < 0 ? w.l[r] : w.u[r];
+      tmp_m[r] = a;
+    }
+    Vec act = tmp_m;
+    if (!w.assemble(s.delta, wact)) return false;
+    std::fill(xq.begin(), xq.end(), 0.0);
+    std::fill(yq.begin(), yq.end(), 0.0);
+    for (int it = 0; it <= s.polish_refine_iter; ++it) {
+      symMatVec(w.Pu, xq, Px);
+      matTVec(w.A, yq, Aty);
+      matVec(w.A, xq, Ax);
+      for (int r = 0; r < m; ++r) tmp_m[r] = wact[r] * (Ax[r] - b[r]);
+      matTVec(w.A, tmp_m, tmp_n);
+      for (int i = 0; i < n; ++i) rd[i] = -(Px[i] + w.q[i] + Aty[i]) - tmp_n[i];
+      w.K.solve(rd, step);
+      for (int i = 0; i < n; ++i) xq[i] += step[i];
+      matVec(w.A, xq, Ax);
+      for (int r = 0; r < m; ++r)
+        if (wact[r] != 0.0) yq[r] += wact[r] * (Ax[r] - b[r]);
+    }
+    matVec(w.A, xq, Ax);
+    symMatVec(w.Pu, xq, Px);
+    matTVec(w.A, yq, Aty);
+    pp = pdres = 0;
+    bool signs_ok = true;
+    for (int r = 0; r < m; ++r) {
+      const double zr = std::min(std::max(Ax[r], w.l[r]), w.u[r]);
+      pp = std::max(pp, std::fabs(w.Einv[r] * (Ax[r] - zr)));
+      if (act[r] != 0 && w.u[r] - w.l[r] >= RHO_TOL) {  // inequality row held active: multiplier sign
+        if (act[r] > 0 && yq[r] < -s.verify_tol) signs_ok = false;
+        if (act[r] < 0 && yq[r] > s.verify_tol) signs_ok = false;
+      }
+    }
+    for (int i = 0; i < n; ++i) pdres = std::max(pdres, std::fabs(w.Dinv[i] * (w.q[i] + Px[i] + Aty[i])));
+    pdres *= w.cinv;
+    verified = signs_ok && pp <= s.verify_tol && std::isfinite(pp) && std::isfinite(pdres);
+    return true;
+  };
+
+  int round = 0;
+  double admm_pri = 0, admm_dua = 0;
+  while (true) {
+    runAdmm();
+    admm_pri = pri_res;
+    admm_dua = dua_res;
+    if (status != QP_SOLVED || !s.polishing) break;
+    bool verified = false;
+    const bool factored = polishOnce(verified);
+    res.pdas = round;
+    if (factored && verified) {
+      res.polish = 1;
+      break;
+    }
+    if (round >= s.verify_rounds || iter >= s.max_iter) {  // OSQP's acceptance rule
+      const bool ok = factored && ((pp < pri_res && pdres < dua_res) || (pp < pri_res && dua_res < 1e-10) ||
+                                   (pdres < dua_res && pri_res < 1e-10)) && std::isfinite(pp) && std::isfinite(pdres);
+      res.polish = ok ? 2 : -1;
+      break;
+    }
+    ++round;
+    eps_scale *= 0.1;
+    if (!w.assemble(s.sigma, w.rho_vec)) {  // back to the ADMM factor
+      status = QP_NON_CVX;
+      break;
     }
   }
   res.iters = iter;
@@ -603,67 +692,22 @@ QPResult qp_solve(const QP& qp, const QPSettings& s, const QPWarmStart* warm) {
   res.rho = rho;
   res.pri_res = pri_res;
   res.dua_res = dua_res;
-
-  // ---- polish (OSQP polish.c [EXT]): equality-constrained QP on the guessed active set, solved as
-  // the delta-regularised KKT system + iterative refinement, written in its reduced (proximal
-  // method of multipliers) form:  K_p = P + delta I + (1/delta) A_act' A_act.
-  if (status == QP_SOLVED && s.polishing) {
-    Vec wact(m, 0.0), b(m, 0.0);
-    for (int r = 0; r < m; ++r) {
-      if (z[r] - w.l[r] < -y[r]) {
-        wact[r] = 1.0 / s.delta;
-        b[r] = w.l[r];
-      } else if (w.u[r] - z[r] < y[r]) {
-        wact[r] = 1.0 / s.delta;
-        b[r] = w.u[r];
-      }
-    }
-    if (w.assemble(s.delta, wact)) {
-      Vec xq(n, 0.0), yq(m, 0.0), rd(n), step(n);
-      for (int it = 0; it <= s.polish_refine_iter; ++it) {
-        symMatVec(w.Pu, xq, Px);
-        matTVec(w.A, yq, Aty);
-        matVec(w.A, xq, Ax);
-        for (int r = 0; r < m; ++r) tmp_m[r] = wact[r] * (Ax[r] - b[r]);
-        matTVec(w.A, tmp_m, tmp_n);
-        for (int i = 0; i < n; ++i) rd[i] = -(Px[i] + w.q[i] + Aty[i]) - tmp_n[i];
-        w.K.solve(rd, step);
-        for (int i = 0; i < n; ++i) xq[i] += step[i];
-        matVec(w.A, xq, Ax);
-        for (int r = 0; r < m; ++r)
-          if (wact[r] != 0.0) yq[r] += wact[r] * (Ax[r] - b[r]);
-      }
-      // residuals of the polished point (z = projection of A x onto [l,u])
-      matVec(w.A, xq, Ax);
-      symMatVec(w.Pu, xq, Px);
-      matTVec(w.A, yq, Aty);
-      double pp = 0, pd = 0;
-      for (int r = 0; r < m; ++r) {
-        const double zr = std::min(std::max(Ax[r], w.l[r]), w.u[r]);
-        pp = std::max(pp, std::fabs(w.Einv[r] * (Ax[r] - zr)));
-      }
-      for (int i = 0; i < n; ++i) pd = std::max(pd, std::fabs(w.Dinv[i] * (w.q[i] + Px[i] + Aty[i])));
-      pd *= w.cinv;
-      const bool ok = (pp < pri_res && pd < dua_res) || (pp < pri_res && dua_res < 1e-10) ||
-                      (pd < dua_res && pri_res < 1e-10);
-      if (ok && std::isfinite(pp) && std::isfinite(pd)) {
-        x = xq;
-        y = yq;
-        res.polish = 1;
-        res.pri_res = pp;
-        res.dua_res = pd;
-      } else {
-        res.polish = -1;
-      }
-    } else {
-      res.polish = -1;
-    }
+  res.admm_pri = admm_pri;
+  res.admm_dua = admm_dua;
+  res.warm = (warm && warm->valid) ? 1 : 0;
+  res.y_admm.assign(m, 0.0);
+  for (int r = 0; r < m; ++r) res.y_admm[r] = w.cinv * w.E[r] * y[r];
+  if (res.polish > 0) {
+    x = xq;
+    y = yq;
+    res.pri_res = pp;
+    res.dua_res = pdres;
   }
   for (int i = 0; i < n; ++i) res.x[i] = w.D[i] * x[i];
   for (int r = 0; r < m; ++r) res.y[r] = w.cinv * w.E[r] * y[r];
   if (getenv("ORACLE_QP_DEBUG"))
-    fprintf(stderr, "QP n=%d m=%d status=%d iters=%d rho_upd=%d polish=%d admm_pri=%.2e admm_dua=%.2e pri=%.2e dua=%.2e warm=%d\n", n, m,
-            status, res.iters, res.rho_updates, res.polish, pri_res, dua_res, res.pri_res, res.dua_res, (int)(warm && warm->valid));
+    fprintf(stderr, "QP n=%d m=%d status=%d iters=%d rho_upd=%d polish=%d pdas=%d admm_pri=%.2e admm_dua=%.2e pri=%.2e dua=%.2e warm=%d\n", n, m,
+            status, res.iters, res.rho_updates, res.polish, res.pdas, admm_pri, admm_dua, res.pri_res, res.dua_res, (int)(warm && warm->valid));
   return res;
 }
 
@@ -752,7 +796,11 @@ CvxStatus Model::optimize() {
   if (same && settings_.warm_starting && (last_.status == QP_SOLVED || last_.status == QP_SOLVED_INACCURATE)) {
     ws.valid = true;
     ws.x = last_.x;
-    ws.y = last_.y;
+    // DEVIATION (documented in DESIGN.md): the reference warm-starts from OSQP's returned duals, which are
+    // the POLISHED duals when polish succeeded.  On degenerate active sets (linearly dependent bounds + rows,
+    // common at trust-box corners) those are non-unique and only fixed by the 1e-6 regularisation, i.e. not
+    // reproducible across linear-algebra back ends.  Primal x from polish, duals from the last ADMM iterate.
+    ws.y = last_.y_admm;
     ws.rho = last_.rho;
   }
   last_ = qp_solve(qp, settings_, ws.valid ? &ws : nullptr);
@@ -1185,6 +1233,11 @@ OptStatus BasicTrustRegionSQP::optimize() {
         ++results_.n_func_evals;
         TraceEntry te{merit_increases, iter, param_.trust_box_size, old_merit, model_merit, new_merit,
                       model->lastResult().status, model->lastResult().iters, 0};
+        te.pri = model->lastResult().admm_pri;
+        te.dua = model->lastResult().admm_dua;
+        te.rho = model->lastResult().rho;
+        te.polish = model->lastResult().polish;
+        te.warm = model->lastResult().warm;
 
         if (approx_merit_improve < param_.min_approx_improve) {
           te.action = 2;

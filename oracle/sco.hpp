@@ -100,6 +100,8 @@ struct QPSettings {
   int adaptive_rho = 1, adaptive_rho_interval = 50;
   int polishing = 1, polish_refine_iter = 3;       // osqp_interface.cpp:86
   int warm_starting = 1;
+  int verify_rounds = 3;     // verified-polish retries with 10x tighter ADMM tolerances (0 = plain OSQP polish)
+  double verify_tol = 1e-9;  // KKT verification: primal feasibility and multiplier-sign tolerance
 };
 enum QPStatus {
   QP_SOLVED = 1,
@@ -120,11 +122,15 @@ struct QPWarmStart {
 struct QPResult {
   int status = QP_UNSOLVED;
   Vec x, y;
+  Vec y_admm;  // duals of the last ADMM iterate (before polish): what the next solve is warm-started from
   int iters = 0;
   int rho_updates = 0;
-  int polish = 0;  // 1 accepted, -1 rejected, 0 not attempted
+  int polish = 0;  // 1 accepted (KKT fixed point), 2 accepted by residual rule only, -1 rejected, 0 not attempted
+  int pdas = 0;    // verified-polish rounds used
   double pri_res = 0, dua_res = 0;
+  double admm_pri = 0, admm_dua = 0;
   double rho = 0.1;
+  int warm = 0;
 };
 QPResult qp_solve(const QP& qp, const QPSettings& s, const QPWarmStart* warm);
 // KKT residuals of (x,y) for `qp` in the original (unscaled) space; used by the tests.
@@ -319,6 +325,8 @@ struct TraceEntry {
   int merit_round, iter;
   double trust, old_merit, model_merit, new_merit;
   int qp_status, admm_iters, action;  // action: 0 shrink, 1 accept, 2 converged(small improve), 3 qp failure
+  double pri = 0, dua = 0, rho = 0;
+  int polish = 0, warm = 0;
 };
 
 class BasicTrustRegionSQP {

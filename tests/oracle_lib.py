@@ -50,7 +50,7 @@ def solve_batch(desc, b0=0, b1=None, n_threads=0, trace_b=-1):
     L = layout(desc)
     buf, res = capi.alloc_results(desc.B, desc.T, desc.D, L.n_costs, L.n_cnts)
     secs = C.c_double(0)
-    trace = np.zeros((4096, 9))
+    trace = np.zeros((4096, 14))
     tlen = C.c_int(0)
     rc = lib().oracle_solve_batch(C.byref(desc.c), b0, b1, n_threads, C.byref(res), C.byref(secs), trace_b,
                                   _dp(trace), 4096, C.byref(tlen))

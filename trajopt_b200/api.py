@@ -109,6 +109,8 @@ class Problem:
                                                   _dp(out["model_cnt_viols"]) if L.n_cnts else None, _ip(out["admm_iters"])))
         out["model_cost_vals"] = out["model_cost_vals"][:, :L.n_costs]
         out["model_cnt_viols"] = out["model_cnt_viols"][:, :L.n_cnts]
+        out["polish"] = np.zeros(d.B, np.int32)
+        self._check(self.lib.tb200_last_qp_polish(self.handle, _ip(out["polish"])))
         return out
 
 

@@ -245,6 +245,7 @@ def load_library():
     lib.tb200_fetch_results.argtypes = [C.c_void_p, C.POINTER(Results)]
     lib.tb200_convexify_batch.argtypes = [C.c_void_p, _dbl_p, C.POINTER(ConvexifyOut)]
     lib.tb200_qp_solve_batch.argtypes = [C.c_void_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _i32_p, _dbl_p, _dbl_p, _i32_p]
+    lib.tb200_last_qp_polish.argtypes = [C.c_void_p, _i32_p]
     lib.tb200_last_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     lib.tb200_default_sqp_params.argtypes = [C.POINTER(SqpParams)]
     lib.tb200_default_qp_settings.argtypes = [C.POINTER(QpSettings)]
@@ -256,5 +257,5 @@ EXPORTED_SYMBOLS = [
     "tb200_version", "tb200_last_error", "tb200_default_sqp_params", "tb200_default_qp_settings",
     "tb200_problem_create", "tb200_problem_destroy", "tb200_problem_layout", "tb200_problem_set_inputs",
     "tb200_solve_batch", "tb200_solve_batch_resident", "tb200_fetch_results", "tb200_convexify_batch",
-    "tb200_qp_solve_batch", "tb200_last_timing",
+    "tb200_qp_solve_batch", "tb200_last_qp_polish", "tb200_last_timing",
 ]

@@ -146,9 +146,13 @@ struct DevProblem {
   int* lists;                  // [B][(T+1) + (D+1) + 2*max_rows + n_objs + 1] per-lane row lists
   double* ws_x;                // [B][N]  warm start: previous QP solution (trajectory part, unscaled)
   double* ws_yb;               // [B][N]  warm start: duals of the variable-bound rows (unscaled)
-  double* scratch;             // [B][4N]
+  double* scratch;             // [B][5N]
   int* ws_meta;                // [B][4]: n_aux, m_rows, nnzA, last status
   double* ws_rho;              // [B]
+  double* trace;               // [B][trace_cap][14] decision trace (same columns as the oracle's TraceEntry)
+  int* trace_len;              // [B]
+  int trace_cap, pad3;
+  double* dbg;                 // [B][16] solver diagnostics of the last QP (residuals, polish residuals, rho, c)
   QpSettings qp;
   SqpParams sqp;
 };

@@ -314,6 +314,9 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
       accept = 2;  // rows of buffer 0 are the rows at x
     } else {
       p.n_qp_solves[b] += 1;
+      double tr_old = 0, tr_model = 0, tr_new = 0;
+      int tr_action = 3;
+      const double tr_trust = trust;
       if (qp_failed) {  // failure ladder, optimizers.cpp:817-842
         int f = p.qp_failures[b];
         if (f < sp.max_qp_solver_failures - 1) {
@@ -348,16 +351,26 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
         s = 0; for (int i = 0; i < p.n_cnts; ++i) s += out_viol[i] * mu[i];
         new_merit += s;
         const double approx = old_merit - model_merit, exact = old_merit - new_merit, ratio = exact / approx;
-        if (approx < sp.min_approx_improve) go = PENALTY;
-        else if (approx / old_merit < sp.min_approx_improve_frac) go = PENALTY;
+        tr_old = old_merit; tr_model = model_merit; tr_new = new_merit;
+        if (approx < sp.min_approx_improve) { go = PENALTY; tr_action = 2; }
+        else if (approx / old_merit < sp.min_approx_improve_frac) { go = PENALTY; tr_action = 2; }
         else if (exact < 0 || ratio < sp.improve_ratio_threshold) {
           trust *= sp.trust_shrink_ratio;
           go = (trust >= sp.min_trust_box_size) ? NEXT_QP : AFTER_LOOP;
+          tr_action = 0;
         } else {
           accept = 1;
           trust *= sp.trust_expand_ratio;
           go = AFTER_LOOP;
+          tr_action = 1;
         }
+      }
+      if (p.trace && p.trace_len[b] < p.trace_cap) {
+        double* te = p.trace + (static_cast<size_t>(b) * p.trace_cap + p.trace_len[b]) * 14;
+        te[0] = p.merit_round[b]; te[1] = p.sqp_iter[b]; te[2] = tr_trust; te[3] = tr_old; te[4] = tr_model; te[5] = tr_new;
+        const double* g = p.dbg + static_cast<size_t>(b) * 16;
+        te[6] = g[0]; te[7] = g[1]; te[8] = tr_action; te[9] = g[4]; te[10] = g[5]; te[11] = g[3]; te[12] = g[2]; te[13] = g[14];
+        p.trace_len[b] += 1;
       }
       if (!finished && go == AFTER_LOOP) {
         const double* kk = accept ? out_viol : kv;

@@ -18,6 +18,8 @@ namespace tb200 {
 
 constexpr double kOsqpInf = 1e30;
 constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4;
+constexpr double kVerifyTol = 1e-9;  // KKT verification of the polished point (deviation D2)
+constexpr int kVerifyRounds = 3;
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoTol = 1e-4, kRhoEqOverIneq = 1e3;
 enum { QPS_UNSOLVED = 0, QPS_SOLVED = 1, QPS_SOLVED_INACC = 2, QPS_PINF = 3, QPS_PINF_INACC = 4, QPS_DINF = 5,
        QPS_DINF_INACC = 6, QPS_MAXITER = 7, QPS_NONCVX = 8 };
@@ -201,8 +203,11 @@ struct SysW {
   bool polish;
   double sig, rho_aux;  // ADMM: rho on the aux bound rows
 };
+// Weights of one row in the current linear system.  With the aux block K_aa = diag(g) + Wr u u' the
+// closed forms below are written cancellation free (den = det(K_aa) / 1, expanded analytically): the polish
+// system has Wr = 1/delta and g = delta, where the textbook Sherman-Morrison form loses ~12 digits.
 __device__ __forceinline__ void row_weights(const QpCtx& q, const SysW& w, const double* F, const RowV& v, double& Wr,
-                                            double& g0, double& g1, double& ssum) {
+                                            double& g0, double& g1, double& den) {
   double wa0, wa1;
   if (w.polish) {
     Wr = fabs(F[F_PW]);
@@ -212,11 +217,9 @@ __device__ __forceinline__ void row_weights(const QpCtx& q, const SysW& w, const
     Wr = v.rho;
     wa0 = wa1 = w.rho_aux;
   }
-  g0 = w.sig + wa0 * v.b0 * v.b0;
-  g1 = w.sig + wa1 * v.b1 * v.b1;
-  ssum = 0.0;
-  if (v.naux >= 1) ssum += v.u0 * v.u0 / g0;
-  if (v.naux == 2) ssum += v.u1 * v.u1 / g1;
+  g0 = (v.naux >= 1) ? w.sig + wa0 * v.b0 * v.b0 : 1.0;
+  g1 = (v.naux == 2) ? w.sig + wa1 * v.b1 * v.b1 : 1.0;
+  den = g0 * g1 + Wr * (v.u0 * v.u0 * g1 + v.u1 * v.u1 * g0);
 }
 __device__ __forceinline__ double xbound_weight(const QpCtx& q, const SysW& w, int j) {
   if (w.polish) return fabs(q.zb[j]);  // zb holds the signed polish weights during polish
@@ -237,10 +240,10 @@ __device__ inline bool assemble_factor(const QpCtx& q, const SysW& w) {
     const double* F = R + q.CN;
     RowV v;
     row_view(q, R, q.I(r), v);
-    double Wr, g0, g1, ssum;
-    row_weights(q, w, F, v, Wr, g0, g1, ssum);
+    double Wr, g0, g1, den;
+    row_weights(q, w, F, v, Wr, g0, g1, den);
     if (Wr == 0.0) return;
-    const double wr = Wr / (1.0 + Wr * ssum);
+    const double wr = Wr * g0 * g1 / den;  // Schur complement weight of the row on the trajectory block
     for (int i = 0; i < v.cnt; ++i) {
       const int vi = v.base + i * v.stride;
       const double ai = v.E * R[i] * q.Dz[vi];
@@ -257,12 +260,10 @@ __device__ inline bool assemble_factor(const QpCtx& q, const SysW& w) {
 // Reduce step of the aux elimination: rows hold their aux right-hand sides in F_RA*; adds the Schur
 // correction to the trajectory right-hand side in v1.
 __device__ __forceinline__ void row_reduce_rhs(const QpCtx& q, const double* R, const double* F, const RowV& v, double Wr,
-                                               double g0, double g1, double ssum, double zcoef) {
+                                               double g0, double g1, double den, double zcoef) {
   // zcoef: multiplier of the row on the trajectory part supplied by the caller (s_r for ADMM, -e_r for polish)
-  double tau = 0.0;
-  if (v.naux >= 1) tau += v.u0 * F[F_RA0] / g0;
-  if (v.naux == 2) tau += v.u1 * F[F_RA1] / g1;
-  const double coef = zcoef - Wr * tau / (1.0 + Wr * ssum);
+  const double ra0 = (v.naux >= 1) ? F[F_RA0] : 0.0, ra1 = (v.naux == 2) ? F[F_RA1] : 0.0;
+  const double coef = zcoef - Wr * (v.u0 * ra0 * g1 + v.u1 * ra1 * g0) / den;
   for (int i = 0; i < v.cnt; ++i) {
     const int vi = v.base + i * v.stride;
     q.v1[vi] += v.E * R[i] * q.Dz[vi] * coef;
@@ -270,7 +271,7 @@ __device__ __forceinline__ void row_reduce_rhs(const QpCtx& q, const double* R, 
 }
 // Back substitution of the aux variables after the banded solve (solution in v1).
 __device__ __forceinline__ void row_backsub(const QpCtx& q, const double* R, const double* F, const RowV& v, double Wr,
-                                            double g0, double g1, double ssum, double& zeta, double& a0, double& a1) {
+                                            double g0, double g1, double den, double& zeta, double& a0, double& a1) {
   zeta = 0.0;
   for (int i = 0; i < v.cnt; ++i) {
     const int vi = v.base + i * v.stride;
@@ -278,25 +279,23 @@ __device__ __forceinline__ void row_backsub(const QpCtx& q, const double* R, con
   }
   a0 = a1 = 0.0;
   if (v.naux == 0) return;
-  const double v0 = F[F_RA0] - Wr * v.u0 * zeta;
-  const double v1 = (v.naux == 2) ? F[F_RA1] - Wr * v.u1 * zeta : 0.0;
-  double kappa = v.u0 * v0 / g0;
-  if (v.naux == 2) kappa += v.u1 * v1 / g1;
-  const double f = Wr * kappa / (1.0 + Wr * ssum);
-  a0 = v0 / g0 - (v.u0 / g0) * f;
-  if (v.naux == 2) a1 = v1 / g1 - (v.u1 / g1) * f;
+  const double ra0 = F[F_RA0], ra1 = (v.naux == 2) ? F[F_RA1] : 0.0;
+  a0 = (g1 * (ra0 - Wr * v.u0 * zeta) + Wr * v.u1 * (v.u1 * ra0 - v.u0 * ra1)) / den;
+  if (v.naux == 2) a1 = (g0 * (ra1 - Wr * v.u1 * zeta) + Wr * v.u0 * (v.u0 * ra1 - v.u1 * ra0)) / den;
 }
 
 struct QpOut {
   int status, iters, polish;
   double rho;
+  double pri_res, dua_res, pol_pri, pol_dua, c;
+  int pol_factor_ok, rho_updates, rounds;
 };
 
 // The whole QP solve for the calling warp's trajectory.  `warm`: rows/ws_* hold the previous solution.
 __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm, double warm_rho, double* ws_x,
                                       double* ws_yb, int n_aux_total) {
   const int N = q.N, lane = q.lane;
-  QpOut out{QPS_UNSOLVED, 0, 0, st.rho};
+  QpOut out{QPS_UNSOLVED, 0, 0, st.rho, 0, 0, 0, 0, 0, -1, 0, 0};
   // ------------------------------------------------------------------ Ruiz equilibration (scale_data) [EXT]
   q.c = 1.0;
   for (int i = lane; i < N; i += 32) {
@@ -445,6 +444,9 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm,
   // ------------------------------------------------------------------ ADMM iterations
   double* dxs = q.scratch;          // [N] last trajectory step (written on check iterations)
   double* dyb = q.scratch + N;      // [N] last dual step of the variable-bound rows
+  double* st_x = q.scratch + 2 * N;   // ADMM x, zb, yb stashed while polish reuses the shared vectors
+  double* st_zb = q.scratch + 3 * N;
+  double* st_yb = q.scratch + 4 * N;
   double pri_res = 0.0, dua_res = 0.0;
   int status = QPS_UNSOLVED, iter = 0;
   // residuals / norms gathered by the info pass
@@ -622,8 +624,9 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm,
     });
     return warp_sum_int(bad) == 0;
   };
+  double eps_scale = 1.0;  // tightened by the verified-polish rounds (DESIGN.md deviation D2)
   auto check_termination = [&](bool approximate) -> int {
-    double eps_abs = st.eps_abs, eps_rel = st.eps_rel, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
+    double eps_abs = st.eps_abs * eps_scale, eps_rel = st.eps_rel * eps_scale, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
     if (approximate) {
       eps_abs *= 10; eps_rel *= 10; epi *= 10; edi *= 10;
     }
@@ -640,131 +643,131 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm,
     return QPS_UNSOLVED;
   };
 
-  for (iter = 1; iter <= st.max_iter; ++iter) {
-    const bool can_check = st.check_termination > 0 && (iter % st.check_termination == 0);
-    const bool rho_iter = st.adaptive_rho && st.adaptive_rho_interval > 0 && (iter % st.adaptive_rho_interval == 0);
-    const bool keep_steps = can_check || iter == st.max_iter;
-    // ---- right-hand side:  sigma x - q + A'(rho z - y), aux part eliminated -------------------------
-    for (int i = lane; i < N; i += 32) {
-      const double beta = q.Eb[i] * q.Dz[i];
-      const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
-      q.v1[i] = q.sigma * q.x[i] - q.qs[i] + beta * (rb * q.zb[i] - q.yb[i]);
-    }
-    __syncwarp();
-    q.for_rows([&](int r) {
-      double* R = q.R(r);
-      double* F = R + q.CN;
-      RowV v;
-      row_view(q, R, q.I(r), v);
-      double Wr, g0, g1, ssum;
-      row_weights(q, sysw, F, v, Wr, g0, g1, ssum);
-      const double s = Wr * F[F_Z] - F[F_Y];
-      if (v.naux >= 1) F[F_RA0] = q.sigma * F[F_XA0] - v.qa0 + v.u0 * s + v.b0 * (sysw.rho_aux * F[F_ZA0] - F[F_YA0]);
-      if (v.naux == 2) F[F_RA1] = q.sigma * F[F_XA1] - v.qa1 + v.u1 * s + v.b1 * (sysw.rho_aux * F[F_ZA1] - F[F_YA1]);
-      row_reduce_rhs(q, R, F, v, Wr, g0, g1, ssum, s);
-    });
-    band_solve(q, q.v1);
-    // ---- rows: back-substitute aux, relax, project, dual update ----------------------------------------
-    q.for_rows([&](int r) {
-      double* R = q.R(r);
-      double* F = R + q.CN;
-      RowV v;
-      row_view(q, R, q.I(r), v);
-      double Wr, g0, g1, ssum, zeta, a0, a1;
-      row_weights(q, sysw, F, v, Wr, g0, g1, ssum);
-      row_backsub(q, R, F, v, Wr, g0, g1, ssum, zeta, a0, a1);
-      const double zt = zeta + v.u0 * a0 + v.u1 * a1;
-      {
-        const double zr = q.alpha * zt + (1.0 - q.alpha) * F[F_Z];
-        double zn = zr + F[F_Y] / Wr;
-        zn = fmin(fmax(zn, v.lo), v.up);
-        const double dy = Wr * (zr - zn);
-        F[F_Z] = zn;
-        F[F_Y] += dy;
-        F[F_DY] = dy;
+  // ADMM iterations, continuing from the current state until a termination test fires or max_iter.
+  auto run_admm = [&]() {
+    status = QPS_UNSOLVED;
+    while (iter < st.max_iter) {
+      ++iter;
+      const bool can_check = st.check_termination > 0 && (iter % st.check_termination == 0);
+      const bool rho_iter = st.adaptive_rho && st.adaptive_rho_interval > 0 && (iter % st.adaptive_rho_interval == 0);
+      const bool keep_steps = can_check || iter == st.max_iter;
+      // ---- right-hand side:  sigma x - q + A'(rho z - y), aux part eliminated -------------------------
+      for (int i = lane; i < N; i += 32) {
+        const double beta = q.Eb[i] * q.Dz[i];
+        const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
+        q.v1[i] = q.sigma * q.x[i] - q.qs[i] + beta * (rb * q.zb[i] - q.yb[i]);
       }
-      for (int k = 0; k < v.naux; ++k) {
-        const double at = k ? a1 : a0, bb = k ? v.b1 : v.b0;
-        const double xo = F[F_XA0 + k];
-        const double xn = q.alpha * at + (1.0 - q.alpha) * xo;
-        F[F_XA0 + k] = xn;
-        F[F_DXA0 + k] = xn - xo;
-        const double zr = q.alpha * (bb * at) + (1.0 - q.alpha) * F[F_ZA0 + k];
-        double zn = zr + F[F_YA0 + k] / sysw.rho_aux;
-        zn = fmin(fmax(zn, 0.0), kOsqpInf * F[F_EA0 + k]);
-        const double dy = sysw.rho_aux * (zr - zn);
-        F[F_ZA0 + k] = zn;
-        F[F_YA0 + k] += dy;
-        F[F_DYA0 + k] = dy;
+      __syncwarp();
+      q.for_rows([&](int r) {
+        double* R = q.R(r);
+        double* F = R + q.CN;
+        RowV v;
+        row_view(q, R, q.I(r), v);
+        double Wr, g0, g1, den;
+        row_weights(q, sysw, F, v, Wr, g0, g1, den);
+        const double s = Wr * F[F_Z] - F[F_Y];
+        if (v.naux >= 1) F[F_RA0] = q.sigma * F[F_XA0] - v.qa0 + v.u0 * s + v.b0 * (sysw.rho_aux * F[F_ZA0] - F[F_YA0]);
+        if (v.naux == 2) F[F_RA1] = q.sigma * F[F_XA1] - v.qa1 + v.u1 * s + v.b1 * (sysw.rho_aux * F[F_ZA1] - F[F_YA1]);
+        row_reduce_rhs(q, R, F, v, Wr, g0, g1, den, s);
+      });
+      band_solve(q, q.v1);
+      // ---- rows: back-substitute aux, relax, project, dual update ----------------------------------------
+      q.for_rows([&](int r) {
+        double* R = q.R(r);
+        double* F = R + q.CN;
+        RowV v;
+        row_view(q, R, q.I(r), v);
+        double Wr, g0, g1, den, zeta, a0, a1;
+        row_weights(q, sysw, F, v, Wr, g0, g1, den);
+        row_backsub(q, R, F, v, Wr, g0, g1, den, zeta, a0, a1);
+        const double zt = zeta + v.u0 * a0 + v.u1 * a1;
+        {
+          const double zr = q.alpha * zt + (1.0 - q.alpha) * F[F_Z];
+          double zn = zr + F[F_Y] / Wr;
+          zn = fmin(fmax(zn, v.lo), v.up);
+          const double dy = Wr * (zr - zn);
+          F[F_Z] = zn;
+          F[F_Y] += dy;
+          F[F_DY] = dy;
+        }
+        for (int k = 0; k < v.naux; ++k) {
+          const double at = k ? a1 : a0, bb = k ? v.b1 : v.b0;
+          const double xo = F[F_XA0 + k];
+          const double xn = q.alpha * at + (1.0 - q.alpha) * xo;
+          F[F_XA0 + k] = xn;
+          F[F_DXA0 + k] = xn - xo;
+          const double zr = q.alpha * (bb * at) + (1.0 - q.alpha) * F[F_ZA0 + k];
+          double zn = zr + F[F_YA0 + k] / sysw.rho_aux;
+          zn = fmin(fmax(zn, 0.0), kOsqpInf * F[F_EA0 + k]);
+          const double dy = sysw.rho_aux * (zr - zn);
+          F[F_ZA0 + k] = zn;
+          F[F_YA0 + k] += dy;
+          F[F_DYA0 + k] = dy;
+        }
+      });
+      // ---- trajectory variables and their bound rows -----------------------------------------------------
+      for (int i = lane; i < N; i += 32) {
+        const double beta = q.Eb[i] * q.Dz[i];
+        const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
+        const double xt = q.v1[i];
+        const double xn = q.alpha * xt + (1.0 - q.alpha) * q.x[i];
+        const double zr = q.alpha * (beta * xt) + (1.0 - q.alpha) * q.zb[i];
+        double zn = zr + q.yb[i] / rb;
+        zn = fmin(fmax(zn, q.lbs[i]), q.ubs[i]);
+        const double dy = rb * (zr - zn);
+        if (keep_steps) {
+          dxs[i] = xn - q.x[i];
+          dyb[i] = dy;
+        }
+        q.x[i] = xn;
+        q.zb[i] = zn;
+        q.yb[i] += dy;
       }
-    });
-    // ---- trajectory variables and their bound rows -----------------------------------------------------
-    for (int i = lane; i < N; i += 32) {
-      const double beta = q.Eb[i] * q.Dz[i];
-      const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
-      const double xt = q.v1[i];
-      const double xn = q.alpha * xt + (1.0 - q.alpha) * q.x[i];
-      const double zr = q.alpha * (beta * xt) + (1.0 - q.alpha) * q.zb[i];
-      double zn = zr + q.yb[i] / rb;
-      zn = fmin(fmax(zn, q.lbs[i]), q.ubs[i]);
-      const double dy = rb * (zr - zn);
-      if (keep_steps) {
-        dxs[i] = xn - q.x[i];
-        dyb[i] = dy;
+      __syncwarp();
+      if (can_check) {
+        info_pass();
+        status = check_termination(false);
+        if (status != QPS_UNSOLVED) return;
       }
-      q.x[i] = xn;
-      q.zb[i] = zn;
-      q.yb[i] += dy;
-    }
-    __syncwarp();
-    if (can_check) {
-      info_pass();
-      status = check_termination(false);
-      if (status != QPS_UNSOLVED) break;
-    }
-    if (rho_iter) {
-      if (!can_check) info_pass();
-      // compute_rho_estimate on the scaled quantities [EXT]
-      const double pn = s_pri / (fmax(s_z, s_ax) + 1e-10);
-      const double dn = s_dua / (fmax(s_q, fmax(s_aty, s_px)) + 1e-10);
-      double rho_new = rho * sqrt(pn / (dn + 1e-10));
-      rho_new = fmin(fmax(rho_new, kRhoMin), kRhoMax);
-      if (rho_new > rho * st.adaptive_rho_tolerance || rho_new < rho / st.adaptive_rho_tolerance) {
-        rho = rho_new;
-        q.rho = rho;
-        q.rho_eq = kRhoEqOverIneq * rho;
-        sysw.rho_aux = rho;
-        if (!assemble_factor(q, sysw)) {
-          status = QPS_NONCVX;
-          break;
+      if (rho_iter) {
+        if (!can_check) info_pass();
+        // compute_rho_estimate on the scaled quantities [EXT]
+        const double pn = s_pri / (fmax(s_z, s_ax) + 1e-10);
+        const double dn = s_dua / (fmax(s_q, fmax(s_aty, s_px)) + 1e-10);
+        double rho_new = rho * sqrt(pn / (dn + 1e-10));
+        rho_new = fmin(fmax(rho_new, kRhoMin), kRhoMax);
+        if (rho_new > rho * st.adaptive_rho_tolerance || rho_new < rho / st.adaptive_rho_tolerance) {
+          rho = rho_new;
+          q.rho = rho;
+          q.rho_eq = kRhoEqOverIneq * rho;
+          sysw.rho_aux = rho;
+          out.rho_updates++;
+          if (!assemble_factor(q, sysw)) {
+            status = QPS_NONCVX;
+            return;
+          }
         }
       }
     }
-  }
-  if (iter > st.max_iter) {
-    iter = st.max_iter;
-    if (status == QPS_UNSOLVED) {
-      // dx / dy of the last iteration are only kept on check iterations; max_iter is a multiple of the
-      // check interval in every configuration used (8192 = 25*327.68 is NOT) -> recompute conservatively:
-      if (!(st.check_termination > 0 && (iter % st.check_termination == 0))) info_pass();
-      status = check_termination(true);
-      if (status == QPS_UNSOLVED) status = QPS_MAXITER;
-    }
-  }
-  out.iters = iter;
-  out.status = status;
-  out.rho = rho;
+    // max_iter reached without a verdict: approximate test, then MAX_ITER_REACHED
+    if (!(st.check_termination > 0 && (iter % st.check_termination == 0))) info_pass();
+    status = check_termination(true);
+    if (status == QPS_UNSOLVED) status = QPS_MAXITER;
+  };
 
-  // ------------------------------------------------------------------ polish (OSQP polish.c [EXT])
+  // ---- polish (OSQP polish.c [EXT]) ---------------------------------------------------------------------
   // Equality-constrained QP on the guessed active set, solved as the delta-regularised KKT system with
   // iterative refinement, in its reduced form K_p = P + delta I + (1/delta) A_act' A_act (same aux
-  // elimination and banded factor as the ADMM system).
-  if (status == QPS_SOLVED && st.polishing) {
-    double* st_x = q.scratch + 2 * N;   // ADMM x, yb stashed while polish reuses x / zb / yb
-    double* st_yb = q.scratch + 3 * N;
-    const double wp = 1.0 / st.delta;
+  // elimination and banded factor as the ADMM system).  Returns false when K_p could not be factored.
+  // `verified`: the polished point is primal feasible to verify_tol and every active inequality row has a
+  // correctly signed multiplier, i.e. it is a KKT point of the QP = the unique minimiser.
+  const double wp = 1.0 / st.delta;
+  const SysW pw{true, st.delta, 0.0};
+  auto polish_once = [&](bool& verified, double& p_pri, double& p_dua) -> bool {
+    verified = false;
     for (int i = lane; i < N; i += 32) {
       st_x[i] = q.x[i];
+      st_zb[i] = q.zb[i];
       st_yb[i] = q.yb[i];
       const double z = q.zb[i], y = q.yb[i];
       double w = 0.0;
@@ -797,106 +800,151 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm,
       F[F_PY] = 0.0;
     });
     __syncwarp();
-    SysW pw{true, st.delta, 0.0};
-    bool ok = assemble_factor(q, pw);
-    if (ok) {
-      for (int it = 0; it <= st.polish_refine_iter + 1; ++it) {
-        const bool last = (it == st.polish_refine_iter + 1);  // final pass: only the pending dual update + residuals
-        // v1 <- P xq ; residual rd = -(P x + q + A'y) - A' W (A x - b), y update of the previous step folded in
-        p_matvec(q, q.x, q.v1);
-        double p_pri = 0.0, p_dua_a = 0.0;
-        for (int i = lane; i < N; i += 32) {
-          const double beta = q.Eb[i] * q.Dz[i];
-          const double ax = beta * q.x[i];
-          const double w = fabs(q.zb[i]);
-          const double bnd = q.zb[i] > 0 ? q.ubs[i] : q.lbs[i];
-          if (it > 0 && w != 0.0) q.yb[i] += w * (ax - bnd);
-          const double e = q.yb[i] + (last ? 0.0 : w * (ax - bnd));
-          const double zc = fmin(fmax(ax, q.lbs[i]), q.ubs[i]);
-          p_pri = fmax(p_pri, fabs((ax - zc) / q.Eb[i]));
-          q.v2[i] = q.v1[i] + q.qs[i] + beta * q.yb[i];  // dual residual (uses y only)
-          q.v1[i] = -(q.v1[i] + q.qs[i]) - beta * e;
-        }
-        __syncwarp();
-        q.for_rows([&](int r) {
-          double* R = q.R(r);
-          double* F = R + q.CN;
-          RowV v;
-          row_view(q, R, q.I(r), v);
-          double Wr, g0, g1, ssum;
-          row_weights(q, pw, F, v, Wr, g0, g1, ssum);
-          double ax = 0.0;
-          for (int i = 0; i < v.cnt; ++i) {
-            const int vi = v.base + i * v.stride;
-            ax += v.E * R[i] * q.Dz[vi] * q.x[vi];
-          }
-          ax += v.u0 * F[F_PX0] + v.u1 * F[F_PX1];
-          if (it > 0 && Wr != 0.0) F[F_PY] += Wr * (ax - F[F_PB]);
-          const double e = F[F_PY] + (last ? 0.0 : Wr * (ax - F[F_PB]));
-          const double zc = fmin(fmax(ax, v.lo), v.up);
-          p_pri = fmax(p_pri, fabs((ax - zc) / v.E));
-          double ea[2] = {0.0, 0.0};
-          for (int k = 0; k < v.naux; ++k) {
-            const double bb = k ? v.b1 : v.b0, u = k ? v.u1 : v.u0, qa = k ? v.qa1 : v.qa0;
-            const double wa = fabs(F[F_PWA0 + k]);
-            const double axb = bb * F[F_PX0 + k];
-            if (it > 0 && wa != 0.0) F[F_PYA0 + k] += wa * (axb - 0.0);
-            ea[k] = F[F_PYA0 + k] + (last ? 0.0 : wa * axb);
-            const double zca = fmax(axb, 0.0);
-            p_pri = fmax(p_pri, fabs((axb - zca) / F[F_EA0 + k]));
-            p_dua_a = fmax(p_dua_a, fabs((qa + u * F[F_PY] + bb * F[F_PYA0 + k]) / F[F_DA0 + k]));
-            F[F_RA0 + k] = -qa - u * e - bb * ea[k];
-          }
-          for (int i = 0; i < v.cnt; ++i) {
-            const int vi = v.base + i * v.stride;
-            q.v2[vi] += v.E * R[i] * q.Dz[vi] * F[F_PY];
-          }
-          if (!last) row_reduce_rhs(q, R, F, v, Wr, g0, g1, ssum, -e);
-        });
-        if (last) {
-          double p_dua = p_dua_a;
-          for (int i = lane; i < N; i += 32) p_dua = fmax(p_dua, fabs(q.v2[i] / q.Dz[i]));
-          p_pri = warp_max(p_pri);
-          p_dua = warp_max(p_dua) * q.cinv;
-          const bool accept = ((p_pri < pri_res && p_dua < dua_res) || (p_pri < pri_res && dua_res < 1e-10) ||
-                               (p_dua < dua_res && pri_res < 1e-10)) && isfinite(p_pri) && isfinite(p_dua);
-          out.polish = accept ? 1 : -1;
-          break;
-        }
-        band_solve(q, q.v1);
-        q.for_rows([&](int r) {
-          double* R = q.R(r);
-          double* F = R + q.CN;
-          RowV v;
-          row_view(q, R, q.I(r), v);
-          double Wr, g0, g1, ssum, zeta, a0, a1;
-          row_weights(q, pw, F, v, Wr, g0, g1, ssum);
-          row_backsub(q, R, F, v, Wr, g0, g1, ssum, zeta, a0, a1);
-          F[F_PX0] += a0;
-          F[F_PX1] += a1;
-        });
-        for (int i = lane; i < N; i += 32) q.x[i] += q.v1[i];
-        __syncwarp();
-      }
-    } else {
-      out.polish = -1;
-    }
-    if (out.polish == 1) {  // adopt the polished point: x <- xq, y <- yq (zero off the active set)
-      q.for_rows([&](int r) {
-        double* F = q.R(r) + q.CN;
-        F[F_Y] = F[F_PY];
-        for (int k = 0; k < 2; ++k) {
-          F[F_XA0 + k] = F[F_PX0 + k];
-          F[F_YA0 + k] = F[F_PYA0 + k];
-        }
-      });
-    } else {
+    if (!assemble_factor(q, pw)) return false;
+    for (int it = 0; it <= st.polish_refine_iter + 1; ++it) {
+      const bool last = (it == st.polish_refine_iter + 1);  // final pass: pending dual update + residuals only
+      // v1 <- P xq ; residual rd = -(P x + q + A'y) - A' W (A x - b), y update of the previous step folded in
+      p_matvec(q, q.x, q.v1);
+      double m_pri = 0.0, m_dua_a = 0.0;
+      int bad_sign = 0;
       for (int i = lane; i < N; i += 32) {
-        q.x[i] = st_x[i];
-        q.yb[i] = st_yb[i];
+        const double beta = q.Eb[i] * q.Dz[i];
+        const double ax = beta * q.x[i];
+        const double w = fabs(q.zb[i]);
+        const double bnd = q.zb[i] > 0 ? q.ubs[i] : q.lbs[i];
+        if (it > 0 && w != 0.0) q.yb[i] += w * (ax - bnd);
+        const double e = q.yb[i] + (last ? 0.0 : w * (ax - bnd));
+        const double zc = fmin(fmax(ax, q.lbs[i]), q.ubs[i]);
+        m_pri = fmax(m_pri, fabs((ax - zc) / q.Eb[i]));
+        if (last && w != 0.0 && q.ubs[i] - q.lbs[i] >= kRhoTol) {
+          if (q.zb[i] > 0 && q.yb[i] < -kVerifyTol) bad_sign = 1;
+          if (q.zb[i] < 0 && q.yb[i] > kVerifyTol) bad_sign = 1;
+        }
+        q.v2[i] = q.v1[i] + q.qs[i] + beta * q.yb[i];  // dual residual (uses y only)
+        q.v1[i] = -(q.v1[i] + q.qs[i]) - beta * e;
       }
       __syncwarp();
+      q.for_rows([&](int r) {
+        double* R = q.R(r);
+        double* F = R + q.CN;
+        RowV v;
+        row_view(q, R, q.I(r), v);
+        double Wr, g0, g1, den;
+        row_weights(q, pw, F, v, Wr, g0, g1, den);
+        double ax = 0.0;
+        for (int i = 0; i < v.cnt; ++i) {
+          const int vi = v.base + i * v.stride;
+          ax += v.E * R[i] * q.Dz[vi] * q.x[vi];
+        }
+        ax += v.u0 * F[F_PX0] + v.u1 * F[F_PX1];
+        if (it > 0 && Wr != 0.0) F[F_PY] += Wr * (ax - F[F_PB]);
+        const double e = F[F_PY] + (last ? 0.0 : Wr * (ax - F[F_PB]));
+        const double zc = fmin(fmax(ax, v.lo), v.up);
+        m_pri = fmax(m_pri, fabs((ax - zc) / v.E));
+        if (last && Wr != 0.0 && v.naux == AUX_HINGE) {  // inequality row (l = -inf): upper active needs y >= 0
+          if (F[F_PY] < -kVerifyTol) bad_sign = 1;
+        }
+        double ea[2] = {0.0, 0.0};
+        for (int k = 0; k < v.naux; ++k) {
+          const double bb = k ? v.b1 : v.b0, u = k ? v.u1 : v.u0, qa = k ? v.qa1 : v.qa0;
+          const double wa = fabs(F[F_PWA0 + k]);
+          const double axb = bb * F[F_PX0 + k];
+          if (it > 0 && wa != 0.0) F[F_PYA0 + k] += wa * (axb - 0.0);
+          ea[k] = F[F_PYA0 + k] + (last ? 0.0 : wa * axb);
+          const double zca = fmax(axb, 0.0);
+          m_pri = fmax(m_pri, fabs((axb - zca) / F[F_EA0 + k]));
+          if (last && wa != 0.0 && F[F_PYA0 + k] > kVerifyTol) bad_sign = 1;  // aux >= 0 held at 0 needs y <= 0
+          m_dua_a = fmax(m_dua_a, fabs((qa + u * F[F_PY] + bb * F[F_PYA0 + k]) / F[F_DA0 + k]));
+          F[F_RA0 + k] = -qa - u * e - bb * ea[k];
+        }
+        for (int i = 0; i < v.cnt; ++i) {
+          const int vi = v.base + i * v.stride;
+          q.v2[vi] += v.E * R[i] * q.Dz[vi] * F[F_PY];
+        }
+        if (!last) row_reduce_rhs(q, R, F, v, Wr, g0, g1, den, -e);
+      });
+      if (last) {
+        double m_dua = m_dua_a;
+        for (int i = lane; i < N; i += 32) m_dua = fmax(m_dua, fabs(q.v2[i] / q.Dz[i]));
+        p_pri = warp_max(m_pri);
+        p_dua = warp_max(m_dua) * q.cinv;
+        const int nbad = warp_sum_int(bad_sign);
+        verified = (nbad == 0) && (p_pri <= kVerifyTol) && isfinite(p_pri) && isfinite(p_dua);
+        break;
+      }
+      band_solve(q, q.v1);
+      q.for_rows([&](int r) {
+        double* R = q.R(r);
+        double* F = R + q.CN;
+        RowV v;
+        row_view(q, R, q.I(r), v);
+        double Wr, g0, g1, den, zeta, a0, a1;
+        row_weights(q, pw, F, v, Wr, g0, g1, den);
+        row_backsub(q, R, F, v, Wr, g0, g1, den, zeta, a0, a1);
+        F[F_PX0] += a0;
+        F[F_PX1] += a1;
+      });
+      for (int i = lane; i < N; i += 32) q.x[i] += q.v1[i];
+      __syncwarp();
     }
+    return true;
+  };
+  auto restore_admm_state = [&](bool keep_polished_x) {
+    for (int i = lane; i < N; i += 32) {
+      if (!keep_polished_x) q.x[i] = st_x[i];
+      q.zb[i] = st_zb[i];
+      q.yb[i] = st_yb[i];
+    }
+    __syncwarp();
+  };
+
+  // ---- main loop: ADMM -> polish -> verify; on a failed verification ADMM continues with 10x tighter ------
+  // tolerances (DESIGN.md deviation D2; verify_rounds = 0 is plain OSQP behaviour).
+  int round = 0;
+  while (true) {
+    run_admm();
+    out.pri_res = pri_res;
+    out.dua_res = dua_res;
+    if (status != QPS_SOLVED || !st.polishing) break;
+    bool verified = false;
+    double p_pri = 0.0, p_dua = 0.0;
+    const bool factored = polish_once(verified, p_pri, p_dua);
+    out.pol_factor_ok = factored ? 1 : 0;
+    out.pol_pri = p_pri;
+    out.pol_dua = p_dua;
+    out.rounds = round;
+    if (factored && verified) {
+      out.polish = 1;
+      break;
+    }
+    if (round >= kVerifyRounds || iter >= st.max_iter) {  // OSQP's acceptance rule
+      const bool ok = factored && ((p_pri < pri_res && p_dua < dua_res) || (p_pri < pri_res && dua_res < 1e-10) ||
+                                   (p_dua < dua_res && pri_res < 1e-10)) && isfinite(p_pri) && isfinite(p_dua);
+      out.polish = ok ? 2 : -1;
+      break;
+    }
+    ++round;
+    eps_scale *= 0.1;
+    restore_admm_state(false);
+    if (!assemble_factor(q, sysw)) {  // back to the ADMM factor
+      status = QPS_NONCVX;
+      break;
+    }
+  }
+  out.iters = iter;
+  out.status = status;
+  out.rho = rho;
+  out.c = q.c;
+  if (out.polish != 0) {
+    // Adopt the polished PRIMAL point when accepted.  The duals kept for the next warm start are always the
+    // ADMM duals: polished duals are non-unique on degenerate active sets (DESIGN.md deviation D1).
+    if (out.polish > 0) {
+      q.for_rows([&](int r) {
+        double* F = q.R(r) + q.CN;
+        for (int k = 0; k < 2; ++k) F[F_XA0 + k] = F[F_PX0 + k];
+      });
+    }
+    restore_admm_state(out.polish > 0);
   }
   return out;
 }
@@ -930,7 +978,7 @@ __global__ void __launch_bounds__(32) qp_kernel(DevProblem p, const double* x_ov
   int* obj_start = mylist + 2 * p.max_rows;  // [n_costs + n_cnts + 1]
   q.list = mylist;
   q.Pband = p.Pband;
-  q.scratch = p.scratch + static_cast<size_t>(b) * 4 * N;
+  q.scratch = p.scratch + static_cast<size_t>(b) * 5 * N;
 
   const double* xc = (x_override ? x_override : p.x) + static_cast<size_t>(b) * N;
   const double trust = trust_override ? trust_override[b] : p.trust[b];
@@ -1144,6 +1192,10 @@ __global__ void __launch_bounds__(32) qp_kernel(DevProblem p, const double* x_ov
     if (!x_override) p.n_admm_iters[b] += res.iters;
     if (admm_iters_out) admm_iters_out[b] = res.iters;
     if (polish_out) polish_out[b] = res.polish;
+    double* g = p.dbg + static_cast<size_t>(b) * 16;
+    g[0] = res.status; g[1] = res.iters; g[2] = res.polish; g[3] = res.rho; g[4] = res.pri_res; g[5] = res.dua_res;
+    g[6] = res.pol_pri; g[7] = res.pol_dua; g[8] = res.c; g[9] = res.pol_factor_ok; g[10] = res.rho_updates;
+    g[11] = nr; g[12] = n_aux; g[13] = nnzA; g[14] = warm ? 1 : 0; g[15] = res.rounds;
   }
 }
 

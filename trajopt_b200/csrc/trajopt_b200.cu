@@ -80,10 +80,10 @@ struct tb200_problem {
   DevBuf<DevCartTerm> cart_terms;
   DevBuf<int> fixed_vars;
   DevBuf<double> x, new_x, trust, merit_coeffs, cost_vals, cnt_viols, new_cost_vals, new_cnt_viols, model_cost_vals,
-      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp;
+      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace;
   DevBuf<unsigned long long> coll_mask;
   DevBuf<int> status, sqp_iter, merit_round, qp_failures, qp_status, cur_buf, n_qp_solves, n_func_evals, n_admm_iters,
-      active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish;
+      active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish, trace_len;
   std::vector<cudaEvent_t> events;
   ~tb200_problem() {
     for (auto e : events) cudaEventDestroy(e);
@@ -94,7 +94,7 @@ struct tb200_problem {
     x.release(); new_x.release(); trust.release(); merit_coeffs.release(); cost_vals.release(); cnt_viols.release();
     new_cost_vals.release(); new_cnt_viols.release(); model_cost_vals.release(); model_cnt_viols.release();
     cart_err.release(); cart_jac.release(); coll_rows.release(); rows.release(); ws_x.release(); ws_yb.release();
-    scratch.release(); ws_rho.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
+    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
     sqp_iter.release(); merit_round.release(); qp_failures.release(); qp_status.release(); cur_buf.release();
     n_qp_solves.release(); n_func_evals.release(); n_admm_iters.release(); active_count.release(); row_ints.release();
     lists.release(); ws_meta.release(); tmp_iters.release(); tmp_polish.release();
@@ -398,9 +398,11 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   ALLOC(coll_mask, 2 * Bs * std::max(1, dp.n_coll_objs * dp.coll_words));
   ALLOC(rows, Bs * max_rows * dp.row_stride); ALLOC(row_ints, Bs * max_rows * RI_NINTS);
   ALLOC(lists, Bs * (2 * static_cast<size_t>(max_rows) + dp.n_costs + dp.n_cnts + 2));
-  ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 4 * N); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 4);
+  ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 5 * N); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 4);
   ALLOC(status, Bs); ALLOC(sqp_iter, Bs); ALLOC(merit_round, Bs); ALLOC(qp_failures, Bs); ALLOC(qp_status, Bs);
   ALLOC(cur_buf, Bs); ALLOC(n_qp_solves, Bs); ALLOC(n_func_evals, Bs); ALLOC(n_admm_iters, Bs); ALLOC(active_count, 1);
+  ALLOC(dbg, Bs * 16);
+  ALLOC(trace_len, Bs);
   ALLOC(x_tmp, Bs * N); ALLOC(trust_tmp, Bs); ALLOC(tmp_iters, Bs); ALLOC(tmp_polish, Bs);
 #undef ALLOC
 #undef UPLOAD
@@ -416,7 +418,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.n_func_evals = P->n_func_evals.p; dp.n_admm_iters = P->n_admm_iters.p; dp.active_count = P->active_count.p;
   dp.cart_err = P->cart_err.p; dp.cart_jac = P->cart_jac.p; dp.coll_rows = P->coll_rows.p; dp.coll_mask = P->coll_mask.p;
   dp.rows = P->rows.p; dp.row_ints = P->row_ints.p; dp.lists = P->lists.p; dp.ws_x = P->ws_x.p; dp.ws_yb = P->ws_yb.p;
-  dp.scratch = P->scratch.p; dp.ws_meta = P->ws_meta.p; dp.ws_rho = P->ws_rho.p;
+  dp.scratch = P->scratch.p; dp.ws_meta = P->ws_meta.p; dp.ws_rho = P->ws_rho.p; dp.dbg = P->dbg.p; dp.trace_len = P->trace_len.p; dp.trace = nullptr; dp.trace_cap = 0;
   P->ex.cart_objs = P->d_cart_objs.p;
   P->ex.coll_objs = P->d_coll_objs.p;
   // settings
@@ -481,6 +483,7 @@ __global__ void reset_state_kernel(DevProblem p) {
   for (int c = 0; c < p.n_cnts; ++c) p.merit_coeffs[static_cast<size_t>(b) * p.n_cnts + c] = p.sqp.initial_merit_error_coeff;
   for (int k = 0; k < 4; ++k) p.ws_meta[b * 4 + k] = 0;
   p.ws_rho[b] = p.qp.rho;
+  p.trace_len[b] = 0;
 }
 
 cudaEvent_t getEvent(tb200_problem* P, size_t i) {
@@ -643,6 +646,39 @@ int tb200_qp_solve_batch(tb200_problem* P, const double* x, const double* trust,
   CK(pull(model_cnt_viols, dp.model_cnt_viols, B * dp.n_cnts * sizeof(double)));
   CK(pull(admm_iters, P->tmp_iters.p, B * sizeof(int)));
   CK(cudaStreamSynchronize(st));
+  return TB200_OK;
+}
+
+int tb200_last_qp_polish(tb200_problem* P, int32_t* polish) {
+  if (!P || !polish) return fail(TB200_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(P->device));
+  CK(cudaMemcpy(polish, P->tmp_polish.p, static_cast<size_t>(P->dp.B) * sizeof(int), cudaMemcpyDeviceToHost));
+  return TB200_OK;
+}
+
+/* not part of the public header: enable the per-decision trace (cap entries per trajectory) / fetch it */
+int tb200_debug_enable_trace(tb200_problem* P, int cap) {
+  if (!P) return fail(TB200_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(P->device));
+  P->trace.release();
+  CK(P->trace.alloc(static_cast<size_t>(P->dp.B) * cap * 14));
+  P->dp.trace = P->trace.p;
+  P->dp.trace_cap = cap;
+  return TB200_OK;
+}
+int tb200_debug_fetch_trace(tb200_problem* P, double* out, int32_t* len) {
+  if (!P || !out || !len) return fail(TB200_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(P->device));
+  CK(cudaMemcpy(out, P->trace.p, P->trace.n * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(len, P->trace_len.p, static_cast<size_t>(P->dp.B) * sizeof(int), cudaMemcpyDeviceToHost));
+  return TB200_OK;
+}
+
+/* not part of the public header: solver diagnostics of the last QP of every trajectory, [B][16] */
+int tb200_debug_last_qp(tb200_problem* P, double* out) {
+  if (!P || !out) return fail(TB200_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(P->device));
+  CK(cudaMemcpy(out, P->dbg.p, static_cast<size_t>(P->dp.B) * 16 * sizeof(double), cudaMemcpyDeviceToHost));
   return TB200_OK;
 }
 
