@@ -56,26 +56,6 @@ struct DevCartTerm {
   int n_idx, pad;
 };
 
-// row record layout in the QP workspace: kRowCoef doubles of coefficients, then these fields
-enum RowField {
-  F_C = 0,   // row constant (unscaled):  a.x + c {<=,=} 0
-  F_W,       // cost on each aux variable (unscaled)
-  F_E,       // Ruiz row scaling
-  F_DA0, F_DA1,   // aux column scalings
-  F_EA0, F_EA1,   // aux bound-row scalings
-  F_XA0, F_XA1,   // aux values (scaled during the solve, unscaled between solves)
-  F_Z, F_Y,
-  F_ZA0, F_ZA1, F_YA0, F_YA1,
-  F_RA0, F_RA1,   // aux part of the current right-hand side
-  F_DY, F_DYA0, F_DYA1,
-  F_DXA0, F_DXA1,         // last aux step (dual infeasibility test)
-  F_PW, F_PWA0, F_PWA1,   // polish weights (0 or 1/delta)
-  F_PB,                   // polish target (scaled bound)
-  F_PY, F_PYA0, F_PYA1,   // polish multipliers
-  F_PX0, F_PX1,           // polish aux values
-  F_MV,                   // model violation of this row at the returned solution
-  F_NFIELDS
-};
 enum RowInt { RI_BASE = 0, RI_CNT, RI_STRIDE, RI_AUX, RI_OBJ, RI_PAD, RI_NINTS };
 enum AuxKind { AUX_NONE = 0, AUX_HINGE = 1, AUX_ABS = 2 };
 
@@ -143,11 +123,16 @@ struct DevProblem {
   // QP workspace (per trajectory)
   double* rows;                // [B][max_rows][row_stride]
   int* row_ints;               // [B][max_rows][RI_NINTS]
-  int* lists;                  // [B][(T+1) + (D+1) + 2*max_rows + n_objs + 1] per-lane row lists
+  int* lists;                  // [B][list_stride]: column pointers, column entries, object row ranges
+  size_t list_stride;
   double* ws_x;                // [B][N]  warm start: previous QP solution (trajectory part, unscaled)
   double* ws_yb;               // [B][N]  warm start: duals of the variable-bound rows (unscaled)
-  double* scratch;             // [B][5N]
-  int* ws_meta;                // [B][4]: n_aux, m_rows, nnzA, last status
+  double* scratch;             // [B][8*Np]: dx dy stash(x zb yb) | scaled q, lb, ub of the trajectory variables
+  double* park;                // [B][5*Np]: x zb yb Dz beta of a QP parked between time slices
+  int* rs_int;                 // [B][4] parked solver state
+  double* rs_dbl;              // [B][4]
+  int* qp_done;                // [B] 1: a QP solution is waiting for its evaluation
+  int* ws_meta;                // [B][8]: warm-start key (n_aux, rows, nnzA, last status), phase, parked sizes
   double* ws_rho;              // [B]
   double* trace;               // [B][trace_cap][14] decision trace (same columns as the oracle's TraceEntry)
   int* trace_len;              // [B]

@@ -113,6 +113,7 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
   const int tid = threadIdx.x;
   const int T = p.T, D = p.D, N = p.N, L = p.L, O = p.O;
   if (mode != EVAL_ONLY && p.status[b] != 5 /*running == INVALID*/) return;
+  if (mode == EVAL_STEP && p.qp_done[b] == 0) return;  // its QP is still being solved (time-sliced)
   const bool qp_failed = (mode == EVAL_STEP) && (p.qp_status[b] != 0);
   const int n_mask_words = p.n_coll_objs * p.coll_words;
   const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_cand, n_mask_words);
@@ -410,6 +411,7 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
       }
     }
     p.trust[b] = trust;
+    if (mode == EVAL_STEP) p.qp_done[b] = 0;
     misc[0] = accept;
     if (finished) {
       misc[1] = 1;

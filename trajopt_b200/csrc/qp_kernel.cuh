@@ -1,15 +1,27 @@
-// QP subproblem kernel: one warp per trajectory.
+// QP subproblem kernel: one warp per trajectory, time sliced.
 //
 // Replaces OSQPModel::optimize() -> osqp_setup/osqp_solve (trajopt_sco/src/osqp_interface.cpp:283-615) for
 // every trajectory of the batch: the l1-penalty QP of optimizers.cpp:781-799 (Appendix B of SURVEY.md) is
 // assembled from the fixed-layout convexification rows, equilibrated (Ruiz), and solved with the
 // OSQP-equivalent ADMM (rho_eq = 1e3 rho, sigma, alpha relaxation, residual tests every 25 iterations,
-// adaptive rho with refactorisation, polish).  Linear algebra: the KKT solve is done in its reduced form
-//   (P + sigma I + A' diag(rho) A) x = rhs
-// after eliminating, row by row and in closed form, the hinge / abs auxiliary variables (each couples to
-// exactly one row): what is left is an N x N symmetric positive definite matrix, N = T*D, with half
-// bandwidth 2*D (block tridiagonal in time).  It is factored once per rho in shared memory and every
-// ADMM iteration is two banded triangular solves + one pass over the rows (projection, dual update).
+// adaptive rho with refactorisation, polish).
+//
+// Linear algebra.  The KKT solve is done in its reduced form (P + sigma I + A' diag(rho) A) x = rhs after
+// eliminating, row by row and in closed form, the hinge / abs auxiliary variables (each couples to exactly
+// one row).  What is left is an N x N symmetric positive definite matrix, N = T*D, with half bandwidth
+// nb = 2*D: block tridiagonal with nb x nb blocks.  It is factored in shared memory (band Cholesky), the
+// diagonal blocks of the factor are inverted once per factorisation, and every triangular solve is then a
+// chain of 2*M small triangular mat-vecs (M = N/nb) done with warp shuffles: two lanes per block row, the
+// running block vector lives in registers.
+//
+// Work distribution inside the warp.  Row-local work (aux back-substitution, projection, dual update) runs
+// one lane per row; accumulations into trajectory variables (A'v, the Hessian assembly, column norms) run one
+// lane per variable over per-column entry lists, so no atomics are needed and every sum has a fixed order.
+//
+// Time slicing.  A launch advances each unfinished QP by at most `slice` ADMM iterations and parks its state
+// in HBM; finished QPs raise qp_done and are consumed by eval_convexify_decide_kernel.  Trajectories
+// therefore walk through their own SQP state machines asynchronously: a slow QP (up to max_iter = 8192
+// iterations) no longer stalls the batch.
 #pragma once
 #include "device_types.cuh"
 #include "eval_kernel.cuh"
@@ -22,7 +34,7 @@ constexpr double kVerifyTol = 1e-9;  // KKT verification of the polished point (
 constexpr int kVerifyRounds = 3;
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoTol = 1e-4, kRhoEqOverIneq = 1e3;
 enum { QPS_UNSOLVED = 0, QPS_SOLVED = 1, QPS_SOLVED_INACC = 2, QPS_PINF = 3, QPS_PINF_INACC = 4, QPS_DINF = 5,
-       QPS_DINF_INACC = 6, QPS_MAXITER = 7, QPS_NONCVX = 8 };
+       QPS_DINF_INACC = 6, QPS_MAXITER = 7, QPS_NONCVX = 8, QPS_YIELD = 100 };
 
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
@@ -44,117 +56,83 @@ __device__ __forceinline__ double limit_scaling(double v) {
   return v > kMaxScaling ? kMaxScaling : v;
 }
 
+// ---- shared memory layout (doubles) ------------------------------------------------------------------
 struct QpSmem {
-  int Kb, Dz, Eb, qs, lbs, ubs, x, zb, yb, v1, v2, invd, ints, total;
+  int Kb, Linv, Dz, beta, x, zb, yb, v1, v2, total;
 };
-__host__ __device__ inline QpSmem qp_smem_layout(int N, int HB, int T, int D) {
+__host__ __device__ inline int qp_block_count(int N, int nb) { return (N + nb - 1) / nb; }
+__host__ __device__ inline QpSmem qp_smem_layout(int N, int nb) {
+  const int M = qp_block_count(N, nb), Np = M * nb, Wd = nb + 2;
   QpSmem s;
   int o = 0;
-  s.Kb = o;   o += N * (HB + 1);
-  s.Dz = o;   o += N;
-  s.Eb = o;   o += N;
-  s.qs = o;   o += N;
-  s.lbs = o;  o += N;
-  s.ubs = o;  o += N;
-  s.x = o;    o += N;
-  s.zb = o;   o += N;
-  s.yb = o;   o += N;
-  s.v1 = o;   o += N;
-  s.v2 = o;   o += N;
-  s.invd = o; o += N;
-  s.ints = o; o += (T + D + 2 + 1) / 2 + 1;
+  s.Kb = o;   o += Np * Wd;
+  s.Linv = o; o += M * (nb * (nb + 1) / 2);
+  s.Dz = o;   o += Np;
+  s.beta = o; o += Np;
+  s.x = o;    o += Np;
+  s.zb = o;   o += Np;
+  s.yb = o;   o += Np;
+  s.v1 = o;   o += Np;
+  s.v2 = o;   o += Np;
   s.total = o;
   return s;
 }
 
-// Per-warp solver context.  All lanes hold identical copies of the scalar members.
+// ---- per-row record (global memory): CN raw coefficients, CN scaled coefficients, then these fields ----
+enum RowF {
+  R_C = 0, R_W,                         // raw: constant, aux cost
+  R_E, R_DA0, R_DA1, R_EA0, R_EA1,      // Ruiz scalings
+  R_U0, R_U1, R_B0, R_B1, R_LO, R_UP, R_QA0, R_QA1, R_RHO,  // scaled view (R_RHO: 1 = equality row)
+  R_XA0, R_XA1, R_Z, R_Y, R_ZA0, R_ZA1, R_YA0, R_YA1,        // ADMM state
+  R_RA0, R_RA1, R_COEF, R_WR, R_G0, R_G1, R_DEN, R_WRR,      // per-solve temporaries (WRR: raw row weight)
+  R_DY, R_DYA0, R_DYA1, R_DXA0, R_DXA1,
+  R_PW, R_PWA0, R_PWA1, R_PB, R_PY, R_PYA0, R_PYA1, R_PX0, R_PX1,  // polish
+  R_MV,
+  R_NF
+};
+__host__ __device__ inline int qp_row_stride(int CN) { return 2 * CN + R_NF; }
+
 struct QpCtx {
-  // geometry
-  int N, HB, T, D, CN, RS, lane;
-  // shared memory
-  double *Kb, *Dz, *Eb, *qs, *lbs, *ubs, *x, *zb, *yb, *v1, *v2, *invd;
-  int* ls;  // list starts: T dense slots then D sparse slots, +1
-  // global memory
-  double* rows;
+  int N, Np, nb, M, Wd, T, D, CN, RS, lane, nrows;
+  double *Kb, *Linv, *Dz, *beta, *x, *zb, *yb, *v1, *v2;   // shared
+  double* rows;          // global
   int* rints;
-  const int* list;
-  const double* Pband;
+  const int* colptr;     // [Np+1]
+  const int* colent;     // entries: (row << 5) | k
+  const double* Pband;   // [N][2D+1]
+  const double *qs, *lbs, *ubs;  // global [Np] scaled cost / bounds of the trajectory variables
   double* scratch;
-  // scalars
-  int nrows;
   double c, cinv, rho, rho_eq, sigma, alpha;
-
   __device__ __forceinline__ double* R(int r) const { return rows + static_cast<size_t>(r) * RS; }
+  __device__ __forceinline__ double* F(int r) const { return rows + static_cast<size_t>(r) * RS + 2 * CN; }
   __device__ __forceinline__ const int* I(int r) const { return rints + static_cast<size_t>(r) * RI_NINTS; }
-
-  template <class F>
-  __device__ __forceinline__ void for_rows(F f) const {
-    for (int slot = lane; slot < T; slot += 32)
-      for (int k = ls[slot]; k < ls[slot + 1]; ++k) f(list[k]);
-    __syncwarp();
-    for (int slot = lane; slot < D; slot += 32)
-      for (int k = ls[T + slot]; k < ls[T + slot + 1]; ++k) f(list[k]);
-    __syncwarp();
-  }
 };
 
-// scaled view of one row
-struct RowV {
-  int base, cnt, stride, naux;
-  double E, u0, u1, b0, b1, lo, up, qa0, qa1, rho;
+// weights of the linear system: ADMM (rho vector, sigma) or polish (1/delta on the active set, delta)
+struct SysW {
+  bool polish;
+  double sig, rho_aux;
 };
-__device__ __forceinline__ void row_view(const QpCtx& q, const double* R, const int* I, RowV& v) {
-  v.base = I[RI_BASE];
-  v.cnt = I[RI_CNT];
-  v.stride = I[RI_STRIDE];
-  const int aux = I[RI_AUX];
-  const double* F = R + q.CN;
-  v.E = F[F_E];
-  v.u0 = v.u1 = v.b0 = v.b1 = v.qa0 = v.qa1 = 0.0;
-  v.naux = aux;  // AUX_NONE 0, HINGE 1, ABS 2 == number of aux variables
-  v.up = -F[F_C] * v.E;
-  if (aux == AUX_HINGE) {
-    v.u0 = -v.E * F[F_DA0];
-    v.b0 = F[F_EA0] * F[F_DA0];
-    v.qa0 = q.c * F[F_DA0] * F[F_W];
-    v.lo = -kOsqpInf * v.E;
-    v.rho = q.rho;
-  } else {
-    if (aux == AUX_ABS) {
-      v.u0 = v.E * F[F_DA0];
-      v.u1 = -v.E * F[F_DA1];
-      v.b0 = F[F_EA0] * F[F_DA0];
-      v.b1 = F[F_EA1] * F[F_DA1];
-      v.qa0 = q.c * F[F_DA0] * F[F_W];
-      v.qa1 = q.c * F[F_DA1] * F[F_W];
-    }
-    v.lo = v.up;
-    v.rho = q.rho_eq;
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------
-// banded Cholesky (in place in Kb, lower band: Kb[i*(HB+1)+k] = K(i, i-k)) and the two triangular solves
+// Band Cholesky in place (lower band, Kb[i*Wd + k] = K(i, i-k), Wd = nb+2 keeps the column walks conflict
+// free) followed by the inversion of the nb x nb diagonal blocks of the factor.
 __device__ inline bool band_factor(const QpCtx& q) {
-  const int N = q.N, HB = q.HB, W = HB + 1, lane = q.lane;
+  const int Np = q.Np, HB = q.nb, W = q.Wd, lane = q.lane;
   bool ok = true;
-  for (int j = 0; j < N; ++j) {
+  for (int j = 0; j < Np; ++j) {
     const double djj = q.Kb[j * W];
     if (!(djj > 0.0)) ok = false;
     const double d = sqrt(djj > 0.0 ? djj : 1.0);
     const double inv = 1.0 / d;
     __syncwarp();
-    for (int k = 1 + lane; k <= HB && j + k < N; k += 32) q.Kb[(j + k) * W + k] *= inv;
-    if (lane == 0) {
-      q.Kb[j * W] = d;
-      q.invd[j] = inv;
-    }
+    const int m = min(HB, Np - 1 - j);
+    if (lane == 0) q.Kb[j * W] = d;
+    if (lane >= 1 && lane <= m) q.Kb[(j + lane) * W + lane] *= inv;
     __syncwarp();
-    // trailing update: K(j+a, j+b) -= L(j+a,j) L(j+b,j), 1 <= b <= a <= HB
-    const int m = min(HB, N - 1 - j);
+    // trailing update: K(j+a, j+b) -= L(j+a,j) L(j+b,j), 1 <= b <= a <= m
     const int npairs = m * (m + 1) / 2;
     for (int pidx = lane; pidx < npairs; pidx += 32) {
-      // invert pidx -> (a,b): a*(a-1)/2 + (b-1) with 1<=b<=a
       int a = static_cast<int>((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5) + 1;
       while (a * (a - 1) / 2 > pidx) --a;
       while ((a + 1) * a / 2 <= pidx) ++a;
@@ -163,125 +141,156 @@ __device__ inline bool band_factor(const QpCtx& q) {
     }
     __syncwarp();
   }
+  // Linv_i = inv(L_ii), packed lower triangle, one (block, column) task per lane
+  const int nb = q.nb, tri = nb * (nb + 1) / 2;
+  for (int task = lane; task < q.M * nb; task += 32) {
+    const int blk = task / nb, c = task % nb;
+    double* Li = q.Linv + blk * tri;
+    const double* Lb = q.Kb + static_cast<size_t>(blk) * nb * W;  // row r of the block: Lb[r*W + (r - col)]
+    for (int r = c; r < nb; ++r) {  // solve L z = e_c by forward substitution; z_r for r >= c
+      double s = (r == c) ? 1.0 : 0.0;
+      for (int k = c; k < r; ++k) s -= Lb[r * W + (r - k)] * Li[k * (k + 1) / 2 + c];
+      Li[r * (r + 1) / 2 + c] = s / Lb[r * W];
+    }
+  }
+  __syncwarp();
   return ok;
 }
-// solves K v = v in place (v in shared memory)
-__device__ inline void band_solve(const QpCtx& q, double* v) {
-  const int N = q.N, HB = q.HB, W = HB + 1, lane = q.lane;
+
+// Solves K v = v in place (v in shared memory, length Np) with the block factor.
+__device__ inline void block_solve(const QpCtx& q, double* v) {
+  const int nb = q.nb, W = q.Wd, M = q.M, tri = nb * (nb + 1) / 2;
+  const int halves = (nb <= 16) ? 2 : 1;
+  const int r = (halves == 2) ? (q.lane & 15) : q.lane;      // block row handled by this lane
+  const int h = (halves == 2) ? (q.lane >> 4) : 0;           // which half of the columns
+  const int chunk = (nb + halves - 1) / halves;
+  const int c0 = h * chunk, c1 = min(nb, c0 + chunk);
+  const bool rowok = r < nb;
+  const int rr = rowok ? r : 0;
   __syncwarp();
-  for (int j = 0; j < N; ++j) {  // forward, column oriented
-    const double yj = v[j] * q.invd[j];
-    __syncwarp();
-    if (lane == 0) v[j] = yj;
-    for (int k = 1 + lane; k <= HB && j + k < N; k += 32) v[j + k] -= q.Kb[(j + k) * W + k] * yj;
-    __syncwarp();
+  // ---- forward: y_i = Linv_i (b_i - W_i y_{i-1}),  W_i[r][c] = Kb[(i nb + r) W + nb + r - c], c >= r
+  double yprev = 0.0;
+  for (int i = 0; i < M; ++i) {
+    double t = rowok ? v[i * nb + rr] : 0.0;
+    if (i > 0) {
+      double acc = 0.0;
+      const double* Wrow = q.Kb + static_cast<size_t>(i * nb + rr) * W + nb + rr;
+      for (int c = c0; c < c1; ++c) {
+        const double yv = __shfl_sync(0xffffffffu, yprev, c);
+        if (rowok && c >= rr) acc += Wrow[-c] * yv;
+      }
+      if (halves == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+      t -= acc;
+    }
+    double acc = 0.0;
+    const double* Lrow = q.Linv + i * tri + rr * (rr + 1) / 2;
+    for (int c = c0; c < c1; ++c) {
+      const double tv = __shfl_sync(0xffffffffu, t, c);
+      if (rowok && c <= rr) acc += Lrow[c] * tv;
+    }
+    if (halves == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    yprev = acc;
+    if (rowok && h == 0) v[i * nb + rr] = acc;
   }
-  for (int j = N - 1; j >= 0; --j) {  // backward: x_j = (y_j - sum_k L(j+k,j) x_{j+k}) / L_jj
-    double s = 0.0;
-    for (int k = 1 + lane; k <= HB && j + k < N; k += 32) s += q.Kb[(j + k) * W + k] * v[j + k];
-    s = warp_sum(s);
-    __syncwarp();
-    if (lane == 0) v[j] = (v[j] - s) * q.invd[j];
-    __syncwarp();
+  // ---- backward: x_i = Linv_i' (y_i - W_{i+1}' x_{i+1})
+  double xnext = 0.0;
+  for (int i = M - 1; i >= 0; --i) {
+    double t = rowok ? ((i == M - 1) ? yprev : v[i * nb + rr]) : 0.0;
+    if (i < M - 1) {
+      double acc = 0.0;
+      for (int c = c0; c < c1; ++c) {
+        const double xv = __shfl_sync(0xffffffffu, xnext, c);
+        // W_{i+1}[c][r] = Kb[((i+1) nb + c) W + nb + c - r], nonzero iff r >= c
+        if (rowok && c <= rr) acc += q.Kb[static_cast<size_t>((i + 1) * nb + c) * W + nb + c - rr] * xv;
+      }
+      if (halves == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+      t -= acc;
+    }
+    double acc = 0.0;
+    for (int c = c0; c < c1; ++c) {
+      const double tv = __shfl_sync(0xffffffffu, t, c);
+      if (rowok && c >= rr) acc += q.Linv[i * tri + c * (c + 1) / 2 + rr] * tv;
+    }
+    if (halves == 2) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    xnext = acc;
+    if (rowok && h == 0) v[i * nb + rr] = acc;
   }
+  __syncwarp();
 }
 
 // scaled P (band) times a shared vector: out = c * Dz .* (P (Dz .* in))
 __device__ inline void p_matvec(const QpCtx& q, const double* in, double* out) {
-  const int N = q.N, HB = q.HB, W = HB + 1;
-  for (int i = q.lane; i < N; i += 32) {
+  const int N = q.N, HB = 2 * q.D, W = HB + 1;
+  for (int i = q.lane; i < q.Np; i += 32) {
     double s = 0.0;
-    for (int k = 0; k <= HB && k <= i; ++k) s += q.Pband[i * W + k] * q.Dz[i - k] * in[i - k];
-    for (int k = 1; k <= HB && i + k < N; ++k) s += q.Pband[(i + k) * W + k] * q.Dz[i + k] * in[i + k];
-    out[i] = q.c * q.Dz[i] * s;
+    if (i < N) {
+      for (int k = 0; k <= HB && k <= i; ++k) s += q.Pband[i * W + k] * q.Dz[i - k] * in[i - k];
+      for (int k = 1; k <= HB && i + k < N; ++k) s += q.Pband[(i + k) * W + k] * q.Dz[i + k] * in[i + k];
+      s *= q.c * q.Dz[i];
+    }
+    out[i] = s;
   }
   __syncwarp();
 }
 
-// weights of the linear system: ADMM (rho vector, sigma) or polish (1/delta on the active set, delta)
-struct SysW {
-  bool polish;
-  double sig, rho_aux;  // ADMM: rho on the aux bound rows
-};
-// Weights of one row in the current linear system.  With the aux block K_aa = diag(g) + Wr u u' the
-// closed forms below are written cancellation free (den = det(K_aa) / 1, expanded analytically): the polish
-// system has Wr = 1/delta and g = delta, where the textbook Sherman-Morrison form loses ~12 digits.
-__device__ __forceinline__ void row_weights(const QpCtx& q, const SysW& w, const double* F, const RowV& v, double& Wr,
-                                            double& g0, double& g1, double& den) {
-  double wa0, wa1;
-  if (w.polish) {
-    Wr = fabs(F[F_PW]);
-    wa0 = fabs(F[F_PWA0]);
-    wa1 = fabs(F[F_PWA1]);
-  } else {
-    Wr = v.rho;
-    wa0 = wa1 = w.rho_aux;
+// per-row weights of the current linear system -> R_WRR (raw row weight), R_G0/G1, R_DEN, R_WR (Schur weight).
+// With the aux block K_aa = diag(g) + Wr u u' everything is written cancellation free (den = det K_aa
+// expanded analytically); the polish system has Wr = 1/delta and g = delta.
+__device__ inline void rows_prepare_weights(const QpCtx& q, const SysW& w) {
+  for (int r = q.lane; r < q.nrows; r += 32) {
+    double* F = q.F(r);
+    const int naux = q.I(r)[RI_AUX];
+    double Wr, wa0, wa1;
+    if (w.polish) {
+      Wr = fabs(F[R_PW]);
+      wa0 = fabs(F[R_PWA0]);
+      wa1 = fabs(F[R_PWA1]);
+    } else {
+      Wr = (F[R_RHO] != 0.0) ? q.rho_eq : q.rho;
+      wa0 = wa1 = w.rho_aux;
+    }
+    const double g0 = (naux >= 1) ? w.sig + wa0 * F[R_B0] * F[R_B0] : 1.0;
+    const double g1 = (naux == 2) ? w.sig + wa1 * F[R_B1] * F[R_B1] : 1.0;
+    const double den = g0 * g1 + Wr * (F[R_U0] * F[R_U0] * g1 + F[R_U1] * F[R_U1] * g0);
+    F[R_WRR] = Wr;
+    F[R_G0] = g0;
+    F[R_G1] = g1;
+    F[R_DEN] = den;
+    F[R_WR] = Wr * g0 * g1 / den;
   }
-  g0 = (v.naux >= 1) ? w.sig + wa0 * v.b0 * v.b0 : 1.0;
-  g1 = (v.naux == 2) ? w.sig + wa1 * v.b1 * v.b1 : 1.0;
-  den = g0 * g1 + Wr * (v.u0 * v.u0 * g1 + v.u1 * v.u1 * g0);
+  __syncwarp();
 }
 __device__ __forceinline__ double xbound_weight(const QpCtx& q, const SysW& w, int j) {
   if (w.polish) return fabs(q.zb[j]);  // zb holds the signed polish weights during polish
   return (q.ubs[j] - q.lbs[j] < kRhoTol) ? q.rho_eq : q.rho;
 }
 
-// K = P + sig I + A' W A with the aux variables eliminated; then factor.
+// K = P + sig I + A' W A with the aux variables eliminated (one lane per matrix row); then factor.
 __device__ inline bool assemble_factor(const QpCtx& q, const SysW& w) {
-  const int N = q.N, HB = q.HB, Wd = HB + 1;
-  for (int i = q.lane; i < N; i += 32) {
-    for (int k = 0; k <= HB; ++k) q.Kb[i * Wd + k] = (k <= i) ? q.c * q.Dz[i] * q.Pband[i * Wd + k] * q.Dz[i - k] : 0.0;
-    const double beta = q.Eb[i] * q.Dz[i];
-    q.Kb[i * Wd] += w.sig + xbound_weight(q, w, i) * beta * beta;
+  rows_prepare_weights(q, w);
+  const int N = q.N, HB = 2 * q.D, PW = HB + 1, Wd = q.Wd;
+  for (int i = q.lane; i < q.Np; i += 32) {
+    double* Ki = q.Kb + static_cast<size_t>(i) * Wd;
+    for (int k = 0; k < Wd; ++k) Ki[k] = 0.0;
+    if (i >= N) {
+      Ki[0] = 1.0;  // padding variable
+      continue;
+    }
+    for (int k = 0; k <= HB && k <= i; ++k) Ki[k] = q.c * q.Dz[i] * q.Pband[i * PW + k] * q.Dz[i - k];
+    Ki[0] += w.sig + xbound_weight(q, w, i) * q.beta[i] * q.beta[i];
+    for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
+      const int ent = q.colent[e], r = ent >> 5, k = ent & 31;
+      const double* R = q.R(r);
+      const double wr = R[2 * q.CN + R_WR];
+      if (wr == 0.0) continue;
+      const int stride = q.I(r)[RI_STRIDE];
+      const double* as = R + q.CN;
+      const double ai = wr * as[k];
+      for (int k2 = 0; k2 <= k; ++k2) Ki[(k - k2) * stride] += ai * as[k2];
+    }
   }
   __syncwarp();
-  q.for_rows([&](int r) {
-    const double* R = q.R(r);
-    const double* F = R + q.CN;
-    RowV v;
-    row_view(q, R, q.I(r), v);
-    double Wr, g0, g1, den;
-    row_weights(q, w, F, v, Wr, g0, g1, den);
-    if (Wr == 0.0) return;
-    const double wr = Wr * g0 * g1 / den;  // Schur complement weight of the row on the trajectory block
-    for (int i = 0; i < v.cnt; ++i) {
-      const int vi = v.base + i * v.stride;
-      const double ai = v.E * R[i] * q.Dz[vi];
-      if (ai == 0.0) continue;
-      for (int j = 0; j <= i; ++j) {
-        const int vj = v.base + j * v.stride;
-        q.Kb[vi * Wd + (vi - vj)] += wr * ai * (v.E * R[j] * q.Dz[vj]);
-      }
-    }
-  });
   return band_factor(q);
-}
-
-// Reduce step of the aux elimination: rows hold their aux right-hand sides in F_RA*; adds the Schur
-// correction to the trajectory right-hand side in v1.
-__device__ __forceinline__ void row_reduce_rhs(const QpCtx& q, const double* R, const double* F, const RowV& v, double Wr,
-                                               double g0, double g1, double den, double zcoef) {
-  // zcoef: multiplier of the row on the trajectory part supplied by the caller (s_r for ADMM, -e_r for polish)
-  const double ra0 = (v.naux >= 1) ? F[F_RA0] : 0.0, ra1 = (v.naux == 2) ? F[F_RA1] : 0.0;
-  const double coef = zcoef - Wr * (v.u0 * ra0 * g1 + v.u1 * ra1 * g0) / den;
-  for (int i = 0; i < v.cnt; ++i) {
-    const int vi = v.base + i * v.stride;
-    q.v1[vi] += v.E * R[i] * q.Dz[vi] * coef;
-  }
-}
-// Back substitution of the aux variables after the banded solve (solution in v1).
-__device__ __forceinline__ void row_backsub(const QpCtx& q, const double* R, const double* F, const RowV& v, double Wr,
-                                            double g0, double g1, double den, double& zeta, double& a0, double& a1) {
-  zeta = 0.0;
-  for (int i = 0; i < v.cnt; ++i) {
-    const int vi = v.base + i * v.stride;
-    zeta += v.E * R[i] * q.Dz[vi] * q.v1[vi];
-  }
-  a0 = a1 = 0.0;
-  if (v.naux == 0) return;
-  const double ra0 = F[F_RA0], ra1 = (v.naux == 2) ? F[F_RA1] : 0.0;
-  a0 = (g1 * (ra0 - Wr * v.u0 * zeta) + Wr * v.u1 * (v.u1 * ra0 - v.u0 * ra1)) / den;
-  if (v.naux == 2) a1 = (g0 * (ra1 - Wr * v.u1 * zeta) + Wr * v.u0 * (v.u0 * ra1 - v.u1 * ra0)) / den;
 }
 
 struct QpOut {
@@ -291,208 +300,276 @@ struct QpOut {
   int pol_factor_ok, rho_updates, rounds;
 };
 
-// The whole QP solve for the calling warp's trajectory.  `warm`: rows/ws_* hold the previous solution.
-__device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm, double warm_rho, double* ws_x,
-                                      double* ws_yb, int n_aux_total) {
-  const int N = q.N, lane = q.lane;
-  QpOut out{QPS_UNSOLVED, 0, 0, st.rho, 0, 0, 0, 0, 0, -1, 0, 0};
-  // ------------------------------------------------------------------ Ruiz equilibration (scale_data) [EXT]
-  q.c = 1.0;
-  for (int i = lane; i < N; i += 32) {
-    q.Dz[i] = 1.0;
-    q.Eb[i] = 1.0;
-  }
-  q.for_rows([&](int r) {
-    double* F = q.R(r) + q.CN;
-    F[F_E] = 1.0;
-    F[F_DA0] = F[F_DA1] = F[F_EA0] = F[F_EA1] = 1.0;
-  });
-  const int W = q.HB + 1;
-  for (int pass = 0; pass < st.scaling; ++pass) {
-    // column norms of [P A'; A 0] restricted to the trajectory variables -> v2
-    for (int i = lane; i < N; i += 32) {
-      double m = 0.0;
-      for (int k = 0; k <= q.HB && k <= i; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[i * W + k] * q.Dz[i - k]));
-      for (int k = 1; k <= q.HB && i + k < N; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[(i + k) * W + k] * q.Dz[i + k]));
-      m = fmax(m, fabs(q.Eb[i] * q.Dz[i]));
-      q.v2[i] = m;
+// Persistent solver state of one QP between time slices.
+struct QpResume {
+  int iter, round, rho_updates, status;
+  double rho, eps_scale, c;
+};
+
+// Scatter pass: v1[i] = base(i) + sum over the column entries of as[k] * R_COEF(row).
+template <class Base>
+__device__ __forceinline__ void scatter_columns(const QpCtx& q, Base base) {
+  for (int i = q.lane; i < q.Np; i += 32) {
+    double s = 0.0;
+    if (i < q.N) {
+      s = base(i);
+      for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
+        const int ent = q.colent[e], r = ent >> 5, k = ent & 31;
+        const double* R = q.R(r);
+        s += R[q.CN + k] * R[2 * q.CN + R_COEF];
+      }
     }
-    __syncwarp();
-    // rows: contribute to column norms, compute own row / aux norms, update own E / aux scalings
-    q.for_rows([&](int r) {
+    q.v1[i] = s;
+  }
+  __syncwarp();
+}
+// zeta_r = as . v(vars of the row)
+__device__ __forceinline__ double row_dot(const QpCtx& q, const double* R, const int* I, const double* v) {
+  double z = 0.0;
+  const int base = I[RI_BASE], stride = I[RI_STRIDE], cnt = I[RI_CNT];
+  for (int k = 0; k < cnt; ++k) z += R[q.CN + k] * v[base + k * stride];
+  return z;
+}
+// aux back-substitution (cancellation free)
+__device__ __forceinline__ void row_backsub(const double* F, int naux, double zeta, double& a0, double& a1) {
+  a0 = a1 = 0.0;
+  if (naux == 0) return;
+  const double Wr = F[R_WRR], ra0 = F[R_RA0], ra1 = (naux == 2) ? F[R_RA1] : 0.0;
+  const double u0 = F[R_U0], u1 = F[R_U1];
+  a0 = (F[R_G1] * (ra0 - Wr * u0 * zeta) + Wr * u1 * (u1 * ra0 - u0 * ra1)) / F[R_DEN];
+  if (naux == 2) a1 = (F[R_G0] * (ra1 - Wr * u1 * zeta) + Wr * u0 * (u0 * ra1 - u1 * ra0)) / F[R_DEN];
+}
+__device__ __forceinline__ double row_reduce_coef(const double* F, int naux, double zcoef) {
+  const double ra0 = (naux >= 1) ? F[R_RA0] : 0.0, ra1 = (naux == 2) ? F[R_RA1] : 0.0;
+  return zcoef - F[R_WRR] * (F[R_U0] * ra0 * F[R_G1] + F[R_U1] * ra1 * F[R_G0]) / F[R_DEN];
+}
+
+// Ruiz equilibration (scale_data of OSQP [EXT]); leaves the scaled view of every row in its record and the
+// scaled trajectory cost / bounds in qs / lbs / ubs (global), Dz / beta in shared memory.
+__device__ inline void qp_scale(QpCtx& q, const QpSettings& st, double* qs, double* lbs, double* ubs, int n_aux_total) {
+  const int N = q.N, lane = q.lane, HB = 2 * q.D, W = HB + 1;
+  double* Eb = q.v2;  // bound-row scalings live in v2 during scaling
+  q.c = 1.0;
+  for (int i = lane; i < q.Np; i += 32) {
+    q.Dz[i] = 1.0;
+    Eb[i] = 1.0;
+  }
+  for (int r = lane; r < q.nrows; r += 32) {
+    double* F = q.F(r);
+    F[R_E] = F[R_DA0] = F[R_DA1] = F[R_EA0] = F[R_EA1] = 1.0;
+  }
+  __syncwarp();
+  for (int pass = 0; pass < st.scaling; ++pass) {
+    // row norms (one lane per row) -> E_temp in R_RA0; aux column / bound-row scalings updated in place
+    for (int r = lane; r < q.nrows; r += 32) {
       double* R = q.R(r);
-      double* F = R + q.CN;
+      double* F = q.F(r);
       const int* I = q.I(r);
       const int base = I[RI_BASE], cnt = I[RI_CNT], stride = I[RI_STRIDE], aux = I[RI_AUX];
-      const double E = F[F_E];
+      const double E = F[R_E];
       double rn = 0.0;
-      for (int i = 0; i < cnt; ++i) {
-        const int vi = base + i * stride;
-        const double a = fabs(E * R[i] * q.Dz[vi]);
-        rn = fmax(rn, a);
-        q.v2[vi] = fmax(q.v2[vi], a);
-      }
+      for (int k = 0; k < cnt; ++k) rn = fmax(rn, fabs(E * R[k] * q.Dz[base + k * stride]));
       double dt0 = 1.0, dt1 = 1.0, et0 = 1.0, et1 = 1.0;
       if (aux >= 1) {
-        const double ua = fabs(E * F[F_DA0]), ba = fabs(F[F_EA0] * F[F_DA0]);
+        const double ua = fabs(E * F[R_DA0]), ba = fabs(F[R_EA0] * F[R_DA0]);
         rn = fmax(rn, ua);
         dt0 = 1.0 / sqrt(limit_scaling(fmax(ua, ba)));
         et0 = 1.0 / sqrt(limit_scaling(ba));
       }
       if (aux == 2) {
-        const double ua = fabs(E * F[F_DA1]), ba = fabs(F[F_EA1] * F[F_DA1]);
+        const double ua = fabs(E * F[R_DA1]), ba = fabs(F[R_EA1] * F[R_DA1]);
         rn = fmax(rn, ua);
         dt1 = 1.0 / sqrt(limit_scaling(fmax(ua, ba)));
         et1 = 1.0 / sqrt(limit_scaling(ba));
       }
-      F[F_RA0] = 1.0 / sqrt(limit_scaling(rn));  // E_temp, applied below once the column pass is complete
-      F[F_DA0] *= dt0;
-      F[F_DA1] *= dt1;
-      F[F_EA0] *= et0;
-      F[F_EA1] *= et1;
-    });
-    q.for_rows([&](int r) {
-      double* F = q.R(r) + q.CN;
-      F[F_E] *= F[F_RA0];
-    });
+      F[R_RA0] = 1.0 / sqrt(limit_scaling(rn));
+      F[R_RA1] = E;  // E before this pass (the column pass below must still see the old value)
+      F[R_DA0] *= dt0;
+      F[R_DA1] *= dt1;
+      F[R_EA0] *= et0;
+      F[R_EA1] *= et1;
+    }
+    __syncwarp();
+    // column norms of [P A'; A 0] restricted to the trajectory variables (one lane per variable)
     for (int i = lane; i < N; i += 32) {
-      const double bn = fabs(q.Eb[i] * q.Dz[i]);
-      const double dt = 1.0 / sqrt(limit_scaling(q.v2[i]));
-      q.Dz[i] *= dt;
-      q.Eb[i] *= 1.0 / sqrt(limit_scaling(bn));
+      double m = 0.0;
+      for (int k = 0; k <= HB && k <= i; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[i * W + k] * q.Dz[i - k]));
+      for (int k = 1; k <= HB && i + k < N; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[(i + k) * W + k] * q.Dz[i + k]));
+      const double bn = fabs(Eb[i] * q.Dz[i]);
+      m = fmax(m, bn);
+      for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
+        const int ent = q.colent[e], r = ent >> 5, k = ent & 31;
+        const double* R = q.R(r);
+        m = fmax(m, fabs(R[2 * q.CN + R_RA1] * R[k] * q.Dz[i]));
+      }
+      q.v1[i] = 1.0 / sqrt(limit_scaling(m));
+      Eb[i] *= 1.0 / sqrt(limit_scaling(bn));
+    }
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) q.Dz[i] *= q.v1[i];
+    for (int r = lane; r < q.nrows; r += 32) {
+      double* F = q.F(r);
+      F[R_E] = F[R_RA1] * F[R_RA0];
     }
     __syncwarp();
     // cost normalisation: mean column inf-norm of the scaled P over ALL n variables (aux columns are 0)
     double csum = 0.0, qn = 0.0;
     for (int i = lane; i < N; i += 32) {
       double m = 0.0;
-      for (int k = 0; k <= q.HB && k <= i; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[i * W + k] * q.Dz[i - k]));
-      for (int k = 1; k <= q.HB && i + k < N; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[(i + k) * W + k] * q.Dz[i + k]));
+      for (int k = 0; k <= HB && k <= i; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[i * W + k] * q.Dz[i - k]));
+      for (int k = 1; k <= HB && i + k < N; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[(i + k) * W + k] * q.Dz[i + k]));
       csum += m;
-      qn = fmax(qn, fabs(q.c * q.Dz[i] * q.qs[i]));
+      qn = fmax(qn, fabs(q.c * q.Dz[i] * qs[i]));
     }
-    double qa = 0.0;
-    q.for_rows([&](int r) {
-      const double* F = q.R(r) + q.CN;
+    for (int r = lane; r < q.nrows; r += 32) {
+      const double* F = q.F(r);
       const int aux = q.I(r)[RI_AUX];
-      if (aux >= 1) qa = fmax(qa, fabs(q.c * F[F_DA0] * F[F_W]));
-      if (aux == 2) qa = fmax(qa, fabs(q.c * F[F_DA1] * F[F_W]));
-    });
+      if (aux >= 1) qn = fmax(qn, fabs(q.c * F[R_DA0] * F[R_W]));
+      if (aux == 2) qn = fmax(qn, fabs(q.c * F[R_DA1] * F[R_W]));
+    }
     csum = warp_sum(csum);
-    qn = warp_max(fmax(qn, qa));
+    qn = warp_max(qn);
     const double mean = limit_scaling(csum / static_cast<double>(N + n_aux_total));
-    const double ct = 1.0 / fmax(mean, limit_scaling(qn));
-    q.c *= ct;
+    q.c *= 1.0 / fmax(mean, limit_scaling(qn));
   }
   q.cinv = 1.0 / q.c;
-  // scaled cost vector and bounds (qs / lbs / ubs enter unscaled)
-  for (int i = lane; i < N; i += 32) {
-    q.qs[i] = q.c * q.Dz[i] * q.qs[i];
-    q.lbs[i] *= q.Eb[i];
-    q.ubs[i] *= q.Eb[i];
+  for (int i = lane; i < q.Np; i += 32) {
+    if (i < N) {
+      qs[i] = q.c * q.Dz[i] * qs[i];
+      lbs[i] *= Eb[i];
+      ubs[i] *= Eb[i];
+      q.beta[i] = Eb[i] * q.Dz[i];
+    } else {
+      qs[i] = 0.0; lbs[i] = -1.0; ubs[i] = 1.0; q.beta[i] = 1.0; q.Dz[i] = 1.0;
+    }
+  }
+  // scaled view of every row
+  for (int r = lane; r < q.nrows; r += 32) {
+    double* R = q.R(r);
+    double* F = q.F(r);
+    const int* I = q.I(r);
+    const int base = I[RI_BASE], cnt = I[RI_CNT], stride = I[RI_STRIDE], aux = I[RI_AUX];
+    const double E = F[R_E];
+    for (int k = 0; k < cnt; ++k) R[q.CN + k] = E * R[k] * q.Dz[base + k * stride];
+    F[R_U0] = F[R_U1] = F[R_B0] = F[R_B1] = F[R_QA0] = F[R_QA1] = 0.0;
+    F[R_UP] = -F[R_C] * E;
+    if (aux == AUX_HINGE) {
+      F[R_U0] = -E * F[R_DA0];
+      F[R_B0] = F[R_EA0] * F[R_DA0];
+      F[R_QA0] = q.c * F[R_DA0] * F[R_W];
+      F[R_LO] = -kOsqpInf * E;
+      F[R_RHO] = 0.0;
+    } else {
+      if (aux == AUX_ABS) {
+        F[R_U0] = E * F[R_DA0];
+        F[R_U1] = -E * F[R_DA1];
+        F[R_B0] = F[R_EA0] * F[R_DA0];
+        F[R_B1] = F[R_EA1] * F[R_DA1];
+        F[R_QA0] = q.c * F[R_DA0] * F[R_W];
+        F[R_QA1] = q.c * F[R_DA1] * F[R_W];
+      }
+      F[R_LO] = F[R_UP];
+      F[R_RHO] = 1.0;
+    }
   }
   __syncwarp();
+}
 
-  // ------------------------------------------------------------------ initial iterate
-  double rho = warm ? warm_rho : st.rho;
-  rho = fmin(fmax(rho, kRhoMin), kRhoMax);
-  q.rho = rho;
-  q.rho_eq = kRhoEqOverIneq * rho;
+// The QP solve for the calling warp's trajectory.  `fresh`: start a new solve (initial iterate from the warm
+// start or zero); otherwise resume from `rs`.  Returns status QPS_YIELD when the slice budget ran out.
+__device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool fresh, bool warm, double warm_rho,
+                                      const double* ws_x, const double* ws_yb, QpResume& rs, int slice) {
+  const int N = q.N, lane = q.lane;
+  QpOut out{QPS_UNSOLVED, 0, 0, st.rho, 0, 0, 0, 0, 0, -1, 0, 0};
+  double rho;
+  double eps_scale;
+  int iter, round;
   q.sigma = st.sigma;
   q.alpha = st.alpha;
-  if (warm) {  // osqp_warm_start: x <- Dinv x, y <- c Einv y, z <- A x
-    for (int i = lane; i < N; i += 32) {
-      q.x[i] = ws_x[i] / q.Dz[i];
-      q.yb[i] = ws_yb[i] / q.Eb[i] * q.c;
-      q.zb[i] = q.Eb[i] * q.Dz[i] * q.x[i];
+  if (fresh) {
+    rho = warm ? warm_rho : st.rho;
+    rho = fmin(fmax(rho, kRhoMin), kRhoMax);
+    eps_scale = 1.0;
+    iter = 0;
+    round = 0;
+    q.rho = rho;
+    q.rho_eq = kRhoEqOverIneq * rho;
+    if (warm) {  // osqp_warm_start: x <- Dinv x, y <- c Einv y, z <- A x
+      for (int i = lane; i < q.Np; i += 32) {
+        if (i < N) {
+          q.x[i] = ws_x[i] / q.Dz[i];
+          q.yb[i] = ws_yb[i] * q.Dz[i] / q.beta[i] * q.c;   // Eb = beta / Dz
+          q.zb[i] = q.beta[i] * q.x[i];
+        } else {
+          q.x[i] = q.yb[i] = q.zb[i] = 0.0;
+        }
+      }
+      __syncwarp();
+      for (int r = lane; r < q.nrows; r += 32) {
+        double* R = q.R(r);
+        double* F = q.F(r);
+        const int naux = q.I(r)[RI_AUX];
+        F[R_XA0] = (naux >= 1) ? F[R_XA0] / F[R_DA0] : 0.0;
+        F[R_XA1] = (naux == 2) ? F[R_XA1] / F[R_DA1] : 0.0;
+        F[R_Y] = F[R_Y] / F[R_E] * q.c;
+        F[R_YA0] = (naux >= 1) ? F[R_YA0] / F[R_EA0] * q.c : 0.0;
+        F[R_YA1] = (naux == 2) ? F[R_YA1] / F[R_EA1] * q.c : 0.0;
+        F[R_Z] = row_dot(q, R, q.I(r), q.x) + F[R_U0] * F[R_XA0] + F[R_U1] * F[R_XA1];
+        F[R_ZA0] = F[R_B0] * F[R_XA0];
+        F[R_ZA1] = F[R_B1] * F[R_XA1];
+      }
+    } else {
+      for (int i = lane; i < q.Np; i += 32) q.x[i] = q.zb[i] = q.yb[i] = 0.0;
+      for (int r = lane; r < q.nrows; r += 32) {
+        double* F = q.F(r);
+        F[R_XA0] = F[R_XA1] = F[R_Z] = F[R_Y] = F[R_ZA0] = F[R_ZA1] = F[R_YA0] = F[R_YA1] = 0.0;
+      }
     }
     __syncwarp();
-    q.for_rows([&](int r) {
-      double* R = q.R(r);
-      double* F = R + q.CN;
-      RowV v;
-      row_view(q, R, q.I(r), v);
-      F[F_XA0] = (v.naux >= 1) ? F[F_XA0] / F[F_DA0] : 0.0;
-      F[F_XA1] = (v.naux == 2) ? F[F_XA1] / F[F_DA1] : 0.0;
-      F[F_Y] = F[F_Y] / v.E * q.c;
-      F[F_YA0] = (v.naux >= 1) ? F[F_YA0] / F[F_EA0] * q.c : 0.0;
-      F[F_YA1] = (v.naux == 2) ? F[F_YA1] / F[F_EA1] * q.c : 0.0;
-      double ax = 0.0;
-      for (int i = 0; i < v.cnt; ++i) {
-        const int vi = v.base + i * v.stride;
-        ax += v.E * R[i] * q.Dz[vi] * q.x[vi];
-      }
-      F[F_Z] = ax + v.u0 * F[F_XA0] + v.u1 * F[F_XA1];
-      F[F_ZA0] = v.b0 * F[F_XA0];
-      F[F_ZA1] = v.b1 * F[F_XA1];
-    });
   } else {
-    for (int i = lane; i < N; i += 32) q.x[i] = q.zb[i] = q.yb[i] = 0.0;
-    q.for_rows([&](int r) {
-      double* F = q.R(r) + q.CN;
-      F[F_XA0] = F[F_XA1] = F[F_Z] = F[F_Y] = F[F_ZA0] = F[F_ZA1] = F[F_YA0] = F[F_YA1] = 0.0;
-    });
+    rho = rs.rho;
+    eps_scale = rs.eps_scale;
+    iter = rs.iter;
+    round = rs.round;
+    out.rho_updates = rs.rho_updates;
+    q.rho = rho;
+    q.rho_eq = kRhoEqOverIneq * rho;
   }
-  __syncwarp();
-
   SysW sysw{false, st.sigma, rho};
   if (!assemble_factor(q, sysw)) {
     out.status = QPS_NONCVX;
     return out;
   }
 
-  // ------------------------------------------------------------------ ADMM iterations
-  double* dxs = q.scratch;          // [N] last trajectory step (written on check iterations)
-  double* dyb = q.scratch + N;      // [N] last dual step of the variable-bound rows
-  double* st_x = q.scratch + 2 * N;   // ADMM x, zb, yb stashed while polish reuses the shared vectors
-  double* st_zb = q.scratch + 3 * N;
-  double* st_yb = q.scratch + 4 * N;
+  double* dxs = q.scratch;              // [Np] last trajectory step (written on check iterations)
+  double* dyb = q.scratch + q.Np;       // [Np] last dual step of the variable-bound rows
+  double* st_x = q.scratch + 2 * q.Np;  // ADMM x, zb, yb stashed while polish reuses the shared vectors
+  double* st_zb = q.scratch + 3 * q.Np;
+  double* st_yb = q.scratch + 4 * q.Np;
   double pri_res = 0.0, dua_res = 0.0;
-  int status = QPS_UNSOLVED, iter = 0;
-  // residuals / norms gathered by the info pass
+  int status = QPS_UNSOLVED, budget = slice;
   double n_z = 0, n_ax = 0, n_q = 0, n_aty = 0, n_px = 0, s_pri = 0, s_dua = 0, s_z = 0, s_ax = 0, s_q = 0, s_aty = 0, s_px = 0;
 
   auto info_pass = [&]() {  // update_info(): v1 <- P x, v2 <- A'y (trajectory part), all norms
     p_matvec(q, q.x, q.v1);
-    double m_pri = 0, m_z = 0, m_ax = 0, m_dua_a = 0, m_aty_a = 0, m_q_a = 0;
-    double ms_pri = 0, ms_z = 0, ms_ax = 0, ms_dua_a = 0, ms_aty_a = 0, ms_q_a = 0;
-    for (int i = lane; i < N; i += 32) {
-      const double beta = q.Eb[i] * q.Dz[i];
-      const double ax = beta * q.x[i];
-      q.v2[i] = beta * q.yb[i];
-      const double einv = 1.0 / q.Eb[i];
-      m_pri = fmax(m_pri, fabs(einv * (ax - q.zb[i])));
-      m_z = fmax(m_z, fabs(einv * q.zb[i]));
-      m_ax = fmax(m_ax, fabs(einv * ax));
-      ms_pri = fmax(ms_pri, fabs(ax - q.zb[i]));
-      ms_z = fmax(ms_z, fabs(q.zb[i]));
-      ms_ax = fmax(ms_ax, fabs(ax));
-    }
-    __syncwarp();
-    q.for_rows([&](int r) {
+    double m_pri = 0, m_z = 0, m_ax = 0, m_dua = 0, m_aty = 0, m_q = 0, m_px = 0;
+    double ms_pri = 0, ms_z = 0, ms_ax = 0, ms_dua = 0, ms_aty = 0, ms_q = 0, ms_px = 0;
+    for (int r = lane; r < q.nrows; r += 32) {
       const double* R = q.R(r);
-      const double* F = R + q.CN;
-      RowV v;
-      row_view(q, R, q.I(r), v);
-      double ax = 0.0;
-      for (int i = 0; i < v.cnt; ++i) {
-        const int vi = v.base + i * v.stride;
-        const double a = v.E * R[i] * q.Dz[vi];
-        ax += a * q.x[vi];
-        q.v2[vi] += a * F[F_Y];
-      }
-      ax += v.u0 * F[F_XA0] + v.u1 * F[F_XA1];
-      const double einv = 1.0 / v.E;
-      m_pri = fmax(m_pri, fabs(einv * (ax - F[F_Z])));
-      m_z = fmax(m_z, fabs(einv * F[F_Z]));
+      const double* F = q.F(r);
+      const int naux = q.I(r)[RI_AUX];
+      const double ax = row_dot(q, R, q.I(r), q.x) + F[R_U0] * F[R_XA0] + F[R_U1] * F[R_XA1];
+      const double einv = 1.0 / F[R_E];
+      m_pri = fmax(m_pri, fabs(einv * (ax - F[R_Z])));
+      m_z = fmax(m_z, fabs(einv * F[R_Z]));
       m_ax = fmax(m_ax, fabs(einv * ax));
-      ms_pri = fmax(ms_pri, fabs(ax - F[F_Z]));
-      ms_z = fmax(ms_z, fabs(F[F_Z]));
+      ms_pri = fmax(ms_pri, fabs(ax - F[R_Z]));
+      ms_z = fmax(ms_z, fabs(F[R_Z]));
       ms_ax = fmax(ms_ax, fabs(ax));
-      for (int k = 0; k < v.naux; ++k) {
-        const double u = k ? v.u1 : v.u0, bb = k ? v.b1 : v.b0, qa = k ? v.qa1 : v.qa0;
-        const double xa = F[F_XA0 + k], za = F[F_ZA0 + k], ya = F[F_YA0 + k];
-        const double da = F[F_DA0 + k], ea = F[F_EA0 + k];
+      for (int k = 0; k < naux; ++k) {
+        const double u = F[R_U0 + k], bb = F[R_B0 + k], qa = F[R_QA0 + k];
+        const double xa = F[R_XA0 + k], za = F[R_ZA0 + k], ya = F[R_YA0 + k];
+        const double da = F[R_DA0 + k], ea = F[R_EA0 + k];
         const double axb = bb * xa;
         m_pri = fmax(m_pri, fabs((axb - za) / ea));
         m_z = fmax(m_z, fabs(za / ea));
@@ -500,28 +577,43 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm,
         ms_pri = fmax(ms_pri, fabs(axb - za));
         ms_z = fmax(ms_z, fabs(za));
         ms_ax = fmax(ms_ax, fabs(axb));
-        const double aty = u * F[F_Y] + bb * ya;
-        m_dua_a = fmax(m_dua_a, fabs((qa + aty) / da));
-        m_aty_a = fmax(m_aty_a, fabs(aty / da));
-        m_q_a = fmax(m_q_a, fabs(qa / da));
-        ms_dua_a = fmax(ms_dua_a, fabs(qa + aty));
-        ms_aty_a = fmax(ms_aty_a, fabs(aty));
-        ms_q_a = fmax(ms_q_a, fabs(qa));
+        const double aty = u * F[R_Y] + bb * ya;
+        m_dua = fmax(m_dua, fabs((qa + aty) / da));
+        m_aty = fmax(m_aty, fabs(aty / da));
+        m_q = fmax(m_q, fabs(qa / da));
+        ms_dua = fmax(ms_dua, fabs(qa + aty));
+        ms_aty = fmax(ms_aty, fabs(aty));
+        ms_q = fmax(ms_q, fabs(qa));
       }
-    });
-    double m_dua = m_dua_a, m_aty = m_aty_a, m_q = m_q_a, m_px = 0, ms_dua = ms_dua_a, ms_aty = ms_aty_a, ms_q = ms_q_a, ms_px = 0;
+    }
     for (int i = lane; i < N; i += 32) {
-      const double dinv = 1.0 / q.Dz[i];
-      const double d = q.qs[i] + q.v1[i] + q.v2[i];
+      const double beta = q.beta[i], eb = beta / q.Dz[i];
+      const double ax = beta * q.x[i];
+      double aty = beta * q.yb[i];
+      for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
+        const int ent = q.colent[e], r = ent >> 5, k = ent & 31;
+        const double* R = q.R(r);
+        aty += R[q.CN + k] * R[2 * q.CN + R_Y];
+      }
+      q.v2[i] = aty;
+      const double einv = 1.0 / eb, dinv = 1.0 / q.Dz[i];
+      m_pri = fmax(m_pri, fabs(einv * (ax - q.zb[i])));
+      m_z = fmax(m_z, fabs(einv * q.zb[i]));
+      m_ax = fmax(m_ax, fabs(einv * ax));
+      ms_pri = fmax(ms_pri, fabs(ax - q.zb[i]));
+      ms_z = fmax(ms_z, fabs(q.zb[i]));
+      ms_ax = fmax(ms_ax, fabs(ax));
+      const double qv = q.qs[i], d = qv + q.v1[i] + aty;
       m_dua = fmax(m_dua, fabs(dinv * d));
-      m_aty = fmax(m_aty, fabs(dinv * q.v2[i]));
-      m_q = fmax(m_q, fabs(dinv * q.qs[i]));
+      m_aty = fmax(m_aty, fabs(dinv * aty));
+      m_q = fmax(m_q, fabs(dinv * qv));
       m_px = fmax(m_px, fabs(dinv * q.v1[i]));
       ms_dua = fmax(ms_dua, fabs(d));
-      ms_aty = fmax(ms_aty, fabs(q.v2[i]));
-      ms_q = fmax(ms_q, fabs(q.qs[i]));
+      ms_aty = fmax(ms_aty, fabs(aty));
+      ms_q = fmax(ms_q, fabs(qv));
       ms_px = fmax(ms_px, fabs(q.v1[i]));
     }
+    __syncwarp();
     pri_res = warp_max(m_pri);
     dua_res = warp_max(m_dua) * q.cinv;
     n_z = warp_max(m_z); n_ax = warp_max(m_ax); n_q = warp_max(m_q); n_aty = warp_max(m_aty); n_px = warp_max(m_px);
@@ -530,41 +622,33 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm,
   };
 
   auto primal_infeasible = [&](double eps) -> bool {  // is_primal_infeasible [EXT]
-    // projected dual step, its E-scaled norm and the support function of [l,u]
-    double nd = 0.0, lhs = 0.0;
+    double nd = 0.0, lhs = 0.0, na = 0.0;
+    for (int r = lane; r < q.nrows; r += 32) {
+      double* F = q.F(r);
+      const int naux = q.I(r)[RI_AUX];
+      double d = F[R_DY];
+      if (naux == AUX_HINGE) d = fmax(d, 0.0);  // l = -inf
+      nd = fmax(nd, fabs(F[R_E] * d));
+      lhs += F[R_UP] * fmax(d, 0.0) + F[R_LO] * fmin(d, 0.0);
+      F[R_COEF] = d;  // projected dual step, consumed by the column pass
+      for (int k = 0; k < naux; ++k) {
+        const double da = fmin(F[R_DYA0 + k], 0.0);  // aux bound rows: u = +inf, l = 0
+        nd = fmax(nd, fabs(F[R_EA0 + k] * da));
+        na = fmax(na, fabs((F[R_U0 + k] * d + F[R_B0 + k] * da) / F[R_DA0 + k]));
+      }
+    }
     for (int i = lane; i < N; i += 32) {  // variable-bound rows: both bounds finite
       const double d = dyb[i];
-      nd = fmax(nd, fabs(q.Eb[i] * d));
+      nd = fmax(nd, fabs(q.beta[i] / q.Dz[i] * d));
       lhs += q.ubs[i] * fmax(d, 0.0) + q.lbs[i] * fmin(d, 0.0);
-      q.v1[i] = q.Eb[i] * q.Dz[i] * d;  // A' dy accumulates in v1
     }
     __syncwarp();
-    double na = 0.0;  // inf-norm of Dinv A'dy over the aux columns
-    q.for_rows([&](int r) {
-      const double* R = q.R(r);
-      const double* F = R + q.CN;
-      RowV v;
-      row_view(q, R, q.I(r), v);
-      double d = F[F_DY];
-      if (v.naux == AUX_HINGE) d = fmax(d, 0.0);  // l = -inf
-      nd = fmax(nd, fabs(v.E * d));
-      lhs += v.up * fmax(d, 0.0) + v.lo * fmin(d, 0.0);
-      for (int i = 0; i < v.cnt; ++i) {
-        const int vi = v.base + i * v.stride;
-        q.v1[vi] += v.E * R[i] * q.Dz[vi] * d;
-      }
-      for (int k = 0; k < v.naux; ++k) {
-        const double da = fmin(F[F_DYA0 + k], 0.0);  // aux bound rows: u = +inf
-        nd = fmax(nd, fabs(F[F_EA0 + k] * da));
-        // l = 0: no contribution to lhs
-        const double u = k ? v.u1 : v.u0, bb = k ? v.b1 : v.b0;
-        na = fmax(na, fabs((u * d + bb * da) / F[F_DA0 + k]));
-      }
-    });
     nd = warp_max(nd);
     lhs = warp_sum(lhs);
+    na = warp_max(na);
     if (nd > eps) {
       if (lhs < -eps * nd) {
+        scatter_columns(q, [&](int i) { return q.beta[i] * dyb[i]; });
         double m = na;
         for (int i = lane; i < N; i += 32) m = fmax(m, fabs(q.v1[i] / q.Dz[i]));
         m = warp_max(m);
@@ -575,20 +659,23 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm,
   };
   auto dual_infeasible = [&](double eps) -> bool {  // is_dual_infeasible [EXT]
     double ndx = 0.0, qdx = 0.0;
-    for (int i = lane; i < N; i += 32) {
-      ndx = fmax(ndx, fabs(q.Dz[i] * dxs[i]));
-      qdx += q.qs[i] * dxs[i];
-      q.v2[i] = dxs[i];
-    }
-    q.for_rows([&](int r) {
-      const double* F = q.R(r) + q.CN;
-      RowV v;
-      row_view(q, q.R(r), q.I(r), v);
-      for (int k = 0; k < v.naux; ++k) {
-        ndx = fmax(ndx, fabs(F[F_DA0 + k] * F[F_DXA0 + k]));
-        qdx += (k ? v.qa1 : v.qa0) * F[F_DXA0 + k];
+    for (int i = lane; i < q.Np; i += 32) {
+      const double dxi = (i < N) ? dxs[i] : 0.0;
+      if (i < N) {
+        ndx = fmax(ndx, fabs(q.Dz[i] * dxi));
+        qdx += q.qs[i] * dxi;
       }
-    });
+      q.v2[i] = dxi;
+    }
+    for (int r = lane; r < q.nrows; r += 32) {
+      const double* F = q.F(r);
+      const int naux = q.I(r)[RI_AUX];
+      for (int k = 0; k < naux; ++k) {
+        ndx = fmax(ndx, fabs(F[R_DA0 + k] * F[R_DXA0 + k]));
+        qdx += F[R_QA0 + k] * F[R_DXA0 + k];
+      }
+    }
+    __syncwarp();
     ndx = warp_max(ndx);
     qdx = warp_sum(qdx);
     if (!(ndx > eps)) return false;
@@ -603,28 +690,21 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm,
       const double vv = q.Dz[i] * dxs[i];  // Einv * (Eb Dz dx)
       if (vv > eps * ndx || vv < -eps * ndx) bad = 1;
     }
-    q.for_rows([&](int r) {
+    for (int r = lane; r < q.nrows; r += 32) {
       const double* R = q.R(r);
-      const double* F = R + q.CN;
-      RowV v;
-      row_view(q, R, q.I(r), v);
-      double ax = 0.0;
-      for (int i = 0; i < v.cnt; ++i) {
-        const int vi = v.base + i * v.stride;
-        ax += v.E * R[i] * q.Dz[vi] * q.v2[vi];
+      const double* F = q.F(r);
+      const int naux = q.I(r)[RI_AUX];
+      const double ax = row_dot(q, R, q.I(r), q.v2) + F[R_U0] * F[R_DXA0] + F[R_U1] * F[R_DXA1];
+      const double vv = ax / F[R_E];
+      if (vv > eps * ndx) bad = 1;                            // u finite for every row
+      if (naux != AUX_HINGE && vv < -eps * ndx) bad = 1;      // l finite unless hinge
+      for (int k = 0; k < naux; ++k) {
+        const double va = F[R_B0 + k] * F[R_DXA0 + k] / F[R_EA0 + k];
+        if (va < -eps * ndx) bad = 1;                         // aux rows: l = 0 finite, u infinite
       }
-      ax += v.u0 * F[F_DXA0] + v.u1 * F[F_DXA1];
-      const double vv = ax / v.E;
-      if (vv > eps * ndx) bad = 1;                               // u finite for every row
-      if (v.naux != AUX_HINGE && vv < -eps * ndx) bad = 1;       // l finite unless hinge
-      for (int k = 0; k < v.naux; ++k) {
-        const double va = (k ? v.b1 : v.b0) * F[F_DXA0 + k] / F[F_EA0 + k];
-        if (va < -eps * ndx) bad = 1;                            // aux rows: l = 0 finite, u infinite
-      }
-    });
+    }
     return warp_sum_int(bad) == 0;
   };
-  double eps_scale = 1.0;  // tightened by the verified-polish rounds (DESIGN.md deviation D2)
   auto check_termination = [&](bool approximate) -> int {
     double eps_abs = st.eps_abs * eps_scale, eps_rel = st.eps_rel * eps_scale, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
     if (approximate) {
@@ -643,77 +723,80 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm,
     return QPS_UNSOLVED;
   };
 
-  // ADMM iterations, continuing from the current state until a termination test fires or max_iter.
+  // ADMM iterations, continuing from the current state until a termination test fires, max_iter, or the
+  // slice budget is exhausted (status QPS_YIELD).
   auto run_admm = [&]() {
     status = QPS_UNSOLVED;
     while (iter < st.max_iter) {
+      if (budget <= 0) {
+        status = QPS_YIELD;
+        return;
+      }
+      --budget;
       ++iter;
       const bool can_check = st.check_termination > 0 && (iter % st.check_termination == 0);
       const bool rho_iter = st.adaptive_rho && st.adaptive_rho_interval > 0 && (iter % st.adaptive_rho_interval == 0);
       const bool keep_steps = can_check || iter == st.max_iter;
-      // ---- right-hand side:  sigma x - q + A'(rho z - y), aux part eliminated -------------------------
-      for (int i = lane; i < N; i += 32) {
-        const double beta = q.Eb[i] * q.Dz[i];
-        const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
-        q.v1[i] = q.sigma * q.x[i] - q.qs[i] + beta * (rb * q.zb[i] - q.yb[i]);
+      // ---- rows: aux right-hand sides and the row multipliers of the reduced system ---------------------
+      for (int r = lane; r < q.nrows; r += 32) {
+        double* F = q.F(r);
+        const int naux = q.I(r)[RI_AUX];
+        const double s = F[R_WRR] * F[R_Z] - F[R_Y];
+        if (naux >= 1) F[R_RA0] = q.sigma * F[R_XA0] - F[R_QA0] + F[R_U0] * s + F[R_B0] * (sysw.rho_aux * F[R_ZA0] - F[R_YA0]);
+        if (naux == 2) F[R_RA1] = q.sigma * F[R_XA1] - F[R_QA1] + F[R_U1] * s + F[R_B1] * (sysw.rho_aux * F[R_ZA1] - F[R_YA1]);
+        F[R_COEF] = row_reduce_coef(F, naux, s);
       }
       __syncwarp();
-      q.for_rows([&](int r) {
-        double* R = q.R(r);
-        double* F = R + q.CN;
-        RowV v;
-        row_view(q, R, q.I(r), v);
-        double Wr, g0, g1, den;
-        row_weights(q, sysw, F, v, Wr, g0, g1, den);
-        const double s = Wr * F[F_Z] - F[F_Y];
-        if (v.naux >= 1) F[F_RA0] = q.sigma * F[F_XA0] - v.qa0 + v.u0 * s + v.b0 * (sysw.rho_aux * F[F_ZA0] - F[F_YA0]);
-        if (v.naux == 2) F[F_RA1] = q.sigma * F[F_XA1] - v.qa1 + v.u1 * s + v.b1 * (sysw.rho_aux * F[F_ZA1] - F[F_YA1]);
-        row_reduce_rhs(q, R, F, v, Wr, g0, g1, den, s);
+      // ---- right-hand side  sigma x - q + A'(rho z - y)  (one lane per variable) ----------------------
+      scatter_columns(q, [&](int i) {
+        const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
+        return q.sigma * q.x[i] - q.qs[i] + q.beta[i] * (rb * q.zb[i] - q.yb[i]);
       });
-      band_solve(q, q.v1);
+      block_solve(q, q.v1);
       // ---- rows: back-substitute aux, relax, project, dual update ----------------------------------------
-      q.for_rows([&](int r) {
-        double* R = q.R(r);
-        double* F = R + q.CN;
-        RowV v;
-        row_view(q, R, q.I(r), v);
-        double Wr, g0, g1, den, zeta, a0, a1;
-        row_weights(q, sysw, F, v, Wr, g0, g1, den);
-        row_backsub(q, R, F, v, Wr, g0, g1, den, zeta, a0, a1);
-        const double zt = zeta + v.u0 * a0 + v.u1 * a1;
+      for (int r = lane; r < q.nrows; r += 32) {
+        const double* R = q.R(r);
+        double* F = q.F(r);
+        const int naux = q.I(r)[RI_AUX];
+        const double zeta = row_dot(q, R, q.I(r), q.v1);
+        double a0, a1;
+        row_backsub(F, naux, zeta, a0, a1);
+        const double zt = zeta + F[R_U0] * a0 + F[R_U1] * a1;
         {
-          const double zr = q.alpha * zt + (1.0 - q.alpha) * F[F_Z];
-          double zn = zr + F[F_Y] / Wr;
-          zn = fmin(fmax(zn, v.lo), v.up);
+          const double Wr = F[R_WRR];
+          const double zr = q.alpha * zt + (1.0 - q.alpha) * F[R_Z];
+          double zn = zr + F[R_Y] / Wr;
+          zn = fmin(fmax(zn, F[R_LO]), F[R_UP]);
           const double dy = Wr * (zr - zn);
-          F[F_Z] = zn;
-          F[F_Y] += dy;
-          F[F_DY] = dy;
+          F[R_Z] = zn;
+          F[R_Y] += dy;
+          F[R_DY] = dy;
         }
-        for (int k = 0; k < v.naux; ++k) {
-          const double at = k ? a1 : a0, bb = k ? v.b1 : v.b0;
-          const double xo = F[F_XA0 + k];
+        for (int k = 0; k < naux; ++k) {
+          const double at = k ? a1 : a0, bb = F[R_B0 + k];
+          const double xo = F[R_XA0 + k];
           const double xn = q.alpha * at + (1.0 - q.alpha) * xo;
-          F[F_XA0 + k] = xn;
-          F[F_DXA0 + k] = xn - xo;
-          const double zr = q.alpha * (bb * at) + (1.0 - q.alpha) * F[F_ZA0 + k];
-          double zn = zr + F[F_YA0 + k] / sysw.rho_aux;
-          zn = fmin(fmax(zn, 0.0), kOsqpInf * F[F_EA0 + k]);
+          F[R_XA0 + k] = xn;
+          F[R_DXA0 + k] = xn - xo;
+          const double zr = q.alpha * (bb * at) + (1.0 - q.alpha) * F[R_ZA0 + k];
+          double zn = zr + F[R_YA0 + k] / sysw.rho_aux;
+          zn = fmin(fmax(zn, 0.0), kOsqpInf * F[R_EA0 + k]);
           const double dy = sysw.rho_aux * (zr - zn);
-          F[F_ZA0 + k] = zn;
-          F[F_YA0 + k] += dy;
-          F[F_DYA0 + k] = dy;
+          F[R_ZA0 + k] = zn;
+          F[R_YA0 + k] += dy;
+          F[R_DYA0 + k] = dy;
         }
-      });
+      }
       // ---- trajectory variables and their bound rows -----------------------------------------------------
       for (int i = lane; i < N; i += 32) {
-        const double beta = q.Eb[i] * q.Dz[i];
-        const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
+        const double beta = q.beta[i];
+        const double lb = q.lbs[i], ub = q.ubs[i];
+        const double rb = (ub - lb < kRhoTol) ? q.rho_eq : q.rho;
         const double xt = q.v1[i];
         const double xn = q.alpha * xt + (1.0 - q.alpha) * q.x[i];
         const double zr = q.alpha * (beta * xt) + (1.0 - q.alpha) * q.zb[i];
         double zn = zr + q.yb[i] / rb;
-        zn = fmin(fmax(zn, q.lbs[i]), q.ubs[i]);
+        zn = fmin(fmax(zn, lb), ub);
         const double dy = rb * (zr - zn);
         if (keep_steps) {
           dxs[i] = xn - q.x[i];
@@ -758,139 +841,139 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm,
   // ---- polish (OSQP polish.c [EXT]) ---------------------------------------------------------------------
   // Equality-constrained QP on the guessed active set, solved as the delta-regularised KKT system with
   // iterative refinement, in its reduced form K_p = P + delta I + (1/delta) A_act' A_act (same aux
-  // elimination and banded factor as the ADMM system).  Returns false when K_p could not be factored.
-  // `verified`: the polished point is primal feasible to verify_tol and every active inequality row has a
+  // elimination and block factor as the ADMM system).  Returns false when K_p could not be factored.
+  // `verified`: the polished point is primal feasible to kVerifyTol and every active inequality row has a
   // correctly signed multiplier, i.e. it is a KKT point of the QP = the unique minimiser.
   const double wp = 1.0 / st.delta;
   const SysW pw{true, st.delta, 0.0};
   auto polish_once = [&](bool& verified, double& p_pri, double& p_dua) -> bool {
     verified = false;
-    for (int i = lane; i < N; i += 32) {
+    for (int i = lane; i < q.Np; i += 32) {
       st_x[i] = q.x[i];
       st_zb[i] = q.zb[i];
       st_yb[i] = q.yb[i];
-      const double z = q.zb[i], y = q.yb[i];
       double w = 0.0;
-      if (z - q.lbs[i] < -y) w = -wp;           // lower active
-      else if (q.ubs[i] - z < y) w = wp;        // upper active
-      q.zb[i] = w;                               // signed polish weight
-      q.x[i] = 0.0;                              // polish iterate
-      q.yb[i] = 0.0;                             // polish multiplier
+      if (i < N) {
+        const double z = q.zb[i], y = q.yb[i];
+        if (z - q.lbs[i] < -y) w = -wp;           // lower active
+        else if (q.ubs[i] - z < y) w = wp;        // upper active
+      }
+      q.zb[i] = w;                                 // signed polish weight
+      q.x[i] = 0.0;                                // polish iterate
+      q.yb[i] = 0.0;                               // polish multiplier
     }
-    q.for_rows([&](int r) {
-      double* R = q.R(r);
-      double* F = R + q.CN;
-      RowV v;
-      row_view(q, R, q.I(r), v);
+    for (int r = lane; r < q.nrows; r += 32) {
+      double* F = q.F(r);
+      const int naux = q.I(r)[RI_AUX];
       double w = 0.0, b = 0.0;
-      if (F[F_Z] - v.lo < -F[F_Y]) { w = -wp; b = v.lo; }
-      else if (v.up - F[F_Z] < F[F_Y]) { w = wp; b = v.up; }
-      F[F_PW] = w;
-      F[F_PB] = b;
+      if (F[R_Z] - F[R_LO] < -F[R_Y]) { w = -wp; b = F[R_LO]; }
+      else if (F[R_UP] - F[R_Z] < F[R_Y]) { w = wp; b = F[R_UP]; }
+      F[R_PW] = w;
+      F[R_PB] = b;
       for (int k = 0; k < 2; ++k) {
         double wa = 0.0;
-        if (k < v.naux) {
-          if (F[F_ZA0 + k] - 0.0 < -F[F_YA0 + k]) wa = -wp;                                    // lower (0) active
-          else if (kOsqpInf * F[F_EA0 + k] - F[F_ZA0 + k] < F[F_YA0 + k]) wa = wp;            // never in practice
+        if (k < naux) {
+          if (F[R_ZA0 + k] - 0.0 < -F[R_YA0 + k]) wa = -wp;                                    // lower (0) active
+          else if (kOsqpInf * F[R_EA0 + k] - F[R_ZA0 + k] < F[R_YA0 + k]) wa = wp;            // never in practice
         }
-        F[F_PWA0 + k] = wa;
-        F[F_PYA0 + k] = 0.0;
-        F[F_PX0 + k] = 0.0;
+        F[R_PWA0 + k] = wa;
+        F[R_PYA0 + k] = 0.0;
+        F[R_PX0 + k] = 0.0;
       }
-      F[F_PY] = 0.0;
-    });
+      F[R_PY] = 0.0;
+    }
     __syncwarp();
     if (!assemble_factor(q, pw)) return false;
     for (int it = 0; it <= st.polish_refine_iter + 1; ++it) {
       const bool last = (it == st.polish_refine_iter + 1);  // final pass: pending dual update + residuals only
-      // v1 <- P xq ; residual rd = -(P x + q + A'y) - A' W (A x - b), y update of the previous step folded in
-      p_matvec(q, q.x, q.v1);
-      double m_pri = 0.0, m_dua_a = 0.0;
+      p_matvec(q, q.x, q.v2);  // v2 <- P xq
+      double m_pri = 0.0, m_dua = 0.0;
       int bad_sign = 0;
-      for (int i = lane; i < N; i += 32) {
-        const double beta = q.Eb[i] * q.Dz[i];
-        const double ax = beta * q.x[i];
-        const double w = fabs(q.zb[i]);
-        const double bnd = q.zb[i] > 0 ? q.ubs[i] : q.lbs[i];
-        if (it > 0 && w != 0.0) q.yb[i] += w * (ax - bnd);
-        const double e = q.yb[i] + (last ? 0.0 : w * (ax - bnd));
-        const double zc = fmin(fmax(ax, q.lbs[i]), q.ubs[i]);
-        m_pri = fmax(m_pri, fabs((ax - zc) / q.Eb[i]));
-        if (last && w != 0.0 && q.ubs[i] - q.lbs[i] >= kRhoTol) {
-          if (q.zb[i] > 0 && q.yb[i] < -kVerifyTol) bad_sign = 1;
-          if (q.zb[i] < 0 && q.yb[i] > kVerifyTol) bad_sign = 1;
+      // rows: residual of the row, pending multiplier update, aux right-hand sides, row multiplier for A'
+      for (int r = lane; r < q.nrows; r += 32) {
+        const double* R = q.R(r);
+        double* F = q.F(r);
+        const int naux = q.I(r)[RI_AUX];
+        const double Wr = F[R_WRR];
+        const double ax = row_dot(q, R, q.I(r), q.x) + F[R_U0] * F[R_PX0] + F[R_U1] * F[R_PX1];
+        if (it > 0 && Wr != 0.0) F[R_PY] += Wr * (ax - F[R_PB]);
+        const double e = F[R_PY] + (last ? 0.0 : Wr * (ax - F[R_PB]));
+        const double zc = fmin(fmax(ax, F[R_LO]), F[R_UP]);
+        m_pri = fmax(m_pri, fabs((ax - zc) / F[R_E]));
+        if (last && Wr != 0.0 && naux == AUX_HINGE && F[R_PY] < -kVerifyTol) bad_sign = 1;  // upper active needs y >= 0
+        double ea[2] = {0.0, 0.0};
+        for (int k = 0; k < naux; ++k) {
+          const double bb = F[R_B0 + k], u = F[R_U0 + k], qa = F[R_QA0 + k];
+          const double wa = fabs(F[R_PWA0 + k]);
+          const double axb = bb * F[R_PX0 + k];
+          if (it > 0 && wa != 0.0) F[R_PYA0 + k] += wa * axb;
+          ea[k] = F[R_PYA0 + k] + (last ? 0.0 : wa * axb);
+          m_pri = fmax(m_pri, fabs((axb - fmax(axb, 0.0)) / F[R_EA0 + k]));
+          if (last && wa != 0.0 && F[R_PYA0 + k] > kVerifyTol) bad_sign = 1;  // aux >= 0 held at 0 needs y <= 0
+          m_dua = fmax(m_dua, fabs((qa + u * F[R_PY] + bb * F[R_PYA0 + k]) / F[R_DA0 + k]));
+          F[R_RA0 + k] = -qa - u * e - bb * ea[k];
         }
-        q.v2[i] = q.v1[i] + q.qs[i] + beta * q.yb[i];  // dual residual (uses y only)
-        q.v1[i] = -(q.v1[i] + q.qs[i]) - beta * e;
+        F[R_COEF] = last ? F[R_PY] : row_reduce_coef(F, naux, -e);
       }
       __syncwarp();
-      q.for_rows([&](int r) {
-        double* R = q.R(r);
-        double* F = R + q.CN;
-        RowV v;
-        row_view(q, R, q.I(r), v);
-        double Wr, g0, g1, den;
-        row_weights(q, pw, F, v, Wr, g0, g1, den);
-        double ax = 0.0;
-        for (int i = 0; i < v.cnt; ++i) {
-          const int vi = v.base + i * v.stride;
-          ax += v.E * R[i] * q.Dz[vi] * q.x[vi];
-        }
-        ax += v.u0 * F[F_PX0] + v.u1 * F[F_PX1];
-        if (it > 0 && Wr != 0.0) F[F_PY] += Wr * (ax - F[F_PB]);
-        const double e = F[F_PY] + (last ? 0.0 : Wr * (ax - F[F_PB]));
-        const double zc = fmin(fmax(ax, v.lo), v.up);
-        m_pri = fmax(m_pri, fabs((ax - zc) / v.E));
-        if (last && Wr != 0.0 && v.naux == AUX_HINGE) {  // inequality row (l = -inf): upper active needs y >= 0
-          if (F[F_PY] < -kVerifyTol) bad_sign = 1;
-        }
-        double ea[2] = {0.0, 0.0};
-        for (int k = 0; k < v.naux; ++k) {
-          const double bb = k ? v.b1 : v.b0, u = k ? v.u1 : v.u0, qa = k ? v.qa1 : v.qa0;
-          const double wa = fabs(F[F_PWA0 + k]);
-          const double axb = bb * F[F_PX0 + k];
-          if (it > 0 && wa != 0.0) F[F_PYA0 + k] += wa * (axb - 0.0);
-          ea[k] = F[F_PYA0 + k] + (last ? 0.0 : wa * axb);
-          const double zca = fmax(axb, 0.0);
-          m_pri = fmax(m_pri, fabs((axb - zca) / F[F_EA0 + k]));
-          if (last && wa != 0.0 && F[F_PYA0 + k] > kVerifyTol) bad_sign = 1;  // aux >= 0 held at 0 needs y <= 0
-          m_dua_a = fmax(m_dua_a, fabs((qa + u * F[F_PY] + bb * F[F_PYA0 + k]) / F[F_DA0 + k]));
-          F[F_RA0 + k] = -qa - u * e - bb * ea[k];
-        }
-        for (int i = 0; i < v.cnt; ++i) {
-          const int vi = v.base + i * v.stride;
-          q.v2[vi] += v.E * R[i] * q.Dz[vi] * F[F_PY];
-        }
-        if (!last) row_reduce_rhs(q, R, F, v, Wr, g0, g1, den, -e);
-      });
       if (last) {
-        double m_dua = m_dua_a;
-        for (int i = lane; i < N; i += 32) m_dua = fmax(m_dua, fabs(q.v2[i] / q.Dz[i]));
+        // dual residual  P x + q + A'y  over the trajectory variables
+        scatter_columns(q, [&](int i) { return q.v2[i] + q.qs[i] + q.beta[i] * q.yb[i]; });
+      }
+      for (int i = lane; i < N; i += 32) {
+        const double beta = q.beta[i];
+        const double ax = beta * q.x[i];
+        const double w = fabs(q.zb[i]);
+        const double lb = q.lbs[i], ub = q.ubs[i];
+        const double zc = fmin(fmax(ax, lb), ub);
+        m_pri = fmax(m_pri, fabs((ax - zc) * q.Dz[i] / beta));
+        if (last) {
+          if (w != 0.0 && ub - lb >= kRhoTol) {
+            if (q.zb[i] > 0 && q.yb[i] < -kVerifyTol) bad_sign = 1;
+            if (q.zb[i] < 0 && q.yb[i] > kVerifyTol) bad_sign = 1;
+          }
+          m_dua = fmax(m_dua, fabs(q.v1[i] / q.Dz[i]));
+        }
+      }
+      if (last) {
         p_pri = warp_max(m_pri);
         p_dua = warp_max(m_dua) * q.cinv;
         const int nbad = warp_sum_int(bad_sign);
         verified = (nbad == 0) && (p_pri <= kVerifyTol) && isfinite(p_pri) && isfinite(p_dua);
         break;
       }
-      band_solve(q, q.v1);
-      q.for_rows([&](int r) {
-        double* R = q.R(r);
-        double* F = R + q.CN;
-        RowV v;
-        row_view(q, R, q.I(r), v);
-        double Wr, g0, g1, den, zeta, a0, a1;
-        row_weights(q, pw, F, v, Wr, g0, g1, den);
-        row_backsub(q, R, F, v, Wr, g0, g1, den, zeta, a0, a1);
-        F[F_PX0] += a0;
-        F[F_PX1] += a1;
+      __syncwarp();
+      // rd = -(P x + q) - beta * (y + W (A x - b)) + A' coef
+      scatter_columns(q, [&](int i) {
+        const double beta = q.beta[i];
+        const double ax = beta * q.x[i];
+        const double w = fabs(q.zb[i]);
+        const double bnd = q.zb[i] > 0 ? q.ubs[i] : q.lbs[i];
+        return -(q.v2[i] + q.qs[i]) - beta * (q.yb[i] + w * (ax - bnd));
       });
-      for (int i = lane; i < N; i += 32) q.x[i] += q.v1[i];
+      block_solve(q, q.v1);
+      for (int r = lane; r < q.nrows; r += 32) {
+        const double* R = q.R(r);
+        double* F = q.F(r);
+        const int naux = q.I(r)[RI_AUX];
+        double a0, a1;
+        row_backsub(F, naux, row_dot(q, R, q.I(r), q.v1), a0, a1);
+        F[R_PX0] += a0;
+        F[R_PX1] += a1;
+      }
+      for (int i = lane; i < N; i += 32) {
+        q.x[i] += q.v1[i];
+        // multiplier update of the variable-bound rows with the new iterate (the rows do theirs at the start
+        // of the next pass, where A x is recomputed anyway)
+        const double w = fabs(q.zb[i]);
+        if (w != 0.0) q.yb[i] += w * (q.beta[i] * q.x[i] - (q.zb[i] > 0 ? q.ubs[i] : q.lbs[i]));
+      }
       __syncwarp();
     }
     return true;
   };
   auto restore_admm_state = [&](bool keep_polished_x) {
-    for (int i = lane; i < N; i += 32) {
+    for (int i = lane; i < q.Np; i += 32) {
       if (!keep_polished_x) q.x[i] = st_x[i];
       q.zb[i] = st_zb[i];
       q.yb[i] = st_yb[i];
@@ -899,12 +982,12 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm,
   };
 
   // ---- main loop: ADMM -> polish -> verify; on a failed verification ADMM continues with 10x tighter ------
-  // tolerances (DESIGN.md deviation D2; verify_rounds = 0 is plain OSQP behaviour).
-  int round = 0;
+  // tolerances (DESIGN.md deviation D2).
   while (true) {
     run_admm();
     out.pri_res = pri_res;
     out.dua_res = dua_res;
+    if (status == QPS_YIELD) break;
     if (status != QPS_SOLVED || !st.polishing) break;
     bool verified = false;
     double p_pri = 0.0, p_dua = 0.0;
@@ -935,213 +1018,267 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool warm,
   out.status = status;
   out.rho = rho;
   out.c = q.c;
+  rs.iter = iter;
+  rs.round = round;
+  rs.rho = rho;
+  rs.eps_scale = eps_scale;
+  rs.rho_updates = out.rho_updates;
+  rs.c = q.c;
   if (out.polish != 0) {
     // Adopt the polished PRIMAL point when accepted.  The duals kept for the next warm start are always the
     // ADMM duals: polished duals are non-unique on degenerate active sets (DESIGN.md deviation D1).
     if (out.polish > 0) {
-      q.for_rows([&](int r) {
-        double* F = q.R(r) + q.CN;
-        for (int k = 0; k < 2; ++k) F[F_XA0 + k] = F[F_PX0 + k];
-      });
+      for (int r = lane; r < q.nrows; r += 32) {
+        double* F = q.F(r);
+        for (int k = 0; k < 2; ++k) F[R_XA0 + k] = F[R_PX0 + k];
+      }
     }
     restore_admm_state(out.polish > 0);
   }
   return out;
 }
 
-}  // namespace tb200
-
-namespace tb200 {
-
 // ---------------------------------------------------------------------------------------------------
-// Kernel: QP assembly (optimizers.cpp:781-799 + osqp_interface.cpp:170-281 in fixed layout) + solve.
+// Kernel: QP assembly (optimizers.cpp:781-799 + osqp_interface.cpp:170-281 in fixed layout) + solve slice.
 // grid = B, block = 32 (one warp per trajectory).
 __global__ void __launch_bounds__(32) qp_kernel(DevProblem p, const double* x_override /*kernel-level API*/,
                                                 const double* trust_override, int* admm_iters_out,
-                                                int* polish_out) {
+                                                int* polish_out, int slice) {
   extern __shared__ double sm[];
   const int b = blockIdx.x;
   const int lane = threadIdx.x;
-  if (!x_override && p.status[b] != 5) return;
-  const int N = p.N, T = p.T, D = p.D, HB = p.HB;
-  const QpSmem S = qp_smem_layout(N, HB, T, D);
+  if (!x_override && (p.status[b] != 5 || p.qp_done[b] != 0)) return;  // finished, or waiting for its evaluation
+  const int N = p.N, T = p.T, D = p.D;
   QpCtx q;
-  q.N = N; q.HB = HB; q.T = T; q.D = D; q.lane = lane;
-  q.CN = p.row_stride - F_NFIELDS;
+  q.N = N; q.T = T; q.D = D; q.lane = lane;
+  q.nb = 2 * D;
+  q.M = qp_block_count(N, q.nb);
+  q.Np = q.M * q.nb;
+  q.Wd = q.nb + 2;
+  const QpSmem S = qp_smem_layout(N, q.nb);
+  q.CN = (p.row_stride - R_NF) / 2;
   q.RS = p.row_stride;
-  q.Kb = sm + S.Kb; q.Dz = sm + S.Dz; q.Eb = sm + S.Eb; q.qs = sm + S.qs; q.lbs = sm + S.lbs; q.ubs = sm + S.ubs;
-  q.x = sm + S.x; q.zb = sm + S.zb; q.yb = sm + S.yb; q.v1 = sm + S.v1; q.v2 = sm + S.v2; q.invd = sm + S.invd;
-  q.ls = reinterpret_cast<int*>(sm + S.ints);
+  q.Kb = sm + S.Kb; q.Linv = sm + S.Linv; q.Dz = sm + S.Dz; q.beta = sm + S.beta;
+  q.x = sm + S.x; q.zb = sm + S.zb; q.yb = sm + S.yb; q.v1 = sm + S.v1; q.v2 = sm + S.v2;
   q.rows = p.rows + static_cast<size_t>(b) * p.max_rows * p.row_stride;
   q.rints = p.row_ints + static_cast<size_t>(b) * p.max_rows * RI_NINTS;
-  int* mylist = p.lists + static_cast<size_t>(b) * (2 * p.max_rows + p.n_costs + p.n_cnts + 2);
-  int* obj_start = mylist + 2 * p.max_rows;  // [n_costs + n_cnts + 1]
-  q.list = mylist;
+  int* mylist = p.lists + static_cast<size_t>(b) * p.list_stride;
+  int* colptr = mylist;                                   // [Np+1]
+  int* colent = mylist + q.Np + 1;                        // [max_rows*CN]
+  int* obj_start = colent + static_cast<size_t>(p.max_rows) * q.CN;  // [n_objs+1]
+  q.colptr = colptr;
+  q.colent = colent;
   q.Pband = p.Pband;
-  q.scratch = p.scratch + static_cast<size_t>(b) * 5 * N;
-
-  const double* xc = (x_override ? x_override : p.x) + static_cast<size_t>(b) * N;
-  const double trust = trust_override ? trust_override[b] : p.trust[b];
-  const double* mu = p.merit_coeffs + static_cast<size_t>(b) * p.n_cnts;
-  const int buf = x_override ? 0 : p.cur_buf[b];
-  const size_t slot = static_cast<size_t>(buf) * p.B + b;
-  const double* cart_err = p.cart_err + slot * p.n_cart_rows;
-  const double* cart_jac = p.cart_jac + slot * static_cast<size_t>(p.n_cart_rows) * p.cart_stride;
-  const double* coll_rows = p.coll_rows + slot * static_cast<size_t>(p.n_coll_cand) * p.coll_stride;
-  const unsigned long long* coll_mask = p.coll_mask + slot * static_cast<size_t>(p.n_coll_objs) * p.coll_words;
-
-  // ---- trajectory part: x, trust box (setTrustBoxConstraints, optimizers.cpp:151-170), linear cost -----
-  for (int i = lane; i < N; i += 32) {
-    const double lb = p.lower[i % D], ub = p.upper[i % D];
-    const double xi = fmin(fmax(xc[i], lb), ub);
-    q.lbs[i] = fmax(fmax(xi - trust, lb), -kOsqpInf);
-    q.ubs[i] = fmin(fmin(xi + trust, ub), kOsqpInf);
-    q.qs[i] = p.qlin[i];
-    q.x[i] = xc[i];  // linearisation point (until the solver takes over x)
-  }
-  __syncwarp();
-
-  // ---- rows in the reference's canonical order: permanent rows, cost rows, penalised constraint rows -----
-  int nr = 0, n_aux = 0, nnzA = 0;
-  // (a) fixed_timesteps / fixed_dofs rows: x_k - init_k == 0
-  for (int f = lane; f < p.n_fixed; f += 32) {
-    const int var = p.fixed_vars[f];
-    double* R = q.R(nr + f);
-    int* I = q.rints + static_cast<size_t>(nr + f) * RI_NINTS;
-    R[0] = 1.0;
-    R[q.CN + F_C] = -p.init_traj[static_cast<size_t>(b) * N + var];
-    R[q.CN + F_W] = 0.0;
-    I[RI_BASE] = var; I[RI_CNT] = 1; I[RI_STRIDE] = D; I[RI_AUX] = AUX_NONE; I[RI_OBJ] = -1; I[RI_PAD] = -1 - (var % D);
-  }
-  nr += p.n_fixed;
-  nnzA += p.n_fixed;
-  // (b) objects
+  double* gvec = p.scratch + static_cast<size_t>(b) * 8 * q.Np;  // dxs dyb st_x st_zb st_yb | qs lbs ubs
+  q.scratch = gvec;
+  double* qs = gvec + 5 * q.Np;
+  double* lbs = gvec + 6 * q.Np;
+  double* ubs = gvec + 7 * q.Np;
+  double* park = p.park + static_cast<size_t>(b) * 5 * q.Np;     // x zb yb Dz beta of a parked solve
+  q.qs = qs; q.lbs = lbs; q.ubs = ubs;
+  int* meta = p.ws_meta + static_cast<size_t>(b) * 8;  // 0..3 warm-start key, 4 phase, 5 nrows, 6 n_aux, 7 nnzA
   const int n_obj = p.n_costs + p.n_cnts;
-  int coll_obj_counter = 0;
-  for (int oi = 0; oi < n_obj; ++oi) {
-    const bool is_cnt = oi >= p.n_costs;
-    const DevObj o = is_cnt ? p.cnt_objs[oi - p.n_costs] : p.cost_objs[oi];
-    if (lane == 0) obj_start[oi] = nr;
-    const double w_aux = is_cnt ? mu[oi - p.n_costs] : 1.0;
-    if (o.kind == OBJ_JOINT_EQ_COST) continue;
-    if (o.kind == OBJ_JOINT_EQ_CNT || o.kind == OBJ_JOINT_INEQ_CNT || o.kind == OBJ_JOINT_INEQ_COST) {
-      const DevJointTerm& jt = p.joint_terms[o.term];
-      const int per = (o.kind == OBJ_JOINT_EQ_CNT) ? 1 : 2;
-      const int total = o.n_steps * D * per;
-      const double wst[3][3] = {{1, 0, 0}, {-1, 1, 0}, {1, -2, 1}};
-      for (int k = lane; k < total; k += 32) {
-        const int t = o.first + k / (D * per), d = (k / per) % D, side = k % per;
-        double* R = q.R(nr + k);
-        int* I = q.rints + static_cast<size_t>(nr + k) * RI_NINTS;
-        const double cd = jt.coeffs[d];
-        double sgn = cd, cst;
-        if (per == 1) cst = -jt.targets[d] * cd;
-        else if (side == 0) cst = (-jt.targets[d] - jt.upper[d]) * cd;        // (e - upper) * c
-        else { sgn = -cd; cst = (jt.lower[d] + jt.targets[d]) * cd; }         // (lower - e) * c
-        for (int i = 0; i <= o.order; ++i) R[i] = wst[o.order][i] * sgn;
-        R[q.CN + F_C] = cst;
-        R[q.CN + F_W] = w_aux;
-        I[RI_BASE] = t * D + d; I[RI_CNT] = o.order + 1; I[RI_STRIDE] = D;
-        I[RI_AUX] = (per == 1) ? AUX_ABS : AUX_HINGE; I[RI_OBJ] = oi; I[RI_PAD] = -1 - d;
-      }
-      nr += total;
-      n_aux += total * ((per == 1) ? 2 : 1);
-      nnzA += total * (o.order + 1 + ((per == 1) ? 2 : 1));
-    } else if (o.kind == OBJ_CART_POSE) {
-      const DevCartTerm& ct = p.cart_terms[o.term];
-      int nz = 0;
-      for (int k = lane; k < o.n_rows; k += 32) {
-        double* R = q.R(nr + k);
-        int* I = q.rints + static_cast<size_t>(nr + k) * RI_NINTS;
-        const double* J = cart_jac + static_cast<size_t>(o.src_off + k) * p.cart_stride;
-        const double thr = 1e-7 * fabs(ct.coeff[k]);  // cleanupAff acts on the unscaled gradient (modeling_utils.cpp:31-39)
-        double dot = 0.0;
-        for (int j = 0; j < D; ++j) {
-          dot += J[j] * q.x[o.first * D + j];
-          const double a = (fabs(J[j]) > thr) ? J[j] : 0.0;
-          R[j] = a;
-          nz += (a != 0.0);
+  QpResume rs{};
+  const bool resume = !x_override && meta[4] == 1;
+  int nr = 0, n_aux = 0, nnzA = 0;
+  bool warm = false;
+
+  if (!resume) {
+    const double* xc = (x_override ? x_override : p.x) + static_cast<size_t>(b) * N;
+    const double trust = trust_override ? trust_override[b] : p.trust[b];
+    const double* mu = p.merit_coeffs + static_cast<size_t>(b) * p.n_cnts;
+    const int buf = x_override ? 0 : p.cur_buf[b];
+    const size_t slot = static_cast<size_t>(buf) * p.B + b;
+    const double* cart_err = p.cart_err + slot * p.n_cart_rows;
+    const double* cart_jac = p.cart_jac + slot * static_cast<size_t>(p.n_cart_rows) * p.cart_stride;
+    const double* coll_rows = p.coll_rows + slot * static_cast<size_t>(p.n_coll_cand) * p.coll_stride;
+    const unsigned long long* coll_mask = p.coll_mask + slot * static_cast<size_t>(p.n_coll_objs) * p.coll_words;
+
+    // ---- trajectory part: x, trust box (setTrustBoxConstraints, optimizers.cpp:151-170), linear cost -----
+    for (int i = lane; i < N; i += 32) {
+      const double lb = p.lower[i % D], ub = p.upper[i % D];
+      const double xi = fmin(fmax(xc[i], lb), ub);
+      lbs[i] = fmax(fmax(xi - trust, lb), -kOsqpInf);
+      ubs[i] = fmin(fmin(xi + trust, ub), kOsqpInf);
+      qs[i] = p.qlin[i];
+      q.x[i] = xc[i];  // linearisation point (until the solver takes over x)
+    }
+    __syncwarp();
+
+    // ---- rows in the reference's canonical order: permanent rows, cost rows, penalised constraint rows -----
+    for (int f = lane; f < p.n_fixed; f += 32) {  // fixed_timesteps / fixed_dofs rows: x_k - init_k == 0
+      const int var = p.fixed_vars[f];
+      double* R = q.R(f);
+      int* I = q.rints + static_cast<size_t>(f) * RI_NINTS;
+      R[0] = 1.0;
+      R[2 * q.CN + R_C] = -p.init_traj[static_cast<size_t>(b) * N + var];
+      R[2 * q.CN + R_W] = 0.0;
+      I[RI_BASE] = var; I[RI_CNT] = 1; I[RI_STRIDE] = D; I[RI_AUX] = AUX_NONE; I[RI_OBJ] = -1;
+    }
+    nr += p.n_fixed;
+    nnzA += p.n_fixed;
+    int coll_obj_counter = 0;
+    for (int oi = 0; oi < n_obj; ++oi) {
+      const bool is_cnt = oi >= p.n_costs;
+      const DevObj o = is_cnt ? p.cnt_objs[oi - p.n_costs] : p.cost_objs[oi];
+      if (lane == 0) obj_start[oi] = nr;
+      const double w_aux = is_cnt ? mu[oi - p.n_costs] : 1.0;
+      if (o.kind == OBJ_JOINT_EQ_COST) continue;
+      if (o.kind == OBJ_JOINT_EQ_CNT || o.kind == OBJ_JOINT_INEQ_CNT || o.kind == OBJ_JOINT_INEQ_COST) {
+        const DevJointTerm& jt = p.joint_terms[o.term];
+        const int per = (o.kind == OBJ_JOINT_EQ_CNT) ? 1 : 2;
+        const int total = o.n_steps * D * per;
+        const double wst[3][3] = {{1, 0, 0}, {-1, 1, 0}, {1, -2, 1}};
+        for (int k = lane; k < total; k += 32) {
+          const int t = o.first + k / (D * per), d = (k / per) % D, side = k % per;
+          double* R = q.R(nr + k);
+          int* I = q.rints + static_cast<size_t>(nr + k) * RI_NINTS;
+          const double cd = jt.coeffs[d];
+          double sgn = cd, cst;
+          if (per == 1) cst = -jt.targets[d] * cd;
+          else if (side == 0) cst = (-jt.targets[d] - jt.upper[d]) * cd;        // (e - upper) * c
+          else { sgn = -cd; cst = (jt.lower[d] + jt.targets[d]) * cd; }         // (lower - e) * c
+          for (int i = 0; i <= o.order; ++i) R[i] = wst[o.order][i] * sgn;
+          R[2 * q.CN + R_C] = cst;
+          R[2 * q.CN + R_W] = w_aux;
+          I[RI_BASE] = t * D + d; I[RI_CNT] = o.order + 1; I[RI_STRIDE] = D;
+          I[RI_AUX] = (per == 1) ? AUX_ABS : AUX_HINGE; I[RI_OBJ] = oi;
         }
-        R[q.CN + F_C] = cart_err[o.src_off + k] - dot;
-        R[q.CN + F_W] = w_aux;
-        I[RI_BASE] = o.first * D; I[RI_CNT] = D; I[RI_STRIDE] = 1; I[RI_AUX] = AUX_ABS; I[RI_OBJ] = oi; I[RI_PAD] = o.first;
-      }
-      nz = warp_sum_int(nz);
-      nr += o.n_rows;
-      n_aux += 2 * o.n_rows;
-      nnzA += nz + 2 * o.n_rows;
-    } else if (o.kind == OBJ_COLL) {
-      // active candidates of this timestep, in candidate order (ballot compaction)
-      const unsigned long long* mw = coll_mask + static_cast<size_t>(coll_obj_counter) * p.coll_words;
-      ++coll_obj_counter;
-      int nz = 0, count = 0;
-      for (int c0 = 0; c0 < o.n_rows; c0 += 32) {
-        const int c = c0 + lane;
-        const bool act = (c < o.n_rows) && ((mw[c / 64] >> (c % 64)) & 1ull);
-        const unsigned bal = __ballot_sync(0xffffffffu, act);
-        if (act) {
-          const int pos = nr + count + __popc(bal & ((1u << lane) - 1u));
-          double* R = q.R(pos);
-          int* I = q.rints + static_cast<size_t>(pos) * RI_NINTS;
-          const double* cr = coll_rows + static_cast<size_t>(o.src_off + c) * p.coll_stride;
-          // dist(q) ~ d0 + g.(q - q0);  constraint: coeff*(margin - dist) <= 0;  cost: hinge(margin - dist)*coeff
-          const double scale = is_cnt ? cr[D + 2] : 1.0;
+        nr += total;
+        n_aux += total * ((per == 1) ? 2 : 1);
+        nnzA += total * (o.order + 1 + ((per == 1) ? 2 : 1));
+      } else if (o.kind == OBJ_CART_POSE) {
+        const DevCartTerm& ct = p.cart_terms[o.term];
+        int nz = 0;
+        for (int k = lane; k < o.n_rows; k += 32) {
+          double* R = q.R(nr + k);
+          int* I = q.rints + static_cast<size_t>(nr + k) * RI_NINTS;
+          const double* J = cart_jac + static_cast<size_t>(o.src_off + k) * p.cart_stride;
+          const double thr = 1e-7 * fabs(ct.coeff[k]);  // cleanupAff acts on the unscaled gradient (modeling_utils.cpp:31-39)
           double dot = 0.0;
           for (int j = 0; j < D; ++j) {
-            dot += cr[j] * q.x[o.first * D + j];
-            const double a = -cr[j] * scale;
+            dot += J[j] * q.x[o.first * D + j];
+            const double a = (fabs(J[j]) > thr) ? J[j] : 0.0;
             R[j] = a;
             nz += (a != 0.0);
           }
-          R[q.CN + F_C] = (cr[D + 1] - cr[D] + dot) * scale;
-          R[q.CN + F_W] = is_cnt ? w_aux : cr[D + 2];
-          I[RI_BASE] = o.first * D; I[RI_CNT] = D; I[RI_STRIDE] = 1; I[RI_AUX] = AUX_HINGE; I[RI_OBJ] = oi; I[RI_PAD] = o.first;
+          R[2 * q.CN + R_C] = cart_err[o.src_off + k] - dot;
+          R[2 * q.CN + R_W] = w_aux;
+          I[RI_BASE] = o.first * D; I[RI_CNT] = D; I[RI_STRIDE] = 1; I[RI_AUX] = AUX_ABS; I[RI_OBJ] = oi;
         }
-        count += __popc(bal);
+        nz = warp_sum_int(nz);
+        nr += o.n_rows;
+        n_aux += 2 * o.n_rows;
+        nnzA += nz + 2 * o.n_rows;
+      } else if (o.kind == OBJ_COLL) {
+        // active candidates of this timestep, in candidate order (ballot compaction)
+        const unsigned long long* mw = coll_mask + static_cast<size_t>(coll_obj_counter) * p.coll_words;
+        ++coll_obj_counter;
+        int nz = 0, count = 0;
+        for (int c0 = 0; c0 < o.n_rows; c0 += 32) {
+          const int c = c0 + lane;
+          const bool act = (c < o.n_rows) && ((mw[c / 64] >> (c % 64)) & 1ull);
+          const unsigned bal = __ballot_sync(0xffffffffu, act);
+          if (act) {
+            const int pos = nr + count + __popc(bal & ((1u << lane) - 1u));
+            double* R = q.R(pos);
+            int* I = q.rints + static_cast<size_t>(pos) * RI_NINTS;
+            const double* cr = coll_rows + static_cast<size_t>(o.src_off + c) * p.coll_stride;
+            // dist(q) ~ d0 + g.(q - q0);  constraint: coeff*(margin - dist) <= 0;  cost: hinge(margin - dist)*coeff
+            const double scale = is_cnt ? cr[D + 2] : 1.0;
+            double dot = 0.0;
+            for (int j = 0; j < D; ++j) {
+              dot += cr[j] * q.x[o.first * D + j];
+              const double a = -cr[j] * scale;
+              R[j] = a;
+              nz += (a != 0.0);
+            }
+            R[2 * q.CN + R_C] = (cr[D + 1] - cr[D] + dot) * scale;
+            R[2 * q.CN + R_W] = is_cnt ? w_aux : cr[D + 2];
+            I[RI_BASE] = o.first * D; I[RI_CNT] = D; I[RI_STRIDE] = 1; I[RI_AUX] = AUX_HINGE; I[RI_OBJ] = oi;
+          }
+          count += __popc(bal);
+        }
+        nz = warp_sum_int(nz);
+        nr += count;
+        n_aux += count;
+        nnzA += nz + count;
       }
-      nz = warp_sum_int(nz);
-      nr += count;
-      n_aux += count;
-      nnzA += nz + count;
     }
-  }
-  if (lane == 0) obj_start[n_obj] = nr;
-  q.nrows = nr;
-  nnzA += N + n_aux;  // identity rows carrying the variable bounds
-  __syncwarp();
-  __threadfence_block();
+    if (lane == 0) obj_start[n_obj] = nr;
+    nnzA += N + n_aux;  // identity rows carrying the variable bounds
+    __syncwarp();
 
-  // ---- per-lane row lists: dense slot t (RI_PAD == t), sparse slot d (RI_PAD == -1-d) -----------------
-  {
-    // counts
-    int* ls = q.ls;
-    for (int sidx = lane; sidx < T + D; sidx += 32) {
-      const int key = (sidx < T) ? sidx : -1 - (sidx - T);
-      int cnt = 0;
-      for (int r = 0; r < nr; ++r) cnt += (q.rints[static_cast<size_t>(r) * RI_NINTS + RI_PAD] == key);
-      ls[sidx + 1] = cnt;
+    // ---- per-column entry lists (canonical row order inside every column) ---------------------------------
+    for (int i = lane; i <= q.Np; i += 32) colptr[i] = 0;
+    __syncwarp();
+    for (int r = lane; r < nr; r += 32) {
+      const int* I = q.I(r);
+      for (int k = 0; k < I[RI_CNT]; ++k) atomicAdd(&colptr[I[RI_BASE] + k * I[RI_STRIDE] + 1], 1);
     }
-    if (lane == 0) ls[0] = 0;
     __syncwarp();
     if (lane == 0)
-      for (int sidx = 0; sidx < T + D; ++sidx) ls[sidx + 1] += ls[sidx];
+      for (int i = 0; i < q.Np; ++i) colptr[i + 1] += colptr[i];
     __syncwarp();
-    for (int sidx = lane; sidx < T + D; sidx += 32) {
-      const int key = (sidx < T) ? sidx : -1 - (sidx - T);
-      int pos = ls[sidx];
-      for (int r = 0; r < nr; ++r)
-        if (q.rints[static_cast<size_t>(r) * RI_NINTS + RI_PAD] == key) mylist[pos++] = r;
+    {
+      int* fill = reinterpret_cast<int*>(q.v2);  // Np ints of scratch
+      for (int i = lane; i < q.Np; i += 32) fill[i] = colptr[i];
+      __syncwarp();
+      for (int r = 0; r < nr; ++r) {  // serial over rows keeps every column in canonical row order
+        const int* I = q.I(r);
+        if (lane < I[RI_CNT]) {
+          const int var = I[RI_BASE] + lane * I[RI_STRIDE];
+          colent[fill[var]++] = (r << 5) | lane;
+        }
+        __syncwarp();
+      }
+    }
+    q.nrows = nr;
+
+    // ---- warm start decision (createOrUpdateSolver, osqp_interface.cpp:283-370) ---------------------------
+    warm = !x_override && p.qp.warm_starting && meta[3] == 1 && meta[0] == n_aux && meta[1] == nr && meta[2] == nnzA;
+    qp_scale(q, p.qp, qs, lbs, ubs, n_aux);
+  } else {
+    nr = meta[5];
+    n_aux = meta[6];
+    nnzA = meta[7];
+    q.nrows = nr;
+    rs.iter = p.rs_int[b * 4 + 0];
+    rs.round = p.rs_int[b * 4 + 1];
+    rs.rho_updates = p.rs_int[b * 4 + 2];
+    rs.rho = p.rs_dbl[b * 4 + 0];
+    rs.eps_scale = p.rs_dbl[b * 4 + 1];
+    rs.c = p.rs_dbl[b * 4 + 2];
+    q.c = rs.c;
+    q.cinv = 1.0 / q.c;
+    for (int i = lane; i < q.Np; i += 32) {
+      q.x[i] = park[i];
+      q.zb[i] = park[q.Np + i];
+      q.yb[i] = park[2 * q.Np + i];
+      q.Dz[i] = park[3 * q.Np + i];
+      q.beta[i] = park[4 * q.Np + i];
     }
     __syncwarp();
-    __threadfence_block();
   }
 
-  // ---- warm start decision (createOrUpdateSolver, osqp_interface.cpp:283-370) ---------------------------
-  int* meta = p.ws_meta + static_cast<size_t>(b) * 4;
-  const bool warm = !x_override && p.qp.warm_starting && meta[3] == 1 && meta[0] == n_aux && meta[1] == nr && meta[2] == nnzA;
-  const double warm_rho = p.ws_rho[b];
+  QpOut res = qp_solve_warp(q, p.qp, !resume, warm, p.ws_rho[b], p.ws_x + static_cast<size_t>(b) * N,
+                            p.ws_yb + static_cast<size_t>(b) * N, rs, x_override ? (1 << 30) : slice);
 
-  QpOut res = qp_solve_warp(q, p.qp, warm, warm_rho, p.ws_x + static_cast<size_t>(b) * N, p.ws_yb + static_cast<size_t>(b) * N, n_aux);
+  if (res.status == QPS_YIELD) {  // park the solve
+    for (int i = lane; i < q.Np; i += 32) {
+      park[i] = q.x[i];
+      park[q.Np + i] = q.zb[i];
+      park[2 * q.Np + i] = q.yb[i];
+      park[3 * q.Np + i] = q.Dz[i];
+      park[4 * q.Np + i] = q.beta[i];
+    }
+    if (lane == 0) {
+      meta[4] = 1; meta[5] = nr; meta[6] = n_aux; meta[7] = nnzA;
+      p.rs_int[b * 4 + 0] = rs.iter; p.rs_int[b * 4 + 1] = rs.round; p.rs_int[b * 4 + 2] = rs.rho_updates;
+      p.rs_dbl[b * 4 + 0] = rs.rho; p.rs_dbl[b * 4 + 1] = rs.eps_scale; p.rs_dbl[b * 4 + 2] = rs.c;
+    }
+    return;
+  }
 
   // ---- unscale, store the solution (and the warm-start state), model values -----------------------------
   double* nx = p.new_x + static_cast<size_t>(b) * N;
@@ -1150,33 +1287,33 @@ __global__ void __launch_bounds__(32) qp_kernel(DevProblem p, const double* x_ov
     nx[i] = xu;
     q.v1[i] = xu;  // unscaled solution for the model-value pass
     p.ws_x[static_cast<size_t>(b) * N + i] = xu;
-    p.ws_yb[static_cast<size_t>(b) * N + i] = q.cinv * q.Eb[i] * q.yb[i];
+    p.ws_yb[static_cast<size_t>(b) * N + i] = q.cinv * (q.beta[i] / q.Dz[i]) * q.yb[i];
   }
   __syncwarp();
-  q.for_rows([&](int r) {
+  for (int r = lane; r < nr; r += 32) {
     double* R = q.R(r);
-    double* F = R + q.CN;
+    double* F = q.F(r);
     const int* I = q.I(r);
     const int aux = I[RI_AUX];
-    F[F_Y] = q.cinv * F[F_E] * F[F_Y];
+    F[R_Y] = q.cinv * F[R_E] * F[R_Y];
     for (int k = 0; k < 2; ++k) {
-      F[F_XA0 + k] = (k < aux) ? F[F_DA0 + k] * F[F_XA0 + k] : 0.0;
-      F[F_YA0 + k] = (k < aux) ? q.cinv * F[F_EA0 + k] * F[F_YA0 + k] : 0.0;
+      F[R_XA0 + k] = (k < aux) ? F[R_DA0 + k] * F[R_XA0 + k] : 0.0;
+      F[R_YA0 + k] = (k < aux) ? q.cinv * F[R_EA0 + k] * F[R_YA0 + k] : 0.0;
     }
-    double val = F[F_C];
+    double val = F[R_C];
     for (int i = 0; i < I[RI_CNT]; ++i) val += R[i] * q.v1[I[RI_BASE] + i * I[RI_STRIDE]];
     // ConvexConstraints::violations (modeling.cpp:132-142) for constraint rows; hinge/abs cost = w * aux values
-    F[F_MV] = (aux == AUX_ABS || aux == AUX_NONE) ? fabs(val) : fmax(val, 0.0);
-  });
-  // per object sums, canonical order, one lane per object (deterministic)
-  for (int oi = lane; oi < n_obj; oi += 32) {
+    F[R_MV] = (aux == AUX_ABS || aux == AUX_NONE) ? fabs(val) : fmax(val, 0.0);
+  }
+  __syncwarp();
+  for (int oi = lane; oi < n_obj; oi += 32) {  // per object sums, canonical order, one lane per object
     const bool is_cnt = oi >= p.n_costs;
     double s = 0.0;
     if (!is_cnt && p.cost_objs[oi].kind == OBJ_JOINT_EQ_COST) s = joint_obj_value(p, p.cost_objs[oi], q.v1);  // exact quadratic
     for (int r = obj_start[oi]; r < obj_start[oi + 1]; ++r) {
-      const double* F = q.R(r) + q.CN;
-      if (is_cnt) s += F[F_MV];
-      else s += F[F_W] * (F[F_XA0] + F[F_XA1]);  // ConvexObjective::value: the penalty terms use the aux values
+      const double* F = q.F(r);
+      if (is_cnt) s += F[R_MV];
+      else s += F[R_W] * (F[R_XA0] + F[R_XA1]);  // ConvexObjective::value: the penalty terms use the aux values
     }
     if (is_cnt) p.model_cnt_viols[static_cast<size_t>(b) * p.n_cnts + (oi - p.n_costs)] = s;
     else p.model_cost_vals[static_cast<size_t>(b) * p.n_costs + oi] = s;
@@ -1187,9 +1324,12 @@ __global__ void __launch_bounds__(32) qp_kernel(DevProblem p, const double* x_ov
     if (res.status == QPS_SOLVED || res.status == QPS_SOLVED_INACC) cvx = 0;
     else if (res.status >= QPS_PINF && res.status <= QPS_DINF_INACC) cvx = 1;
     p.qp_status[b] = cvx;
-    meta[0] = n_aux; meta[1] = nr; meta[2] = nnzA; meta[3] = (cvx == 0) ? 1 : 0;
+    meta[0] = n_aux; meta[1] = nr; meta[2] = nnzA; meta[3] = (cvx == 0) ? 1 : 0; meta[4] = 0;
     p.ws_rho[b] = res.rho;
-    if (!x_override) p.n_admm_iters[b] += res.iters;
+    if (!x_override) {
+      p.n_admm_iters[b] += res.iters;
+      p.qp_done[b] = 1;
+    }
     if (admm_iters_out) admm_iters_out[b] = res.iters;
     if (polish_out) polish_out[b] = res.polish;
     double* g = p.dbg + static_cast<size_t>(b) * 16;

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -67,6 +68,7 @@ struct tb200_problem {
   tb200_layout layout{};
   int B = 0, T = 0, D = 0, N = 0;
   size_t eval_smem = 0, qp_smem = 0;
+  int slice = 100;  // ADMM iterations per QP per launch (TB200_SLICE overrides)
   cudaStream_t stream = nullptr;
   tb200_timing timing{};
   // host copies of the flattened description
@@ -80,10 +82,10 @@ struct tb200_problem {
   DevBuf<DevCartTerm> cart_terms;
   DevBuf<int> fixed_vars;
   DevBuf<double> x, new_x, trust, merit_coeffs, cost_vals, cnt_viols, new_cost_vals, new_cnt_viols, model_cost_vals,
-      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace;
+      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace, park, rs_dbl;
   DevBuf<unsigned long long> coll_mask;
   DevBuf<int> status, sqp_iter, merit_round, qp_failures, qp_status, cur_buf, n_qp_solves, n_func_evals, n_admm_iters,
-      active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish, trace_len;
+      active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish, trace_len, rs_int, qp_done;
   std::vector<cudaEvent_t> events;
   ~tb200_problem() {
     for (auto e : events) cudaEventDestroy(e);
@@ -94,7 +96,7 @@ struct tb200_problem {
     x.release(); new_x.release(); trust.release(); merit_coeffs.release(); cost_vals.release(); cnt_viols.release();
     new_cost_vals.release(); new_cnt_viols.release(); model_cost_vals.release(); model_cnt_viols.release();
     cart_err.release(); cart_jac.release(); coll_rows.release(); rows.release(); ws_x.release(); ws_yb.release();
-    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
+    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); park.release(); rs_dbl.release(); rs_int.release(); qp_done.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
     sqp_iter.release(); merit_round.release(); qp_failures.release(); qp_status.release(); cur_buf.release();
     n_qp_solves.release(); n_func_evals.release(); n_admm_iters.release(); active_count.release(); row_ints.release();
     lists.release(); ws_meta.release(); tmp_iters.release(); tmp_polish.release();
@@ -342,7 +344,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.coll_stride = D + 3;
   dp.n_fixed = static_cast<int>(fixed.size());
   dp.max_rows = max_rows;
-  dp.row_stride = std::max(D, 3) + F_NFIELDS;
+  dp.row_stride = qp_row_stride(std::max(D, 3));
   dp.coll_words = std::max(1, (dp.L * dp.O + 63) / 64);
   dp.n_coll_objs = static_cast<int>(P->coll_objs.size());
   P->ex.n_cart_objs = static_cast<int>(P->cart_objs.size());
@@ -358,13 +360,16 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   // ---- kernel resources --------------------------------------------------------------------------------
   const EvalSmem es = eval_smem_layout(T, D, dp.L, P->ex.n_cart_objs, n_coll_cand, dp.n_coll_objs * dp.coll_words);
   P->eval_smem = static_cast<size_t>(es.total) * sizeof(double);
-  const QpSmem qs = qp_smem_layout(N, dp.HB, T, D);
+  const QpSmem qs = qp_smem_layout(N, 2 * D);
+  const int Np = qp_block_count(N, 2 * D) * 2 * D;
+  dp.list_stride = static_cast<size_t>(Np + 1) + static_cast<size_t>(max_rows) * std::max(D, 3) + dp.n_costs + dp.n_cnts + 2;
   P->qp_smem = static_cast<size_t>(qs.total) * sizeof(double);
   if (P->eval_smem > 227 * 1024 || P->qp_smem > 227 * 1024)
     return fail(TB200_ERR_UNSUPPORTED, "problem does not fit the 227 KB shared memory of one CTA");
   CK(cudaFuncSetAttribute(eval_convexify_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->eval_smem)));
   CK(cudaFuncSetAttribute(qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->qp_smem)));
   CK(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+  if (const char* e = std::getenv("TB200_SLICE")) P->slice = std::max(1, std::atoi(e));
 
   // ---- device buffers ------------------------------------------------------------------------------------
 #define ALLOC(buf, count) CK(P->buf.alloc(count))
@@ -397,8 +402,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   ALLOC(coll_rows, 2 * Bs * std::max(1, n_coll_cand) * (D + 3));
   ALLOC(coll_mask, 2 * Bs * std::max(1, dp.n_coll_objs * dp.coll_words));
   ALLOC(rows, Bs * max_rows * dp.row_stride); ALLOC(row_ints, Bs * max_rows * RI_NINTS);
-  ALLOC(lists, Bs * (2 * static_cast<size_t>(max_rows) + dp.n_costs + dp.n_cnts + 2));
-  ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 5 * N); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 4);
+  ALLOC(lists, Bs * dp.list_stride);
+  ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 8 * Np); ALLOC(park, Bs * 5 * Np); ALLOC(rs_int, Bs * 4); ALLOC(rs_dbl, Bs * 4); ALLOC(qp_done, Bs); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 8);
   ALLOC(status, Bs); ALLOC(sqp_iter, Bs); ALLOC(merit_round, Bs); ALLOC(qp_failures, Bs); ALLOC(qp_status, Bs);
   ALLOC(cur_buf, Bs); ALLOC(n_qp_solves, Bs); ALLOC(n_func_evals, Bs); ALLOC(n_admm_iters, Bs); ALLOC(active_count, 1);
   ALLOC(dbg, Bs * 16);
@@ -419,6 +424,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.cart_err = P->cart_err.p; dp.cart_jac = P->cart_jac.p; dp.coll_rows = P->coll_rows.p; dp.coll_mask = P->coll_mask.p;
   dp.rows = P->rows.p; dp.row_ints = P->row_ints.p; dp.lists = P->lists.p; dp.ws_x = P->ws_x.p; dp.ws_yb = P->ws_yb.p;
   dp.scratch = P->scratch.p; dp.ws_meta = P->ws_meta.p; dp.ws_rho = P->ws_rho.p; dp.dbg = P->dbg.p; dp.trace_len = P->trace_len.p; dp.trace = nullptr; dp.trace_cap = 0;
+  dp.park = P->park.p; dp.rs_int = P->rs_int.p; dp.rs_dbl = P->rs_dbl.p; dp.qp_done = P->qp_done.p;
   P->ex.cart_objs = P->d_cart_objs.p;
   P->ex.coll_objs = P->d_coll_objs.p;
   // settings
@@ -481,7 +487,8 @@ __global__ void reset_state_kernel(DevProblem p) {
   p.n_admm_iters[b] = 0;
   p.trust[b] = p.sqp.trust_box_size;
   for (int c = 0; c < p.n_cnts; ++c) p.merit_coeffs[static_cast<size_t>(b) * p.n_cnts + c] = p.sqp.initial_merit_error_coeff;
-  for (int k = 0; k < 4; ++k) p.ws_meta[b * 4 + k] = 0;
+  for (int k = 0; k < 8; ++k) p.ws_meta[b * 8 + k] = 0;
+  p.qp_done[b] = 0;
   p.ws_rho[b] = p.qp.rho;
   p.trace_len[b] = 0;
 }
@@ -520,20 +527,21 @@ int tb200_solve_batch_resident(tb200_problem* P) {
   auto launch_qp = [&]() {
     const size_t i0 = ne;
     cudaEventRecord(getEvent(P, ne++), st);
-    qp_kernel<<<dp.B, 32, P->qp_smem, st>>>(dp, nullptr, nullptr, nullptr, nullptr);
+    qp_kernel<<<dp.B, 32, P->qp_smem, st>>>(dp, nullptr, nullptr, nullptr, nullptr, P->slice);
     cudaEventRecord(getEvent(P, ne++), st);
     spans.push_back({i0, 1});
   };
   launch_eval(EVAL_INIT);
   // every trajectory needs at most this many QP solves (penalty rounds x SQP iterations x trust retries)
-  const long cap = static_cast<long>(std::ceil(dp.sqp.max_merit_coeff_increases)) * dp.sqp.max_iter * 12 + 64;
+  const long qp_cap = static_cast<long>(std::ceil(dp.sqp.max_merit_coeff_increases)) * dp.sqp.max_iter * 12 + 64;
+  const long cap = qp_cap * (dp.qp.max_iter / P->slice + 2);
   int active = dp.B;
   long steps = 0;
   while (active > 0 && steps < cap) {
     launch_qp();
     launch_eval(EVAL_STEP);
     ++steps;
-    if (steps % 2 == 0 || steps < 4) {
+    if (steps % 8 == 0) {
       CK(cudaMemcpyAsync(&active, dp.active_count, sizeof(int), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
     }
@@ -632,9 +640,9 @@ int tb200_qp_solve_batch(tb200_problem* P, const double* x, const double* trust,
   CK(cudaMemcpyAsync(P->x_tmp.p, x, B * dp.N * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(P->trust_tmp.p, trust, B * sizeof(double), cudaMemcpyHostToDevice, st));
   if (dp.n_cnts > 0) CK(cudaMemcpyAsync(P->merit_coeffs.p, merit_coeffs, B * dp.n_cnts * sizeof(double), cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(P->ws_meta.p, 0, B * 4 * sizeof(int), st));
+  CK(cudaMemsetAsync(P->ws_meta.p, 0, B * 8 * sizeof(int), st));
   eval_convexify_decide_kernel<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
-  qp_kernel<<<dp.B, 32, P->qp_smem, st>>>(dp, P->x_tmp.p, P->trust_tmp.p, P->tmp_iters.p, P->tmp_polish.p);
+  qp_kernel<<<dp.B, 32, P->qp_smem, st>>>(dp, P->x_tmp.p, P->trust_tmp.p, P->tmp_iters.p, P->tmp_polish.p, 1 << 30);
   CK(cudaGetLastError());
   auto pull = [&](void* dst, const void* src, size_t n) {
     if (!dst || n == 0) return cudaSuccess;
