@@ -127,8 +127,8 @@ struct DevProblem {
   size_t list_stride;
   double* ws_x;                // [B][N]  warm start: previous QP solution (trajectory part, unscaled)
   double* ws_yb;               // [B][N]  warm start: duals of the variable-bound rows (unscaled)
-  double* scratch;             // [B][8*Np]: dx dy stash(x zb yb) | scaled q, lb, ub of the trajectory variables
-  double* park;                // [B][5*Np]: x zb yb Dz beta of a QP parked between time slices
+  double* scratch;             // [B][10*Np]: dx dy stash(x zb yb) | scaled q, lb, ub | Dz | v2
+  double* park;                // [B][4*Np]: x zb yb beta of a QP parked between time slices
   int* rs_int;                 // [B][4] parked solver state
   double* rs_dbl;              // [B][4]
   int* qp_done;                // [B] 1: a QP solution is waiting for its evaluation

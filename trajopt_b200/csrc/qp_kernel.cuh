@@ -58,8 +58,9 @@ __device__ __forceinline__ double limit_scaling(double v) {
 
 // ---- shared memory layout (doubles) ------------------------------------------------------------------
 struct QpSmem {
-  int Kb, Linv, Dz, beta, x, zb, yb, v1, v2, total;
+  int Kb, Linv, beta, x, zb, yb, v1, qs, lbs, ubs, coef, colptr, total;
 };
+constexpr int kCoefCap = 64;  // rows whose scatter multiplier lives in shared memory (the rest use R_COEF)
 __host__ __device__ inline int qp_block_count(int N, int nb) { return (N + nb - 1) / nb; }
 __host__ __device__ inline QpSmem qp_smem_layout(int N, int nb) {
   const int M = qp_block_count(N, nb), Np = M * nb, Wd = nb + 2;
@@ -67,13 +68,16 @@ __host__ __device__ inline QpSmem qp_smem_layout(int N, int nb) {
   int o = 0;
   s.Kb = o;   o += Np * Wd;
   s.Linv = o; o += M * (nb * (nb + 1) / 2);
-  s.Dz = o;   o += Np;
   s.beta = o; o += Np;
   s.x = o;    o += Np;
   s.zb = o;   o += Np;
   s.yb = o;   o += Np;
   s.v1 = o;   o += Np;
-  s.v2 = o;   o += Np;
+  s.qs = o;   o += Np;
+  s.lbs = o;  o += Np;
+  s.ubs = o;  o += Np;
+  s.coef = o; o += kCoefCap;
+  s.colptr = o; o += (Np + 2) / 2 + 1;
   s.total = o;
   return s;
 }
@@ -94,19 +98,25 @@ __host__ __device__ inline int qp_row_stride(int CN) { return 2 * CN + R_NF; }
 
 struct QpCtx {
   int N, Np, nb, M, Wd, T, D, CN, RS, lane, nrows;
-  double *Kb, *Linv, *Dz, *beta, *x, *zb, *yb, *v1, *v2;   // shared
+  double *Kb, *Linv, *beta, *x, *zb, *yb, *v1, *qs, *lbs, *ubs, *coef;   // shared
+  int* colptr;           // shared [Np+1]
+  double *Dz, *v2;       // global [Np] (used by the residual / polish passes only)
   double* rows;          // global
   int* rints;
-  const int* colptr;     // [Np+1]
-  const int* colent;     // entries: (row << 5) | k
-  const double* Pband;   // [N][2D+1]
-  const double *qs, *lbs, *ubs;  // global [Np] scaled cost / bounds of the trajectory variables
+  const int* colent;     // global entries: (row << 5) | k
+  const double* Pband;   // global [N][2D+1]
   double* scratch;
   double c, cinv, rho, rho_eq, sigma, alpha;
   __device__ __forceinline__ double* R(int r) const { return rows + static_cast<size_t>(r) * RS; }
   __device__ __forceinline__ double* F(int r) const { return rows + static_cast<size_t>(r) * RS + 2 * CN; }
   __device__ __forceinline__ const int* I(int r) const { return rints + static_cast<size_t>(r) * RI_NINTS; }
 };
+
+__device__ __forceinline__ void set_coef(const QpCtx& q, int r, double v) {
+  if (r < kCoefCap) q.coef[r] = v;
+  else q.F(r)[R_COEF] = v;
+}
+__device__ __forceinline__ double get_coef(const QpCtx& q, int r) { return (r < kCoefCap) ? q.coef[r] : q.F(r)[R_COEF]; }
 
 // weights of the linear system: ADMM (rho vector, sigma) or polish (1/delta on the active set, delta)
 struct SysW {
@@ -315,8 +325,7 @@ __device__ __forceinline__ void scatter_columns(const QpCtx& q, Base base) {
       s = base(i);
       for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
         const int ent = q.colent[e], r = ent >> 5, k = ent & 31;
-        const double* R = q.R(r);
-        s += R[q.CN + k] * R[2 * q.CN + R_COEF];
+        s += __ldcg(q.R(r) + q.CN + k) * get_coef(q, r);
       }
     }
     q.v1[i] = s;
@@ -346,9 +355,10 @@ __device__ __forceinline__ double row_reduce_coef(const double* F, int naux, dou
 
 // Ruiz equilibration (scale_data of OSQP [EXT]); leaves the scaled view of every row in its record and the
 // scaled trajectory cost / bounds in qs / lbs / ubs (global), Dz / beta in shared memory.
-__device__ inline void qp_scale(QpCtx& q, const QpSettings& st, double* qs, double* lbs, double* ubs, int n_aux_total) {
+__device__ inline void qp_scale(QpCtx& q, const QpSettings& st, int n_aux_total) {
+  double *qs = q.qs, *lbs = q.lbs, *ubs = q.ubs;
   const int N = q.N, lane = q.lane, HB = 2 * q.D, W = HB + 1;
-  double* Eb = q.v2;  // bound-row scalings live in v2 during scaling
+  double* Eb = q.zb;  // bound-row scalings live in zb during scaling
   q.c = 1.0;
   for (int i = lane; i < q.Np; i += 32) {
     q.Dz[i] = 1.0;
@@ -630,7 +640,7 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool fresh
       if (naux == AUX_HINGE) d = fmax(d, 0.0);  // l = -inf
       nd = fmax(nd, fabs(F[R_E] * d));
       lhs += F[R_UP] * fmax(d, 0.0) + F[R_LO] * fmin(d, 0.0);
-      F[R_COEF] = d;  // projected dual step, consumed by the column pass
+      set_coef(q, r, d);  // projected dual step, consumed by the column pass
       for (int k = 0; k < naux; ++k) {
         const double da = fmin(F[R_DYA0 + k], 0.0);  // aux bound rows: u = +inf, l = 0
         nd = fmax(nd, fabs(F[R_EA0 + k] * da));
@@ -744,7 +754,7 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool fresh
         const double s = F[R_WRR] * F[R_Z] - F[R_Y];
         if (naux >= 1) F[R_RA0] = q.sigma * F[R_XA0] - F[R_QA0] + F[R_U0] * s + F[R_B0] * (sysw.rho_aux * F[R_ZA0] - F[R_YA0]);
         if (naux == 2) F[R_RA1] = q.sigma * F[R_XA1] - F[R_QA1] + F[R_U1] * s + F[R_B1] * (sysw.rho_aux * F[R_ZA1] - F[R_YA1]);
-        F[R_COEF] = row_reduce_coef(F, naux, s);
+        set_coef(q, r, row_reduce_coef(F, naux, s));
       }
       __syncwarp();
       // ---- right-hand side  sigma x - q + A'(rho z - y)  (one lane per variable) ----------------------
@@ -913,7 +923,7 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool fresh
           m_dua = fmax(m_dua, fabs((qa + u * F[R_PY] + bb * F[R_PYA0 + k]) / F[R_DA0 + k]));
           F[R_RA0 + k] = -qa - u * e - bb * ea[k];
         }
-        F[R_COEF] = last ? F[R_PY] : row_reduce_coef(F, naux, -e);
+        set_coef(q, r, last ? F[R_PY] : row_reduce_coef(F, naux, -e));
       }
       __syncwarp();
       if (last) {
@@ -1041,7 +1051,7 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool fresh
 // ---------------------------------------------------------------------------------------------------
 // Kernel: QP assembly (optimizers.cpp:781-799 + osqp_interface.cpp:170-281 in fixed layout) + solve slice.
 // grid = B, block = 32 (one warp per trajectory).
-__global__ void __launch_bounds__(32) qp_kernel(DevProblem p, const double* x_override /*kernel-level API*/,
+__global__ void __launch_bounds__(32, 4) qp_kernel(DevProblem p, const double* x_override /*kernel-level API*/,
                                                 const double* trust_override, int* admm_iters_out,
                                                 int* polish_out, int slice) {
   extern __shared__ double sm[];
@@ -1058,24 +1068,28 @@ __global__ void __launch_bounds__(32) qp_kernel(DevProblem p, const double* x_ov
   const QpSmem S = qp_smem_layout(N, q.nb);
   q.CN = (p.row_stride - R_NF) / 2;
   q.RS = p.row_stride;
-  q.Kb = sm + S.Kb; q.Linv = sm + S.Linv; q.Dz = sm + S.Dz; q.beta = sm + S.beta;
-  q.x = sm + S.x; q.zb = sm + S.zb; q.yb = sm + S.yb; q.v1 = sm + S.v1; q.v2 = sm + S.v2;
+  q.Kb = sm + S.Kb; q.Linv = sm + S.Linv; q.beta = sm + S.beta;
+  q.x = sm + S.x; q.zb = sm + S.zb; q.yb = sm + S.yb; q.v1 = sm + S.v1;
+  q.qs = sm + S.qs; q.lbs = sm + S.lbs; q.ubs = sm + S.ubs; q.coef = sm + S.coef;
+  q.colptr = reinterpret_cast<int*>(sm + S.colptr);
   q.rows = p.rows + static_cast<size_t>(b) * p.max_rows * p.row_stride;
   q.rints = p.row_ints + static_cast<size_t>(b) * p.max_rows * RI_NINTS;
   int* mylist = p.lists + static_cast<size_t>(b) * p.list_stride;
-  int* colptr = mylist;                                   // [Np+1]
+  int* colptr = mylist;                                   // [Np+1] master copy (shared copy in q.colptr)
   int* colent = mylist + q.Np + 1;                        // [max_rows*CN]
   int* obj_start = colent + static_cast<size_t>(p.max_rows) * q.CN;  // [n_objs+1]
-  q.colptr = colptr;
   q.colent = colent;
   q.Pband = p.Pband;
-  double* gvec = p.scratch + static_cast<size_t>(b) * 8 * q.Np;  // dxs dyb st_x st_zb st_yb | qs lbs ubs
+  // per-trajectory global vectors: dxs dyb st_x st_zb st_yb | scaled qs lbs ubs (master) | Dz | v2
+  double* gvec = p.scratch + static_cast<size_t>(b) * 10 * q.Np;
   q.scratch = gvec;
-  double* qs = gvec + 5 * q.Np;
-  double* lbs = gvec + 6 * q.Np;
-  double* ubs = gvec + 7 * q.Np;
-  double* park = p.park + static_cast<size_t>(b) * 5 * q.Np;     // x zb yb Dz beta of a parked solve
-  q.qs = qs; q.lbs = lbs; q.ubs = ubs;
+  double* g_qs = gvec + 5 * q.Np;
+  double* g_lbs = gvec + 6 * q.Np;
+  double* g_ubs = gvec + 7 * q.Np;
+  q.Dz = gvec + 8 * q.Np;
+  q.v2 = gvec + 9 * q.Np;
+  double* park = p.park + static_cast<size_t>(b) * 4 * q.Np;     // x zb yb beta of a parked solve
+  double *qs = q.qs, *lbs = q.lbs, *ubs = q.ubs;
   int* meta = p.ws_meta + static_cast<size_t>(b) * 8;  // 0..3 warm-start key, 4 phase, 5 nrows, 6 n_aux, 7 nnzA
   const int n_obj = p.n_costs + p.n_cnts;
   QpResume rs{};
@@ -1221,7 +1235,7 @@ __global__ void __launch_bounds__(32) qp_kernel(DevProblem p, const double* x_ov
       for (int i = 0; i < q.Np; ++i) colptr[i + 1] += colptr[i];
     __syncwarp();
     {
-      int* fill = reinterpret_cast<int*>(q.v2);  // Np ints of scratch
+      int* fill = reinterpret_cast<int*>(q.v1);  // Np ints of scratch
       for (int i = lane; i < q.Np; i += 32) fill[i] = colptr[i];
       __syncwarp();
       for (int r = 0; r < nr; ++r) {  // serial over rows keeps every column in canonical row order
@@ -1234,10 +1248,17 @@ __global__ void __launch_bounds__(32) qp_kernel(DevProblem p, const double* x_ov
       }
     }
     q.nrows = nr;
+    for (int i = lane; i <= q.Np; i += 32) q.colptr[i] = colptr[i];
+    __syncwarp();
 
     // ---- warm start decision (createOrUpdateSolver, osqp_interface.cpp:283-370) ---------------------------
     warm = !x_override && p.qp.warm_starting && meta[3] == 1 && meta[0] == n_aux && meta[1] == nr && meta[2] == nnzA;
-    qp_scale(q, p.qp, qs, lbs, ubs, n_aux);
+    qp_scale(q, p.qp, n_aux);
+    for (int i = lane; i < q.Np; i += 32) {  // master copies for the resume path
+      g_qs[i] = qs[i];
+      g_lbs[i] = lbs[i];
+      g_ubs[i] = ubs[i];
+    }
   } else {
     nr = meta[5];
     n_aux = meta[6];
@@ -1255,9 +1276,12 @@ __global__ void __launch_bounds__(32) qp_kernel(DevProblem p, const double* x_ov
       q.x[i] = park[i];
       q.zb[i] = park[q.Np + i];
       q.yb[i] = park[2 * q.Np + i];
-      q.Dz[i] = park[3 * q.Np + i];
-      q.beta[i] = park[4 * q.Np + i];
+      q.beta[i] = park[3 * q.Np + i];
+      qs[i] = g_qs[i];
+      lbs[i] = g_lbs[i];
+      ubs[i] = g_ubs[i];
     }
+    for (int i = lane; i <= q.Np; i += 32) q.colptr[i] = colptr[i];
     __syncwarp();
   }
 
@@ -1269,8 +1293,7 @@ __global__ void __launch_bounds__(32) qp_kernel(DevProblem p, const double* x_ov
       park[i] = q.x[i];
       park[q.Np + i] = q.zb[i];
       park[2 * q.Np + i] = q.yb[i];
-      park[3 * q.Np + i] = q.Dz[i];
-      park[4 * q.Np + i] = q.beta[i];
+      park[3 * q.Np + i] = q.beta[i];
     }
     if (lane == 0) {
       meta[4] = 1; meta[5] = nr; meta[6] = n_aux; meta[7] = nnzA;
