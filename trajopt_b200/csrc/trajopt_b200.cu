@@ -682,6 +682,14 @@ int tb200_debug_fetch_trace(tb200_problem* P, double* out, int32_t* len) {
   return TB200_OK;
 }
 
+#ifdef TB200_PROFILE
+int tb200_debug_prof(unsigned long long* out, int reset) {
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); return 0; }
+  cudaMemcpyFromSymbol(out, g_prof, 16 * sizeof(unsigned long long));
+  return 0;
+}
+#endif
+
 /* not part of the public header: solver diagnostics of the last QP of every trajectory, [B][16] */
 int tb200_debug_last_qp(tb200_problem* P, double* out) {
   if (!P || !out) return fail(TB200_ERR_INVALID, "null argument");
