@@ -544,6 +544,8 @@ QPResult qp_solve(const QP& qp, const QPSettings& s, const QPWarmStart* warm) {
   };
 
   int status = QP_UNSOLVED, iter = 0;
+  bool early_verified = false;
+  std::function<bool(bool&)> polishOnce;
   // ADMM iterations, continuing from the current state until a termination test fires or max_iter.
   auto runAdmm = [&]() {
     status = QP_UNSOLVED;
@@ -574,6 +576,26 @@ QPResult qp_solve(const QP& qp, const QPSettings& s, const QPWarmStart* warm) {
         updateInfo();
         status = checkTermination(false);
         if (status != QP_UNSOLVED) return;
+        if (s.early_polish_every > 0 && iter >= s.early_polish_from && (iter % s.early_polish_every == 0)) {
+          // optimisation O1: try the polish before ADMM has met its own tolerances; a VERIFIED polished point is
+          // the exact minimiser no matter how rough the iterate that produced the active-set guess was
+          bool verified = false;
+          const double keep_pri = pri_res, keep_dua = dua_res;
+          const bool factored = polishOnce(verified);
+          ++res.early_tries;
+          if (factored && verified) {
+            early_verified = true;
+            status = QP_SOLVED;
+            return;
+          }
+          (void)keep_pri;
+          (void)keep_dua;
+          updateInfo();  // the polish scratch vectors are shared with the residual bookkeeping
+          if (!w.assemble(s.sigma, w.rho_vec)) {
+            status = QP_NON_CVX;
+            return;
+          }
+        }
       }
       if (s.adaptive_rho && s.adaptive_rho_interval > 0 && (iter % s.adaptive_rho_interval == 0)) {
         if (!can_check) updateInfo();
@@ -614,7 +636,7 @@ QPResult qp_solve(const QP& qp, const QPSettings& s, const QPWarmStart* warm) {
   // acceptance rule is used.  verify_rounds = 0 is plain OSQP behaviour.
   Vec wact(m), b(m), xq(n), yq(m), rd(n), step(n);
   double pp = 0, pdres = 0;
-  auto polishOnce = [&](bool& verified) -> bool {
+  polishOnce = [&](bool& verified) -> bool {
     verified = false;
     for (int r = 0; r < m; ++r) {
       int a = 0;
@@ -667,6 +689,10 @@ QPResult qp_solve(const QP& qp, const QPSettings& s, const QPWarmStart* warm) {
     admm_pri = pri_res;
     admm_dua = dua_res;
     if (status != QP_SOLVED || !s.polishing) break;
+    if (early_verified) {
+      res.polish = 1;
+      break;
+    }
     bool verified = false;
     const bool factored = polishOnce(verified);
     res.pdas = round;

@@ -102,6 +102,8 @@ struct QPSettings {
   int warm_starting = 1;
   int verify_rounds = 3;     // verified-polish retries with 10x tighter ADMM tolerances (0 = plain OSQP polish)
   double verify_tol = 1e-9;  // KKT verification: primal feasibility and multiplier-sign tolerance
+  int early_polish_every = 0;  // >0: also try the (verified) polish every this many iterations (optimisation O1)
+  int early_polish_from = 50;
 };
 enum QPStatus {
   QP_SOLVED = 1,
@@ -127,6 +129,7 @@ struct QPResult {
   int rho_updates = 0;
   int polish = 0;  // 1 accepted (KKT fixed point), 2 accepted by residual rule only, -1 rejected, 0 not attempted
   int pdas = 0;    // verified-polish rounds used
+  int early_tries = 0;
   double pri_res = 0, dua_res = 0;
   double admm_pri = 0, admm_dua = 0;
   double rho = 0.1;

@@ -79,7 +79,7 @@ __device__ __forceinline__ double limit_scaling(double v) {
 
 // ---- shared memory layout (doubles) ------------------------------------------------------------------
 struct QpSmem {
-  int Kb, Linv, beta, x, zb, yb, v1, qs, lbs, ubs, colptr, maxcol, total;
+  int Kb, Linv, beta, x, zb, yb, v1, qs, lbs, ubs, xch, colptr, maxcol, total;
 };
 __host__ __device__ inline int qp_block_count(int N, int nb) { return (N + nb - 1) / nb; }
 __host__ __device__ inline QpSmem qp_smem_layout(int N, int nb) {
@@ -96,6 +96,7 @@ __host__ __device__ inline QpSmem qp_smem_layout(int N, int nb) {
   s.qs = o;   o += Np;
   s.lbs = o;  o += Np;
   s.ubs = o;  o += Np;
+  s.xch = o;  o += 32;  // two 16-double exchange buffers of the block solve
   s.colptr = o; o += (Np + 2) / 2 + 1;
   s.maxcol = o; o += ((Np + 31) / 32 + 1) / 2 + 1;
   s.total = o;
@@ -110,6 +111,7 @@ enum RowF {
   R_U0, R_U1, R_B0, R_B1, R_LO, R_UP, R_QA0, R_QA1, R_RHO,  // scaled view (R_RHO: 1 = equality row)
   R_XA0, R_XA1, R_Z, R_Y, R_ZA0, R_ZA1, R_YA0, R_YA1,        // ADMM state
   R_RA0, R_RA1, R_COEF, R_WR, R_G0, R_G1, R_DEN, R_WRR,      // per-solve temporaries (WRR: raw row weight)
+  R_IDEN, R_IWRR,                                            // reciprocals of DEN / WRR (0 when WRR == 0)
   R_DY, R_DYA0, R_DYA1, R_DXA0, R_DXA1,
   R_PW, R_PWA0, R_PWA1, R_PB, R_PY, R_PYA0, R_PYA1, R_PX0, R_PX1,  // polish
   R_MV,
@@ -120,7 +122,7 @@ __host__ __device__ inline int qp_row_stride(int CN) { return 2 * CN + R_NF; }
 struct QpCtx {
   int N, Np, nb, M, Wd, T, D, CN, RS, lane, nrows;
   int npl, nrl;          // uniform trip counts of the per-variable / per-row lane loops
-  double *Kb, *Linv, *beta, *x, *zb, *yb, *v1, *qs, *lbs, *ubs;   // shared
+  double *Kb, *Linv, *beta, *x, *zb, *yb, *v1, *qs, *lbs, *ubs, *xch;   // shared
   int* colptr;           // shared [Np+1]
   int* maxcol;           // shared [npl]: longest column of each 32-variable chunk
   double *Dz, *v2;       // global [Np] (used by the residual / polish passes only)
@@ -199,7 +201,7 @@ __device__ inline bool band_factor(const QpCtx& q) {
 }
 
 // Solves K v = v in place (v in shared memory, length Np) with the block factor.
-__device__ inline void block_solve(const QpCtx& q, double* v) {
+__device__ inline void block_solve_generic(const QpCtx& q, double* v) {
   const int nb = q.nb, W = q.Wd, M = q.M, tri = nb * (nb + 1) / 2;
   const int halves = (nb <= 16) ? 2 : 1;
   const int r = (halves == 2) ? (q.lane & 15) : q.lane;      // block row handled by this lane
@@ -273,6 +275,98 @@ __device__ inline void block_solve(const QpCtx& q, double* v) {
   __syncwarp();
 }
 
+// Fast path of the block solve for nb = NB <= 16 (two lanes per block row, CH columns each), fully unrolled.
+// The block vectors travel through two small shared exchange buffers (half 0 at [0,CH), half 1 at [8,8+CH)).
+template <int NB>
+__device__ __forceinline__ void block_solve_t(const QpCtx& q, double* v) {
+  constexpr int CH = (NB + 1) / 2;
+  constexpr int TRI = NB * (NB + 1) / 2;
+  const int W = q.Wd, M = q.M;
+  const int r = q.lane & 15, h = q.lane >> 4;
+  const bool rowok = r < NB;
+  const int ra = rowok ? r : 0;             // row used for addressing
+  const int rge = rowok ? r : 1 << 20;      // "c >= r" never true for idle lanes
+  const int rle = rowok ? r : -1;           // "c <= r" never true for idle lanes
+  const int c0 = h * CH;
+  const bool writer = rowok && h == 0;
+  const int xi = (ra < CH) ? ra : 8 + ra - CH;   // slot of element `ra` in an exchange buffer
+  double* xa = q.xch;
+  double* xb = q.xch + 16;
+  const double* seg_a = xa + h * 8;
+  const double* seg_b = xb + h * 8;
+  int ltri[CH];                              // packed-triangle offsets of Linv[c][ra], c = c0 + j
+#pragma unroll
+  for (int j = 0; j < CH; ++j) ltri[j] = (c0 + j) * (c0 + j + 1) / 2 + ra;
+  __syncwarp();
+  // ---- forward: y_i = Linv_i (b_i - W_i y_{i-1})
+  double yseg[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) yseg[j] = 0.0;
+  const double* Wrow = q.Kb + ra * W + NB + ra - c0;        // W_i[ra][c0+j] = Wrow[i*NB*W - j]
+  const double* Lrow = q.Linv + ra * (ra + 1) / 2 + c0;     // Linv_i[ra][c0+j] = Lrow[i*TRI + j]
+  for (int i = 0; i < M; ++i) {
+    double t = v[i * NB + ra];
+    if (i > 0) {
+      const double* wp = Wrow + i * NB * W;
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (c0 + j >= rge && c0 + j < NB) acc = fma(wp[-j], yseg[j], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+      t -= acc;
+    }
+    if (writer) xa[xi] = t;
+    __syncwarp();
+    const double* lp = Lrow + i * TRI;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (c0 + j <= rle) acc = fma(lp[j], seg_a[j], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (writer) {
+      v[i * NB + ra] = acc;
+      xb[xi] = acc;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < CH; ++j) yseg[j] = seg_b[j];
+  }
+  // ---- backward: x_i = Linv_i' (y_i - W_{i+1}' x_{i+1});  yseg now holds y_{M-1}, reused as x_{i+1} below
+  const double* Wcol = q.Kb + c0 * (W + 1) + NB - ra;        // W_{i+1}[c0+j][ra] = Wcol[(i+1)*NB*W + j*(W+1)]
+  for (int i = M - 1; i >= 0; --i) {
+    double t = v[i * NB + ra];
+    if (i < M - 1) {
+      const double* wp = Wcol + (i + 1) * NB * W;
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (c0 + j <= rle) acc = fma(wp[j * (W + 1)], yseg[j], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+      t -= acc;
+    }
+    if (writer) xa[xi] = t;
+    __syncwarp();
+    const double* lp = q.Linv + i * TRI;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (c0 + j >= rge && c0 + j < NB) acc = fma(lp[ltri[j]], seg_a[j], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (writer) {
+      v[i * NB + ra] = acc;
+      xb[xi] = acc;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < CH; ++j) yseg[j] = seg_b[j];
+  }
+}
+
+__device__ __forceinline__ void block_solve(const QpCtx& q, double* v) {
+  if (q.nb == 14) block_solve_t<14>(q, v);
+  else block_solve_generic(q, v);
+}
+
 // variable index of coefficient k of a row (padding coefficients alias the last real one; their value is 0)
 __device__ __forceinline__ int row_var(const int* I, int k) {
   return I[RI_BASE] + min(k, I[RI_CNT] - 1) * I[RI_STRIDE];
@@ -322,6 +416,8 @@ __device__ inline void rows_prepare_weights(const QpCtx& q, const SysW& w) {
       F[R_G0] = g0;
       F[R_G1] = g1;
       F[R_DEN] = den;
+      F[R_IDEN] = 1.0 / den;
+      F[R_IWRR] = (Wr != 0.0) ? 1.0 / Wr : 0.0;
       F[R_WR] = Wr * g0 * g1 / den;
     }
   }
@@ -412,11 +508,12 @@ __device__ __forceinline__ double row_dot(const QpCtx& q, const double* R, const
 // aux back-substitution (cancellation free; absent aux slots have u = ra = 0 and g = 1 and come out 0)
 __device__ __forceinline__ void row_backsub(const double* F, double zeta, double& a0, double& a1) {
   const double Wr = F[R_WRR], ra0 = F[R_RA0], ra1 = F[R_RA1], u0 = F[R_U0], u1 = F[R_U1];
-  a0 = (F[R_G1] * (ra0 - Wr * u0 * zeta) + Wr * u1 * (u1 * ra0 - u0 * ra1)) / F[R_DEN];
-  a1 = (F[R_G0] * (ra1 - Wr * u1 * zeta) + Wr * u0 * (u0 * ra1 - u1 * ra0)) / F[R_DEN];
+  const double iden = F[R_IDEN];
+  a0 = (F[R_G1] * (ra0 - Wr * u0 * zeta) + Wr * u1 * (u1 * ra0 - u0 * ra1)) * iden;
+  a1 = (F[R_G0] * (ra1 - Wr * u1 * zeta) + Wr * u0 * (u0 * ra1 - u1 * ra0)) * iden;
 }
 __device__ __forceinline__ double row_reduce_coef(const double* F, double ra0, double ra1, double zcoef) {
-  return zcoef - F[R_WRR] * (F[R_U0] * ra0 * F[R_G1] + F[R_U1] * ra1 * F[R_G0]) / F[R_DEN];
+  return zcoef - F[R_WRR] * (F[R_U0] * ra0 * F[R_G1] + F[R_U1] * ra1 * F[R_G0]) * F[R_IDEN];
 }
 
 // Ruiz equilibration (scale_data of OSQP [EXT]); leaves the scaled view of every row in its record and the
@@ -867,10 +964,11 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool fresh
       const double zt = zeta + F[R_U0] * a0 + F[R_U1] * a1;
       const double Wr = F[R_WRR];
       const double zr = q.alpha * zt + (1.0 - q.alpha) * F[R_Z];
-      double zn = zr + F[R_Y] / Wr;
+      double zn = zr + F[R_Y] * F[R_IWRR];
       zn = fmin(fmax(zn, F[R_LO]), F[R_UP]);
       const double dy = Wr * (zr - zn);
       double xn[2], dxa[2], zan[2], dya[2];
+      const double inv_rho_aux = 1.0 / sysw.rho_aux;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const double at = k ? a1 : a0, bb = F[R_B0 + k];
@@ -878,7 +976,7 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool fresh
         xn[k] = q.alpha * at + (1.0 - q.alpha) * xo;
         dxa[k] = xn[k] - xo;
         const double zra = q.alpha * (bb * at) + (1.0 - q.alpha) * F[R_ZA0 + k];
-        double z2 = zra + F[R_YA0 + k] / sysw.rho_aux;
+        double z2 = zra + F[R_YA0 + k] * inv_rho_aux;
         z2 = fmin(fmax(z2, 0.0), kOsqpInf * F[R_EA0 + k]);
         zan[k] = z2;
         dya[k] = sysw.rho_aux * (zra - z2);
@@ -900,17 +998,19 @@ __device__ inline QpOut qp_solve_warp(QpCtx& q, const QpSettings& st, bool fresh
     PROF_ADD(3); }
     { PROF_T0();
     // trajectory variables and their bound rows
+    const double inv_rho = 1.0 / q.rho, inv_rho_eq = 1.0 / q.rho_eq;
     for (int kk = 0; kk < q.npl; ++kk) {
       const int iraw = lane + 32 * kk;
       const bool act = iraw < N;
       const int i = act ? iraw : 0;
       const double beta = q.beta[i];
       const double lb = q.lbs[i], ub = q.ubs[i];
-      const double rb = (ub - lb < kRhoTol) ? q.rho_eq : q.rho;
+      const bool beq = ub - lb < kRhoTol;
+      const double rb = beq ? q.rho_eq : q.rho, irb = beq ? inv_rho_eq : inv_rho;
       const double xt = q.v1[i];
       const double xn = q.alpha * xt + (1.0 - q.alpha) * q.x[i];
       const double zr = q.alpha * (beta * xt) + (1.0 - q.alpha) * q.zb[i];
-      double zn = zr + q.yb[i] / rb;
+      double zn = zr + q.yb[i] * irb;
       zn = fmin(fmax(zn, lb), ub);
       const double dy = rb * (zr - zn);
       if (act && keep_steps) {
@@ -1243,7 +1343,7 @@ __global__ void __launch_bounds__(32, 4) qp_kernel(DevProblem p, const double* x
   q.RS = p.row_stride;
   q.Kb = sm + S.Kb; q.Linv = sm + S.Linv; q.beta = sm + S.beta;
   q.x = sm + S.x; q.zb = sm + S.zb; q.yb = sm + S.yb; q.v1 = sm + S.v1;
-  q.qs = sm + S.qs; q.lbs = sm + S.lbs; q.ubs = sm + S.ubs;
+  q.qs = sm + S.qs; q.lbs = sm + S.lbs; q.ubs = sm + S.ubs; q.xch = sm + S.xch;
   q.colptr = reinterpret_cast<int*>(sm + S.colptr);
   q.maxcol = reinterpret_cast<int*>(sm + S.maxcol);
   q.rows = p.rows + static_cast<size_t>(b) * p.max_rows * p.row_stride;
