@@ -18,7 +18,7 @@
 
 #include "../../include/trajopt_b200.h"
 #include "eval_kernel.cuh"
-#include "qp_kernel.cuh"
+#include "qp_block_kernel.cuh"
 
 using namespace tb200;
 
@@ -366,6 +366,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   P->qp_smem = static_cast<size_t>(qs.total) * sizeof(double);
   if (P->eval_smem > 227 * 1024 || P->qp_smem > 227 * 1024)
     return fail(TB200_ERR_UNSUPPORTED, "problem does not fit the 227 KB shared memory of one CTA");
+  if ((qp_block_count(N, 2 * D) + 1) / 2 * 2 * D > kQpThreads)
+    return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for one CTA per block-cyclic-reduction level");
   CK(cudaFuncSetAttribute(eval_convexify_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->eval_smem)));
   CK(cudaFuncSetAttribute(qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->qp_smem)));
   CK(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
@@ -527,7 +529,7 @@ int tb200_solve_batch_resident(tb200_problem* P) {
   auto launch_qp = [&]() {
     const size_t i0 = ne;
     cudaEventRecord(getEvent(P, ne++), st);
-    qp_kernel<<<dp.B, 32, P->qp_smem, st>>>(dp, nullptr, nullptr, nullptr, nullptr, P->slice);
+    qp_kernel<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, nullptr, nullptr, nullptr, nullptr, P->slice);
     cudaEventRecord(getEvent(P, ne++), st);
     spans.push_back({i0, 1});
   };
@@ -642,7 +644,7 @@ int tb200_qp_solve_batch(tb200_problem* P, const double* x, const double* trust,
   if (dp.n_cnts > 0) CK(cudaMemcpyAsync(P->merit_coeffs.p, merit_coeffs, B * dp.n_cnts * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(P->ws_meta.p, 0, B * 8 * sizeof(int), st));
   eval_convexify_decide_kernel<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
-  qp_kernel<<<dp.B, 32, P->qp_smem, st>>>(dp, P->x_tmp.p, P->trust_tmp.p, P->tmp_iters.p, P->tmp_polish.p, 1 << 30);
+  qp_kernel<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, P->x_tmp.p, P->trust_tmp.p, P->tmp_iters.p, P->tmp_polish.p, 1 << 30);
   CK(cudaGetLastError());
   auto pull = [&](void* dst, const void* src, size_t n) {
     if (!dst || n == 0) return cudaSuccess;
