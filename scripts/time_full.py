@@ -22,3 +22,10 @@ if nref:
           "max dcost %.2e" % np.abs(got["total_cost"][sl] - ref["total_cost"][sl]).max(), "max dx %.2e" % np.abs(got["x"][sl] - ref["x"][sl]).max())
     bad = np.where(np.abs(got["total_cost"][sl] - ref["total_cost"][sl]) > 1e-6)[0]
     print("trajectories off by >1e-6 in cost:", bad.tolist())
+import ctypes as C
+dbg = np.zeros((B, 16))
+p.lib.tb200_debug_last_qp(p.handle, dbg.ctypes.data_as(C.POINTER(C.c_double)))
+nr = dbg[:, 11]
+print("rows of the last QP: mean %.0f p50 %.0f p90 %.0f max %.0f | n_aux mean %.0f | admm iters total per traj: mean %.0f p90 %.0f max %.0f" % (
+    nr.mean(), np.percentile(nr, 50), np.percentile(nr, 90), nr.max(), dbg[:, 12].mean(),
+    got["n_admm_iters"].mean(), np.percentile(got["n_admm_iters"], 90), got["n_admm_iters"].max()))

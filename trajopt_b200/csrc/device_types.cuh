@@ -129,6 +129,7 @@ struct DevProblem {
   double* ws_yb;               // [B][N]  warm start: duals of the variable-bound rows (unscaled)
   double* scratch;             // [B][10*Np]: dx dy stash(x zb yb) | scaled q, lb, ub | Dz | v2
   double* park;                // [B][4*Np]: x zb yb beta of a QP parked between time slices
+  double* park_factor;         // [B][3*M*nb*nb]: the block-cyclic-reduction factor of a parked QP
   int* rs_int;                 // [B][4] parked solver state
   double* rs_dbl;              // [B][4]
   int* qp_done;                // [B] 1: a QP solution is waiting for its evaluation

@@ -1,0 +1,1555 @@
+// QP subproblem kernel, latency-optimised: one 256-thread CTA per trajectory, time sliced.
+//
+// Replaces OSQPModel::optimize() -> osqp_setup/osqp_solve (trajopt_sco/src/osqp_interface.cpp:283-615) for
+// every trajectory of the batch (same algorithm and arithmetic as the oracle's qp_solve: Ruiz equilibration,
+// OSQP-equivalent ADMM, adaptive rho, verified polish).
+//
+// Why a CTA per trajectory.  At batch 1024 the wall time of a batched solve is the slowest trajectory's
+// sequential chain of ADMM iterations (~8x the mean) times the latency of one iteration.  So the kernel is
+// built for per-trajectory latency: 8 warps work on ONE reduced KKT system,
+//   (P + sigma I + A' diag(rho) A) x = rhs,   N = T*D unknowns, block tridiagonal with nb = 2*D blocks,
+// which is factored and solved by BLOCK CYCLIC REDUCTION: log2(M) levels instead of M sequential block
+// steps (M = N/nb = 15 for 7-DOF x 30).  Level l eliminates every other remaining block p with
+//   Ainv_p = A_p^-1,  Um_p = L_p' Ainv_p,  Up_p = L_{p+s} Ainv_p,   (L_p = K(p, p-s), s = 2^l)
+//   A_{p-s} -= Um_p L_p,  A_{p+s} -= Up_p L_{p+s}',  L'_{p+s} = -Up_p L_p
+// and a solve is  rhs_{p-+s} -= U rhs_p  going down,  x_p = Ainv_p rhs_p - Um_p' x_{p-s} - Up_p' x_{p+s}  going up:
+// 2*log2(M)+1 dependent mat-vec steps of 14..42 terms, two threads per (block,row).
+//
+// Everything an ADMM iteration touches is in shared memory: the factor (3 x M x nb x nb), the trajectory
+// vectors, and - when the QP has at most `row_cap` rows, the common case - the rows of the QP themselves.
+// The hinge / abs auxiliary variables of the l1 penalty are eliminated per row in closed form (cancellation
+// free), exactly as in DESIGN.md §5.2.  A solve that runs out of its time slice parks its state (vectors, rows
+// and factor) in HBM and resumes from it in the next launch.
+#pragma once
+#include "device_types.cuh"
+#include "eval_kernel.cuh"
+
+namespace tb200 {
+
+constexpr int kQpThreads = 256;
+constexpr double kOsqpInf = 1e30;
+constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4;
+constexpr double kVerifyTol = 1e-9;  // KKT verification of the polished point (deviation D2)
+constexpr int kVerifyRounds = 3;
+constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoTol = 1e-4, kRhoEqOverIneq = 1e3;
+enum { QPS_UNSOLVED = 0, QPS_SOLVED = 1, QPS_SOLVED_INACC = 2, QPS_PINF = 3, QPS_PINF_INACC = 4, QPS_DINF = 5,
+       QPS_DINF_INACC = 6, QPS_MAXITER = 7, QPS_NONCVX = 8, QPS_YIELD = 100 };
+
+__device__ __forceinline__ double limit_scaling(double v) {
+  v = v < kMinScaling ? 1.0 : v;
+  return v > kMaxScaling ? kMaxScaling : v;
+}
+
+// ---- shared memory layout (doubles) ------------------------------------------------------------------
+// SA: A_p -> Ainv_p.  SLM: left couplings L_p during the factorisation, Um_p afterwards.  SU: Up_p (while a
+// level is being eliminated the still unused slot of the left survivor holds a temporary).
+struct QpSmem {
+  int SA, SLM, SU, beta, x, zb, yb, v1, w, qs, lbs, ubs, tmp, red, colptr, colent, rints, rows, total, row_cap;
+};
+constexpr int kQpSmemBudget = 14400;  // doubles per CTA: two CTAs per SM (227 KB / 2 minus the 1 KB reserve)
+__host__ __device__ inline int qp_block_count(int N, int nb) { return (N + nb - 1) / nb; }
+__host__ __device__ inline int qp_even(int v) { return (v + 1) & ~1; }
+__host__ __device__ inline QpSmem qp_smem_layout(int N, int nb, int row_stride, int CN, int max_rows) {
+  const int M = qp_block_count(N, nb), Np = M * nb, blk = nb * nb;
+  QpSmem s;
+  int o = 0;
+  s.SA = o;   o += qp_even(M * blk);
+  s.SLM = o;  o += qp_even(M * blk);
+  s.SU = o;   o += qp_even(M * blk);
+  s.beta = o; o += qp_even(Np);
+  s.x = o;    o += qp_even(Np);
+  s.zb = o;   o += qp_even(Np);
+  s.yb = o;   o += qp_even(Np);
+  s.v1 = o;   o += qp_even(Np);
+  s.w = o;    o += qp_even(Np);
+  s.qs = o;   o += qp_even(Np);
+  s.lbs = o;  o += qp_even(Np);
+  s.ubs = o;  o += qp_even(Np);
+  s.tmp = o;  o += qp_even((M + 1) / 2 * 2 * nb) + 8;  // Gauss-Jordan pivot rows / columns, 8 scalars at the end
+  s.red = o;  o += 16 * 8;                            // block reductions: 16 quantities x 8 warps
+  s.colptr = o; o += qp_even((Np + 2) / 2 + 1);
+  // whatever is left of the two-CTAs-per-SM budget holds rows: record + column entries + row ints
+  const int per_row2 = 2 * row_stride + CN + RI_NINTS;  // in half doubles
+  int cap = (o < kQpSmemBudget) ? 2 * (kQpSmemBudget - o) / per_row2 - 1 : 0;
+  cap = cap > max_rows ? max_rows : cap;
+  cap = cap > 1023 ? 1023 : cap;
+  cap = cap < 0 ? 0 : cap;
+  s.row_cap = cap;
+  s.colent = o; o += qp_even((cap * CN + 1) / 2);
+  s.rints = o;  o += qp_even((cap * RI_NINTS + 1) / 2);
+  s.rows = o;   o += cap * row_stride;
+  s.total = o;
+  return s;
+}
+
+// ---- per-row record (global memory): CN raw coefficients, CN scaled coefficients, then these fields ----
+// Every row is padded to CN coefficients (zeros) and two aux slots (absent aux: u = b = qa = 0, scalings 1).
+enum RowF {
+  R_C = 0, R_W,                         // raw: constant, aux cost
+  R_E, R_DA0, R_DA1, R_EA0, R_EA1,      // Ruiz scalings
+  R_U0, R_U1, R_B0, R_B1, R_LO, R_UP, R_QA0, R_QA1, R_RHO,  // scaled view (R_RHO: 1 = equality row)
+  R_XA0, R_XA1, R_Z, R_Y, R_ZA0, R_ZA1, R_YA0, R_YA1,        // ADMM state
+  R_RA0, R_RA1, R_COEF, R_WR, R_G0, R_G1, R_DEN, R_WRR,      // per-solve temporaries (WRR: raw row weight)
+  R_IDEN, R_IWRR,                                            // reciprocals of DEN / WRR (0 when WRR == 0)
+  R_DY, R_DYA0, R_DYA1, R_DXA0, R_DXA1,
+  R_PW, R_PWA0, R_PWA1, R_PB, R_PY, R_PYA0, R_PYA1, R_PX0, R_PX1,  // polish
+  R_MV,
+  R_NF
+};
+__host__ __device__ inline int qp_row_stride(int CN) { return 2 * CN + R_NF; }
+
+struct QpCtx {
+  int N, Np, nb, M, T, D, CN, RS, tid, nrows;
+  double *SA, *SLM, *SU, *beta, *x, *zb, *yb, *v1, *w, *qs, *lbs, *ubs, *tmp, *red, *flag;   // shared (flag: 8 scalars)
+  int* colptr;           // shared [Np+1]
+  double *Dz, *v2;       // global [Np] (used by the residual / polish passes only)
+  double* rows;          // shared when the QP has at most row_cap rows, else global
+  int* rints;
+  const int* colent;     // entries: (row << 5) | k (shared or global, like the rows)
+  const double* Pband;   // global [N][2D+1]
+  double* scratch;
+  double c, cinv, rho, rho_eq, sigma, alpha;
+  __device__ __forceinline__ double* R(int r) const { return rows + static_cast<size_t>(r) * RS; }
+  __device__ __forceinline__ double* F(int r) const { return rows + static_cast<size_t>(r) * RS + 2 * CN; }
+  __device__ __forceinline__ const int* I(int r) const { return rints + static_cast<size_t>(r) * RI_NINTS; }
+};
+
+// ---- block reductions: xor butterfly inside each warp, then 8 partials through shared memory ---------------
+// vals[k] -> max, or (bit k of sum_mask set) the sum; fixed order, every thread gets the result.
+template <int NQ>
+__device__ inline void block_reduce(const QpCtx& q, double (&vals)[NQ], unsigned sum_mask) {
+  static_assert(NQ <= 16, "red area too small");
+  const int lane = q.tid & 31, wid = q.tid >> 5;
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) {
+    double v = vals[k];
+    const bool sum = (sum_mask >> k) & 1u;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double o = __shfl_xor_sync(0xffffffffu, v, off);
+      v = sum ? v + o : fmax(v, o);
+    }
+    if (lane == 0) q.red[k * 8 + wid] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) {
+    const bool sum = (sum_mask >> k) & 1u;
+    double acc = q.red[k * 8];
+#pragma unroll
+    for (int w = 1; w < kQpThreads / 32; ++w) acc = sum ? acc + q.red[k * 8 + w] : fmax(acc, q.red[k * 8 + w]);
+    vals[k] = acc;
+  }
+  __syncthreads();
+}
+
+// weights of the linear system: ADMM (rho vector, sigma) or polish (1/delta on the active set, delta)
+struct SysW {
+  bool polish;
+  double sig, rho_aux;
+};
+
+// variable index of coefficient k of a row (padding coefficients alias the last real one; their value is 0)
+__device__ __forceinline__ int row_var(const int* I, int k) {
+  return I[RI_BASE] + min(k, I[RI_CNT] - 1) * I[RI_STRIDE];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Block cyclic reduction: factorisation.  On entry SA[p] = K(p,p), SLM[p] = K(p,p-1) (p >= 1).  On exit
+// SA[p] = Ainv_p, SLM[p] = Um_p, SU[p] = Up_p for the level at which block p is eliminated.
+template <int NB>
+__device__ inline bool bcr_factor(const QpCtx& q) {
+  constexpr int BLK = NB * NB;
+  const int M = q.M, tid = q.tid;
+  int bad = 0;
+  for (int l = 0; (1 << l) - 1 < M; ++l) {
+    const int s = 1 << l, first = s - 1, sh = l + 1;  // eliminated p = first + (e << sh); survivors j = p + s
+    const int nE = (M + s) >> sh, nS = M >> sh;
+    // ---- 1. Ainv_p in place (Gauss-Jordan without pivoting: the blocks are symmetric positive definite)
+    double* prow = q.tmp;             // [nE][NB]
+    double* pcol = q.tmp + nE * NB;   // [nE][NB]
+    for (int k = 0; k < NB; ++k) {
+      for (int t = tid; t < nE * NB; t += kQpThreads) {
+        const int e = t / NB, j = t % NB;
+        const double* A = q.SA + (first + (e << sh)) * BLK;
+        const double piv = A[k * NB + k];
+        if (j == k && !(piv > 0.0)) bad = 1;
+        const double ip = 1.0 / piv;
+        prow[t] = (j == k) ? ip : A[k * NB + j] * ip;
+        pcol[t] = A[j * NB + k];
+      }
+      __syncthreads();
+      for (int t = tid; t < nE * BLK; t += kQpThreads) {
+        const int e = t / BLK, i = (t % BLK) / NB, j = t % NB;
+        double* A = q.SA + (first + (e << sh)) * BLK;
+        const double* pr = prow + e * NB;
+        const double f = pcol[e * NB + i];
+        const double upd = A[i * NB + j] - f * pr[j];
+        A[i * NB + j] = (i == k) ? pr[j] : ((j == k) ? -f * pr[k] : upd);
+      }
+      __syncthreads();
+    }
+    // ---- 2. Up_p = L_{p+s} Ainv_p -> SU[p];  Um_p = L_p' Ainv_p -> SU[p-s] (temporary home)
+    for (int t = tid; t < nE * BLK; t += kQpThreads) {
+      const int e = t / BLK, i = (t % BLK) / NB, j = t % NB;
+      const int p = first + (e << sh);
+      const double* Ai = q.SA + p * BLK;
+      if (p + s < M) {
+        const double* L2 = q.SLM + (p + s) * BLK + i * NB;
+        double up = 0.0;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) up += L2[k] * Ai[k * NB + j];
+        q.SU[p * BLK + i * NB + j] = up;
+      }
+      if (p - s >= 0) {
+        const double* L = q.SLM + p * BLK + i;
+        double um = 0.0;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) um += L[k * NB] * Ai[k * NB + j];
+        q.SU[(p - s) * BLK + i * NB + j] = um;
+      }
+    }
+    __syncthreads();
+    // ---- 3. survivors j:  A_j -= Up_{j-s} L_j' + Um_{j+s} L_{j+s}     (Um_{j+s} sits in SU[j])
+    for (int t = tid; t < nS * BLK; t += kQpThreads) {
+      const int e = t / BLK, i = (t % BLK) / NB, jj = t % NB;
+      const int j = first + s + (e << sh);
+      double acc = 0.0;
+      {
+        const double* Up = q.SU + (j - s) * BLK + i * NB;
+        const double* Lj = q.SLM + j * BLK + jj * NB;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) acc += Up[k] * Lj[k];
+      }
+      if (j + s < M) {
+        const double* Um = q.SU + j * BLK + i * NB;
+        const double* Lp = q.SLM + (j + s) * BLK + jj;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) acc += Um[k] * Lp[k * NB];
+      }
+      q.SA[j * BLK + i * NB + jj] -= acc;
+    }
+    __syncthreads();
+    // ---- 4. new left couplings of the survivors: L'_j = -Up_p L_p with p = j - s (0 without a left survivor)
+    for (int t = tid; t < nS * BLK; t += kQpThreads) {
+      const int e = t / BLK, i = (t % BLK) / NB, jj = t % NB;
+      const int j = first + s + (e << sh), p = j - s;
+      double acc = 0.0;
+      if (p - s >= 0) {
+        const double* Up = q.SU + p * BLK + i * NB;
+        const double* Lp = q.SLM + p * BLK + jj;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) acc += Up[k] * Lp[k * NB];
+      }
+      q.SLM[j * BLK + i * NB + jj] = -acc;
+    }
+    __syncthreads();
+    // ---- 5. Um_p moves from its temporary home into SLM[p] (L_p is dead now)
+    for (int t = tid; t < nE * BLK; t += kQpThreads) {
+      const int e = t / BLK, r = t % BLK;
+      const int p = first + (e << sh);
+      if (p - s >= 0) q.SLM[p * BLK + r] = q.SU[(p - s) * BLK + r];
+    }
+    __syncthreads();
+  }
+  // every thread must agree on the verdict
+  if (tid == 0) q.flag[0] = 0.0;
+  __syncthreads();
+  if (bad) q.flag[0] = 1.0;
+  __syncthreads();
+  const bool ok = q.flag[0] == 0.0;
+  __syncthreads();
+  return ok;
+}
+
+// Block cyclic reduction: solve K w = v (both in shared memory, length Np; v is overwritten by the reduced
+// right-hand sides).  Two threads per (block,row) task, combined with one shuffle; every level ends in a barrier.
+template <int NB>
+__device__ __forceinline__ double dot_row(const double* __restrict__ m, const double* __restrict__ v) {
+  const double2* m2 = reinterpret_cast<const double2*>(m);
+  const double2* v2 = reinterpret_cast<const double2*>(v);
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int k = 0; k < NB / 2; ++k) {
+    const double2 mm = m2[k], vv = v2[k];
+    a0 += mm.x * vv.x;
+    a1 += mm.y * vv.y;
+  }
+  return a0 + a1;
+}
+template <int NB>
+__device__ inline void bcr_solve(const QpCtx& q, double* v, double* w) {
+  constexpr int BLK = NB * NB, H = NB / 2;
+  const int M = q.M, tid = q.tid, side = tid & 1, task0 = tid >> 1;
+  __syncthreads();
+  int l = 0;
+  // ---- down: survivors absorb their eliminated neighbours
+  for (; (2 << l) - 1 < M; ++l) {
+    const int s = 1 << l, sh = l + 1, nS = M >> sh;
+    for (int tb = 0; tb < nS * NB; tb += kQpThreads / 2) {
+      const int task = tb + task0;
+      const int e = task / NB, r = task % NB;
+      const bool act = e < nS;
+      const int j = 2 * s - 1 + ((act ? e : 0) << sh);
+      const int pb = side ? j + s : j - s;           // side 0: left eliminated neighbour, side 1: right one
+      const bool valid = act && pb < M;
+      const int pbc = valid ? pb : j - s;
+      const double* mat = (side ? q.SLM : q.SU) + pbc * BLK + r * NB;
+      double a = dot_row<NB>(mat, v + pbc * NB);
+      a = valid ? a : 0.0;
+      const double o = __shfl_xor_sync(0xffffffffu, a, 1);
+      if (act && side == 0) v[j * NB + r] -= a + o;  // survivors are not read by any other task of this level
+    }
+    __syncthreads();
+  }
+  // ---- up: eliminated blocks, from the last level back to the first
+  for (; l >= 0; --l) {
+    const int s = 1 << l, first = s - 1, sh = l + 1;
+    if (first >= M) continue;
+    const int nE = (M + s) >> sh;
+    for (int tb = 0; tb < nE * NB; tb += kQpThreads / 2) {
+      const int task = tb + task0;
+      const int e = task / NB, r = task % NB;
+      const bool act = e < nE;
+      const int p = first + ((act ? e : 0) << sh);
+      const bool hasl = p - s >= 0, hasr = p + s < M;
+      // both sides run the same instruction stream: a column dot of length NB plus half of the Um column dot
+      //   side 0:  +Ainv_p(:,r) . v_p        - Um_p(0:H,r) . w_{p-s}(0:H)      (Ainv is symmetric)
+      //   side 1:  -Up_p(:,r)   . w_{p+s}    - Um_p(H:NB,r) . w_{p-s}(H:NB)
+      const double* X = (side ? q.SU : q.SA) + p * BLK + r;
+      const double* y = side ? w + (hasr ? p + s : 0) * NB : v + p * NB;
+      const double* Um = q.SLM + p * BLK + (side ? H * NB : 0) + r;
+      const double* wl = w + (hasl ? p - s : 0) * NB + (side ? H : 0);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < NB; k += 2) {
+        a0 += X[k * NB] * y[k];
+        a1 += X[(k + 1) * NB] * y[k + 1];
+      }
+#pragma unroll
+      for (int k = 0; k < H; ++k) a2 += Um[k * NB] * wl[k];
+      const double dx = a0 + a1;
+      const double acc = (side ? (hasr ? -dx : 0.0) : dx) - (hasl ? a2 : 0.0);
+      const double o = __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (act && side == 0) w[p * NB + r] = acc + o;
+    }
+    __syncthreads();
+  }
+}
+
+// scaled P (band) times a vector: out = c * Dz .* (P (Dz .* in)); in: shared or global, out: global/shared
+__device__ inline void p_matvec(const QpCtx& q, const double* in, double* out) {
+  const int N = q.N, HB = 2 * q.D, W = HB + 1;
+  for (int i = q.tid; i < q.Np; i += kQpThreads) {
+    double s = 0.0;
+    if (i < N) {
+      for (int k = 0; k <= HB && k <= i; ++k) s += q.Pband[i * W + k] * q.Dz[i - k] * in[i - k];
+      for (int k = 1; k <= HB && i + k < N; ++k) s += q.Pband[(i + k) * W + k] * q.Dz[i + k] * in[i + k];
+      s *= q.c * q.Dz[i];
+    }
+    out[i] = s;
+  }
+  __syncthreads();
+}
+
+// per-row weights of the current linear system -> R_WRR (raw row weight), R_G0/G1, R_DEN, R_WR (Schur weight).
+// With the aux block K_aa = diag(g) + Wr u u' everything is written cancellation free (den = det K_aa
+// expanded analytically); the polish system has Wr = 1/delta and g = delta.
+__device__ inline void rows_prepare_weights(const QpCtx& q, const SysW& w) {
+  for (int r = q.tid; r < q.nrows; r += kQpThreads) {
+    double* F = q.F(r);
+    const int naux = q.I(r)[RI_AUX];
+    const double Wr = w.polish ? fabs(F[R_PW]) : ((F[R_RHO] != 0.0) ? q.rho_eq : q.rho);
+    const double wa0 = w.polish ? fabs(F[R_PWA0]) : w.rho_aux;
+    const double wa1 = w.polish ? fabs(F[R_PWA1]) : w.rho_aux;
+    const double g0 = (naux >= 1) ? w.sig + wa0 * F[R_B0] * F[R_B0] : 1.0;
+    const double g1 = (naux == 2) ? w.sig + wa1 * F[R_B1] * F[R_B1] : 1.0;
+    const double den = g0 * g1 + Wr * (F[R_U0] * F[R_U0] * g1 + F[R_U1] * F[R_U1] * g0);
+    F[R_WRR] = Wr;
+    F[R_G0] = g0;
+    F[R_G1] = g1;
+    F[R_DEN] = den;
+    F[R_IDEN] = 1.0 / den;
+    F[R_IWRR] = (Wr != 0.0) ? 1.0 / Wr : 0.0;
+    F[R_WR] = Wr * g0 * g1 / den;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ double xbound_weight(const QpCtx& q, const SysW& w, int j) {
+  const double adm = (q.ubs[j] - q.lbs[j] < kRhoTol) ? q.rho_eq : q.rho;
+  return w.polish ? fabs(q.zb[j]) : adm;  // zb holds the signed polish weights during polish
+}
+
+// K = P + sig I + A' W A with the aux variables eliminated, written straight into the block storage
+// (SA: diagonal blocks, SLM: left couplings); one thread per matrix row; then factor.
+template <int NB>
+__device__ inline bool assemble_factor(const QpCtx& q, const SysW& w) {
+  rows_prepare_weights(q, w);
+  constexpr int nb = NB, blk = NB * NB;
+  const int N = q.N, HB = 2 * q.D, PW = HB + 1, CN = q.CN;
+  for (int t = q.tid; t < q.M * blk; t += kQpThreads) {
+    q.SA[t] = 0.0;
+    q.SLM[t] = 0.0;
+  }
+  __syncthreads();
+  for (int i = q.tid; i < q.Np; i += kQpThreads) {
+    const int p = i / nb, r = i % nb;
+    double* Arow = q.SA + static_cast<size_t>(p) * blk + r * nb;   // K(i, p*nb + c)
+    double* Lrow = q.SLM + static_cast<size_t>(p) * blk + r * nb;   // K(i, (p-1)*nb + c)
+    if (i >= N) {
+      Arow[r] = 1.0;  // padding variable
+      continue;
+    }
+    // element K(i, i-k), k = 0..HB, lands in the diagonal block (k <= r) or the left coupling block
+    auto add = [&](int k, double val) {
+      if (k <= r) Arow[r - k] += val;
+      else Lrow[nb + r - k] += val;
+    };
+    for (int k = 0; k <= HB && k <= i; ++k) add(k, q.c * q.Dz[i] * q.Pband[i * PW + k] * q.Dz[i - k]);
+    add(0, w.sig + xbound_weight(q, w, i) * q.beta[i] * q.beta[i]);
+    for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
+      const int ent = q.colent[e], rw = ent >> 5, k = ent & 31;
+      const double* R = q.R(rw);
+      const double wr = R[2 * CN + R_WR];
+      if (wr == 0.0) continue;
+      const int stride = q.I(rw)[RI_STRIDE];
+      const double* as = R + CN;
+      const double ai = wr * as[k];
+      for (int k2 = 0; k2 <= k; ++k2) add((k - k2) * stride, ai * as[k2]);
+    }
+  }
+  __syncthreads();
+  // mirror the strictly lower part of every diagonal block into its upper part
+  for (int t = q.tid; t < q.M * blk; t += kQpThreads) {
+    const int p = t / blk, i = (t % blk) / nb, j = t % nb;
+    if (j > i) q.SA[static_cast<size_t>(p) * blk + i * nb + j] = q.SA[static_cast<size_t>(p) * blk + j * nb + i];
+  }
+  __syncthreads();
+  return bcr_factor<NB>(q);
+}
+
+struct QpOut {
+  int status, iters, polish;
+  double rho;
+  double pri_res, dua_res, pol_pri, pol_dua, c;
+  int pol_factor_ok, rho_updates, rounds;
+};
+
+// Persistent solver state of one QP between time slices.
+struct QpResume {
+  int iter, round, rho_updates, status;
+  double rho, eps_scale, c;
+};
+
+// Scatter pass: v1[i] = base(i) + sum over the column entries of as[k] * R_COEF(row).
+template <class Base>
+__device__ __forceinline__ void scatter_columns(const QpCtx& q, Base base) {
+  const int CN = q.CN;
+  for (int i = q.tid; i < q.Np; i += kQpThreads) {
+    double s = 0.0;
+    if (i < q.N) {
+      s = base(i);
+      for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
+        const int ent = q.colent[e], r = ent >> 5, k = ent & 31;
+        const double* R = q.R(r);
+        s += R[CN + k] * R[2 * CN + R_COEF];
+      }
+    }
+    q.v1[i] = s;
+  }
+  __syncthreads();
+}
+// zeta_r = as . v(vars of the row); all CN (zero padded) coefficients
+__device__ __forceinline__ double row_dot(const QpCtx& q, const double* R, const int* I, const double* v) {
+  double z = 0.0;
+  const int base = I[RI_BASE], stride = I[RI_STRIDE], last = I[RI_CNT] - 1;
+  for (int k = 0; k < q.CN; ++k) z += R[q.CN + k] * v[base + min(k, last) * stride];
+  return z;
+}
+// aux back-substitution (cancellation free; absent aux slots have u = ra = 0 and g = 1 and come out 0)
+__device__ __forceinline__ void row_backsub(const double* F, double zeta, double& a0, double& a1) {
+  const double Wr = F[R_WRR], ra0 = F[R_RA0], ra1 = F[R_RA1], u0 = F[R_U0], u1 = F[R_U1];
+  const double iden = F[R_IDEN];
+  a0 = (F[R_G1] * (ra0 - Wr * u0 * zeta) + Wr * u1 * (u1 * ra0 - u0 * ra1)) * iden;
+  a1 = (F[R_G0] * (ra1 - Wr * u1 * zeta) + Wr * u0 * (u0 * ra1 - u1 * ra0)) * iden;
+}
+__device__ __forceinline__ double row_reduce_coef(const double* F, double ra0, double ra1, double zcoef) {
+  return zcoef - F[R_WRR] * (F[R_U0] * ra0 * F[R_G1] + F[R_U1] * ra1 * F[R_G0]) * F[R_IDEN];
+}
+
+// Ruiz equilibration (scale_data of OSQP [EXT]); leaves the scaled view of every row in its record and the
+// scaled trajectory cost / bounds in q.qs / q.lbs / q.ubs, Dz (global) / beta (shared).
+__device__ inline void qp_scale(QpCtx& q, const QpSettings& st, int n_aux_total) {
+  double *qs = q.qs, *lbs = q.lbs, *ubs = q.ubs;
+  const int N = q.N, tid = q.tid, HB = 2 * q.D, W = HB + 1;
+  double* Eb = q.zb;  // bound-row scalings live in zb during scaling
+  q.c = 1.0;
+  for (int i = tid; i < q.Np; i += kQpThreads) {
+    q.Dz[i] = 1.0;
+    Eb[i] = 1.0;
+  }
+  for (int r = tid; r < q.nrows; r += kQpThreads) {
+    double* F = q.F(r);
+    F[R_E] = F[R_DA0] = F[R_DA1] = F[R_EA0] = F[R_EA1] = 1.0;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < st.scaling; ++pass) {
+    // row norms (one thread per row) -> E_temp in R_RA0; aux column / bound-row scalings updated in place
+    for (int r = tid; r < q.nrows; r += kQpThreads) {
+      double* R = q.R(r);
+      double* F = q.F(r);
+      const int* I = q.I(r);
+      const int base = I[RI_BASE], cnt = I[RI_CNT], stride = I[RI_STRIDE], aux = I[RI_AUX];
+      const double E = F[R_E];
+      double rn = 0.0;
+      for (int k = 0; k < cnt; ++k) rn = fmax(rn, fabs(E * R[k] * q.Dz[base + k * stride]));
+      double dt0 = 1.0, dt1 = 1.0, et0 = 1.0, et1 = 1.0;
+      if (aux >= 1) {
+        const double ua = fabs(E * F[R_DA0]), ba = fabs(F[R_EA0] * F[R_DA0]);
+        rn = fmax(rn, ua);
+        dt0 = 1.0 / sqrt(limit_scaling(fmax(ua, ba)));
+        et0 = 1.0 / sqrt(limit_scaling(ba));
+      }
+      if (aux == 2) {
+        const double ua = fabs(E * F[R_DA1]), ba = fabs(F[R_EA1] * F[R_DA1]);
+        rn = fmax(rn, ua);
+        dt1 = 1.0 / sqrt(limit_scaling(fmax(ua, ba)));
+        et1 = 1.0 / sqrt(limit_scaling(ba));
+      }
+      F[R_RA0] = 1.0 / sqrt(limit_scaling(rn));
+      F[R_RA1] = E;  // E before this pass (the column pass below must still see the old value)
+      F[R_DA0] *= dt0;
+      F[R_DA1] *= dt1;
+      F[R_EA0] *= et0;
+      F[R_EA1] *= et1;
+    }
+    __syncthreads();
+    // column norms of [P A'; A 0] restricted to the trajectory variables (one thread per variable)
+    for (int i = tid; i < N; i += kQpThreads) {
+      double m = 0.0;
+      for (int k = 0; k <= HB && k <= i; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[i * W + k] * q.Dz[i - k]));
+      for (int k = 1; k <= HB && i + k < N; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[(i + k) * W + k] * q.Dz[i + k]));
+      const double bn = fabs(Eb[i] * q.Dz[i]);
+      m = fmax(m, bn);
+      for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
+        const int ent = q.colent[e], r = ent >> 5, k = ent & 31;
+        const double* R = q.R(r);
+        m = fmax(m, fabs(R[2 * q.CN + R_RA1] * R[k] * q.Dz[i]));
+      }
+      q.v1[i] = 1.0 / sqrt(limit_scaling(m));
+      Eb[i] *= 1.0 / sqrt(limit_scaling(bn));
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += kQpThreads) q.Dz[i] *= q.v1[i];
+    for (int r = tid; r < q.nrows; r += kQpThreads) {
+      double* F = q.F(r);
+      F[R_E] = F[R_RA1] * F[R_RA0];
+    }
+    __syncthreads();
+    // cost normalisation: mean column inf-norm of the scaled P over ALL n variables (aux columns are 0)
+    double csum = 0.0, qn = 0.0;
+    for (int i = tid; i < N; i += kQpThreads) {
+      double m = 0.0;
+      for (int k = 0; k <= HB && k <= i; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[i * W + k] * q.Dz[i - k]));
+      for (int k = 1; k <= HB && i + k < N; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[(i + k) * W + k] * q.Dz[i + k]));
+      csum += m;
+      qn = fmax(qn, fabs(q.c * q.Dz[i] * qs[i]));
+    }
+    for (int r = tid; r < q.nrows; r += kQpThreads) {
+      const double* F = q.F(r);
+      const int aux = q.I(r)[RI_AUX];
+      if (aux >= 1) qn = fmax(qn, fabs(q.c * F[R_DA0] * F[R_W]));
+      if (aux == 2) qn = fmax(qn, fabs(q.c * F[R_DA1] * F[R_W]));
+    }
+    double red2[2] = {csum, qn};
+    block_reduce<2>(q, red2, 0x1u);
+    const double mean = limit_scaling(red2[0] / static_cast<double>(N + n_aux_total));
+    q.c *= 1.0 / fmax(mean, limit_scaling(red2[1]));
+  }
+  q.cinv = 1.0 / q.c;
+  for (int i = tid; i < q.Np; i += kQpThreads) {
+    if (i < N) {
+      qs[i] = q.c * q.Dz[i] * qs[i];
+      lbs[i] *= Eb[i];
+      ubs[i] *= Eb[i];
+      q.beta[i] = Eb[i] * q.Dz[i];
+    } else {
+      qs[i] = 0.0; lbs[i] = -1.0; ubs[i] = 1.0; q.beta[i] = 1.0; q.Dz[i] = 1.0;
+    }
+  }
+  // scaled view of every row (padding coefficients stay exactly 0)
+  for (int r = tid; r < q.nrows; r += kQpThreads) {
+    double* R = q.R(r);
+    double* F = q.F(r);
+    const int* I = q.I(r);
+    const int aux = I[RI_AUX];
+    const double E = F[R_E];
+    for (int k = 0; k < q.CN; ++k) R[q.CN + k] = E * R[k] * q.Dz[row_var(I, k)];
+    F[R_U0] = F[R_U1] = F[R_B0] = F[R_B1] = F[R_QA0] = F[R_QA1] = 0.0;
+    F[R_UP] = -F[R_C] * E;
+    if (aux == AUX_HINGE) {
+      F[R_U0] = -E * F[R_DA0];
+      F[R_B0] = F[R_EA0] * F[R_DA0];
+      F[R_QA0] = q.c * F[R_DA0] * F[R_W];
+      F[R_LO] = -kOsqpInf * E;
+      F[R_RHO] = 0.0;
+    } else {
+      if (aux == AUX_ABS) {
+        F[R_U0] = E * F[R_DA0];
+        F[R_U1] = -E * F[R_DA1];
+        F[R_B0] = F[R_EA0] * F[R_DA0];
+        F[R_B1] = F[R_EA1] * F[R_DA1];
+        F[R_QA0] = q.c * F[R_DA0] * F[R_W];
+        F[R_QA1] = q.c * F[R_DA1] * F[R_W];
+      }
+      F[R_LO] = F[R_UP];
+      F[R_RHO] = 1.0;
+    }
+  }
+  __syncthreads();
+}
+
+// The QP solve for the calling CTA's trajectory.  `fresh`: start a new solve (initial iterate from the warm
+// start or zero); otherwise resume from `rs`.  Returns status QPS_YIELD when the slice budget ran out.
+// Every scalar that steers control flow is derived from block-reduced values, so all threads take the same path.
+template <int NB>
+__device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fresh, bool warm, double warm_rho,
+                                       const double* ws_x, const double* ws_yb, QpResume& rs, int slice,
+                                       bool have_factor) {
+  const int N = q.N, tid = q.tid;
+  QpOut out{QPS_UNSOLVED, 0, 0, st.rho, 0, 0, 0, 0, 0, -1, 0, 0};
+  double rho;
+  double eps_scale;
+  int iter, round;
+  q.sigma = st.sigma;
+  q.alpha = st.alpha;
+  if (fresh) {
+    rho = warm ? warm_rho : st.rho;
+    rho = fmin(fmax(rho, kRhoMin), kRhoMax);
+    eps_scale = 1.0;
+    iter = 0;
+    round = 0;
+    q.rho = rho;
+    q.rho_eq = kRhoEqOverIneq * rho;
+    if (warm) {  // osqp_warm_start: x <- Dinv x, y <- c Einv y, z <- A x
+      for (int i = tid; i < q.Np; i += kQpThreads) {
+        if (i < N) {
+          q.x[i] = ws_x[i] / q.Dz[i];
+          q.yb[i] = ws_yb[i] * q.Dz[i] / q.beta[i] * q.c;   // Eb = beta / Dz
+          q.zb[i] = q.beta[i] * q.x[i];
+        } else {
+          q.x[i] = q.yb[i] = q.zb[i] = 0.0;
+        }
+      }
+      __syncthreads();
+      for (int r = tid; r < q.nrows; r += kQpThreads) {
+        double* R = q.R(r);
+        double* F = q.F(r);
+        const int naux = q.I(r)[RI_AUX];
+        F[R_XA0] = (naux >= 1) ? F[R_XA0] / F[R_DA0] : 0.0;
+        F[R_XA1] = (naux == 2) ? F[R_XA1] / F[R_DA1] : 0.0;
+        F[R_Y] = F[R_Y] / F[R_E] * q.c;
+        F[R_YA0] = (naux >= 1) ? F[R_YA0] / F[R_EA0] * q.c : 0.0;
+        F[R_YA1] = (naux == 2) ? F[R_YA1] / F[R_EA1] * q.c : 0.0;
+        F[R_Z] = row_dot(q, R, q.I(r), q.x) + F[R_U0] * F[R_XA0] + F[R_U1] * F[R_XA1];
+        F[R_ZA0] = F[R_B0] * F[R_XA0];
+        F[R_ZA1] = F[R_B1] * F[R_XA1];
+      }
+    } else {
+      for (int i = tid; i < q.Np; i += kQpThreads) q.x[i] = q.zb[i] = q.yb[i] = 0.0;
+      for (int r = tid; r < q.nrows; r += kQpThreads) {
+        double* F = q.F(r);
+        F[R_XA0] = F[R_XA1] = F[R_Z] = F[R_Y] = F[R_ZA0] = F[R_ZA1] = F[R_YA0] = F[R_YA1] = 0.0;
+      }
+    }
+    __syncthreads();
+  } else {
+    rho = rs.rho;
+    eps_scale = rs.eps_scale;
+    iter = rs.iter;
+    round = rs.round;
+    out.rho_updates = rs.rho_updates;
+    q.rho = rho;
+    q.rho_eq = kRhoEqOverIneq * rho;
+  }
+  SysW sysw{false, st.sigma, rho};
+  const bool factor_ok = have_factor ? true : assemble_factor<NB>(q, sysw);  // a resumed solve brings its factor
+
+  double* dxs = q.scratch;              // [Np] last trajectory step (written on check iterations)
+  double* dyb = q.scratch + q.Np;       // [Np] last dual step of the variable-bound rows
+  double* st_x = q.scratch + 2 * q.Np;  // ADMM x, zb, yb stashed while polish reuses the shared vectors
+  double* st_zb = q.scratch + 3 * q.Np;
+  double* st_yb = q.scratch + 4 * q.Np;
+  double pri_res = 0.0, dua_res = 0.0;
+  int status = factor_ok ? QPS_UNSOLVED : QPS_NONCVX, budget = slice;
+  double n_z = 0, n_ax = 0, n_q = 0, n_aty = 0, n_px = 0, s_pri = 0, s_dua = 0, s_z = 0, s_ax = 0, s_q = 0, s_aty = 0, s_px = 0;
+
+  // ---------------------------------------------------------------- update_info(): residuals and norms
+  auto info_pass = [&]() {
+    p_matvec(q, q.x, q.v2);  // v2 <- P x
+    double m[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // 0 pri 1 z 2 ax 3 dua 4 aty 5 q 6 px | 7..13 the same on the scaled quantities
+    for (int r = tid; r < q.nrows; r += kQpThreads) {
+      const double* R = q.R(r);
+      double* F = q.F(r);
+      const double ax = row_dot(q, R, q.I(r), q.x) + F[R_U0] * F[R_XA0] + F[R_U1] * F[R_XA1];
+      const double einv = 1.0 / F[R_E];
+      m[0] = fmax(m[0], fabs(einv * (ax - F[R_Z])));
+      m[1] = fmax(m[1], fabs(einv * F[R_Z]));
+      m[2] = fmax(m[2], fabs(einv * ax));
+      m[7] = fmax(m[7], fabs(ax - F[R_Z]));
+      m[8] = fmax(m[8], fabs(F[R_Z]));
+      m[9] = fmax(m[9], fabs(ax));
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {  // absent aux slots contribute exact zeros
+        const double u = F[R_U0 + k], bb = F[R_B0 + k], qa = F[R_QA0 + k];
+        const double xa = F[R_XA0 + k], za = F[R_ZA0 + k], ya = F[R_YA0 + k];
+        const double da = F[R_DA0 + k], ea = F[R_EA0 + k];
+        const double axb = bb * xa;
+        m[0] = fmax(m[0], fabs((axb - za) / ea));
+        m[1] = fmax(m[1], fabs(za / ea));
+        m[2] = fmax(m[2], fabs(axb / ea));
+        m[7] = fmax(m[7], fabs(axb - za));
+        m[8] = fmax(m[8], fabs(za));
+        m[9] = fmax(m[9], fabs(axb));
+        const double aty = u * F[R_Y] + bb * ya;
+        m[3] = fmax(m[3], fabs((qa + aty) / da));
+        m[4] = fmax(m[4], fabs(aty / da));
+        m[5] = fmax(m[5], fabs(qa / da));
+        m[10] = fmax(m[10], fabs(qa + aty));
+        m[11] = fmax(m[11], fabs(aty));
+        m[12] = fmax(m[12], fabs(qa));
+      }
+      F[R_COEF] = F[R_Y];
+    }
+    __syncthreads();
+    scatter_columns(q, [&](int i) { return q.beta[i] * q.yb[i]; });  // v1 <- A'y (trajectory part)
+    for (int i = tid; i < N; i += kQpThreads) {
+      const double dz = q.Dz[i], beta = q.beta[i];
+      const double ax = beta * q.x[i], aty = q.v1[i], px = q.v2[i];
+      const double einv = dz / beta, dinv = 1.0 / dz;
+      m[0] = fmax(m[0], fabs(einv * (ax - q.zb[i])));
+      m[1] = fmax(m[1], fabs(einv * q.zb[i]));
+      m[2] = fmax(m[2], fabs(einv * ax));
+      m[7] = fmax(m[7], fabs(ax - q.zb[i]));
+      m[8] = fmax(m[8], fabs(q.zb[i]));
+      m[9] = fmax(m[9], fabs(ax));
+      const double qv = q.qs[i], d = qv + px + aty;
+      m[3] = fmax(m[3], fabs(dinv * d));
+      m[4] = fmax(m[4], fabs(dinv * aty));
+      m[5] = fmax(m[5], fabs(dinv * qv));
+      m[6] = fmax(m[6], fabs(dinv * px));
+      m[10] = fmax(m[10], fabs(d));
+      m[11] = fmax(m[11], fabs(aty));
+      m[12] = fmax(m[12], fabs(qv));
+      m[13] = fmax(m[13], fabs(px));
+    }
+    block_reduce<14>(q, m, 0u);
+    pri_res = m[0];
+    dua_res = m[3] * q.cinv;
+    n_z = m[1]; n_ax = m[2]; n_aty = m[4]; n_q = m[5]; n_px = m[6];
+    s_pri = m[7]; s_z = m[8]; s_ax = m[9]; s_dua = m[10]; s_aty = m[11]; s_q = m[12]; s_px = m[13];
+  };
+
+  auto primal_infeasible = [&](double eps) -> bool {  // is_primal_infeasible [EXT]
+    double a[3] = {0.0, 0.0, 0.0};  // nd (max), lhs (sum), na (max)
+    for (int r = tid; r < q.nrows; r += kQpThreads) {
+      double* F = q.F(r);
+      const int naux = q.I(r)[RI_AUX];
+      double d = F[R_DY];
+      d = (naux == AUX_HINGE) ? fmax(d, 0.0) : d;  // l = -inf
+      a[0] = fmax(a[0], fabs(F[R_E] * d));
+      a[1] += F[R_UP] * fmax(d, 0.0) + F[R_LO] * fmin(d, 0.0);
+      F[R_COEF] = d;  // projected dual step, consumed by the column pass
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double da = fmin(F[R_DYA0 + k], 0.0);  // aux bound rows: u = +inf, l = 0
+        a[0] = fmax(a[0], fabs(F[R_EA0 + k] * da));
+        a[2] = fmax(a[2], fabs((F[R_U0 + k] * d + F[R_B0 + k] * da) / F[R_DA0 + k]));
+      }
+    }
+    for (int i = tid; i < N; i += kQpThreads) {  // variable-bound rows: both bounds finite
+      const double d = dyb[i];
+      a[0] = fmax(a[0], fabs(q.beta[i] / q.Dz[i] * d));
+      a[1] += q.ubs[i] * fmax(d, 0.0) + q.lbs[i] * fmin(d, 0.0);
+    }
+    block_reduce<3>(q, a, 0x2u);
+    scatter_columns(q, [&](int i) { return q.beta[i] * dyb[i]; });
+    double mm[1] = {a[2]};
+    for (int i = tid; i < N; i += kQpThreads) mm[0] = fmax(mm[0], fabs(q.v1[i] / q.Dz[i]));
+    block_reduce<1>(q, mm, 0u);
+    return (a[0] > eps) && (a[1] < -eps * a[0]) && (mm[0] < eps * a[0]);
+  };
+  auto dual_infeasible = [&](double eps) -> bool {  // is_dual_infeasible [EXT]
+    double a[2] = {0.0, 0.0};  // ndx (max), qdx (sum)
+    for (int i = tid; i < q.Np; i += kQpThreads) {
+      const double dxi = (i < N) ? dxs[i] : 0.0;
+      if (i < N) {
+        a[0] = fmax(a[0], fabs(q.Dz[i] * dxi));
+        a[1] += q.qs[i] * dxi;
+      }
+      q.v1[i] = dxi;
+    }
+    for (int r = tid; r < q.nrows; r += kQpThreads) {
+      const double* F = q.F(r);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        a[0] = fmax(a[0], fabs(F[R_DA0 + k] * F[R_DXA0 + k]));
+        a[1] += F[R_QA0 + k] * F[R_DXA0 + k];
+      }
+    }
+    block_reduce<2>(q, a, 0x2u);
+    const double ndx = a[0], qdx = a[1];
+    p_matvec(q, q.v1, q.v2);  // v2 <- P dx
+    double b2[2] = {0.0, 0.0};  // max |Dinv P dx|, bad count (sum)
+    for (int i = tid; i < N; i += kQpThreads) {
+      b2[0] = fmax(b2[0], fabs(q.v2[i] / q.Dz[i]));
+      const double vv = q.Dz[i] * q.v1[i];  // Einv * (Eb Dz dx); both bounds finite
+      b2[1] += (vv > eps * ndx || vv < -eps * ndx) ? 1.0 : 0.0;
+    }
+    for (int r = tid; r < q.nrows; r += kQpThreads) {
+      const double* R = q.R(r);
+      const double* F = q.F(r);
+      const int naux = q.I(r)[RI_AUX];
+      const double ax = row_dot(q, R, q.I(r), q.v1) + F[R_U0] * F[R_DXA0] + F[R_U1] * F[R_DXA1];
+      const double vv = ax / F[R_E];
+      b2[1] += (vv > eps * ndx) ? 1.0 : 0.0;                              // u finite for every row
+      b2[1] += (naux != AUX_HINGE && vv < -eps * ndx) ? 1.0 : 0.0;        // l finite unless hinge
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double va = F[R_B0 + k] * F[R_DXA0 + k] / F[R_EA0 + k];
+        b2[1] += (k < naux && va < -eps * ndx) ? 1.0 : 0.0;               // aux rows: l = 0 finite, u infinite
+      }
+    }
+    block_reduce<2>(q, b2, 0x2u);
+    return (ndx > eps) && (qdx < -q.c * eps * ndx) && (b2[0] < q.c * eps * ndx) && (b2[1] == 0.0);
+  };
+  auto check_termination = [&](bool approximate) -> int {
+    double eps_abs = st.eps_abs * eps_scale, eps_rel = st.eps_rel * eps_scale, epi = st.eps_prim_inf, edi = st.eps_dual_inf;
+    if (approximate) {
+      eps_abs *= 10; eps_rel *= 10; epi *= 10; edi *= 10;
+    }
+    const double eps_pri = eps_abs + eps_rel * fmax(n_z, n_ax);
+    const double eps_dua = eps_abs + eps_rel * q.cinv * fmax(n_q, fmax(n_aty, n_px));
+    const bool pri_ok = pri_res < eps_pri, dua_ok = dua_res < eps_dua;
+    int res = QPS_UNSOLVED;
+    if (pri_res > kOsqpInf || dua_res > kOsqpInf) res = QPS_NONCVX;
+    else if (pri_ok && dua_ok) res = approximate ? QPS_SOLVED_INACC : QPS_SOLVED;
+    else {  // block-uniform branch; the certificates are only evaluated when their residual test failed
+      const bool pinf = pri_ok ? false : primal_infeasible(epi);
+      const bool dinf = dua_ok ? false : dual_infeasible(edi);
+      if (pinf) res = approximate ? QPS_PINF_INACC : QPS_PINF;
+      else if (dinf) res = approximate ? QPS_DINF_INACC : QPS_DINF;
+    }
+    return res;
+  };
+
+  // ---------------------------------------------------------------- one ADMM iteration
+  // Rows are handled by the high thread ids so that they run beside the per-variable work of the low ones.
+  // rows_coef: aux right-hand sides R_RA0/1 and the row multiplier R_COEF of the reduced system for the next
+  // solve; the iteration itself refreshes them at its end, so this pass only runs after something else touched
+  // the row state or R_COEF (start, residual pass, refactorisation).
+  auto rows_coef = [&]() {
+    for (int r = kQpThreads - 1 - tid; r < q.nrows; r += kQpThreads) {
+      double* F = q.F(r);
+      const double s = F[R_WRR] * F[R_Z] - F[R_Y];
+      const double ra0 = q.sigma * F[R_XA0] - F[R_QA0] + F[R_U0] * s + F[R_B0] * (sysw.rho_aux * F[R_ZA0] - F[R_YA0]);
+      const double ra1 = q.sigma * F[R_XA1] - F[R_QA1] + F[R_U1] * s + F[R_B1] * (sysw.rho_aux * F[R_ZA1] - F[R_YA1]);
+      F[R_RA0] = ra0;
+      F[R_RA1] = ra1;
+      F[R_COEF] = row_reduce_coef(F, ra0, ra1, s);
+    }
+    __syncthreads();
+  };
+  auto admm_iteration = [&](bool keep_steps) {
+    // right-hand side  sigma x - q + A'(rho z - y)  (one thread per variable)
+    scatter_columns(q, [&](int i) {
+      const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
+      return q.sigma * q.x[i] - q.qs[i] + q.beta[i] * (rb * q.zb[i] - q.yb[i]);
+    });
+    bcr_solve<NB>(q, q.v1, q.w);
+    // rows: back-substitute aux, relax, project, dual update, and the multipliers for the next solve
+    const double inv_rho_aux = 1.0 / sysw.rho_aux;
+    for (int r = kQpThreads - 1 - tid; r < q.nrows; r += kQpThreads) {
+      const double* R = q.R(r);
+      double* F = q.F(r);
+      const double zeta = row_dot(q, R, q.I(r), q.w);
+      double a0, a1;
+      row_backsub(F, zeta, a0, a1);
+      const double zt = zeta + F[R_U0] * a0 + F[R_U1] * a1;
+      const double Wr = F[R_WRR];
+      const double zr = q.alpha * zt + (1.0 - q.alpha) * F[R_Z];
+      double zn = zr + F[R_Y] * F[R_IWRR];
+      zn = fmin(fmax(zn, F[R_LO]), F[R_UP]);
+      const double dy = Wr * (zr - zn);
+      const double yn = F[R_Y] + dy;
+      F[R_Z] = zn;
+      F[R_Y] = yn;
+      F[R_DY] = dy;
+      const double s = Wr * zn - yn;
+      double ra[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double at = k ? a1 : a0, bb = F[R_B0 + k];
+        const double xo = F[R_XA0 + k];
+        const double xn = q.alpha * at + (1.0 - q.alpha) * xo;
+        const double zra = q.alpha * (bb * at) + (1.0 - q.alpha) * F[R_ZA0 + k];
+        double z2 = zra + F[R_YA0 + k] * inv_rho_aux;
+        z2 = fmin(fmax(z2, 0.0), kOsqpInf * F[R_EA0 + k]);
+        const double dya = sysw.rho_aux * (zra - z2);
+        const double yan = F[R_YA0 + k] + dya;
+        F[R_XA0 + k] = xn;
+        F[R_DXA0 + k] = xn - xo;
+        F[R_ZA0 + k] = z2;
+        F[R_YA0 + k] = yan;
+        F[R_DYA0 + k] = dya;
+        ra[k] = q.sigma * xn - F[R_QA0 + k] + F[R_U0 + k] * s + bb * (sysw.rho_aux * z2 - yan);
+      }
+      F[R_RA0] = ra[0];
+      F[R_RA1] = ra[1];
+      F[R_COEF] = row_reduce_coef(F, ra[0], ra[1], s);
+    }
+    // trajectory variables and their bound rows (one thread per variable)
+    const double inv_rho = 1.0 / q.rho, inv_rho_eq = 1.0 / q.rho_eq;
+    for (int i = tid; i < N; i += kQpThreads) {
+      const double beta = q.beta[i];
+      const double lb = q.lbs[i], ub = q.ubs[i];
+      const bool beq = ub - lb < kRhoTol;
+      const double rb = beq ? q.rho_eq : q.rho, irb = beq ? inv_rho_eq : inv_rho;
+      const double xt = q.w[i];
+      const double xn = q.alpha * xt + (1.0 - q.alpha) * q.x[i];
+      const double zr = q.alpha * (beta * xt) + (1.0 - q.alpha) * q.zb[i];
+      double zn = zr + q.yb[i] * irb;
+      zn = fmin(fmax(zn, lb), ub);
+      const double dy = rb * (zr - zn);
+      if (keep_steps) {
+        dxs[i] = xn - q.x[i];
+        dyb[i] = dy;
+      }
+      q.x[i] = xn;
+      q.zb[i] = zn;
+      q.yb[i] += dy;
+    }
+    __syncthreads();
+  };
+
+  // ADMM iterations, continuing from the current state until a termination test fires, max_iter, or the
+  // slice budget is exhausted (status QPS_YIELD).
+  auto run_admm = [&]() {
+    status = QPS_UNSOLVED;
+    bool stop = false, need_coef = true;
+    while (!stop) {
+      if (iter >= st.max_iter) {  // max_iter reached without a verdict: approximate test, then MAX_ITER_REACHED
+        if (!(st.check_termination > 0 && (iter % st.check_termination == 0))) info_pass();
+        status = check_termination(true);
+        if (status == QPS_UNSOLVED) status = QPS_MAXITER;
+        stop = true;
+      } else if (budget <= 0) {
+        status = QPS_YIELD;
+        stop = true;
+      } else {
+        --budget;
+        ++iter;
+        const bool can_check = st.check_termination > 0 && (iter % st.check_termination == 0);
+        const bool rho_iter = st.adaptive_rho && st.adaptive_rho_interval > 0 && (iter % st.adaptive_rho_interval == 0);
+        if (need_coef) rows_coef();
+        need_coef = false;
+        admm_iteration(can_check || iter == st.max_iter);
+        if (can_check) {
+          info_pass();
+          status = check_termination(false);
+          need_coef = true;  // the residual passes reuse R_COEF
+          if (status != QPS_UNSOLVED) stop = true;
+        }
+        if (!stop && rho_iter) {
+          if (!can_check) info_pass();
+          need_coef = true;
+          // compute_rho_estimate on the scaled quantities [EXT]
+          const double pn = s_pri / (fmax(s_z, s_ax) + 1e-10);
+          const double dn = s_dua / (fmax(s_q, fmax(s_aty, s_px)) + 1e-10);
+          double rho_new = rho * sqrt(pn / (dn + 1e-10));
+          rho_new = fmin(fmax(rho_new, kRhoMin), kRhoMax);
+          if (rho_new > rho * st.adaptive_rho_tolerance || rho_new < rho / st.adaptive_rho_tolerance) {
+            rho = rho_new;
+            q.rho = rho;
+            q.rho_eq = kRhoEqOverIneq * rho;
+            sysw.rho_aux = rho;
+            out.rho_updates++;
+            if (!assemble_factor<NB>(q, sysw)) {
+              status = QPS_NONCVX;
+              stop = true;
+            }
+          }
+        }
+      }
+    }
+  };
+
+  // ---------------------------------------------------------------- polish (OSQP polish.c [EXT])
+  // Equality-constrained QP on the guessed active set, solved as the delta-regularised KKT system with
+  // iterative refinement, in its reduced form K_p = P + delta I + (1/delta) A_act' A_act (same aux
+  // elimination and block factor as the ADMM system).  Returns false when K_p could not be factored.
+  // `verified`: the polished point is primal feasible to kVerifyTol and every active inequality row has a
+  // correctly signed multiplier, i.e. it is a KKT point of the QP = the unique minimiser.
+  const double wp = 1.0 / st.delta;
+  const SysW pw{true, st.delta, 0.0};
+  auto polish_once = [&](bool& verified, double& p_pri, double& p_dua) -> bool {
+    verified = false;
+    for (int i = tid; i < q.Np; i += kQpThreads) {
+      const double z = q.zb[i], y = q.yb[i];
+      double w = 0.0;
+      if (i < N) {
+        if (z - q.lbs[i] < -y) w = -wp;           // lower active
+        else if (q.ubs[i] - z < y) w = wp;        // upper active
+      }
+      st_x[i] = q.x[i];
+      st_zb[i] = z;
+      st_yb[i] = y;
+      q.zb[i] = w;                                 // signed polish weight
+      q.x[i] = 0.0;                                // polish iterate
+      q.yb[i] = 0.0;                               // polish multiplier
+    }
+    for (int r = tid; r < q.nrows; r += kQpThreads) {
+      double* F = q.F(r);
+      const int naux = q.I(r)[RI_AUX];
+      double w = 0.0, b = 0.0;
+      if (F[R_Z] - F[R_LO] < -F[R_Y]) { w = -wp; b = F[R_LO]; }
+      else if (F[R_UP] - F[R_Z] < F[R_Y]) { w = wp; b = F[R_UP]; }
+      F[R_PW] = w;
+      F[R_PB] = b;
+      F[R_PY] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        double wa = 0.0;
+        if (k < naux) {
+          if (F[R_ZA0 + k] - 0.0 < -F[R_YA0 + k]) wa = -wp;                                    // lower (0) active
+          else if (kOsqpInf * F[R_EA0 + k] - F[R_ZA0 + k] < F[R_YA0 + k]) wa = wp;            // never in practice
+        }
+        F[R_PWA0 + k] = wa;
+        F[R_PYA0 + k] = 0.0;
+        F[R_PX0 + k] = 0.0;
+      }
+    }
+    __syncthreads();
+    if (!assemble_factor<NB>(q, pw)) return false;
+    for (int it = 0; it <= st.polish_refine_iter + 1; ++it) {
+      const bool last = (it == st.polish_refine_iter + 1);  // final pass: pending dual update + residuals only
+      p_matvec(q, q.x, q.v2);  // v2 <- P xq
+      double mm[3] = {0.0, 0.0, 0.0};  // m_pri (max), m_dua (max), bad signs (sum)
+      // rows: residual of the row, pending multiplier update, aux right-hand sides, row multiplier for A'
+      for (int r = tid; r < q.nrows; r += kQpThreads) {
+        const double* R = q.R(r);
+        double* F = q.F(r);
+        const int naux = q.I(r)[RI_AUX];
+        const double Wr = F[R_WRR];
+        const double ax = row_dot(q, R, q.I(r), q.x) + F[R_U0] * F[R_PX0] + F[R_U1] * F[R_PX1];
+        const double py = F[R_PY] + ((it > 0) ? Wr * (ax - F[R_PB]) : 0.0);
+        const double e = py + (last ? 0.0 : Wr * (ax - F[R_PB]));
+        const double zc = fmin(fmax(ax, F[R_LO]), F[R_UP]);
+        mm[0] = fmax(mm[0], fabs((ax - zc) / F[R_E]));
+        mm[2] += (last && Wr != 0.0 && naux == AUX_HINGE && py < -kVerifyTol) ? 1.0 : 0.0;  // upper active needs y >= 0
+        double pya[2], ra[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const double bb = F[R_B0 + k], u = F[R_U0 + k], qa = F[R_QA0 + k];
+          const double wa = fabs(F[R_PWA0 + k]);
+          const double axb = bb * F[R_PX0 + k];
+          pya[k] = F[R_PYA0 + k] + ((it > 0) ? wa * axb : 0.0);
+          const double ea = pya[k] + (last ? 0.0 : wa * axb);
+          mm[0] = fmax(mm[0], fabs((axb - fmax(axb, 0.0)) / F[R_EA0 + k]));
+          mm[2] += (last && wa != 0.0 && pya[k] > kVerifyTol) ? 1.0 : 0.0;  // aux >= 0 held at 0 needs y <= 0
+          mm[1] = fmax(mm[1], fabs((qa + u * py + bb * pya[k]) / F[R_DA0 + k]));
+          ra[k] = -qa - u * e - bb * ea;
+        }
+        F[R_PY] = py;
+        F[R_PYA0] = pya[0];
+        F[R_PYA1] = pya[1];
+        F[R_RA0] = ra[0];
+        F[R_RA1] = ra[1];
+        F[R_COEF] = last ? py : row_reduce_coef(F, ra[0], ra[1], -e);
+      }
+      __syncthreads();
+      if (last) {
+        // dual residual  P x + q + A'y  over the trajectory variables
+        scatter_columns(q, [&](int i) { return q.v2[i] + q.qs[i] + q.beta[i] * q.yb[i]; });
+      } else {
+        // rd = -(P x + q) - beta * (y + W (A x - b)) + A' coef
+        scatter_columns(q, [&](int i) {
+          const double beta = q.beta[i];
+          const double w = fabs(q.zb[i]);
+          const double bnd = q.zb[i] > 0 ? q.ubs[i] : q.lbs[i];
+          return -(q.v2[i] + q.qs[i]) - beta * (q.yb[i] + w * (beta * q.x[i] - bnd));
+        });
+      }
+      for (int i = tid; i < N; i += kQpThreads) {
+        const double beta = q.beta[i];
+        const double ax = beta * q.x[i];
+        const double w = fabs(q.zb[i]);
+        const double lb = q.lbs[i], ub = q.ubs[i];
+        const double zc = fmin(fmax(ax, lb), ub);
+        mm[0] = fmax(mm[0], fabs((ax - zc) * q.Dz[i] / beta));
+        const bool ineq = last && w != 0.0 && (ub - lb >= kRhoTol);
+        mm[2] += (ineq && q.zb[i] > 0 && q.yb[i] < -kVerifyTol) ? 1.0 : 0.0;
+        mm[2] += (ineq && q.zb[i] < 0 && q.yb[i] > kVerifyTol) ? 1.0 : 0.0;
+        if (last) mm[1] = fmax(mm[1], fabs(q.v1[i] / q.Dz[i]));
+      }
+      if (last) {
+        block_reduce<3>(q, mm, 0x4u);
+        p_pri = mm[0];
+        p_dua = mm[1] * q.cinv;
+        verified = (mm[2] == 0.0) && (p_pri <= kVerifyTol) && isfinite(p_pri) && isfinite(p_dua);
+      } else {
+        bcr_solve<NB>(q, q.v1, q.w);
+        for (int r = tid; r < q.nrows; r += kQpThreads) {
+          const double* R = q.R(r);
+          double* F = q.F(r);
+          double a0, a1;
+          row_backsub(F, row_dot(q, R, q.I(r), q.w), a0, a1);
+          F[R_PX0] += a0;
+          F[R_PX1] += a1;
+        }
+        for (int i = tid; i < N; i += kQpThreads) {
+          const double xn = q.x[i] + q.w[i];
+          // multiplier update of the variable-bound rows with the new iterate (the rows do theirs at the
+          // start of the next pass, where A x is recomputed anyway)
+          const double w = fabs(q.zb[i]);
+          q.yb[i] += w * (q.beta[i] * xn - (q.zb[i] > 0 ? q.ubs[i] : q.lbs[i]));
+          q.x[i] = xn;
+        }
+        __syncthreads();
+      }
+    }
+    return true;
+  };
+  auto restore_admm_state = [&](bool keep_polished_x) {
+    for (int i = tid; i < q.Np; i += kQpThreads) {
+      if (!keep_polished_x) q.x[i] = st_x[i];
+      q.zb[i] = st_zb[i];
+      q.yb[i] = st_yb[i];
+    }
+    __syncthreads();
+  };
+
+  // ---- main loop: ADMM -> polish -> verify; on a failed verification ADMM continues with 10x tighter ------
+  // tolerances (DESIGN.md deviation D2).
+  bool done = !factor_ok;
+  while (!done) {
+    run_admm();
+    out.pri_res = pri_res;
+    out.dua_res = dua_res;
+    if (status != QPS_SOLVED || !st.polishing) {
+      done = true;
+    } else {
+      bool verified = false;
+      double p_pri = 0.0, p_dua = 0.0;
+      const bool factored = polish_once(verified, p_pri, p_dua);
+      out.pol_factor_ok = factored ? 1 : 0;
+      out.pol_pri = p_pri;
+      out.pol_dua = p_dua;
+      out.rounds = round;
+      if (factored && verified) {
+        out.polish = 1;
+        done = true;
+      } else if (round >= kVerifyRounds || iter >= st.max_iter) {  // OSQP's acceptance rule
+        const bool ok = factored && ((p_pri < pri_res && p_dua < dua_res) || (p_pri < pri_res && dua_res < 1e-10) ||
+                                     (p_dua < dua_res && pri_res < 1e-10)) && isfinite(p_pri) && isfinite(p_dua);
+        out.polish = ok ? 2 : -1;
+        done = true;
+      } else {
+        ++round;
+        eps_scale *= 0.1;
+        restore_admm_state(false);
+        if (!assemble_factor<NB>(q, sysw)) {  // back to the ADMM factor
+          status = QPS_NONCVX;
+          done = true;
+        }
+      }
+    }
+  }
+  out.iters = iter;
+  out.status = status;
+  out.rho = rho;
+  out.c = q.c;
+  rs.iter = iter;
+  rs.round = round;
+  rs.rho = rho;
+  rs.eps_scale = eps_scale;
+  rs.rho_updates = out.rho_updates;
+  rs.c = q.c;
+  if (out.polish != 0) {
+    // Adopt the polished PRIMAL point when accepted.  The duals kept for the next warm start are always the
+    // ADMM duals: polished duals are non-unique on degenerate active sets (DESIGN.md deviation D1).
+    if (out.polish > 0) {
+      for (int r = tid; r < q.nrows; r += kQpThreads) {
+        double* F = q.F(r);
+        for (int k = 0; k < 2; ++k) F[R_XA0 + k] = F[R_PX0 + k];
+      }
+    }
+    restore_admm_state(out.polish > 0);
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Kernel: QP assembly (optimizers.cpp:781-799 + osqp_interface.cpp:170-281 in fixed layout) + solve slice.
+// grid = B, block = 256 (one CTA per trajectory).  DD = degrees of freedom (block size NB = 2*DD).
+template <int DD>
+__global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const double* x_override /*kernel-level API*/,
+                                                           const double* trust_override, int* admm_iters_out,
+                                                           int* polish_out, int slice) {
+  constexpr int NB = 2 * DD;
+  extern __shared__ double sm[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (!x_override && (p.status[b] != 5 || p.qp_done[b] != 0)) return;  // finished, or waiting for its evaluation
+  const int N = p.N, T = p.T, D = p.D;
+  QpCtx q;
+  q.N = N; q.T = T; q.D = D; q.tid = tid;
+  q.nb = NB;
+  q.M = qp_block_count(N, NB);
+  q.Np = q.M * NB;
+  q.CN = (p.row_stride - R_NF) / 2;
+  q.RS = p.row_stride;
+  const QpSmem S = qp_smem_layout(N, NB, q.RS, q.CN, p.max_rows);
+  q.SA = sm + S.SA; q.SLM = sm + S.SLM; q.SU = sm + S.SU; q.beta = sm + S.beta;
+  q.x = sm + S.x; q.zb = sm + S.zb; q.yb = sm + S.yb; q.v1 = sm + S.v1; q.w = sm + S.w;
+  q.qs = sm + S.qs; q.lbs = sm + S.lbs; q.ubs = sm + S.ubs; q.tmp = sm + S.tmp; q.red = sm + S.red;
+  q.flag = sm + S.red - 8;
+  q.colptr = reinterpret_cast<int*>(sm + S.colptr);
+  double* const rows_g = p.rows + static_cast<size_t>(b) * p.max_rows * p.row_stride;
+  int* const rints_g = p.row_ints + static_cast<size_t>(b) * p.max_rows * RI_NINTS;
+  q.rows = rows_g;
+  q.rints = rints_g;
+  int* mylist = p.lists + static_cast<size_t>(b) * p.list_stride;
+  int* colptr = mylist;                                   // [Np+1] master copy (shared copy in q.colptr)
+  int* colent = mylist + q.Np + 1;                        // [max_rows*CN]
+  int* obj_start = colent + static_cast<size_t>(p.max_rows) * q.CN;  // [n_objs+1]
+  q.colent = colent;
+  q.Pband = p.Pband;
+  // per-trajectory global vectors: dxs dyb st_x st_zb st_yb | scaled qs lbs ubs (master) | Dz | v2
+  double* gvec = p.scratch + static_cast<size_t>(b) * 10 * q.Np;
+  q.scratch = gvec;
+  double* g_qs = gvec + 5 * q.Np;
+  double* g_lbs = gvec + 6 * q.Np;
+  double* g_ubs = gvec + 7 * q.Np;
+  q.Dz = gvec + 8 * q.Np;
+  q.v2 = gvec + 9 * q.Np;
+  double* park = p.park + static_cast<size_t>(b) * 4 * q.Np;     // x zb yb beta of a parked solve
+  double *qs = q.qs, *lbs = q.lbs, *ubs = q.ubs;
+  int* meta = p.ws_meta + static_cast<size_t>(b) * 8;  // 0..3 warm-start key, 4 phase, 5 nrows, 6 n_aux, 7 nnzA
+  const int n_obj = p.n_costs + p.n_cnts;
+  QpResume rs{};
+  const bool resume = !x_override && meta[4] == 1;
+  int nr = 0, n_aux = 0, nnzA = 0;
+  bool warm = false;
+  int* sh_i = reinterpret_cast<int*>(q.flag + 2);  // small shared int scratch during assembly
+
+  if (!resume) {
+    const double* xc = (x_override ? x_override : p.x) + static_cast<size_t>(b) * N;
+    const double trust = trust_override ? trust_override[b] : p.trust[b];
+    const double* mu = p.merit_coeffs + static_cast<size_t>(b) * p.n_cnts;
+    const int buf = x_override ? 0 : p.cur_buf[b];
+    const size_t slot = static_cast<size_t>(buf) * p.B + b;
+    const double* cart_err = p.cart_err + slot * p.n_cart_rows;
+    const double* cart_jac = p.cart_jac + slot * static_cast<size_t>(p.n_cart_rows) * p.cart_stride;
+    const double* coll_rows = p.coll_rows + slot * static_cast<size_t>(p.n_coll_cand) * p.coll_stride;
+    const unsigned long long* coll_mask = p.coll_mask + slot * static_cast<size_t>(p.n_coll_objs) * p.coll_words;
+
+    // ---- trajectory part: x, trust box (setTrustBoxConstraints, optimizers.cpp:151-170), linear cost -----
+    for (int i = tid; i < N; i += kQpThreads) {
+      const double lb = p.lower[i % D], ub = p.upper[i % D];
+      const double xi = fmin(fmax(xc[i], lb), ub);
+      lbs[i] = fmax(fmax(xi - trust, lb), -kOsqpInf);
+      ubs[i] = fmin(fmin(xi + trust, ub), kOsqpInf);
+      qs[i] = p.qlin[i];
+      q.x[i] = xc[i];  // linearisation point (until the solver takes over x)
+    }
+    __syncthreads();
+
+    // ---- rows in the reference's canonical order: permanent rows, cost rows, penalised constraint rows -----
+    // (every record is padded: CN coefficients, zeros beyond the row's own count)
+    for (int f = tid; f < p.n_fixed; f += kQpThreads) {  // fixed_timesteps / fixed_dofs rows: x_k - init_k == 0
+      const int var = p.fixed_vars[f];
+      double* R = q.R(f);
+      int* I = q.rints + static_cast<size_t>(f) * RI_NINTS;
+      for (int k = 0; k < q.CN; ++k) R[k] = (k == 0) ? 1.0 : 0.0;
+      R[2 * q.CN + R_C] = -p.init_traj[static_cast<size_t>(b) * N + var];
+      R[2 * q.CN + R_W] = 0.0;
+      I[RI_BASE] = var; I[RI_CNT] = 1; I[RI_STRIDE] = D; I[RI_AUX] = AUX_NONE; I[RI_OBJ] = -1;
+    }
+    nr += p.n_fixed;
+    nnzA += p.n_fixed;
+    int coll_obj_counter = 0;
+    for (int oi = 0; oi < n_obj; ++oi) {
+      const bool is_cnt = oi >= p.n_costs;
+      const DevObj o = is_cnt ? p.cnt_objs[oi - p.n_costs] : p.cost_objs[oi];
+      if (tid == 0) obj_start[oi] = nr;
+      const double w_aux = is_cnt ? mu[oi - p.n_costs] : 1.0;
+      if (o.kind == OBJ_JOINT_EQ_COST) continue;
+      if (o.kind == OBJ_JOINT_EQ_CNT || o.kind == OBJ_JOINT_INEQ_CNT || o.kind == OBJ_JOINT_INEQ_COST) {
+        const DevJointTerm& jt = p.joint_terms[o.term];
+        const int per = (o.kind == OBJ_JOINT_EQ_CNT) ? 1 : 2;
+        const int total = o.n_steps * D * per;
+        const double wst[3][3] = {{1, 0, 0}, {-1, 1, 0}, {1, -2, 1}};
+        for (int k = tid; k < total; k += kQpThreads) {
+          const int t = o.first + k / (D * per), d = (k / per) % D, side = k % per;
+          double* R = q.R(nr + k);
+          int* I = q.rints + static_cast<size_t>(nr + k) * RI_NINTS;
+          const double cd = jt.coeffs[d];
+          double sgn = cd, cst;
+          if (per == 1) cst = -jt.targets[d] * cd;
+          else if (side == 0) cst = (-jt.targets[d] - jt.upper[d]) * cd;        // (e - upper) * c
+          else { sgn = -cd; cst = (jt.lower[d] + jt.targets[d]) * cd; }         // (lower - e) * c
+          for (int i = 0; i < q.CN; ++i) R[i] = (i <= o.order) ? wst[o.order][i] * sgn : 0.0;
+          R[2 * q.CN + R_C] = cst;
+          R[2 * q.CN + R_W] = w_aux;
+          I[RI_BASE] = t * D + d; I[RI_CNT] = o.order + 1; I[RI_STRIDE] = D;
+          I[RI_AUX] = (per == 1) ? AUX_ABS : AUX_HINGE; I[RI_OBJ] = oi;
+        }
+        nr += total;
+        n_aux += total * ((per == 1) ? 2 : 1);
+        nnzA += total * (o.order + 1 + ((per == 1) ? 2 : 1));
+      } else if (o.kind == OBJ_CART_POSE) {
+        const DevCartTerm& ct = p.cart_terms[o.term];
+        if (tid == 0) sh_i[0] = 0;
+        __syncthreads();
+        int nz = 0;
+        for (int k = tid; k < o.n_rows; k += kQpThreads) {
+          double* R = q.R(nr + k);
+          int* I = q.rints + static_cast<size_t>(nr + k) * RI_NINTS;
+          const double* J = cart_jac + static_cast<size_t>(o.src_off + k) * p.cart_stride;
+          const double thr = 1e-7 * fabs(ct.coeff[k]);  // cleanupAff acts on the unscaled gradient (modeling_utils.cpp:31-39)
+          double dot = 0.0;
+          for (int j = 0; j < q.CN; ++j) {
+            const double Jj = (j < D) ? J[j] : 0.0;
+            dot += Jj * q.x[o.first * D + min(j, D - 1)];
+            const double a = (fabs(Jj) > thr) ? Jj : 0.0;
+            R[j] = a;
+            nz += (a != 0.0);
+          }
+          R[2 * q.CN + R_C] = cart_err[o.src_off + k] - dot;
+          R[2 * q.CN + R_W] = w_aux;
+          I[RI_BASE] = o.first * D; I[RI_CNT] = D; I[RI_STRIDE] = 1; I[RI_AUX] = AUX_ABS; I[RI_OBJ] = oi;
+        }
+        if (nz) atomicAdd(&sh_i[0], nz);
+        __syncthreads();
+        nz = sh_i[0];
+        __syncthreads();
+        nr += o.n_rows;
+        n_aux += 2 * o.n_rows;
+        nnzA += nz + 2 * o.n_rows;
+      } else if (o.kind == OBJ_COLL) {
+        // active candidates of this timestep, in candidate order: thread 0 scans the mask and assigns slots
+        const unsigned long long* mw = coll_mask + static_cast<size_t>(coll_obj_counter) * p.coll_words;
+        ++coll_obj_counter;
+        // slot of candidate c = number of active candidates before it (popcount of the mask prefix)
+        if (tid == 0) { sh_i[0] = 0; sh_i[1] = 0; }
+        __syncthreads();
+        int nz = 0;
+        for (int c = tid; c < o.n_rows; c += kQpThreads) {
+          const bool act = (mw[c / 64] >> (c % 64)) & 1ull;
+          if (act) {
+            int before = 0;
+            for (int wdx = 0; wdx < c / 64; ++wdx) before += __popcll(mw[wdx]);
+            before += __popcll(mw[c / 64] & ((1ull << (c % 64)) - 1ull));
+            const int pos = nr + before;
+            double* R = q.R(pos);
+            int* I = q.rints + static_cast<size_t>(pos) * RI_NINTS;
+            const double* cr = coll_rows + static_cast<size_t>(o.src_off + c) * p.coll_stride;
+            // dist(q) ~ d0 + g.(q - q0);  constraint: coeff*(margin - dist) <= 0;  cost: hinge(margin - dist)*coeff
+            const double scale = is_cnt ? cr[D + 2] : 1.0;
+            double dot = 0.0;
+            for (int j = 0; j < q.CN; ++j) {
+              const double g = (j < D) ? cr[j] : 0.0;
+              dot += g * q.x[o.first * D + min(j, D - 1)];
+              const double a = -g * scale;
+              R[j] = (j < D) ? a : 0.0;
+              nz += (j < D && a != 0.0);
+            }
+            R[2 * q.CN + R_C] = (cr[D + 1] - cr[D] + dot) * scale;
+            R[2 * q.CN + R_W] = is_cnt ? w_aux : cr[D + 2];
+            I[RI_BASE] = o.first * D; I[RI_CNT] = D; I[RI_STRIDE] = 1; I[RI_AUX] = AUX_HINGE; I[RI_OBJ] = oi;
+          }
+        }
+        if (nz) atomicAdd(&sh_i[0], nz);
+        __syncthreads();
+        nz = sh_i[0];
+        int count = 0;
+        for (int wdx = 0; wdx < p.coll_words; ++wdx) count += __popcll(mw[wdx]);
+        __syncthreads();
+        nr += count;
+        n_aux += count;
+        nnzA += nz + count;
+      }
+    }
+    if (tid == 0) obj_start[n_obj] = nr;
+    nnzA += N + n_aux;  // identity rows carrying the variable bounds
+    __syncthreads();
+
+    // ---- per-column entry lists (canonical row order inside every column; real coefficients only) ---------
+    for (int i = tid; i <= q.Np; i += kQpThreads) colptr[i] = 0;
+    __syncthreads();
+    for (int r = tid; r < nr; r += kQpThreads) {
+      const int* I = q.I(r);
+      for (int k = 0; k < I[RI_CNT]; ++k) atomicAdd(&colptr[I[RI_BASE] + k * I[RI_STRIDE] + 1], 1);
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (int i = 0; i < q.Np; ++i) colptr[i + 1] += colptr[i];
+    __syncthreads();
+    // one thread per column walks the rows in canonical order (columns are short; rows are few)
+    for (int i = tid; i < N; i += kQpThreads) {
+      if (colptr[i + 1] == colptr[i]) continue;
+      int pos = colptr[i];
+      for (int r = 0; r < nr && pos < colptr[i + 1]; ++r) {
+        const int* I = q.I(r);
+        const int base = I[RI_BASE], stride = I[RI_STRIDE], cnt = I[RI_CNT];
+        const int off = i - base;
+        if (off >= 0 && off % stride == 0 && off / stride < cnt) colent[pos++] = (r << 5) | (off / stride);
+      }
+    }
+    __syncthreads();
+    q.nrows = nr;
+  } else {
+    nr = meta[5];
+    n_aux = meta[6];
+    nnzA = meta[7];
+    q.nrows = nr;
+  }
+  for (int i = tid; i <= q.Np; i += kQpThreads) q.colptr[i] = colptr[i];
+  __syncthreads();
+  // ---- the rows move into shared memory when they fit (the common case) ---------------------------------
+  const bool rows_in_smem = nr <= S.row_cap;
+  double* const rows_s = sm + S.rows;
+  const int fac_doubles = 3 * qp_even(q.M * NB * NB);
+  double* const park_fac = p.park_factor + static_cast<size_t>(b) * fac_doubles;
+  if (rows_in_smem) {
+    int* rints_s = reinterpret_cast<int*>(sm + S.rints);
+    int* colent_s = reinterpret_cast<int*>(sm + S.colent);
+    for (int t = tid; t < nr * q.RS; t += kQpThreads) rows_s[t] = rows_g[t];
+    for (int t = tid; t < nr * RI_NINTS; t += kQpThreads) rints_s[t] = rints_g[t];
+    for (int t = tid; t < q.colptr[q.Np]; t += kQpThreads) colent_s[t] = colent[t];
+    q.rows = rows_s;
+    q.rints = rints_s;
+    q.colent = colent_s;
+  }
+  if (resume)
+    for (int t = tid; t < fac_doubles; t += kQpThreads) q.SA[t] = park_fac[t];  // SA, SLM, SU are contiguous
+  __syncthreads();
+
+  if (!resume) {
+    // ---- warm start decision (createOrUpdateSolver, osqp_interface.cpp:283-370) ---------------------------
+    warm = !x_override && p.qp.warm_starting && meta[3] == 1 && meta[0] == n_aux && meta[1] == nr && meta[2] == nnzA;
+    qp_scale(q, p.qp, n_aux);
+    for (int i = tid; i < q.Np; i += kQpThreads) {  // master copies for the resume path
+      g_qs[i] = qs[i];
+      g_lbs[i] = lbs[i];
+      g_ubs[i] = ubs[i];
+    }
+  } else {
+    rs.iter = p.rs_int[b * 4 + 0];
+    rs.round = p.rs_int[b * 4 + 1];
+    rs.rho_updates = p.rs_int[b * 4 + 2];
+    rs.rho = p.rs_dbl[b * 4 + 0];
+    rs.eps_scale = p.rs_dbl[b * 4 + 1];
+    rs.c = p.rs_dbl[b * 4 + 2];
+    q.c = rs.c;
+    q.cinv = 1.0 / q.c;
+    for (int i = tid; i < q.Np; i += kQpThreads) {
+      q.x[i] = park[i];
+      q.zb[i] = park[q.Np + i];
+      q.yb[i] = park[2 * q.Np + i];
+      q.beta[i] = park[3 * q.Np + i];
+      qs[i] = g_qs[i];
+      lbs[i] = g_lbs[i];
+      ubs[i] = g_ubs[i];
+    }
+  }
+  __syncthreads();
+
+  QpOut res = qp_solve_block<NB>(q, p.qp, !resume, warm, p.ws_rho[b], p.ws_x + static_cast<size_t>(b) * N,
+                                 p.ws_yb + static_cast<size_t>(b) * N, rs, x_override ? (1 << 30) : slice, resume);
+  __syncthreads();
+
+  if (res.status == QPS_YIELD) {  // park the solve
+    for (int i = tid; i < q.Np; i += kQpThreads) {
+      park[i] = q.x[i];
+      park[q.Np + i] = q.zb[i];
+      park[2 * q.Np + i] = q.yb[i];
+      park[3 * q.Np + i] = q.beta[i];
+    }
+    for (int t = tid; t < fac_doubles; t += kQpThreads) park_fac[t] = q.SA[t];
+    if (rows_in_smem)
+      for (int t = tid; t < nr * q.RS; t += kQpThreads) rows_g[t] = rows_s[t];
+    if (tid == 0) {
+      meta[4] = 1; meta[5] = nr; meta[6] = n_aux; meta[7] = nnzA;
+      p.rs_int[b * 4 + 0] = rs.iter; p.rs_int[b * 4 + 1] = rs.round; p.rs_int[b * 4 + 2] = rs.rho_updates;
+      p.rs_dbl[b * 4 + 0] = rs.rho; p.rs_dbl[b * 4 + 1] = rs.eps_scale; p.rs_dbl[b * 4 + 2] = rs.c;
+    }
+    return;
+  }
+
+  // ---- unscale, store the solution (and the warm-start state), model values -----------------------------
+  double* nx = p.new_x + static_cast<size_t>(b) * N;
+  for (int i = tid; i < N; i += kQpThreads) {
+    const double xu = q.Dz[i] * q.x[i];
+    nx[i] = xu;
+    q.v1[i] = xu;  // unscaled solution for the model-value pass
+    p.ws_x[static_cast<size_t>(b) * N + i] = xu;
+    p.ws_yb[static_cast<size_t>(b) * N + i] = q.cinv * (q.beta[i] / q.Dz[i]) * q.yb[i];
+  }
+  __syncthreads();
+  for (int r = tid; r < nr; r += kQpThreads) {
+    double* R = q.R(r);
+    double* F = q.F(r);
+    const int* I = q.I(r);
+    const int aux = I[RI_AUX];
+    F[R_Y] = q.cinv * F[R_E] * F[R_Y];
+    for (int k = 0; k < 2; ++k) {
+      F[R_XA0 + k] = (k < aux) ? F[R_DA0 + k] * F[R_XA0 + k] : 0.0;
+      F[R_YA0 + k] = (k < aux) ? q.cinv * F[R_EA0 + k] * F[R_YA0 + k] : 0.0;
+    }
+    double val = F[R_C];
+    for (int i = 0; i < I[RI_CNT]; ++i) val += R[i] * q.v1[I[RI_BASE] + i * I[RI_STRIDE]];
+    // ConvexConstraints::violations (modeling.cpp:132-142) for constraint rows; hinge/abs cost = w * aux values
+    F[R_MV] = (aux == AUX_ABS || aux == AUX_NONE) ? fabs(val) : fmax(val, 0.0);
+  }
+  __syncthreads();
+  for (int oi = tid; oi < n_obj; oi += kQpThreads) {  // per object sums, canonical order, one thread per object
+    const bool is_cnt = oi >= p.n_costs;
+    double s = 0.0;
+    if (!is_cnt && p.cost_objs[oi].kind == OBJ_JOINT_EQ_COST) s = joint_obj_value(p, p.cost_objs[oi], q.v1);  // exact quadratic
+    for (int r = obj_start[oi]; r < obj_start[oi + 1]; ++r) {
+      const double* F = q.F(r);
+      if (is_cnt) s += F[R_MV];
+      else s += F[R_W] * (F[R_XA0] + F[R_XA1]);  // ConvexObjective::value: the penalty terms use the aux values
+    }
+    if (is_cnt) p.model_cnt_viols[static_cast<size_t>(b) * p.n_cnts + (oi - p.n_costs)] = s;
+    else p.model_cost_vals[static_cast<size_t>(b) * p.n_costs + oi] = s;
+  }
+  __syncthreads();
+  if (rows_in_smem)  // the unscaled primal / dual row state is the next QP's warm start
+    for (int t = tid; t < nr * q.RS; t += kQpThreads) rows_g[t] = rows_s[t];
+  if (tid == 0) {
+    // status map of osqp_interface.cpp:565-614
+    int cvx = 2;
+    if (res.status == QPS_SOLVED || res.status == QPS_SOLVED_INACC) cvx = 0;
+    else if (res.status >= QPS_PINF && res.status <= QPS_DINF_INACC) cvx = 1;
+    p.qp_status[b] = cvx;
+    meta[0] = n_aux; meta[1] = nr; meta[2] = nnzA; meta[3] = (cvx == 0) ? 1 : 0; meta[4] = 0;
+    p.ws_rho[b] = res.rho;
+    if (!x_override) {
+      p.n_admm_iters[b] += res.iters;
+      p.qp_done[b] = 1;
+    }
+    if (admm_iters_out) admm_iters_out[b] = res.iters;
+    if (polish_out) polish_out[b] = res.polish;
+    double* g = p.dbg + static_cast<size_t>(b) * 16;
+    g[0] = res.status; g[1] = res.iters; g[2] = res.polish; g[3] = res.rho; g[4] = res.pri_res; g[5] = res.dua_res;
+    g[6] = res.pol_pri; g[7] = res.pol_dua; g[8] = res.c; g[9] = res.pol_factor_ok; g[10] = res.rho_updates;
+    g[11] = nr; g[12] = n_aux; g[13] = nnzA; g[14] = warm ? 1 : 0; g[15] = res.rounds;
+  }
+}
+
+}  // namespace tb200

@@ -18,7 +18,7 @@
 
 #include "../../include/trajopt_b200.h"
 #include "eval_kernel.cuh"
-#include "qp_block_kernel.cuh"
+#include "qp_cta_kernel.cuh"
 
 using namespace tb200;
 
@@ -61,6 +61,18 @@ void quatToRot(const double* q, double* R) {
 }
 }  // namespace
 
+// QP kernel instances: the block size of the block-cyclic-reduction factor is a compile-time constant (2*D).
+using QpKernelFn = void (*)(DevProblem, const double*, const double*, int*, int*, int);
+static QpKernelFn qp_kernel_for(int D) {
+  switch (D) {
+    case 2: return qp_kernel<2>;
+    case 3: return qp_kernel<3>;
+    case 6: return qp_kernel<6>;
+    case 7: return qp_kernel<7>;
+    default: return nullptr;
+  }
+}
+
 struct tb200_problem {
   int device = 0;
   DevProblem dp{};
@@ -82,7 +94,7 @@ struct tb200_problem {
   DevBuf<DevCartTerm> cart_terms;
   DevBuf<int> fixed_vars;
   DevBuf<double> x, new_x, trust, merit_coeffs, cost_vals, cnt_viols, new_cost_vals, new_cnt_viols, model_cost_vals,
-      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace, park, rs_dbl;
+      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace, park, park_factor, rs_dbl;
   DevBuf<unsigned long long> coll_mask;
   DevBuf<int> status, sqp_iter, merit_round, qp_failures, qp_status, cur_buf, n_qp_solves, n_func_evals, n_admm_iters,
       active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish, trace_len, rs_int, qp_done;
@@ -96,7 +108,7 @@ struct tb200_problem {
     x.release(); new_x.release(); trust.release(); merit_coeffs.release(); cost_vals.release(); cnt_viols.release();
     new_cost_vals.release(); new_cnt_viols.release(); model_cost_vals.release(); model_cnt_viols.release();
     cart_err.release(); cart_jac.release(); coll_rows.release(); rows.release(); ws_x.release(); ws_yb.release();
-    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); park.release(); rs_dbl.release(); rs_int.release(); qp_done.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
+    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); park.release(); park_factor.release(); rs_dbl.release(); rs_int.release(); qp_done.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
     sqp_iter.release(); merit_round.release(); qp_failures.release(); qp_status.release(); cur_buf.release();
     n_qp_solves.release(); n_func_evals.release(); n_admm_iters.release(); active_count.release(); row_ints.release();
     lists.release(); ws_meta.release(); tmp_iters.release(); tmp_polish.release();
@@ -360,7 +372,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   // ---- kernel resources --------------------------------------------------------------------------------
   const EvalSmem es = eval_smem_layout(T, D, dp.L, P->ex.n_cart_objs, n_coll_cand, dp.n_coll_objs * dp.coll_words);
   P->eval_smem = static_cast<size_t>(es.total) * sizeof(double);
-  const QpSmem qs = qp_smem_layout(N, 2 * D);
+  const QpSmem qs = qp_smem_layout(N, 2 * D, dp.row_stride, std::max(D, 3), max_rows);
   const int Np = qp_block_count(N, 2 * D) * 2 * D;
   dp.list_stride = static_cast<size_t>(Np + 1) + static_cast<size_t>(max_rows) * std::max(D, 3) + dp.n_costs + dp.n_cnts + 2;
   P->qp_smem = static_cast<size_t>(qs.total) * sizeof(double);
@@ -369,7 +381,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   if ((qp_block_count(N, 2 * D) + 1) / 2 * 2 * D > kQpThreads)
     return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for one CTA per block-cyclic-reduction level");
   CK(cudaFuncSetAttribute(eval_convexify_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->eval_smem)));
-  CK(cudaFuncSetAttribute(qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->qp_smem)));
+  if (!qp_kernel_for(D)) return fail(TB200_ERR_UNSUPPORTED, "no QP kernel instance for this number of joints");
+  CK(cudaFuncSetAttribute(qp_kernel_for(D), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->qp_smem)));
   CK(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
   if (const char* e = std::getenv("TB200_SLICE")) P->slice = std::max(1, std::atoi(e));
 
@@ -405,7 +418,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   ALLOC(coll_mask, 2 * Bs * std::max(1, dp.n_coll_objs * dp.coll_words));
   ALLOC(rows, Bs * max_rows * dp.row_stride); ALLOC(row_ints, Bs * max_rows * RI_NINTS);
   ALLOC(lists, Bs * dp.list_stride);
-  ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 10 * Np); ALLOC(park, Bs * 4 * Np); ALLOC(rs_int, Bs * 4); ALLOC(rs_dbl, Bs * 4); ALLOC(qp_done, Bs); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 8);
+  ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 10 * Np); ALLOC(park, Bs * 4 * Np); ALLOC(park_factor, Bs * 3 * qp_even(qp_block_count(N, 2 * D) * 4 * D * D)); ALLOC(rs_int, Bs * 4); ALLOC(rs_dbl, Bs * 4); ALLOC(qp_done, Bs); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 8);
   ALLOC(status, Bs); ALLOC(sqp_iter, Bs); ALLOC(merit_round, Bs); ALLOC(qp_failures, Bs); ALLOC(qp_status, Bs);
   ALLOC(cur_buf, Bs); ALLOC(n_qp_solves, Bs); ALLOC(n_func_evals, Bs); ALLOC(n_admm_iters, Bs); ALLOC(active_count, 1);
   ALLOC(dbg, Bs * 16);
@@ -426,7 +439,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.cart_err = P->cart_err.p; dp.cart_jac = P->cart_jac.p; dp.coll_rows = P->coll_rows.p; dp.coll_mask = P->coll_mask.p;
   dp.rows = P->rows.p; dp.row_ints = P->row_ints.p; dp.lists = P->lists.p; dp.ws_x = P->ws_x.p; dp.ws_yb = P->ws_yb.p;
   dp.scratch = P->scratch.p; dp.ws_meta = P->ws_meta.p; dp.ws_rho = P->ws_rho.p; dp.dbg = P->dbg.p; dp.trace_len = P->trace_len.p; dp.trace = nullptr; dp.trace_cap = 0;
-  dp.park = P->park.p; dp.rs_int = P->rs_int.p; dp.rs_dbl = P->rs_dbl.p; dp.qp_done = P->qp_done.p;
+  dp.park = P->park.p; dp.park_factor = P->park_factor.p; dp.rs_int = P->rs_int.p; dp.rs_dbl = P->rs_dbl.p; dp.qp_done = P->qp_done.p;
   P->ex.cart_objs = P->d_cart_objs.p;
   P->ex.coll_objs = P->d_coll_objs.p;
   // settings
@@ -529,7 +542,7 @@ int tb200_solve_batch_resident(tb200_problem* P) {
   auto launch_qp = [&]() {
     const size_t i0 = ne;
     cudaEventRecord(getEvent(P, ne++), st);
-    qp_kernel<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, nullptr, nullptr, nullptr, nullptr, P->slice);
+    qp_kernel_for(P->D)<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, nullptr, nullptr, nullptr, nullptr, P->slice);
     cudaEventRecord(getEvent(P, ne++), st);
     spans.push_back({i0, 1});
   };
@@ -644,7 +657,7 @@ int tb200_qp_solve_batch(tb200_problem* P, const double* x, const double* trust,
   if (dp.n_cnts > 0) CK(cudaMemcpyAsync(P->merit_coeffs.p, merit_coeffs, B * dp.n_cnts * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(P->ws_meta.p, 0, B * 8 * sizeof(int), st));
   eval_convexify_decide_kernel<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
-  qp_kernel<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, P->x_tmp.p, P->trust_tmp.p, P->tmp_iters.p, P->tmp_polish.p, 1 << 30);
+  qp_kernel_for(P->D)<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, P->x_tmp.p, P->trust_tmp.p, P->tmp_iters.p, P->tmp_polish.p, 1 << 30);
   CK(cudaGetLastError());
   auto pull = [&](void* dst, const void* src, size_t n) {
     if (!dst || n == 0) return cudaSuccess;
