@@ -172,6 +172,10 @@ typedef struct tb200_qp_settings {
   int32_t polishing;        /* 1 (reference) */
   int32_t polish_refine_iter; /* 3 */
   int32_t warm_starting;    /* 1 */
+  int32_t early_polish_every; /* 25: also try the VERIFIED polish at every such check before ADMM has met its own
+                                 tolerances (DESIGN.md optimisation O1; same QP minimiser, fewer iterations);
+                                 0 = OSQP's order (polish only after ADMM converged) */
+  int32_t early_polish_from;  /* 25: first iteration at which the early polish is tried */
 } tb200_qp_settings;
 
 typedef struct tb200_problem_desc {

@@ -1,5 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see sco.hpp header comment).
 #include "sco.hpp"
+#include <cstdint>
+#include <atomic>
 
 #include <algorithm>
 #include <cassert>
@@ -423,6 +425,14 @@ void setRhoVec(Work& w, double rho) {
 }
 }  // namespace
 
+// splitmix64 finaliser: the per-row term of the active-set hash of optimisation O1
+static inline uint64_t guess_mix(uint64_t v) {
+  v += 0x9e3779b97f4a7c15ull;
+  v = (v ^ (v >> 30)) * 0xbf58476d1ce4e5b9ull;
+  v = (v ^ (v >> 27)) * 0x94d049bb133111ebull;
+  return v ^ (v >> 31);
+}
+
 QPResult qp_solve(const QP& qp, const QPSettings& s, const QPWarmStart* warm) {
   const int n = qp.n, m = qp.m;
   Work w;
@@ -546,6 +556,19 @@ QPResult qp_solve(const QP& qp, const QPSettings& s, const QPWarmStart* warm) {
   int status = QP_UNSOLVED, iter = 0;
   bool early_verified = false;
   std::function<bool(bool&)> polishOnce;
+  // hash of the active-set guess the polish would start from (order independent sum, wraps mod 2^64)
+  uint64_t prev_guess = 0, failed_guess = 0, pending_guess = 0;
+  bool have_prev_guess = false, have_failed_guess = false;
+  auto guessHash = [&]() -> uint64_t {
+    uint64_t h = 0;
+    for (int r = 0; r < m; ++r) {
+      int a = 0;
+      if (z[r] - w.l[r] < -y[r]) a = -1;
+      else if (w.u[r] - z[r] < y[r]) a = 1;
+      if (a) h += guess_mix(2 * static_cast<uint64_t>(r) + (a > 0 ? 1 : 0));
+    }
+    return h;
+  };
   // ADMM iterations, continuing from the current state until a termination test fires or max_iter.
   auto runAdmm = [&]() {
     status = QP_UNSOLVED;
@@ -576,13 +599,24 @@ QPResult qp_solve(const QP& qp, const QPSettings& s, const QPWarmStart* warm) {
         updateInfo();
         status = checkTermination(false);
         if (status != QP_UNSOLVED) return;
-        if (s.early_polish_every > 0 && iter >= s.early_polish_from && (iter % s.early_polish_every == 0)) {
+        bool try_early = s.early_polish_every > 0 && iter >= s.early_polish_from && (iter % s.early_polish_every == 0);
+        if (try_early && s.early_polish_stable) {
+          // only when the active-set guess has settled (same as at the previous test) and has not failed before
+          const uint64_t h = guessHash();
+          const bool stable = have_prev_guess && h == prev_guess;
+          prev_guess = h;
+          have_prev_guess = true;
+          try_early = stable && !(have_failed_guess && h == failed_guess);
+          if (try_early) pending_guess = h;
+        }
+        if (try_early) {
           // optimisation O1: try the polish before ADMM has met its own tolerances; a VERIFIED polished point is
           // the exact minimiser no matter how rough the iterate that produced the active-set guess was
           bool verified = false;
           const double keep_pri = pri_res, keep_dua = dua_res;
           const bool factored = polishOnce(verified);
           ++res.early_tries;
+          if (getenv("ORACLE_COUNT_TRIES")) { static std::atomic<long> n{0}; long v = ++n; if (v % 1000 == 0) fprintf(stderr, "early tries so far %ld\n", v); }
           if (factored && verified) {
             early_verified = true;
             status = QP_SOLVED;
@@ -590,6 +624,8 @@ QPResult qp_solve(const QP& qp, const QPSettings& s, const QPWarmStart* warm) {
           }
           (void)keep_pri;
           (void)keep_dua;
+          failed_guess = pending_guess;
+          have_failed_guess = true;
           updateInfo();  // the polish scratch vectors are shared with the residual bookkeeping
           if (!w.assemble(s.sigma, w.rho_vec)) {
             status = QP_NON_CVX;

@@ -104,6 +104,7 @@ struct QPSettings {
   double verify_tol = 1e-9;  // KKT verification: primal feasibility and multiplier-sign tolerance
   int early_polish_every = 0;  // >0: also try the (verified) polish every this many iterations (optimisation O1)
   int early_polish_from = 50;
+  int early_polish_stable = 1; // only try when the active-set guess is unchanged since the previous test and has not failed yet
 };
 enum QPStatus {
   QP_SOLVED = 1,

@@ -484,8 +484,9 @@ QPSettings qpSettingsFrom(const tb200_qp_settings& q) {
   s.max_iter = q.max_iter; s.scaling = q.scaling; s.check_termination = q.check_termination;
   s.adaptive_rho = q.adaptive_rho; s.adaptive_rho_interval = q.adaptive_rho_interval;
   s.polishing = q.polishing; s.polish_refine_iter = q.polish_refine_iter; s.warm_starting = q.warm_starting;
-  if (const char* e = getenv("ORACLE_EARLY_POLISH")) { s.early_polish_every = atoi(e); }
-  if (const char* e = getenv("ORACLE_EARLY_FROM")) { s.early_polish_from = atoi(e); }
+  s.early_polish_every = q.early_polish_every; s.early_polish_from = q.early_polish_from;
+  if (const char* e = getenv("ORACLE_EARLY_STABLE")) s.early_polish_stable = atoi(e);
+  if (const char* e = getenv("ORACLE_EARLY_EVERY")) s.early_polish_every = atoi(e);
   return s;
 }
 

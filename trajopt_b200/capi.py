@@ -67,7 +67,7 @@ class QpSettings(C.Structure):
                 ("delta", C.c_double), ("adaptive_rho_tolerance", C.c_double), ("max_iter", C.c_int32),
                 ("scaling", C.c_int32), ("check_termination", C.c_int32), ("adaptive_rho", C.c_int32),
                 ("adaptive_rho_interval", C.c_int32), ("polishing", C.c_int32), ("polish_refine_iter", C.c_int32),
-                ("warm_starting", C.c_int32)]
+                ("warm_starting", C.c_int32), ("early_polish_every", C.c_int32), ("early_polish_from", C.c_int32)]
 
 
 class ProblemDescC(C.Structure):
@@ -131,6 +131,7 @@ def default_qp_settings():
     s.max_iter, s.scaling, s.check_termination = 8192, 10, 25
     s.adaptive_rho, s.adaptive_rho_interval = 1, 50
     s.polishing, s.polish_refine_iter, s.warm_starting = 1, 3, 1
+    s.early_polish_every, s.early_polish_from = 25, 25  # optimisation O1; 0 = OSQP's order
     return s
 
 

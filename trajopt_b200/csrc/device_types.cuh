@@ -62,7 +62,7 @@ enum AuxKind { AUX_NONE = 0, AUX_HINGE = 1, AUX_ABS = 2 };
 struct QpSettings {
   double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, delta, adaptive_rho_tolerance;
   int max_iter, scaling, check_termination, adaptive_rho, adaptive_rho_interval, polishing, polish_refine_iter,
-      warm_starting;
+      warm_starting, early_polish_every, early_polish_from;
 };
 struct SqpParams {
   double improve_ratio_threshold, min_trust_box_size, min_approx_improve, min_approx_improve_frac;
@@ -132,6 +132,7 @@ struct DevProblem {
   double* park_factor;         // [B][3*M*nb*nb]: the block-cyclic-reduction factor of a parked QP
   int* rs_int;                 // [B][4] parked solver state
   double* rs_dbl;              // [B][4]
+  unsigned long long* rs_guess; // [B][2] parked active-set hashes (early polish)
   int* qp_done;                // [B] 1: a QP solution is waiting for its evaluation
   int* ws_meta;                // [B][8]: warm-start key (n_aux, rows, nnzA, last status), phase, parked sizes
   double* ws_rho;              // [B]

@@ -26,6 +26,15 @@
 
 namespace tb200 {
 
+#ifdef TB200_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_T0() const long long prof_t0_ = clock64()
+#define PROF_ADD(slot) do { if (q.tid == 0) atomicAdd(&g_prof[slot], (unsigned long long)(clock64() - prof_t0_)); } while (0)
+#else
+#define PROF_T0()
+#define PROF_ADD(slot)
+#endif
+
 constexpr int kQpThreads = 256;
 constexpr double kOsqpInf = 1e30;
 constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4;
@@ -158,91 +167,157 @@ __device__ __forceinline__ int row_var(const int* I, int k) {
 // ---------------------------------------------------------------------------------------------------
 // Block cyclic reduction: factorisation.  On entry SA[p] = K(p,p), SLM[p] = K(p,p-1) (p >= 1).  On exit
 // SA[p] = Ainv_p, SLM[p] = Um_p, SU[p] = Up_p for the level at which block p is eliminated.
+// One thread owns one matrix row (NB doubles in registers) in every phase; rows of the other operand are read
+// from shared memory as 16-byte broadcasts.
+template <int NB>
+__device__ __forceinline__ void load_row(double (&a)[NB], const double* src) {
+  const double2* s2 = reinterpret_cast<const double2*>(src);
+#pragma unroll
+  for (int k = 0; k < NB / 2; ++k) {
+    const double2 v = s2[k];
+    a[2 * k] = v.x;
+    a[2 * k + 1] = v.y;
+  }
+}
+template <int NB>
+__device__ __forceinline__ void store_row(double* dst, const double (&a)[NB]) {
+  double2* d2 = reinterpret_cast<double2*>(dst);
+#pragma unroll
+  for (int k = 0; k < NB / 2; ++k) d2[k] = make_double2(a[2 * k], a[2 * k + 1]);
+}
+// out[j] (+)= sum_k x[k] * Y[k][j]   (x in registers, Y row major in shared memory)
+template <int NB>
+__device__ __forceinline__ void row_times_mat(double (&out)[NB], const double (&x)[NB], const double* Y) {
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    double y[NB];
+    load_row<NB>(y, Y + k * NB);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) out[j] += x[k] * y[j];
+  }
+}
+// out[j] (+)= sum_k x[k] * Y[j][k]   (x times Y transposed)
+template <int NB>
+__device__ __forceinline__ void row_times_matT(double (&out)[NB], const double (&x)[NB], const double* Y) {
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    double y[NB];
+    load_row<NB>(y, Y + j * NB);
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < NB; k += 2) {
+      a0 += x[k] * y[k];
+      a1 += x[k + 1] * y[k + 1];
+    }
+    out[j] += a0 + a1;
+  }
+}
 template <int NB>
 __device__ inline bool bcr_factor(const QpCtx& q) {
-  constexpr int BLK = NB * NB;
+  constexpr int BLK = NB * NB, G = kQpThreads / 2;  // two thread groups work side by side where possible
   const int M = q.M, tid = q.tid;
+  const int grp = tid >= G, gt = tid - (grp ? G : 0);
   int bad = 0;
   for (int l = 0; (1 << l) - 1 < M; ++l) {
     const int s = 1 << l, first = s - 1, sh = l + 1;  // eliminated p = first + (e << sh); survivors j = p + s
-    const int nE = (M + s) >> sh, nS = M >> sh;
-    // ---- 1. Ainv_p in place (Gauss-Jordan without pivoting: the blocks are symmetric positive definite)
-    double* prow = q.tmp;             // [nE][NB]
-    double* pcol = q.tmp + nE * NB;   // [nE][NB]
-    for (int k = 0; k < NB; ++k) {
-      for (int t = tid; t < nE * NB; t += kQpThreads) {
-        const int e = t / NB, j = t % NB;
-        const double* A = q.SA + (first + (e << sh)) * BLK;
-        const double piv = A[k * NB + k];
-        if (j == k && !(piv > 0.0)) bad = 1;
-        const double ip = 1.0 / piv;
-        prow[t] = (j == k) ? ip : A[k * NB + j] * ip;
-        pcol[t] = A[j * NB + k];
+    const int nE = (M + s) >> sh, nS = M >> sh;       // host guarantees nE * NB <= G
+    // ---- 1. Ainv_p in place: Gauss-Jordan without pivoting (the blocks are symmetric positive definite);
+    //         thread (e,i) keeps row i of block e in registers, the pivot row goes through shared memory
+    {
+      const bool act = tid < nE * NB;
+      const int e = act ? tid / NB : 0, i = tid % NB;
+      double* A = q.SA + (first + (e << sh)) * BLK + i * NB;
+      double a[NB];
+      load_row<NB>(a, A);
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        double* prow = q.tmp + (k & 1) * (nE * NB) + e * NB;
+        if (act && i == k) {
+          const double piv = a[k];
+          if (!(piv > 0.0)) bad = 1;
+          const double ip = 1.0 / piv;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) a[j] = (j == k) ? ip : a[j] * ip;
+          store_row<NB>(prow, a);
+        }
+        __syncthreads();
+        if (act && i != k) {
+          double pr[NB];
+          load_row<NB>(pr, prow);
+          const double f = a[k];
+#pragma unroll
+          for (int j = 0; j < NB; ++j) a[j] = (j == k) ? -f * pr[k] : a[j] - f * pr[j];
+        }
       }
-      __syncthreads();
-      for (int t = tid; t < nE * BLK; t += kQpThreads) {
-        const int e = t / BLK, i = (t % BLK) / NB, j = t % NB;
-        double* A = q.SA + (first + (e << sh)) * BLK;
-        const double* pr = prow + e * NB;
-        const double f = pcol[e * NB + i];
-        const double upd = A[i * NB + j] - f * pr[j];
-        A[i * NB + j] = (i == k) ? pr[j] : ((j == k) ? -f * pr[k] : upd);
-      }
-      __syncthreads();
+      if (act) store_row<NB>(A, a);
     }
-    // ---- 2. Up_p = L_{p+s} Ainv_p -> SU[p];  Um_p = L_p' Ainv_p -> SU[p-s] (temporary home)
-    for (int t = tid; t < nE * BLK; t += kQpThreads) {
-      const int e = t / BLK, i = (t % BLK) / NB, j = t % NB;
+    __syncthreads();
+    // ---- 2. group 0: Up_p = L_{p+s} Ainv_p -> SU[p];  group 1: Um_p = L_p' Ainv_p -> SU[p-s] (temporary home)
+    {
+      const bool act = gt < nE * NB;
+      const int e = act ? gt / NB : 0, i = gt % NB;
       const int p = first + (e << sh);
       const double* Ai = q.SA + p * BLK;
-      if (p + s < M) {
-        const double* L2 = q.SLM + (p + s) * BLK + i * NB;
-        double up = 0.0;
+      if (act && grp == 0 && p + s < M) {
+        double x[NB], out[NB];
+        load_row<NB>(x, q.SLM + (p + s) * BLK + i * NB);
 #pragma unroll
-        for (int k = 0; k < NB; ++k) up += L2[k] * Ai[k * NB + j];
-        q.SU[p * BLK + i * NB + j] = up;
+        for (int j = 0; j < NB; ++j) out[j] = 0.0;
+        row_times_mat<NB>(out, x, Ai);
+        store_row<NB>(q.SU + p * BLK + i * NB, out);
       }
-      if (p - s >= 0) {
-        const double* L = q.SLM + p * BLK + i;
-        double um = 0.0;
+      if (act && grp == 1 && p - s >= 0) {
+        double x[NB], out[NB];
+        const double* L = q.SLM + p * BLK + i;  // column i of L_p
 #pragma unroll
-        for (int k = 0; k < NB; ++k) um += L[k * NB] * Ai[k * NB + j];
-        q.SU[(p - s) * BLK + i * NB + j] = um;
+        for (int k = 0; k < NB; ++k) x[k] = L[k * NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) out[j] = 0.0;
+        row_times_mat<NB>(out, x, Ai);
+        store_row<NB>(q.SU + (p - s) * BLK + i * NB, out);
       }
     }
     __syncthreads();
-    // ---- 3. survivors j:  A_j -= Up_{j-s} L_j' + Um_{j+s} L_{j+s}     (Um_{j+s} sits in SU[j])
-    for (int t = tid; t < nS * BLK; t += kQpThreads) {
-      const int e = t / BLK, i = (t % BLK) / NB, jj = t % NB;
-      const int j = first + s + (e << sh);
-      double acc = 0.0;
-      {
-        const double* Up = q.SU + (j - s) * BLK + i * NB;
-        const double* Lj = q.SLM + j * BLK + jj * NB;
-#pragma unroll
-        for (int k = 0; k < NB; ++k) acc += Up[k] * Lj[k];
-      }
-      if (j + s < M) {
-        const double* Um = q.SU + j * BLK + i * NB;
-        const double* Lp = q.SLM + (j + s) * BLK + jj;
-#pragma unroll
-        for (int k = 0; k < NB; ++k) acc += Um[k] * Lp[k * NB];
-      }
-      q.SA[j * BLK + i * NB + jj] -= acc;
-    }
-    __syncthreads();
-    // ---- 4. new left couplings of the survivors: L'_j = -Up_p L_p with p = j - s (0 without a left survivor)
-    for (int t = tid; t < nS * BLK; t += kQpThreads) {
-      const int e = t / BLK, i = (t % BLK) / NB, jj = t % NB;
+    // ---- 3./4. survivors j = p + s.  group 0: A_j -= Up_{j-s} L_j', and L'_j = -Up_{j-s} L_{j-s} (kept in registers);
+    //            group 1: t2 = Um_{j+s} L_{j+s} (Um_{j+s} sits in SU[j]), subtracted from A_j after the barrier
+    {
+      const bool act = gt < nS * NB;
+      const int e = act ? gt / NB : 0, i = gt % NB;
       const int j = first + s + (e << sh), p = j - s;
-      double acc = 0.0;
-      if (p - s >= 0) {
-        const double* Up = q.SU + p * BLK + i * NB;
-        const double* Lp = q.SLM + p * BLK + jj;
+      double keep[NB];
 #pragma unroll
-        for (int k = 0; k < NB; ++k) acc += Up[k] * Lp[k * NB];
+      for (int c = 0; c < NB; ++c) keep[c] = 0.0;
+      if (act && grp == 0) {
+        double x[NB], t1[NB];
+        load_row<NB>(x, q.SU + p * BLK + i * NB);  // row i of Up_p
+#pragma unroll
+        for (int c = 0; c < NB; ++c) t1[c] = 0.0;
+        row_times_matT<NB>(t1, x, q.SLM + j * BLK);
+        if (p - s >= 0) row_times_mat<NB>(keep, x, q.SLM + p * BLK);
+        double arow[NB];
+        load_row<NB>(arow, q.SA + j * BLK + i * NB);
+#pragma unroll
+        for (int c = 0; c < NB; ++c) arow[c] -= t1[c];
+        store_row<NB>(q.SA + j * BLK + i * NB, arow);
       }
-      q.SLM[j * BLK + i * NB + jj] = -acc;
+      if (act && grp == 1 && j + s < M) {
+        double x[NB];
+        load_row<NB>(x, q.SU + j * BLK + i * NB);  // row i of Um_{j+s}
+        row_times_mat<NB>(keep, x, q.SLM + (j + s) * BLK);
+      }
+      __syncthreads();
+      if (act && grp == 0) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) keep[c] = -keep[c];
+        store_row<NB>(q.SLM + j * BLK + i * NB, keep);  // new left coupling (0 without a left survivor)
+      }
+      if (act && grp == 1 && j + s < M) {
+        double arow[NB];
+        load_row<NB>(arow, q.SA + j * BLK + i * NB);
+#pragma unroll
+        for (int c = 0; c < NB; ++c) arow[c] -= keep[c];
+        store_row<NB>(q.SA + j * BLK + i * NB, arow);
+      }
     }
     __syncthreads();
     // ---- 5. Um_p moves from its temporary home into SLM[p] (L_p is dead now)
@@ -288,6 +363,7 @@ __device__ inline void bcr_solve(const QpCtx& q, double* v, double* w) {
   for (; (2 << l) - 1 < M; ++l) {
     const int s = 1 << l, sh = l + 1, nS = M >> sh;
     for (int tb = 0; tb < nS * NB; tb += kQpThreads / 2) {
+      if (tb + ((tid & ~31) >> 1) >= nS * NB) continue;  // warp-uniform: this warp has no task in this chunk
       const int task = tb + task0;
       const int e = task / NB, r = task % NB;
       const bool act = e < nS;
@@ -309,6 +385,7 @@ __device__ inline void bcr_solve(const QpCtx& q, double* v, double* w) {
     if (first >= M) continue;
     const int nE = (M + s) >> sh;
     for (int tb = 0; tb < nE * NB; tb += kQpThreads / 2) {
+      if (tb + ((tid & ~31) >> 1) >= nE * NB) continue;  // warp-uniform: this warp has no task in this chunk
       const int task = tb + task0;
       const int e = task / NB, r = task % NB;
       const bool act = e < nE;
@@ -338,14 +415,34 @@ __device__ inline void bcr_solve(const QpCtx& q, double* v, double* w) {
   }
 }
 
-// scaled P (band) times a vector: out = c * Dz .* (P (Dz .* in)); in: shared or global, out: global/shared
+// scaled P (band) times a vector: out = c * Dz .* (P (Dz .* in)); in: shared or global, out: global/shared.
+// The band loads are independent and fully unrolled, so the pass costs one memory round trip, not 2*HB+1.
+template <int NB>
 __device__ inline void p_matvec(const QpCtx& q, const double* in, double* out) {
-  const int N = q.N, HB = 2 * q.D, W = HB + 1;
+  constexpr int HB = NB, W = HB + 1;
+  const int N = q.N;
   for (int i = q.tid; i < q.Np; i += kQpThreads) {
     double s = 0.0;
     if (i < N) {
-      for (int k = 0; k <= HB && k <= i; ++k) s += q.Pband[i * W + k] * q.Dz[i - k] * in[i - k];
-      for (int k = 1; k <= HB && i + k < N; ++k) s += q.Pband[(i + k) * W + k] * q.Dz[i + k] * in[i + k];
+      double pl[W], pu[HB], xl[W], xu[HB];  // (P * Dz) and x, multiplied in the reference's order
+#pragma unroll
+      for (int k = 0; k <= HB; ++k) {
+        const bool on = k <= i;
+        const int j = on ? i - k : i;
+        pl[k] = (on ? q.Pband[i * W + k] : 0.0) * q.Dz[j];
+        xl[k] = in[j];
+      }
+#pragma unroll
+      for (int k = 1; k <= HB; ++k) {
+        const bool on = i + k < N;
+        const int j = on ? i + k : i;
+        pu[k - 1] = (on ? q.Pband[j * W + k] : 0.0) * q.Dz[j];
+        xu[k - 1] = in[j];
+      }
+#pragma unroll
+      for (int k = 0; k <= HB; ++k) s += pl[k] * xl[k];
+#pragma unroll
+      for (int k = 0; k < HB; ++k) s += pu[k] * xu[k];
       s *= q.c * q.Dz[i];
     }
     out[i] = s;
@@ -385,6 +482,7 @@ __device__ __forceinline__ double xbound_weight(const QpCtx& q, const SysW& w, i
 // (SA: diagonal blocks, SLM: left couplings); one thread per matrix row; then factor.
 template <int NB>
 __device__ inline bool assemble_factor(const QpCtx& q, const SysW& w) {
+  PROF_T0();
   rows_prepare_weights(q, w);
   constexpr int nb = NB, blk = NB * NB;
   const int N = q.N, HB = 2 * q.D, PW = HB + 1, CN = q.CN;
@@ -426,7 +524,10 @@ __device__ inline bool assemble_factor(const QpCtx& q, const SysW& w) {
     if (j > i) q.SA[static_cast<size_t>(p) * blk + i * nb + j] = q.SA[static_cast<size_t>(p) * blk + j * nb + i];
   }
   __syncthreads();
-  return bcr_factor<NB>(q);
+  PROF_ADD(10);
+  bool ok;
+  { PROF_T0(); ok = bcr_factor<NB>(q); PROF_ADD(11); }
+  return ok;
 }
 
 struct QpOut {
@@ -438,14 +539,14 @@ struct QpOut {
 
 // Persistent solver state of one QP between time slices.
 struct QpResume {
-  int iter, round, rho_updates, status;
+  int iter, round, rho_updates, status, guess_flags;  // guess_flags: bit 0 prev_guess valid, bit 1 failed_guess valid
   double rho, eps_scale, c;
+  unsigned long long prev_guess, failed_guess;      // active-set hashes of optimisation O1
 };
 
 // Scatter pass: v1[i] = base(i) + sum over the column entries of as[k] * R_COEF(row).
-template <class Base>
+template <int CN, class Base>
 __device__ __forceinline__ void scatter_columns(const QpCtx& q, Base base) {
-  const int CN = q.CN;
   for (int i = q.tid; i < q.Np; i += kQpThreads) {
     double s = 0.0;
     if (i < q.N) {
@@ -461,10 +562,12 @@ __device__ __forceinline__ void scatter_columns(const QpCtx& q, Base base) {
   __syncthreads();
 }
 // zeta_r = as . v(vars of the row); all CN (zero padded) coefficients
+template <int CN>
 __device__ __forceinline__ double row_dot(const QpCtx& q, const double* R, const int* I, const double* v) {
   double z = 0.0;
   const int base = I[RI_BASE], stride = I[RI_STRIDE], last = I[RI_CNT] - 1;
-  for (int k = 0; k < q.CN; ++k) z += R[q.CN + k] * v[base + min(k, last) * stride];
+#pragma unroll
+  for (int k = 0; k < CN; ++k) z += R[CN + k] * v[base + min(k, last) * stride];
   return z;
 }
 // aux back-substitution (cancellation free; absent aux slots have u = ra = 0 and g = 1 and come out 0)
@@ -617,6 +720,7 @@ template <int NB>
 __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fresh, bool warm, double warm_rho,
                                        const double* ws_x, const double* ws_yb, QpResume& rs, int slice,
                                        bool have_factor) {
+  constexpr int CNc = (NB / 2 > 3) ? NB / 2 : 3;  // coefficients per (padded) row
   const int N = q.N, tid = q.tid;
   QpOut out{QPS_UNSOLVED, 0, 0, st.rho, 0, 0, 0, 0, 0, -1, 0, 0};
   double rho;
@@ -652,7 +756,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
         F[R_Y] = F[R_Y] / F[R_E] * q.c;
         F[R_YA0] = (naux >= 1) ? F[R_YA0] / F[R_EA0] * q.c : 0.0;
         F[R_YA1] = (naux == 2) ? F[R_YA1] / F[R_EA1] * q.c : 0.0;
-        F[R_Z] = row_dot(q, R, q.I(r), q.x) + F[R_U0] * F[R_XA0] + F[R_U1] * F[R_XA1];
+        F[R_Z] = row_dot<CNc>(q, R, q.I(r), q.x) + F[R_U0] * F[R_XA0] + F[R_U1] * F[R_XA1];
         F[R_ZA0] = F[R_B0] * F[R_XA0];
         F[R_ZA1] = F[R_B1] * F[R_XA1];
       }
@@ -674,7 +778,8 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
     q.rho_eq = kRhoEqOverIneq * rho;
   }
   SysW sysw{false, st.sigma, rho};
-  const bool factor_ok = have_factor ? true : assemble_factor<NB>(q, sysw);  // a resumed solve brings its factor
+  bool factor_ok = true;
+  { PROF_T0(); if (!have_factor) factor_ok = assemble_factor<NB>(q, sysw); PROF_ADD(6); }  // a resumed solve brings its factor
 
   double* dxs = q.scratch;              // [Np] last trajectory step (written on check iterations)
   double* dyb = q.scratch + q.Np;       // [Np] last dual step of the variable-bound rows
@@ -683,17 +788,20 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
   double* st_yb = q.scratch + 4 * q.Np;
   double pri_res = 0.0, dua_res = 0.0;
   int status = factor_ok ? QPS_UNSOLVED : QPS_NONCVX, budget = slice;
+  bool early_verified = false;
+  unsigned long long prev_guess = fresh ? 0ull : rs.prev_guess, failed_guess = fresh ? 0ull : rs.failed_guess, pending_guess = 0ull;
+  bool have_prev_guess = fresh ? false : (rs.guess_flags & 1), have_failed_guess = fresh ? false : (rs.guess_flags & 2);
   double n_z = 0, n_ax = 0, n_q = 0, n_aty = 0, n_px = 0, s_pri = 0, s_dua = 0, s_z = 0, s_ax = 0, s_q = 0, s_aty = 0, s_px = 0;
 
   // ---------------------------------------------------------------- update_info(): residuals and norms
   auto info_pass = [&]() {
-    p_matvec(q, q.x, q.v2);  // v2 <- P x
+    p_matvec<NB>(q, q.x, q.v2);  // v2 <- P x
     double m[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     // 0 pri 1 z 2 ax 3 dua 4 aty 5 q 6 px | 7..13 the same on the scaled quantities
     for (int r = tid; r < q.nrows; r += kQpThreads) {
       const double* R = q.R(r);
       double* F = q.F(r);
-      const double ax = row_dot(q, R, q.I(r), q.x) + F[R_U0] * F[R_XA0] + F[R_U1] * F[R_XA1];
+      const double ax = row_dot<CNc>(q, R, q.I(r), q.x) + F[R_U0] * F[R_XA0] + F[R_U1] * F[R_XA1];
       const double einv = 1.0 / F[R_E];
       m[0] = fmax(m[0], fabs(einv * (ax - F[R_Z])));
       m[1] = fmax(m[1], fabs(einv * F[R_Z]));
@@ -724,7 +832,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
       F[R_COEF] = F[R_Y];
     }
     __syncthreads();
-    scatter_columns(q, [&](int i) { return q.beta[i] * q.yb[i]; });  // v1 <- A'y (trajectory part)
+    scatter_columns<CNc>(q, [&](int i) { return q.beta[i] * q.yb[i]; });  // v1 <- A'y (trajectory part)
     for (int i = tid; i < N; i += kQpThreads) {
       const double dz = q.Dz[i], beta = q.beta[i];
       const double ax = beta * q.x[i], aty = q.v1[i], px = q.v2[i];
@@ -775,7 +883,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
       a[1] += q.ubs[i] * fmax(d, 0.0) + q.lbs[i] * fmin(d, 0.0);
     }
     block_reduce<3>(q, a, 0x2u);
-    scatter_columns(q, [&](int i) { return q.beta[i] * dyb[i]; });
+    scatter_columns<CNc>(q, [&](int i) { return q.beta[i] * dyb[i]; });
     double mm[1] = {a[2]};
     for (int i = tid; i < N; i += kQpThreads) mm[0] = fmax(mm[0], fabs(q.v1[i] / q.Dz[i]));
     block_reduce<1>(q, mm, 0u);
@@ -801,7 +909,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
     }
     block_reduce<2>(q, a, 0x2u);
     const double ndx = a[0], qdx = a[1];
-    p_matvec(q, q.v1, q.v2);  // v2 <- P dx
+    p_matvec<NB>(q, q.v1, q.v2);  // v2 <- P dx
     double b2[2] = {0.0, 0.0};  // max |Dinv P dx|, bad count (sum)
     for (int i = tid; i < N; i += kQpThreads) {
       b2[0] = fmax(b2[0], fabs(q.v2[i] / q.Dz[i]));
@@ -812,7 +920,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
       const double* R = q.R(r);
       const double* F = q.F(r);
       const int naux = q.I(r)[RI_AUX];
-      const double ax = row_dot(q, R, q.I(r), q.v1) + F[R_U0] * F[R_DXA0] + F[R_U1] * F[R_DXA1];
+      const double ax = row_dot<CNc>(q, R, q.I(r), q.v1) + F[R_U0] * F[R_DXA0] + F[R_U1] * F[R_DXA1];
       const double vv = ax / F[R_E];
       b2[1] += (vv > eps * ndx) ? 1.0 : 0.0;                              // u finite for every row
       b2[1] += (naux != AUX_HINGE && vv < -eps * ndx) ? 1.0 : 0.0;        // l finite unless hinge
@@ -864,17 +972,22 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
   };
   auto admm_iteration = [&](bool keep_steps) {
     // right-hand side  sigma x - q + A'(rho z - y)  (one thread per variable)
-    scatter_columns(q, [&](int i) {
+    { PROF_T0();
+    scatter_columns<CNc>(q, [&](int i) {
       const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
       return q.sigma * q.x[i] - q.qs[i] + q.beta[i] * (rb * q.zb[i] - q.yb[i]);
     });
+    PROF_ADD(1); }
+    { PROF_T0();
     bcr_solve<NB>(q, q.v1, q.w);
+    PROF_ADD(2); }
+    PROF_T0();
     // rows: back-substitute aux, relax, project, dual update, and the multipliers for the next solve
     const double inv_rho_aux = 1.0 / sysw.rho_aux;
     for (int r = kQpThreads - 1 - tid; r < q.nrows; r += kQpThreads) {
       const double* R = q.R(r);
       double* F = q.F(r);
-      const double zeta = row_dot(q, R, q.I(r), q.w);
+      const double zeta = row_dot<CNc>(q, R, q.I(r), q.w);
       double a0, a1;
       row_backsub(F, zeta, a0, a1);
       const double zt = zeta + F[R_U0] * a0 + F[R_U1] * a1;
@@ -932,11 +1045,58 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
       q.yb[i] += dy;
     }
     __syncthreads();
+    PROF_ADD(3);
+  };
+
+  // ---------------------------------------------------------------- optimisation O1: when to try the polish early
+  // Hash of the active-set guess the polish would start from: an order-independent sum (mod 2^64) of one
+  // splitmix64 term per active row, keyed by the row's index in the canonical QP ([rows; trajectory bounds;
+  // aux bounds]) and the side it is active on.  The polish is tried early only when the guess is the same as at
+  // the previous test and has not failed before.
+  auto guess_mix = [](unsigned long long v) -> unsigned long long {
+    v += 0x9e3779b97f4a7c15ull;
+    v = (v ^ (v >> 30)) * 0xbf58476d1ce4e5b9ull;
+    v = (v ^ (v >> 27)) * 0x94d049bb133111ebull;
+    return v ^ (v >> 31);
+  };
+  auto early_guess_settled = [&]() -> bool {
+    unsigned long long h = 0ull;
+    const unsigned long long mc = static_cast<unsigned long long>(q.nrows);
+    for (int r = tid; r < q.nrows; r += kQpThreads) {
+      const double* F = q.F(r);
+      const int* I = q.I(r);
+      if (F[R_Z] - F[R_LO] < -F[R_Y]) h += guess_mix(2ull * r);
+      else if (F[R_UP] - F[R_Z] < F[R_Y]) h += guess_mix(2ull * r + 1ull);
+      for (int k = 0; k < I[RI_AUX]; ++k) {
+        const unsigned long long idx = mc + N + I[RI_PAD] + k;
+        if (F[R_ZA0 + k] - 0.0 < -F[R_YA0 + k]) h += guess_mix(2ull * idx);
+        else if (kOsqpInf * F[R_EA0 + k] - F[R_ZA0 + k] < F[R_YA0 + k]) h += guess_mix(2ull * idx + 1ull);
+      }
+    }
+    for (int i = tid; i < N; i += kQpThreads) {
+      const unsigned long long idx = mc + i;
+      if (q.zb[i] - q.lbs[i] < -q.yb[i]) h += guess_mix(2ull * idx);
+      else if (q.ubs[i] - q.zb[i] < q.yb[i]) h += guess_mix(2ull * idx + 1ull);
+    }
+    // block sum (wraps): butterfly inside the warp, then the 8 partials through shared memory
+    __syncwarp();
+    for (int off = 16; off > 0; off >>= 1) h += __shfl_xor_sync(0xffffffffu, h, off);
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(q.red);
+    if ((tid & 31) == 0) red[tid >> 5] = h;
+    __syncthreads();
+    h = 0ull;
+    for (int w = 0; w < kQpThreads / 32; ++w) h += red[w];
+    __syncthreads();
+    const bool stable = have_prev_guess && h == prev_guess;
+    prev_guess = h;
+    have_prev_guess = true;
+    pending_guess = h;
+    return stable && !(have_failed_guess && h == failed_guess);
   };
 
   // ADMM iterations, continuing from the current state until a termination test fires, max_iter, or the
   // slice budget is exhausted (status QPS_YIELD).
-  auto run_admm = [&]() {
+  auto run_admm = [&](auto& polish_fn, auto& restore_fn) {
     status = QPS_UNSOLVED;
     bool stop = false, need_coef = true;
     while (!stop) {
@@ -953,14 +1113,41 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
         ++iter;
         const bool can_check = st.check_termination > 0 && (iter % st.check_termination == 0);
         const bool rho_iter = st.adaptive_rho && st.adaptive_rho_interval > 0 && (iter % st.adaptive_rho_interval == 0);
-        if (need_coef) rows_coef();
+        { PROF_T0(); if (need_coef) rows_coef(); PROF_ADD(0); }
         need_coef = false;
         admm_iteration(can_check || iter == st.max_iter);
         if (can_check) {
+          PROF_T0();
           info_pass();
           status = check_termination(false);
+          PROF_ADD(5);
           need_coef = true;  // the residual passes reuse R_COEF
           if (status != QPS_UNSOLVED) stop = true;
+          else if (st.polishing && st.early_polish_every > 0 && iter >= st.early_polish_from &&
+                   (iter % st.early_polish_every == 0) && early_guess_settled()) {
+            // optimisation O1: try the polish before ADMM has met its own tolerances; a VERIFIED polished point
+            // is the exact minimiser no matter how rough the iterate that produced the active-set guess was
+            bool verified = false;
+            double p_pri = 0.0, p_dua = 0.0;
+            const bool factored = polish_fn(verified, p_pri, p_dua);
+            if (factored && verified) {
+              early_verified = true;
+              out.pol_factor_ok = 1;
+              out.pol_pri = p_pri;
+              out.pol_dua = p_dua;
+              status = QPS_SOLVED;
+              stop = true;
+            } else {
+              failed_guess = pending_guess;
+              have_failed_guess = true;
+              restore_fn(false);
+              info_pass();  // the polish reuses the vectors of the residual bookkeeping
+              if (!assemble_factor<NB>(q, sysw)) {
+                status = QPS_NONCVX;
+                stop = true;
+              }
+            }
+          }
         }
         if (!stop && rho_iter) {
           if (!can_check) info_pass();
@@ -995,6 +1182,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
   const double wp = 1.0 / st.delta;
   const SysW pw{true, st.delta, 0.0};
   auto polish_once = [&](bool& verified, double& p_pri, double& p_dua) -> bool {
+    PROF_T0();
     verified = false;
     for (int i = tid; i < q.Np; i += kQpThreads) {
       const double z = q.zb[i], y = q.yb[i];
@@ -1035,7 +1223,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
     if (!assemble_factor<NB>(q, pw)) return false;
     for (int it = 0; it <= st.polish_refine_iter + 1; ++it) {
       const bool last = (it == st.polish_refine_iter + 1);  // final pass: pending dual update + residuals only
-      p_matvec(q, q.x, q.v2);  // v2 <- P xq
+      p_matvec<NB>(q, q.x, q.v2);  // v2 <- P xq
       double mm[3] = {0.0, 0.0, 0.0};  // m_pri (max), m_dua (max), bad signs (sum)
       // rows: residual of the row, pending multiplier update, aux right-hand sides, row multiplier for A'
       for (int r = tid; r < q.nrows; r += kQpThreads) {
@@ -1043,7 +1231,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
         double* F = q.F(r);
         const int naux = q.I(r)[RI_AUX];
         const double Wr = F[R_WRR];
-        const double ax = row_dot(q, R, q.I(r), q.x) + F[R_U0] * F[R_PX0] + F[R_U1] * F[R_PX1];
+        const double ax = row_dot<CNc>(q, R, q.I(r), q.x) + F[R_U0] * F[R_PX0] + F[R_U1] * F[R_PX1];
         const double py = F[R_PY] + ((it > 0) ? Wr * (ax - F[R_PB]) : 0.0);
         const double e = py + (last ? 0.0 : Wr * (ax - F[R_PB]));
         const double zc = fmin(fmax(ax, F[R_LO]), F[R_UP]);
@@ -1072,10 +1260,10 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
       __syncthreads();
       if (last) {
         // dual residual  P x + q + A'y  over the trajectory variables
-        scatter_columns(q, [&](int i) { return q.v2[i] + q.qs[i] + q.beta[i] * q.yb[i]; });
+        scatter_columns<CNc>(q, [&](int i) { return q.v2[i] + q.qs[i] + q.beta[i] * q.yb[i]; });
       } else {
         // rd = -(P x + q) - beta * (y + W (A x - b)) + A' coef
-        scatter_columns(q, [&](int i) {
+        scatter_columns<CNc>(q, [&](int i) {
           const double beta = q.beta[i];
           const double w = fabs(q.zb[i]);
           const double bnd = q.zb[i] > 0 ? q.ubs[i] : q.lbs[i];
@@ -1105,7 +1293,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
           const double* R = q.R(r);
           double* F = q.F(r);
           double a0, a1;
-          row_backsub(F, row_dot(q, R, q.I(r), q.w), a0, a1);
+          row_backsub(F, row_dot<CNc>(q, R, q.I(r), q.w), a0, a1);
           F[R_PX0] += a0;
           F[R_PX1] += a1;
         }
@@ -1120,6 +1308,10 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
         __syncthreads();
       }
     }
+    PROF_ADD(12);
+#ifdef TB200_PROFILE
+    if (tid == 0) atomicAdd(&g_prof[13], 1ull);
+#endif
     return true;
   };
   auto restore_admm_state = [&](bool keep_polished_x) {
@@ -1135,10 +1327,14 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
   // tolerances (DESIGN.md deviation D2).
   bool done = !factor_ok;
   while (!done) {
-    run_admm();
+    run_admm(polish_once, restore_admm_state);
     out.pri_res = pri_res;
     out.dua_res = dua_res;
     if (status != QPS_SOLVED || !st.polishing) {
+      done = true;
+    } else if (early_verified) {
+      out.polish = 1;
+      out.rounds = round;
       done = true;
     } else {
       bool verified = false;
@@ -1177,6 +1373,9 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
   rs.eps_scale = eps_scale;
   rs.rho_updates = out.rho_updates;
   rs.c = q.c;
+  rs.prev_guess = prev_guess;
+  rs.failed_guess = failed_guess;
+  rs.guess_flags = (have_prev_guess ? 1 : 0) | (have_failed_guess ? 2 : 0);
   if (out.polish != 0) {
     // Adopt the polished PRIMAL point when accepted.  The duals kept for the next warm start are always the
     // ADMM duals: polished duals are non-unique on degenerate active sets (DESIGN.md deviation D1).
@@ -1276,7 +1475,7 @@ __global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const d
       for (int k = 0; k < q.CN; ++k) R[k] = (k == 0) ? 1.0 : 0.0;
       R[2 * q.CN + R_C] = -p.init_traj[static_cast<size_t>(b) * N + var];
       R[2 * q.CN + R_W] = 0.0;
-      I[RI_BASE] = var; I[RI_CNT] = 1; I[RI_STRIDE] = D; I[RI_AUX] = AUX_NONE; I[RI_OBJ] = -1;
+      I[RI_BASE] = var; I[RI_CNT] = 1; I[RI_STRIDE] = D; I[RI_AUX] = AUX_NONE; I[RI_OBJ] = -1; I[RI_PAD] = 0;
     }
     nr += p.n_fixed;
     nnzA += p.n_fixed;
@@ -1306,6 +1505,7 @@ __global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const d
           R[2 * q.CN + R_W] = w_aux;
           I[RI_BASE] = t * D + d; I[RI_CNT] = o.order + 1; I[RI_STRIDE] = D;
           I[RI_AUX] = (per == 1) ? AUX_ABS : AUX_HINGE; I[RI_OBJ] = oi;
+          I[RI_PAD] = n_aux + k * ((per == 1) ? 2 : 1);  // index of the row's first aux variable
         }
         nr += total;
         n_aux += total * ((per == 1) ? 2 : 1);
@@ -1331,6 +1531,7 @@ __global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const d
           R[2 * q.CN + R_C] = cart_err[o.src_off + k] - dot;
           R[2 * q.CN + R_W] = w_aux;
           I[RI_BASE] = o.first * D; I[RI_CNT] = D; I[RI_STRIDE] = 1; I[RI_AUX] = AUX_ABS; I[RI_OBJ] = oi;
+          I[RI_PAD] = n_aux + 2 * k;
         }
         if (nz) atomicAdd(&sh_i[0], nz);
         __syncthreads();
@@ -1370,6 +1571,7 @@ __global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const d
             R[2 * q.CN + R_C] = (cr[D + 1] - cr[D] + dot) * scale;
             R[2 * q.CN + R_W] = is_cnt ? w_aux : cr[D + 2];
             I[RI_BASE] = o.first * D; I[RI_CNT] = D; I[RI_STRIDE] = 1; I[RI_AUX] = AUX_HINGE; I[RI_OBJ] = oi;
+            I[RI_PAD] = n_aux + before;
           }
         }
         if (nz) atomicAdd(&sh_i[0], nz);
@@ -1441,7 +1643,7 @@ __global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const d
   if (!resume) {
     // ---- warm start decision (createOrUpdateSolver, osqp_interface.cpp:283-370) ---------------------------
     warm = !x_override && p.qp.warm_starting && meta[3] == 1 && meta[0] == n_aux && meta[1] == nr && meta[2] == nnzA;
-    qp_scale(q, p.qp, n_aux);
+    { PROF_T0(); qp_scale(q, p.qp, n_aux); PROF_ADD(7); }
     for (int i = tid; i < q.Np; i += kQpThreads) {  // master copies for the resume path
       g_qs[i] = qs[i];
       g_lbs[i] = lbs[i];
@@ -1454,6 +1656,9 @@ __global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const d
     rs.rho = p.rs_dbl[b * 4 + 0];
     rs.eps_scale = p.rs_dbl[b * 4 + 1];
     rs.c = p.rs_dbl[b * 4 + 2];
+    rs.guess_flags = p.rs_int[b * 4 + 3];
+    rs.prev_guess = p.rs_guess[b * 2 + 0];
+    rs.failed_guess = p.rs_guess[b * 2 + 1];
     q.c = rs.c;
     q.cinv = 1.0 / q.c;
     for (int i = tid; i < q.Np; i += kQpThreads) {
@@ -1468,9 +1673,14 @@ __global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const d
   }
   __syncthreads();
 
+  PROF_T0();
   QpOut res = qp_solve_block<NB>(q, p.qp, !resume, warm, p.ws_rho[b], p.ws_x + static_cast<size_t>(b) * N,
                                  p.ws_yb + static_cast<size_t>(b) * N, rs, x_override ? (1 << 30) : slice, resume);
   __syncthreads();
+  PROF_ADD(8);
+#ifdef TB200_PROFILE
+  if (tid == 0) atomicAdd(&g_prof[9], 1ull);
+#endif
 
   if (res.status == QPS_YIELD) {  // park the solve
     for (int i = tid; i < q.Np; i += kQpThreads) {
@@ -1486,6 +1696,7 @@ __global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const d
       meta[4] = 1; meta[5] = nr; meta[6] = n_aux; meta[7] = nnzA;
       p.rs_int[b * 4 + 0] = rs.iter; p.rs_int[b * 4 + 1] = rs.round; p.rs_int[b * 4 + 2] = rs.rho_updates;
       p.rs_dbl[b * 4 + 0] = rs.rho; p.rs_dbl[b * 4 + 1] = rs.eps_scale; p.rs_dbl[b * 4 + 2] = rs.c;
+      p.rs_int[b * 4 + 3] = rs.guess_flags; p.rs_guess[b * 2 + 0] = rs.prev_guess; p.rs_guess[b * 2 + 1] = rs.failed_guess;
     }
     return;
   }

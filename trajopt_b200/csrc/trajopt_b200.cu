@@ -95,6 +95,7 @@ struct tb200_problem {
   DevBuf<int> fixed_vars;
   DevBuf<double> x, new_x, trust, merit_coeffs, cost_vals, cnt_viols, new_cost_vals, new_cnt_viols, model_cost_vals,
       model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace, park, park_factor, rs_dbl;
+  DevBuf<unsigned long long> rs_guess;
   DevBuf<unsigned long long> coll_mask;
   DevBuf<int> status, sqp_iter, merit_round, qp_failures, qp_status, cur_buf, n_qp_solves, n_func_evals, n_admm_iters,
       active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish, trace_len, rs_int, qp_done;
@@ -108,7 +109,7 @@ struct tb200_problem {
     x.release(); new_x.release(); trust.release(); merit_coeffs.release(); cost_vals.release(); cnt_viols.release();
     new_cost_vals.release(); new_cnt_viols.release(); model_cost_vals.release(); model_cnt_viols.release();
     cart_err.release(); cart_jac.release(); coll_rows.release(); rows.release(); ws_x.release(); ws_yb.release();
-    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); park.release(); park_factor.release(); rs_dbl.release(); rs_int.release(); qp_done.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
+    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); park.release(); park_factor.release(); rs_dbl.release(); rs_guess.release(); rs_int.release(); qp_done.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
     sqp_iter.release(); merit_round.release(); qp_failures.release(); qp_status.release(); cur_buf.release();
     n_qp_solves.release(); n_func_evals.release(); n_admm_iters.release(); active_count.release(); row_ints.release();
     lists.release(); ws_meta.release(); tmp_iters.release(); tmp_polish.release();
@@ -145,6 +146,7 @@ void tb200_default_qp_settings(tb200_qp_settings* s) {  // osqp_interface.cpp:78
   s->max_iter = 8192; s->scaling = 10; s->check_termination = 25;
   s->adaptive_rho = 1; s->adaptive_rho_interval = 50;
   s->polishing = 1; s->polish_refine_iter = 3; s->warm_starting = 1;
+  s->early_polish_every = 25; s->early_polish_from = 25;
 }
 
 int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem** out) {
@@ -378,7 +380,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   P->qp_smem = static_cast<size_t>(qs.total) * sizeof(double);
   if (P->eval_smem > 227 * 1024 || P->qp_smem > 227 * 1024)
     return fail(TB200_ERR_UNSUPPORTED, "problem does not fit the 227 KB shared memory of one CTA");
-  if ((qp_block_count(N, 2 * D) + 1) / 2 * 2 * D > kQpThreads)
+  if ((qp_block_count(N, 2 * D) + 1) / 2 * 2 * D > kQpThreads / 2)
     return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for one CTA per block-cyclic-reduction level");
   CK(cudaFuncSetAttribute(eval_convexify_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->eval_smem)));
   if (!qp_kernel_for(D)) return fail(TB200_ERR_UNSUPPORTED, "no QP kernel instance for this number of joints");
@@ -418,7 +420,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   ALLOC(coll_mask, 2 * Bs * std::max(1, dp.n_coll_objs * dp.coll_words));
   ALLOC(rows, Bs * max_rows * dp.row_stride); ALLOC(row_ints, Bs * max_rows * RI_NINTS);
   ALLOC(lists, Bs * dp.list_stride);
-  ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 10 * Np); ALLOC(park, Bs * 4 * Np); ALLOC(park_factor, Bs * 3 * qp_even(qp_block_count(N, 2 * D) * 4 * D * D)); ALLOC(rs_int, Bs * 4); ALLOC(rs_dbl, Bs * 4); ALLOC(qp_done, Bs); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 8);
+  ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 10 * Np); ALLOC(park, Bs * 4 * Np); ALLOC(park_factor, Bs * 3 * qp_even(qp_block_count(N, 2 * D) * 4 * D * D)); ALLOC(rs_int, Bs * 4); ALLOC(rs_dbl, Bs * 4); ALLOC(rs_guess, Bs * 2); ALLOC(qp_done, Bs); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 8);
   ALLOC(status, Bs); ALLOC(sqp_iter, Bs); ALLOC(merit_round, Bs); ALLOC(qp_failures, Bs); ALLOC(qp_status, Bs);
   ALLOC(cur_buf, Bs); ALLOC(n_qp_solves, Bs); ALLOC(n_func_evals, Bs); ALLOC(n_admm_iters, Bs); ALLOC(active_count, 1);
   ALLOC(dbg, Bs * 16);
@@ -439,14 +441,15 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.cart_err = P->cart_err.p; dp.cart_jac = P->cart_jac.p; dp.coll_rows = P->coll_rows.p; dp.coll_mask = P->coll_mask.p;
   dp.rows = P->rows.p; dp.row_ints = P->row_ints.p; dp.lists = P->lists.p; dp.ws_x = P->ws_x.p; dp.ws_yb = P->ws_yb.p;
   dp.scratch = P->scratch.p; dp.ws_meta = P->ws_meta.p; dp.ws_rho = P->ws_rho.p; dp.dbg = P->dbg.p; dp.trace_len = P->trace_len.p; dp.trace = nullptr; dp.trace_cap = 0;
-  dp.park = P->park.p; dp.park_factor = P->park_factor.p; dp.rs_int = P->rs_int.p; dp.rs_dbl = P->rs_dbl.p; dp.qp_done = P->qp_done.p;
+  dp.park = P->park.p; dp.park_factor = P->park_factor.p; dp.rs_int = P->rs_int.p; dp.rs_dbl = P->rs_dbl.p; dp.rs_guess = P->rs_guess.p; dp.qp_done = P->qp_done.p;
   P->ex.cart_objs = P->d_cart_objs.p;
   P->ex.coll_objs = P->d_coll_objs.p;
   // settings
   const tb200_qp_settings& q = d->qp;
   dp.qp = QpSettings{q.rho, q.sigma, q.alpha, q.eps_abs, q.eps_rel, q.eps_prim_inf, q.eps_dual_inf, q.delta,
                      q.adaptive_rho_tolerance, q.max_iter, q.scaling, q.check_termination, q.adaptive_rho,
-                     q.adaptive_rho_interval, q.polishing, q.polish_refine_iter, q.warm_starting};
+                     q.adaptive_rho_interval, q.polishing, q.polish_refine_iter, q.warm_starting,
+                     q.early_polish_every, q.early_polish_from};
   const tb200_sqp_params& s = d->sqp;
   dp.sqp = SqpParams{s.improve_ratio_threshold, s.min_trust_box_size, s.min_approx_improve, s.min_approx_improve_frac,
                      s.trust_shrink_ratio, s.trust_expand_ratio, s.cnt_tolerance, s.max_merit_coeff_increases,
