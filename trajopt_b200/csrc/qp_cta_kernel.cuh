@@ -53,9 +53,9 @@ __device__ __forceinline__ double limit_scaling(double v) {
 // SA: A_p -> Ainv_p.  SLM: left couplings L_p during the factorisation, Um_p afterwards.  SU: Up_p (while a
 // level is being eliminated the still unused slot of the left survivor holds a temporary).
 struct QpSmem {
-  int SA, SLM, SU, beta, x, zb, yb, v1, w, qs, lbs, ubs, tmp, red, colptr, colent, rints, rows, total, row_cap;
+  int SA, SLM, SU, beta, x, zb, yb, v1, w, qs, lbs, ubs, Dz, v2, Pb, tmp, red, colptr, colent, rints, rows, total, row_cap;
 };
-constexpr int kQpSmemBudget = 14400;  // doubles per CTA: two CTAs per SM (227 KB / 2 minus the 1 KB reserve)
+constexpr int kQpSmemBudget = 20000;  // doubles per CTA (160 KB): one CTA per SM, the registers hold the factor rows
 __host__ __device__ inline int qp_block_count(int N, int nb) { return (N + nb - 1) / nb; }
 __host__ __device__ inline int qp_even(int v) { return (v + 1) & ~1; }
 __host__ __device__ inline QpSmem qp_smem_layout(int N, int nb, int row_stride, int CN, int max_rows) {
@@ -74,6 +74,9 @@ __host__ __device__ inline QpSmem qp_smem_layout(int N, int nb, int row_stride, 
   s.qs = o;   o += qp_even(Np);
   s.lbs = o;  o += qp_even(Np);
   s.ubs = o;  o += qp_even(Np);
+  s.Dz = o;   o += qp_even(Np);
+  s.v2 = o;   o += qp_even(Np);
+  s.Pb = o;   o += qp_even(N * (nb + 1));  // the objective's band P(i, i-k), shared by every trajectory
   s.tmp = o;  o += qp_even((M + 1) / 2 * 2 * nb) + 8;  // Gauss-Jordan pivot rows / columns, 8 scalars at the end
   s.red = o;  o += 16 * 8;                            // block reductions: 16 quantities x 8 warps
   s.colptr = o; o += qp_even((Np + 2) / 2 + 1);
@@ -105,17 +108,19 @@ enum RowF {
   R_MV,
   R_NF
 };
-__host__ __device__ inline int qp_row_stride(int CN) { return 2 * CN + R_NF; }
+// record = CN raw coefficients | CN scaled coefficients | R_NF fields | CN contributions as[k] * R_COEF of the
+// row to the right-hand side of the next ADMM solve
+__host__ __device__ inline int qp_row_stride(int CN) { return 3 * CN + R_NF; }
 
 struct QpCtx {
   int N, Np, nb, M, T, D, CN, RS, tid, nrows;
   double *SA, *SLM, *SU, *beta, *x, *zb, *yb, *v1, *w, *qs, *lbs, *ubs, *tmp, *red, *flag;   // shared (flag: 8 scalars)
   int* colptr;           // shared [Np+1]
-  double *Dz, *v2;       // global [Np] (used by the residual / polish passes only)
+  double *Dz, *v2;       // shared [Np]: variable scalings, scratch of the residual / polish passes
   double* rows;          // shared when the QP has at most row_cap rows, else global
   int* rints;
   const int* colent;     // entries: (row << 5) | k (shared or global, like the rows)
-  const double* Pband;   // global [N][2D+1]
+  const double* Pband;   // shared copy of the objective band [N][2D+1]
   double* scratch;
   double c, cinv, rho, rho_eq, sigma, alpha;
   __device__ __forceinline__ double* R(int r) const { return rows + static_cast<size_t>(r) * RS; }
@@ -413,6 +418,191 @@ __device__ inline void bcr_solve(const QpCtx& q, double* v, double* w) {
     }
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Register-resident variant of the solve for the ADMM loop.  The factor does not change between two
+// refactorisations, and every thread applies the same few matrix rows in every solve: level 0 gives each
+// thread one forward row (NB doubles) and one backward row (NB + NB/2), and the upper levels are spread over
+// the threads so that nobody owns more than one upper forward and one upper backward row.  A solve then
+// reads only the right-hand side from shared memory (16-byte broadcasts): per level ~NB loads instead of
+// ~3*NB, no bank conflicts, and a third of the instructions.
+struct SolveRoles {
+  int n_fwd, n_lvl;                       // forward levels, all levels (the last ones only go up)
+  int f0_warps, b0_warps;                 // thread ranges (rounded up to warps) with level-0 work
+  int f0_vec, f0_dst, b0_y, b0_wl, b0_dst;
+  int fu_level, fu_vec, fu_dst, bu_level, bu_y, bu_wl, bu_dst;
+  bool f0_valid, f0_store, b0_store, b0_hasl, b0_hasr, b0_yw;
+  bool fu_valid, fu_store, bu_store, bu_hasl, bu_hasr, bu_yw;  // *_yw: the NB-long operand is read from w, not v
+};
+template <int NB>
+__device__ inline SolveRoles solve_roles(const QpCtx& q) {
+  SolveRoles R{};
+  const int M = q.M, tid = q.tid;
+  int nf = 0;
+  while ((2 << nf) - 1 < M) ++nf;
+  int nl = 0;
+  while ((1 << nl) - 1 < M) ++nl;
+  R.n_fwd = nf;
+  R.n_lvl = nl;
+  auto fwd_role = [&](int l, int u, int& vec, int& dst, bool& valid, bool& store) {
+    const int s = 1 << l, sh = l + 1, nS = M >> sh;
+    const int task = u >> 1, side = u & 1, e = task / NB, r = task % NB;
+    const bool act = e < nS;
+    const int j = 2 * s - 1 + ((act ? e : 0) << sh);
+    const int pb = side ? j + s : j - s;
+    valid = act && pb < M;
+    vec = (valid ? pb : j - s) * NB;
+    dst = j * NB + r;
+    store = act && side == 0;
+  };
+  auto bwd_role = [&](int l, int u, int& y, int& wl, int& dst, bool& store, bool& hasl, bool& hasr, bool& yw) {
+    const int s = 1 << l, first = s - 1, sh = l + 1, nE = (M + s) >> sh;
+    const int task = u >> 1, side = u & 1, e = task / NB, r = task % NB;
+    const bool act = e < nE;
+    const int p = first + ((act ? e : 0) << sh);
+    hasl = p - s >= 0;
+    hasr = p + s < M;
+    yw = side;
+    y = side ? (hasr ? p + s : 0) * NB : p * NB;
+    wl = (hasl ? p - s : 0) * NB + (side ? NB / 2 : 0);
+    dst = p * NB + r;
+    store = act && side == 0;
+  };
+  // level 0: thread = (task, side)
+  fwd_role(0, tid, R.f0_vec, R.f0_dst, R.f0_valid, R.f0_store);
+  R.f0_warps = (2 * (M >> 1) * NB + 31) & ~31;
+  bwd_role(0, tid, R.b0_y, R.b0_wl, R.b0_dst, R.b0_store, R.b0_hasl, R.b0_hasr, R.b0_yw);
+  R.b0_warps = (2 * ((M + 1) >> 1) * NB + 31) & ~31;
+  // upper levels: consecutive thread ranges (even offsets keep the (u, u^1) pairs inside a warp)
+  R.fu_level = -1;
+  R.bu_level = -1;
+  int off = 0;
+  for (int l = 1; l < nf; ++l) {
+    const int cnt = 2 * (M >> (l + 1)) * NB;
+    if (tid >= off && tid < off + cnt) {
+      R.fu_level = l;
+      fwd_role(l, tid - off, R.fu_vec, R.fu_dst, R.fu_valid, R.fu_store);
+    }
+    off += cnt;
+  }
+  off = 0;
+  for (int l = 1; l < nl; ++l) {
+    const int cnt = 2 * ((M + (1 << l)) >> (l + 1)) * NB;
+    if (tid >= off && tid < off + cnt) {
+      R.bu_level = l;
+      bwd_role(l, tid - off, R.bu_y, R.bu_wl, R.bu_dst, R.bu_store, R.bu_hasl, R.bu_hasr, R.bu_yw);
+    }
+    off += cnt;
+  }
+  return R;
+}
+// true when the upper-level roles fit the CTA (host-checked as well)
+__host__ __device__ inline bool solve_roles_fit(int M, int NB) {
+  int f = 0, b = 0;
+  for (int l = 1; (2 << l) - 1 < M; ++l) f += 2 * (M >> (l + 1)) * NB;
+  for (int l = 1; (1 << l) - 1 < M; ++l) b += 2 * ((M + (1 << l)) >> (l + 1)) * NB;
+  return f <= kQpThreads && b <= kQpThreads && 2 * ((M + 1) >> 1) * NB <= kQpThreads;
+}
+// the thread's matrix rows, from the factor in shared memory
+template <int NB>
+__device__ __forceinline__ void load_fwd_row(const QpCtx& q, int l, int u, double (&m)[NB]) {
+  constexpr int BLK = NB * NB;
+  const int M = q.M, s = 1 << l, sh = l + 1, nS = M >> sh;
+  const int task = u >> 1, side = u & 1, e = task / NB, r = task % NB;
+  const bool act = e < nS;
+  const int j = 2 * s - 1 + ((act ? e : 0) << sh);
+  const int pb = side ? j + s : j - s;
+  const bool valid = act && pb < M;
+  const double* row = (side ? q.SLM : q.SU) + (valid ? pb : j - s) * BLK + r * NB;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) m[k] = valid ? row[k] : 0.0;
+}
+template <int NB>
+__device__ __forceinline__ void load_bwd_row(const QpCtx& q, int l, int u, double (&m)[NB + NB / 2]) {
+  constexpr int BLK = NB * NB, H = NB / 2;
+  const int M = q.M, s = 1 << l, first = s - 1, sh = l + 1, nE = (M + s) >> sh;
+  const int task = u >> 1, side = u & 1, e = task / NB, r = task % NB;
+  const bool act = e < nE;
+  const int p = first + ((act ? e : 0) << sh);
+  const double* X = (side ? q.SU : q.SA) + p * BLK + r;
+  const double* Um = q.SLM + p * BLK + (side ? H * NB : 0) + r;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) m[k] = act ? X[k * NB] : 0.0;
+#pragma unroll
+  for (int k = 0; k < H; ++k) m[NB + k] = act ? Um[k * NB] : 0.0;
+}
+template <int NB>
+__device__ __forceinline__ double fwd_dot(const double (&m)[NB], const double* y) {
+  const double2* y2 = reinterpret_cast<const double2*>(y);
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int k = 0; k < NB / 2; ++k) {
+    const double2 yy = y2[k];
+    a0 += m[2 * k] * yy.x;
+    a1 += m[2 * k + 1] * yy.y;
+  }
+  return a0 + a1;
+}
+template <int NB>
+__device__ __forceinline__ double bwd_dot(const double (&m)[NB + NB / 2], const double* y, const double* wl, bool side,
+                                          bool hasl, bool hasr) {
+  const double2* y2 = reinterpret_cast<const double2*>(y);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < NB / 2; ++k) {
+    const double2 yy = y2[k];
+    a0 += m[2 * k] * yy.x;
+    a1 += m[2 * k + 1] * yy.y;
+  }
+#pragma unroll
+  for (int k = 0; k < NB / 2; ++k) a2 += m[NB + k] * wl[k];
+  const double dx = a0 + a1;
+  return (side ? (hasr ? -dx : 0.0) : dx) - (hasl ? a2 : 0.0);
+}
+template <int NB>
+__device__ __forceinline__ void bcr_solve_reg(const QpCtx& q, const SolveRoles& R, const double (&mF0)[NB],
+                                              const double (&mB0)[NB + NB / 2], const double (&mFU)[NB],
+                                              const double (&mBU)[NB + NB / 2], double* v, double* w) {
+  const int tid = q.tid, wbase = tid & ~31;
+  const bool side = tid & 1;
+  __syncthreads();
+  // ---- down
+  if (wbase < R.f0_warps) {
+    double a = fwd_dot<NB>(mF0, v + R.f0_vec);
+    a = R.f0_valid ? a : 0.0;
+    const double o = __shfl_xor_sync(0xffffffffu, a, 1);
+    if (R.f0_store) v[R.f0_dst] -= a + o;
+  }
+  __syncthreads();
+  for (int l = 1; l < R.n_fwd; ++l) {
+    const bool mine = R.fu_level == l;
+    if (__any_sync(0xffffffffu, mine)) {
+      double a = fwd_dot<NB>(mFU, v + (mine ? R.fu_vec : 0));
+      a = (mine && R.fu_valid) ? a : 0.0;
+      const double o = __shfl_xor_sync(0xffffffffu, a, 1);
+      if (mine && R.fu_store) v[R.fu_dst] -= a + o;
+    }
+    __syncthreads();
+  }
+  // ---- up
+  for (int l = R.n_lvl - 1; l >= 1; --l) {
+    const bool mine = R.bu_level == l;
+    if (__any_sync(0xffffffffu, mine)) {
+      const double* y = (R.bu_yw ? w : v) + (mine ? R.bu_y : 0);
+      double acc = bwd_dot<NB>(mBU, y, w + (mine ? R.bu_wl : 0), R.bu_yw, R.bu_hasl, R.bu_hasr);
+      acc = mine ? acc : 0.0;
+      const double o = __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (mine && R.bu_store) w[R.bu_dst] = acc + o;
+    }
+    __syncthreads();
+  }
+  if (wbase < R.b0_warps) {
+    const double acc = bwd_dot<NB>(mB0, (side ? w : v) + R.b0_y, w + R.b0_wl, side, R.b0_hasl, R.b0_hasr);
+    const double o = __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (R.b0_store) w[R.b0_dst] = acc + o;
+  }
+  __syncthreads();
 }
 
 // scaled P (band) times a vector: out = c * Dz .* (P (Dz .* in)); in: shared or global, out: global/shared.
@@ -779,7 +969,27 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
   }
   SysW sysw{false, st.sigma, rho};
   bool factor_ok = true;
-  { PROF_T0(); if (!have_factor) factor_ok = assemble_factor<NB>(q, sysw); PROF_ADD(6); }  // a resumed solve brings its factor
+  { PROF_T0(); if (!have_factor) factor_ok = assemble_factor<NB>(q, sysw); PROF_ADD(6); }
+  // the thread's rows of the ADMM factor, kept in registers between refactorisations
+  const SolveRoles roles = solve_roles<NB>(q);
+  const int my_e0 = (tid < N) ? q.colptr[tid] : 0, my_e1 = (tid < N) ? q.colptr[tid + 1] : 0;
+  double mF0[NB], mB0[NB + NB / 2], mFU[NB], mBU[NB + NB / 2];
+  auto load_factor_regs = [&]() {
+    load_fwd_row<NB>(q, 0, tid, mF0);
+    load_bwd_row<NB>(q, 0, tid, mB0);
+    int off = 0;
+    for (int l = 1; l < roles.n_fwd; ++l) {
+      const int cnt = 2 * (q.M >> (l + 1)) * NB;
+      if (roles.fu_level == l) load_fwd_row<NB>(q, l, tid - off, mFU);
+      off += cnt;
+    }
+    off = 0;
+    for (int l = 1; l < roles.n_lvl; ++l) {
+      const int cnt = 2 * ((q.M + (1 << l)) >> (l + 1)) * NB;
+      if (roles.bu_level == l) load_bwd_row<NB>(q, l, tid - off, mBU);
+      off += cnt;
+    }
+  };  // a resumed solve brings its factor
 
   double* dxs = q.scratch;              // [Np] last trajectory step (written on check iterations)
   double* dyb = q.scratch + q.Np;       // [Np] last dual step of the variable-bound rows
@@ -883,6 +1093,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
       a[1] += q.ubs[i] * fmax(d, 0.0) + q.lbs[i] * fmin(d, 0.0);
     }
     block_reduce<3>(q, a, 0x2u);
+    if (!((a[0] > eps) && (a[1] < -eps * a[0]))) return false;  // block-uniform: the A'dy test cannot rescue it
     scatter_columns<CNc>(q, [&](int i) { return q.beta[i] * dyb[i]; });
     double mm[1] = {a[2]};
     for (int i = tid; i < N; i += kQpThreads) mm[0] = fmax(mm[0], fabs(q.v1[i] / q.Dz[i]));
@@ -909,6 +1120,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
     }
     block_reduce<2>(q, a, 0x2u);
     const double ndx = a[0], qdx = a[1];
+    if (!((ndx > eps) && (qdx < -q.c * eps * ndx))) return false;  // block-uniform: skip the P dx / A dx tests
     p_matvec<NB>(q, q.v1, q.v2);  // v2 <- P dx
     double b2[2] = {0.0, 0.0};  // max |Dinv P dx|, bad count (sum)
     for (int i = tid; i < N; i += kQpThreads) {
@@ -966,20 +1178,33 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
       const double ra1 = q.sigma * F[R_XA1] - F[R_QA1] + F[R_U1] * s + F[R_B1] * (sysw.rho_aux * F[R_ZA1] - F[R_YA1]);
       F[R_RA0] = ra0;
       F[R_RA1] = ra1;
-      F[R_COEF] = row_reduce_coef(F, ra0, ra1, s);
+      const double cf = row_reduce_coef(F, ra0, ra1, s);
+      F[R_COEF] = cf;
+      const double* as = q.R(r) + CNc;
+#pragma unroll
+      for (int k = 0; k < CNc; ++k) F[R_NF + k] = as[k] * cf;
     }
     __syncthreads();
   };
   auto admm_iteration = [&](bool keep_steps) {
     // right-hand side  sigma x - q + A'(rho z - y)  (one thread per variable)
     { PROF_T0();
-    scatter_columns<CNc>(q, [&](int i) {
-      const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
-      return q.sigma * q.x[i] - q.qs[i] + q.beta[i] * (rb * q.zb[i] - q.yb[i]);
-    });
+    {  // one thread per variable (N <= 256): its column range is loop invariant, the rows left their terms behind
+      const int i = tid;
+      double s = 0.0;
+      if (i < N) {
+        const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
+        s = q.sigma * q.x[i] - q.qs[i] + q.beta[i] * (rb * q.zb[i] - q.yb[i]);
+        for (int e = my_e0; e < my_e1; ++e) {
+          const int ent = q.colent[e];
+          s += q.rows[static_cast<size_t>(ent >> 5) * q.RS + (2 * CNc + R_NF) + (ent & 31)];
+        }
+      }
+      if (i < q.Np) q.v1[i] = s;
+    }
     PROF_ADD(1); }
     { PROF_T0();
-    bcr_solve<NB>(q, q.v1, q.w);
+    bcr_solve_reg<NB>(q, roles, mF0, mB0, mFU, mBU, q.v1, q.w);
     PROF_ADD(2); }
     PROF_T0();
     // rows: back-substitute aux, relax, project, dual update, and the multipliers for the next solve
@@ -1021,7 +1246,10 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
       }
       F[R_RA0] = ra[0];
       F[R_RA1] = ra[1];
-      F[R_COEF] = row_reduce_coef(F, ra[0], ra[1], s);
+      const double cf = row_reduce_coef(F, ra[0], ra[1], s);
+      F[R_COEF] = cf;
+#pragma unroll
+      for (int k = 0; k < CNc; ++k) F[R_NF + k] = R[CNc + k] * cf;
     }
     // trajectory variables and their bound rows (one thread per variable)
     const double inv_rho = 1.0 / q.rho, inv_rho_eq = 1.0 / q.rho_eq;
@@ -1098,7 +1326,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
   // slice budget is exhausted (status QPS_YIELD).
   auto run_admm = [&](auto& polish_fn, auto& restore_fn) {
     status = QPS_UNSOLVED;
-    bool stop = false, need_coef = true;
+    bool stop = false, need_coef = true, need_regs = true;
     while (!stop) {
       if (iter >= st.max_iter) {  // max_iter reached without a verdict: approximate test, then MAX_ITER_REACHED
         if (!(st.check_termination > 0 && (iter % st.check_termination == 0))) info_pass();
@@ -1115,6 +1343,8 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
         const bool rho_iter = st.adaptive_rho && st.adaptive_rho_interval > 0 && (iter % st.adaptive_rho_interval == 0);
         { PROF_T0(); if (need_coef) rows_coef(); PROF_ADD(0); }
         need_coef = false;
+        if (need_regs) load_factor_regs();
+        need_regs = false;
         admm_iteration(can_check || iter == st.max_iter);
         if (can_check) {
           PROF_T0();
@@ -1142,6 +1372,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
               have_failed_guess = true;
               restore_fn(false);
               info_pass();  // the polish reuses the vectors of the residual bookkeeping
+              need_regs = true;
               if (!assemble_factor<NB>(q, sysw)) {
                 status = QPS_NONCVX;
                 stop = true;
@@ -1163,6 +1394,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
             q.rho_eq = kRhoEqOverIneq * rho;
             sysw.rho_aux = rho;
             out.rho_updates++;
+            need_regs = true;
             if (!assemble_factor<NB>(q, sysw)) {
               status = QPS_NONCVX;
               stop = true;
@@ -1221,6 +1453,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
     }
     __syncthreads();
     if (!assemble_factor<NB>(q, pw)) return false;
+    load_factor_regs();  // the polish factor replaces the ADMM factor in the registers until the next reload
     for (int it = 0; it <= st.polish_refine_iter + 1; ++it) {
       const bool last = (it == st.polish_refine_iter + 1);  // final pass: pending dual update + residuals only
       p_matvec<NB>(q, q.x, q.v2);  // v2 <- P xq
@@ -1288,7 +1521,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
         p_dua = mm[1] * q.cinv;
         verified = (mm[2] == 0.0) && (p_pri <= kVerifyTol) && isfinite(p_pri) && isfinite(p_dua);
       } else {
-        bcr_solve<NB>(q, q.v1, q.w);
+        bcr_solve_reg<NB>(q, roles, mF0, mB0, mFU, mBU, q.v1, q.w);
         for (int r = tid; r < q.nrows; r += kQpThreads) {
           const double* R = q.R(r);
           double* F = q.F(r);
@@ -1394,7 +1627,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
 // Kernel: QP assembly (optimizers.cpp:781-799 + osqp_interface.cpp:170-281 in fixed layout) + solve slice.
 // grid = B, block = 256 (one CTA per trajectory).  DD = degrees of freedom (block size NB = 2*DD).
 template <int DD>
-__global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const double* x_override /*kernel-level API*/,
+__global__ void __launch_bounds__(kQpThreads, 1) qp_kernel(DevProblem p, const double* x_override /*kernel-level API*/,
                                                            const double* trust_override, int* admm_iters_out,
                                                            int* polish_out, int slice) {
   constexpr int NB = 2 * DD;
@@ -1408,7 +1641,7 @@ __global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const d
   q.nb = NB;
   q.M = qp_block_count(N, NB);
   q.Np = q.M * NB;
-  q.CN = (p.row_stride - R_NF) / 2;
+  q.CN = (p.row_stride - R_NF) / 3;
   q.RS = p.row_stride;
   const QpSmem S = qp_smem_layout(N, NB, q.RS, q.CN, p.max_rows);
   q.SA = sm + S.SA; q.SLM = sm + S.SLM; q.SU = sm + S.SU; q.beta = sm + S.beta;
@@ -1425,15 +1658,17 @@ __global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const d
   int* colent = mylist + q.Np + 1;                        // [max_rows*CN]
   int* obj_start = colent + static_cast<size_t>(p.max_rows) * q.CN;  // [n_objs+1]
   q.colent = colent;
-  q.Pband = p.Pband;
+  q.Pband = sm + S.Pb;
+  for (int t = tid; t < N * (NB + 1); t += kQpThreads) sm[S.Pb + t] = p.Pband[t];
   // per-trajectory global vectors: dxs dyb st_x st_zb st_yb | scaled qs lbs ubs (master) | Dz | v2
   double* gvec = p.scratch + static_cast<size_t>(b) * 10 * q.Np;
   q.scratch = gvec;
   double* g_qs = gvec + 5 * q.Np;
   double* g_lbs = gvec + 6 * q.Np;
   double* g_ubs = gvec + 7 * q.Np;
-  q.Dz = gvec + 8 * q.Np;
-  q.v2 = gvec + 9 * q.Np;
+  q.Dz = sm + S.Dz;
+  double* g_Dz = gvec + 8 * q.Np;  // master copy for the resume path
+  q.v2 = sm + S.v2;
   double* park = p.park + static_cast<size_t>(b) * 4 * q.Np;     // x zb yb beta of a parked solve
   double *qs = q.qs, *lbs = q.lbs, *ubs = q.ubs;
   int* meta = p.ws_meta + static_cast<size_t>(b) * 8;  // 0..3 warm-start key, 4 phase, 5 nrows, 6 n_aux, 7 nnzA
@@ -1648,6 +1883,7 @@ __global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const d
       g_qs[i] = qs[i];
       g_lbs[i] = lbs[i];
       g_ubs[i] = ubs[i];
+      g_Dz[i] = q.Dz[i];
     }
   } else {
     rs.iter = p.rs_int[b * 4 + 0];
@@ -1669,6 +1905,7 @@ __global__ void __launch_bounds__(kQpThreads, 2) qp_kernel(DevProblem p, const d
       qs[i] = g_qs[i];
       lbs[i] = g_lbs[i];
       ubs[i] = g_ubs[i];
+      q.Dz[i] = g_Dz[i];
     }
   }
   __syncthreads();

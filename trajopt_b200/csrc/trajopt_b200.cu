@@ -80,7 +80,7 @@ struct tb200_problem {
   tb200_layout layout{};
   int B = 0, T = 0, D = 0, N = 0;
   size_t eval_smem = 0, qp_smem = 0;
-  int slice = 100;  // ADMM iterations per QP per launch (TB200_SLICE overrides)
+  int slice = 500;  // ADMM iterations per QP per launch (TB200_SLICE overrides)
   cudaStream_t stream = nullptr;
   tb200_timing timing{};
   // host copies of the flattened description
@@ -382,6 +382,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
     return fail(TB200_ERR_UNSUPPORTED, "problem does not fit the 227 KB shared memory of one CTA");
   if ((qp_block_count(N, 2 * D) + 1) / 2 * 2 * D > kQpThreads / 2)
     return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for one CTA per block-cyclic-reduction level");
+  if (!solve_roles_fit(qp_block_count(N, 2 * D), 2 * D))
+    return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for the register-resident block-cyclic-reduction solve");
   CK(cudaFuncSetAttribute(eval_convexify_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->eval_smem)));
   if (!qp_kernel_for(D)) return fail(TB200_ERR_UNSUPPORTED, "no QP kernel instance for this number of joints");
   CK(cudaFuncSetAttribute(qp_kernel_for(D), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->qp_smem)));
