@@ -96,6 +96,14 @@ class Problem:
         out["cnt_viols"] = out["cnt_viols"][:, :L.n_cnts]
         return out
 
+    def convexify_timed(self, x):
+        """One full-batch launch of the convexify kernel at `x` without fetching its rows; returns the device
+        time (CUDA events on the launching stream) and the algorithmic bytes of the launch."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        co = capi.ConvexifyOut(None, None, None, None, None)
+        self._check(self.lib.tb200_convexify_batch(self.handle, _dp(x), C.byref(co)))
+        return self.timing()
+
     def qp_solve(self, x, trust, merit_coeffs):
         L, d = self.layout, self.desc
         x = np.ascontiguousarray(x, dtype=np.float64)

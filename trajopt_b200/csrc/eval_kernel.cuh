@@ -115,6 +115,7 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
   if (mode != EVAL_ONLY && p.status[b] != 5 /*running == INVALID*/) return;
   if (mode == EVAL_STEP && p.qp_done[b] == 0) return;  // its QP is still being solved (time-sliced)
   const bool qp_failed = (mode == EVAL_STEP) && (p.qp_status[b] != 0);
+  if (tid == 0 && !qp_failed) atomicAdd(p.active_count + 1, 1);  // trajectories actually convexified (bench: bytes moved)
   const int n_mask_words = p.n_coll_objs * p.coll_words;
   const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_cand, n_mask_words);
   double* xs = sm + S.x;

@@ -424,7 +424,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   ALLOC(lists, Bs * dp.list_stride);
   ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 10 * Np); ALLOC(park, Bs * 4 * Np); ALLOC(park_factor, Bs * 3 * qp_even(qp_block_count(N, 2 * D) * 4 * D * D)); ALLOC(rs_int, Bs * 4); ALLOC(rs_dbl, Bs * 4); ALLOC(rs_guess, Bs * 2); ALLOC(qp_done, Bs); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 8);
   ALLOC(status, Bs); ALLOC(sqp_iter, Bs); ALLOC(merit_round, Bs); ALLOC(qp_failures, Bs); ALLOC(qp_status, Bs);
-  ALLOC(cur_buf, Bs); ALLOC(n_qp_solves, Bs); ALLOC(n_func_evals, Bs); ALLOC(n_admm_iters, Bs); ALLOC(active_count, 1);
+  ALLOC(cur_buf, Bs); ALLOC(n_qp_solves, Bs); ALLOC(n_func_evals, Bs); ALLOC(n_admm_iters, Bs); ALLOC(active_count, 2);
   ALLOC(dbg, Bs * 16);
   ALLOC(trace_len, Bs);
   ALLOC(x_tmp, Bs * N); ALLOC(trust_tmp, Bs); ALLOC(tmp_iters, Bs); ALLOC(tmp_polish, Bs);
@@ -494,7 +494,7 @@ int tb200_problem_set_inputs(tb200_problem* P, const double* init_traj, const do
 namespace {
 __global__ void reset_state_kernel(DevProblem p) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) *p.active_count = p.B;
+  if (b == 0) { p.active_count[0] = p.B; p.active_count[1] = 0; }
   if (b >= p.B) return;
   p.status[b] = 5;
   p.sqp_iter[b] = 1;
@@ -582,7 +582,9 @@ int tb200_solve_batch_resident(tb200_problem* P) {
   // rows and the exact values, per trajectory
   const int64_t per_traj = 8LL * (dp.N + static_cast<int64_t>(dp.n_coll_cand) * dp.coll_stride +
                                   static_cast<int64_t>(dp.n_cart_rows) * (dp.cart_stride + 1) + dp.n_costs + dp.n_cnts);
-  tm.convexify_bytes = per_traj * dp.B;  // per launch with every trajectory active
+  int counters[2] = {0, 0};
+  CK(cudaMemcpy(counters, dp.active_count, sizeof(counters), cudaMemcpyDeviceToHost));
+  tm.convexify_bytes = per_traj * counters[1];  // summed over all launches: trajectories actually convexified
   if (active > 0) return fail(TB200_ERR_CUDA, "SQP driver hit its step cap with trajectories still active");
   return TB200_OK;
 }
@@ -635,12 +637,25 @@ int tb200_convexify_batch(tb200_problem* P, const double* x, tb200_convexify_out
   const size_t B = dp.B;
   cudaStream_t st = P->stream;
   CK(cudaMemcpyAsync(P->x_tmp.p, x, B * dp.N * sizeof(double), cudaMemcpyHostToDevice, st));
+  cudaEvent_t e0 = getEvent(P, 0), e1 = getEvent(P, 1);
+  CK(cudaEventRecord(e0, st));
   eval_convexify_decide_kernel<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
+  CK(cudaEventRecord(e1, st));
   CK(cudaGetLastError());
   auto pull = [&](void* dst, const void* src, size_t n) {
     if (!dst || n == 0) return cudaSuccess;
     return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st);
   };
+  {  // device time and algorithmic bytes of this one full-batch launch (bench.py: roofline of the kernel)
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    P->timing = tb200_timing{};
+    P->timing.total_ms = P->timing.convexify_ms = ms;
+    P->timing.convexify_launches = 1;
+    P->timing.convexify_bytes = 8LL * (dp.N + static_cast<int64_t>(dp.n_coll_cand) * dp.coll_stride +
+                                       static_cast<int64_t>(dp.n_cart_rows) * (dp.cart_stride + 1) + dp.n_costs + dp.n_cnts) * dp.B;
+  }
   CK(pull(out->cart_err, dp.cart_err, B * dp.n_cart_rows * sizeof(double)));
   CK(pull(out->cart_jac, dp.cart_jac, B * dp.n_cart_rows * dp.cart_stride * sizeof(double)));
   CK(pull(out->coll_rows, dp.coll_rows, B * dp.n_coll_cand * dp.coll_stride * sizeof(double)));
