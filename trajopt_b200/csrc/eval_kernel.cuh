@@ -18,10 +18,10 @@ enum EvalMode { EVAL_INIT = 0, EVAL_STEP = 1, EVAL_ONLY = 2 };
 
 struct EvalSmem {
   // offsets in doubles into the dynamic shared buffer
-  int x, sph, jax, jor, cartf, viol, mask, misc, total;
+  int x, sph, jax, jor, cartf, viol, mask, misc, fr, terms, total;
 };
 __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_cart_objs, int n_coll_cand,
-                                                      int n_mask_words) {
+                                                      int n_mask_words, int S = 0, int n_joint_objs = 0) {
   EvalSmem s;
   int o = 0;
   s.x = o;      o += T * D;
@@ -32,49 +32,19 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   s.viol = o;   o += n_coll_cand;
   s.mask = o;   o += n_mask_words;
   s.misc = o;   o += 8;
+  s.fr = o;     o += (T + n_cart_objs * D) * S * 12;  // frames of every FK job: local, then (in place) world
+  s.terms = o;  o += n_joint_objs * 2 * T * D;        // per-(step, joint) terms of the joint-space objects
   s.total = o;
   return s;
 }
 
 struct EvalExtra {
-  int n_cart_objs, n_coll_objs;
+  int n_cart_objs, n_coll_objs, n_joint_objs, pad;
   const DevObj* cart_objs;   // pad0 = index in its own list (cost / cnt), is_cnt says which list
   const DevObj* coll_objs;
   int qtype[kMaxDof];                // joint type per trajectory column
   unsigned sphere_jmask[kMaxSpheres];  // which columns move each sphere
 };
-
-// FK of one configuration; emits the per-waypoint quantities the row writers need.
-__device__ inline void fk_emit(const DevProblem& p, const double* q, double* sph, double* jax, double* jor,
-                               int link, double* link_frame) {
-  Frame fr[kMaxSeg];
-  for (int s = 0; s < p.S; ++s) {
-    const DevSegment g = p.segs[s];
-    Frame loc;
-    segment_local(g, q, loc);
-    if (g.parent < 0)
-      fr[s] = loc;
-    else
-      frame_mul(fr[g.parent], loc, fr[s]);
-    if (g.q_index >= 0 && jax) {
-      const Frame& f = fr[s];
-      for (int i = 0; i < 3; ++i) {
-        jax[g.q_index * 3 + i] = f.R[i * 3] * g.axis[0] + f.R[i * 3 + 1] * g.axis[1] + f.R[i * 3 + 2] * g.axis[2];
-        jor[g.q_index * 3 + i] = f.p[i];
-      }
-    }
-  }
-  if (sph)
-    for (int s = 0; s < p.L; ++s) {
-      const DevSphere sp = p.spheres[s];
-      const Frame& f = fr[sp.segment];
-      for (int i = 0; i < 3; ++i) sph[s * 3 + i] = f.R[i * 3] * sp.c[0] + f.R[i * 3 + 1] * sp.c[1] + f.R[i * 3 + 2] * sp.c[2] + f.p[i];
-    }
-  if (link >= 0 && link_frame) {
-    for (int i = 0; i < 9; ++i) link_frame[i] = fr[link].R[i];
-    for (int i = 0; i < 3; ++i) link_frame[9 + i] = fr[link].p[i];
-  }
-}
 
 __device__ inline double joint_err(const double* x, int D, int order, int t, int d, double target) {
   double e;
@@ -117,7 +87,7 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
   const bool qp_failed = (mode == EVAL_STEP) && (p.qp_status[b] != 0);
   if (tid == 0 && !qp_failed) atomicAdd(p.active_count + 1, 1);  // trajectories actually convexified (bench: bytes moved)
   const int n_mask_words = p.n_coll_objs * p.coll_words;
-  const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_cand, n_mask_words);
+  const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_cand, n_mask_words, p.S, ex.n_joint_objs);
   double* xs = sm + S.x;
   unsigned long long* mask = reinterpret_cast<unsigned long long*>(sm + S.mask);
   int* misc = reinterpret_cast<int*>(sm + S.misc);
@@ -139,38 +109,77 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
     for (int i = tid; i < n_mask_words; i += kEvalThreads) mask[i] = 0ull;
     __syncthreads();
 
-    // ---- FK jobs: one per waypoint, plus D perturbed configurations per CartPose object --------
-    const int n_jobs = T + ex.n_cart_objs * D;
-    for (int job = tid; job < n_jobs; job += kEvalThreads) {
-      if (job < T) {
-        // nominal waypoint; also the nominal link frame of every CartPose object at this step
-        int link = -1;
-        double* lf = nullptr;
-        for (int c = 0; c < ex.n_cart_objs; ++c)
-          if (ex.cart_objs[c].first == job) {
-            link = ex.cart_objs[c].link;
-            lf = sm + S.cartf + c * (1 + D) * 12;
-          }
-        fk_emit(p, xs + job * D, sm + S.sph + job * L * 3, sm + S.jax + job * D * 3, sm + S.jor + job * D * 3, link, lf);
-        // (two CartPose objects on the same step with different links: handled below by a second pass)
-      } else {
-        const int c = (job - T) / D, i = (job - T) % D;
-        const DevObj& o = ex.cart_objs[c];
-        double q[kMaxDof];
-        for (int d = 0; d < D; ++d) q[d] = xs[o.first * D + d];
-        q[i] += 1e-5;  // DEFAULT_EPSILON, kinematic_terms.hpp:14
-        fk_emit(p, q, nullptr, nullptr, nullptr, o.link, sm + S.cartf + (c * (1 + D) + 1 + i) * 12);
+    // ---- FK: one job per waypoint, plus D perturbed configurations per CartPose object ---------------
+    // (1) local frames of every (job, segment) in parallel (this is where the sincos are), (2) the chain
+    // products, one lane per (job, frame row): row i of a world frame depends only on row i of the parent's,
+    // so the three lanes of a job never wait for each other, (3) emission of what the row writers need.
+    const int n_jobs = T + ex.n_cart_objs * D, Sg = p.S;
+    double* FR = sm + S.fr;
+    for (int w = tid; w < n_jobs * Sg; w += kEvalThreads) {
+      const int job = w / Sg, sg = w % Sg;
+      const DevSegment g = p.segs[sg];
+      double qv = 0.0;
+      if (g.q_index >= 0) {
+        if (job < T) qv = xs[job * D + g.q_index];
+        else {
+          const int c = (job - T) / D, i = (job - T) % D;
+          qv = xs[ex.cart_objs[c].first * D + g.q_index] + (g.q_index == i ? 1e-5 : 0.0);  // DEFAULT_EPSILON, kinematic_terms.hpp:14
+        }
+      }
+      Frame loc;
+      segment_local_q(g, qv, loc);
+      double* f = FR + static_cast<size_t>(w) * 12;
+      for (int i = 0; i < 9; ++i) f[i] = loc.R[i];
+      for (int i = 0; i < 3; ++i) f[9 + i] = loc.p[i];
+    }
+    __syncthreads();
+    for (int w = tid; w < ((n_jobs * 4 + 31) & ~31); w += kEvalThreads) {  // whole warps: __syncwarp below
+      // four lanes per job (three rows + one idle) so that the rows of a job always sit in the same warp
+      const bool act = w < n_jobs * 4 && (w & 3) < 3;
+      const int job = (w < n_jobs * 4) ? w / 4 : 0, i = (w & 3) % 3;
+      double* F = FR + static_cast<size_t>(job) * Sg * 12;
+      for (int sg = 0; sg < Sg; ++sg) {
+        const int parent = p.segs[sg].parent;
+        double l[12];
+        for (int k = 0; k < 12; ++k) l[k] = F[sg * 12 + k];
+        __syncwarp();  // the other rows of this job have read the local frame before it is overwritten
+        if (act && parent >= 0) {
+          const double* P = F + parent * 12;
+          const double r0 = P[i * 3], r1 = P[i * 3 + 1], r2 = P[i * 3 + 2], pi = P[9 + i];
+          F[sg * 12 + i * 3 + 0] = r0 * l[0] + r1 * l[3] + r2 * l[6];
+          F[sg * 12 + i * 3 + 1] = r0 * l[1] + r1 * l[4] + r2 * l[7];
+          F[sg * 12 + i * 3 + 2] = r0 * l[2] + r1 * l[5] + r2 * l[8];
+          F[sg * 12 + 9 + i] = r0 * l[9] + r1 * l[10] + r2 * l[11] + pi;
+        }
+        __syncwarp();
       }
     }
     __syncthreads();
-    // nominal frames for CartPose objects that share a timestep with another object
-    for (int c = tid; c < ex.n_cart_objs; c += kEvalThreads) {
-      bool shared_step = false;
-      for (int c2 = c + 1; c2 < ex.n_cart_objs; ++c2) shared_step |= (ex.cart_objs[c2].first == ex.cart_objs[c].first);
-      if (shared_step) {
-        const DevObj& o = ex.cart_objs[c];
-        fk_emit(p, xs + o.first * D, nullptr, nullptr, nullptr, o.link, sm + S.cartf + c * (1 + D) * 12);
+    // joint axes / origins per (waypoint, moving segment), sphere centres per (waypoint, sphere), link frames
+    for (int w = tid; w < T * Sg; w += kEvalThreads) {
+      const int t = w / Sg, sg = w % Sg;
+      const DevSegment& g = p.segs[sg];
+      if (g.q_index < 0) continue;
+      const double* f = FR + static_cast<size_t>(w) * 12;
+      double* jax = sm + S.jax + (t * D + g.q_index) * 3;
+      double* jor = sm + S.jor + (t * D + g.q_index) * 3;
+      for (int i = 0; i < 3; ++i) {
+        jax[i] = f[i * 3] * g.axis[0] + f[i * 3 + 1] * g.axis[1] + f[i * 3 + 2] * g.axis[2];
+        jor[i] = f[9 + i];
       }
+    }
+    for (int w = tid; w < T * L; w += kEvalThreads) {
+      const int t = w / L, sl = w % L;
+      const DevSphere sp = p.spheres[sl];
+      const double* f = FR + (static_cast<size_t>(t) * Sg + sp.segment) * 12;
+      double* sph = sm + S.sph + w * 3;
+      for (int i = 0; i < 3; ++i) sph[i] = f[i * 3] * sp.c[0] + f[i * 3 + 1] * sp.c[1] + f[i * 3 + 2] * sp.c[2] + f[9 + i];
+    }
+    for (int w = tid; w < ex.n_cart_objs * (1 + D) * 12; w += kEvalThreads) {
+      const int c = w / ((1 + D) * 12), col = (w / 12) % (1 + D), k = w % 12;
+      const DevObj& o = ex.cart_objs[c];
+      const int job = (col == 0) ? o.first : T + c * D + (col - 1);
+      sm[S.cartf + w] = FR[(static_cast<size_t>(job) * Sg + o.link) * 12 + k];
     }
     __syncthreads();
 
@@ -260,45 +269,81 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
     for (int i = tid; i < n_mask_words; i += kEvalThreads) p.coll_mask[slot * n_mask_words + i] = mask[i];
   }
 
-  if (mode == EVAL_ONLY) {
-    // tb200_convexify_batch: exact values only, no SQP state touched
-    __syncthreads();  // cart_err rows written by other threads of this CTA
-    for (int i = tid; i < p.n_costs + p.n_cnts; i += kEvalThreads) {
-      const bool is_cnt = i >= p.n_costs;
-      const DevObj& o = is_cnt ? p.cnt_objs[i - p.n_costs] : p.cost_objs[i];
-      double v = 0.0;
-      if (o.kind <= OBJ_JOINT_INEQ_CNT) v = joint_obj_value(p, o, xs);
-      else if (o.kind == OBJ_CART_POSE) {
-        const double* e = p.cart_err + slot * p.n_cart_rows + o.src_off;
-        for (int r = 0; r < o.n_rows; ++r) v += fabs(e[r]);
-      } else {
-        for (int r = 0; r < o.n_rows; ++r) v += sm[S.viol + o.src_off + r];
-      }
-      (is_cnt ? p.cnt_viols : p.cost_vals)[static_cast<size_t>(b) * (is_cnt ? p.n_cnts : p.n_costs) + (is_cnt ? i - p.n_costs : i)] = v;
-    }
-    return;
-  }
-
   // ---- exact values at the evaluated point (Cost::value / Constraint::violation) -------------------
-  double* out_cost = (mode == EVAL_INIT ? p.cost_vals : p.new_cost_vals) + static_cast<size_t>(b) * p.n_costs;
-  double* out_viol = (mode == EVAL_INIT ? p.cnt_viols : p.new_cnt_viols) + static_cast<size_t>(b) * p.n_cnts;
+  // Every object's value is the SEQUENTIAL sum of its terms in the reference's order (the merit decisions compare
+  // such sums), so the terms are produced in parallel and one lane adds them up in order: joint-space objects
+  // from the term buffer, collision objects by walking the non-zero candidates of the warp in lane order.
+  double* out_cost = (mode == EVAL_ONLY) ? p.cost_vals + static_cast<size_t>(b) * p.n_costs
+                                         : (mode == EVAL_INIT ? p.cost_vals : p.new_cost_vals) + static_cast<size_t>(b) * p.n_costs;
+  double* out_viol = (mode == EVAL_ONLY) ? p.cnt_viols + static_cast<size_t>(b) * p.n_cnts
+                                         : (mode == EVAL_INIT ? p.cnt_viols : p.new_cnt_viols) + static_cast<size_t>(b) * p.n_cnts;
   if (!qp_failed) {
-    __syncthreads();  // cart_err written by other threads of this CTA (global) -> make visible
-    for (int i = tid; i < p.n_costs + p.n_cnts; i += kEvalThreads) {
+    const int n_obj = p.n_costs + p.n_cnts;
+    double* terms = sm + S.terms;
+    // joint-space terms: slot j of the term buffer belongs to the j-th joint-space object in (costs, cnts) order
+    {
+      int slot_j = 0;
+      for (int i = 0; i < n_obj; ++i) {
+        const bool is_cnt = i >= p.n_costs;
+        const DevObj& o = is_cnt ? p.cnt_objs[i - p.n_costs] : p.cost_objs[i];
+        if (o.kind > OBJ_JOINT_INEQ_CNT) continue;
+        const DevJointTerm& jt = p.joint_terms[o.term];
+        double* tb = terms + static_cast<size_t>(slot_j) * 2 * T * D;
+        for (int w = tid; w < o.n_steps * D; w += kEvalThreads) {
+          const int t = o.first + w / D, d = w % D;
+          const double e = joint_err(xs, D, o.order, t, d, jt.targets[d]);
+          double v0, v1 = 0.0;
+          if (o.kind == OBJ_JOINT_EQ_COST) v0 = e * e * jt.coeffs[d];
+          else if (o.kind == OBJ_JOINT_EQ_CNT) v0 = fabs(e * e * jt.coeffs[d]);  // value() is c*e^2 while the row is c*e (trajectory_costs.cpp:160 vs 173)
+          else {
+            v0 = fmax((e - jt.upper[d]) * jt.coeffs[d], 0.0);
+            v1 = fmax((jt.lower[d] - e) * jt.coeffs[d], 0.0);
+          }
+          tb[2 * w] = v0;
+          tb[2 * w + 1] = v1;
+        }
+        ++slot_j;
+      }
+    }
+    __syncthreads();  // terms, collision violations (shared) and cart_err rows (global, this CTA) are complete
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int i = wid; i < n_obj; i += kEvalThreads / 32) {  // one warp per object
       const bool is_cnt = i >= p.n_costs;
       const DevObj& o = is_cnt ? p.cnt_objs[i - p.n_costs] : p.cost_objs[i];
       double v = 0.0;
-      if (o.kind <= OBJ_JOINT_INEQ_CNT) v = joint_obj_value(p, o, xs);
-      else if (o.kind == OBJ_CART_POSE) {
-        const double* e = p.cart_err + slot * p.n_cart_rows + o.src_off;
-        for (int r = 0; r < o.n_rows; ++r) v += fabs(e[r]);
+      if (o.kind <= OBJ_JOINT_INEQ_CNT) {
+        int slot_j = 0;
+        for (int k = 0; k < i; ++k) slot_j += ((k >= p.n_costs ? p.cnt_objs[k - p.n_costs] : p.cost_objs[k]).kind <= OBJ_JOINT_INEQ_CNT);
+        const double* tb = terms + static_cast<size_t>(slot_j) * 2 * T * D;
+        const bool two = o.kind == OBJ_JOINT_INEQ_COST || o.kind == OBJ_JOINT_INEQ_CNT;
+        if (lane == 0) {
+          if (two) for (int w = 0; w < 2 * o.n_steps * D; ++w) v += tb[w];
+          else for (int w = 0; w < o.n_steps * D; ++w) v += tb[2 * w];
+        }
+      } else if (o.kind == OBJ_CART_POSE) {
+        if (lane == 0) {
+          const double* e = p.cart_err + slot * p.n_cart_rows + o.src_off;
+          for (int r = 0; r < o.n_rows; ++r) v += fabs(e[r]);
+        }
       } else {
-        for (int r = 0; r < o.n_rows; ++r) v += sm[S.viol + o.src_off + r];
+        for (int r0 = 0; r0 < o.n_rows; r0 += 32) {
+          const int r = r0 + lane;
+          const double mine = (r < o.n_rows) ? sm[S.viol + o.src_off + r] : 0.0;
+          unsigned nz = __ballot_sync(0xffffffffu, mine != 0.0);
+          while (nz) {  // warp-uniform: add the non-zero terms in candidate order (zeros do not change the sum)
+            const int src = __ffs(nz) - 1;
+            v += __shfl_sync(0xffffffffu, mine, src);
+            nz &= nz - 1;
+          }
+        }
       }
-      if (is_cnt) out_viol[i - p.n_costs] = v;
-      else out_cost[i] = v;
+      if (lane == 0) {
+        if (is_cnt) out_viol[i - p.n_costs] = v;
+        else out_cost[i] = v;
+      }
     }
   }
+  if (mode == EVAL_ONLY) return;  // tb200_convexify_batch: exact values only, no SQP state touched
   __threadfence_block();
   __syncthreads();
 

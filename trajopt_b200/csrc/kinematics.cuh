@@ -23,14 +23,18 @@ __device__ __forceinline__ void frame_mul(const Frame& a, const Frame& b, Frame&
 }
 
 // Local transform of one segment: origin * motion(q).
+__device__ __forceinline__ void segment_local_q(const DevSegment& g, double qv, Frame& t);
 __device__ __forceinline__ void segment_local(const DevSegment& g, const double* q, Frame& t) {
+  segment_local_q(g, g.q_index >= 0 ? q[g.q_index] : 0.0, t);
+}
+__device__ __forceinline__ void segment_local_q(const DevSegment& g, double qv, Frame& t) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) t.R[i] = g.R[i];
 #pragma unroll
   for (int i = 0; i < 3; ++i) t.p[i] = g.p[i];
   if (g.joint_type == 1) {  // revolute: Rodrigues about the joint axis
     double sn, c;
-    sincos(q[g.q_index], &sn, &c);
+    sincos(qv, &sn, &c);
     const double v = 1.0 - c, x = g.axis[0], y = g.axis[1], z = g.axis[2];
     double m[9];
     m[0] = c + x * x * v;      m[1] = x * y * v - z * sn;  m[2] = x * z * v + y * sn;
@@ -44,7 +48,7 @@ __device__ __forceinline__ void segment_local(const DevSegment& g, const double*
 #pragma unroll
     for (int i = 0; i < 9; ++i) t.R[i] = r[i];
   } else if (g.joint_type == 2) {  // prismatic
-    const double d = q[g.q_index];
+    const double d = qv;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
       t.p[i] = g.p[i] + (g.R[i * 3] * g.axis[0] + g.R[i * 3 + 1] * g.axis[1] + g.R[i * 3 + 2] * g.axis[2]) * d;

@@ -363,6 +363,9 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.n_coll_objs = static_cast<int>(P->coll_objs.size());
   P->ex.n_cart_objs = static_cast<int>(P->cart_objs.size());
   P->ex.n_coll_objs = dp.n_coll_objs;
+  P->ex.n_joint_objs = 0;
+  for (const DevObj& o : P->cost_objs) P->ex.n_joint_objs += (o.kind <= OBJ_JOINT_INEQ_CNT);
+  for (const DevObj& o : P->cnt_objs) P->ex.n_joint_objs += (o.kind <= OBJ_JOINT_INEQ_CNT);
   P->layout.n_costs = dp.n_costs;
   P->layout.n_cnts = dp.n_cnts;
   P->layout.n_cart_rows = n_cart_rows;
@@ -372,7 +375,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   P->layout.n_vars = N;
 
   // ---- kernel resources --------------------------------------------------------------------------------
-  const EvalSmem es = eval_smem_layout(T, D, dp.L, P->ex.n_cart_objs, n_coll_cand, dp.n_coll_objs * dp.coll_words);
+  const EvalSmem es = eval_smem_layout(T, D, dp.L, P->ex.n_cart_objs, n_coll_cand, dp.n_coll_objs * dp.coll_words, dp.S,
+                                       P->ex.n_joint_objs);
   P->eval_smem = static_cast<size_t>(es.total) * sizeof(double);
   const QpSmem qs = qp_smem_layout(N, 2 * D, dp.row_stride, std::max(D, 3), max_rows);
   const int Np = qp_block_count(N, 2 * D) * 2 * D;
