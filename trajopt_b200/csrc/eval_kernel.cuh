@@ -18,10 +18,11 @@ enum EvalMode { EVAL_INIT = 0, EVAL_STEP = 1, EVAL_ONLY = 2 };
 
 struct EvalSmem {
   // offsets in doubles into the dynamic shared buffer
-  int x, sph, jax, jor, cartf, viol, mask, misc, fr, terms, total;
+  int x, sph, jax, jor, cartf, viol, mask, misc, fr, terms, obst, stage, total;
 };
 __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_cart_objs, int n_coll_cand,
-                                                      int n_mask_words, int S = 0, int n_joint_objs = 0) {
+                                                      int n_mask_words, int S = 0, int n_joint_objs = 0,
+                                                      int stage_per_warp = 0) {
   EvalSmem s;
   int o = 0;
   s.x = o;      o += T * D;
@@ -29,17 +30,26 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   s.jax = o;    o += T * D * 3;
   s.jor = o;    o += T * D * 3;
   s.cartf = o;  o += n_cart_objs * (1 + D) * 12;
-  s.viol = o;   o += n_coll_cand;
   s.mask = o;   o += n_mask_words;
   s.misc = o;   o += 8;
-  s.fr = o;     o += (T + n_cart_objs * D) * S * 12;  // frames of every FK job: local, then (in place) world
-  s.terms = o;  o += n_joint_objs * 2 * T * D;        // per-(step, joint) terms of the joint-space objects
+  s.obst = o;   o += 4 * 64;                          // this trajectory's obstacle spheres (x, y, z, r)
+  o += o & 1;                                         // 16-byte alignment of everything below
+  // the FK frames are dead once the joint axes / sphere centres are emitted: the violation and term buffers of the
+  // later phases reuse their space
+  s.fr = o;                                           // frames of every FK job: local, then (in place) world
+  s.viol = o;
+  s.terms = o + n_coll_cand;                          // per-(step, joint) terms of the joint-space objects
+  s.stage = s.terms + n_joint_objs * 2 * T * D;       // 8 warps x one collision object's rows (L*O x (D+3))
+  const int a = (T + n_cart_objs * D) * S * 12, b2 = n_coll_cand + n_joint_objs * 2 * T * D + 8 * stage_per_warp;
+  o += a > b2 ? a : b2;
+  o += o & 1;
   s.total = o;
   return s;
 }
 
 struct EvalExtra {
   int n_cart_objs, n_coll_objs, n_joint_objs, pad;
+  int joint_obj_idx[8];  // positions of the joint-space objects in the (costs, cnts) list
   const DevObj* cart_objs;   // pad0 = index in its own list (cost / cnt), is_cnt says which list
   const DevObj* coll_objs;
   int qtype[kMaxDof];                // joint type per trajectory column
@@ -76,18 +86,21 @@ __device__ inline double joint_obj_value(const DevProblem& p, const DevObj& o, c
   return s;
 }
 
-__global__ void __launch_bounds__(kEvalThreads)
+template <int DD>
+__global__ void __launch_bounds__(kEvalThreads, 3)
 eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double* x_in /*EVAL_ONLY*/) {
   extern __shared__ double sm[];
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
-  const int T = p.T, D = p.D, N = p.N, L = p.L, O = p.O;
+  constexpr int D = DD;
+  const int T = p.T, N = p.N, L = p.L, O = p.O;
   if (mode != EVAL_ONLY && p.status[b] != 5 /*running == INVALID*/) return;
   if (mode == EVAL_STEP && p.qp_done[b] == 0) return;  // its QP is still being solved (time-sliced)
   const bool qp_failed = (mode == EVAL_STEP) && (p.qp_status[b] != 0);
   if (tid == 0 && !qp_failed) atomicAdd(p.active_count + 1, 1);  // trajectories actually convexified (bench: bytes moved)
   const int n_mask_words = p.n_coll_objs * p.coll_words;
-  const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_cand, n_mask_words, p.S, ex.n_joint_objs);
+  const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_cand, n_mask_words, p.S, ex.n_joint_objs,
+                                      (L * O * (D + 3) + 1) & ~1);
   double* xs = sm + S.x;
   unsigned long long* mask = reinterpret_cast<unsigned long long*>(sm + S.mask);
   int* misc = reinterpret_cast<int*>(sm + S.misc);
@@ -107,6 +120,10 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
       xs[i] = v;
     }
     for (int i = tid; i < n_mask_words; i += kEvalThreads) mask[i] = 0ull;
+    {
+      const double* og = p.obstacles + (p.obstacles_per_traj ? static_cast<size_t>(b) * O * 4 : 0);
+      for (int i = tid; i < O * 4; i += kEvalThreads) sm[S.obst + i] = og[i];
+    }
     __syncthreads();
 
     // ---- FK: one job per waypoint, plus D perturbed configurations per CartPose object ---------------
@@ -228,42 +245,64 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
 
     // ---- dense candidate collision rows (collision_terms.cpp:203-250, 343-383, 540-556, 655-691) ----
     // candidate r = (collision object k, robot sphere s, obstacle o);  row = {grad[D], dist0, margin, coeff|0}
-    const int LO = L * O;
-    const double* obst = p.obstacles + (p.obstacles_per_traj ? static_cast<size_t>(b) * O * 4 : 0);
+    // One warp per collision object (= waypoint): its L*O candidate rows are contiguous in HBM, so the warp builds
+    // them in a shared staging area and writes them out as fully coalesced 16-byte stores; the activity mask of
+    // 32 candidates is one ballot.  No block barrier inside the phase.
+    const int LO = L * O, lane_c = tid & 31, warp_c = tid >> 5;
+    const double* obst = sm + S.obst;
     double* rows_out = p.coll_rows + slot * static_cast<size_t>(p.n_coll_cand) * p.coll_stride;
-    for (int r = tid; r < p.n_coll_cand; r += kEvalThreads) {
-      const int k = r / LO, s = (r % LO) / O, o = r % O;
+    double* stage = sm + S.stage + static_cast<size_t>(warp_c) * LO * (D + 3);
+    for (int k = warp_c; k < p.n_coll_objs; k += kEvalThreads / 32) {
       const DevObj& co = ex.coll_objs[k];
       const int t = co.first;
-      const double* c = sm + S.sph + (t * L + s) * 3;
-      const double dx = obst[o * 4] - c[0], dy = obst[o * 4 + 1] - c[1], dz = obst[o * 4 + 2] - c[2];
-      const double len = sqrt(dx * dx + dy * dy + dz * dz);
-      const double dist = len - p.spheres[s].r - obst[o * 4 + 3];
-      const double inv = 1.0 / len;
-      const double nx = dx * inv, ny = dy * inv, nz = dz * inv;  // from the robot sphere towards the obstacle
-      double* row = rows_out + static_cast<size_t>(r) * p.coll_stride;
-      const unsigned jm = ex.sphere_jmask[s];
-      for (int j = 0; j < D; ++j) {
-        double g = 0.0;
-        if (jm & (1u << j)) {
+      const double margin = co.margin, reach = co.margin + co.buffer, coeff = co.coeff;
+      for (int c0 = 0; c0 < LO; c0 += 32) {
+        const int cnd = c0 + lane_c;
+        const bool in = cnd < LO;
+        const int sl = in ? cnd / O : 0, o = in ? cnd % O : 0;
+        const double* c = sm + S.sph + (t * L + sl) * 3;
+        const double cx = c[0], cy = c[1], cz = c[2];
+        const double dx = obst[o * 4] - cx, dy = obst[o * 4 + 1] - cy, dz = obst[o * 4 + 2] - cz;
+        const double len = sqrt(dx * dx + dy * dy + dz * dz);
+        const double dist = len - p.spheres[sl].r - obst[o * 4 + 3];
+        const double inv = 1.0 / len;
+        const double nx = dx * inv, ny = dy * inv, nz = dz * inv;  // from the robot sphere towards the obstacle
+        const unsigned jm = ex.sphere_jmask[sl];
+        double* row = stage + cnd * (D + 3);
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
           const double* a = sm + S.jax + (t * D + j) * 3;
-          if (ex.qtype[j] == 1) {
-            const double* oj = sm + S.jor + (t * D + j) * 3;
-            const double rx = c[0] - oj[0], ry = c[1] - oj[1], rz = c[2] - oj[2];
-            // -n . (a x r)
-            g = -(nx * (a[1] * rz - a[2] * ry) + ny * (a[2] * rx - a[0] * rz) + nz * (a[0] * ry - a[1] * rx));
-          } else {
-            g = -(nx * a[0] + ny * a[1] + nz * a[2]);
-          }
+          const double* oj = sm + S.jor + (t * D + j) * 3;
+          const double rx = cx - oj[0], ry = cy - oj[1], rz = cz - oj[2];
+          // -n . (a x r) for a revolute joint, -n . a for a prismatic one, 0 when the joint does not move the sphere
+          const double grev = -(nx * (a[1] * rz - a[2] * ry) + ny * (a[2] * rx - a[0] * rz) + nz * (a[0] * ry - a[1] * rx));
+          const double gpri = -(nx * a[0] + ny * a[1] + nz * a[2]);
+          const double g = ((jm >> j) & 1u) ? (ex.qtype[j] == 1 ? grev : gpri) : 0.0;
+          if (in) row[j] = g;
         }
-        row[j] = g;
+        const bool active = in && !(dist > reach);
+        if (in) {
+          row[D] = dist;
+          row[D + 1] = margin;
+          row[D + 2] = active ? coeff : 0.0;
+          sm[S.viol + co.src_off + cnd] = active ? fmax(margin - dist, 0.0) * coeff : 0.0;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, active);
+        if (lane_c == 0 && bal) atomicOr(&mask[k * p.coll_words + (c0 >> 6)], static_cast<unsigned long long>(bal) << (c0 & 63));
       }
-      const bool active = !(dist > co.margin + co.buffer);
-      row[D] = dist;
-      row[D + 1] = co.margin;
-      row[D + 2] = active ? co.coeff : 0.0;
-      sm[S.viol + r] = active ? fmax(co.margin - dist, 0.0) * co.coeff : 0.0;
-      if (active) atomicOr(&mask[k * p.coll_words + (r % LO) / 64], 1ull << ((r % LO) % 64));
+      __syncwarp();
+      {  // coalesced copy of the object's rows: LO*(D+3) doubles, 16 bytes per lane per step (the offset is even)
+        const int n = LO * (D + 3);
+        double* dstp = rows_out + static_cast<size_t>(co.src_off) * p.coll_stride;
+        if (((co.src_off * p.coll_stride) & 1) == 0 && (n & 1) == 0) {
+          const double2* s2 = reinterpret_cast<const double2*>(stage);
+          double2* d2 = reinterpret_cast<double2*>(dstp);
+          for (int i = lane_c; i < n / 2; i += 32) d2[i] = s2[i];
+        } else {
+          for (int i = lane_c; i < n; i += 32) dstp[i] = stage[i];
+        }
+      }
+      __syncwarp();
     }
     __syncthreads();
     for (int i = tid; i < n_mask_words; i += kEvalThreads) p.coll_mask[slot * n_mask_words + i] = mask[i];
@@ -281,28 +320,24 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
     const int n_obj = p.n_costs + p.n_cnts;
     double* terms = sm + S.terms;
     // joint-space terms: slot j of the term buffer belongs to the j-th joint-space object in (costs, cnts) order
-    {
-      int slot_j = 0;
-      for (int i = 0; i < n_obj; ++i) {
-        const bool is_cnt = i >= p.n_costs;
-        const DevObj& o = is_cnt ? p.cnt_objs[i - p.n_costs] : p.cost_objs[i];
-        if (o.kind > OBJ_JOINT_INEQ_CNT) continue;
-        const DevJointTerm& jt = p.joint_terms[o.term];
-        double* tb = terms + static_cast<size_t>(slot_j) * 2 * T * D;
-        for (int w = tid; w < o.n_steps * D; w += kEvalThreads) {
-          const int t = o.first + w / D, d = w % D;
-          const double e = joint_err(xs, D, o.order, t, d, jt.targets[d]);
-          double v0, v1 = 0.0;
-          if (o.kind == OBJ_JOINT_EQ_COST) v0 = e * e * jt.coeffs[d];
-          else if (o.kind == OBJ_JOINT_EQ_CNT) v0 = fabs(e * e * jt.coeffs[d]);  // value() is c*e^2 while the row is c*e (trajectory_costs.cpp:160 vs 173)
-          else {
-            v0 = fmax((e - jt.upper[d]) * jt.coeffs[d], 0.0);
-            v1 = fmax((jt.lower[d] - e) * jt.coeffs[d], 0.0);
-          }
-          tb[2 * w] = v0;
-          tb[2 * w + 1] = v1;
+    for (int slot_j = 0; slot_j < ex.n_joint_objs; ++slot_j) {
+      const int i = ex.joint_obj_idx[slot_j];
+      const DevObj& o = (i >= p.n_costs) ? p.cnt_objs[i - p.n_costs] : p.cost_objs[i];
+      const DevJointTerm& jt = p.joint_terms[o.term];
+      double* tb = terms + static_cast<size_t>(slot_j) * 2 * T * D;
+      const int kind = o.kind, order = o.order, first = o.first;
+      for (int w = tid; w < o.n_steps * D; w += kEvalThreads) {
+        const int t = first + w / D, d = w % D;
+        const double e = joint_err(xs, D, order, t, d, jt.targets[d]);
+        double v0, v1 = 0.0;
+        if (kind == OBJ_JOINT_EQ_COST) v0 = e * e * jt.coeffs[d];
+        else if (kind == OBJ_JOINT_EQ_CNT) v0 = fabs(e * e * jt.coeffs[d]);  // value() is c*e^2 while the row is c*e (trajectory_costs.cpp:160 vs 173)
+        else {
+          v0 = fmax((e - jt.upper[d]) * jt.coeffs[d], 0.0);
+          v1 = fmax((jt.lower[d] - e) * jt.coeffs[d], 0.0);
         }
-        ++slot_j;
+        tb[2 * w] = v0;
+        tb[2 * w + 1] = v1;
       }
     }
     __syncthreads();  // terms, collision violations (shared) and cart_err rows (global, this CTA) are complete
@@ -313,7 +348,7 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
       double v = 0.0;
       if (o.kind <= OBJ_JOINT_INEQ_CNT) {
         int slot_j = 0;
-        for (int k = 0; k < i; ++k) slot_j += ((k >= p.n_costs ? p.cnt_objs[k - p.n_costs] : p.cost_objs[k]).kind <= OBJ_JOINT_INEQ_CNT);
+        for (int k = 0; k < ex.n_joint_objs; ++k) slot_j = (ex.joint_obj_idx[k] == i) ? k : slot_j;
         const double* tb = terms + static_cast<size_t>(slot_j) * 2 * T * D;
         const bool two = o.kind == OBJ_JOINT_INEQ_COST || o.kind == OBJ_JOINT_INEQ_CNT;
         if (lane == 0) {

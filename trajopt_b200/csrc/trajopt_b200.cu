@@ -73,6 +73,17 @@ static QpKernelFn qp_kernel_for(int D) {
   }
 }
 
+using EvalKernelFn = void (*)(DevProblem, EvalExtra, int, const double*);
+static EvalKernelFn eval_kernel_for(int D) {
+  switch (D) {
+    case 2: return eval_convexify_decide_kernel<2>;
+    case 3: return eval_convexify_decide_kernel<3>;
+    case 6: return eval_convexify_decide_kernel<6>;
+    case 7: return eval_convexify_decide_kernel<7>;
+    default: return nullptr;
+  }
+}
+
 struct tb200_problem {
   int device = 0;
   DevProblem dp{};
@@ -364,8 +375,20 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   P->ex.n_cart_objs = static_cast<int>(P->cart_objs.size());
   P->ex.n_coll_objs = dp.n_coll_objs;
   P->ex.n_joint_objs = 0;
-  for (const DevObj& o : P->cost_objs) P->ex.n_joint_objs += (o.kind <= OBJ_JOINT_INEQ_CNT);
-  for (const DevObj& o : P->cnt_objs) P->ex.n_joint_objs += (o.kind <= OBJ_JOINT_INEQ_CNT);
+  {
+    int idx = 0;
+    auto note = [&](const DevObj& o) {
+      if (o.kind <= OBJ_JOINT_INEQ_CNT) {
+        if (P->ex.n_joint_objs < 8) P->ex.joint_obj_idx[P->ex.n_joint_objs] = idx;
+        P->ex.n_joint_objs++;
+      }
+      ++idx;
+    };
+    for (const DevObj& o : P->cost_objs) note(o);
+    for (const DevObj& o : P->cnt_objs) note(o);
+    if (P->ex.n_joint_objs > 8) return fail(TB200_ERR_UNSUPPORTED, "more than 8 joint-space cost/constraint objects");
+    if (dp.O > 64) return fail(TB200_ERR_UNSUPPORTED, "more than 64 obstacle spheres per trajectory");
+  }
   P->layout.n_costs = dp.n_costs;
   P->layout.n_cnts = dp.n_cnts;
   P->layout.n_cart_rows = n_cart_rows;
@@ -376,7 +399,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
 
   // ---- kernel resources --------------------------------------------------------------------------------
   const EvalSmem es = eval_smem_layout(T, D, dp.L, P->ex.n_cart_objs, n_coll_cand, dp.n_coll_objs * dp.coll_words, dp.S,
-                                       P->ex.n_joint_objs);
+                                       P->ex.n_joint_objs, (dp.L * dp.O * (D + 3) + 1) & ~1);
   P->eval_smem = static_cast<size_t>(es.total) * sizeof(double);
   const QpSmem qs = qp_smem_layout(N, 2 * D, dp.row_stride, std::max(D, 3), max_rows);
   const int Np = qp_block_count(N, 2 * D) * 2 * D;
@@ -388,8 +411,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
     return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for one CTA per block-cyclic-reduction level");
   if (!solve_roles_fit(qp_block_count(N, 2 * D), 2 * D))
     return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for the register-resident block-cyclic-reduction solve");
-  CK(cudaFuncSetAttribute(eval_convexify_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->eval_smem)));
-  if (!qp_kernel_for(D)) return fail(TB200_ERR_UNSUPPORTED, "no QP kernel instance for this number of joints");
+  if (!qp_kernel_for(D) || !eval_kernel_for(D)) return fail(TB200_ERR_UNSUPPORTED, "no kernel instance for this number of joints");
+  CK(cudaFuncSetAttribute(eval_kernel_for(D), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->eval_smem)));
   CK(cudaFuncSetAttribute(qp_kernel_for(D), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->qp_smem)));
   CK(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
   if (const char* e = std::getenv("TB200_SLICE")) P->slice = std::max(1, std::atoi(e));
@@ -544,7 +567,7 @@ int tb200_solve_batch_resident(tb200_problem* P) {
   auto launch_eval = [&](int mode) {
     const size_t i0 = ne;
     cudaEventRecord(getEvent(P, ne++), st);
-    eval_convexify_decide_kernel<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, mode, nullptr);
+    eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, mode, nullptr);
     cudaEventRecord(getEvent(P, ne++), st);
     spans.push_back({i0, 0});
   };
@@ -643,7 +666,7 @@ int tb200_convexify_batch(tb200_problem* P, const double* x, tb200_convexify_out
   CK(cudaMemcpyAsync(P->x_tmp.p, x, B * dp.N * sizeof(double), cudaMemcpyHostToDevice, st));
   cudaEvent_t e0 = getEvent(P, 0), e1 = getEvent(P, 1);
   CK(cudaEventRecord(e0, st));
-  eval_convexify_decide_kernel<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
+  eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
   CK(cudaEventRecord(e1, st));
   CK(cudaGetLastError());
   auto pull = [&](void* dst, const void* src, size_t n) {
@@ -680,7 +703,7 @@ int tb200_qp_solve_batch(tb200_problem* P, const double* x, const double* trust,
   CK(cudaMemcpyAsync(P->trust_tmp.p, trust, B * sizeof(double), cudaMemcpyHostToDevice, st));
   if (dp.n_cnts > 0) CK(cudaMemcpyAsync(P->merit_coeffs.p, merit_coeffs, B * dp.n_cnts * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(P->ws_meta.p, 0, B * 8 * sizeof(int), st));
-  eval_convexify_decide_kernel<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
+  eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
   qp_kernel_for(P->D)<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, P->x_tmp.p, P->trust_tmp.p, P->tmp_iters.p, P->tmp_polish.p, 1 << 30);
   CK(cudaGetLastError());
   auto pull = [&](void* dst, const void* src, size_t n) {
