@@ -38,9 +38,10 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   // later phases reuse their space
   s.fr = o;                                           // frames of every FK job: local, then (in place) world
   s.viol = o;
-  s.terms = o + n_coll_cand;                          // per-(step, joint) terms of the joint-space objects
-  s.stage = s.terms + n_joint_objs * 2 * T * D;       // 8 warps x one collision object's rows (L*O x (D+3))
-  const int a = (T + n_cart_objs * D) * S * 12, b2 = n_coll_cand + n_joint_objs * 2 * T * D + 8 * stage_per_warp;
+  s.stage = o + n_coll_cand;                          // 8 warps x (32 candidate rows + the object's lever arms)
+  s.terms = s.stage;                                  // per-(step, joint) terms of the joint-space objects (later phase)
+  const int st = 8 * stage_per_warp, tm = n_joint_objs * 2 * T * D;
+  const int a = (T + n_cart_objs * D) * S * 12, b2 = n_coll_cand + (st > tm ? st : tm);
   o += a > b2 ? a : b2;
   o += o & 1;
   s.total = o;
@@ -100,7 +101,7 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
   if (tid == 0 && !qp_failed) atomicAdd(p.active_count + 1, 1);  // trajectories actually convexified (bench: bytes moved)
   const int n_mask_words = p.n_coll_objs * p.coll_words;
   const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_cand, n_mask_words, p.S, ex.n_joint_objs,
-                                      (L * O * (D + 3) + 1) & ~1);
+                                      ((32 * (D + 3) + 1) & ~1) + ((L * D * 3 + 1) & ~1));
   double* xs = sm + S.x;
   unsigned long long* mask = reinterpret_cast<unsigned long long*>(sm + S.mask);
   int* misc = reinterpret_cast<int*>(sm + S.misc);
@@ -120,6 +121,7 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
       xs[i] = v;
     }
     for (int i = tid; i < n_mask_words; i += kEvalThreads) mask[i] = 0ull;
+    if (tid == 0) misc[2] = 0;  // work counter of the collision phase
     {
       const double* og = p.obstacles + (p.obstacles_per_traj ? static_cast<size_t>(b) * O * 4 : 0);
       for (int i = tid; i < O * 4; i += kEvalThreads) sm[S.obst + i] = og[i];
@@ -251,34 +253,48 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
     const int LO = L * O, lane_c = tid & 31, warp_c = tid >> 5;
     const double* obst = sm + S.obst;
     double* rows_out = p.coll_rows + slot * static_cast<size_t>(p.n_coll_cand) * p.coll_stride;
-    double* stage = sm + S.stage + static_cast<size_t>(warp_c) * LO * (D + 3);
-    for (int k = warp_c; k < p.n_coll_objs; k += kEvalThreads / 32) {
+    const int stage_sz = ((32 * (D + 3) + 1) & ~1) + ((L * D * 3 + 1) & ~1);
+    double* stage = sm + S.stage + static_cast<size_t>(warp_c) * stage_sz;  // 32 candidate rows at a time
+    double* lever = stage + ((32 * (D + 3) + 1) & ~1);  // d(centre of sphere s)/dq_j for the object being processed
+    for (;;) {
+      int k = 0;
+      if (lane_c == 0) k = atomicAdd(&misc[2], 1);  // next collision object: warps take them as they get free
+      k = __shfl_sync(0xffffffffu, k, 0);
+      if (k >= p.n_coll_objs) break;
       const DevObj& co = ex.coll_objs[k];
       const int t = co.first;
       const double margin = co.margin, reach = co.margin + co.buffer, coeff = co.coeff;
+      // lever arms a_j x (c_s - o_j) (revolute) / a_j (prismatic) / 0 (joint does not move the sphere): they do
+      // not depend on the obstacle, so they are built once per (sphere, joint)
+      for (int w = lane_c; w < L * D; w += 32) {
+        const int sl = w / D, j = w % D;
+        const double* c = sm + S.sph + (t * L + sl) * 3;
+        const double* a = sm + S.jax + (t * D + j) * 3;
+        const double* oj = sm + S.jor + (t * D + j) * 3;
+        const bool moves = (ex.sphere_jmask[sl] >> j) & 1u, rev = ex.qtype[j] == 1;
+        const double rx = c[0] - oj[0], ry = c[1] - oj[1], rz = c[2] - oj[2];
+        lever[w * 3 + 0] = moves ? (rev ? a[1] * rz - a[2] * ry : a[0]) : 0.0;
+        lever[w * 3 + 1] = moves ? (rev ? a[2] * rx - a[0] * rz : a[1]) : 0.0;
+        lever[w * 3 + 2] = moves ? (rev ? a[0] * ry - a[1] * rx : a[2]) : 0.0;
+      }
+      __syncwarp();
       for (int c0 = 0; c0 < LO; c0 += 32) {
         const int cnd = c0 + lane_c;
         const bool in = cnd < LO;
         const int sl = in ? cnd / O : 0, o = in ? cnd % O : 0;
         const double* c = sm + S.sph + (t * L + sl) * 3;
-        const double cx = c[0], cy = c[1], cz = c[2];
-        const double dx = obst[o * 4] - cx, dy = obst[o * 4 + 1] - cy, dz = obst[o * 4 + 2] - cz;
+        const double dx = obst[o * 4] - c[0], dy = obst[o * 4 + 1] - c[1], dz = obst[o * 4 + 2] - c[2];
         const double len = sqrt(dx * dx + dy * dy + dz * dz);
         const double dist = len - p.spheres[sl].r - obst[o * 4 + 3];
         const double inv = 1.0 / len;
         const double nx = dx * inv, ny = dy * inv, nz = dz * inv;  // from the robot sphere towards the obstacle
         const unsigned jm = ex.sphere_jmask[sl];
-        double* row = stage + cnd * (D + 3);
+        double* row = stage + lane_c * (D + 3);
+        const double* lv = lever + sl * D * 3;
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-          const double* a = sm + S.jax + (t * D + j) * 3;
-          const double* oj = sm + S.jor + (t * D + j) * 3;
-          const double rx = cx - oj[0], ry = cy - oj[1], rz = cz - oj[2];
-          // -n . (a x r) for a revolute joint, -n . a for a prismatic one, 0 when the joint does not move the sphere
-          const double grev = -(nx * (a[1] * rz - a[2] * ry) + ny * (a[2] * rx - a[0] * rz) + nz * (a[0] * ry - a[1] * rx));
-          const double gpri = -(nx * a[0] + ny * a[1] + nz * a[2]);
-          const double g = ((jm >> j) & 1u) ? (ex.qtype[j] == 1 ? grev : gpri) : 0.0;
-          if (in) row[j] = g;
+          const double g = -(nx * lv[j * 3] + ny * lv[j * 3 + 1] + nz * lv[j * 3 + 2]);  // -n . (a x r)
+          if (in) row[j] = ((jm >> j) & 1u) ? g : 0.0;
         }
         const bool active = in && !(dist > reach);
         if (in) {
@@ -289,20 +305,19 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
         }
         const unsigned bal = __ballot_sync(0xffffffffu, active);
         if (lane_c == 0 && bal) atomicOr(&mask[k * p.coll_words + (c0 >> 6)], static_cast<unsigned long long>(bal) << (c0 & 63));
-      }
-      __syncwarp();
-      {  // coalesced copy of the object's rows: LO*(D+3) doubles, 16 bytes per lane per step (the offset is even)
-        const int n = LO * (D + 3);
-        double* dstp = rows_out + static_cast<size_t>(co.src_off) * p.coll_stride;
-        if (((co.src_off * p.coll_stride) & 1) == 0 && (n & 1) == 0) {
+        __syncwarp();
+        // coalesced copy of these (up to) 32 rows: 16 bytes per lane per step when the offset is even
+        const int n = (LO - c0 < 32 ? LO - c0 : 32) * (D + 3);
+        double* dstp = rows_out + static_cast<size_t>(co.src_off + c0) * p.coll_stride;
+        if ((((co.src_off + c0) * p.coll_stride) & 1) == 0 && (n & 1) == 0) {
           const double2* s2 = reinterpret_cast<const double2*>(stage);
           double2* d2 = reinterpret_cast<double2*>(dstp);
           for (int i = lane_c; i < n / 2; i += 32) d2[i] = s2[i];
         } else {
           for (int i = lane_c; i < n; i += 32) dstp[i] = stage[i];
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
     __syncthreads();
     for (int i = tid; i < n_mask_words; i += kEvalThreads) p.coll_mask[slot * n_mask_words + i] = mask[i];

@@ -399,7 +399,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
 
   // ---- kernel resources --------------------------------------------------------------------------------
   const EvalSmem es = eval_smem_layout(T, D, dp.L, P->ex.n_cart_objs, n_coll_cand, dp.n_coll_objs * dp.coll_words, dp.S,
-                                       P->ex.n_joint_objs, (dp.L * dp.O * (D + 3) + 1) & ~1);
+                                       P->ex.n_joint_objs, ((32 * (D + 3) + 1) & ~1) + ((dp.L * D * 3 + 1) & ~1));
   P->eval_smem = static_cast<size_t>(es.total) * sizeof(double);
   const QpSmem qs = qp_smem_layout(N, 2 * D, dp.row_stride, std::max(D, 3), max_rows);
   const int Np = qp_block_count(N, 2 * D) * 2 * D;
