@@ -30,6 +30,9 @@ extern "C" {
 #define TB200_VERSION_MINOR 1
 #define TB200_MAX_DOF 16      /* joints per manipulator group (7 single arm, 14 dual arm) */
 #define TB200_MAX_STEPS 64    /* waypoints per trajectory */
+#define TB200_MAX_LVS_SEGMENTS 4 /* LVS_CONTINUOUS collision: sub-segments per step pair (the reference's
+                                    CastCollisionEvaluator::CalcCollisions, collision_terms.cpp:1118-1155, is
+                                    unbounded; the fixed candidate layout needs a bound — DESIGN.md deviations) */
 
 /* ---- return codes ------------------------------------------------------- */
 enum {

@@ -21,7 +21,7 @@ Layout layoutOf(const tb200_problem_desc& d, const TrajProblem& tp) {
   L.n_costs = static_cast<int>(tp.cost_names.size());
   L.n_cnts = static_cast<int>(tp.cnt_names.size());
   const int D = d.robot.n_dof;
-  bool has_vel = false;
+  bool has_vel = false, has_cast = false;
   for (int k = 0; k < d.n_terms; ++k) {
     const tb200_term& t = d.terms[k];
     if (t.kind == TB200_TERM_CART_POSE) {
@@ -31,6 +31,11 @@ Layout layoutOf(const tb200_problem_desc& d, const TrajProblem& tp) {
       L.n_cart_rows += 6 * (t.last_step - t.first_step + 1);
       has_vel = true;
     } else if (t.kind == TB200_TERM_COLLISION) {
+      if (t.evaluator_type != TB200_COLL_DISCRETE) {  // one object per step pair, dense over sub-segments
+        L.n_coll_cand += (t.last_step - t.first_step) * d.robot.n_spheres * d.n_obstacles * TB200_MAX_LVS_SEGMENTS;
+        has_cast = true;
+        continue;
+      }
       int steps = 0;
       for (int s = t.first_step; s <= t.last_step; ++s) {
         bool fixed = false;
@@ -41,7 +46,7 @@ Layout layoutOf(const tb200_problem_desc& d, const TrajProblem& tp) {
     }
   }
   L.cart_stride = has_vel ? 2 * D : D;
-  L.coll_stride = D + 3;
+  L.coll_stride = has_cast ? 2 * D + 3 : D + 3;
   return L;
 }
 }  // namespace

@@ -2,6 +2,9 @@
 #include "trajopt.hpp"
 
 #include <algorithm>
+#include <cmath>
+#include <functional>
+#include <limits>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -410,9 +413,188 @@ struct CollisionEval {
     return out;
   }
 };
+// ============================================================================ collision (continuous, "cast")
+// CastCollisionEvaluator (collision_terms.cpp:1071-1173) + GetGradient(q0, q1, ...) (:262-323) +
+// CalcDistExpressions{BothFree,StartFree,EndFree} (:468-538) + the fixed-state contact filter
+// (trajopt_common/src/collision_utils.cpp:73-114), for the synthetic sphere model of SURVEY.md §8d:
+// the swept robot sphere of a (sub-)segment is the capsule between its two centres; contact with a static
+// obstacle sphere is closed form (closest point of the centre segment, parameter s clamped to [0,1]).
+//   * LVS: ||q1-q0|| > longest_valid_segment_length  =>  ceil(dist/lvs) sub-segments between linearly
+//     interpolated joint states (the reference's LinSpaced sub-trajectory, :1118-1155); here at most
+//     TB200_MAX_LVS_SEGMENTS (the reference is unbounded; the fixed candidate layout needs a bound).
+//     CONTINUOUS (evaluator 3) never subdivides (lvs = max double, problem_description.cpp:1782-1784).
+//   * cc_time of a contact in sub-segment i of n: (i + s)/n  (addInterpolatedCollisionResults [EXT]);
+//     type Time0 iff i == 0 and s == 0, Time1 iff i == n-1 and s == 1, else Between.
+//   * filter: distance > margin + buffer; start fixed and Time0; end fixed and Time1.
+//   * gradient: Jacobian of the link at q0 + (q1-q0)*cc_time, reference point moved by
+//     R_link(sub-segment start | end) * c_local for the timestep-0 | timestep-1 expression
+//     (jacobianChangeRefPoint with transform | cc_transform), g_k = -n' J_lin, scaled (1-cc_time) | cc_time.
+//   * row: dist + g_0.(q_t - q0) + g_1.(q_t+1 - q1), coefficients |c| <= 1e-7 dropped (cleanupAff IS applied
+//     on this path, :481,502,536); a fixed side contributes nothing.
+struct CastContact {
+  int sphere, obstacle, sub;
+  double dist, cc_time;
+  double normal[3];
+  Vec g0, g1;  // scaled gradients over q_t and q_{t+1} (zero on a fixed side)
+};
+struct CastCollisionEval {
+  std::shared_ptr<Robot> robot;
+  Vec obstacles;  // [O][4]
+  int t, D;
+  double margin, coeff, buffer, lvs;
+  bool start_fixed, end_fixed;
+
+  int subSegments(const double* q0, const double* q1) const {
+    double d2 = 0;
+    for (int j = 0; j < D; ++j) d2 += (q1[j] - q0[j]) * (q1[j] - q0[j]);
+    const double dist = std::sqrt(d2);
+    if (!(dist > lvs)) return 1;
+    const double n = std::ceil(dist / lvs);
+    return n > TB200_MAX_LVS_SEGMENTS ? TB200_MAX_LVS_SEGMENTS : static_cast<int>(n);
+  }
+  void sphereCentre(const std::vector<Pose>& fr, int s, double* c) const {
+    const tb200_sphere& sp = robot->spheres[s];
+    const Pose& f = fr[sp.segment];
+    for (int i = 0; i < 3; ++i)
+      c[i] = f.R[i * 3] * sp.center[0] + f.R[i * 3 + 1] * sp.center[1] + f.R[i * 3 + 2] * sp.center[2] + f.p[i];
+  }
+  // every candidate (sphere, obstacle, sub-segment); `all` keeps the filtered ones too (flag active)
+  struct Cand {
+    bool exists, active;
+    CastContact ct;
+  };
+  void candidates(const Vec& x, std::vector<Cand>& out) const {
+    const double* q0 = x.data() + t * D;
+    const double* q1 = x.data() + (t + 1) * D;
+    const int n = subSegments(q0, q1);
+    const int O = static_cast<int>(obstacles.size() / 4), L = static_cast<int>(robot->spheres.size());
+    std::vector<std::vector<Pose>> fr(n + 1);
+    Vec u(D);
+    for (int i = 0; i <= n; ++i) {
+      for (int j = 0; j < D; ++j) u[j] = (i == n) ? q1[j] : q0[j] + (q1[j] - q0[j]) * (static_cast<double>(i) / n);
+      robot->fk(u.data(), fr[i]);
+    }
+    out.assign(static_cast<size_t>(L) * O * TB200_MAX_LVS_SEGMENTS, Cand{});
+    std::vector<Pose> frt;
+    std::vector<Vec> J;
+    for (int s = 0; s < L; ++s) {
+      const tb200_sphere& sp = robot->spheres[s];
+      for (int o = 0; o < O; ++o) {
+        const double* ob = &obstacles[o * 4];
+        for (int i = 0; i < n; ++i) {
+          Cand& cd = out[(static_cast<size_t>(s) * O + o) * TB200_MAX_LVS_SEGMENTS + i];
+          cd.exists = true;
+          double ca[3], cb[3], w[3], ww = 0, wd = 0;
+          sphereCentre(fr[i], s, ca);
+          sphereCentre(fr[i + 1], s, cb);
+          for (int k = 0; k < 3; ++k) {
+            w[k] = cb[k] - ca[k];
+            ww += w[k] * w[k];
+            wd += (ob[k] - ca[k]) * w[k];
+          }
+          double sc = (ww > 0) ? wd / ww : 0.0;
+          sc = sc < 0 ? 0.0 : (sc > 1 ? 1.0 : sc);
+          double d[3], len2 = 0;
+          for (int k = 0; k < 3; ++k) {
+            d[k] = ob[k] - (ca[k] + sc * w[k]);
+            len2 += d[k] * d[k];
+          }
+          const double len = std::sqrt(len2);
+          CastContact& ct = cd.ct;
+          ct.sphere = s; ct.obstacle = o; ct.sub = i;
+          ct.dist = len - sp.radius - ob[3];
+          ct.cc_time = (i + sc) / n;
+          for (int k = 0; k < 3; ++k) ct.normal[k] = d[k] / len;
+          const bool time0 = (i == 0 && sc == 0.0), time1 = (i == n - 1 && sc == 1.0);
+          cd.active = !(ct.dist > margin + buffer) && !(start_fixed && time0) && !(end_fixed && time1);
+          ct.g0.assign(D, 0.0);
+          ct.g1.assign(D, 0.0);
+          if (!cd.active) continue;
+          // Jacobian at the contact-time state, reference point shifted with the sub-segment's start / end rotation
+          Vec qt(D);
+          for (int j = 0; j < D; ++j) qt[j] = (ct.cc_time == 1.0) ? q1[j] : q0[j] + (q1[j] - q0[j]) * ct.cc_time;
+          robot->fk(qt.data(), frt);
+          const Pose& lt = frt[sp.segment];
+          for (int k = 0; k < 2; ++k) {
+            if ((k == 0 && start_fixed) || (k == 1 && end_fixed)) continue;
+            const Pose& lk = fr[i + k][sp.segment];
+            double pt[3];
+            for (int a = 0; a < 3; ++a)
+              pt[a] = lk.R[a * 3] * sp.center[0] + lk.R[a * 3 + 1] * sp.center[1] + lk.R[a * 3 + 2] * sp.center[2] + lt.p[a];
+            robot->jacobian(frt, sp.segment, pt, J);
+            const double scale = (k == 0) ? 1.0 - ct.cc_time : ct.cc_time;
+            Vec& g = (k == 0) ? ct.g0 : ct.g1;
+            for (int j = 0; j < D; ++j)
+              g[j] = -(ct.normal[0] * J[0][j] + ct.normal[1] * J[1][j] + ct.normal[2] * J[2][j]) * scale;
+          }
+        }
+      }
+    }
+  }
+  void distExpressions(const Vec& x, std::vector<AffExpr>& exprs) const {
+    std::vector<Cand> cands;
+    candidates(x, cands);
+    exprs.clear();
+    for (const Cand& cd : cands) {
+      if (!cd.exists || !cd.active) continue;
+      AffExpr e;
+      e.constant = cd.ct.dist;
+      for (int k = 0; k < 2; ++k) {
+        if ((k == 0 && start_fixed) || (k == 1 && end_fixed)) continue;
+        const Vec& g = (k == 0) ? cd.ct.g0 : cd.ct.g1;
+        double dot = 0;
+        for (int j = 0; j < D; ++j) {
+          e.vars.push_back((t + k) * D + j);
+          e.coeffs.push_back(g[j]);
+          dot += g[j] * x[(t + k) * D + j];
+        }
+        e.constant -= dot;
+      }
+      exprs.push_back(cleanupAff(e));
+    }
+  }
+  // fixed GPU layout: candidate (sphere, obstacle, sub) -> {g0[D], g1[D], dist0, margin, coeff | 0}
+  void denseRows(const Vec& x, std::vector<Vec>& rows) const {
+    std::vector<Cand> cands;
+    candidates(x, cands);
+    for (const Cand& cd : cands) {
+      Vec row(2 * D + 3, 0.0);
+      if (cd.exists) {
+        for (int j = 0; j < D; ++j) {
+          row[j] = cd.ct.g0[j];
+          row[D + j] = cd.ct.g1[j];
+        }
+        row[2 * D] = cd.ct.dist;
+        row[2 * D + 1] = margin;
+        row[2 * D + 2] = cd.active ? coeff : 0.0;
+      }
+      rows.push_back(row);
+    }
+  }
+  Vec values(const Vec& x) const {
+    std::vector<Cand> cands;
+    candidates(x, cands);
+    Vec out;
+    for (const Cand& cd : cands)
+      if (cd.exists && cd.active) out.push_back(std::max(margin - cd.ct.dist, 0.0) * coeff);
+    return out;
+  }
+};
+
+// what CollisionCost / CollisionConstraint need from an evaluator (collision_terms.cpp:1283-1412)
+struct CollisionCalc {
+  std::function<void(const Vec&, std::vector<AffExpr>&)> distExpressions;
+  std::function<Vec(const Vec&)> values;
+  double margin, coeff;
+};
+template <class E>
+CollisionCalc calcOf(const E& e) {
+  return CollisionCalc{[e](const Vec& x, std::vector<AffExpr>& ex) { e.distExpressions(x, ex); },
+                       [e](const Vec& x) { return e.values(x); }, e.margin, e.coeff};
+}
 class CollisionConstraint : public Constraint {
 public:
-  explicit CollisionConstraint(CollisionEval e) : e_(std::move(e)) {}
+  explicit CollisionConstraint(CollisionCalc e) : e_(std::move(e)) {}
   CntType type() const override { return INEQ; }
   Vec value(const Vec& x) override { return e_.values(x); }
   std::shared_ptr<ConvexConstraints> convex(const Vec& x, Model*) override {
@@ -429,11 +611,11 @@ public:
   }
 
 private:
-  CollisionEval e_;
+  CollisionCalc e_;
 };
 class CollisionCost : public Cost {
 public:
-  explicit CollisionCost(CollisionEval e) : e_(std::move(e)) {}
+  explicit CollisionCost(CollisionCalc e) : e_(std::move(e)) {}
   double value(const Vec& x) override {
     double s = 0;
     for (double v : e_.values(x)) s += v;
@@ -452,7 +634,7 @@ public:
   }
 
 private:
-  CollisionEval e_;
+  CollisionCalc e_;
 };
 }  // namespace
 
@@ -693,8 +875,35 @@ TrajProblem buildProblem(const tb200_problem_desc& desc, int b) {
         break;
       }
       case TB200_TERM_COLLISION: {
-        if (tm.evaluator_type != TB200_COLL_DISCRETE)
-          throw std::runtime_error("oracle: only the DISCRETE collision evaluator is restated so far");
+        if (tm.evaluator_type == TB200_COLL_LVS_DISCRETE)
+          throw std::runtime_error("oracle: the LVS_DISCRETE collision evaluator is not restated");
+        if (tm.evaluator_type != TB200_COLL_DISCRETE) {
+          // CollisionTermInfo::hatch continuous branch (problem_description.cpp:1776-1819 / cost: 1714-1760):
+          // one object per step pair [first, last), expression type from the fixed steps
+          const double lvs = (tm.evaluator_type == TB200_COLL_CONTINUOUS) ? std::numeric_limits<double>::max()
+                                                                          : tm.longest_valid_segment_length;
+          for (int t = tm.first_step; t < tm.last_step; ++t) {
+            bool cur_fixed = false, next_fixed = false;
+            for (int f = 0; f < tm.n_fixed_steps; ++f) {
+              cur_fixed |= (tm.fixed_steps[f] == t);
+              next_fixed |= (tm.fixed_steps[f] == t + 1);
+            }
+            // (two adjacent fixed steps fall into the START_FIXED_END_FREE branch: the reference's throw is unreachable)
+            CastCollisionEval e{tp.robot, obstacles, t, D, tm.margin, tm.coeff, tm.margin_buffer, lvs, cur_fixed,
+                                !cur_fixed && next_fixed};
+            tp.coll_hooks.push_back([e](const Vec& x, std::vector<Vec>& rows) { e.denseRows(x, rows); });
+            if (is_cost) {
+              auto c = std::make_shared<CollisionCost>(calcOf(e));
+              c->name = nm + "_" + std::to_string(t);
+              tp.prob->addCost(c);
+            } else {
+              auto c = std::make_shared<CollisionConstraint>(calcOf(e));
+              c->name = nm + "_" + std::to_string(t);
+              tp.prob->addConstraint(c);
+            }
+          }
+          break;
+        }
         // CollisionTermInfo::hatch discrete branch (problem_description.cpp:1762-1775, 1824-1833)
         for (int t = tm.first_step; t <= tm.last_step; ++t) {
           bool fixed = false;
@@ -703,11 +912,11 @@ TrajProblem buildProblem(const tb200_problem_desc& desc, int b) {
           CollisionEval e{tp.robot, obstacles, t, D, tm.margin, tm.coeff, tm.margin_buffer};
           tp.coll_hooks.push_back([e](const Vec& x, std::vector<Vec>& rows) { e.denseRows(x, rows); });
           if (is_cost) {
-            auto c = std::make_shared<CollisionCost>(e);
+            auto c = std::make_shared<CollisionCost>(calcOf(e));
             c->name = nm + "_" + std::to_string(t);
             tp.prob->addCost(c);
           } else {
-            auto c = std::make_shared<CollisionConstraint>(e);
+            auto c = std::make_shared<CollisionConstraint>(calcOf(e));
             c->name = nm + "_" + std::to_string(t);
             tp.prob->addConstraint(c);
           }

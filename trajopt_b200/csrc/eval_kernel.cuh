@@ -18,30 +18,28 @@ enum EvalMode { EVAL_INIT = 0, EVAL_STEP = 1, EVAL_ONLY = 2 };
 
 struct EvalSmem {
   // offsets in doubles into the dynamic shared buffer
-  int x, sph, jax, jor, cartf, viol, mask, misc, fr, terms, obst, stage, total;
+  int x, sph, jax, cartf, viol, mask, misc, fr, terms, obst, sphr, total;
 };
 __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_cart_objs, int n_coll_cand,
-                                                      int n_mask_words, int S = 0, int n_joint_objs = 0,
-                                                      int stage_per_warp = 0) {
+                                                      int n_mask_words, int S = 0, int n_joint_objs = 0) {
   EvalSmem s;
   int o = 0;
   s.x = o;      o += T * D;
   s.sph = o;    o += T * L * 3;
-  s.jax = o;    o += T * D * 3;
-  s.jor = o;    o += T * D * 3;
+  o += o & 1;                                         // 16-byte alignment (vector loads)
+  s.jax = o;    o += T * D * 6;                       // per (waypoint, joint): A[3], B[3] (see the kernel)
+  s.obst = o;   o += 4 * 64;                          // this trajectory's obstacle spheres (x, y, z, r)
+  s.sphr = o;   o += L + (L & 1);                     // radii of the robot spheres
   s.cartf = o;  o += n_cart_objs * (1 + D) * 12;
   s.mask = o;   o += n_mask_words;
   s.misc = o;   o += 8;
-  s.obst = o;   o += 4 * 64;                          // this trajectory's obstacle spheres (x, y, z, r)
-  o += o & 1;                                         // 16-byte alignment of everything below
+  o += o & 1;
   // the FK frames are dead once the joint axes / sphere centres are emitted: the violation and term buffers of the
   // later phases reuse their space
   s.fr = o;                                           // frames of every FK job: local, then (in place) world
   s.viol = o;
-  s.stage = o + n_coll_cand;                          // 8 warps x (32 candidate rows + the object's lever arms)
-  s.terms = s.stage;                                  // per-(step, joint) terms of the joint-space objects (later phase)
-  const int st = 8 * stage_per_warp, tm = n_joint_objs * 2 * T * D;
-  const int a = (T + n_cart_objs * D) * S * 12, b2 = n_coll_cand + (st > tm ? st : tm);
+  s.terms = o + n_coll_cand;                          // per-(step, joint) terms of the joint-space objects (later phase)
+  const int a = (T + n_cart_objs * D) * S * 12, b2 = n_coll_cand + n_joint_objs * 2 * T * D;
   o += a > b2 ? a : b2;
   o += o & 1;
   s.total = o;
@@ -100,8 +98,7 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
   const bool qp_failed = (mode == EVAL_STEP) && (p.qp_status[b] != 0);
   if (tid == 0 && !qp_failed) atomicAdd(p.active_count + 1, 1);  // trajectories actually convexified (bench: bytes moved)
   const int n_mask_words = p.n_coll_objs * p.coll_words;
-  const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_cand, n_mask_words, p.S, ex.n_joint_objs,
-                                      ((32 * (D + 3) + 1) & ~1) + ((L * D * 3 + 1) & ~1));
+  const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_cand, n_mask_words, p.S, ex.n_joint_objs);
   double* xs = sm + S.x;
   unsigned long long* mask = reinterpret_cast<unsigned long long*>(sm + S.mask);
   int* misc = reinterpret_cast<int*>(sm + S.misc);
@@ -125,6 +122,7 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
     {
       const double* og = p.obstacles + (p.obstacles_per_traj ? static_cast<size_t>(b) * O * 4 : 0);
       for (int i = tid; i < O * 4; i += kEvalThreads) sm[S.obst + i] = og[i];
+      for (int i = tid; i < L; i += kEvalThreads) sm[S.sphr + i] = p.spheres[i].r;
     }
     __syncthreads();
 
@@ -174,17 +172,25 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
       }
     }
     __syncthreads();
-    // joint axes / origins per (waypoint, moving segment), sphere centres per (waypoint, sphere), link frames
+    // per (waypoint, joint) the two vectors the gradient of a point on the chain needs: for a point c and a unit
+    // direction n,  n . d(c)/dq_j = n . (a_j x (c - o_j)) = A_j . (c x n) - B_j . n  with A_j = a_j, B_j = a_j x o_j
+    // (revolute; a_j axis, o_j origin of the joint in the scene root) and A_j = 0, B_j = -a_j (prismatic).
+    // Six doubles per (waypoint, joint), 16-byte aligned: the row writers read them as broadcasts.
     for (int w = tid; w < T * Sg; w += kEvalThreads) {
       const int t = w / Sg, sg = w % Sg;
       const DevSegment& g = p.segs[sg];
       if (g.q_index < 0) continue;
       const double* f = FR + static_cast<size_t>(w) * 12;
-      double* jax = sm + S.jax + (t * D + g.q_index) * 3;
-      double* jor = sm + S.jor + (t * D + g.q_index) * 3;
-      for (int i = 0; i < 3; ++i) {
-        jax[i] = f[i * 3] * g.axis[0] + f[i * 3 + 1] * g.axis[1] + f[i * 3 + 2] * g.axis[2];
-        jor[i] = f[9 + i];
+      double* ab = sm + S.jax + (t * D + g.q_index) * 6;
+      double a[3];
+      for (int i = 0; i < 3; ++i) a[i] = f[i * 3] * g.axis[0] + f[i * 3 + 1] * g.axis[1] + f[i * 3 + 2] * g.axis[2];
+      if (g.joint_type == 1) {
+        const double ox = f[9], oy = f[10], oz = f[11];
+        ab[0] = a[0]; ab[1] = a[1]; ab[2] = a[2];
+        ab[3] = a[1] * oz - a[2] * oy; ab[4] = a[2] * ox - a[0] * oz; ab[5] = a[0] * oy - a[1] * ox;
+      } else {
+        ab[0] = 0.0; ab[1] = 0.0; ab[2] = 0.0;
+        ab[3] = -a[0]; ab[4] = -a[1]; ab[5] = -a[2];
       }
     }
     for (int w = tid; w < T * L; w += kEvalThreads) {
@@ -247,15 +253,13 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
 
     // ---- dense candidate collision rows (collision_terms.cpp:203-250, 343-383, 540-556, 655-691) ----
     // candidate r = (collision object k, robot sphere s, obstacle o);  row = {grad[D], dist0, margin, coeff|0}
-    // One warp per collision object (= waypoint): its L*O candidate rows are contiguous in HBM, so the warp builds
-    // them in a shared staging area and writes them out as fully coalesced 16-byte stores; the activity mask of
-    // 32 candidates is one ballot.  No block barrier inside the phase.
-    const int LO = L * O, lane_c = tid & 31, warp_c = tid >> 5;
+    // One warp per collision object (= waypoint), one lane per candidate: the lane builds its row in registers and
+    // stores it straight to HBM as 16-byte pieces (the L*O rows of an object are contiguous, so a warp fills whole
+    // sectors between its stores); the activity mask of 32 candidates is one ballot.  No block barrier inside.
+    const int LO = L * O, lane_c = tid & 31;
     const double* obst = sm + S.obst;
     double* rows_out = p.coll_rows + slot * static_cast<size_t>(p.n_coll_cand) * p.coll_stride;
-    const int stage_sz = ((32 * (D + 3) + 1) & ~1) + ((L * D * 3 + 1) & ~1);
-    double* stage = sm + S.stage + static_cast<size_t>(warp_c) * stage_sz;  // 32 candidate rows at a time
-    double* lever = stage + ((32 * (D + 3) + 1) & ~1);  // d(centre of sphere s)/dq_j for the object being processed
+    const float inv_O = 1.0f / static_cast<float>(O);
     for (;;) {
       int k = 0;
       if (lane_c == 0) k = atomicAdd(&misc[2], 1);  // next collision object: warps take them as they get free
@@ -264,59 +268,49 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
       const DevObj& co = ex.coll_objs[k];
       const int t = co.first;
       const double margin = co.margin, reach = co.margin + co.buffer, coeff = co.coeff;
-      // lever arms a_j x (c_s - o_j) (revolute) / a_j (prismatic) / 0 (joint does not move the sphere): they do
-      // not depend on the obstacle, so they are built once per (sphere, joint)
-      for (int w = lane_c; w < L * D; w += 32) {
-        const int sl = w / D, j = w % D;
-        const double* c = sm + S.sph + (t * L + sl) * 3;
-        const double* a = sm + S.jax + (t * D + j) * 3;
-        const double* oj = sm + S.jor + (t * D + j) * 3;
-        const bool moves = (ex.sphere_jmask[sl] >> j) & 1u, rev = ex.qtype[j] == 1;
-        const double rx = c[0] - oj[0], ry = c[1] - oj[1], rz = c[2] - oj[2];
-        lever[w * 3 + 0] = moves ? (rev ? a[1] * rz - a[2] * ry : a[0]) : 0.0;
-        lever[w * 3 + 1] = moves ? (rev ? a[2] * rx - a[0] * rz : a[1]) : 0.0;
-        lever[w * 3 + 2] = moves ? (rev ? a[0] * ry - a[1] * rx : a[2]) : 0.0;
-      }
-      __syncwarp();
+      const double* AB = sm + S.jax + t * D * 6;
       for (int c0 = 0; c0 < LO; c0 += 32) {
         const int cnd = c0 + lane_c;
         const bool in = cnd < LO;
-        const int sl = in ? cnd / O : 0, o = in ? cnd % O : 0;
+        const int sl = in ? static_cast<int>((static_cast<float>(cnd) + 0.5f) * inv_O) : 0, o = in ? cnd - sl * O : 0;
         const double* c = sm + S.sph + (t * L + sl) * 3;
-        const double dx = obst[o * 4] - c[0], dy = obst[o * 4 + 1] - c[1], dz = obst[o * 4 + 2] - c[2];
+        const double cx = c[0], cy = c[1], cz = c[2];
+        const double4 ob = *reinterpret_cast<const double4*>(obst + o * 4);
+        const double dx = ob.x - cx, dy = ob.y - cy, dz = ob.z - cz;
         const double len = sqrt(dx * dx + dy * dy + dz * dz);
-        const double dist = len - p.spheres[sl].r - obst[o * 4 + 3];
+        const double dist = len - sm[S.sphr + sl] - ob.w;
         const double inv = 1.0 / len;
         const double nx = dx * inv, ny = dy * inv, nz = dz * inv;  // from the robot sphere towards the obstacle
+        const double mx = cy * nz - cz * ny, my = cz * nx - cx * nz, mz = cx * ny - cy * nx;  // c x n
         const unsigned jm = ex.sphere_jmask[sl];
-        double* row = stage + lane_c * (D + 3);
-        const double* lv = lever + sl * D * 3;
+        const bool active = in && !(dist > reach);
+        double row[D + 3 + ((D + 3) & 1)];
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-          const double g = -(nx * lv[j * 3] + ny * lv[j * 3 + 1] + nz * lv[j * 3 + 2]);  // -n . (a x r)
-          if (in) row[j] = ((jm >> j) & 1u) ? g : 0.0;
+          const double2 a01 = *reinterpret_cast<const double2*>(AB + j * 6);
+          const double2 a2b0 = *reinterpret_cast<const double2*>(AB + j * 6 + 2);
+          const double2 b12 = *reinterpret_cast<const double2*>(AB + j * 6 + 4);
+          // d(dist)/dq_j = -n . d(c)/dq_j = B_j . n - A_j . (c x n)
+          const double g = (a2b0.y * nx + b12.x * ny + b12.y * nz) - (a01.x * mx + a01.y * my + a2b0.x * mz);
+          row[j] = ((jm >> j) & 1u) ? g : 0.0;
         }
-        const bool active = in && !(dist > reach);
+        row[D] = dist;
+        row[D + 1] = margin;
+        row[D + 2] = active ? coeff : 0.0;
         if (in) {
-          row[D] = dist;
-          row[D + 1] = margin;
-          row[D + 2] = active ? coeff : 0.0;
           sm[S.viol + co.src_off + cnd] = active ? fmax(margin - dist, 0.0) * coeff : 0.0;
+          double* dstp = rows_out + static_cast<size_t>(co.src_off + cnd) * (D + 3);
+          if constexpr (((D + 3) & 1) == 0) {  // rows are 16-byte aligned: D + 3 even, buffers 256-byte aligned
+            double2* d2 = reinterpret_cast<double2*>(dstp);
+#pragma unroll
+            for (int i = 0; i < (D + 3) / 2; ++i) d2[i] = make_double2(row[2 * i], row[2 * i + 1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < D + 3; ++i) dstp[i] = row[i];
+          }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, active);
         if (lane_c == 0 && bal) atomicOr(&mask[k * p.coll_words + (c0 >> 6)], static_cast<unsigned long long>(bal) << (c0 & 63));
-        __syncwarp();
-        // coalesced copy of these (up to) 32 rows: 16 bytes per lane per step when the offset is even
-        const int n = (LO - c0 < 32 ? LO - c0 : 32) * (D + 3);
-        double* dstp = rows_out + static_cast<size_t>(co.src_off + c0) * p.coll_stride;
-        if ((((co.src_off + c0) * p.coll_stride) & 1) == 0 && (n & 1) == 0) {
-          const double2* s2 = reinterpret_cast<const double2*>(stage);
-          double2* d2 = reinterpret_cast<double2*>(dstp);
-          for (int i = lane_c; i < n / 2; i += 32) d2[i] = s2[i];
-        } else {
-          for (int i = lane_c; i < n; i += 32) dstp[i] = stage[i];
-        }
-        __syncwarp();
       }
     }
     __syncthreads();

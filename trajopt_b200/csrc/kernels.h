@@ -1,0 +1,13 @@
+// Kernel instances live in their own translation units (eval_kernels.cu, qp_kernels.cu) so that they build in
+// parallel; the host side of the C ABI (trajopt_b200.cu) reaches them through these look-ups.
+#pragma once
+#include "device_types.cuh"
+
+namespace tb200 {
+struct EvalExtra;
+using QpKernelFn = void (*)(DevProblem, const double*, const double*, int*, int*, int);
+using EvalKernelFn = void (*)(DevProblem, EvalExtra, int, const double*);
+QpKernelFn qp_kernel_for(int D);      // nullptr: no instance for this number of joints
+EvalKernelFn eval_kernel_for(int D);
+int qp_debug_prof(unsigned long long* out, int reset);  // TB200_PROFILE builds only (else returns -1)
+}  // namespace tb200

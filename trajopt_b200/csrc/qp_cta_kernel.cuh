@@ -22,12 +22,11 @@
 // and factor) in HBM and resumes from it in the next launch.
 #pragma once
 #include "device_types.cuh"
-#include "eval_kernel.cuh"
 
 namespace tb200 {
 
 #ifdef TB200_PROFILE
-__device__ unsigned long long g_prof[16];
+static __device__ unsigned long long g_prof[16];
 #define PROF_T0() const long long prof_t0_ = clock64()
 #define PROF_ADD(slot) do { if (q.tid == 0) atomicAdd(&g_prof[slot], (unsigned long long)(clock64() - prof_t0_)); } while (0)
 #else

@@ -19,6 +19,7 @@
 #include "../../include/trajopt_b200.h"
 #include "eval_kernel.cuh"
 #include "qp_cta_kernel.cuh"
+#include "kernels.h"
 
 using namespace tb200;
 
@@ -60,29 +61,6 @@ void quatToRot(const double* q, double* R) {
   R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
 }
 }  // namespace
-
-// QP kernel instances: the block size of the block-cyclic-reduction factor is a compile-time constant (2*D).
-using QpKernelFn = void (*)(DevProblem, const double*, const double*, int*, int*, int);
-static QpKernelFn qp_kernel_for(int D) {
-  switch (D) {
-    case 2: return qp_kernel<2>;
-    case 3: return qp_kernel<3>;
-    case 6: return qp_kernel<6>;
-    case 7: return qp_kernel<7>;
-    default: return nullptr;
-  }
-}
-
-using EvalKernelFn = void (*)(DevProblem, EvalExtra, int, const double*);
-static EvalKernelFn eval_kernel_for(int D) {
-  switch (D) {
-    case 2: return eval_convexify_decide_kernel<2>;
-    case 3: return eval_convexify_decide_kernel<3>;
-    case 6: return eval_convexify_decide_kernel<6>;
-    case 7: return eval_convexify_decide_kernel<7>;
-    default: return nullptr;
-  }
-}
 
 struct tb200_problem {
   int device = 0;
@@ -399,7 +377,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
 
   // ---- kernel resources --------------------------------------------------------------------------------
   const EvalSmem es = eval_smem_layout(T, D, dp.L, P->ex.n_cart_objs, n_coll_cand, dp.n_coll_objs * dp.coll_words, dp.S,
-                                       P->ex.n_joint_objs, ((32 * (D + 3) + 1) & ~1) + ((dp.L * D * 3 + 1) & ~1));
+                                       P->ex.n_joint_objs);
   P->eval_smem = static_cast<size_t>(es.total) * sizeof(double);
   const QpSmem qs = qp_smem_layout(N, 2 * D, dp.row_stride, std::max(D, 3), max_rows);
   const int Np = qp_block_count(N, 2 * D) * 2 * D;
@@ -744,13 +722,7 @@ int tb200_debug_fetch_trace(tb200_problem* P, double* out, int32_t* len) {
   return TB200_OK;
 }
 
-#ifdef TB200_PROFILE
-int tb200_debug_prof(unsigned long long* out, int reset) {
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); return 0; }
-  cudaMemcpyFromSymbol(out, g_prof, 16 * sizeof(unsigned long long));
-  return 0;
-}
-#endif
+int tb200_debug_prof(unsigned long long* out, int reset) { return qp_debug_prof(out, reset); }
 
 /* not part of the public header: solver diagnostics of the last QP of every trajectory, [B][16] */
 int tb200_debug_last_qp(tb200_problem* P, double* out) {

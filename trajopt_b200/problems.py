@@ -6,8 +6,8 @@ inputs fed to both the CUDA path and the CPU oracle.
 import numpy as np
 
 from . import capi, robots
-from .capi import (COLL_DISCRETE, ROLE_CNT, ROLE_COST, TERM_CART_POSE, TERM_COLLISION, TERM_JOINT_ACC,
-                   TERM_JOINT_POS, TERM_JOINT_VEL, ProblemDesc, Term)
+from .capi import (COLL_DISCRETE, COLL_LVS_CONTINUOUS, ROLE_CNT, ROLE_COST, TERM_CART_POSE, TERM_CART_VEL, TERM_COLLISION,
+                   TERM_JOINT_ACC, TERM_JOINT_POS, TERM_JOINT_VEL, ProblemDesc, Term)
 
 SEED = 20260923
 
@@ -49,6 +49,14 @@ def cart_pose_term(role, timestep, link, target_slot=-1, target_pose=None, pos_c
     t.target_pose[:] = target_pose if target_pose is not None else (0, 0, 0, 1, 0, 0, 0)
     t.pos_coeffs[:] = pos_coeffs
     t.rot_coeffs[:] = rot_coeffs
+    return t
+
+
+def cart_vel_term(role, first, last, link, max_displacement):
+    """CartVelTermInfo (problem_description.cpp:989-1057): one object per step pair first..last (pair t = (t, t+1))."""
+    t = Term()
+    t.kind, t.role, t.first_step, t.last_step = TERM_CART_VEL, role, first, last
+    t.link, t.target_slot, t.max_displacement = link, -1, max_displacement
     return t
 
 
@@ -117,6 +125,16 @@ def config2(B=1024, T=30, seed=SEED + 2, n_obstacles=8):
     D = 7
     q0, q1 = _sample_endpoints(rng, robot, B)
     init = interpolate(q0, q1, T)
+    obstacles = _sample_obstacles(rng, robot, q0, q1, n_obstacles)
+    terms = [joint_term(TERM_JOINT_VEL, ROLE_COST, D, 0, T - 1), joint_term(TERM_JOINT_ACC, ROLE_COST, D, 0, T - 1),
+             cart_pose_term(ROLE_CNT, T - 1, robot["tool"], target_slot=0),
+             collision_term(ROLE_CNT, 0, T - 1, margin=0.02, coeff=20.0, buffer=0.01, fixed_steps=[0])]
+    return ProblemDesc(robot, T, terms, init, fixed_timesteps=[0],
+                       cart_targets=_targets_from_goal(robot, q1, robot["tool"]), obstacles=obstacles)
+
+
+def _sample_obstacles(rng, robot, q0, q1, n_obstacles):
+    B = len(q0)
     radii = np.array([s.radius for s in robot["spheres"]])
     obstacles = np.zeros((B, n_obstacles, 4))
     lo, hi = np.array([0.35, -0.70, 0.55]), np.array([0.95, 0.10, 1.25])
@@ -129,11 +147,37 @@ def config2(B=1024, T=30, seed=SEED + 2, n_obstacles=8):
             if np.min(np.linalg.norm(ends - c, axis=1) - rr - 0.10) >= 0.05:
                 obstacles[b, k] = (*c, 0.10)
                 k += 1
-    terms = [joint_term(TERM_JOINT_VEL, ROLE_COST, D, 0, T - 1), joint_term(TERM_JOINT_ACC, ROLE_COST, D, 0, T - 1),
-             cart_pose_term(ROLE_CNT, T - 1, robot["tool"], target_slot=0),
-             collision_term(ROLE_CNT, 0, T - 1, margin=0.02, coeff=20.0, buffer=0.01, fixed_steps=[0])]
-    return ProblemDesc(robot, T, terms, init, fixed_timesteps=[0],
-                       cart_targets=_targets_from_goal(robot, q1, robot["tool"]), obstacles=obstacles)
+    return obstacles
 
 
-CONFIGS = {"cfg0": config0, "cfg1": config1, "cfg2": config2}
+def config3(B=4096, T=50, seed=SEED + 3, n_obstacles=8, via_every=10, lvs=0.05):
+    """configs[3]: the configs[2] world with LVS_CONTINUOUS collision (longest_valid_segment_length 0.05) between
+    consecutive waypoints, position-only CartPose constraints on every 10th waypoint along the straight Cartesian
+    line start -> goal, the full CartPose constraint at the last waypoint, and a CartVel INEQ constraint
+    (max_displacement 0.05) on every step pair."""
+    robot = robots.pr2_arm("r", with_spheres=True)
+    rng = np.random.default_rng(seed)
+    D = 7
+    q0, q1 = _sample_endpoints(rng, robot, B)
+    init = interpolate(q0, q1, T)
+    obstacles = _sample_obstacles(rng, robot, q0, q1, n_obstacles)
+    tool = robot["tool"]
+    goal = _targets_from_goal(robot, q1, tool)[:, 0]
+    start = _targets_from_goal(robot, q0, tool)[:, 0]
+    vias = [t for t in range(via_every, T - 1, via_every)]
+    targets = np.zeros((B, len(vias) + 1, 7))
+    terms = [joint_term(TERM_JOINT_VEL, ROLE_COST, D, 0, T - 1), joint_term(TERM_JOINT_ACC, ROLE_COST, D, 0, T - 1)]
+    for k, t in enumerate(vias):
+        w = t / (T - 1)
+        targets[:, k, :3] = (1 - w) * start[:, :3] + w * goal[:, :3]
+        targets[:, k, 3:] = goal[:, 3:]
+        terms.append(cart_pose_term(ROLE_CNT, t, tool, target_slot=k, rot_coeffs=(0, 0, 0)))
+    targets[:, len(vias)] = goal
+    terms.append(cart_pose_term(ROLE_CNT, T - 1, tool, target_slot=len(vias)))
+    terms.append(cart_vel_term(ROLE_CNT, 0, T - 2, tool, 0.05))
+    terms.append(collision_term(ROLE_CNT, 0, T - 1, margin=0.02, coeff=20.0, buffer=0.01, fixed_steps=[0],
+                                evaluator=COLL_LVS_CONTINUOUS, lvs=lvs))
+    return ProblemDesc(robot, T, terms, init, fixed_timesteps=[0], cart_targets=targets, obstacles=obstacles)
+
+
+CONFIGS = {"cfg0": config0, "cfg1": config1, "cfg2": config2, "cfg3": config3}
