@@ -8,7 +8,8 @@ np.set_printoptions(linewidth=220, precision=6)
 name = sys.argv[1]
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 12
-d = {"cfg1": problems.config1, "cfg2": problems.config2}[name](B=B, T=T)
+d = {"cfg1": problems.config1, "cfg2": problems.config2,
+     "cfg3": lambda B, T: problems.config3(B=B, T=T, via_every=4 if T < 20 else 10)}[name](B=B, T=T)
 p = api.Problem(d)
 cap = 600
 p.lib.tb200_debug_enable_trace(p.handle, cap)

@@ -12,12 +12,27 @@ QP_X_ATOL = 1e-7      # one QP solve: ADMM + polish, reduced banded solve vs env
 COST_ATOL = 1e-6      # final total cost of the SQP
 
 
+_MAKERS = {"cfg1": lambda: problems.config1(B=16, T=12), "cfg2": lambda: problems.config2(B=16, T=12),
+           "cfg1_full_T": lambda: problems.config1(B=4, T=30), "cfg2_full_T": lambda: problems.config2(B=4, T=30),
+           # configs[3] terms (CartVel + LVS_CONTINUOUS collision + via-point CartPose) at the lengths the QP kernel holds
+           "cfg3": lambda: problems.config3(B=16, T=12, via_every=4), "cfg3_T30": lambda: problems.config3(B=4, T=30),
+           "cfg3_no_lvs": lambda: problems.config3(B=8, T=12, via_every=4, lvs=10.0)}
+
+
+class _Cfgs(dict):
+    def __missing__(self, name):
+        self[name] = _MAKERS[name]()
+        return self[name]
+
+
+_CACHE = _Cfgs()
+
+
 def _cfgs():
-    return {"cfg1": problems.config1(B=16, T=12), "cfg2": problems.config2(B=16, T=12),
-            "cfg1_full_T": problems.config1(B=4, T=30), "cfg2_full_T": problems.config2(B=4, T=30)}
+    return _CACHE
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_full_T"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_full_T", "cfg3", "cfg3_T30", "cfg3_no_lvs"])
 def test_convexify_rows_match_oracle(oracle, name):
     d = _cfgs()[name]
     rng = np.random.default_rng(7)
@@ -35,7 +50,7 @@ def test_convexify_rows_match_oracle(oracle, name):
         assert ((got["coll_rows"][..., -1] != 0) == (ref["coll_rows"][..., -1] != 0)).all()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
 @pytest.mark.parametrize("trust", [0.1, 0.01])
 def test_qp_solve_matches_oracle(oracle, name, trust):
     d = _cfgs()[name]
@@ -54,16 +69,38 @@ def test_qp_solve_matches_oracle(oracle, name, trust):
     np.testing.assert_allclose(got["model_cost_vals"], ref["model_cost_vals"], rtol=1e-6, atol=1e-7)
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg1_full_T", "cfg2_full_T"])
+def _solve_with_trace(d, cap=600):
+    """Solve on the GPU with the per-QP decision trace on; returns results and, per trajectory, whether any of its
+    QPs ran into OSQP's iteration limit (such a QP returns an unconverged ADMM iterate, which depends on rounding:
+    no two linear-algebra back ends agree on it, so those trajectories cannot be compared step by step)."""
+    import ctypes as C
+    p = api.Problem(d)
+    p.lib.tb200_debug_enable_trace(p.handle, cap)
+    got = p.solve()
+    tr = np.zeros((d.B, cap, 14))
+    tl = np.zeros(d.B, np.int32)
+    p.lib.tb200_debug_fetch_trace(p.handle, tr.ctypes.data_as(C.POINTER(C.c_double)), tl.ctypes.data_as(C.POINTER(C.c_int32)))
+    p.close()
+    hit = np.array([(tr[b, :tl[b], 7] >= d.c.qp.max_iter).any() for b in range(d.B)])
+    return got, hit
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg1_full_T", "cfg2_full_T", "cfg3", "cfg3_T30"])
 def test_sqp_solve_matches_oracle(oracle, name):
     d = _cfgs()[name]
-    got = api.solve(d)
+    got, hit = _solve_with_trace(d)
     ref = oracle.solve_batch(d)
-    assert (got["status"] == ref["status"]).all(), (got["status"], ref["status"])
-    assert (got["n_qp_solves"] == ref["n_qp_solves"]).all(), (got["n_qp_solves"], ref["n_qp_solves"])
-    np.testing.assert_allclose(got["total_cost"], ref["total_cost"], atol=COST_ATOL)
-    np.testing.assert_allclose(got["x"], ref["x"], atol=1e-5)
-    np.testing.assert_allclose(got["cnt_viols"], ref["cnt_viols"], atol=1e-6)
+    ok = ~hit
+    if not name.startswith("cfg3"):
+        assert ok.all(), "a QP of configs[1]/[2] ran into the ADMM iteration limit"
+    assert ok.mean() >= 0.7, hit
+    assert (got["status"][ok] == ref["status"][ok]).all(), (got["status"], ref["status"], hit)
+    assert (got["n_qp_solves"][ok] == ref["n_qp_solves"][ok]).all(), (got["n_qp_solves"], ref["n_qp_solves"], hit)
+    np.testing.assert_allclose(got["total_cost"][ok], ref["total_cost"][ok], atol=COST_ATOL)
+    np.testing.assert_allclose(got["x"][ok], ref["x"][ok], atol=1e-5)
+    np.testing.assert_allclose(got["cnt_viols"][ok], ref["cnt_viols"][ok], atol=1e-6)
+    # the others still end in a terminal state of the same SQP (not compared step by step)
+    assert (got["status"][hit] != capi.OPT_INVALID).all()
 
 
 def test_joint_terms_cfg0(oracle):

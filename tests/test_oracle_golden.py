@@ -258,3 +258,70 @@ def test_qp_kkt_on_trajectory_subproblems(oracle):
         ok = r["polish"] == 1
         assert ok.sum() >= 4
         assert r["kkt"][ok][:, 0].max() < 1e-6 and r["kkt"][ok][:, 1].max() < 1e-9
+
+
+# ---- continuous (cast) collision of the synthetic sphere model (Bullet itself is unpinned) ----
+def _cast_problem(lvs, T=6, B=3, seed=5):
+    from trajopt_b200 import problems
+    return problems.config3(B=B, T=T, seed=seed, via_every=2, lvs=lvs)
+
+
+def test_cast_collision_layout_and_activity(oracle):
+    d = _cast_problem(0.05)
+    L = oracle.layout(d)
+    assert L.coll_row_stride == 2 * d.D + 3 and L.cart_jac_stride == 2 * d.D
+    assert L.n_coll_cand == (d.T - 1) * 7 * 8 * 4
+    x = d.init_traj + 0.02 * np.random.default_rng(3).standard_normal(d.init_traj.shape)
+    r = oracle.convexify_batch(d, x)
+    rows = r["coll_rows"].reshape(d.B, d.T - 1, 7 * 8, 4, 2 * d.D + 3)
+    # sub-segments beyond ceil(|dq| / lvs) do not exist: all-zero rows
+    nsub = np.minimum(np.ceil(np.linalg.norm(np.diff(x, axis=1), axis=2) / 0.05), 4)
+    nsub = np.where(np.linalg.norm(np.diff(x, axis=1), axis=2) > 0.05, nsub, 1)
+    for b in range(d.B):
+        for t in range(d.T - 1):
+            assert (rows[b, t, :, int(nsub[b, t]):] == 0).all()
+            assert (rows[b, t, :, :int(nsub[b, t]), 2 * d.D + 1] == 0.02).all()
+    # the first pair starts at the fixed waypoint 0: its timestep-0 gradient block is empty
+    assert (rows[:, 0, :, :, :d.D] == 0).all()
+    # inactive candidates carry no gradient
+    inactive = rows[..., -1] == 0
+    assert (rows[inactive][:, :2 * d.D] == 0).all()
+
+
+def test_cast_collision_gradient_is_a_distance_derivative(oracle):
+    """For one sub-segment and a small step the row must agree with the finite difference of the swept-sphere
+    distance (the reference linearises at the contact-time state; the mismatch is O(|q1 - q0|))."""
+    from trajopt_b200 import problems
+    d = problems.config3(B=2, T=4, seed=11, via_every=2, lvs=10.0)
+    # shrink the motion so the linearisation point and the waypoints nearly coincide, and move an obstacle close
+    x = d.init_traj.copy()
+    x[:, 1:] = x[:, :1] + 0.002 * np.arange(1, d.T)[None, :, None]
+    from trajopt_b200 import robots
+    robot = robots.pr2_arm("r", with_spheres=True)
+    obst = d.obstacles.copy()
+    for b in range(d.B):
+        c = robots.sphere_centers(robot, x[b, 2])[5]
+        obst[b, 0, :3] = c + np.array([0.0, 0.0, 0.10 + robot["spheres"][5].radius + 0.015])
+    d2 = capi.ProblemDesc(d.robot_spec, d.T, d.terms, x, fixed_timesteps=[0], cart_targets=d.cart_targets, obstacles=obst)
+    r = oracle.convexify_batch(d2, x)
+    rows = r["coll_rows"].reshape(d.B, d.T - 1, 7, 8, 4, 2 * d.D + 3)
+    row = rows[0, 1, 5, 0, 0]  # pair (1,2), sphere 5, obstacle 0, first sub-segment
+    assert row[-1] != 0, "the contact must be active"
+    eps = 1e-6
+    for k in range(2):
+        for j in range(d.D):
+            xp = x.copy()
+            xp[0, 1 + k, j] += eps
+            rp = oracle.convexify_batch(d2, xp)["coll_rows"].reshape(rows.shape)[0, 1, 5, 0, 0]
+            fd = (rp[2 * d.D] - row[2 * d.D]) / eps
+            assert abs(fd - row[k * d.D + j]) < 2e-2 * max(1.0, abs(fd)), (k, j, fd, row[k * d.D + j])
+
+
+def test_cast_collision_sqp_clears_the_swept_volume(oracle):
+    d = _cast_problem(0.05, T=8, B=4, seed=9)
+    r = oracle.solve_batch(d)
+    assert (r["status"] != capi.OPT_FAILED).all()
+    L = oracle.layout(d)
+    conv = r["status"] == capi.OPT_CONVERGED
+    assert conv.any()
+    assert (r["cnt_viols"][conv] < 1e-4).all()

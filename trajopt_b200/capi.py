@@ -221,6 +221,8 @@ _LIB = None
 
 
 def library_path():
+    if os.environ.get("TB200_LIB"):  # an alternative build of the SAME CUDA library (kernel experiments)
+        return os.environ["TB200_LIB"]
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libtrajopt_b200.so")
 
 

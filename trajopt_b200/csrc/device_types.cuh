@@ -29,8 +29,11 @@ enum ObjKind {
   OBJ_JOINT_EQ_CNT = 2,    // Joint*EqConstraint           trajectory_costs.cpp:139-183
   OBJ_JOINT_INEQ_CNT = 3,  // Joint*IneqConstraint         trajectory_costs.cpp:185-254
   OBJ_CART_POSE = 4,       // CartPose ABS cost / EQ cnt   kinematic_terms.cpp:187-366
-  OBJ_COLL = 5             // discrete collision per step  collision_terms.cpp:1283-1412
+  OBJ_COLL = 5,            // discrete collision per step  collision_terms.cpp:1283-1412
+  OBJ_CART_VEL = 6,        // CartVel per step pair        kinematic_terms.cpp:368-425, problem_description.cpp:1011-1057
+  OBJ_COLL_CAST = 7        // continuous (cast) collision per step pair  collision_terms.cpp:262-323, 468-538, 1071-1173
 };
+constexpr int kMaxLvsSegments = 4;  // = TB200_MAX_LVS_SEGMENTS (include/trajopt_b200.h)
 struct DevObj {
   int kind;
   int is_cnt;     // 0 cost, 1 constraint
@@ -42,8 +45,10 @@ struct DevObj {
   int n_rows;     // cart: rows; collision: candidates (n_spheres * n_obstacles); joint: rows emitted
   int link;       // cart: segment
   int target_slot;
-  int pad0, pad1;
+  int pad0;       // index of the object in its own list (cost / cnt)
+  int pad1;       // cart_vel: joints moving the link (bit mask); cast collision: bit 0 start fixed, bit 1 end fixed
   double coeff, margin, buffer;
+  double lvs;     // cast collision: longest valid segment length (max double: never subdivide); cart_vel: max_displacement
 };
 struct DevJointTerm {
   double coeffs[kMaxDof], targets[kMaxDof], upper[kMaxDof], lower[kMaxDof];

@@ -9,6 +9,7 @@
 // Outputs are the fixed-layout rows of DESIGN.md §3: CartPose error/Jacobian rows and the dense
 // candidate collision rows {grad[D], dist0, margin, coeff|0}.
 #pragma once
+#include "joint_terms.cuh"
 #include "kinematics.cuh"
 
 namespace tb200 {
@@ -18,28 +19,36 @@ enum EvalMode { EVAL_INIT = 0, EVAL_STEP = 1, EVAL_ONLY = 2 };
 
 struct EvalSmem {
   // offsets in doubles into the dynamic shared buffer
-  int x, sph, jax, cartf, viol, mask, misc, fr, terms, obst, sphr, total;
+  int x, sph, spo, jax, cartf, velp, objv, mask, misc, fr, terms, obst, sphr, wscr, wscr_stride, total;
 };
-__host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_cart_objs, int n_coll_cand,
-                                                      int n_mask_words, int S = 0, int n_joint_objs = 0) {
+// n_vel_objs: CartVel step pairs; cast: the collision objects are step pairs (continuous evaluator)
+__host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_cart_objs, int n_coll_objs,
+                                                      int n_mask_words, int S, int n_joint_objs, int n_vel_objs,
+                                                      int cast) {
   EvalSmem s;
   int o = 0;
   s.x = o;      o += T * D;
-  s.sph = o;    o += T * L * 3;
+  s.sph = o;    o += T * L * 3;                       // sphere centres per waypoint
+  s.spo = o;    o += cast ? T * L * 3 : 0;            // centre - link origin (R_link * c_local) per waypoint
   o += o & 1;                                         // 16-byte alignment (vector loads)
   s.jax = o;    o += T * D * 6;                       // per (waypoint, joint): A[3], B[3] (see the kernel)
   s.obst = o;   o += 4 * 64;                          // this trajectory's obstacle spheres (x, y, z, r)
   s.sphr = o;   o += L + (L & 1);                     // radii of the robot spheres
   s.cartf = o;  o += n_cart_objs * (1 + D) * 12;
+  s.velp = o;   o += n_vel_objs * 6;                  // link position at both waypoints of a CartVel pair
+  s.objv = o;   o += n_coll_objs;                     // exact value of every collision object (in-order sums)
   s.mask = o;   o += n_mask_words;
   s.misc = o;   o += 8;
   o += o & 1;
-  // the FK frames are dead once the joint axes / sphere centres are emitted: the violation and term buffers of the
-  // later phases reuse their space
+  // per-warp scratch of the cast collision objects: one set of frames, the sphere data of the interior
+  // sub-segment states, one joint vector
+  s.wscr_stride = cast ? (S * 12 + (kMaxLvsSegments - 1) * L * 6 + ((D + 1) & ~1)) : 0;
+  s.wscr = o;   o += 8 * s.wscr_stride;
+  // the FK frames are dead once the joint axes / sphere centres are emitted: the term buffer of the later
+  // phase reuses their space
   s.fr = o;                                           // frames of every FK job: local, then (in place) world
-  s.viol = o;
-  s.terms = o + n_coll_cand;                          // per-(step, joint) terms of the joint-space objects (later phase)
-  const int a = (T + n_cart_objs * D) * S * 12, b2 = n_coll_cand + n_joint_objs * 2 * T * D;
+  s.terms = o;                                        // per-(step, joint) terms of the joint-space objects (later phase)
+  const int a = (T + n_cart_objs * D) * S * 12, b2 = n_joint_objs * 2 * T * D;
   o += a > b2 ? a : b2;
   o += o & 1;
   s.total = o;
@@ -47,7 +56,10 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
 }
 
 struct EvalExtra {
-  int n_cart_objs, n_coll_objs, n_joint_objs, pad;
+  int n_cart_objs, n_coll_objs, n_joint_objs, n_vel_objs;
+  int cast, pad;                     // cast: the collision objects are step pairs (continuous evaluator)
+  const DevObj* vel_objs;            // CartVel step pairs
+  int joint_seg[kMaxDof];            // segment that carries trajectory column j
   int joint_obj_idx[8];  // positions of the joint-space objects in the (costs, cnts) list
   const DevObj* cart_objs;   // pad0 = index in its own list (cost / cnt), is_cnt says which list
   const DevObj* coll_objs;
@@ -55,38 +67,43 @@ struct EvalExtra {
   unsigned sphere_jmask[kMaxSpheres];  // which columns move each sphere
 };
 
-__device__ inline double joint_err(const double* x, int D, int order, int t, int d, double target) {
-  double e;
-  if (order == 0)
-    e = x[t * D + d];
-  else if (order == 1)
-    e = x[(t + 1) * D + d] - x[t * D + d];
-  else
-    e = x[t * D + d] - 2.0 * x[(t + 1) * D + d] + x[(t + 2) * D + d];
-  return e - target;
-}
-
-// exact Cost::value / Constraint::violation of a joint-space object at x
-__device__ inline double joint_obj_value(const DevProblem& p, const DevObj& o, const double* x) {
-  const DevJointTerm& jt = p.joint_terms[o.term];
-  double s = 0.0;
-  for (int t = o.first; t < o.first + o.n_steps; ++t)
-    for (int d = 0; d < p.D; ++d) {
-      const double e = joint_err(x, p.D, o.order, t, d, jt.targets[d]);
-      if (o.kind == OBJ_JOINT_EQ_COST)
-        s += e * e * jt.coeffs[d];
-      else if (o.kind == OBJ_JOINT_EQ_CNT)
-        s += fabs(e * e * jt.coeffs[d]);  // value() is c*e^2 while the row is c*e (trajectory_costs.cpp:160 vs 173)
-      else {
-        s += fmax((e - jt.upper[d]) * jt.coeffs[d], 0.0);
-        s += fmax((jt.lower[d] - e) * jt.coeffs[d], 0.0);
-      }
+// FK of ONE joint state by a warp: local frames (lanes over segments), then the chain products row by row
+// (lanes 0-2; the other lanes only keep the barriers).  F: [S][12] world frames (R row-major, p).
+__device__ inline void warp_fk(const DevProblem& p, const double* q, double* F, int lane) {
+  const int Sg = p.S;
+  for (int sg = lane; sg < Sg; sg += 32) {
+    const DevSegment g = p.segs[sg];
+    Frame loc;
+    segment_local_q(g, g.q_index >= 0 ? q[g.q_index] : 0.0, loc);
+    double* f = F + sg * 12;
+    for (int i = 0; i < 9; ++i) f[i] = loc.R[i];
+    for (int i = 0; i < 3; ++i) f[9 + i] = loc.p[i];
+  }
+  __syncwarp();
+  const bool act = lane < 3;
+  const int i = act ? lane : 0;
+  for (int sg = 0; sg < Sg; ++sg) {
+    const int parent = p.segs[sg].parent;
+    double l[12];
+    for (int k = 0; k < 12; ++k) l[k] = F[sg * 12 + k];
+    __syncwarp();  // every row has read the local frame before it is overwritten
+    if (act && parent >= 0) {
+      const double* P = F + parent * 12;
+      const double r0 = P[i * 3], r1 = P[i * 3 + 1], r2 = P[i * 3 + 2], pi = P[9 + i];
+      F[sg * 12 + i * 3 + 0] = r0 * l[0] + r1 * l[3] + r2 * l[6];
+      F[sg * 12 + i * 3 + 1] = r0 * l[1] + r1 * l[4] + r2 * l[7];
+      F[sg * 12 + i * 3 + 2] = r0 * l[2] + r1 * l[5] + r2 * l[8];
+      F[sg * 12 + 9 + i] = r0 * l[9] + r1 * l[10] + r2 * l[11] + pi;
     }
-  return s;
+    __syncwarp();
+  }
 }
 
+#ifndef TB200_EVAL_MIN_BLOCKS
+#define TB200_EVAL_MIN_BLOCKS 3
+#endif
 template <int DD>
-__global__ void __launch_bounds__(kEvalThreads, 3)
+__global__ void __launch_bounds__(kEvalThreads, TB200_EVAL_MIN_BLOCKS)
 eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double* x_in /*EVAL_ONLY*/) {
   extern __shared__ double sm[];
   const int b = blockIdx.x;
@@ -98,7 +115,8 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
   const bool qp_failed = (mode == EVAL_STEP) && (p.qp_status[b] != 0);
   if (tid == 0 && !qp_failed) atomicAdd(p.active_count + 1, 1);  // trajectories actually convexified (bench: bytes moved)
   const int n_mask_words = p.n_coll_objs * p.coll_words;
-  const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_cand, n_mask_words, p.S, ex.n_joint_objs);
+  const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_objs, n_mask_words, p.S, ex.n_joint_objs,
+                                      ex.n_vel_objs, ex.cast);
   double* xs = sm + S.x;
   unsigned long long* mask = reinterpret_cast<unsigned long long*>(sm + S.mask);
   int* misc = reinterpret_cast<int*>(sm + S.misc);
@@ -198,7 +216,16 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
       const DevSphere sp = p.spheres[sl];
       const double* f = FR + (static_cast<size_t>(t) * Sg + sp.segment) * 12;
       double* sph = sm + S.sph + w * 3;
-      for (int i = 0; i < 3; ++i) sph[i] = f[i * 3] * sp.c[0] + f[i * 3 + 1] * sp.c[1] + f[i * 3 + 2] * sp.c[2] + f[9 + i];
+      for (int i = 0; i < 3; ++i) {
+        const double off = f[i * 3] * sp.c[0] + f[i * 3 + 1] * sp.c[1] + f[i * 3 + 2] * sp.c[2];
+        sph[i] = off + f[9 + i];
+        if (ex.cast) sm[S.spo + w * 3 + i] = off;
+      }
+    }
+    for (int w = tid; w < ex.n_vel_objs * 6; w += kEvalThreads) {  // link position at both ends of a CartVel pair
+      const int c = w / 6, k = (w % 6) / 3, i = w % 3;
+      const DevObj& o = ex.vel_objs[c];
+      sm[S.velp + w] = FR[(static_cast<size_t>(o.first + k) * Sg + o.link) * 12 + 9 + i];
     }
     for (int w = tid; w < ex.n_cart_objs * (1 + D) * 12; w += kEvalThreads) {
       const int c = w / ((1 + D) * 12), col = (w / 12) % (1 + D), k = w % 12;
@@ -251,6 +278,33 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
       }
     }
 
+    // ---- CartVel rows (kinematic_terms.cpp:376-425): err = [p1 - p0 - lim; p0 - p1 - lim], rows over (q_t, q_t+1)
+    // with the translational geometric Jacobians J_k(:, j) = a_j x (p_k - o_j) = A_j x p_k - B_j ------------------
+    for (int w = tid; w < ex.n_vel_objs * (2 * D + 6); w += kEvalThreads) {
+      const int c = w / (2 * D + 6), e = w % (2 * D + 6);
+      const DevObj& o = ex.vel_objs[c];
+      const double* p0 = sm + S.velp + c * 6;
+      const double* p1 = p0 + 3;
+      double* err_out = p.cart_err + slot * p.n_cart_rows + o.src_off;
+      double* jac_out = p.cart_jac + (slot * p.n_cart_rows + o.src_off) * p.cart_stride;
+      if (e < 6) {
+        const int i = e % 3;
+        err_out[e] = (e < 3) ? p1[i] - p0[i] - o.lvs : p0[i] - p1[i] - o.lvs;
+      } else {
+        const int col = e - 6, k = col / D, j = col % D;
+        const double* ab = sm + S.jax + ((o.first + k) * D + j) * 6;
+        const double* pk = k ? p1 : p0;
+        const bool moves = (o.pad1 >> j) & 1;
+        const double J[3] = {ab[1] * pk[2] - ab[2] * pk[1] - ab[3], ab[2] * pk[0] - ab[0] * pk[2] - ab[4],
+                             ab[0] * pk[1] - ab[1] * pk[0] - ab[5]};
+        for (int i = 0; i < 3; ++i) {
+          const double v = moves ? (k ? J[i] : -J[i]) : 0.0;
+          jac_out[i * p.cart_stride + col] = v;
+          jac_out[(3 + i) * p.cart_stride + col] = -v;
+        }
+      }
+    }
+
     // ---- dense candidate collision rows (collision_terms.cpp:203-250, 343-383, 540-556, 655-691) ----
     // candidate r = (collision object k, robot sphere s, obstacle o);  row = {grad[D], dist0, margin, coeff|0}
     // One warp per collision object (= waypoint), one lane per candidate: the lane builds its row in registers and
@@ -268,50 +322,173 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
       const DevObj& co = ex.coll_objs[k];
       const int t = co.first;
       const double margin = co.margin, reach = co.margin + co.buffer, coeff = co.coeff;
-      const double* AB = sm + S.jax + t * D * 6;
-      for (int c0 = 0; c0 < LO; c0 += 32) {
-        const int cnd = c0 + lane_c;
-        const bool in = cnd < LO;
-        const int sl = in ? static_cast<int>((static_cast<float>(cnd) + 0.5f) * inv_O) : 0, o = in ? cnd - sl * O : 0;
-        const double* c = sm + S.sph + (t * L + sl) * 3;
-        const double cx = c[0], cy = c[1], cz = c[2];
-        const double4 ob = *reinterpret_cast<const double4*>(obst + o * 4);
-        const double dx = ob.x - cx, dy = ob.y - cy, dz = ob.z - cz;
-        const double len = sqrt(dx * dx + dy * dy + dz * dz);
-        const double dist = len - sm[S.sphr + sl] - ob.w;
-        const double inv = 1.0 / len;
-        const double nx = dx * inv, ny = dy * inv, nz = dz * inv;  // from the robot sphere towards the obstacle
-        const double mx = cy * nz - cz * ny, my = cz * nx - cx * nz, mz = cx * ny - cy * nx;  // c x n
-        const unsigned jm = ex.sphere_jmask[sl];
-        const bool active = in && !(dist > reach);
-        double row[D + 3 + ((D + 3) & 1)];
+      double vsum = 0.0;  // exact value of the object: its terms added in candidate order (warp-uniform)
+      if (co.kind == OBJ_COLL) {
+        const double* AB = sm + S.jax + t * D * 6;
+        for (int c0 = 0; c0 < LO; c0 += 32) {
+          const int cnd = c0 + lane_c;
+          const bool in = cnd < LO;
+          const int sl = in ? static_cast<int>((static_cast<float>(cnd) + 0.5f) * inv_O) : 0, o = in ? cnd - sl * O : 0;
+          const double* c = sm + S.sph + (t * L + sl) * 3;
+          const double cx = c[0], cy = c[1], cz = c[2];
+          const double4 ob = *reinterpret_cast<const double4*>(obst + o * 4);
+          const double dx = ob.x - cx, dy = ob.y - cy, dz = ob.z - cz;
+          const double len = sqrt(dx * dx + dy * dy + dz * dz);
+          const double dist = len - sm[S.sphr + sl] - ob.w;
+          const double inv = 1.0 / len;
+          const double nx = dx * inv, ny = dy * inv, nz = dz * inv;  // from the robot sphere towards the obstacle
+          const double mx = cy * nz - cz * ny, my = cz * nx - cx * nz, mz = cx * ny - cy * nx;  // c x n
+          const unsigned jm = ex.sphere_jmask[sl];
+          const bool active = in && !(dist > reach);
+          double row[D + 3 + ((D + 3) & 1)];
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-          const double2 a01 = *reinterpret_cast<const double2*>(AB + j * 6);
-          const double2 a2b0 = *reinterpret_cast<const double2*>(AB + j * 6 + 2);
-          const double2 b12 = *reinterpret_cast<const double2*>(AB + j * 6 + 4);
-          // d(dist)/dq_j = -n . d(c)/dq_j = B_j . n - A_j . (c x n)
-          const double g = (a2b0.y * nx + b12.x * ny + b12.y * nz) - (a01.x * mx + a01.y * my + a2b0.x * mz);
-          row[j] = ((jm >> j) & 1u) ? g : 0.0;
-        }
-        row[D] = dist;
-        row[D + 1] = margin;
-        row[D + 2] = active ? coeff : 0.0;
-        if (in) {
-          sm[S.viol + co.src_off + cnd] = active ? fmax(margin - dist, 0.0) * coeff : 0.0;
-          double* dstp = rows_out + static_cast<size_t>(co.src_off + cnd) * (D + 3);
-          if constexpr (((D + 3) & 1) == 0) {  // rows are 16-byte aligned: D + 3 even, buffers 256-byte aligned
-            double2* d2 = reinterpret_cast<double2*>(dstp);
+          for (int j = 0; j < D; ++j) {
+            const double2 a01 = *reinterpret_cast<const double2*>(AB + j * 6);
+            const double2 a2b0 = *reinterpret_cast<const double2*>(AB + j * 6 + 2);
+            const double2 b12 = *reinterpret_cast<const double2*>(AB + j * 6 + 4);
+            // d(dist)/dq_j = -n . d(c)/dq_j = B_j . n - A_j . (c x n)
+            const double g = (a2b0.y * nx + b12.x * ny + b12.y * nz) - (a01.x * mx + a01.y * my + a2b0.x * mz);
+            row[j] = ((jm >> j) & 1u) ? g : 0.0;
+          }
+          row[D] = dist;
+          row[D + 1] = margin;
+          row[D + 2] = active ? coeff : 0.0;
+          if (in) {
+            double* dstp = rows_out + static_cast<size_t>(co.src_off + cnd) * (D + 3);
+            if constexpr (((D + 3) & 1) == 0) {  // rows are 16-byte aligned: D + 3 even, buffers 256-byte aligned
+              double2* d2 = reinterpret_cast<double2*>(dstp);
 #pragma unroll
-            for (int i = 0; i < (D + 3) / 2; ++i) d2[i] = make_double2(row[2 * i], row[2 * i + 1]);
-          } else {
+              for (int i = 0; i < (D + 3) / 2; ++i) d2[i] = make_double2(row[2 * i], row[2 * i + 1]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < D + 3; ++i) dstp[i] = row[i];
+              for (int i = 0; i < D + 3; ++i) dstp[i] = row[i];
+            }
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, active);
+          if (lane_c == 0 && bal) atomicOr(&mask[k * p.coll_words + (c0 >> 6)], static_cast<unsigned long long>(bal) << (c0 & 63));
+          const double mine = active ? fmax(margin - dist, 0.0) * coeff : 0.0;
+          unsigned nzb = __ballot_sync(0xffffffffu, mine != 0.0);
+          while (nzb) {  // warp-uniform: the non-zero terms in candidate order (zeros do not change the sum)
+            vsum += __shfl_sync(0xffffffffu, mine, __ffs(nzb) - 1);
+            nzb &= nzb - 1;
           }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, active);
-        if (lane_c == 0 && bal) atomicOr(&mask[k * p.coll_words + (c0 >> 6)], static_cast<unsigned long long>(bal) << (c0 & 63));
+      } else {
+        // ---- continuous ("cast") collision of the step pair (t, t+1): collision_terms.cpp:262-323, 468-538,
+        // 1071-1173 with the closed-form swept sphere (capsule) of SURVEY.md section 8d; the same rules as the oracle's
+        // CastCollisionEval.  candidate = (robot sphere, obstacle, sub-segment); row = {g0[D], g1[D], dist, margin,
+        // coeff|0}.  The gradients need one FK per ACTIVE contact (at its own contact-time state), done by the warp.
+        constexpr int MS = kMaxLvsSegments;
+        const bool sfix = co.pad1 & 1, efix = co.pad1 & 2;
+        const double* q0 = xs + t * D;
+        const double* q1 = q0 + D;
+        double d2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) d2 += (q1[j] - q0[j]) * (q1[j] - q0[j]);
+        const double qd = sqrt(d2);
+        int nsub = 1;
+        if (qd > co.lvs) {
+          const double nn = ceil(qd / co.lvs);
+          nsub = nn > MS ? MS : static_cast<int>(nn);
+        }
+        double* F = sm + S.wscr + (tid >> 5) * S.wscr_stride;  // frames of one state
+        double* sub = F + p.S * 12;                             // [MS-1][L][6]: centre, centre - link origin
+        double* qv = sub + (MS - 1) * L * 6;
+        for (int i = 1; i < nsub; ++i) {  // interior states of the LinSpaced sub-trajectory
+          if (lane_c < D) qv[lane_c] = q0[lane_c] + (q1[lane_c] - q0[lane_c]) * (static_cast<double>(i) / nsub);
+          __syncwarp();
+          warp_fk(p, qv, F, lane_c);
+          for (int w = lane_c; w < L; w += 32) {
+            const DevSphere sp = p.spheres[w];
+            const double* f = F + sp.segment * 12;
+            double* o6 = sub + ((i - 1) * L + w) * 6;
+            for (int a = 0; a < 3; ++a) {
+              const double off = f[a * 3] * sp.c[0] + f[a * 3 + 1] * sp.c[1] + f[a * 3 + 2] * sp.c[2];
+              o6[a] = off + f[9 + a];
+              o6[3 + a] = off;
+            }
+          }
+          __syncwarp();
+        }
+        const int NC = LO * MS, CS = 2 * D + 3;
+        for (int c0 = 0; c0 < NC; c0 += 32) {
+          const int cnd = c0 + lane_c;
+          const bool in = cnd < NC;
+          const int pr = in ? cnd / MS : 0, i = cnd % MS;
+          const int sl = static_cast<int>((static_cast<float>(pr) + 0.5f) * inv_O), o = pr - sl * O;
+          const bool exists = in && i < nsub;
+          const int ia = exists ? i : 0;
+          const double* ca = (ia == 0) ? sm + S.sph + (t * L + sl) * 3 : sub + ((ia - 1) * L + sl) * 6;
+          const double* cb = (ia + 1 >= nsub) ? sm + S.sph + ((t + 1) * L + sl) * 3 : sub + (ia * L + sl) * 6;
+          const double4 ob = *reinterpret_cast<const double4*>(obst + o * 4);
+          const double wx = cb[0] - ca[0], wy = cb[1] - ca[1], wz = cb[2] - ca[2];
+          const double ww = wx * wx + wy * wy + wz * wz;
+          const double wd = (ob.x - ca[0]) * wx + (ob.y - ca[1]) * wy + (ob.z - ca[2]) * wz;
+          double sc = (ww > 0.0) ? wd / ww : 0.0;
+          sc = sc < 0.0 ? 0.0 : (sc > 1.0 ? 1.0 : sc);
+          const double dx = ob.x - (ca[0] + sc * wx), dy = ob.y - (ca[1] + sc * wy), dz = ob.z - (ca[2] + sc * wz);
+          const double len = sqrt(dx * dx + dy * dy + dz * dz);
+          const double dist = len - sm[S.sphr + sl] - ob.w;
+          const double cc = (ia + sc) / nsub;
+          const double nx = dx / len, ny = dy / len, nz = dz / len;
+          const bool time0 = (ia == 0 && sc == 0.0), time1 = (ia == nsub - 1 && sc == 1.0);
+          const bool active = exists && !(dist > reach) && !(sfix && time0) && !(efix && time1);
+          if (in) {
+            double* dstp = rows_out + static_cast<size_t>(co.src_off + cnd) * CS;
+#pragma unroll
+            for (int j = 0; j < 2 * D; ++j) dstp[j] = 0.0;
+            dstp[2 * D] = exists ? dist : 0.0;
+            dstp[2 * D + 1] = exists ? margin : 0.0;
+            dstp[2 * D + 2] = active ? coeff : 0.0;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, active);
+          if (lane_c == 0 && bal) atomicOr(&mask[k * p.coll_words + (c0 >> 6)], static_cast<unsigned long long>(bal) << (c0 & 63));
+          const double mine = active ? fmax(margin - dist, 0.0) * coeff : 0.0;
+          unsigned nzb = __ballot_sync(0xffffffffu, mine != 0.0);
+          while (nzb) {
+            vsum += __shfl_sync(0xffffffffu, mine, __ffs(nzb) - 1);
+            nzb &= nzb - 1;
+          }
+          __syncwarp();  // the zero-filled rows are written before the gradients of the active ones
+          unsigned todo = bal;
+          while (todo) {  // warp-uniform loop over the active contacts of this chunk
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int sl_s = __shfl_sync(0xffffffffu, sl, src), i_s = __shfl_sync(0xffffffffu, ia, src);
+            const double cc_s = __shfl_sync(0xffffffffu, cc, src);
+            const double nxs = __shfl_sync(0xffffffffu, nx, src), nys = __shfl_sync(0xffffffffu, ny, src),
+                         nzs = __shfl_sync(0xffffffffu, nz, src);
+            if (lane_c < D) qv[lane_c] = (cc_s == 1.0) ? q1[lane_c] : q0[lane_c] + (q1[lane_c] - q0[lane_c]) * cc_s;
+            __syncwarp();
+            warp_fk(p, qv, F, lane_c);  // Jacobian at the contact-time state (GetGradient, :276-285)
+            if (lane_c < D) {
+              const int j = lane_c, sg = ex.joint_seg[j];
+              const DevSegment& g = p.segs[sg];
+              const double* f = F + sg * 12;
+              const double* pl = F + p.spheres[sl_s].segment * 12 + 9;
+              const double ax = f[0] * g.axis[0] + f[1] * g.axis[1] + f[2] * g.axis[2];
+              const double ay = f[3] * g.axis[0] + f[4] * g.axis[1] + f[5] * g.axis[2];
+              const double az = f[6] * g.axis[0] + f[7] * g.axis[1] + f[8] * g.axis[2];
+              const bool moves = (ex.sphere_jmask[sl_s] >> j) & 1u, rev = g.joint_type == 1;
+              double* rowp = rows_out + static_cast<size_t>(co.src_off + c0 + src) * CS;
+              for (int kk = 0; kk < 2; ++kk) {
+                if ((kk == 0 && sfix) || (kk == 1 && efix)) continue;  // a fixed side contributes nothing
+                // reference point: link origin at the contact-time state + R_link(sub-segment start | end) * c_local
+                const int st = i_s + kk;
+                const double* off = (st == 0) ? sm + S.spo + (t * L + sl_s) * 3
+                                    : (st >= nsub) ? sm + S.spo + ((t + 1) * L + sl_s) * 3 : sub + ((st - 1) * L + sl_s) * 6 + 3;
+                const double rx = pl[0] + off[0] - f[9], ry = pl[1] + off[1] - f[10], rz = pl[2] + off[2] - f[11];
+                const double jx = rev ? ay * rz - az * ry : ax, jy = rev ? az * rx - ax * rz : ay,
+                             jz = rev ? ax * ry - ay * rx : az;
+                const double gg = -(nxs * jx + nys * jy + nzs * jz) * (kk == 0 ? 1.0 - cc_s : cc_s);
+                rowp[kk * D + j] = moves ? gg : 0.0;
+              }
+            }
+            __syncwarp();
+          }
+        }
       }
+      if (lane_c == 0) sm[S.objv + k] = vsum;
     }
     __syncthreads();
     for (int i = tid; i < n_mask_words; i += kEvalThreads) p.coll_mask[slot * n_mask_words + i] = mask[i];
@@ -369,17 +546,13 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
           const double* e = p.cart_err + slot * p.n_cart_rows + o.src_off;
           for (int r = 0; r < o.n_rows; ++r) v += fabs(e[r]);
         }
-      } else {
-        for (int r0 = 0; r0 < o.n_rows; r0 += 32) {
-          const int r = r0 + lane;
-          const double mine = (r < o.n_rows) ? sm[S.viol + o.src_off + r] : 0.0;
-          unsigned nz = __ballot_sync(0xffffffffu, mine != 0.0);
-          while (nz) {  // warp-uniform: add the non-zero terms in candidate order (zeros do not change the sum)
-            const int src = __ffs(nz) - 1;
-            v += __shfl_sync(0xffffffffu, mine, src);
-            nz &= nz - 1;
-          }
+      } else if (o.kind == OBJ_CART_VEL) {
+        if (lane == 0) {
+          const double* e = p.cart_err + slot * p.n_cart_rows + o.src_off;
+          for (int r = 0; r < 6; ++r) v += is_cnt ? fmax(e[r], 0.0) : fabs(e[r]);  // INEQ violation | ABS cost
         }
+      } else {
+        if (lane == 0) v = sm[S.objv + o.target_slot];  // collision object: summed by the warp that built its rows
       }
       if (lane == 0) {
         if (is_cnt) out_viol[i - p.n_costs] = v;

@@ -7,7 +7,8 @@ namespace tb200 {
 struct EvalExtra;
 using QpKernelFn = void (*)(DevProblem, const double*, const double*, int*, int*, int);
 using EvalKernelFn = void (*)(DevProblem, EvalExtra, int, const double*);
-QpKernelFn qp_kernel_for(int D);      // nullptr: no instance for this number of joints
+// pair_rows: QP rows may span two consecutive waypoints (2*D coefficients per padded row instead of D)
+QpKernelFn qp_kernel_for(int D, bool pair_rows);  // nullptr: no instance for this number of joints
 EvalKernelFn eval_kernel_for(int D);
 int qp_debug_prof(unsigned long long* out, int reset);  // TB200_PROFILE builds only (else returns -1)
 }  // namespace tb200

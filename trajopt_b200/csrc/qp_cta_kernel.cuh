@@ -22,6 +22,7 @@
 // and factor) in HBM and resumes from it in the next launch.
 #pragma once
 #include "device_types.cuh"
+#include "joint_terms.cuh"
 
 namespace tb200 {
 
@@ -905,11 +906,12 @@ __device__ inline void qp_scale(QpCtx& q, const QpSettings& st, int n_aux_total)
 // The QP solve for the calling CTA's trajectory.  `fresh`: start a new solve (initial iterate from the warm
 // start or zero); otherwise resume from `rs`.  Returns status QPS_YIELD when the slice budget ran out.
 // Every scalar that steers control flow is derived from block-reduced values, so all threads take the same path.
-template <int NB>
+template <int NB, int PAIR>
 __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fresh, bool warm, double warm_rho,
                                        const double* ws_x, const double* ws_yb, QpResume& rs, int slice,
                                        bool have_factor) {
-  constexpr int CNc = (NB / 2 > 3) ? NB / 2 : 3;  // coefficients per (padded) row
+  // coefficients per (padded) row: D, or 2*D when rows may span two consecutive waypoints (CartVel, cast collision)
+  constexpr int CNc = PAIR ? ((NB > 3) ? NB : 3) : ((NB / 2 > 3) ? NB / 2 : 3);
   const int N = q.N, tid = q.tid;
   QpOut out{QPS_UNSOLVED, 0, 0, st.rho, 0, 0, 0, 0, 0, -1, 0, 0};
   double rho;
@@ -1625,7 +1627,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
 // ---------------------------------------------------------------------------------------------------
 // Kernel: QP assembly (optimizers.cpp:781-799 + osqp_interface.cpp:170-281 in fixed layout) + solve slice.
 // grid = B, block = 256 (one CTA per trajectory).  DD = degrees of freedom (block size NB = 2*DD).
-template <int DD>
+template <int DD, int PAIR>
 __global__ void __launch_bounds__(kQpThreads, 1) qp_kernel(DevProblem p, const double* x_override /*kernel-level API*/,
                                                            const double* trust_override, int* admm_iters_out,
                                                            int* polish_out, int slice) {
@@ -1774,7 +1776,38 @@ __global__ void __launch_bounds__(kQpThreads, 1) qp_kernel(DevProblem p, const d
         nr += o.n_rows;
         n_aux += 2 * o.n_rows;
         nnzA += nz + 2 * o.n_rows;
-      } else if (o.kind == OBJ_COLL) {
+      } else if (o.kind == OBJ_CART_VEL) {
+        // CartVel step pair: 6 rows over (q_t, q_t+1); INEQ constraint rows (hinge) or ABS cost rows
+        // (problem_description.cpp:1011-1057, modeling_utils.cpp:143-211, 238-269; coefficients |c| <= 1e-7 dropped)
+        if (tid == 0) sh_i[0] = 0;
+        __syncthreads();
+        int nz = 0;
+        const int per = is_cnt ? 1 : 2;
+        for (int k = tid; k < 6; k += kQpThreads) {
+          double* R = q.R(nr + k);
+          int* I = q.rints + static_cast<size_t>(nr + k) * RI_NINTS;
+          const double* J = cart_jac + static_cast<size_t>(o.src_off + k) * p.cart_stride;
+          double dot = 0.0;
+          for (int j = 0; j < q.CN; ++j) {
+            const double Jj = (j < 2 * D) ? J[j] : 0.0;
+            dot += Jj * q.x[o.first * D + min(j, 2 * D - 1)];
+            const double a = (fabs(Jj) > 1e-7) ? Jj : 0.0;
+            R[j] = a;
+            nz += (a != 0.0);
+          }
+          R[2 * q.CN + R_C] = cart_err[o.src_off + k] - dot;
+          R[2 * q.CN + R_W] = w_aux;
+          I[RI_BASE] = o.first * D; I[RI_CNT] = 2 * D; I[RI_STRIDE] = 1; I[RI_AUX] = is_cnt ? AUX_HINGE : AUX_ABS;
+          I[RI_OBJ] = oi; I[RI_PAD] = n_aux + per * k;
+        }
+        if (nz) atomicAdd(&sh_i[0], nz);
+        __syncthreads();
+        nz = sh_i[0];
+        __syncthreads();
+        nr += 6;
+        n_aux += per * 6;
+        nnzA += nz + per * 6;
+      } else if (o.kind == OBJ_COLL || o.kind == OBJ_COLL_CAST) {
         // active candidates of this timestep, in candidate order: thread 0 scans the mask and assigns slots
         const unsigned long long* mw = coll_mask + static_cast<size_t>(coll_obj_counter) * p.coll_words;
         ++coll_obj_counter;
@@ -1793,18 +1826,22 @@ __global__ void __launch_bounds__(kQpThreads, 1) qp_kernel(DevProblem p, const d
             int* I = q.rints + static_cast<size_t>(pos) * RI_NINTS;
             const double* cr = coll_rows + static_cast<size_t>(o.src_off + c) * p.coll_stride;
             // dist(q) ~ d0 + g.(q - q0);  constraint: coeff*(margin - dist) <= 0;  cost: hinge(margin - dist)*coeff
-            const double scale = is_cnt ? cr[D + 2] : 1.0;
+            // W coefficients: D (one waypoint) or 2*D (step pair of the continuous evaluator, where cleanupAff drops
+            // |g| <= 1e-7: collision_terms.cpp:481,502,536)
+            const int W = (o.kind == OBJ_COLL_CAST) ? 2 * D : D;
+            const double thr = (o.kind == OBJ_COLL_CAST) ? 1e-7 : -1.0;
+            const double scale = is_cnt ? cr[W + 2] : 1.0;
             double dot = 0.0;
             for (int j = 0; j < q.CN; ++j) {
-              const double g = (j < D) ? cr[j] : 0.0;
-              dot += g * q.x[o.first * D + min(j, D - 1)];
-              const double a = -g * scale;
-              R[j] = (j < D) ? a : 0.0;
-              nz += (j < D && a != 0.0);
+              const double g = (j < W) ? cr[j] : 0.0;
+              dot += g * q.x[o.first * D + min(j, W - 1)];
+              const double a = (fabs(g) > thr) ? -g * scale : 0.0;
+              R[j] = (j < W) ? a : 0.0;
+              nz += (j < W && a != 0.0);
             }
-            R[2 * q.CN + R_C] = (cr[D + 1] - cr[D] + dot) * scale;
-            R[2 * q.CN + R_W] = is_cnt ? w_aux : cr[D + 2];
-            I[RI_BASE] = o.first * D; I[RI_CNT] = D; I[RI_STRIDE] = 1; I[RI_AUX] = AUX_HINGE; I[RI_OBJ] = oi;
+            R[2 * q.CN + R_C] = (cr[W + 1] - cr[W] + dot) * scale;
+            R[2 * q.CN + R_W] = is_cnt ? w_aux : cr[W + 2];
+            I[RI_BASE] = o.first * D; I[RI_CNT] = W; I[RI_STRIDE] = 1; I[RI_AUX] = AUX_HINGE; I[RI_OBJ] = oi;
             I[RI_PAD] = n_aux + before;
           }
         }
@@ -1910,7 +1947,7 @@ __global__ void __launch_bounds__(kQpThreads, 1) qp_kernel(DevProblem p, const d
   __syncthreads();
 
   PROF_T0();
-  QpOut res = qp_solve_block<NB>(q, p.qp, !resume, warm, p.ws_rho[b], p.ws_x + static_cast<size_t>(b) * N,
+  QpOut res = qp_solve_block<NB, PAIR>(q, p.qp, !resume, warm, p.ws_rho[b], p.ws_x + static_cast<size_t>(b) * N,
                                  p.ws_yb + static_cast<size_t>(b) * N, rs, x_override ? (1 << 30) : slice, resume);
   __syncthreads();
   PROF_ADD(8);

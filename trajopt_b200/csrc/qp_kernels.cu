@@ -6,12 +6,14 @@
 #include "kernels.h"
 
 namespace tb200 {
-QpKernelFn qp_kernel_for(int D) {
+QpKernelFn qp_pair_kernel_for(int D);  // qp_kernels_pair.cu: rows over two consecutive waypoints
+QpKernelFn qp_kernel_for(int D, bool pair_rows) {
+  if (pair_rows) return qp_pair_kernel_for(D);
   switch (D) {
-    case 2: return qp_kernel<2>;
-    case 3: return qp_kernel<3>;
-    case 6: return qp_kernel<6>;
-    case 7: return qp_kernel<7>;
+    case 2: return qp_kernel<2, 0>;
+    case 3: return qp_kernel<3, 0>;
+    case 6: return qp_kernel<6, 0>;
+    case 7: return qp_kernel<7, 0>;
     default: return nullptr;
   }
 }

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <string>
 #include <vector>
@@ -73,12 +74,13 @@ struct tb200_problem {
   cudaStream_t stream = nullptr;
   tb200_timing timing{};
   // host copies of the flattened description
-  std::vector<DevObj> cost_objs, cnt_objs, cart_objs, coll_objs;
+  std::vector<DevObj> cost_objs, cnt_objs, cart_objs, coll_objs, vel_objs;
+  bool pair_rows = false;  // QP rows span two waypoints (CartVel, continuous collision): 2*D coefficients per row
   // device storage
   DevBuf<DevSegment> segs;
   DevBuf<DevSphere> spheres;
   DevBuf<double> lower, upper, Pband, qlin, init_traj, cart_targets, obstacles;
-  DevBuf<DevObj> d_cost_objs, d_cnt_objs, d_cart_objs, d_coll_objs;
+  DevBuf<DevObj> d_cost_objs, d_cnt_objs, d_cart_objs, d_coll_objs, d_vel_objs;
   DevBuf<DevJointTerm> joint_terms;
   DevBuf<DevCartTerm> cart_terms;
   DevBuf<int> fixed_vars;
@@ -94,7 +96,7 @@ struct tb200_problem {
     if (stream) cudaStreamDestroy(stream);
     segs.release(); spheres.release(); lower.release(); upper.release(); Pband.release(); qlin.release();
     init_traj.release(); cart_targets.release(); obstacles.release(); d_cost_objs.release(); d_cnt_objs.release();
-    d_cart_objs.release(); d_coll_objs.release(); joint_terms.release(); cart_terms.release(); fixed_vars.release();
+    d_cart_objs.release(); d_coll_objs.release(); d_vel_objs.release(); joint_terms.release(); cart_terms.release(); fixed_vars.release();
     x.release(); new_x.release(); trust.release(); merit_coeffs.release(); cost_vals.release(); cnt_viols.release();
     new_cost_vals.release(); new_cnt_viols.release(); model_cost_vals.release(); model_cnt_viols.release();
     cart_err.release(); cart_jac.release(); coll_rows.release(); rows.release(); ws_x.release(); ws_yb.release();
@@ -193,7 +195,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   std::vector<DevCartTerm> cts;
   std::vector<DevObj> costs, eqs, ineqs;
   int n_cart_rows = 0, n_coll_cand = 0, max_rows = 0;
-  std::vector<std::pair<int, int>> cart_ref, coll_ref;  // (list id: 0 cost 1 eq 2 ineq, index)
+  std::vector<std::pair<int, int>> cart_ref, coll_ref, vel_ref;  // (list id: 0 cost 1 eq 2 ineq, index)
+  bool has_vel = false, has_cast = false, has_discrete = false;
   for (int k = 0; k < d->n_terms; ++k) {
     const tb200_term& tm = d->terms[k];
     if (tm.role != TB200_ROLE_COST && tm.role != TB200_ROLE_CNT) return fail(TB200_ERR_INVALID, "term role must be COST or CNT");
@@ -249,27 +252,61 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
       if (is_cnt) { cart_ref.push_back({1, static_cast<int>(eqs.size())}); eqs.push_back(o); }
       else { cart_ref.push_back({0, static_cast<int>(costs.size())}); costs.push_back(o); }
     } else if (tm.kind == TB200_TERM_COLLISION) {
-      if (tm.evaluator_type != TB200_COLL_DISCRETE)
-        return fail(TB200_ERR_UNSUPPORTED, "only the DISCRETE collision evaluator is implemented on the device so far");
+      if (tm.evaluator_type == TB200_COLL_LVS_DISCRETE)
+        return fail(TB200_ERR_UNSUPPORTED, "the LVS_DISCRETE collision evaluator is not implemented");
+      if (tm.evaluator_type < TB200_COLL_DISCRETE || tm.evaluator_type > TB200_COLL_LVS_CONTINUOUS)
+        return fail(TB200_ERR_INVALID, "unknown collision evaluator type");
       if (dp.L == 0 || dp.O == 0) return fail(TB200_ERR_INVALID, "collision term needs robot spheres and obstacles");
-      for (int t = tm.first_step; t <= tm.last_step; ++t) {
-        bool fixed = false;
-        for (int f = 0; f < tm.n_fixed_steps; ++f) fixed |= tm.fixed_steps[f] == t;
-        if (fixed) continue;
-        if (t < 0 || t >= T) return fail(TB200_ERR_INVALID, "collision step outside the trajectory");
+      const bool cast = tm.evaluator_type != TB200_COLL_DISCRETE;
+      if ((cast && has_discrete) || (!cast && has_cast))
+        return fail(TB200_ERR_UNSUPPORTED, "discrete and continuous collision terms in one problem are not supported");
+      (cast ? has_cast : has_discrete) = true;
+      // discrete: one object per non-fixed step (problem_description.cpp:1762-1775, 1824-1833); continuous: one per
+      // step pair [first, last) with the expression type taken from the fixed steps (:1714-1760, 1776-1819)
+      for (int t = tm.first_step; cast ? t < tm.last_step : t <= tm.last_step; ++t) {
+        bool fixed = false, next_fixed = false;
+        for (int f = 0; f < tm.n_fixed_steps; ++f) {
+          fixed |= tm.fixed_steps[f] == t;
+          next_fixed |= tm.fixed_steps[f] == t + 1;
+        }
+        if (!cast && fixed) continue;
+        if (t < 0 || t + (cast ? 1 : 0) >= T) return fail(TB200_ERR_INVALID, "collision step outside the trajectory");
         DevObj c = o;
-        c.kind = OBJ_COLL;
+        c.kind = cast ? OBJ_COLL_CAST : OBJ_COLL;
         c.first = t;
         c.src_off = n_coll_cand;
-        c.n_rows = dp.L * dp.O;
+        c.n_rows = dp.L * dp.O * (cast ? kMaxLvsSegments : 1);
         c.coeff = tm.coeff; c.margin = tm.margin; c.buffer = tm.margin_buffer;
+        // (two adjacent fixed steps take the START_FIXED_END_FREE branch: the reference's throw is unreachable)
+        c.pad1 = cast ? ((fixed ? 1 : 0) | ((!fixed && next_fixed) ? 2 : 0)) : 0;
+        c.lvs = (tm.evaluator_type == TB200_COLL_CONTINUOUS) ? std::numeric_limits<double>::max() : tm.longest_valid_segment_length;
         n_coll_cand += c.n_rows;
         max_rows += c.n_rows;
         if (is_cnt) { coll_ref.push_back({2, static_cast<int>(ineqs.size())}); ineqs.push_back(c); }
         else { coll_ref.push_back({0, static_cast<int>(costs.size())}); costs.push_back(c); }
       }
     } else if (tm.kind == TB200_TERM_CART_VEL) {
-      return fail(TB200_ERR_UNSUPPORTED, "cart_vel is not implemented on the device yet");
+      // CartVelTermInfo::hatch (problem_description.cpp:1011-1057): one object per step pair (t, t+1)
+      if (tm.link < 0 || tm.link >= dp.S) return fail(TB200_ERR_INVALID, "cart_vel link out of range");
+      unsigned lm = 0;
+      for (int a = tm.link; a >= 0; a = segs[a].parent)
+        if (segs[a].q_index >= 0) lm |= 1u << segs[a].q_index;
+      for (int t = tm.first_step; t <= tm.last_step; ++t) {
+        if (t < 0 || t + 1 >= T) return fail(TB200_ERR_INVALID, "cart_vel: step pair beyond the trajectory");
+        DevObj c = o;
+        c.kind = OBJ_CART_VEL;
+        c.first = t;
+        c.link = tm.link;
+        c.src_off = n_cart_rows;
+        c.n_rows = 6;
+        c.pad1 = static_cast<int>(lm);
+        c.lvs = tm.max_displacement;
+        n_cart_rows += 6;
+        max_rows += 6;
+        has_vel = true;
+        if (is_cnt) { vel_ref.push_back({2, static_cast<int>(ineqs.size())}); ineqs.push_back(c); }
+        else { vel_ref.push_back({0, static_cast<int>(costs.size())}); costs.push_back(c); }
+      }
     } else {
       return fail(TB200_ERR_INVALID, "unknown term kind");
     }
@@ -283,6 +320,11 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
     o.pad0 = r.second;
     P->cart_objs.push_back(o);
   }
+  for (auto& r : vel_ref) {
+    DevObj o = (r.first == 0) ? costs[r.second] : ineqs[r.second];
+    o.pad0 = (r.first == 0) ? r.second : n_eq + r.second;
+    P->vel_objs.push_back(o);
+  }
   // collision objects in the order the QP kernel meets them: cost objects first, then constraint objects
   for (int pass = 0; pass < 2; ++pass)
     for (auto& r : coll_ref) {
@@ -293,11 +335,14 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
     }
   // candidates are laid out in P->coll_objs order (src_off) : re-number so that layout == kernel order
   {
-    int off = 0;
+    int off = 0, k = 0;
     for (auto& o : P->coll_objs) {
       o.src_off = off;
+      o.target_slot = k;  // position in the kernel order: where the evaluation kernel leaves the object's value
       off += o.n_rows;
-      (o.is_cnt ? P->cnt_objs[o.pad0] : P->cost_objs[o.pad0]).src_off = o.src_off;
+      DevObj& m = o.is_cnt ? P->cnt_objs[o.pad0] : P->cost_objs[o.pad0];
+      m.src_off = o.src_off;
+      m.target_slot = k++;
     }
   }
   // fixed rows
@@ -342,16 +387,21 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.n_costs = static_cast<int>(P->cost_objs.size());
   dp.n_cnts = static_cast<int>(P->cnt_objs.size());
   dp.n_cart_rows = n_cart_rows;
-  dp.cart_stride = D;
+  const int CN = (has_vel || has_cast) ? std::max(2 * D, 3) : std::max(D, 3);  // coefficients per (padded) QP row
+  dp.cart_stride = has_vel ? 2 * D : D;
   dp.n_coll_cand = n_coll_cand;
-  dp.coll_stride = D + 3;
+  dp.coll_stride = has_cast ? 2 * D + 3 : D + 3;
   dp.n_fixed = static_cast<int>(fixed.size());
   dp.max_rows = max_rows;
-  dp.row_stride = qp_row_stride(std::max(D, 3));
-  dp.coll_words = std::max(1, (dp.L * dp.O + 63) / 64);
+  dp.row_stride = qp_row_stride(CN);
+  dp.coll_words = std::max(1, (dp.L * dp.O * (has_cast ? kMaxLvsSegments : 1) + 63) / 64);
   dp.n_coll_objs = static_cast<int>(P->coll_objs.size());
   P->ex.n_cart_objs = static_cast<int>(P->cart_objs.size());
   P->ex.n_coll_objs = dp.n_coll_objs;
+  P->ex.n_vel_objs = static_cast<int>(P->vel_objs.size());
+  P->ex.cast = has_cast ? 1 : 0;
+  for (int sg = 0; sg < dp.S; ++sg)
+    if (segs[sg].q_index >= 0) P->ex.joint_seg[segs[sg].q_index] = sg;
   P->ex.n_joint_objs = 0;
   {
     int idx = 0;
@@ -370,18 +420,19 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   P->layout.n_costs = dp.n_costs;
   P->layout.n_cnts = dp.n_cnts;
   P->layout.n_cart_rows = n_cart_rows;
-  P->layout.cart_jac_stride = D;
+  P->layout.cart_jac_stride = dp.cart_stride;
   P->layout.n_coll_cand = n_coll_cand;
-  P->layout.coll_row_stride = D + 3;
+  P->layout.coll_row_stride = dp.coll_stride;
   P->layout.n_vars = N;
 
   // ---- kernel resources --------------------------------------------------------------------------------
-  const EvalSmem es = eval_smem_layout(T, D, dp.L, P->ex.n_cart_objs, n_coll_cand, dp.n_coll_objs * dp.coll_words, dp.S,
-                                       P->ex.n_joint_objs);
+  const EvalSmem es = eval_smem_layout(T, D, dp.L, P->ex.n_cart_objs, dp.n_coll_objs, dp.n_coll_objs * dp.coll_words, dp.S,
+                                       P->ex.n_joint_objs, P->ex.n_vel_objs, P->ex.cast);
+  P->pair_rows = (CN > std::max(D, 3));
   P->eval_smem = static_cast<size_t>(es.total) * sizeof(double);
-  const QpSmem qs = qp_smem_layout(N, 2 * D, dp.row_stride, std::max(D, 3), max_rows);
+  const QpSmem qs = qp_smem_layout(N, 2 * D, dp.row_stride, CN, max_rows);
   const int Np = qp_block_count(N, 2 * D) * 2 * D;
-  dp.list_stride = static_cast<size_t>(Np + 1) + static_cast<size_t>(max_rows) * std::max(D, 3) + dp.n_costs + dp.n_cnts + 2;
+  dp.list_stride = static_cast<size_t>(Np + 1) + static_cast<size_t>(max_rows) * CN + dp.n_costs + dp.n_cnts + 2;
   P->qp_smem = static_cast<size_t>(qs.total) * sizeof(double);
   if (P->eval_smem > 227 * 1024 || P->qp_smem > 227 * 1024)
     return fail(TB200_ERR_UNSUPPORTED, "problem does not fit the 227 KB shared memory of one CTA");
@@ -389,9 +440,9 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
     return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for one CTA per block-cyclic-reduction level");
   if (!solve_roles_fit(qp_block_count(N, 2 * D), 2 * D))
     return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for the register-resident block-cyclic-reduction solve");
-  if (!qp_kernel_for(D) || !eval_kernel_for(D)) return fail(TB200_ERR_UNSUPPORTED, "no kernel instance for this number of joints");
+  if (!qp_kernel_for(D, P->pair_rows) || !eval_kernel_for(D)) return fail(TB200_ERR_UNSUPPORTED, "no kernel instance for this number of joints");
   CK(cudaFuncSetAttribute(eval_kernel_for(D), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->eval_smem)));
-  CK(cudaFuncSetAttribute(qp_kernel_for(D), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->qp_smem)));
+  CK(cudaFuncSetAttribute(qp_kernel_for(D, P->pair_rows), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->qp_smem)));
   CK(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
   if (const char* e = std::getenv("TB200_SLICE")) P->slice = std::max(1, std::atoi(e));
 
@@ -411,6 +462,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   UPLOAD(d_cnt_objs, P->cnt_objs);
   UPLOAD(d_cart_objs, P->cart_objs);
   UPLOAD(d_coll_objs, P->coll_objs);
+  UPLOAD(d_vel_objs, P->vel_objs);
   UPLOAD(joint_terms, jts);
   UPLOAD(cart_terms, cts);
   UPLOAD(fixed_vars, fixed);
@@ -422,8 +474,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   ALLOC(cost_vals, Bs * std::max(1, dp.n_costs)); ALLOC(cnt_viols, Bs * std::max(1, dp.n_cnts));
   ALLOC(new_cost_vals, Bs * std::max(1, dp.n_costs)); ALLOC(new_cnt_viols, Bs * std::max(1, dp.n_cnts));
   ALLOC(model_cost_vals, Bs * std::max(1, dp.n_costs)); ALLOC(model_cnt_viols, Bs * std::max(1, dp.n_cnts));
-  ALLOC(cart_err, 2 * Bs * std::max(1, n_cart_rows)); ALLOC(cart_jac, 2 * Bs * std::max(1, n_cart_rows) * D);
-  ALLOC(coll_rows, 2 * Bs * std::max(1, n_coll_cand) * (D + 3));
+  ALLOC(cart_err, 2 * Bs * std::max(1, n_cart_rows)); ALLOC(cart_jac, 2 * Bs * std::max(1, n_cart_rows) * dp.cart_stride);
+  ALLOC(coll_rows, 2 * Bs * std::max(1, n_coll_cand) * dp.coll_stride);
   ALLOC(coll_mask, 2 * Bs * std::max(1, dp.n_coll_objs * dp.coll_words));
   ALLOC(rows, Bs * max_rows * dp.row_stride); ALLOC(row_ints, Bs * max_rows * RI_NINTS);
   ALLOC(lists, Bs * dp.list_stride);
@@ -451,6 +503,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.park = P->park.p; dp.park_factor = P->park_factor.p; dp.rs_int = P->rs_int.p; dp.rs_dbl = P->rs_dbl.p; dp.rs_guess = P->rs_guess.p; dp.qp_done = P->qp_done.p;
   P->ex.cart_objs = P->d_cart_objs.p;
   P->ex.coll_objs = P->d_coll_objs.p;
+  P->ex.vel_objs = P->d_vel_objs.p;
   // settings
   const tb200_qp_settings& q = d->qp;
   dp.qp = QpSettings{q.rho, q.sigma, q.alpha, q.eps_abs, q.eps_rel, q.eps_prim_inf, q.eps_dual_inf, q.delta,
@@ -552,7 +605,7 @@ int tb200_solve_batch_resident(tb200_problem* P) {
   auto launch_qp = [&]() {
     const size_t i0 = ne;
     cudaEventRecord(getEvent(P, ne++), st);
-    qp_kernel_for(P->D)<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, nullptr, nullptr, nullptr, nullptr, P->slice);
+    qp_kernel_for(P->D, P->pair_rows)<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, nullptr, nullptr, nullptr, nullptr, P->slice);
     cudaEventRecord(getEvent(P, ne++), st);
     spans.push_back({i0, 1});
   };
@@ -682,7 +735,7 @@ int tb200_qp_solve_batch(tb200_problem* P, const double* x, const double* trust,
   if (dp.n_cnts > 0) CK(cudaMemcpyAsync(P->merit_coeffs.p, merit_coeffs, B * dp.n_cnts * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(P->ws_meta.p, 0, B * 8 * sizeof(int), st));
   eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
-  qp_kernel_for(P->D)<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, P->x_tmp.p, P->trust_tmp.p, P->tmp_iters.p, P->tmp_polish.p, 1 << 30);
+  qp_kernel_for(P->D, P->pair_rows)<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, P->x_tmp.p, P->trust_tmp.p, P->tmp_iters.p, P->tmp_polish.p, 1 << 30);
   CK(cudaGetLastError());
   auto pull = [&](void* dst, const void* src, size_t n) {
     if (!dst || n == 0) return cudaSuccess;
