@@ -90,9 +90,7 @@ def test_sqp_solve_matches_oracle(oracle, name):
     d = _cfgs()[name]
     got, hit = _solve_with_trace(d)
     ref = oracle.solve_batch(d)
-    ok = ~hit
-    if not name.startswith("cfg3"):
-        assert ok.all(), "a QP of configs[1]/[2] ran into the ADMM iteration limit"
+    ok = ~hit if name.startswith("cfg3") else np.ones(d.B, bool)  # configs[1]/[2]: every trajectory is compared
     assert ok.mean() >= 0.7, hit
     assert (got["status"][ok] == ref["status"][ok]).all(), (got["status"], ref["status"], hit)
     assert (got["n_qp_solves"][ok] == ref["n_qp_solves"][ok]).all(), (got["n_qp_solves"], ref["n_qp_solves"], hit)
@@ -100,7 +98,7 @@ def test_sqp_solve_matches_oracle(oracle, name):
     np.testing.assert_allclose(got["x"][ok], ref["x"][ok], atol=1e-5)
     np.testing.assert_allclose(got["cnt_viols"][ok], ref["cnt_viols"][ok], atol=1e-6)
     # the others still end in a terminal state of the same SQP (not compared step by step)
-    assert (got["status"][hit] != capi.OPT_INVALID).all()
+    assert (got["status"] != capi.OPT_INVALID).all()
 
 
 def test_joint_terms_cfg0(oracle):
