@@ -145,6 +145,8 @@ struct DevProblem {
   int* trace_len;              // [B]
   int trace_cap, pad3;
   double* dbg;                 // [B][16] solver diagnostics of the last QP (residuals, polish residuals, rho, c)
+  int* sched_state;            // [B] persistent SQP kernel: 0 ready, 1 running, 2 finished
+  unsigned long long* sched_timers;  // [4] ns in QP steps, ns in evaluation steps, evaluation steps, claims
   QpSettings qp;
   SqpParams sqp;
 };

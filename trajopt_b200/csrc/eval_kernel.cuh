@@ -99,14 +99,10 @@ __device__ inline void warp_fk(const DevProblem& p, const double* q, double* F, 
   }
 }
 
-#ifndef TB200_EVAL_MIN_BLOCKS
-#define TB200_EVAL_MIN_BLOCKS 3
-#endif
 template <int DD>
-__global__ void __launch_bounds__(kEvalThreads, TB200_EVAL_MIN_BLOCKS)
-eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double* x_in /*EVAL_ONLY*/) {
+__device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& ex, const int mode, const int b,
+                                          const double* x_in /*EVAL_ONLY*/) {
   extern __shared__ double sm[];
-  const int b = blockIdx.x;
   const int tid = threadIdx.x;
   constexpr int D = DD;
   const int T = p.T, N = p.N, L = p.L, O = p.O;
@@ -695,6 +691,17 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
     }
     if (tid == 0) p.cur_buf[b] = dst;
   }
+}
+
+#ifndef TB200_EVAL_MIN_BLOCKS
+#define TB200_EVAL_MIN_BLOCKS 3
+#endif
+// Stand-alone launch, one CTA per trajectory: the initial evaluation of a solve (EVAL_INIT) and the kernel-level
+// convexify entry point (EVAL_ONLY).  Inside a solve the same code runs as a step of solve_kernel.cuh.
+template <int DD>
+__global__ void __launch_bounds__(kEvalThreads, TB200_EVAL_MIN_BLOCKS)
+eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double* x_in /*EVAL_ONLY*/) {
+  eval_step<DD>(p, ex, mode, blockIdx.x, x_in);
 }
 
 }  // namespace tb200

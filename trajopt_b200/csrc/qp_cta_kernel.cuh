@@ -1628,12 +1628,10 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
 // Kernel: QP assembly (optimizers.cpp:781-799 + osqp_interface.cpp:170-281 in fixed layout) + solve slice.
 // grid = B, block = 256 (one CTA per trajectory).  DD = degrees of freedom (block size NB = 2*DD).
 template <int DD, int PAIR>
-__global__ void __launch_bounds__(kQpThreads, 1) qp_kernel(DevProblem p, const double* x_override /*kernel-level API*/,
-                                                           const double* trust_override, int* admm_iters_out,
-                                                           int* polish_out, int slice) {
+__device__ __forceinline__ void qp_step(const DevProblem& p, const int b, const double* x_override /*kernel-level API*/,
+                                        const double* trust_override, int* admm_iters_out, int* polish_out, int slice) {
   constexpr int NB = 2 * DD;
   extern __shared__ double sm[];
-  const int b = blockIdx.x;
   const int tid = threadIdx.x;
   if (!x_override && (p.status[b] != 5 || p.qp_done[b] != 0)) return;  // finished, or waiting for its evaluation
   const int N = p.N, T = p.T, D = p.D;

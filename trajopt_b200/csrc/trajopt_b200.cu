@@ -19,7 +19,7 @@
 
 #include "../../include/trajopt_b200.h"
 #include "eval_kernel.cuh"
-#include "qp_cta_kernel.cuh"
+#include "solve_kernel.cuh"
 #include "kernels.h"
 
 using namespace tb200;
@@ -69,8 +69,9 @@ struct tb200_problem {
   EvalExtra ex{};
   tb200_layout layout{};
   int B = 0, T = 0, D = 0, N = 0;
-  size_t eval_smem = 0, qp_smem = 0;
-  int slice = 500;  // ADMM iterations per QP per launch (TB200_SLICE overrides)
+  size_t eval_smem = 0, qp_smem = 0, solve_smem = 0;
+  int n_sm = 148;
+  int quantum = 3;  // SQP steps a CTA runs of a trajectory before it looks for a more urgent one (TB200_QUANTUM overrides)
   cudaStream_t stream = nullptr;
   tb200_timing timing{};
   // host copies of the flattened description
@@ -86,7 +87,8 @@ struct tb200_problem {
   DevBuf<int> fixed_vars;
   DevBuf<double> x, new_x, trust, merit_coeffs, cost_vals, cnt_viols, new_cost_vals, new_cnt_viols, model_cost_vals,
       model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace, park, park_factor, rs_dbl;
-  DevBuf<unsigned long long> rs_guess;
+  DevBuf<unsigned long long> rs_guess, sched_timers;
+  DevBuf<int> sched_state;
   DevBuf<unsigned long long> coll_mask;
   DevBuf<int> status, sqp_iter, merit_round, qp_failures, qp_status, cur_buf, n_qp_solves, n_func_evals, n_admm_iters,
       active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish, trace_len, rs_int, qp_done;
@@ -100,7 +102,7 @@ struct tb200_problem {
     x.release(); new_x.release(); trust.release(); merit_coeffs.release(); cost_vals.release(); cnt_viols.release();
     new_cost_vals.release(); new_cnt_viols.release(); model_cost_vals.release(); model_cnt_viols.release();
     cart_err.release(); cart_jac.release(); coll_rows.release(); rows.release(); ws_x.release(); ws_yb.release();
-    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); park.release(); park_factor.release(); rs_dbl.release(); rs_guess.release(); rs_int.release(); qp_done.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
+    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); park.release(); park_factor.release(); rs_dbl.release(); rs_guess.release(); rs_int.release(); qp_done.release(); sched_state.release(); sched_timers.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
     sqp_iter.release(); merit_round.release(); qp_failures.release(); qp_status.release(); cur_buf.release();
     n_qp_solves.release(); n_func_evals.release(); n_admm_iters.release(); active_count.release(); row_ints.release();
     lists.release(); ws_meta.release(); tmp_iters.release(); tmp_polish.release();
@@ -440,11 +442,19 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
     return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for one CTA per block-cyclic-reduction level");
   if (!solve_roles_fit(qp_block_count(N, 2 * D), 2 * D))
     return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for the register-resident block-cyclic-reduction solve");
-  if (!qp_kernel_for(D, P->pair_rows) || !eval_kernel_for(D)) return fail(TB200_ERR_UNSUPPORTED, "no kernel instance for this number of joints");
+  if (!solve_kernel_for(D, P->pair_rows) || !eval_kernel_for(D))
+    return fail(TB200_ERR_UNSUPPORTED, P->pair_rows ? "no kernel instance with two-waypoint rows (CartVel, continuous collision) for this number of joints"
+                                                    : "no kernel instance for this number of joints");
   CK(cudaFuncSetAttribute(eval_kernel_for(D), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->eval_smem)));
-  CK(cudaFuncSetAttribute(qp_kernel_for(D, P->pair_rows), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->qp_smem)));
+  P->solve_smem = std::max(P->qp_smem, P->eval_smem);  // the QP step and the evaluation step share one buffer
+  CK(cudaFuncSetAttribute(solve_kernel_for(D, P->pair_rows), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->solve_smem)));
+  {
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    P->n_sm = std::max(1, sms);
+  }
+  if (const char* e = std::getenv("TB200_QUANTUM")) P->quantum = std::max(1, std::atoi(e));
   CK(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
-  if (const char* e = std::getenv("TB200_SLICE")) P->slice = std::max(1, std::atoi(e));
 
   // ---- device buffers ------------------------------------------------------------------------------------
 #define ALLOC(buf, count) CK(P->buf.alloc(count))
@@ -483,6 +493,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   ALLOC(status, Bs); ALLOC(sqp_iter, Bs); ALLOC(merit_round, Bs); ALLOC(qp_failures, Bs); ALLOC(qp_status, Bs);
   ALLOC(cur_buf, Bs); ALLOC(n_qp_solves, Bs); ALLOC(n_func_evals, Bs); ALLOC(n_admm_iters, Bs); ALLOC(active_count, 2);
   ALLOC(dbg, Bs * 16);
+  ALLOC(sched_state, Bs); ALLOC(sched_timers, 8 + 2 * Bs);
   ALLOC(trace_len, Bs);
   ALLOC(x_tmp, Bs * N); ALLOC(trust_tmp, Bs); ALLOC(tmp_iters, Bs); ALLOC(tmp_polish, Bs);
 #undef ALLOC
@@ -499,7 +510,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.n_func_evals = P->n_func_evals.p; dp.n_admm_iters = P->n_admm_iters.p; dp.active_count = P->active_count.p;
   dp.cart_err = P->cart_err.p; dp.cart_jac = P->cart_jac.p; dp.coll_rows = P->coll_rows.p; dp.coll_mask = P->coll_mask.p;
   dp.rows = P->rows.p; dp.row_ints = P->row_ints.p; dp.lists = P->lists.p; dp.ws_x = P->ws_x.p; dp.ws_yb = P->ws_yb.p;
-  dp.scratch = P->scratch.p; dp.ws_meta = P->ws_meta.p; dp.ws_rho = P->ws_rho.p; dp.dbg = P->dbg.p; dp.trace_len = P->trace_len.p; dp.trace = nullptr; dp.trace_cap = 0;
+  dp.scratch = P->scratch.p; dp.ws_meta = P->ws_meta.p; dp.ws_rho = P->ws_rho.p; dp.dbg = P->dbg.p; dp.sched_state = P->sched_state.p; dp.sched_timers = P->sched_timers.p; dp.trace_len = P->trace_len.p; dp.trace = nullptr; dp.trace_cap = 0;
   dp.park = P->park.p; dp.park_factor = P->park_factor.p; dp.rs_int = P->rs_int.p; dp.rs_dbl = P->rs_dbl.p; dp.rs_guess = P->rs_guess.p; dp.qp_done = P->qp_done.p;
   P->ex.cart_objs = P->d_cart_objs.p;
   P->ex.coll_objs = P->d_coll_objs.p;
@@ -552,7 +563,11 @@ int tb200_problem_set_inputs(tb200_problem* P, const double* init_traj, const do
 namespace {
 __global__ void reset_state_kernel(DevProblem p) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) { p.active_count[0] = p.B; p.active_count[1] = 0; }
+  if (b == 0) {
+    p.active_count[0] = p.B;
+    p.active_count[1] = 0;
+    for (int k = 0; k < 8; ++k) p.sched_timers[k] = (k == 4) ? ~0ull : 0ull;
+  }
   if (b >= p.B) return;
   p.status[b] = 5;
   p.sqp_iter[b] = 1;
@@ -567,6 +582,9 @@ __global__ void reset_state_kernel(DevProblem p) {
   for (int c = 0; c < p.n_cnts; ++c) p.merit_coeffs[static_cast<size_t>(b) * p.n_cnts + c] = p.sqp.initial_merit_error_coeff;
   for (int k = 0; k < 8; ++k) p.ws_meta[b * 8 + k] = 0;
   p.qp_done[b] = 0;
+  p.sched_state[b] = 0;
+  p.sched_timers[8 + b] = 0ull;
+  p.sched_timers[8 + p.B + b] = 0ull;
   p.ws_rho[b] = p.qp.rho;
   p.trace_len[b] = 0;
 }
@@ -590,52 +608,39 @@ int tb200_solve_batch_resident(tb200_problem* P) {
   const int64_t h2d = tm.h2d_bytes;
   tm = tb200_timing{};
   tm.h2d_bytes = h2d;
-  size_t ne = 0;
-  cudaEvent_t e_begin = getEvent(P, ne++), e_end = getEvent(P, ne++);
-  std::vector<std::pair<size_t, int>> spans;  // (event index, kind 0 eval / 1 qp)
+  cudaEvent_t e_begin = getEvent(P, 0), e_end = getEvent(P, 1), e_init0 = getEvent(P, 2), e_init1 = getEvent(P, 3);
   CK(cudaEventRecord(e_begin, st));
   reset_state_kernel<<<(dp.B + 127) / 128, 128, 0, st>>>(dp);
-  auto launch_eval = [&](int mode) {
-    const size_t i0 = ne;
-    cudaEventRecord(getEvent(P, ne++), st);
-    eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, mode, nullptr);
-    cudaEventRecord(getEvent(P, ne++), st);
-    spans.push_back({i0, 0});
-  };
-  auto launch_qp = [&]() {
-    const size_t i0 = ne;
-    cudaEventRecord(getEvent(P, ne++), st);
-    qp_kernel_for(P->D, P->pair_rows)<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, nullptr, nullptr, nullptr, nullptr, P->slice);
-    cudaEventRecord(getEvent(P, ne++), st);
-    spans.push_back({i0, 1});
-  };
-  launch_eval(EVAL_INIT);
-  // every trajectory needs at most this many QP solves (penalty rounds x SQP iterations x trust retries)
-  const long qp_cap = static_cast<long>(std::ceil(dp.sqp.max_merit_coeff_increases)) * dp.sqp.max_iter * 12 + 64;
-  const long cap = qp_cap * (dp.qp.max_iter / P->slice + 2);
-  int active = dp.B;
-  long steps = 0;
-  while (active > 0 && steps < cap) {
-    launch_qp();
-    launch_eval(EVAL_STEP);
-    ++steps;
-    if (steps % 8 == 0) {
-      CK(cudaMemcpyAsync(&active, dp.active_count, sizeof(int), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-    }
-  }
+  // the initial evaluation + convexification of every trajectory: one CTA per trajectory (optimizers.cpp:761-783)
+  CK(cudaEventRecord(e_init0, st));
+  eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_INIT, nullptr);
+  CK(cudaEventRecord(e_init1, st));
+  // everything else: one persistent CTA per SM (solve_kernel.cuh); no host round trips until every trajectory is done
+  SolveCtl ctl{};
+  ctl.mode = SOLVE_FULL;
+  ctl.quantum = P->quantum;
+  ctl.sched_state = dp.sched_state;
+  ctl.timers = dp.sched_timers;
+  solve_kernel_for(P->D, P->pair_rows)<<<std::min(dp.B, P->n_sm), kQpThreads, P->solve_smem, st>>>(dp, P->ex, ctl);
   CK(cudaEventRecord(e_end, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
-  float ms = 0;
+  float ms = 0, ms_init = 0;
   CK(cudaEventElapsedTime(&ms, e_begin, e_end));
+  CK(cudaEventElapsedTime(&ms_init, e_init0, e_init1));
   tm.total_ms = ms;
-  tm.outer_steps = static_cast<int32_t>(steps);
-  for (auto& sp : spans) {
-    CK(cudaEventElapsedTime(&ms, P->events[sp.first], P->events[sp.first + 1]));
-    if (sp.second == 0) { tm.convexify_ms += ms; tm.convexify_launches++; }
-    else { tm.qp_ms += ms; tm.qp_launches++; }
-  }
+  unsigned long long tmr[4] = {0, 0, 0, 0};
+  CK(cudaMemcpy(tmr, dp.sched_timers, sizeof(tmr), cudaMemcpyDeviceToHost));
+  // share of the persistent launch spent in evaluation steps vs QP steps (SM-time, %globaltimer around each step)
+  const double in_steps = static_cast<double>(tmr[0]) + static_cast<double>(tmr[1]);
+  const double ev_share = in_steps > 0 ? static_cast<double>(tmr[1]) / in_steps : 0.0;
+  tm.convexify_ms = ms_init + (ms - ms_init) * ev_share;
+  tm.qp_ms = (ms - ms_init) * (1.0 - ev_share);
+  tm.convexify_launches = 1 + static_cast<int32_t>(tmr[2]);  // INIT launch + evaluation steps inside the solve
+  tm.qp_launches = static_cast<int32_t>(tmr[2]);             // QP steps (one per evaluation step)
+  tm.outer_steps = static_cast<int32_t>(tmr[3]);             // trajectory claims of the scheduler
+  int active = 0;
+  CK(cudaMemcpy(&active, dp.active_count, sizeof(int), cudaMemcpyDeviceToHost));
   // algorithmic HBM bytes of one convexify launch: read x, write cart rows, dense collision
   // rows and the exact values, per trajectory
   const int64_t per_traj = 8LL * (dp.N + static_cast<int64_t>(dp.n_coll_cand) * dp.coll_stride +
@@ -643,7 +648,7 @@ int tb200_solve_batch_resident(tb200_problem* P) {
   int counters[2] = {0, 0};
   CK(cudaMemcpy(counters, dp.active_count, sizeof(counters), cudaMemcpyDeviceToHost));
   tm.convexify_bytes = per_traj * counters[1];  // summed over all launches: trajectories actually convexified
-  if (active > 0) return fail(TB200_ERR_CUDA, "SQP driver hit its step cap with trajectories still active");
+  if (active > 0) return fail(TB200_ERR_CUDA, "the SQP kernel returned with trajectories still active");
   return TB200_OK;
 }
 
@@ -735,7 +740,12 @@ int tb200_qp_solve_batch(tb200_problem* P, const double* x, const double* trust,
   if (dp.n_cnts > 0) CK(cudaMemcpyAsync(P->merit_coeffs.p, merit_coeffs, B * dp.n_cnts * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(P->ws_meta.p, 0, B * 8 * sizeof(int), st));
   eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
-  qp_kernel_for(P->D, P->pair_rows)<<<dp.B, kQpThreads, P->qp_smem, st>>>(dp, P->x_tmp.p, P->trust_tmp.p, P->tmp_iters.p, P->tmp_polish.p, 1 << 30);
+  SolveCtl ctl{};
+  ctl.mode = SOLVE_QP_ONLY;  // one QP step per trajectory (one CTA each), no evaluation / decision
+  ctl.quantum = 1;
+  ctl.x_override = P->x_tmp.p; ctl.trust_override = P->trust_tmp.p;
+  ctl.admm_iters_out = P->tmp_iters.p; ctl.polish_out = P->tmp_polish.p;
+  solve_kernel_for(P->D, P->pair_rows)<<<dp.B, kQpThreads, P->solve_smem, st>>>(dp, P->ex, ctl);
   CK(cudaGetLastError());
   auto pull = [&](void* dst, const void* src, size_t n) {
     if (!dst || n == 0) return cudaSuccess;
@@ -776,6 +786,17 @@ int tb200_debug_fetch_trace(tb200_problem* P, double* out, int32_t* len) {
 }
 
 int tb200_debug_prof(unsigned long long* out, int reset) { return qp_debug_prof(out, reset); }
+
+/* not part of the public header: schedule of the last solve: out[0] = first claim (ns), out[1 + b] = finish time of
+   trajectory b (ns), out[1 + B + b] = ns it was being worked on */
+int tb200_debug_schedule(tb200_problem* P, unsigned long long* out) {
+  if (!P || !out) return fail(TB200_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(P->device));
+  const size_t B = P->dp.B;
+  CK(cudaMemcpy(out, P->sched_timers.p + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out + 1, P->sched_timers.p + 8, 2 * B * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return TB200_OK;
+}
 
 /* not part of the public header: solver diagnostics of the last QP of every trajectory, [B][16] */
 int tb200_debug_last_qp(tb200_problem* P, double* out) {
