@@ -694,7 +694,7 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
 }
 
 #ifndef TB200_EVAL_MIN_BLOCKS
-#define TB200_EVAL_MIN_BLOCKS 3
+#define TB200_EVAL_MIN_BLOCKS 4
 #endif
 // Stand-alone launch, one CTA per trajectory: the initial evaluation of a solve (EVAL_INIT) and the kernel-level
 // convexify entry point (EVAL_ONLY).  Inside a solve the same code runs as a step of solve_kernel.cuh.
