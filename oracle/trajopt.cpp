@@ -377,7 +377,7 @@ struct CollisionEval {
       exprs.push_back(e);  // (cleanupAff result is discarded in the reference: collision_terms.cpp:554)
     }
   }
-  // every (sphere, obstacle) candidate, filtered ones flagged by weight 0 (fixed GPU layout)
+  // every (sphere, obstacle) candidate; filtered ones carry weight 0 and a zero gradient (fixed GPU layout)
   void denseRows(const Vec& x, std::vector<Vec>& rows) const {
     std::vector<Pose> frames;
     robot->fk(x.data() + t * D, frames);
@@ -395,11 +395,13 @@ struct CollisionEval {
         const double d[3] = {ob[0] - c[0], ob[1] - c[1], ob[2] - c[2]};
         const double len = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
         const double dist = len - sp.radius - ob[3];
-        Vec row(D + 3);
-        for (int j = 0; j < D; ++j) row[j] = -(d[0] * J[0][j] + d[1] * J[1][j] + d[2] * J[2][j]) / len;
+        Vec row(D + 3, 0.0);
+        const bool filtered = dist > margin + buffer;  // no expression is ever built for a filtered contact
+        if (!filtered)
+          for (int j = 0; j < D; ++j) row[j] = -(d[0] * J[0][j] + d[1] * J[1][j] + d[2] * J[2][j]) / len;
         row[D] = dist;
         row[D + 1] = margin;
-        row[D + 2] = (dist > margin + buffer) ? 0.0 : coeff;
+        row[D + 2] = filtered ? 0.0 : coeff;
         rows.push_back(row);
       }
     }

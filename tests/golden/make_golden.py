@@ -20,7 +20,8 @@ from trajopt_b200 import problems  # noqa: E402
 import oracle_lib  # noqa: E402
 
 CASES = {"cfg1_B4_T12": lambda: problems.config1(B=4, T=12), "cfg2_B4_T12": lambda: problems.config2(B=4, T=12),
-         "cfg2_B2_T30": lambda: problems.config2(B=2, T=30)}
+         "cfg2_B2_T30": lambda: problems.config2(B=2, T=30),
+         "cfg3_B4_T12": lambda: problems.config3(B=4, T=12, via_every=4)}
 
 
 def perturbed(desc):

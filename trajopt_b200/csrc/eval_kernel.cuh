@@ -19,7 +19,7 @@ enum EvalMode { EVAL_INIT = 0, EVAL_STEP = 1, EVAL_ONLY = 2 };
 
 struct EvalSmem {
   // offsets in doubles into the dynamic shared buffer
-  int x, sph, spo, jax, cartf, velp, objv, mask, misc, fr, terms, obst, sphr, wscr, wscr_stride, total;
+  int x, sph, spo, jax, cartf, velp, objv, mask, misc, fr, terms, obst, sphr, segs, sphs, wscr, wscr_stride, total;
 };
 // n_vel_objs: CartVel step pairs; cast: the collision objects are step pairs (continuous evaluator)
 __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_cart_objs, int n_coll_objs,
@@ -34,6 +34,8 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   s.jax = o;    o += T * D * 6;                       // per (waypoint, joint): A[3], B[3] (see the kernel)
   s.obst = o;   o += 4 * 64;                          // this trajectory's obstacle spheres (x, y, z, r)
   s.sphr = o;   o += L + (L & 1);                     // radii of the robot spheres
+  s.segs = o;   o += S * static_cast<int>(sizeof(DevSegment) / 8);   // the robot tables, read by every phase
+  s.sphs = o;   o += L * static_cast<int>(sizeof(DevSphere) / 8);
   s.cartf = o;  o += n_cart_objs * (1 + D) * 12;
   s.velp = o;   o += n_vel_objs * 6;                  // link position at both waypoints of a CartVel pair
   s.objv = o;   o += n_coll_objs;                     // exact value of every collision object (in-order sums)
@@ -48,8 +50,11 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   // phase reuses their space
   s.fr = o;                                           // frames of every FK job: local, then (in place) world
   s.terms = o;                                        // per-(step, joint) terms of the joint-space objects (later phase)
+  // ... and, while the collision rows are written, the per-warp staging tiles of the bulk (TMA) row stores
   const int a = (T + n_cart_objs * D) * S * 12, b2 = n_joint_objs * 2 * T * D;
-  o += a > b2 ? a : b2;
+  const int st = (((D + 3) & 1) == 0 && !cast) ? 8 * 32 * (D + 3) : 0;
+  const int m = a > b2 ? a : b2;
+  o += m > st ? m : st;
   o += o & 1;
   s.total = o;
   return s;
@@ -66,6 +71,33 @@ struct EvalExtra {
   int qtype[kMaxDof];                // joint type per trajectory column
   unsigned sphere_jmask[kMaxSpheres];  // which columns move each sphere
 };
+
+#ifdef TB200_EVAL_PROFILE
+// cycles of thread 0 between the block barriers of eval_step, summed over CTAs (scripts/eval_phases.py)
+static __device__ unsigned long long g_eval_prof[16];
+static __device__ unsigned long long g_eval_trace[3 * 4096];  // per CTA: start ns, end ns, SM id
+#define EVAL_PROF(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_eval_prof[k], (unsigned long long)(now_ - prof_t_)); prof_t_ = now_; } } while (0)
+#define EVAL_PROF_BEGIN()                                                                          \
+  long long prof_t_ = clock64();                                                                   \
+  if (threadIdx.x == 0 && b < 4096) {                                                              \
+    unsigned long long t_;                                                                         \
+    unsigned sm_;                                                                                  \
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                         \
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm_));                                               \
+    g_eval_trace[3 * b] = t_;                                                                      \
+    g_eval_trace[3 * b + 2] = sm_;                                                                 \
+  }
+#define EVAL_PROF_END()                                                                            \
+  if (threadIdx.x == 0 && b < 4096) {                                                              \
+    unsigned long long t_;                                                                         \
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                         \
+    g_eval_trace[3 * b + 1] = t_;                                                                  \
+  }
+#else
+#define EVAL_PROF_END()
+#define EVAL_PROF(k)
+#define EVAL_PROF_BEGIN()
+#endif
 
 // FK of ONE joint state by a warp: local frames (lanes over segments), then the chain products row by row
 // (lanes 0-2; the other lanes only keep the barriers).  F: [S][12] world frames (R row-major, p).
@@ -105,6 +137,7 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
   constexpr int D = DD;
+  EVAL_PROF_BEGIN();
   const int T = p.T, N = p.N, L = p.L, O = p.O;
   if (mode != EVAL_ONLY && p.status[b] != 5 /*running == INVALID*/) return;
   if (mode == EVAL_STEP && p.qp_done[b] == 0) return;  // its QP is still being solved (time-sliced)
@@ -137,8 +170,13 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
       const double* og = p.obstacles + (p.obstacles_per_traj ? static_cast<size_t>(b) * O * 4 : 0);
       for (int i = tid; i < O * 4; i += kEvalThreads) sm[S.obst + i] = og[i];
       for (int i = tid; i < L; i += kEvalThreads) sm[S.sphr + i] = p.spheres[i].r;
+      const double* sg_g = reinterpret_cast<const double*>(p.segs);
+      for (int i = tid; i < p.S * static_cast<int>(sizeof(DevSegment) / 8); i += kEvalThreads) sm[S.segs + i] = sg_g[i];
+      const double* sp_g = reinterpret_cast<const double*>(p.spheres);
+      for (int i = tid; i < L * static_cast<int>(sizeof(DevSphere) / 8); i += kEvalThreads) sm[S.sphs + i] = sp_g[i];
     }
     __syncthreads();
+    EVAL_PROF(1);
 
     // ---- FK: one job per waypoint, plus D perturbed configurations per CartPose object ---------------
     // (1) local frames of every (job, segment) in parallel (this is where the sincos are), (2) the chain
@@ -146,9 +184,11 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
     // so the three lanes of a job never wait for each other, (3) emission of what the row writers need.
     const int n_jobs = T + ex.n_cart_objs * D, Sg = p.S;
     double* FR = sm + S.fr;
+    const DevSegment* segs = reinterpret_cast<const DevSegment*>(sm + S.segs);
+    const DevSphere* sphs = reinterpret_cast<const DevSphere*>(sm + S.sphs);
     for (int w = tid; w < n_jobs * Sg; w += kEvalThreads) {
       const int job = w / Sg, sg = w % Sg;
-      const DevSegment g = p.segs[sg];
+      const DevSegment& g = segs[sg];
       double qv = 0.0;
       if (g.q_index >= 0) {
         if (job < T) qv = xs[job * D + g.q_index];
@@ -164,35 +204,52 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
       for (int i = 0; i < 3; ++i) f[9 + i] = loc.p[i];
     }
     __syncthreads();
+    EVAL_PROF(2);
     for (int w = tid; w < ((n_jobs * 4 + 31) & ~31); w += kEvalThreads) {  // whole warps: __syncwarp below
-      // four lanes per job (three rows + one idle) so that the rows of a job always sit in the same warp
+      // four lanes per job (three rows + one idle) so that the rows of a job always sit in the same warp.  A lane
+      // only ever needs ITS row of the parent frame: along a chain (parent == previous segment) it is still in
+      // registers, at a branch point it reads back what it wrote itself.  The one barrier per step keeps the
+      // in-place overwrite of a local frame behind its readers.
       const bool act = w < n_jobs * 4 && (w & 3) < 3;
       const int job = (w < n_jobs * 4) ? w / 4 : 0, i = (w & 3) % 3;
       double* F = FR + static_cast<size_t>(job) * Sg * 12;
+      double r0 = 0.0, r1 = 0.0, r2 = 0.0, rp = 0.0;
       for (int sg = 0; sg < Sg; ++sg) {
-        const int parent = p.segs[sg].parent;
+        const int parent = segs[sg].parent;
         double l[12];
         for (int k = 0; k < 12; ++k) l[k] = F[sg * 12 + k];
-        __syncwarp();  // the other rows of this job have read the local frame before it is overwritten
-        if (act && parent >= 0) {
-          const double* P = F + parent * 12;
-          const double r0 = P[i * 3], r1 = P[i * 3 + 1], r2 = P[i * 3 + 2], pi = P[9 + i];
-          F[sg * 12 + i * 3 + 0] = r0 * l[0] + r1 * l[3] + r2 * l[6];
-          F[sg * 12 + i * 3 + 1] = r0 * l[1] + r1 * l[4] + r2 * l[7];
-          F[sg * 12 + i * 3 + 2] = r0 * l[2] + r1 * l[5] + r2 * l[8];
-          F[sg * 12 + 9 + i] = r0 * l[9] + r1 * l[10] + r2 * l[11] + pi;
-        }
         __syncwarp();
+        if (parent >= 0) {
+          if (parent != sg - 1) {
+            const double* P = F + parent * 12;
+            r0 = P[i * 3]; r1 = P[i * 3 + 1]; r2 = P[i * 3 + 2]; rp = P[9 + i];
+          }
+          const double n0 = r0 * l[0] + r1 * l[3] + r2 * l[6], n1 = r0 * l[1] + r1 * l[4] + r2 * l[7],
+                       n2 = r0 * l[2] + r1 * l[5] + r2 * l[8], np = r0 * l[9] + r1 * l[10] + r2 * l[11] + rp;
+          r0 = n0; r1 = n1; r2 = n2; rp = np;
+          if (act) {
+            F[sg * 12 + i * 3 + 0] = r0;
+            F[sg * 12 + i * 3 + 1] = r1;
+            F[sg * 12 + i * 3 + 2] = r2;
+            F[sg * 12 + 9 + i] = rp;
+          }
+        } else {  // a root segment: its world frame is its local frame
+          r0 = (i == 0) ? l[0] : ((i == 1) ? l[3] : l[6]);  // (selects, not l[3 * i]: the frame stays in registers)
+          r1 = (i == 0) ? l[1] : ((i == 1) ? l[4] : l[7]);
+          r2 = (i == 0) ? l[2] : ((i == 1) ? l[5] : l[8]);
+          rp = (i == 0) ? l[9] : ((i == 1) ? l[10] : l[11]);
+        }
       }
     }
     __syncthreads();
+    EVAL_PROF(3);
     // per (waypoint, joint) the two vectors the gradient of a point on the chain needs: for a point c and a unit
     // direction n,  n . d(c)/dq_j = n . (a_j x (c - o_j)) = A_j . (c x n) - B_j . n  with A_j = a_j, B_j = a_j x o_j
     // (revolute; a_j axis, o_j origin of the joint in the scene root) and A_j = 0, B_j = -a_j (prismatic).
     // Six doubles per (waypoint, joint), 16-byte aligned: the row writers read them as broadcasts.
     for (int w = tid; w < T * Sg; w += kEvalThreads) {
       const int t = w / Sg, sg = w % Sg;
-      const DevSegment& g = p.segs[sg];
+      const DevSegment& g = segs[sg];
       if (g.q_index < 0) continue;
       const double* f = FR + static_cast<size_t>(w) * 12;
       double* ab = sm + S.jax + (t * D + g.q_index) * 6;
@@ -209,7 +266,7 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
     }
     for (int w = tid; w < T * L; w += kEvalThreads) {
       const int t = w / L, sl = w % L;
-      const DevSphere sp = p.spheres[sl];
+      const DevSphere& sp = sphs[sl];
       const double* f = FR + (static_cast<size_t>(t) * Sg + sp.segment) * 12;
       double* sph = sm + S.sph + w * 3;
       for (int i = 0; i < 3; ++i) {
@@ -230,37 +287,41 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
       sm[S.cartf + w] = FR[(static_cast<size_t>(job) * Sg + o.link) * 12 + k];
     }
     __syncthreads();
+    EVAL_PROF(4);
 
     // ---- CartPose rows: error + forward-difference Jacobian (kinematic_terms.cpp:250-263, 348-366) ----
-    for (int w = tid; w < ex.n_cart_objs * (1 + D); w += kEvalThreads) {
-      const int c = w / (1 + D), col = w % (1 + D);  // col 0 = error, col 1+i = Jacobian column i
+    // One warp per CartPose object, lane 0 the unperturbed frame, lane 1+i the frame at q + eps e_i: every lane runs
+    // the pose-error pipeline ONCE (it is a long dependent chain of fp64 divisions, square roots and an atan2); the
+    // base error reaches the difference quotients by shuffle.
+    for (int c = tid >> 5; c < ex.n_cart_objs; c += kEvalThreads / 32) {
+      const int col = tid & 31;  // col 0 = error, col 1+i = Jacobian column i
+      const bool work = col < 1 + D;
       const DevObj& o = ex.cart_objs[c];
       const DevCartTerm& ct = p.cart_terms[o.term];
-      Frame tgt, off, lf, src, e0;
+      Frame tgt, off, lf, src, e1;
       quat_to_frame(o.target_slot >= 0 ? p.cart_targets + (static_cast<size_t>(b) * p.n_cart_targets + o.target_slot) * 7 : ct.tgt, tgt);
       for (int i = 0; i < 9; ++i) off.R[i] = ct.src_R[i];
       for (int i = 0; i < 3; ++i) off.p[i] = ct.src_p[i];
-      const double* f0 = sm + S.cartf + c * (1 + D) * 12;
-      for (int i = 0; i < 9; ++i) lf.R[i] = f0[i];
-      for (int i = 0; i < 3; ++i) lf.p[i] = f0[9 + i];
+      const double* f1 = sm + S.cartf + (c * (1 + D) + (work ? col : 0)) * 12;
+      for (int i = 0; i < 9; ++i) lf.R[i] = f1[i];
+      for (int i = 0; i < 3; ++i) lf.p[i] = f1[9 + i];
       frame_mul(lf, off, src);
-      rel_pose(tgt, src, e0);
-      double a0[3], g0;
-      rot_err_decomposed(e0.R, a0, g0);
+      rel_pose(tgt, src, e1);
+      double a1[3], g1;
+      rot_err_decomposed(e1.R, a1, g1);
+      double a0[3], e0p[3];
+      const double g0 = __shfl_sync(0xffffffffu, g1, 0);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        a0[i] = __shfl_sync(0xffffffffu, a1[i], 0);
+        e0p[i] = __shfl_sync(0xffffffffu, e1.p[i], 0);
+      }
       double* err_out = p.cart_err + slot * p.n_cart_rows + o.src_off;
       double* jac_out = p.cart_jac + (slot * p.n_cart_rows + o.src_off) * p.cart_stride;
       if (col == 0) {
-        const double e[6] = {e0.p[0], e0.p[1], e0.p[2], a0[0] * g0, a0[1] * g0, a0[2] * g0};
+        const double e[6] = {e1.p[0], e1.p[1], e1.p[2], a1[0] * g1, a1[1] * g1, a1[2] * g1};
         for (int r = 0; r < ct.n_idx; ++r) err_out[r] = e[ct.idx[r]] * ct.coeff[r];
-      } else {
-        const double* f1 = sm + S.cartf + (c * (1 + D) + col) * 12;
-        Frame lf1, src1, e1;
-        for (int i = 0; i < 9; ++i) lf1.R[i] = f1[i];
-        for (int i = 0; i < 3; ++i) lf1.p[i] = f1[9 + i];
-        frame_mul(lf1, off, src1);
-        rel_pose(tgt, src1, e1);
-        double a1[3], g1;
-        rot_err_decomposed(e1.R, a1, g1);
+      } else if (work) {
         if (a1[0] * a0[0] + a1[1] * a0[1] + a1[2] * a0[2] < 0) {
           a1[0] = -a1[0]; a1[1] = -a1[1]; a1[2] = -a1[2];
           g1 = -g1;
@@ -268,7 +329,7 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
         const double diff = g1 - g0, pi = 3.14159265358979323846;
         if (diff > pi) g1 -= 2.0 * pi;
         else if (diff < -pi) g1 += 2.0 * pi;
-        const double dlt[6] = {e1.p[0] - e0.p[0], e1.p[1] - e0.p[1], e1.p[2] - e0.p[2],
+        const double dlt[6] = {e1.p[0] - e0p[0], e1.p[1] - e0p[1], e1.p[2] - e0p[2],
                                a1[0] * g1 - a0[0] * g0, a1[1] * g1 - a0[1] * g0, a1[2] * g1 - a0[2] * g0};
         for (int r = 0; r < ct.n_idx; ++r) jac_out[r * p.cart_stride + (col - 1)] = dlt[ct.idx[r]] / 1e-5 * ct.coeff[r];
       }
@@ -321,6 +382,7 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
       double vsum = 0.0;  // exact value of the object: its terms added in candidate order (warp-uniform)
       if (co.kind == OBJ_COLL) {
         const double* AB = sm + S.jax + t * D * 6;
+        double* stage = sm + S.fr + (tid >> 5) * (32 * (D + 3));  // this warp's tile (the FK frames are dead by now)
         for (int c0 = 0; c0 < LO; c0 += 32) {
           const int cnd = c0 + lane_c;
           const bool in = cnd < LO;
@@ -331,34 +393,56 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
           const double dx = ob.x - cx, dy = ob.y - cy, dz = ob.z - cz;
           const double len = sqrt(dx * dx + dy * dy + dz * dz);
           const double dist = len - sm[S.sphr + sl] - ob.w;
-          const double inv = 1.0 / len;
-          const double nx = dx * inv, ny = dy * inv, nz = dz * inv;  // from the robot sphere towards the obstacle
-          const double mx = cy * nz - cz * ny, my = cz * nx - cx * nz, mz = cx * ny - cy * nx;  // c x n
-          const unsigned jm = ex.sphere_jmask[sl];
           const bool active = in && !(dist > reach);
           double row[D + 3 + ((D + 3) & 1)];
 #pragma unroll
-          for (int j = 0; j < D; ++j) {
-            const double2 a01 = *reinterpret_cast<const double2*>(AB + j * 6);
-            const double2 a2b0 = *reinterpret_cast<const double2*>(AB + j * 6 + 2);
-            const double2 b12 = *reinterpret_cast<const double2*>(AB + j * 6 + 4);
-            // d(dist)/dq_j = -n . d(c)/dq_j = B_j . n - A_j . (c x n)
-            const double g = (a2b0.y * nx + b12.x * ny + b12.y * nz) - (a01.x * mx + a01.y * my + a2b0.x * mz);
-            row[j] = ((jm >> j) & 1u) ? g : 0.0;
+          for (int j = 0; j < D; ++j) row[j] = 0.0;
+          // The gradient exists only for contacts inside margin + buffer (the reference never builds an expression
+          // for a filtered contact, collision_terms.cpp:655-691): the other candidates keep a zero gradient.
+          if (active) {
+            const double inv = 1.0 / len;
+            const double nx = dx * inv, ny = dy * inv, nz = dz * inv;  // from the robot sphere towards the obstacle
+            const double mx = cy * nz - cz * ny, my = cz * nx - cx * nz, mz = cx * ny - cy * nx;  // c x n
+            const unsigned jm = ex.sphere_jmask[sl];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+              const double2 a01 = *reinterpret_cast<const double2*>(AB + j * 6);
+              const double2 a2b0 = *reinterpret_cast<const double2*>(AB + j * 6 + 2);
+              const double2 b12 = *reinterpret_cast<const double2*>(AB + j * 6 + 4);
+              // d(dist)/dq_j = -n . d(c)/dq_j = B_j . n - A_j . (c x n)
+              const double g = (a2b0.y * nx + b12.x * ny + b12.y * nz) - (a01.x * mx + a01.y * my + a2b0.x * mz);
+              row[j] = ((jm >> j) & 1u) ? g : 0.0;
+            }
           }
           row[D] = dist;
           row[D + 1] = margin;
           row[D + 2] = active ? coeff : 0.0;
-          if (in) {
-            double* dstp = rows_out + static_cast<size_t>(co.src_off + cnd) * (D + 3);
-            if constexpr (((D + 3) & 1) == 0) {  // rows are 16-byte aligned: D + 3 even, buffers 256-byte aligned
-              double2* d2 = reinterpret_cast<double2*>(dstp);
+          if constexpr (((D + 3) & 1) == 0) {
+            // rows are 16-byte aligned (D + 3 even, 256-byte aligned buffers): the 32 rows of the chunk are staged in
+            // shared memory and leave as ONE asynchronous bulk store (cp.async.bulk, 2.5 KB contiguous in HBM).
+            // Measured (scripts/probes/store_probe.cu): lane-per-row 16-byte stores reach 2.7 TB/s, this 5.2 TB/s.
+            if (in) {
+              double2* d2 = reinterpret_cast<double2*>(stage + lane_c * (D + 3));
 #pragma unroll
               for (int i = 0; i < (D + 3) / 2; ++i) d2[i] = make_double2(row[2 * i], row[2 * i + 1]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < D + 3; ++i) dstp[i] = row[i];
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane_c == 0) {
+              const int nrows = (LO - c0 < 32) ? LO - c0 : 32;
+              const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(stage));
+              double* dstp = rows_out + static_cast<size_t>(co.src_off + c0) * (D + 3);
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstp), "r"(saddr),
+                           "r"(nrows * (D + 3) * 8)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile may be refilled
+            }
+            __syncwarp();
+          } else if (in) {
+            double* dstp = rows_out + static_cast<size_t>(co.src_off + cnd) * (D + 3);
+#pragma unroll
+            for (int i = 0; i < D + 3; ++i) dstp[i] = row[i];
           }
           const unsigned bal = __ballot_sync(0xffffffffu, active);
           if (lane_c == 0 && bal) atomicOr(&mask[k * p.coll_words + (c0 >> 6)], static_cast<unsigned long long>(bal) << (c0 & 63));
@@ -486,7 +570,9 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
       }
       if (lane_c == 0) sm[S.objv + k] = vsum;
     }
+    if (lane_c == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's row stores have landed
     __syncthreads();
+    EVAL_PROF(5);
     for (int i = tid; i < n_mask_words; i += kEvalThreads) p.coll_mask[slot * n_mask_words + i] = mask[i];
   }
 
@@ -523,6 +609,7 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
       }
     }
     __syncthreads();  // terms, collision violations (shared) and cart_err rows (global, this CTA) are complete
+    EVAL_PROF(6);
     const int lane = tid & 31, wid = tid >> 5;
     for (int i = wid; i < n_obj; i += kEvalThreads / 32) {  // one warp per object
       const bool is_cnt = i >= p.n_costs;
@@ -556,6 +643,8 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
       }
     }
   }
+  EVAL_PROF(7);
+  EVAL_PROF_END();
   if (mode == EVAL_ONLY) return;  // tb200_convexify_batch: exact values only, no SQP state touched
   __threadfence_block();
   __syncthreads();

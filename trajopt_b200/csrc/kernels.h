@@ -12,5 +12,6 @@ using EvalKernelFn = void (*)(DevProblem, EvalExtra, int, const double*);
 // coefficients per padded row instead of D).  nullptr: no instance for this number of joints.
 SolveKernelFn solve_kernel_for(int D, bool pair_rows);
 EvalKernelFn eval_kernel_for(int D);
+int eval_debug_prof(unsigned long long* out, int reset);  // TB200_EVAL_PROFILE builds of eval_kernels.cu only
 int qp_debug_prof(unsigned long long* out, int reset);  // TB200_PROFILE builds only (else returns -1)
 }  // namespace tb200

@@ -98,7 +98,8 @@ __device__ __forceinline__ void rot_err_decomposed(const double* m, double* axis
   axis[2] = q3 / n;
   const double two_pi = 6.283185307179586476925286766559;
   const double pi = 3.14159265358979323846;
-  ang = copysign(fmod(fabs(ang), two_pi), ang);
+  // (tesseract reduces with fmod(|angle|, 2 pi) first; |angle| = 2 atan2(n, |q0|) <= pi never needs it, and fp64
+  // fmod is a long loop on the GPU)
   if (ang < -pi)
     ang += two_pi;
   else if (ang > pi)

@@ -180,14 +180,55 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
     for (int i = 0; i < 3; ++i) { segs[s].p[i] = g.origin_xyz[i]; segs[s].axis[i] = g.axis[i]; }
     if (g.joint_type != TB200_JOINT_FIXED) P->ex.qtype[g.q_index] = g.joint_type;
   }
+  // Fixed segments nobody refers to (no collision sphere, no Cartesian term) are folded into their children:
+  // child.origin <- fixed.origin * child.origin.  The kernels then carry fewer frames per waypoint (shared memory of
+  // the evaluation kernel: 12 doubles per frame and waypoint).
+  std::vector<int> remap(dp.S, -1);
+  {
+    std::vector<char> used(dp.S, 0);
+    for (int s = 0; s < dp.L; ++s) {
+      const int g = d->robot.spheres[s].segment;
+      if (g < 0 || g >= dp.S) return fail(TB200_ERR_INVALID, "sphere attached to a bad segment");
+      used[g] = 1;
+    }
+    for (int k = 0; k < d->n_terms; ++k)
+      if ((d->terms[k].kind == TB200_TERM_CART_POSE || d->terms[k].kind == TB200_TERM_CART_VEL) && d->terms[k].link >= 0 &&
+          d->terms[k].link < dp.S)
+        used[d->terms[k].link] = 1;
+    std::vector<DevSegment> kept;
+    std::vector<DevSegment> acc(dp.S);  // transform from the nearest kept ancestor's frame to this (folded) segment
+    for (int s = 0; s < dp.S; ++s) {
+      DevSegment g = segs[s];
+      const int par = g.parent;
+      if (par >= 0 && remap[par] < 0) {  // parent was folded: compose its accumulated origin in front of ours
+        const DevSegment& a = acc[par];
+        double R[9], pp[3];
+        for (int i = 0; i < 3; ++i) {
+          for (int j = 0; j < 3; ++j) R[i * 3 + j] = a.R[i * 3] * g.R[j] + a.R[i * 3 + 1] * g.R[3 + j] + a.R[i * 3 + 2] * g.R[6 + j];
+          pp[i] = a.R[i * 3] * g.p[0] + a.R[i * 3 + 1] * g.p[1] + a.R[i * 3 + 2] * g.p[2] + a.p[i];
+        }
+        for (int i = 0; i < 9; ++i) g.R[i] = R[i];
+        for (int i = 0; i < 3; ++i) g.p[i] = pp[i];
+        g.parent = a.parent;  // nearest kept ancestor (original index) or -1
+      }
+      if (g.joint_type == TB200_JOINT_FIXED && !used[s]) {
+        acc[s] = g;  // folded: remembered for its children
+      } else {
+        remap[s] = static_cast<int>(kept.size());
+        g.parent = (g.parent >= 0) ? remap[g.parent] : -1;
+        kept.push_back(g);
+      }
+    }
+    segs.swap(kept);
+    dp.S = static_cast<int>(segs.size());
+  }
   std::vector<DevSphere> sph(std::max(dp.L, 1));
   for (int s = 0; s < dp.L; ++s) {
     const tb200_sphere& sp = d->robot.spheres[s];
-    if (sp.segment < 0 || sp.segment >= dp.S) return fail(TB200_ERR_INVALID, "sphere attached to a bad segment");
-    sph[s].segment = sp.segment; sph[s].r = sp.radius;
+    sph[s].segment = remap[sp.segment]; sph[s].r = sp.radius;
     for (int i = 0; i < 3; ++i) sph[s].c[i] = sp.center[i];
     unsigned m = 0;
-    for (int a = sp.segment; a >= 0; a = segs[a].parent)
+    for (int a = sph[s].segment; a >= 0; a = segs[a].parent)
       if (segs[a].q_index >= 0) m |= 1u << segs[a].q_index;
     P->ex.sphere_jmask[s] = m;
   }
@@ -231,7 +272,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
       max_rows += o.n_rows;
     } else if (tm.kind == TB200_TERM_CART_POSE) {
       if (tm.first_step < 0 || tm.first_step >= T) return fail(TB200_ERR_INVALID, "cart_pose timestep outside the trajectory");
-      if (tm.link < 0 || tm.link >= dp.S) return fail(TB200_ERR_INVALID, "cart_pose link out of range");
+      if (tm.link < 0 || tm.link >= d->robot.n_segments) return fail(TB200_ERR_INVALID, "cart_pose link out of range");
       if (tm.target_slot >= d->n_cart_targets) return fail(TB200_ERR_INVALID, "cart_pose target_slot out of range");
       DevCartTerm ct{};
       quatToRot(tm.source_offset + 3, ct.src_R);
@@ -243,7 +284,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
         if (std::fabs(tm.rot_coeffs[i]) > 1e-5) { ct.idx[ct.n_idx] = 3 + i; ct.coeff[ct.n_idx++] = tm.rot_coeffs[i]; }
       o.kind = OBJ_CART_POSE;
       o.first = tm.first_step;
-      o.link = tm.link;
+      o.link = remap[tm.link];
       o.target_slot = tm.target_slot;
       o.term = static_cast<int>(cts.size());
       o.src_off = n_cart_rows;
@@ -289,16 +330,16 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
       }
     } else if (tm.kind == TB200_TERM_CART_VEL) {
       // CartVelTermInfo::hatch (problem_description.cpp:1011-1057): one object per step pair (t, t+1)
-      if (tm.link < 0 || tm.link >= dp.S) return fail(TB200_ERR_INVALID, "cart_vel link out of range");
+      if (tm.link < 0 || tm.link >= d->robot.n_segments) return fail(TB200_ERR_INVALID, "cart_vel link out of range");
       unsigned lm = 0;
-      for (int a = tm.link; a >= 0; a = segs[a].parent)
+      for (int a = remap[tm.link]; a >= 0; a = segs[a].parent)
         if (segs[a].q_index >= 0) lm |= 1u << segs[a].q_index;
       for (int t = tm.first_step; t <= tm.last_step; ++t) {
         if (t < 0 || t + 1 >= T) return fail(TB200_ERR_INVALID, "cart_vel: step pair beyond the trajectory");
         DevObj c = o;
         c.kind = OBJ_CART_VEL;
         c.first = t;
-        c.link = tm.link;
+        c.link = remap[tm.link];
         c.src_off = n_cart_rows;
         c.n_rows = 6;
         c.pad1 = static_cast<int>(lm);
@@ -786,6 +827,7 @@ int tb200_debug_fetch_trace(tb200_problem* P, double* out, int32_t* len) {
 }
 
 int tb200_debug_prof(unsigned long long* out, int reset) { return qp_debug_prof(out, reset); }
+int tb200_debug_eval_prof(unsigned long long* out, int reset) { return eval_debug_prof(out, reset); }
 
 /* not part of the public header: schedule of the last solve: out[0] = first claim (ns), out[1 + b] = finish time of
    trajectory b (ns), out[1 + B + b] = ns it was being worked on */
