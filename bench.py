@@ -32,7 +32,7 @@ from trajopt_b200 import problems  # noqa: E402
 
 METRIC = "converged trajectories/sec (7-DOF x 30 wp, batch 1024)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-batch convexify launch (ncu --set full, profiles/)
-TRAFFIC = {}
+TRAFFIC = {"cfg2": 101.3e6}  # 4.6 MB read + 96.8 MB written (r01; the 126 MB L2 still holds part of the rows at kernel end)
 
 
 def make_batch(config, batch, seed):
@@ -51,6 +51,15 @@ def workload_name(config, batch):
                 "LVS continuous collision (8 sphere obstacles) = configs[3] terms at 30 waypoints")
     extra = " + discrete collision (8 sphere obstacles), safety_margin 0.02" if config == "cfg2" else ""
     return f"batch {batch} x 7-DOF x 30 waypoints, JointVel/JointAcc + CartPose terminal constraint{extra}"
+
+
+def host_threads():
+    """Host threads of the CPU legs: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which
+    must not shrink the CPU baseline)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 class ClockSampler:
@@ -95,7 +104,7 @@ def run_reference(args, rank, world):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     oracle_lib.build()
-    threads = oracle_lib.lib().oracle_num_threads()
+    threads = host_threads()
     sample = args.cpu_sample
     times, conv = [], []
     for it in range(args.warmup + args.steps):
@@ -268,7 +277,7 @@ def main():
     if not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib  # CPU baseline leg: the oracle is the timed CPU path, never part of the product
-        threads = oracle_lib.lib().oracle_num_threads()
+        threads = host_threads()
         desc = make_batch(args.config, args.cpu_sample, problems.SEED + 999)
         t0 = time.perf_counter()
         r = oracle_lib.solve_batch(desc, n_threads=threads)

@@ -180,4 +180,25 @@ def config3(B=4096, T=50, seed=SEED + 3, n_obstacles=8, via_every=10, lvs=0.05):
     return ProblemDesc(robot, T, terms, init, fixed_timesteps=[0], cart_targets=targets, obstacles=obstacles)
 
 
-CONFIGS = {"cfg0": config0, "cfg1": config1, "cfg2": config2, "cfg3": config3}
+def config_variants(B=8, T=10, seed=SEED + 7, n_obstacles=8):
+    """Every term flavour the device path has that configs[1]-[3] do not use: JointVel cost with a target, JointAcc
+    INEQ cost, JointPos INEQ constraint (a band around the initial path), CartPose as an ABS cost (position only),
+    CartVel as an ABS cost, collision as a hinge COST, one fixed DOF (fixed_dofs) on top of the fixed first waypoint."""
+    robot = robots.pr2_arm("r", with_spheres=True)
+    rng = np.random.default_rng(seed)
+    D = 7
+    q0, q1 = _sample_endpoints(rng, robot, B)
+    init = interpolate(q0, q1, T)
+    obstacles = _sample_obstacles(rng, robot, q0, q1, n_obstacles)
+    tool = robot["tool"]
+    terms = [joint_term(TERM_JOINT_VEL, ROLE_COST, D, 0, T - 1, coeffs=2.0, targets=0.01),
+             joint_term(TERM_JOINT_ACC, ROLE_COST, D, 0, T - 1, coeffs=1.0, upper=0.05, lower=-0.05),
+             cart_pose_term(ROLE_COST, T - 1, tool, target_slot=0, rot_coeffs=(0, 0, 0), pos_coeffs=(5, 5, 5)),
+             cart_vel_term(ROLE_COST, 0, T - 2, tool, 0.08),
+             collision_term(ROLE_COST, 0, T - 1, margin=0.02, coeff=20.0, buffer=0.01, fixed_steps=[0]),
+             joint_term(TERM_JOINT_POS, ROLE_CNT, D, 1, T - 1, coeffs=1.0, upper=[3.2] * 6 + [7.0], lower=[-3.2] * 6 + [-7.0])]
+    return ProblemDesc(robot, T, terms, init, fixed_timesteps=[0], fixed_dofs=[6],
+                       cart_targets=_targets_from_goal(robot, q1, tool), obstacles=obstacles)
+
+
+CONFIGS = {"cfg0": config0, "cfg1": config1, "cfg2": config2, "cfg3": config3, "variants": config_variants}
