@@ -9,8 +9,9 @@
  * C++ virtuals: sco::Model, sco::Cost, sco::Constraint); the POD structs below are the
  * flattened form of what trajopt::ConstructProblem() produces from a
  * trajopt::ProblemConstructionInfo (trajopt/include/trajopt/problem_description.hpp:235-259).
- * The C++ shim in trajopt_b200/host/ re-exposes it under the reference's own names
- * (ProblemConstructionInfo / TermInfo / ModelType / BasicTrustRegionSQPParameters).
+ * The C++ host layer include/trajopt_b200.hpp re-exposes it under the reference's own names
+ * (ProblemConstructionInfo / TermInfo subclasses / ModelType / BasicTrustRegionSQPParameters /
+ * ConstructProblem / OptResults).
  *
  * Conventions: plain pointers + sizes, caller-owned buffers, int return codes
  * (0 = ok), no exceptions cross the boundary, thread-local tb200_last_error().

@@ -1,0 +1,85 @@
+"""The C++ host layer (include/trajopt_b200.hpp: ProblemConstructionInfo / TermInfo / ConstructProblem /
+OptimizeProblem under the reference's names) against the Python mirror of the same C ABI.
+CPU: it compiles, flattens configs[2] to the byte-identical POD description, and fails loudly without a device.
+GPU (-m gpu): solving through it gives the results of the Python path."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from trajopt_b200 import api, capi, problems, robots
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "trajopt_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def host_bin(tmp_path_factory):
+    capi.load_library()  # the CUDA build must exist (no GPU needed to load it)
+    out = str(tmp_path_factory.mktemp("cpp") / "host_mirror")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "host_mirror.cpp"), "-o", out, "-L", CSRC, "-ltrajopt_b200",
+           "-Wl,-rpath," + CSRC, "-Wl,--allow-shlib-undefined"]
+    subprocess.run(cmd, check=True)
+    return out
+
+
+def _write_input(path, d, q0, q1):
+    robot = d.robot_spec
+    names = [f"link{i}" for i in range(len(robot["segments"]))]
+    with open(path, "w") as f:
+        f.write(f"{d.B} {d.T} {d.D} {len(robot['segments'])}\n")
+        for i, s in enumerate(robot["segments"]):
+            vals = [s.parent, s.joint_type, s.q_index, *s.origin_xyz, *s.origin_wxyz, *s.axis]
+            f.write(" ".join(repr(float(v)) if isinstance(v, float) else str(v) for v in vals) + f" {names[i]}\n")
+        f.write(" ".join(repr(float(v)) for v in robot["lower"]) + "\n")
+        f.write(" ".join(repr(float(v)) for v in robot["upper"]) + "\n")
+        f.write(f"{len(robot['spheres'])}\n")
+        for sp in robot["spheres"]:
+            f.write(f"{names[sp.segment]} " + " ".join(repr(float(v)) for v in (*sp.center, sp.radius)) + "\n")
+        f.write(names[robot["tool"]] + "\n")
+        for arr in (q0, q1, d.cart_targets.reshape(d.B, 7)):
+            f.write(" ".join(repr(float(v)) for v in arr.ravel()) + "\n")
+        f.write(f"{d.obstacles.shape[1]}\n" + " ".join(repr(float(v)) for v in d.obstacles.ravel()) + "\n")
+
+
+def _case(tmp_path):
+    d = problems.config2(B=3, T=10)
+    q0, q1 = d.init_traj[:, 0].copy(), d.init_traj[:, -1].copy()
+    path = str(tmp_path / "in.txt")
+    _write_input(path, d, q0, q1)
+    return d, path
+
+
+def test_cpp_host_flattens_to_the_same_description(host_bin, tmp_path):
+    d, path = _case(tmp_path)
+    out = subprocess.run([host_bin, path, "dump"], check=True, capture_output=True, text=True).stdout.splitlines()
+    assert out[0] == f"n_terms {len(d.terms)} n_cart_targets 1 n_fixed 1"
+    assert out[1].split()[1] == bytes(d._terms).hex()  # tb200_term[] byte for byte
+    init = np.array(out[2].split()[1:], float).reshape(d.init_traj.shape)
+    np.testing.assert_allclose(init, d.init_traj, rtol=0, atol=1e-14)  # LinSpaced vs numpy linspace rounding
+    tg = np.array(out[3].split()[1:], float).reshape(d.cart_targets.shape)
+    np.testing.assert_array_equal(tg, d.cart_targets)
+
+
+def test_cpp_host_fails_loudly_without_a_device(host_bin, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    _, path = _case(tmp_path)
+    r = subprocess.run([host_bin, path, "solve"], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CUDA device" in r.stderr  # std::runtime_error, never a CPU fallback
+
+
+@pytest.mark.gpu
+def test_cpp_host_solves_like_the_python_path(host_bin, tmp_path):
+    d, path = _case(tmp_path)
+    out = subprocess.run([host_bin, path, "solve"], check=True, capture_output=True, text=True).stdout.splitlines()
+    ref = api.solve(d)
+    assert len(out) == d.B
+    for b, line in enumerate(out):
+        v = line.split()
+        assert int(v[1]) == ref["status"][b] and int(v[3]) == ref["n_qp_solves"][b]
+        assert abs(float(v[2]) - ref["total_cost"][b]) < 1e-6
+        np.testing.assert_allclose(np.array(v[5:], float), ref["x"][b].ravel(), atol=1e-5)
