@@ -1,8 +1,7 @@
 import sys, os, time, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from trajopt_b200 import capi
-capi.library_path = lambda: os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "trajopt_b200", "csrc", "libtrajopt_b200_prof.so")
+# needs a build of solve_kernels.cu with -DTB200_PROFILE, selected with TB200_LIB=<path to that .so>
 from trajopt_b200 import api, problems
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 d = {"cfg1": problems.config1, "cfg2": problems.config2}[sys.argv[2] if len(sys.argv) > 2 else "cfg2"](B=B, T=30)
