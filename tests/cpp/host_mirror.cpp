@@ -6,7 +6,9 @@
 #include <fstream>
 #include <iostream>
 
-#include "trajopt_b200.hpp"
+#include <sstream>
+
+#include "trajopt_b200_json.hpp"
 
 namespace tb = trajopt_b200;
 using namespace tb::trajopt;
@@ -55,6 +57,36 @@ int main(int argc, char** argv) {
   pci.obstacles.resize(static_cast<size_t>(B) * pci.n_obstacles * 4);
   for (double& v : pci.obstacles) in >> v;
   if (!in) { std::fprintf(stderr, "bad input file\n"); return 2; }
+
+  if (mode == "json") {  // the description comes from a JSON document in the reference's schema (argv[3])
+    try {
+      std::ifstream jf(argv[3]);
+      std::stringstream ss;
+      ss << jf.rdbuf();
+      ProblemConstructionInfo jp;
+      jp.kin = kin;
+      jp.batch = B;
+      jp.obstacles = pci.obstacles;
+      jp.n_obstacles = pci.n_obstacles;
+      fromJson(jp, tb::json::parse(ss.str()));
+      jp.init_info.start = pci.init_info.start;  // the environment's current joint values, one state per problem
+      auto fp = FlattenProblem(jp);
+      std::printf("n_terms %d n_cart_targets %d n_fixed %d max_iter %d trust %.17g\n", fp->desc.n_terms, fp->desc.n_cart_targets,
+                  fp->desc.n_fixed_timesteps, fp->desc.sqp.max_iter, fp->desc.sqp.trust_box_size);
+      const unsigned char* p = reinterpret_cast<const unsigned char*>(fp->terms.data());
+      std::printf("terms ");
+      for (size_t i = 0; i < fp->terms.size() * sizeof(tb200_term); ++i) std::printf("%02x", p[i]);
+      std::printf("\ninit");
+      for (double v : fp->init_traj) std::printf(" %.17g", v);
+      std::printf("\ntargets");
+      for (double v : fp->cart_targets) std::printf(" %.17g", v);
+      std::printf("\n");
+      return 0;
+    } catch (const std::runtime_error& e) {
+      std::fprintf(stderr, "runtime_error: %s\n", e.what());
+      return 3;
+    }
+  }
 
   auto vel = std::make_shared<JointVelTermInfo>();
   vel->term_type = TT_COST;

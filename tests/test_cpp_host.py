@@ -72,6 +72,67 @@ def test_cpp_host_fails_loudly_without_a_device(host_bin, tmp_path):
     assert r.returncode == 3 and "no CUDA device" in r.stderr  # std::runtime_error, never a CPU fallback
 
 
+JSON_DOC = """
+{
+  "basic_info": {"n_steps": 10, "manip": "right_arm", "fixed_timesteps": [0], "convex_solver": "OSQP"},
+  "opt_info": {"max_iter": 40, "trust_box_size": 0.2},
+  "costs": [
+    {"type": "joint_vel", "params": {"coeffs": [2], "targets": [0]}},
+    {"type": "joint_acc", "name": "smooth", "params": {"targets": [0, 0, 0, 0, 0, 0, 0], "upper_tols": [0.1], "lower_tols": [-0.1]}},
+    {"type": "collision", "params": {"coeffs": 20, "dist_pen": 0.025, "evaluator_type": 4, "fixed_steps": [0],
+                                      "longest_valid_segment_length": 0.05}}
+  ],
+  "constraints": [
+    {"type": "cart_pose", "params": {"timestep": 9, "source_frame": "link9", "target_frame": "base_footprint",
+                                      "target_frame_offset_xyz": [0.6, -0.2, 0.9], "target_frame_offset_wxyz": [0, 0, 1, 0],
+                                      "rot_coeffs": [1, 1, 0]}},
+    {"type": "cart_vel", "params": {"first_step": 0, "last_step": 8, "max_displacement": 0.05, "link": "link9"}},
+    {"type": "joint_pos", "name": "end", "params": {"targets": [0.1, 0.2, 0.3, -0.4, 0.5, -0.6, 0.7], "first_step": 9, "last_step": 9}}
+  ],
+  "init_info": {"type": "JOINT_interpolated", "endpoint": [0.1, 0.2, 0.3, -0.4, 0.5, -0.6, 0.7]}
+}
+"""
+
+
+def test_json_front_end_matches_the_struct_description(host_bin, tmp_path):
+    """ProblemConstructionInfo::fromJson in the reference's schema (SURVEY.md Appendix A) against the same description
+    written with the Python mirror: byte-identical terms, same initial trajectory, opt_info overrides taken."""
+    d, path = _case(tmp_path)
+    jpath = str(tmp_path / "prob.json")
+    open(jpath, "w").write(JSON_DOC)
+    out = subprocess.run([host_bin, path, "json", jpath], check=True, capture_output=True, text=True).stdout.splitlines()
+    T, D = 10, 7
+    tool = d.robot_spec["tool"]
+    assert tool == 9  # "link9" above
+    terms = [problems.joint_term(capi.TERM_JOINT_VEL, capi.ROLE_COST, D, 0, T - 1, coeffs=2.0, T=T),
+             problems.joint_term(capi.TERM_JOINT_ACC, capi.ROLE_COST, D, 0, T - 1, upper=0.1, lower=-0.1, T=T),
+             problems.collision_term(capi.ROLE_COST, 0, T - 1, margin=0.025, coeff=20.0, buffer=0.5, fixed_steps=[0],
+                                     evaluator=capi.COLL_LVS_CONTINUOUS, lvs=0.05),
+             problems.cart_pose_term(capi.ROLE_CNT, 9, tool, target_slot=0, rot_coeffs=(1, 1, 0)),
+             problems.cart_vel_term(capi.ROLE_CNT, 0, 8, tool, 0.05),
+             problems.joint_term(capi.TERM_JOINT_POS, capi.ROLE_CNT, D, 9, 9, targets=[0.1, 0.2, 0.3, -0.4, 0.5, -0.6, 0.7], T=T)]
+    ref_terms = (capi.Term * len(terms))(*terms)
+    assert out[0] == "n_terms 6 n_cart_targets 1 n_fixed 1 max_iter 40 trust 0.20000000000000001"
+    assert out[1].split()[1] == bytes(ref_terms).hex()
+    init = np.array(out[2].split()[1:], float).reshape(d.B, T, D)
+    q0 = d.init_traj[:, 0]
+    want = problems.interpolate(q0, np.tile([0.1, 0.2, 0.3, -0.4, 0.5, -0.6, 0.7], (d.B, 1)), T)
+    np.testing.assert_allclose(init, want, rtol=0, atol=1e-14)
+    tg = np.array(out[3].split()[1:], float).reshape(d.B, 7)
+    np.testing.assert_array_equal(tg, np.tile([0.6, -0.2, 0.9, 0, 0, 1, 0], (d.B, 1)))
+
+
+@pytest.mark.parametrize("bad,msg", [
+    ('"params": {"coeffs": [2], "targets": [0], "bogus": 1}', "illegal field"),   # ensure_only_members
+    ('"params": {"coeffs": [2]}', "missing field: targets")])
+def test_json_front_end_rejects_what_the_reference_rejects(host_bin, tmp_path, bad, msg):
+    _, path = _case(tmp_path)
+    jpath = str(tmp_path / "bad.json")
+    open(jpath, "w").write(JSON_DOC.replace('"params": {"coeffs": [2], "targets": [0]}', bad))
+    r = subprocess.run([host_bin, path, "json", jpath], capture_output=True, text=True)
+    assert r.returncode == 3 and msg in r.stderr
+
+
 @pytest.mark.gpu
 def test_cpp_host_solves_like_the_python_path(host_bin, tmp_path):
     d, path = _case(tmp_path)
