@@ -32,7 +32,7 @@ from trajopt_b200 import problems  # noqa: E402
 
 METRIC = "converged trajectories/sec (7-DOF x 30 wp, batch 1024)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-batch convexify launch (ncu --set full, profiles/)
-TRAFFIC = {"cfg2": 101.3e6}  # 4.6 MB read + 96.8 MB written (r01; the 126 MB L2 still holds part of the rows at kernel end)
+TRAFFIC = {"cfg2": 103.0e6}  # 4.2 MB read + 98.8 MB written (r01; the 126 MB L2 still holds part of the rows at kernel end)
 
 
 def make_batch(config, batch, seed):

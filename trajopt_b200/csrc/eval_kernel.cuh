@@ -19,12 +19,12 @@ enum EvalMode { EVAL_INIT = 0, EVAL_STEP = 1, EVAL_ONLY = 2 };
 
 struct EvalSmem {
   // offsets in doubles into the dynamic shared buffer
-  int x, sph, spo, jax, cartf, velp, objv, mask, misc, fr, terms, obst, sphr, segs, sphs, wscr, wscr_stride, total;
+  int x, sph, spo, jax, cartf, velp, objv, mask, misc, fr, terms, obst, sphr, segs, sphs, cobj, aobj, wscr, wscr_stride, total;
 };
 // n_vel_objs: CartVel step pairs; cast: the collision objects are step pairs (continuous evaluator)
 __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_cart_objs, int n_coll_objs,
                                                       int n_mask_words, int S, int n_joint_objs, int n_vel_objs,
-                                                      int cast) {
+                                                      int cast, int n_objs) {
   EvalSmem s;
   int o = 0;
   s.x = o;      o += T * D;
@@ -36,6 +36,8 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   s.sphr = o;   o += L + (L & 1);                     // radii of the robot spheres
   s.segs = o;   o += S * static_cast<int>(sizeof(DevSegment) / 8);   // the robot tables, read by every phase
   s.sphs = o;   o += L * static_cast<int>(sizeof(DevSphere) / 8);
+  s.cobj = o;   o += n_coll_objs * static_cast<int>(sizeof(DevObj) / 8);   // the collision objects in kernel order
+  s.aobj = o;   o += n_objs * static_cast<int>(sizeof(DevObj) / 8);        // every object: costs, then constraints
   s.cartf = o;  o += n_cart_objs * (1 + D) * 12;
   s.velp = o;   o += n_vel_objs * 6;                  // link position at both waypoints of a CartVel pair
   s.objv = o;   o += n_coll_objs;                     // exact value of every collision object (in-order sums)
@@ -145,7 +147,10 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
   if (tid == 0 && !qp_failed) atomicAdd(p.active_count + 1, 1);  // trajectories actually convexified (bench: bytes moved)
   const int n_mask_words = p.n_coll_objs * p.coll_words;
   const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_objs, n_mask_words, p.S, ex.n_joint_objs,
-                                      ex.n_vel_objs, ex.cast);
+                                      ex.n_vel_objs, ex.cast, p.n_costs + p.n_cnts);
+  static_assert(sizeof(DevObj) % 8 == 0 && sizeof(DevSegment) % 8 == 0 && sizeof(DevSphere) % 8 == 0, "tables are copied as doubles");
+  const DevObj* cobjs = reinterpret_cast<const DevObj*>(sm + S.cobj);
+  const DevObj* aobjs = reinterpret_cast<const DevObj*>(sm + S.aobj);
   double* xs = sm + S.x;
   unsigned long long* mask = reinterpret_cast<unsigned long long*>(sm + S.mask);
   int* misc = reinterpret_cast<int*>(sm + S.misc);
@@ -174,6 +179,13 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
       for (int i = tid; i < p.S * static_cast<int>(sizeof(DevSegment) / 8); i += kEvalThreads) sm[S.segs + i] = sg_g[i];
       const double* sp_g = reinterpret_cast<const double*>(p.spheres);
       for (int i = tid; i < L * static_cast<int>(sizeof(DevSphere) / 8); i += kEvalThreads) sm[S.sphs + i] = sp_g[i];
+      constexpr int OD = static_cast<int>(sizeof(DevObj) / 8);
+      const double* co_g = reinterpret_cast<const double*>(ex.coll_objs);
+      for (int i = tid; i < p.n_coll_objs * OD; i += kEvalThreads) sm[S.cobj + i] = co_g[i];
+      const double* cs_g = reinterpret_cast<const double*>(p.cost_objs);
+      for (int i = tid; i < p.n_costs * OD; i += kEvalThreads) sm[S.aobj + i] = cs_g[i];
+      const double* cn_g = reinterpret_cast<const double*>(p.cnt_objs);
+      for (int i = tid; i < p.n_cnts * OD; i += kEvalThreads) sm[S.aobj + p.n_costs * OD + i] = cn_g[i];
     }
     __syncthreads();
     EVAL_PROF(1);
@@ -376,7 +388,7 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
       if (lane_c == 0) k = atomicAdd(&misc[2], 1);  // next collision object: warps take them as they get free
       k = __shfl_sync(0xffffffffu, k, 0);
       if (k >= p.n_coll_objs) break;
-      const DevObj& co = ex.coll_objs[k];
+      const DevObj& co = cobjs[k];
       const int t = co.first;
       const double margin = co.margin, reach = co.margin + co.buffer, coeff = co.coeff;
       double vsum = 0.0;  // exact value of the object: its terms added in candidate order (warp-uniform)
@@ -590,7 +602,7 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
     // joint-space terms: slot j of the term buffer belongs to the j-th joint-space object in (costs, cnts) order
     for (int slot_j = 0; slot_j < ex.n_joint_objs; ++slot_j) {
       const int i = ex.joint_obj_idx[slot_j];
-      const DevObj& o = (i >= p.n_costs) ? p.cnt_objs[i - p.n_costs] : p.cost_objs[i];
+      const DevObj& o = aobjs[i];
       const DevJointTerm& jt = p.joint_terms[o.term];
       double* tb = terms + static_cast<size_t>(slot_j) * 2 * T * D;
       const int kind = o.kind, order = o.order, first = o.first;
@@ -613,7 +625,7 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
     const int lane = tid & 31, wid = tid >> 5;
     for (int i = wid; i < n_obj; i += kEvalThreads / 32) {  // one warp per object
       const bool is_cnt = i >= p.n_costs;
-      const DevObj& o = is_cnt ? p.cnt_objs[i - p.n_costs] : p.cost_objs[i];
+      const DevObj& o = aobjs[i];
       double v = 0.0;
       if (o.kind <= OBJ_JOINT_INEQ_CNT) {
         int slot_j = 0;

@@ -470,7 +470,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
 
   // ---- kernel resources --------------------------------------------------------------------------------
   const EvalSmem es = eval_smem_layout(T, D, dp.L, P->ex.n_cart_objs, dp.n_coll_objs, dp.n_coll_objs * dp.coll_words, dp.S,
-                                       P->ex.n_joint_objs, P->ex.n_vel_objs, P->ex.cast);
+                                       P->ex.n_joint_objs, P->ex.n_vel_objs, P->ex.cast, dp.n_costs + dp.n_cnts);
   P->pair_rows = (CN > std::max(D, 3));
   P->eval_smem = static_cast<size_t>(es.total) * sizeof(double);
   const QpSmem qs = qp_smem_layout(N, 2 * D, dp.row_stride, CN, max_rows);
