@@ -54,12 +54,21 @@ def workload_name(config, batch):
 
 
 def host_threads():
-    """Host threads of the CPU legs: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which
-    must not shrink the CPU baseline)."""
+    """Host threads of the CPU legs: one per physical core this process may run on (torchrun exports OMP_NUM_THREADS=1,
+    which must not shrink the CPU baseline).  Measured on the GPU box (2 x 64 hardware threads), full batch of 1024:
+    64 threads 6.3 s, 128 threads 8.5 s - the oracle is bound by its allocator and caches, SMT siblings only hurt."""
+    if os.environ.get("TB200_CPU_THREADS"):
+        return int(os.environ["TB200_CPU_THREADS"])
     try:
-        return len(os.sched_getaffinity(0))
+        logical = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        logical = os.cpu_count() or 1
+    try:
+        import psutil
+        physical = psutil.cpu_count(logical=False) or logical
+    except ImportError:
+        physical = logical
+    return max(1, min(logical, physical))
 
 
 class ClockSampler:
@@ -134,7 +143,9 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3"])
     ap.add_argument("--batch", type=int, default=1024, help="trajectories per GPU (weak scaling)")
-    ap.add_argument("--cpu-sample", type=int, default=256, help="trajectories per CPU baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=1024,
+                    help="trajectories per CPU baseline step (default: one whole batch, so that the CPU path is bound by "
+                         "its longest trajectory exactly as the GPU path is)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
