@@ -101,6 +101,29 @@ def test_equality_joint_acc(oracle):  # joint_costs_unit.cpp:677-760
     np.testing.assert_allclose(a[1:], 0.1, atol=1e-2)
 
 
+def _joint_ineq_problem(kind):
+    """joint_costs_unit.cpp:152-262 (pos), 354-463 (vel), 768-877 (acc): an INEQ constraint keeps the quantity in
+    [-0.1, 0.2] at every step while two Ineq costs pull the first half towards +0.5 and the second half towards -0.5."""
+    robot = robots.pr2_arm("r", continuous_limit=4 * math.pi, with_spheres=False)
+    T, D = 10, 7
+    half = (T - 1) // 2
+    terms = [problems.joint_term(kind, ROLE_COST, D, 0, half, targets=0.5, upper=0.01, lower=-0.01, T=T),
+             problems.joint_term(kind, ROLE_COST, D, half + 1, T - 1, targets=-0.5, upper=0.01, lower=-0.01, T=T),
+             problems.joint_term(kind, ROLE_CNT, D, 0, T - 1, targets=0.0, upper=0.2, lower=-0.1, T=T)]
+    return capi.ProblemDesc(robot, T, terms, np.zeros((1, T, D)))
+
+
+@pytest.mark.parametrize("kind,order", [(TERM_JOINT_POS, 0), (TERM_JOINT_VEL, 1), (TERM_JOINT_ACC, 2)])
+def test_inequality_joint_terms(oracle, kind, order):
+    r = oracle.solve_batch(_joint_ineq_problem(kind))
+    q = np.diff(r["x"][0], n=order, axis=0) if order else r["x"][0]
+    cnt_tol = 1e-4
+    assert (q < 0.2 + cnt_tol).all() and (q > -0.1 - cnt_tol).all()
+    # the costs do pull: the first half sits at the upper edge of the band, the second half at the lower edge
+    # (joints whose own limits are tighter than the band stay at their limit, e.g. elbow / wrist flex: upper limit 0)
+    assert q[0].max() > 0.2 - 1e-2 and q[-1].min() < -0.1 + 1e-2
+
+
 def test_finite_difference_stencils(oracle):  # joint_costs_unit.cpp:883-937 (x = t^3): Cost::value == sum of squares
     T, D, dt = 10, 7, 0.1
     traj = np.repeat(((np.arange(T) * dt) ** 3)[:, None], D, axis=1)[None]
