@@ -430,6 +430,12 @@ int oracle_small_problem(int id, double* x_out, int* status, int* n_out) {
   return 0;
 }
 
+// the trust box of one variable (setTrustBoxConstraints, optimizers.cpp:151-170)
+int oracle_trust_box(double x, double lb, double ub, double trust, double* lo, double* hi) {
+  trustBox(x, lb, ub, trust, *lo, *hi);
+  return 0;
+}
+
 int oracle_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

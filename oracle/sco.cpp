@@ -1187,13 +1187,20 @@ std::shared_ptr<ConvexConstraints> ConstraintFromErrFunc::convex(const Vec& xall
 }
 
 // ============================================================================ SQP driver
+// The box of one variable: centred on the iterate clamped into [lb, ub], cut at the variable's own bounds
+// (optimizers.cpp:163-168; the identities of trajopt_sqp/test/trust_box_floor_unit.cpp:62-141 hold for it).
+void trustBox(double x, double lb, double ub, double trust, double& lo, double& hi) {
+  const double xi = std::min(std::max(x, lb), ub);
+  lo = std::max(xi - trust, lb);
+  hi = std::min(xi + trust, ub);
+}
 void BasicTrustRegionSQP::setTrustBoxConstraints(const Vec& x) {
   const Vec& lb = prob_->lower();
   const Vec& ub = prob_->upper();
   for (size_t i = 0; i < x.size(); ++i) {
-    const double xi = std::min(std::max(x[i], lb[i]), ub[i]);
-    prob_->model()->setVarBounds(static_cast<int>(i), std::max(xi - param_.trust_box_size, lb[i]),
-                                 std::min(xi + param_.trust_box_size, ub[i]));
+    double lo, hi;
+    trustBox(x[i], lb[i], ub[i], param_.trust_box_size, lo, hi);
+    prob_->model()->setVarBounds(static_cast<int>(i), lo, hi);
   }
 }
 

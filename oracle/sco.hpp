@@ -333,6 +333,8 @@ struct TraceEntry {
   int polish = 0, warm = 0;
 };
 
+void trustBox(double x, double lb, double ub, double trust, double& lo, double& hi);  // optimizers.cpp:163-168
+
 class BasicTrustRegionSQP {
 public:
   explicit BasicTrustRegionSQP(std::shared_ptr<OptProb> prob) : prob_(std::move(prob)) {}

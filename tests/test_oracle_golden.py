@@ -71,6 +71,27 @@ def test_small_problems(oracle, pid, expect, tol):
     np.testing.assert_allclose(x[:n.value], expect, atol=tol)
 
 
+# ---------------------------------------------------------------- trajopt_sqp/test/trust_box_floor_unit.cpp:62-141
+def test_trust_box_identities(oracle):
+    """The same clamp as optimizers.cpp:163-168: box centred on the iterate clamped into [lb, ub], cut at the bounds."""
+    lb, ub, bi = -2.5, 2.5, 0.0015
+
+    def box(x, lo=lb, hi=ub, d=bi):
+        a, b = C.c_double(0), C.c_double(0)
+        lib = oracle.lib()
+        lib.oracle_trust_box.argtypes = [C.c_double] * 4 + [C.POINTER(C.c_double)] * 2
+        assert lib.oracle_trust_box(x, lo, hi, d, C.byref(a), C.byref(b)) == 0
+        return a.value, b.value
+
+    assert box(0.0) == pytest.approx((-bi, bi), abs=1e-12)                    # interior: centred, width 2*bi
+    x = ub - bi / 2
+    assert box(x) == pytest.approx((x - bi, ub), abs=1e-12)                    # near the upper bound: asymmetric, 1.5*bi
+    assert box(ub) == pytest.approx((ub - bi, ub), abs=1e-12)                  # at the bound: width bi
+    assert box(2.6) == pytest.approx((ub - bi, ub), abs=1e-12)                 # far past the bound: flush, no inversion
+    assert box(-2.6) == pytest.approx((lb, lb + bi), abs=1e-12)                # mirror
+    assert box(0.05, 0.0, 0.1, 0.5) == pytest.approx((0.0, 0.1), abs=1e-12)    # range narrower than the trust radius
+
+
 # ---------------------------------------------------------------- trajopt/test/joint_costs_unit.cpp
 def _joint_problem(kind, cost_targ):
     robot = robots.pr2_arm("r", continuous_limit=4 * math.pi, with_spheres=False)
