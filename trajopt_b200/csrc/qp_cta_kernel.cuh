@@ -1,8 +1,10 @@
-// QP subproblem kernel, latency-optimised: one 256-thread CTA per trajectory, time sliced.
+// QP subproblem step (qp_step), latency-optimised: one 256-thread CTA works on one trajectory's QP.  A device
+// function: solve_kernel.cuh calls it from its persistent loop (and, with the override arguments, for the kernel-level
+// entry point tb200_qp_solve_batch).
 //
 // Replaces OSQPModel::optimize() -> osqp_setup/osqp_solve (trajopt_sco/src/osqp_interface.cpp:283-615) for
 // every trajectory of the batch (same algorithm and arithmetic as the oracle's qp_solve: Ruiz equilibration,
-// OSQP-equivalent ADMM, adaptive rho, verified polish; see DESIGN.md §5).
+// OSQP-equivalent ADMM, adaptive rho, verified polish; see DESIGN.md §4).
 //
 // Why a CTA per trajectory.  At batch 1024 the wall time of a batched solve is the slowest trajectory's
 // sequential chain of ADMM iterations (~8x the mean) times the latency of one iteration.  So the kernel is
@@ -18,8 +20,9 @@
 // Everything an ADMM iteration touches is in shared memory: the factor (3 x M x nb x nb), the trajectory
 // vectors, and - when the QP has at most `row_cap` rows, the common case - the rows of the QP themselves.
 // The hinge / abs auxiliary variables of the l1 penalty are eliminated per row in closed form (cancellation
-// free), exactly as in DESIGN.md §5.2.  A solve that runs out of its time slice parks its state (vectors, rows
-// and factor) in HBM and resumes from it in the next launch.
+// free), exactly as in DESIGN.md §4.2.  (The `slice` argument and the park / resume path belong to the earlier
+// lock-step launch design - a solve that ran out of its slice parked its state in HBM; the persistent kernel passes
+// an unbounded slice, so a QP always runs to its end in one call.)
 #pragma once
 #include "device_types.cuh"
 #include "joint_terms.cuh"
@@ -1625,8 +1628,8 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Kernel: QP assembly (optimizers.cpp:781-799 + osqp_interface.cpp:170-281 in fixed layout) + solve slice.
-// grid = B, block = 256 (one CTA per trajectory).  DD = degrees of freedom (block size NB = 2*DD).
+// QP assembly (optimizers.cpp:781-799 + osqp_interface.cpp:170-281 in fixed layout) + solve of trajectory b by the
+// calling CTA (256 threads).  DD = degrees of freedom (block size NB = 2*DD); PAIR: rows may span two waypoints.
 template <int DD, int PAIR>
 __device__ __forceinline__ void qp_step(const DevProblem& p, const int b, const double* x_override /*kernel-level API*/,
                                         const double* trust_override, int* admm_iters_out, int* polish_out, int slice) {
