@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from trajopt_b200 import api, capi, problems, robots
+from trajopt_b200 import api, capi, problems, robots  # noqa: F401
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "trajopt_b200", "csrc")
@@ -120,6 +120,44 @@ def test_json_front_end_matches_the_struct_description(host_bin, tmp_path):
     np.testing.assert_allclose(init, want, rtol=0, atol=1e-14)
     tg = np.array(out[3].split()[1:], float).reshape(d.B, 7)
     np.testing.assert_array_equal(tg, np.tile([0.6, -0.2, 0.9, 0, 0, 1, 0], (d.B, 1)))
+
+
+def test_python_json_loader_is_the_twin_of_the_cpp_one(host_bin, tmp_path):
+    from trajopt_b200 import json_io
+    d, path = _case(tmp_path)
+    jpath = str(tmp_path / "prob.json")
+    open(jpath, "w").write(JSON_DOC)
+    out = subprocess.run([host_bin, path, "json", jpath], check=True, capture_output=True, text=True).stdout.splitlines()
+    pd = json_io.from_json(JSON_DOC, d.robot_spec, d.init_traj[:, 0], obstacles=d.obstacles)
+    assert out[1].split()[1] == bytes(pd._terms).hex()
+    np.testing.assert_allclose(np.array(out[2].split()[1:], float).reshape(pd.init_traj.shape), pd.init_traj, rtol=0, atol=1e-14)
+    np.testing.assert_array_equal(np.array(out[3].split()[1:], float).reshape(pd.cart_targets.shape), pd.cart_targets)
+    assert pd.c.sqp.max_iter == 40 and pd.c.sqp.trust_box_size == 0.2
+    with pytest.raises(ValueError, match="illegal field"):
+        json_io.from_json(JSON_DOC.replace('"targets": [0]}', '"targets": [0], "bogus": 1}'), d.robot_spec, d.init_traj[:, 0])
+
+
+def test_python_json_loader_solves_on_the_oracle(oracle):
+    """A document in the reference's schema end to end on the CPU path (arm_around_table.json's shape: joint_vel cost,
+    collision cost with the LVS_CONTINUOUS evaluator and fixed end steps, joint_pos end constraint, given_traj init)."""
+    from trajopt_b200 import json_io
+    robot = robots.pr2_arm("r", with_spheres=True)
+    q0 = np.array([-1.832, -0.332, -1.011, -1.437, -1.1, -1.926, 3.074])
+    q1 = np.array([0.062, 1.287, 0.1, -1.554, -3.011, -0.268, 2.988])
+    traj = [list(q0 + (q1 - q0) * k / 5) for k in range(6)]
+    doc = {"basic_info": {"n_steps": 6, "manip": "right_arm", "fixed_timesteps": [0]},
+           "costs": [{"type": "joint_vel", "params": {"coeffs": [1], "targets": [0] * 7}},
+                     {"type": "collision", "params": {"coeffs": 20, "dist_pen": 0.025, "evaluator_type": 4, "fixed_steps": [0, 5],
+                                                      "longest_valid_segment_length": 0.2}}],
+           "constraints": [{"type": "joint_pos", "name": "joint0",
+                            "params": {"coeffs": [1] * 7, "targets": list(q1), "first_step": 5, "last_step": 5}}],
+           "init_info": {"type": "given_traj", "data": traj}}
+    obstacles = np.array([[[0.9, 0.4, 1.6, 0.05]]])  # one small sphere away from the arm
+    pd = json_io.from_json(doc, robot, q0[None], obstacles=obstacles)
+    r = oracle.solve_batch(pd)
+    assert r["status"][0] == capi.OPT_CONVERGED
+    np.testing.assert_allclose(r["x"][0, 0], q0, atol=1e-9)       # fixed_timesteps
+    np.testing.assert_allclose(r["x"][0, 5], q1, atol=1e-3)       # the joint_pos constraint
 
 
 @pytest.mark.parametrize("bad,msg", [
