@@ -13,6 +13,8 @@ MAX_DOF = 16
 
 # enums (include/trajopt_b200.h)
 JOINT_FIXED, JOINT_REVOLUTE, JOINT_PRISMATIC = 0, 1, 2
+# return codes of the C ABI (include/trajopt_b200.h)
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = range(5)
 TERM_JOINT_POS, TERM_JOINT_VEL, TERM_JOINT_ACC, TERM_CART_POSE, TERM_CART_VEL, TERM_COLLISION = range(6)
 ROLE_COST, ROLE_CNT = 1, 2
 COLL_DISCRETE, COLL_LVS_DISCRETE, COLL_CONTINUOUS, COLL_LVS_CONTINUOUS = 1, 2, 3, 4

@@ -145,11 +145,8 @@ void tb200_default_qp_settings(tb200_qp_settings* s) {  // osqp_interface.cpp:78
 int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem** out) {
   if (!d || !out) return fail(TB200_ERR_INVALID, "null argument");
   *out = nullptr;
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    return fail(TB200_ERR_NO_DEVICE, "no CUDA device: trajopt_b200 has no CPU fallback");
-  if (device < 0 || device >= ndev) return fail(TB200_ERR_INVALID, "bad device ordinal");
-  CK(cudaSetDevice(device));
+  // (the description is checked and flattened first - pure host work, so that a bad description gets the same
+  // error with or without a device - and only then the device is touched)
   const int T = d->n_steps, D = d->robot.n_dof, B = d->batch, N = T * D;
   if (T < 1 || T > TB200_MAX_STEPS) return fail(TB200_ERR_INVALID, "n_steps out of range");
   if (D < 1 || D > TB200_MAX_DOF) return fail(TB200_ERR_INVALID, "n_dof out of range");
@@ -486,6 +483,12 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   if (!solve_kernel_for(D, P->pair_rows) || !eval_kernel_for(D))
     return fail(TB200_ERR_UNSUPPORTED, P->pair_rows ? "no kernel instance with two-waypoint rows (CartVel, continuous collision) for this number of joints"
                                                     : "no kernel instance for this number of joints");
+  // ---- from here on the device is needed ---------------------------------------------------------------------
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(TB200_ERR_NO_DEVICE, "no CUDA device: trajopt_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(TB200_ERR_INVALID, "bad device ordinal");
+  CK(cudaSetDevice(device));
   CK(cudaFuncSetAttribute(eval_kernel_for(D), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->eval_smem)));
   P->solve_smem = std::max(P->qp_smem, P->eval_smem);  // the QP step and the evaluation step share one buffer
   CK(cudaFuncSetAttribute(solve_kernel_for(D, P->pair_rows), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->solve_smem)));
