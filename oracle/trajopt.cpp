@@ -422,8 +422,9 @@ struct CollisionEval {
 // the swept robot sphere of a (sub-)segment is the capsule between its two centres; contact with a static
 // obstacle sphere is closed form (closest point of the centre segment, parameter s clamped to [0,1]).
 //   * LVS: ||q1-q0|| > longest_valid_segment_length  =>  ceil(dist/lvs) sub-segments between linearly
-//     interpolated joint states (the reference's LinSpaced sub-trajectory, :1118-1155); here at most
-//     TB200_MAX_LVS_SEGMENTS (the reference is unbounded; the fixed candidate layout needs a bound).
+//     interpolated joint states (the reference's LinSpaced sub-trajectory, :1118-1155), unbounded as in the
+//     reference.  Only the DENSE row output (denseRows, the layout the CUDA path is compared in) has a fixed
+//     number of slots per (sphere, obstacle): `layout_sub`, sized by tb200inl_lvs_layout_segments.
 //     CONTINUOUS (evaluator 3) never subdivides (lvs = max double, problem_description.cpp:1782-1784).
 //   * cc_time of a contact in sub-segment i of n: (i + s)/n  (addInterpolatedCollisionResults [EXT]);
 //     type Time0 iff i == 0 and s == 0, Time1 iff i == n-1 and s == 1, else Between.
@@ -445,14 +446,14 @@ struct CastCollisionEval {
   int t, D;
   double margin, coeff, buffer, lvs;
   bool start_fixed, end_fixed;
+  int layout_sub;  // slots per (sphere, obstacle) of the dense row output
 
   int subSegments(const double* q0, const double* q1) const {
     double d2 = 0;
     for (int j = 0; j < D; ++j) d2 += (q1[j] - q0[j]) * (q1[j] - q0[j]);
     const double dist = std::sqrt(d2);
     if (!(dist > lvs)) return 1;
-    const double n = std::ceil(dist / lvs);
-    return n > TB200_MAX_LVS_SEGMENTS ? TB200_MAX_LVS_SEGMENTS : static_cast<int>(n);
+    return static_cast<int>(std::ceil(dist / lvs));
   }
   void sphereCentre(const std::vector<Pose>& fr, int s, double* c) const {
     const tb200_sphere& sp = robot->spheres[s];
@@ -465,7 +466,8 @@ struct CastCollisionEval {
     bool exists, active;
     CastContact ct;
   };
-  void candidates(const Vec& x, std::vector<Cand>& out) const {
+  // out: [sphere][obstacle][n] with n = the sub-segments of this step pair (returned)
+  int candidates(const Vec& x, std::vector<Cand>& out) const {
     const double* q0 = x.data() + t * D;
     const double* q1 = x.data() + (t + 1) * D;
     const int n = subSegments(q0, q1);
@@ -476,7 +478,7 @@ struct CastCollisionEval {
       for (int j = 0; j < D; ++j) u[j] = (i == n) ? q1[j] : q0[j] + (q1[j] - q0[j]) * (static_cast<double>(i) / n);
       robot->fk(u.data(), fr[i]);
     }
-    out.assign(static_cast<size_t>(L) * O * TB200_MAX_LVS_SEGMENTS, Cand{});
+    out.assign(static_cast<size_t>(L) * O * n, Cand{});
     std::vector<Pose> frt;
     std::vector<Vec> J;
     for (int s = 0; s < L; ++s) {
@@ -484,7 +486,7 @@ struct CastCollisionEval {
       for (int o = 0; o < O; ++o) {
         const double* ob = &obstacles[o * 4];
         for (int i = 0; i < n; ++i) {
-          Cand& cd = out[(static_cast<size_t>(s) * O + o) * TB200_MAX_LVS_SEGMENTS + i];
+          Cand& cd = out[(static_cast<size_t>(s) * O + o) * n + i];
           cd.exists = true;
           double ca[3], cb[3], w[3], ww = 0, wd = 0;
           sphereCentre(fr[i], s, ca);
@@ -532,6 +534,7 @@ struct CastCollisionEval {
         }
       }
     }
+    return n;
   }
   void distExpressions(const Vec& x, std::vector<AffExpr>& exprs) const {
     std::vector<Cand> cands;
@@ -555,11 +558,16 @@ struct CastCollisionEval {
       exprs.push_back(cleanupAff(e));
     }
   }
-  // fixed GPU layout: candidate (sphere, obstacle, sub) -> {g0[D], g1[D], dist0, margin, coeff | 0}
+  // fixed GPU layout: candidate (sphere, obstacle, slot < layout_sub) -> {g0[D], g1[D], dist0, margin, coeff | 0}
   void denseRows(const Vec& x, std::vector<Vec>& rows) const {
     std::vector<Cand> cands;
-    candidates(x, cands);
-    for (const Cand& cd : cands) {
+    const int n = candidates(x, cands);
+    if (n > layout_sub) throw std::runtime_error("oracle: step pair needs more LVS sub-segments than the dense layout holds");
+    const size_t pairs = cands.size() / n;
+    for (size_t pr = 0; pr < pairs; ++pr)
+    for (int slot = 0; slot < layout_sub; ++slot) {
+      const Cand none{};
+      const Cand& cd = (slot < n) ? cands[pr * n + slot] : none;
       Vec row(2 * D + 3, 0.0);
       if (cd.exists) {
         for (int j = 0; j < D; ++j) {
@@ -674,7 +682,22 @@ QPSettings qpSettingsFrom(const tb200_qp_settings& q) {
   return s;
 }
 
-TrajProblem buildProblem(const tb200_problem_desc& desc, int b) {
+int lvsLayout(const tb200_problem_desc& desc) {
+  int lay = 1;
+  for (int k = 0; k < desc.n_terms; ++k) {
+    const tb200_term& tm = desc.terms[k];
+    if (tm.kind != TB200_TERM_COLLISION || tm.evaluator_type == TB200_COLL_DISCRETE) continue;
+    const int l = tb200inl_lvs_layout_segments(&desc, &tm);
+    if (l <= 0) return 0;
+    lay = std::max(lay, l);
+  }
+  return lay;
+}
+
+TrajProblem buildProblem(const tb200_problem_desc& desc, int b, int lvs_layout) {
+  if (lvs_layout < 0) lvs_layout = lvsLayout(desc);
+  // lvs_layout == 0 (beyond TB200_MAX_LVS_LAYOUT): the SQP path below is unbounded like the reference's and still
+  // runs; only the dense row output (denseRows) has no layout then and throws when asked for.
   TrajProblem tp;
   tp.robot = std::make_shared<Robot>(desc.robot);
   const int T = desc.n_steps, D = desc.robot.n_dof;
@@ -892,7 +915,7 @@ TrajProblem buildProblem(const tb200_problem_desc& desc, int b) {
             }
             // (two adjacent fixed steps fall into the START_FIXED_END_FREE branch: the reference's throw is unreachable)
             CastCollisionEval e{tp.robot, obstacles, t, D, tm.margin, tm.coeff, tm.margin_buffer, lvs, cur_fixed,
-                                !cur_fixed && next_fixed};
+                                !cur_fixed && next_fixed, lvs_layout};
             tp.coll_hooks.push_back([e](const Vec& x, std::vector<Vec>& rows) { e.denseRows(x, rows); });
             if (is_cost) {
               auto c = std::make_shared<CollisionCost>(calcOf(e));

@@ -66,14 +66,39 @@ def test_fixed_timestep_outside_the_trajectory():
     assert rc == capi.ERR_INVALID and "Fixed timestep index is outside the bounds" in msg  # the reference's text
 
 
-def test_sizes_the_qp_step_does_not_hold_yet_are_refused_loudly():
-    rc, msg = _create(problems.config3(B=1, T=50))  # configs[3] at its full length
-    assert rc == capi.ERR_UNSUPPORTED and "trajectory too long" in msg
+def test_full_size_configs_pass_validation():
+    """configs[3] at its full length (50 waypoints: 25 factor blocks) and the 14-DOF dual arm of configs[4] (factor
+    blocks of 28, kept in global memory) are accepted: validation ends at the device check."""
     from trajopt_b200 import robots
+    ok = capi.ERR_NO_DEVICE if _no_device() else 0
+    rc, msg = _create(problems.config3(B=1, T=50))
+    assert rc == ok, (rc, msg)
     robot = robots.pr2_dual_arm()
     d = capi.ProblemDesc(robot, 10, [problems.joint_term(capi.TERM_JOINT_VEL, capi.ROLE_COST, 14, 0, 9)], np.zeros((1, 10, 14)))
     rc, msg = _create(d)
-    assert rc == capi.ERR_UNSUPPORTED  # 14-DOF dual arm (configs[4])
+    assert rc == ok, (rc, msg)
+
+
+def test_lvs_layout_beyond_the_limit_is_refused():
+    """A longest_valid_segment_length that needs more sub-segments per step pair than a layout can hold is refused at
+    problem_create (never truncated, collision_terms.cpp:1118-1155 is unbounded)."""
+    rc, msg = _create(problems.config3(B=1, T=12, via_every=4, lvs=1e-4))
+    assert rc == capi.ERR_UNSUPPORTED and "longest_valid_segment_length" in msg, (rc, msg)
+
+
+def test_null_arrays_with_positive_counts_are_refused():
+    d = problems.config2(B=1, T=10)
+    d.c.obstacles = None
+    rc, msg = _create(d)
+    assert rc == capi.ERR_INVALID and "obstacles is NULL" in msg, (rc, msg)
+    d = problems.config2(B=1, T=10)
+    d.c.cart_targets = None
+    rc, msg = _create(d)
+    assert rc == capi.ERR_INVALID and "cart_targets is NULL" in msg, (rc, msg)
+    d = problems.config2(B=1, T=10)
+    _set_term(d, 3, n_fixed_steps=9)
+    rc, msg = _create(d)
+    assert rc == capi.ERR_INVALID and "n_fixed_steps" in msg, (rc, msg)
 
 
 def test_mixing_discrete_and_continuous_collision_is_refused():

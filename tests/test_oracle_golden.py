@@ -310,17 +310,29 @@ def _cast_problem(lvs, T=6, B=3, seed=5):
     return problems.config3(B=B, T=T, seed=seed, via_every=2, lvs=lvs)
 
 
+def _lvs_layout(d, lvs):
+    """tb200inl_lvs_layout_segments (include/trajopt_b200.h): slots per (sphere, obstacle) of a step pair."""
+    step = np.linalg.norm(np.diff(d.init_traj, axis=1), axis=2)
+    need = max(1.0, np.ceil(step[step > lvs] / lvs).max(initial=1.0))
+    return int(max(4.0, np.ceil(1.5 * need) + 1.0))
+
+
 def test_cast_collision_layout_and_activity(oracle):
-    d = _cast_problem(0.05)
+    lvs = 0.25
+    d = _cast_problem(lvs)
     L = oracle.layout(d)
+    MS = _lvs_layout(d, lvs)
+    assert 4 < MS <= 32
     assert L.coll_row_stride == 2 * d.D + 3 and L.cart_jac_stride == 2 * d.D
-    assert L.n_coll_cand == (d.T - 1) * 7 * 8 * 4
+    assert L.n_coll_cand == (d.T - 1) * 7 * 8 * MS
     x = d.init_traj + 0.02 * np.random.default_rng(3).standard_normal(d.init_traj.shape)
     r = oracle.convexify_batch(d, x)
-    rows = r["coll_rows"].reshape(d.B, d.T - 1, 7 * 8, 4, 2 * d.D + 3)
-    # sub-segments beyond ceil(|dq| / lvs) do not exist: all-zero rows
-    nsub = np.minimum(np.ceil(np.linalg.norm(np.diff(x, axis=1), axis=2) / 0.05), 4)
-    nsub = np.where(np.linalg.norm(np.diff(x, axis=1), axis=2) > 0.05, nsub, 1)
+    rows = r["coll_rows"].reshape(d.B, d.T - 1, 7 * 8, MS, 2 * d.D + 3)
+    # sub-segments beyond ceil(|dq| / lvs) do not exist: all-zero rows (the count itself is unbounded, as in the
+    # reference: collision_terms.cpp:1118-1155)
+    step = np.linalg.norm(np.diff(x, axis=1), axis=2)
+    nsub = np.where(step > lvs, np.ceil(step / lvs), 1)
+    assert nsub.max() > 4  # more than the cap of 4 this layout used to have
     for b in range(d.B):
         for t in range(d.T - 1):
             assert (rows[b, t, :, int(nsub[b, t]):] == 0).all()
@@ -348,7 +360,7 @@ def test_cast_collision_gradient_is_a_distance_derivative(oracle):
         obst[b, 0, :3] = c + np.array([0.0, 0.0, 0.10 + robot["spheres"][5].radius + 0.015])
     d2 = capi.ProblemDesc(d.robot_spec, d.T, d.terms, x, fixed_timesteps=[0], cart_targets=d.cart_targets, obstacles=obst)
     r = oracle.convexify_batch(d2, x)
-    rows = r["coll_rows"].reshape(d.B, d.T - 1, 7, 8, 4, 2 * d.D + 3)
+    rows = r["coll_rows"].reshape(d.B, d.T - 1, 7, 8, 4, 2 * d.D + 3)  # (no subdivision: the minimum layout of 4 slots)
     row = rows[0, 1, 5, 0, 0]  # pair (1,2), sphere 5, obstacle 0, first sub-segment
     assert row[-1] != 0, "the contact must be active"
     eps = 1e-6

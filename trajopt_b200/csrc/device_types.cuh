@@ -33,7 +33,7 @@ enum ObjKind {
   OBJ_CART_VEL = 6,        // CartVel per step pair        kinematic_terms.cpp:368-425, problem_description.cpp:1011-1057
   OBJ_COLL_CAST = 7        // continuous (cast) collision per step pair  collision_terms.cpp:262-323, 468-538, 1071-1173
 };
-constexpr int kMaxLvsSegments = 4;  // = TB200_MAX_LVS_SEGMENTS (include/trajopt_b200.h)
+constexpr int kMaxLvsLayout = 32;  // = TB200_MAX_LVS_LAYOUT (include/trajopt_b200.h): upper limit of the per-problem bound
 struct DevObj {
   int kind;
   int is_cnt;     // 0 cost, 1 constraint
@@ -132,14 +132,12 @@ struct DevProblem {
   size_t list_stride;
   double* ws_x;                // [B][N]  warm start: previous QP solution (trajectory part, unscaled)
   double* ws_yb;               // [B][N]  warm start: duals of the variable-bound rows (unscaled)
-  double* scratch;             // [B][10*Np]: dx dy stash(x zb yb) | scaled q, lb, ub | Dz | v2
-  double* park;                // [B][4*Np]: x zb yb beta of a QP parked between time slices
-  double* park_factor;         // [B][3*M*nb*nb]: the block-cyclic-reduction factor of a parked QP
-  int* rs_int;                 // [B][4] parked solver state
-  double* rs_dbl;              // [B][4]
-  unsigned long long* rs_guess; // [B][2] parked active-set hashes (early polish)
+  double* scratch;             // [B][5*Np]: dx dy stash(x zb yb)
+  double* factor_g;            // [grid][3*M*nb*nb]: per-CTA home of a block-cyclic-reduction factor that does not fit
+                               // shared memory (14 joints: blocks of 28); stays L2 resident
+  int* lvs_overflow;           // [B] 1: a step pair needed more LVS sub-segments than the candidate layout holds
   int* qp_done;                // [B] 1: a QP solution is waiting for its evaluation
-  int* ws_meta;                // [B][8]: warm-start key (n_aux, rows, nnzA, last status), phase, parked sizes
+  int* ws_meta;                // [B][8]: warm-start key (n_aux, rows, nnzA, last status)
   double* ws_rho;              // [B]
   double* trace;               // [B][trace_cap][14] decision trace (same columns as the oracle's TraceEntry)
   int* trace_len;              // [B]

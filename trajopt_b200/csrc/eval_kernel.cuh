@@ -19,12 +19,12 @@ enum EvalMode { EVAL_INIT = 0, EVAL_STEP = 1, EVAL_ONLY = 2 };
 
 struct EvalSmem {
   // offsets in doubles into the dynamic shared buffer
-  int x, sph, spo, jax, cartf, velp, objv, mask, misc, fr, terms, obst, sphr, segs, sphs, cobj, aobj, wscr, wscr_stride, total;
+  int x, sph, spo, jax, velp, objv, mask, misc, fr, terms, obst, sphr, segs, sphs, cobj, aobj, wscr, wscr_stride, total;
 };
-// n_vel_objs: CartVel step pairs; cast: the collision objects are step pairs (continuous evaluator)
-__host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_cart_objs, int n_coll_objs,
-                                                      int n_mask_words, int S, int n_joint_objs, int n_vel_objs,
-                                                      int cast, int n_objs) {
+// n_vel_objs: CartVel step pairs; cast: the collision objects are step pairs (continuous evaluator) with at most
+// max_sub LVS sub-segments each
+__host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_coll_objs, int n_mask_words, int S,
+                                                      int n_joint_objs, int n_vel_objs, int cast, int max_sub, int n_objs) {
   EvalSmem s;
   int o = 0;
   s.x = o;      o += T * D;
@@ -38,7 +38,6 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   s.sphs = o;   o += L * static_cast<int>(sizeof(DevSphere) / 8);
   s.cobj = o;   o += n_coll_objs * static_cast<int>(sizeof(DevObj) / 8);   // the collision objects in kernel order
   s.aobj = o;   o += n_objs * static_cast<int>(sizeof(DevObj) / 8);        // every object: costs, then constraints
-  s.cartf = o;  o += n_cart_objs * (1 + D) * 12;
   s.velp = o;   o += n_vel_objs * 6;                  // link position at both waypoints of a CartVel pair
   s.objv = o;   o += n_coll_objs;                     // exact value of every collision object (in-order sums)
   s.mask = o;   o += n_mask_words;
@@ -46,14 +45,14 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   o += o & 1;
   // per-warp scratch of the cast collision objects: one set of frames, the sphere data of the interior
   // sub-segment states, one joint vector
-  s.wscr_stride = cast ? (S * 12 + (kMaxLvsSegments - 1) * L * 6 + ((D + 1) & ~1)) : 0;
+  s.wscr_stride = cast ? (S * 12 + (max_sub - 1) * L * 6 + ((D + 1) & ~1)) : 0;
   s.wscr = o;   o += 8 * s.wscr_stride;
   // the FK frames are dead once the joint axes / sphere centres are emitted: the term buffer of the later
   // phase reuses their space
   s.fr = o;                                           // frames of every FK job: local, then (in place) world
   s.terms = o;                                        // per-(step, joint) terms of the joint-space objects (later phase)
   // ... and, while the collision rows are written, the per-warp staging tiles of the bulk (TMA) row stores
-  const int a = (T + n_cart_objs * D) * S * 12, b2 = n_joint_objs * 2 * T * D;
+  const int a = T * S * 12, b2 = n_joint_objs * 2 * T * D;
   const int st = (((D + 3) & 1) == 0 && !cast) ? 8 * 32 * (D + 3) : 0;
   const int m = a > b2 ? a : b2;
   o += m > st ? m : st;
@@ -64,7 +63,10 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
 
 struct EvalExtra {
   int n_cart_objs, n_coll_objs, n_joint_objs, n_vel_objs;
-  int cast, pad;                     // cast: the collision objects are step pairs (continuous evaluator)
+  int cast, max_sub;                 // cast: the collision objects are step pairs (continuous evaluator), each with at
+                                     // most max_sub LVS sub-segments in the candidate layout
+  const int* link_chain;             // [S][kMaxSeg + 1]: per segment, the number of segments on its chain from the root,
+                                     // then the chain itself (root first, the segment last)
   const DevObj* vel_objs;            // CartVel step pairs
   int joint_seg[kMaxDof];            // segment that carries trajectory column j
   int joint_obj_idx[8];  // positions of the joint-space objects in the (costs, cnts) list
@@ -146,8 +148,8 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
   const bool qp_failed = (mode == EVAL_STEP) && (p.qp_status[b] != 0);
   if (tid == 0 && !qp_failed) atomicAdd(p.active_count + 1, 1);  // trajectories actually convexified (bench: bytes moved)
   const int n_mask_words = p.n_coll_objs * p.coll_words;
-  const EvalSmem S = eval_smem_layout(T, D, L, ex.n_cart_objs, p.n_coll_objs, n_mask_words, p.S, ex.n_joint_objs,
-                                      ex.n_vel_objs, ex.cast, p.n_costs + p.n_cnts);
+  const EvalSmem S = eval_smem_layout(T, D, L, p.n_coll_objs, n_mask_words, p.S, ex.n_joint_objs, ex.n_vel_objs,
+                                      ex.cast, ex.max_sub, p.n_costs + p.n_cnts);
   static_assert(sizeof(DevObj) % 8 == 0 && sizeof(DevSegment) % 8 == 0 && sizeof(DevSphere) % 8 == 0, "tables are copied as doubles");
   const DevObj* cobjs = reinterpret_cast<const DevObj*>(sm + S.cobj);
   const DevObj* aobjs = reinterpret_cast<const DevObj*>(sm + S.aobj);
@@ -190,25 +192,18 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
     __syncthreads();
     EVAL_PROF(1);
 
-    // ---- FK: one job per waypoint, plus D perturbed configurations per CartPose object ---------------
+    // ---- FK: one job per waypoint (the perturbed states of the CartPose objects are handled by their own warps) ---
     // (1) local frames of every (job, segment) in parallel (this is where the sincos are), (2) the chain
     // products, one lane per (job, frame row): row i of a world frame depends only on row i of the parent's,
     // so the three lanes of a job never wait for each other, (3) emission of what the row writers need.
-    const int n_jobs = T + ex.n_cart_objs * D, Sg = p.S;
+    const int n_jobs = T, Sg = p.S;
     double* FR = sm + S.fr;
     const DevSegment* segs = reinterpret_cast<const DevSegment*>(sm + S.segs);
     const DevSphere* sphs = reinterpret_cast<const DevSphere*>(sm + S.sphs);
     for (int w = tid; w < n_jobs * Sg; w += kEvalThreads) {
       const int job = w / Sg, sg = w % Sg;
       const DevSegment& g = segs[sg];
-      double qv = 0.0;
-      if (g.q_index >= 0) {
-        if (job < T) qv = xs[job * D + g.q_index];
-        else {
-          const int c = (job - T) / D, i = (job - T) % D;
-          qv = xs[ex.cart_objs[c].first * D + g.q_index] + (g.q_index == i ? 1e-5 : 0.0);  // DEFAULT_EPSILON, kinematic_terms.hpp:14
-        }
-      }
+      const double qv = (g.q_index >= 0) ? xs[job * D + g.q_index] : 0.0;
       Frame loc;
       segment_local_q(g, qv, loc);
       double* f = FR + static_cast<size_t>(w) * 12;
@@ -292,19 +287,15 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
       const DevObj& o = ex.vel_objs[c];
       sm[S.velp + w] = FR[(static_cast<size_t>(o.first + k) * Sg + o.link) * 12 + 9 + i];
     }
-    for (int w = tid; w < ex.n_cart_objs * (1 + D) * 12; w += kEvalThreads) {
-      const int c = w / ((1 + D) * 12), col = (w / 12) % (1 + D), k = w % 12;
-      const DevObj& o = ex.cart_objs[c];
-      const int job = (col == 0) ? o.first : T + c * D + (col - 1);
-      sm[S.cartf + w] = FR[(static_cast<size_t>(job) * Sg + o.link) * 12 + k];
-    }
     __syncthreads();
     EVAL_PROF(4);
 
     // ---- CartPose rows: error + forward-difference Jacobian (kinematic_terms.cpp:250-263, 348-366) ----
-    // One warp per CartPose object, lane 0 the unperturbed frame, lane 1+i the frame at q + eps e_i: every lane runs
-    // the pose-error pipeline ONCE (it is a long dependent chain of fp64 divisions, square roots and an atan2); the
-    // base error reaches the difference quotients by shuffle.
+    // One warp per CartPose object, lane 0 the unperturbed state, lane 1+i the state q + eps e_i (DEFAULT_EPSILON,
+    // kinematic_terms.hpp:14).  Every lane runs the FK of ITS state along the link's chain in registers (same products
+    // in the same order as the waypoint FK above) and then the pose-error pipeline ONCE (a long dependent chain of fp64
+    // divisions, square roots and an atan2); the base error reaches the difference quotients by shuffle.  No shared
+    // memory per object, so a problem may carry any number of them (configs[4]: two per waypoint).
     for (int c = tid >> 5; c < ex.n_cart_objs; c += kEvalThreads / 32) {
       const int col = tid & 31;  // col 0 = error, col 1+i = Jacobian column i
       const bool work = col < 1 + D;
@@ -314,9 +305,23 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
       quat_to_frame(o.target_slot >= 0 ? p.cart_targets + (static_cast<size_t>(b) * p.n_cart_targets + o.target_slot) * 7 : ct.tgt, tgt);
       for (int i = 0; i < 9; ++i) off.R[i] = ct.src_R[i];
       for (int i = 0; i < 3; ++i) off.p[i] = ct.src_p[i];
-      const double* f1 = sm + S.cartf + (c * (1 + D) + (work ? col : 0)) * 12;
-      for (int i = 0; i < 9; ++i) lf.R[i] = f1[i];
-      for (int i = 0; i < 3; ++i) lf.p[i] = f1[9 + i];
+      {
+        const int* chain = ex.link_chain + o.link * (kMaxSeg + 1);
+        const int clen = chain[0], pj = work ? col - 1 : -1;
+        const double* qw = xs + o.first * D;
+        for (int k = 0; k < clen; ++k) {
+          const DevSegment& g = segs[chain[1 + k]];
+          const double qv = (g.q_index >= 0) ? qw[g.q_index] + (g.q_index == pj ? 1e-5 : 0.0) : 0.0;
+          Frame loc;
+          segment_local_q(g, qv, loc);
+          if (k == 0) lf = loc;
+          else {
+            Frame nx;
+            frame_mul(lf, loc, nx);
+            lf = nx;
+          }
+        }
+      }
       frame_mul(lf, off, src);
       rel_pose(tgt, src, e1);
       double a1[3], g1;
@@ -470,7 +475,10 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
         // 1071-1173 with the closed-form swept sphere (capsule) of SURVEY.md section 8d; the same rules as the oracle's
         // CastCollisionEval.  candidate = (robot sphere, obstacle, sub-segment); row = {g0[D], g1[D], dist, margin,
         // coeff|0}.  The gradients need one FK per ACTIVE contact (at its own contact-time state), done by the warp.
-        constexpr int MS = kMaxLvsSegments;
+        // MS sub-segments fit the candidate layout (sized at tb200_problem_create from the initial trajectories); a
+        // step pair that needs more raises the trajectory's overflow flag and the solve reports it (never truncated
+        // silently: the reference's sub-trajectory is unbounded, collision_terms.cpp:1118-1155).
+        const int MS = ex.max_sub;
         const bool sfix = co.pad1 & 1, efix = co.pad1 & 2;
         const double* q0 = xs + t * D;
         const double* q1 = q0 + D;
@@ -481,7 +489,12 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
         int nsub = 1;
         if (qd > co.lvs) {
           const double nn = ceil(qd / co.lvs);
-          nsub = nn > MS ? MS : static_cast<int>(nn);
+          if (nn > MS) {
+            if (lane_c == 0) p.lvs_overflow[b] = 1;
+            nsub = MS;
+          } else {
+            nsub = static_cast<int>(nn);
+          }
         }
         double* F = sm + S.wscr + (tid >> 5) * S.wscr_stride;  // frames of one state
         double* sub = F + p.S * 12;                             // [MS-1][L][6]: centre, centre - link origin
@@ -670,7 +683,12 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
     double trust = p.trust[b];
     int accept = 0, finished = 0, status = 5;
     enum { NEXT_QP = 0, AFTER_LOOP = 1, PENALTY = 2 } go = NEXT_QP;
-    if (mode == EVAL_INIT) {
+    if (ex.cast && p.lvs_overflow[b]) {
+      // a step pair needed more LVS sub-segments than the candidate layout holds: the trajectory stops here and
+      // tb200_solve_batch reports TB200_ERR_UNSUPPORTED (the layout is never truncated silently)
+      status = 4;  // OPT_FAILED
+      finished = 1;
+    } else if (mode == EVAL_INIT) {
       p.n_func_evals[b] = 1;
       accept = 2;  // rows of buffer 0 are the rows at x
     } else {
@@ -800,7 +818,7 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
 // Stand-alone launch, one CTA per trajectory: the initial evaluation of a solve (EVAL_INIT) and the kernel-level
 // convexify entry point (EVAL_ONLY).  Inside a solve the same code runs as a step of solve_kernel.cuh.
 template <int DD>
-__global__ void __launch_bounds__(kEvalThreads, TB200_EVAL_MIN_BLOCKS)
+__global__ void __launch_bounds__(kEvalThreads, (DD <= 8) ? TB200_EVAL_MIN_BLOCKS : 2)
 eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double* x_in /*EVAL_ONLY*/) {
   eval_step<DD>(p, ex, mode, blockIdx.x, x_in);
 }

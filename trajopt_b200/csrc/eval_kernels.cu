@@ -11,6 +11,7 @@ EvalKernelFn eval_kernel_for(int D) {
     case 3: return eval_convexify_decide_kernel<3>;
     case 6: return eval_convexify_decide_kernel<6>;
     case 7: return eval_convexify_decide_kernel<7>;
+    case 14: return eval_convexify_decide_kernel<14>;
     default: return nullptr;
   }
 }

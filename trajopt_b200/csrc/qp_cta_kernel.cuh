@@ -20,9 +20,14 @@
 // Everything an ADMM iteration touches is in shared memory: the factor (3 x M x nb x nb), the trajectory
 // vectors, and - when the QP has at most `row_cap` rows, the common case - the rows of the QP themselves.
 // The hinge / abs auxiliary variables of the l1 penalty are eliminated per row in closed form (cancellation
-// free), exactly as in DESIGN.md §4.2.  (The `slice` argument and the park / resume path belong to the earlier
-// lock-step launch design - a solve that ran out of its slice parked its state in HBM; the persistent kernel passes
-// an unbounded slice, so a QP always runs to its end in one call.)
+// free), exactly as in DESIGN.md §4.2.
+//
+// Sizes.  The level loops of the factorisation and of the generic solve run over task chunks, so the number of
+// blocks M is not tied to the CTA size (configs[3]: 50 waypoints = 25 blocks of 14).  The register-resident solve of
+// the ADMM loop is used whenever its roles fit the 256 threads (M <= 15 at 7 joints), the generic solve (factor rows
+// read from memory) otherwise.  With 14 joints (blocks of 28, configs[4]) the factor (3*M*28*28 doubles = 376 KB at
+// 40 waypoints) does not fit shared memory: it lives in a per-CTA region of global memory that stays L2 resident
+// (template flag FG), everything else is unchanged.
 #pragma once
 #include "device_types.cuh"
 #include "joint_terms.cuh"
@@ -39,13 +44,14 @@ static __device__ unsigned long long g_prof[16];
 #endif
 
 constexpr int kQpThreads = 256;
+constexpr int kQpThreadsC = 256;  // (usable in __host__ __device__ constant expressions)
 constexpr double kOsqpInf = 1e30;
 constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4;
 constexpr double kVerifyTol = 1e-9;  // KKT verification of the polished point (deviation D2)
 constexpr int kVerifyRounds = 3;
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoTol = 1e-4, kRhoEqOverIneq = 1e3;
 enum { QPS_UNSOLVED = 0, QPS_SOLVED = 1, QPS_SOLVED_INACC = 2, QPS_PINF = 3, QPS_PINF_INACC = 4, QPS_DINF = 5,
-       QPS_DINF_INACC = 6, QPS_MAXITER = 7, QPS_NONCVX = 8, QPS_YIELD = 100 };
+       QPS_DINF_INACC = 6, QPS_MAXITER = 7, QPS_NONCVX = 8 };
 
 __device__ __forceinline__ double limit_scaling(double v) {
   v = v < kMinScaling ? 1.0 : v;
@@ -57,17 +63,16 @@ __device__ __forceinline__ double limit_scaling(double v) {
 // level is being eliminated the still unused slot of the left survivor holds a temporary).
 struct QpSmem {
   int SA, SLM, SU, beta, x, zb, yb, v1, w, qs, lbs, ubs, Dz, v2, Pb, tmp, red, colptr, colent, rints, rows, total, row_cap;
+  int factor_smem, pband_smem;  // 1: lives in shared memory; 0: in global memory (factor: per-CTA region, band: the shared table)
 };
-constexpr int kQpSmemBudget = 20000;  // doubles per CTA (160 KB): one CTA per SM, the registers hold the factor rows
+constexpr int kQpSmemBudget = 28800;  // doubles per CTA (225 KB of the 227 KB a CTA may use): one CTA per SM
 __host__ __device__ inline int qp_block_count(int N, int nb) { return (N + nb - 1) / nb; }
 __host__ __device__ inline int qp_even(int v) { return (v + 1) & ~1; }
-__host__ __device__ inline QpSmem qp_smem_layout(int N, int nb, int row_stride, int CN, int max_rows) {
+__host__ __device__ inline int qp_factor_doubles(int N, int nb) { return 3 * qp_even(qp_block_count(N, nb) * nb * nb); }
+__host__ __device__ inline QpSmem qp_smem_layout(int N, int nb, int row_stride, int CN, int max_rows, bool factor_global) {
   const int M = qp_block_count(N, nb), Np = M * nb, blk = nb * nb;
   QpSmem s;
   int o = 0;
-  s.SA = o;   o += qp_even(M * blk);
-  s.SLM = o;  o += qp_even(M * blk);
-  s.SU = o;   o += qp_even(M * blk);
   s.beta = o; o += qp_even(Np);
   s.x = o;    o += qp_even(Np);
   s.zb = o;   o += qp_even(Np);
@@ -79,12 +84,17 @@ __host__ __device__ inline QpSmem qp_smem_layout(int N, int nb, int row_stride, 
   s.ubs = o;  o += qp_even(Np);
   s.Dz = o;   o += qp_even(Np);
   s.v2 = o;   o += qp_even(Np);
-  s.Pb = o;   o += qp_even(N * (nb + 1));  // the objective's band P(i, i-k), shared by every trajectory
-  s.tmp = o;  o += qp_even((M + 1) / 2 * 2 * nb) + 8;  // Gauss-Jordan pivot rows / columns, 8 scalars at the end
+  s.tmp = o;  o += 2 * kQpThreadsC + 8;               // Gauss-Jordan pivot rows of one task chunk, 8 scalars at the end
   s.red = o;  o += 16 * 8;                            // block reductions: 16 quantities x 8 warps
   s.colptr = o; o += qp_even((Np + 2) / 2 + 1);
-  // whatever is left of the two-CTAs-per-SM budget holds rows: record + column entries + row ints
-  const int per_row2 = 2 * row_stride + CN + RI_NINTS;  // in half doubles
+  // the factor (SA, SLM, SU contiguous) when it fits, then the objective's band P(i, i-k), then rows with what is left
+  s.factor_smem = (!factor_global && o + 3 * qp_even(M * blk) <= kQpSmemBudget) ? 1 : 0;
+  s.SA = o;   o += s.factor_smem ? qp_even(M * blk) : 0;
+  s.SLM = o;  o += s.factor_smem ? qp_even(M * blk) : 0;
+  s.SU = o;   o += s.factor_smem ? qp_even(M * blk) : 0;
+  s.pband_smem = (o + qp_even(N * (nb + 1)) <= kQpSmemBudget) ? 1 : 0;
+  s.Pb = o;   o += s.pband_smem ? qp_even(N * (nb + 1)) : 0;
+  const int per_row2 = 2 * row_stride + CN + RI_NINTS;  // in half doubles: record + column entries + row ints
   int cap = (o < kQpSmemBudget) ? 2 * (kQpSmemBudget - o) / per_row2 - 1 : 0;
   cap = cap > max_rows ? max_rows : cap;
   cap = cap > 1023 ? 1023 : cap;
@@ -223,23 +233,25 @@ __device__ __forceinline__ void row_times_matT(double (&out)[NB], const double (
 template <int NB>
 __device__ inline bool bcr_factor(const QpCtx& q) {
   constexpr int BLK = NB * NB, G = kQpThreads / 2;  // two thread groups work side by side where possible
+  constexpr int CH1 = kQpThreads / NB, CH2 = G / NB;  // blocks per task chunk: inversion (all threads) / products (per group)
   const int M = q.M, tid = q.tid;
   const int grp = tid >= G, gt = tid - (grp ? G : 0);
   int bad = 0;
   for (int l = 0; (1 << l) - 1 < M; ++l) {
     const int s = 1 << l, first = s - 1, sh = l + 1;  // eliminated p = first + (e << sh); survivors j = p + s
-    const int nE = (M + s) >> sh, nS = M >> sh;       // host guarantees nE * NB <= G
+    const int nE = (M + s) >> sh, nS = M >> sh;
     // ---- 1. Ainv_p in place: Gauss-Jordan without pivoting (the blocks are symmetric positive definite);
     //         thread (e,i) keeps row i of block e in registers, the pivot row goes through shared memory
-    {
-      const bool act = tid < nE * NB;
+    for (int e0 = 0; e0 < nE; e0 += CH1) {
+      const int nc = (nE - e0 < CH1) ? nE - e0 : CH1;
+      const bool act = tid < nc * NB;
       const int e = act ? tid / NB : 0, i = tid % NB;
-      double* A = q.SA + (first + (e << sh)) * BLK + i * NB;
+      double* A = q.SA + (first + ((e0 + e) << sh)) * BLK + i * NB;
       double a[NB];
       load_row<NB>(a, A);
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
-        double* prow = q.tmp + (k & 1) * (nE * NB) + e * NB;
+        double* prow = q.tmp + (k & 1) * (CH1 * NB) + e * NB;
         if (act && i == k) {
           const double piv = a[k];
           if (!(piv > 0.0)) bad = 1;
@@ -261,9 +273,10 @@ __device__ inline bool bcr_factor(const QpCtx& q) {
     }
     __syncthreads();
     // ---- 2. group 0: Up_p = L_{p+s} Ainv_p -> SU[p];  group 1: Um_p = L_p' Ainv_p -> SU[p-s] (temporary home)
-    {
-      const bool act = gt < nE * NB;
-      const int e = act ? gt / NB : 0, i = gt % NB;
+    for (int e0 = 0; e0 < nE; e0 += CH2) {
+      const int nc = (nE - e0 < CH2) ? nE - e0 : CH2;
+      const bool act = gt < nc * NB;
+      const int e = e0 + (act ? gt / NB : 0), i = gt % NB;
       const int p = first + (e << sh);
       const double* Ai = q.SA + p * BLK;
       if (act && grp == 0 && p + s < M) {
@@ -287,10 +300,12 @@ __device__ inline bool bcr_factor(const QpCtx& q) {
     }
     __syncthreads();
     // ---- 3./4. survivors j = p + s.  group 0: A_j -= Up_{j-s} L_j', and L'_j = -Up_{j-s} L_{j-s} (kept in registers);
-    //            group 1: t2 = Um_{j+s} L_{j+s} (Um_{j+s} sits in SU[j]), subtracted from A_j after the barrier
-    {
-      const bool act = gt < nS * NB;
-      const int e = act ? gt / NB : 0, i = gt % NB;
+    //            group 1: t2 = Um_{j+s} L_{j+s} (Um_{j+s} sits in SU[j]), subtracted from A_j after the barrier.
+    //            (A chunk only writes blocks of its own survivors, which no other chunk reads: no barrier between chunks.)
+    for (int e0 = 0; e0 < nS; e0 += CH2) {
+      const int nc = (nS - e0 < CH2) ? nS - e0 : CH2;
+      const bool act = gt < nc * NB;
+      const int e = e0 + (act ? gt / NB : 0), i = gt % NB;
       const int j = first + s + (e << sh), p = j - s;
       double keep[NB];
 #pragma unroll
@@ -730,13 +745,6 @@ struct QpOut {
   int pol_factor_ok, rho_updates, rounds;
 };
 
-// Persistent solver state of one QP between time slices.
-struct QpResume {
-  int iter, round, rho_updates, status, guess_flags;  // guess_flags: bit 0 prev_guess valid, bit 1 failed_guess valid
-  double rho, eps_scale, c;
-  unsigned long long prev_guess, failed_guess;      // active-set hashes of optimisation O1
-};
-
 // Scatter pass: v1[i] = base(i) + sum over the column entries of as[k] * R_COEF(row).
 template <int CN, class Base>
 __device__ __forceinline__ void scatter_columns(const QpCtx& q, Base base) {
@@ -906,13 +914,12 @@ __device__ inline void qp_scale(QpCtx& q, const QpSettings& st, int n_aux_total)
   __syncthreads();
 }
 
-// The QP solve for the calling CTA's trajectory.  `fresh`: start a new solve (initial iterate from the warm
-// start or zero); otherwise resume from `rs`.  Returns status QPS_YIELD when the slice budget ran out.
+// The QP solve for the calling CTA's trajectory (initial iterate from the warm start or zero).
 // Every scalar that steers control flow is derived from block-reduced values, so all threads take the same path.
-template <int NB, int PAIR>
-__device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fresh, bool warm, double warm_rho,
-                                       const double* ws_x, const double* ws_yb, QpResume& rs, int slice,
-                                       bool have_factor) {
+// REGOK: the register-resident solve may be used (its per-thread factor rows fit the register file: blocks of <= 14).
+template <int NB, int PAIR, bool REGOK>
+__device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm, double warm_rho,
+                                       const double* ws_x, const double* ws_yb) {
   // coefficients per (padded) row: D, or 2*D when rows may span two consecutive waypoints (CartVel, cast collision)
   constexpr int CNc = PAIR ? ((NB > 3) ? NB : 3) : ((NB / 2 > 3) ? NB / 2 : 3);
   const int N = q.N, tid = q.tid;
@@ -922,7 +929,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
   int iter, round;
   q.sigma = st.sigma;
   q.alpha = st.alpha;
-  if (fresh) {
+  {
     rho = warm ? warm_rho : st.rho;
     rho = fmin(fmax(rho, kRhoMin), kRhoMax);
     eps_scale = 1.0;
@@ -962,23 +969,30 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
       }
     }
     __syncthreads();
-  } else {
-    rho = rs.rho;
-    eps_scale = rs.eps_scale;
-    iter = rs.iter;
-    round = rs.round;
-    out.rho_updates = rs.rho_updates;
-    q.rho = rho;
-    q.rho_eq = kRhoEqOverIneq * rho;
   }
   SysW sysw{false, st.sigma, rho};
   bool factor_ok = true;
-  { PROF_T0(); if (!have_factor) factor_ok = assemble_factor<NB>(q, sysw); PROF_ADD(6); }
-  // the thread's rows of the ADMM factor, kept in registers between refactorisations
-  const SolveRoles roles = solve_roles<NB>(q);
-  const int my_e0 = (tid < N) ? q.colptr[tid] : 0, my_e1 = (tid < N) ? q.colptr[tid + 1] : 0;
-  double mF0[NB], mB0[NB + NB / 2], mFU[NB], mBU[NB + NB / 2];
+  { PROF_T0(); factor_ok = assemble_factor<NB>(q, sysw); PROF_ADD(6); }
+  // the thread's rows of the ADMM factor, kept in registers between refactorisations (when the roles fit the CTA)
+  const bool use_reg = REGOK && solve_roles_fit(q.M, NB);
+  constexpr int RNB = REGOK ? NB : 2;  // (no register rows in instances that never use them)
+  const SolveRoles roles = use_reg ? solve_roles<NB>(q) : SolveRoles{};
+  const bool one_var = q.Np <= kQpThreads;  // one thread per variable: its column range is loop invariant
+  const int my_e0 = (one_var && tid < N) ? q.colptr[tid] : 0, my_e1 = (one_var && tid < N) ? q.colptr[tid + 1] : 0;
+  double mF0[RNB], mB0[RNB + RNB / 2], mFU[RNB], mBU[RNB + RNB / 2];
+  auto solve_sys = [&](double* v, double* w) {  // K w = v with the current factor (v is overwritten)
+    if constexpr (REGOK) {
+      if (use_reg) {
+        bcr_solve_reg<NB>(q, roles, mF0, mB0, mFU, mBU, v, w);
+        return;
+      }
+    }
+    bcr_solve<NB>(q, v, w);
+  };
   auto load_factor_regs = [&]() {
+    if constexpr (!REGOK) return;
+    else {
+    if (!use_reg) return;
     load_fwd_row<NB>(q, 0, tid, mF0);
     load_bwd_row<NB>(q, 0, tid, mB0);
     int off = 0;
@@ -993,7 +1007,8 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
       if (roles.bu_level == l) load_bwd_row<NB>(q, l, tid - off, mBU);
       off += cnt;
     }
-  };  // a resumed solve brings its factor
+    }
+  };
 
   double* dxs = q.scratch;              // [Np] last trajectory step (written on check iterations)
   double* dyb = q.scratch + q.Np;       // [Np] last dual step of the variable-bound rows
@@ -1001,10 +1016,10 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
   double* st_zb = q.scratch + 3 * q.Np;
   double* st_yb = q.scratch + 4 * q.Np;
   double pri_res = 0.0, dua_res = 0.0;
-  int status = factor_ok ? QPS_UNSOLVED : QPS_NONCVX, budget = slice;
+  int status = factor_ok ? QPS_UNSOLVED : QPS_NONCVX;
   bool early_verified = false;
-  unsigned long long prev_guess = fresh ? 0ull : rs.prev_guess, failed_guess = fresh ? 0ull : rs.failed_guess, pending_guess = 0ull;
-  bool have_prev_guess = fresh ? false : (rs.guess_flags & 1), have_failed_guess = fresh ? false : (rs.guess_flags & 2);
+  unsigned long long prev_guess = 0ull, failed_guess = 0ull, pending_guess = 0ull;
+  bool have_prev_guess = false, have_failed_guess = false;
   double n_z = 0, n_ax = 0, n_q = 0, n_aty = 0, n_px = 0, s_pri = 0, s_dua = 0, s_z = 0, s_ax = 0, s_q = 0, s_aty = 0, s_px = 0;
 
   // ---------------------------------------------------------------- update_info(): residuals and norms
@@ -1193,7 +1208,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
   auto admm_iteration = [&](bool keep_steps) {
     // right-hand side  sigma x - q + A'(rho z - y)  (one thread per variable)
     { PROF_T0();
-    {  // one thread per variable (N <= 256): its column range is loop invariant, the rows left their terms behind
+    if (one_var) {  // one thread per variable: its column range is loop invariant, the rows left their terms behind
       const int i = tid;
       double s = 0.0;
       if (i < N) {
@@ -1205,10 +1220,23 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
         }
       }
       if (i < q.Np) q.v1[i] = s;
+    } else {
+      for (int i = tid; i < q.Np; i += kQpThreads) {
+        double s = 0.0;
+        if (i < N) {
+          const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
+          s = q.sigma * q.x[i] - q.qs[i] + q.beta[i] * (rb * q.zb[i] - q.yb[i]);
+          for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
+            const int ent = q.colent[e];
+            s += q.rows[static_cast<size_t>(ent >> 5) * q.RS + (2 * CNc + R_NF) + (ent & 31)];
+          }
+        }
+        q.v1[i] = s;
+      }
     }
     PROF_ADD(1); }
     { PROF_T0();
-    bcr_solve_reg<NB>(q, roles, mF0, mB0, mFU, mBU, q.v1, q.w);
+    solve_sys(q.v1, q.w);
     PROF_ADD(2); }
     PROF_T0();
     // rows: back-substitute aux, relax, project, dual update, and the multipliers for the next solve
@@ -1326,8 +1354,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
     return stable && !(have_failed_guess && h == failed_guess);
   };
 
-  // ADMM iterations, continuing from the current state until a termination test fires, max_iter, or the
-  // slice budget is exhausted (status QPS_YIELD).
+  // ADMM iterations, continuing from the current state until a termination test fires or max_iter is reached.
   auto run_admm = [&](auto& polish_fn, auto& restore_fn) {
     status = QPS_UNSOLVED;
     bool stop = false, need_coef = true, need_regs = true;
@@ -1337,11 +1364,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
         status = check_termination(true);
         if (status == QPS_UNSOLVED) status = QPS_MAXITER;
         stop = true;
-      } else if (budget <= 0) {
-        status = QPS_YIELD;
-        stop = true;
       } else {
-        --budget;
         ++iter;
         const bool can_check = st.check_termination > 0 && (iter % st.check_termination == 0);
         const bool rho_iter = st.adaptive_rho && st.adaptive_rho_interval > 0 && (iter % st.adaptive_rho_interval == 0);
@@ -1525,7 +1548,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
         p_dua = mm[1] * q.cinv;
         verified = (mm[2] == 0.0) && (p_pri <= kVerifyTol) && isfinite(p_pri) && isfinite(p_dua);
       } else {
-        bcr_solve_reg<NB>(q, roles, mF0, mB0, mFU, mBU, q.v1, q.w);
+        solve_sys(q.v1, q.w);
         for (int r = tid; r < q.nrows; r += kQpThreads) {
           const double* R = q.R(r);
           double* F = q.F(r);
@@ -1604,15 +1627,6 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
   out.status = status;
   out.rho = rho;
   out.c = q.c;
-  rs.iter = iter;
-  rs.round = round;
-  rs.rho = rho;
-  rs.eps_scale = eps_scale;
-  rs.rho_updates = out.rho_updates;
-  rs.c = q.c;
-  rs.prev_guess = prev_guess;
-  rs.failed_guess = failed_guess;
-  rs.guess_flags = (have_prev_guess ? 1 : 0) | (have_failed_guess ? 2 : 0);
   if (out.polish != 0) {
     // Adopt the polished PRIMAL point when accepted.  The duals kept for the next warm start are always the
     // ADMM duals: polished duals are non-unique on degenerate active sets (DESIGN.md deviation D1).
@@ -1632,8 +1646,9 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool fres
 // calling CTA (256 threads).  DD = degrees of freedom (block size NB = 2*DD); PAIR: rows may span two waypoints.
 template <int DD, int PAIR>
 __device__ __forceinline__ void qp_step(const DevProblem& p, const int b, const double* x_override /*kernel-level API*/,
-                                        const double* trust_override, int* admm_iters_out, int* polish_out, int slice) {
+                                        const double* trust_override, int* admm_iters_out, int* polish_out) {
   constexpr int NB = 2 * DD;
+  constexpr bool FG = DD > 8;  // blocks of more than 16: the factor lives in this CTA's region of global memory
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
   if (!x_override && (p.status[b] != 5 || p.qp_done[b] != 0)) return;  // finished, or waiting for its evaluation
@@ -1645,8 +1660,15 @@ __device__ __forceinline__ void qp_step(const DevProblem& p, const int b, const 
   q.Np = q.M * NB;
   q.CN = (p.row_stride - R_NF) / 3;
   q.RS = p.row_stride;
-  const QpSmem S = qp_smem_layout(N, NB, q.RS, q.CN, p.max_rows);
-  q.SA = sm + S.SA; q.SLM = sm + S.SLM; q.SU = sm + S.SU; q.beta = sm + S.beta;
+  const QpSmem S = qp_smem_layout(N, NB, q.RS, q.CN, p.max_rows, FG);
+  if (FG || !S.factor_smem) {  // (a factor of <= 16-wide blocks that does not fit shared memory goes the same way)
+    double* fg = p.factor_g + static_cast<size_t>(blockIdx.x) * qp_factor_doubles(N, NB);
+    const int fb = qp_even(q.M * NB * NB);
+    q.SA = fg; q.SLM = fg + fb; q.SU = fg + 2 * fb;
+  } else {
+    q.SA = sm + S.SA; q.SLM = sm + S.SLM; q.SU = sm + S.SU;
+  }
+  q.beta = sm + S.beta;
   q.x = sm + S.x; q.zb = sm + S.zb; q.yb = sm + S.yb; q.v1 = sm + S.v1; q.w = sm + S.w;
   q.qs = sm + S.qs; q.lbs = sm + S.lbs; q.ubs = sm + S.ubs; q.tmp = sm + S.tmp; q.red = sm + S.red;
   q.flag = sm + S.red - 8;
@@ -1660,28 +1682,25 @@ __device__ __forceinline__ void qp_step(const DevProblem& p, const int b, const 
   int* colent = mylist + q.Np + 1;                        // [max_rows*CN]
   int* obj_start = colent + static_cast<size_t>(p.max_rows) * q.CN;  // [n_objs+1]
   q.colent = colent;
-  q.Pband = sm + S.Pb;
-  for (int t = tid; t < N * (NB + 1); t += kQpThreads) sm[S.Pb + t] = p.Pband[t];
-  // per-trajectory global vectors: dxs dyb st_x st_zb st_yb | scaled qs lbs ubs (master) | Dz | v2
-  double* gvec = p.scratch + static_cast<size_t>(b) * 10 * q.Np;
+  if (S.pband_smem) {
+    q.Pband = sm + S.Pb;
+    for (int t = tid; t < N * (NB + 1); t += kQpThreads) sm[S.Pb + t] = p.Pband[t];
+  } else {
+    q.Pband = p.Pband;  // long trajectories: the band stays in (L2-resident) global memory
+  }
+  // per-trajectory global vectors: dxs dyb st_x st_zb st_yb (the ADMM state stashed while the polish runs)
+  double* gvec = p.scratch + static_cast<size_t>(b) * 5 * q.Np;
   q.scratch = gvec;
-  double* g_qs = gvec + 5 * q.Np;
-  double* g_lbs = gvec + 6 * q.Np;
-  double* g_ubs = gvec + 7 * q.Np;
   q.Dz = sm + S.Dz;
-  double* g_Dz = gvec + 8 * q.Np;  // master copy for the resume path
   q.v2 = sm + S.v2;
-  double* park = p.park + static_cast<size_t>(b) * 4 * q.Np;     // x zb yb beta of a parked solve
   double *qs = q.qs, *lbs = q.lbs, *ubs = q.ubs;
-  int* meta = p.ws_meta + static_cast<size_t>(b) * 8;  // 0..3 warm-start key, 4 phase, 5 nrows, 6 n_aux, 7 nnzA
+  int* meta = p.ws_meta + static_cast<size_t>(b) * 8;  // 0..3 warm-start key (n_aux, rows, nnzA, last status)
   const int n_obj = p.n_costs + p.n_cnts;
-  QpResume rs{};
-  const bool resume = !x_override && meta[4] == 1;
   int nr = 0, n_aux = 0, nnzA = 0;
   bool warm = false;
   int* sh_i = reinterpret_cast<int*>(q.flag + 2);  // small shared int scratch during assembly
 
-  if (!resume) {
+  {
     const double* xc = (x_override ? x_override : p.x) + static_cast<size_t>(b) * N;
     const double trust = trust_override ? trust_override[b] : p.trust[b];
     const double* mu = p.merit_coeffs + static_cast<size_t>(b) * p.n_cnts;
@@ -1885,19 +1904,12 @@ __device__ __forceinline__ void qp_step(const DevProblem& p, const int b, const 
     }
     __syncthreads();
     q.nrows = nr;
-  } else {
-    nr = meta[5];
-    n_aux = meta[6];
-    nnzA = meta[7];
-    q.nrows = nr;
   }
   for (int i = tid; i <= q.Np; i += kQpThreads) q.colptr[i] = colptr[i];
   __syncthreads();
   // ---- the rows move into shared memory when they fit (the common case) ---------------------------------
   const bool rows_in_smem = nr <= S.row_cap;
   double* const rows_s = sm + S.rows;
-  const int fac_doubles = 3 * qp_even(q.M * NB * NB);
-  double* const park_fac = p.park_factor + static_cast<size_t>(b) * fac_doubles;
   if (rows_in_smem) {
     int* rints_s = reinterpret_cast<int*>(sm + S.rints);
     int* colent_s = reinterpret_cast<int*>(sm + S.colent);
@@ -1908,72 +1920,21 @@ __device__ __forceinline__ void qp_step(const DevProblem& p, const int b, const 
     q.rints = rints_s;
     q.colent = colent_s;
   }
-  if (resume)
-    for (int t = tid; t < fac_doubles; t += kQpThreads) q.SA[t] = park_fac[t];  // SA, SLM, SU are contiguous
   __syncthreads();
 
-  if (!resume) {
-    // ---- warm start decision (createOrUpdateSolver, osqp_interface.cpp:283-370) ---------------------------
-    warm = !x_override && p.qp.warm_starting && meta[3] == 1 && meta[0] == n_aux && meta[1] == nr && meta[2] == nnzA;
-    { PROF_T0(); qp_scale(q, p.qp, n_aux); PROF_ADD(7); }
-    for (int i = tid; i < q.Np; i += kQpThreads) {  // master copies for the resume path
-      g_qs[i] = qs[i];
-      g_lbs[i] = lbs[i];
-      g_ubs[i] = ubs[i];
-      g_Dz[i] = q.Dz[i];
-    }
-  } else {
-    rs.iter = p.rs_int[b * 4 + 0];
-    rs.round = p.rs_int[b * 4 + 1];
-    rs.rho_updates = p.rs_int[b * 4 + 2];
-    rs.rho = p.rs_dbl[b * 4 + 0];
-    rs.eps_scale = p.rs_dbl[b * 4 + 1];
-    rs.c = p.rs_dbl[b * 4 + 2];
-    rs.guess_flags = p.rs_int[b * 4 + 3];
-    rs.prev_guess = p.rs_guess[b * 2 + 0];
-    rs.failed_guess = p.rs_guess[b * 2 + 1];
-    q.c = rs.c;
-    q.cinv = 1.0 / q.c;
-    for (int i = tid; i < q.Np; i += kQpThreads) {
-      q.x[i] = park[i];
-      q.zb[i] = park[q.Np + i];
-      q.yb[i] = park[2 * q.Np + i];
-      q.beta[i] = park[3 * q.Np + i];
-      qs[i] = g_qs[i];
-      lbs[i] = g_lbs[i];
-      ubs[i] = g_ubs[i];
-      q.Dz[i] = g_Dz[i];
-    }
-  }
+  // ---- warm start decision (createOrUpdateSolver, osqp_interface.cpp:283-370) ---------------------------
+  warm = !x_override && p.qp.warm_starting && meta[3] == 1 && meta[0] == n_aux && meta[1] == nr && meta[2] == nnzA;
+  { PROF_T0(); qp_scale(q, p.qp, n_aux); PROF_ADD(7); }
   __syncthreads();
 
   PROF_T0();
-  QpOut res = qp_solve_block<NB, PAIR>(q, p.qp, !resume, warm, p.ws_rho[b], p.ws_x + static_cast<size_t>(b) * N,
-                                 p.ws_yb + static_cast<size_t>(b) * N, rs, x_override ? (1 << 30) : slice, resume);
+  QpOut res = qp_solve_block<NB, PAIR, (DD <= 7)>(q, p.qp, warm, p.ws_rho[b], p.ws_x + static_cast<size_t>(b) * N,
+                                                  p.ws_yb + static_cast<size_t>(b) * N);
   __syncthreads();
   PROF_ADD(8);
 #ifdef TB200_PROFILE
   if (tid == 0) atomicAdd(&g_prof[9], 1ull);
 #endif
-
-  if (res.status == QPS_YIELD) {  // park the solve
-    for (int i = tid; i < q.Np; i += kQpThreads) {
-      park[i] = q.x[i];
-      park[q.Np + i] = q.zb[i];
-      park[2 * q.Np + i] = q.yb[i];
-      park[3 * q.Np + i] = q.beta[i];
-    }
-    for (int t = tid; t < fac_doubles; t += kQpThreads) park_fac[t] = q.SA[t];
-    if (rows_in_smem)
-      for (int t = tid; t < nr * q.RS; t += kQpThreads) rows_g[t] = rows_s[t];
-    if (tid == 0) {
-      meta[4] = 1; meta[5] = nr; meta[6] = n_aux; meta[7] = nnzA;
-      p.rs_int[b * 4 + 0] = rs.iter; p.rs_int[b * 4 + 1] = rs.round; p.rs_int[b * 4 + 2] = rs.rho_updates;
-      p.rs_dbl[b * 4 + 0] = rs.rho; p.rs_dbl[b * 4 + 1] = rs.eps_scale; p.rs_dbl[b * 4 + 2] = rs.c;
-      p.rs_int[b * 4 + 3] = rs.guess_flags; p.rs_guess[b * 2 + 0] = rs.prev_guess; p.rs_guess[b * 2 + 1] = rs.failed_guess;
-    }
-    return;
-  }
 
   // ---- unscale, store the solution (and the warm-start state), model values -----------------------------
   double* nx = p.new_x + static_cast<size_t>(b) * N;

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kQpThreads, 1) solve_kernel(DevProblem p, Eval
     for (int step = 0; step < ctl.quantum && !finished; ++step) {
       const unsigned long long t0 = global_ns();
       // (a single call site: the QP solve stays inlined in the kernel, as tuned)
-      qp_step<DD, PAIR>(p, b, ctl.x_override, ctl.trust_override, ctl.admm_iters_out, ctl.polish_out, 1 << 30);
+      qp_step<DD, PAIR>(p, b, ctl.x_override, ctl.trust_override, ctl.admm_iters_out, ctl.polish_out);
       if (qp_only) return;
       __syncthreads();
       const unsigned long long t1 = global_ns();

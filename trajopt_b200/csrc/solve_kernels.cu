@@ -1,34 +1,30 @@
-// Instances of the persistent SQP kernel (solve_kernel.cuh): the block size of the block-cyclic-reduction factor
-// of its QP step is a compile-time constant (2*D).
+// Look-up of the persistent SQP kernel instances (one translation unit each: solve_inst_<D>_<PAIR>.cu).
 #include <cuda_runtime.h>
 
-#include "solve_kernel.cuh"
 #include "kernels.h"
 
 namespace tb200 {
-SolveKernelFn solve_pair_kernel_for(int D);  // solve_kernels_pair.cu: rows over two consecutive waypoints
+#define TB200_INSTANCES(X) X(2, 0) X(3, 0) X(6, 0) X(7, 0) X(14, 0) X(2, 1) X(7, 1)
+#define TB200_DECL(D, P)                  \
+  SolveKernelFn solve_kernel_inst_##D##_##P(); \
+  int qp_prof_inst_##D##_##P(unsigned long long*, int);
+TB200_INSTANCES(TB200_DECL)
+#undef TB200_DECL
+
 SolveKernelFn solve_kernel_for(int D, bool pair_rows) {
-  if (pair_rows) return solve_pair_kernel_for(D);
-  switch (D) {
-    case 2: return solve_kernel<2, 0>;
-    case 3: return solve_kernel<3, 0>;
-    case 6: return solve_kernel<6, 0>;
-    case 7: return solve_kernel<7, 0>;
-    default: return nullptr;
-  }
+#define TB200_PICK(DD, P) \
+  if (D == DD && pair_rows == static_cast<bool>(P)) return solve_kernel_inst_##DD##_##P();
+  TB200_INSTANCES(TB200_PICK)
+#undef TB200_PICK
+  return nullptr;
 }
 int qp_debug_prof(unsigned long long* out, int reset) {
-#ifdef TB200_PROFILE
-  if (reset) {
-    unsigned long long z[16] = {0};
-    cudaMemcpyToSymbol(g_prof, z, sizeof(z));
-    return 0;
-  }
-  cudaMemcpyFromSymbol(out, g_prof, 16 * sizeof(unsigned long long));
-  return 0;
-#else
-  (void)out; (void)reset;
-  return -1;
-#endif
+  int rc = -1;
+  if (!reset && out)
+    for (int i = 0; i < 16; ++i) out[i] = 0;
+#define TB200_PROF(D, P) rc = qp_prof_inst_##D##_##P(out, reset);
+  TB200_INSTANCES(TB200_PROF)
+#undef TB200_PROF
+  return rc;
 }
 }  // namespace tb200

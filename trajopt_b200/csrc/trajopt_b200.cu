@@ -1,9 +1,9 @@
 // Host side of the C ABI (include/trajopt_b200.h): validates and flattens the problem description the
 // way trajopt::ConstructProblem / TermInfo::hatch do (trajopt/src/problem_description.cpp:410-542,
 // 901-987, 1078-1176, 1197-1372, 1393-1493, 1714-1837), owns the device buffers, and drives the
-// batched trust-region SQP (trajopt_sco/src/optimizers.cpp:699-991) as a lock-step sequence of two
-// kernels per outer step: qp_kernel (QP subproblem per trajectory) and eval_convexify_decide_kernel
-// (exact merit evaluation + next convexification + accept/shrink/penalty decision).
+// batched trust-region SQP (trajopt_sco/src/optimizers.cpp:699-991): one launch of eval_convexify_decide_kernel
+// (first evaluation + convexification of every trajectory) and one persistent launch of solve_kernel, which runs
+// every trajectory's QP subproblems, merit evaluations, re-convexifications and accept/shrink/penalty decisions.
 // CUDA only: every entry point fails with TB200_ERR_CUDA / TB200_ERR_NO_DEVICE when no device is usable.
 #include <cuda_runtime.h>
 
@@ -86,12 +86,14 @@ struct tb200_problem {
   DevBuf<DevCartTerm> cart_terms;
   DevBuf<int> fixed_vars;
   DevBuf<double> x, new_x, trust, merit_coeffs, cost_vals, cnt_viols, new_cost_vals, new_cnt_viols, model_cost_vals,
-      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace, park, park_factor, rs_dbl;
-  DevBuf<unsigned long long> rs_guess, sched_timers;
+      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace, factor_g;
+  DevBuf<unsigned long long> sched_timers;
   DevBuf<int> sched_state;
   DevBuf<unsigned long long> coll_mask;
   DevBuf<int> status, sqp_iter, merit_round, qp_failures, qp_status, cur_buf, n_qp_solves, n_func_evals, n_admm_iters,
-      active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish, trace_len, rs_int, qp_done;
+      active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish, trace_len, qp_done, lvs_overflow, link_chain;
+  int max_sub = 1;        // LVS sub-segments per step pair the candidate layout holds
+  size_t factor_grid = 0;  // CTAs that own a region of factor_g (0: the factor lives in shared memory)
   std::vector<cudaEvent_t> events;
   ~tb200_problem() {
     for (auto e : events) cudaEventDestroy(e);
@@ -102,7 +104,7 @@ struct tb200_problem {
     x.release(); new_x.release(); trust.release(); merit_coeffs.release(); cost_vals.release(); cnt_viols.release();
     new_cost_vals.release(); new_cnt_viols.release(); model_cost_vals.release(); model_cnt_viols.release();
     cart_err.release(); cart_jac.release(); coll_rows.release(); rows.release(); ws_x.release(); ws_yb.release();
-    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); park.release(); park_factor.release(); rs_dbl.release(); rs_guess.release(); rs_int.release(); qp_done.release(); sched_state.release(); sched_timers.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
+    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); factor_g.release(); lvs_overflow.release(); link_chain.release(); qp_done.release(); sched_state.release(); sched_timers.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
     sqp_iter.release(); merit_round.release(); qp_failures.release(); qp_status.release(); cur_buf.release();
     n_qp_solves.release(); n_func_evals.release(); n_admm_iters.release(); active_count.release(); row_ints.release();
     lists.release(); ws_meta.release(); tmp_iters.release(); tmp_polish.release();
@@ -154,6 +156,19 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   if (d->robot.n_segments < 1 || d->robot.n_segments > kMaxSeg) return fail(TB200_ERR_INVALID, "n_segments out of range");
   if (d->robot.n_spheres > kMaxSpheres) return fail(TB200_ERR_INVALID, "too many collision spheres");
   if (!d->init_traj) return fail(TB200_ERR_INVALID, "init_traj is required");
+  if (d->n_terms < 0 || (d->n_terms > 0 && !d->terms)) return fail(TB200_ERR_INVALID, "terms is NULL with n_terms > 0");
+  if (!d->robot.segments) return fail(TB200_ERR_INVALID, "robot.segments is NULL");
+  if (!d->robot.lower || !d->robot.upper) return fail(TB200_ERR_INVALID, "robot joint limits are NULL");
+  if (d->robot.n_spheres < 0 || (d->robot.n_spheres > 0 && !d->robot.spheres))
+    return fail(TB200_ERR_INVALID, "robot.spheres is NULL with n_spheres > 0");
+  if (d->n_fixed_timesteps < 0 || (d->n_fixed_timesteps > 0 && !d->fixed_timesteps))
+    return fail(TB200_ERR_INVALID, "fixed_timesteps is NULL with n_fixed_timesteps > 0");
+  if (d->n_fixed_dofs < 0 || (d->n_fixed_dofs > 0 && !d->fixed_dofs))
+    return fail(TB200_ERR_INVALID, "fixed_dofs is NULL with n_fixed_dofs > 0");
+  if (d->n_obstacles < 0 || (d->n_obstacles > 0 && !d->obstacles))
+    return fail(TB200_ERR_INVALID, "obstacles is NULL with n_obstacles > 0");
+  if (d->n_cart_targets < 0 || (d->n_cart_targets > 0 && !d->cart_targets))
+    return fail(TB200_ERR_INVALID, "cart_targets is NULL with n_cart_targets > 0");
 
   auto P = new tb200_problem();
   std::unique_ptr<tb200_problem> guard(P);
@@ -234,7 +249,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   std::vector<DevJointTerm> jts;
   std::vector<DevCartTerm> cts;
   std::vector<DevObj> costs, eqs, ineqs;
-  int n_cart_rows = 0, n_coll_cand = 0, max_rows = 0;
+  int n_cart_rows = 0, n_coll_cand = 0, max_rows = 0, max_sub = 1;
   std::vector<std::pair<int, int>> cart_ref, coll_ref, vel_ref;  // (list id: 0 cost 1 eq 2 ineq, index)
   bool has_vel = false, has_cast = false, has_discrete = false;
   for (int k = 0; k < d->n_terms; ++k) {
@@ -297,7 +312,15 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
       if (tm.evaluator_type < TB200_COLL_DISCRETE || tm.evaluator_type > TB200_COLL_LVS_CONTINUOUS)
         return fail(TB200_ERR_INVALID, "unknown collision evaluator type");
       if (dp.L == 0 || dp.O == 0) return fail(TB200_ERR_INVALID, "collision term needs robot spheres and obstacles");
+      if (tm.n_fixed_steps < 0 || tm.n_fixed_steps > 8) return fail(TB200_ERR_INVALID, "collision term: n_fixed_steps outside [0, 8]");
       const bool cast = tm.evaluator_type != TB200_COLL_DISCRETE;
+      if (cast) {
+        const int lay = tb200inl_lvs_layout_segments(d, &tm);
+        if (lay <= 0)
+          return fail(TB200_ERR_UNSUPPORTED, "longest_valid_segment_length needs more than TB200_MAX_LVS_LAYOUT sub-segments per "
+                                             "step pair on the initial trajectories");
+        max_sub = std::max(max_sub, lay);
+      }
       if ((cast && has_discrete) || (!cast && has_cast))
         return fail(TB200_ERR_UNSUPPORTED, "discrete and continuous collision terms in one problem are not supported");
       (cast ? has_cast : has_discrete) = true;
@@ -315,13 +338,11 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
         c.kind = cast ? OBJ_COLL_CAST : OBJ_COLL;
         c.first = t;
         c.src_off = n_coll_cand;
-        c.n_rows = dp.L * dp.O * (cast ? kMaxLvsSegments : 1);
+        c.n_rows = dp.L * dp.O;  // (continuous: times the layout's sub-segments, set below once every term is seen)
         c.coeff = tm.coeff; c.margin = tm.margin; c.buffer = tm.margin_buffer;
         // (two adjacent fixed steps take the START_FIXED_END_FREE branch: the reference's throw is unreachable)
         c.pad1 = cast ? ((fixed ? 1 : 0) | ((!fixed && next_fixed) ? 2 : 0)) : 0;
         c.lvs = (tm.evaluator_type == TB200_COLL_CONTINUOUS) ? std::numeric_limits<double>::max() : tm.longest_valid_segment_length;
-        n_coll_cand += c.n_rows;
-        max_rows += c.n_rows;
         if (is_cnt) { coll_ref.push_back({2, static_cast<int>(ineqs.size())}); ineqs.push_back(c); }
         else { coll_ref.push_back({0, static_cast<int>(costs.size())}); costs.push_back(c); }
       }
@@ -351,6 +372,15 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
       return fail(TB200_ERR_INVALID, "unknown term kind");
     }
   }
+  // every continuous collision object gets the same number of sub-segment slots
+  for (auto* lst : {&costs, &ineqs})
+    for (DevObj& o : *lst)
+      if (o.kind == OBJ_COLL || o.kind == OBJ_COLL_CAST) {
+        if (o.kind == OBJ_COLL_CAST) o.n_rows *= max_sub;
+        n_coll_cand += o.n_rows;
+        max_rows += o.n_rows;
+      }
+  P->max_sub = max_sub;
   P->cost_objs = costs;
   P->cnt_objs = eqs;
   P->cnt_objs.insert(P->cnt_objs.end(), ineqs.begin(), ineqs.end());
@@ -434,12 +464,13 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.n_fixed = static_cast<int>(fixed.size());
   dp.max_rows = max_rows;
   dp.row_stride = qp_row_stride(CN);
-  dp.coll_words = std::max(1, (dp.L * dp.O * (has_cast ? kMaxLvsSegments : 1) + 63) / 64);
+  dp.coll_words = std::max(1, (dp.L * dp.O * (has_cast ? max_sub : 1) + 63) / 64);
   dp.n_coll_objs = static_cast<int>(P->coll_objs.size());
   P->ex.n_cart_objs = static_cast<int>(P->cart_objs.size());
   P->ex.n_coll_objs = dp.n_coll_objs;
   P->ex.n_vel_objs = static_cast<int>(P->vel_objs.size());
   P->ex.cast = has_cast ? 1 : 0;
+  P->ex.max_sub = max_sub;
   for (int sg = 0; sg < dp.S; ++sg)
     if (segs[sg].q_index >= 0) P->ex.joint_seg[segs[sg].q_index] = sg;
   P->ex.n_joint_objs = 0;
@@ -466,20 +497,18 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   P->layout.n_vars = N;
 
   // ---- kernel resources --------------------------------------------------------------------------------
-  const EvalSmem es = eval_smem_layout(T, D, dp.L, P->ex.n_cart_objs, dp.n_coll_objs, dp.n_coll_objs * dp.coll_words, dp.S,
-                                       P->ex.n_joint_objs, P->ex.n_vel_objs, P->ex.cast, dp.n_costs + dp.n_cnts);
+  const EvalSmem es = eval_smem_layout(T, D, dp.L, dp.n_coll_objs, dp.n_coll_objs * dp.coll_words, dp.S, P->ex.n_joint_objs,
+                                       P->ex.n_vel_objs, P->ex.cast, max_sub, dp.n_costs + dp.n_cnts);
   P->pair_rows = (CN > std::max(D, 3));
   P->eval_smem = static_cast<size_t>(es.total) * sizeof(double);
-  const QpSmem qs = qp_smem_layout(N, 2 * D, dp.row_stride, CN, max_rows);
+  const bool factor_global = D > 8;  // = FG of qp_step: blocks of 2*D > 16 never fit
+  const QpSmem qs = qp_smem_layout(N, 2 * D, dp.row_stride, CN, max_rows, factor_global);
   const int Np = qp_block_count(N, 2 * D) * 2 * D;
   dp.list_stride = static_cast<size_t>(Np + 1) + static_cast<size_t>(max_rows) * CN + dp.n_costs + dp.n_cnts + 2;
   P->qp_smem = static_cast<size_t>(qs.total) * sizeof(double);
-  if (P->eval_smem > 227 * 1024 || P->qp_smem > 227 * 1024)
+  if (P->eval_smem > 226 * 1024 || P->qp_smem > 226 * 1024)
     return fail(TB200_ERR_UNSUPPORTED, "problem does not fit the 227 KB shared memory of one CTA");
-  if ((qp_block_count(N, 2 * D) + 1) / 2 * 2 * D > kQpThreads / 2)
-    return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for one CTA per block-cyclic-reduction level");
-  if (!solve_roles_fit(qp_block_count(N, 2 * D), 2 * D))
-    return fail(TB200_ERR_UNSUPPORTED, "trajectory too long for the register-resident block-cyclic-reduction solve");
+  if (CN > 32) return fail(TB200_ERR_UNSUPPORTED, "more than 32 coefficients per QP row");
   if (!solve_kernel_for(D, P->pair_rows) || !eval_kernel_for(D))
     return fail(TB200_ERR_UNSUPPORTED, P->pair_rows ? "no kernel instance with two-waypoint rows (CartVel, continuous collision) for this number of joints"
                                                     : "no kernel instance for this number of joints");
@@ -533,7 +562,22 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   ALLOC(coll_mask, 2 * Bs * std::max(1, dp.n_coll_objs * dp.coll_words));
   ALLOC(rows, Bs * max_rows * dp.row_stride); ALLOC(row_ints, Bs * max_rows * RI_NINTS);
   ALLOC(lists, Bs * dp.list_stride);
-  ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 10 * Np); ALLOC(park, Bs * 4 * Np); ALLOC(park_factor, Bs * 3 * qp_even(qp_block_count(N, 2 * D) * 4 * D * D)); ALLOC(rs_int, Bs * 4); ALLOC(rs_dbl, Bs * 4); ALLOC(rs_guess, Bs * 2); ALLOC(qp_done, Bs); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 8);
+  ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 5 * Np); ALLOC(qp_done, Bs); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 8);
+  ALLOC(lvs_overflow, Bs);
+  // a factor that does not fit shared memory lives in a per-CTA region (the kernel-level QP entry point launches B CTAs)
+  P->factor_grid = (factor_global || !qs.factor_smem) ? std::max<size_t>(Bs, static_cast<size_t>(P->n_sm)) : 0;
+  ALLOC(factor_g, P->factor_grid * qp_factor_doubles(N, 2 * D));
+  {
+    std::vector<int> chain(static_cast<size_t>(dp.S) * (kMaxSeg + 1), 0);
+    for (int sg = 0; sg < dp.S; ++sg) {
+      std::vector<int> up;
+      for (int a = sg; a >= 0; a = segs[a].parent) up.push_back(a);
+      int* c = chain.data() + static_cast<size_t>(sg) * (kMaxSeg + 1);
+      c[0] = static_cast<int>(up.size());
+      for (size_t k = 0; k < up.size(); ++k) c[1 + k] = up[up.size() - 1 - k];
+    }
+    UPLOAD(link_chain, chain);
+  }
   ALLOC(status, Bs); ALLOC(sqp_iter, Bs); ALLOC(merit_round, Bs); ALLOC(qp_failures, Bs); ALLOC(qp_status, Bs);
   ALLOC(cur_buf, Bs); ALLOC(n_qp_solves, Bs); ALLOC(n_func_evals, Bs); ALLOC(n_admm_iters, Bs); ALLOC(active_count, 2);
   ALLOC(dbg, Bs * 16);
@@ -555,7 +599,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.cart_err = P->cart_err.p; dp.cart_jac = P->cart_jac.p; dp.coll_rows = P->coll_rows.p; dp.coll_mask = P->coll_mask.p;
   dp.rows = P->rows.p; dp.row_ints = P->row_ints.p; dp.lists = P->lists.p; dp.ws_x = P->ws_x.p; dp.ws_yb = P->ws_yb.p;
   dp.scratch = P->scratch.p; dp.ws_meta = P->ws_meta.p; dp.ws_rho = P->ws_rho.p; dp.dbg = P->dbg.p; dp.sched_state = P->sched_state.p; dp.sched_timers = P->sched_timers.p; dp.trace_len = P->trace_len.p; dp.trace = nullptr; dp.trace_cap = 0;
-  dp.park = P->park.p; dp.park_factor = P->park_factor.p; dp.rs_int = P->rs_int.p; dp.rs_dbl = P->rs_dbl.p; dp.rs_guess = P->rs_guess.p; dp.qp_done = P->qp_done.p;
+  dp.factor_g = P->factor_g.p; dp.lvs_overflow = P->lvs_overflow.p; dp.qp_done = P->qp_done.p;
+  P->ex.link_chain = P->link_chain.p;
   P->ex.cart_objs = P->d_cart_objs.p;
   P->ex.coll_objs = P->d_coll_objs.p;
   P->ex.vel_objs = P->d_vel_objs.p;
@@ -626,6 +671,7 @@ __global__ void reset_state_kernel(DevProblem p) {
   for (int c = 0; c < p.n_cnts; ++c) p.merit_coeffs[static_cast<size_t>(b) * p.n_cnts + c] = p.sqp.initial_merit_error_coeff;
   for (int k = 0; k < 8; ++k) p.ws_meta[b * 8 + k] = 0;
   p.qp_done[b] = 0;
+  p.lvs_overflow[b] = 0;
   p.sched_state[b] = 0;
   p.sched_timers[8 + b] = 0ull;
   p.sched_timers[8 + p.B + b] = 0ull;
@@ -696,6 +742,28 @@ int tb200_solve_batch_resident(tb200_problem* P) {
   return TB200_OK;
 }
 
+namespace {
+// trajectories whose step pairs outgrew the LVS candidate layout (they ended OPT_FAILED; never truncated silently)
+int lvsOverflowCount(tb200_problem* P, int* count) {
+  *count = 0;
+  if (!P->ex.cast) return TB200_OK;
+  std::vector<int> f(P->dp.B);
+  CK(cudaMemcpy(f.data(), P->lvs_overflow.p, f.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int v : f) *count += v != 0;
+  return TB200_OK;
+}
+int lvsOverflowError(tb200_problem* P) {
+  int n = 0;
+  int rc = lvsOverflowCount(P, &n);
+  if (rc != TB200_OK) return rc;
+  if (n > 0)
+    return fail(TB200_ERR_UNSUPPORTED, std::to_string(n) + " trajectories have a step pair that needs more than " +
+                                           std::to_string(P->max_sub) + " longest-valid-segment sub-segments (the candidate layout "
+                                           "was sized from the initial trajectories); they are reported OPT_FAILED");
+  return TB200_OK;
+}
+}  // namespace
+
 int tb200_fetch_results(tb200_problem* P, tb200_results* out) {
   if (!P || !out) return fail(TB200_ERR_INVALID, "null argument");
   CK(cudaSetDevice(P->device));
@@ -734,7 +802,9 @@ int tb200_solve_batch(tb200_problem* P, tb200_results* out) {
   if (!P || !out) return fail(TB200_ERR_INVALID, "null argument");
   int rc = tb200_solve_batch_resident(P);
   if (rc != TB200_OK) return rc;
-  return tb200_fetch_results(P, out);
+  rc = tb200_fetch_results(P, out);
+  if (rc != TB200_OK) return rc;
+  return lvsOverflowError(P);  // (after the results: the other trajectories of the batch are valid)
 }
 
 int tb200_convexify_batch(tb200_problem* P, const double* x, tb200_convexify_out* out) {
@@ -744,6 +814,7 @@ int tb200_convexify_batch(tb200_problem* P, const double* x, tb200_convexify_out
   const size_t B = dp.B;
   cudaStream_t st = P->stream;
   CK(cudaMemcpyAsync(P->x_tmp.p, x, B * dp.N * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(P->lvs_overflow.p, 0, B * sizeof(int), st));
   cudaEvent_t e0 = getEvent(P, 0), e1 = getEvent(P, 1);
   CK(cudaEventRecord(e0, st));
   eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
@@ -769,7 +840,7 @@ int tb200_convexify_batch(tb200_problem* P, const double* x, tb200_convexify_out
   CK(pull(out->cost_vals, dp.cost_vals, B * dp.n_costs * sizeof(double)));
   CK(pull(out->cnt_viols, dp.cnt_viols, B * dp.n_cnts * sizeof(double)));
   CK(cudaStreamSynchronize(st));
-  return TB200_OK;
+  return lvsOverflowError(P);
 }
 
 int tb200_qp_solve_batch(tb200_problem* P, const double* x, const double* trust, const double* merit_coeffs, double* new_x,
@@ -783,6 +854,7 @@ int tb200_qp_solve_batch(tb200_problem* P, const double* x, const double* trust,
   CK(cudaMemcpyAsync(P->trust_tmp.p, trust, B * sizeof(double), cudaMemcpyHostToDevice, st));
   if (dp.n_cnts > 0) CK(cudaMemcpyAsync(P->merit_coeffs.p, merit_coeffs, B * dp.n_cnts * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(P->ws_meta.p, 0, B * 8 * sizeof(int), st));
+  CK(cudaMemsetAsync(P->lvs_overflow.p, 0, B * sizeof(int), st));
   eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
   SolveCtl ctl{};
   ctl.mode = SOLVE_QP_ONLY;  // one QP step per trajectory (one CTA each), no evaluation / decision
