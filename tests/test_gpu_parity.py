@@ -17,6 +17,15 @@ _MAKERS = {"cfg1": lambda: problems.config1(B=16, T=12), "cfg2": lambda: problem
            # configs[3] terms (CartVel + LVS_CONTINUOUS collision + via-point CartPose) at the lengths the QP kernel holds
            "cfg3": lambda: problems.config3(B=16, T=12, via_every=4), "cfg3_T30": lambda: problems.config3(B=4, T=30),
            "cfg3_no_lvs": lambda: problems.config3(B=8, T=12, via_every=4, lvs=10.0),
+           # configs[3] at its stated length (50 waypoints: 25 factor blocks) and configs[4] (14-DOF dual arm, upright
+           # constraints on every waypoint, 40 waypoints: factor blocks of 28 in global memory) with three points of its
+           # trust-region sweep (trust_box_size, trust_shrink_ratio, trust_expand_ratio)
+           "cfg3_T50": lambda: problems.config3(B=8, T=50),
+           "cfg4": lambda: problems.config4(B=8, T=40),
+           "cfg4_short": lambda: problems.config4(B=4, T=12),
+           "cfg4_sweep_a": lambda: problems.config4(B=8, T=40, trust_box_size=0.01, trust_shrink_ratio=0.1, trust_expand_ratio=2.0),
+           "cfg4_sweep_b": lambda: problems.config4(B=8, T=40, trust_box_size=0.5, trust_shrink_ratio=0.5, trust_expand_ratio=1.2),
+           "cfg4_sweep_c": lambda: problems.config4(B=8, T=40, trust_box_size=0.05, trust_shrink_ratio=0.5, trust_expand_ratio=1.5),
            # the term flavours configs[1]-[3] do not use: Ineq joint terms, CartPose / CartVel / collision as COSTS, fixed_dofs
            "variants": lambda: problems.config_variants(B=8, T=10)}
 
@@ -34,7 +43,8 @@ def _cfgs():
     return _CACHE
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_full_T", "cfg3", "cfg3_T30", "cfg3_no_lvs", "variants"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_full_T", "cfg3", "cfg3_T30", "cfg3_no_lvs", "variants", "cfg3_T50",
+                                  "cfg4", "cfg4_short"])
 def test_convexify_rows_match_oracle(oracle, name):
     d = _cfgs()[name]
     rng = np.random.default_rng(7)
@@ -52,7 +62,7 @@ def test_convexify_rows_match_oracle(oracle, name):
         assert ((got["coll_rows"][..., -1] != 0) == (ref["coll_rows"][..., -1] != 0)).all()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "variants"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "variants", "cfg3_T50", "cfg4", "cfg4_short"])
 @pytest.mark.parametrize("trust", [0.1, 0.01])
 def test_qp_solve_matches_oracle(oracle, name, trust):
     d = _cfgs()[name]
@@ -89,14 +99,17 @@ def _solve_with_trace(d, cap=600):
     return got, hit
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg1_full_T", "cfg2_full_T", "cfg3", "cfg3_T30", "variants"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg1_full_T", "cfg2_full_T", "cfg3", "cfg3_T30", "variants", "cfg3_T50",
+                                  "cfg4", "cfg4_short", "cfg4_sweep_a", "cfg4_sweep_b", "cfg4_sweep_c"])
 def test_sqp_solve_matches_oracle(oracle, name):
     d = _cfgs()[name]
     got, hit = _solve_with_trace(d)
     ref = oracle.solve_batch(d)
     loose = name.startswith("cfg3") or name == "variants"
-    ok = ~hit if loose else np.ones(d.B, bool)  # configs[1]/[2]: every trajectory is compared
-    assert ok.mean() >= 0.5, hit
+    # configs[1] / [2] / [4]: every trajectory is compared.  configs[3] terms: a trajectory one of whose QPs ended WITHOUT
+    # a KKT-verified polished point (named in `hit`) cannot be compared step by step; at least 3 of 4 must be comparable.
+    ok = ~hit if loose else np.ones(d.B, bool)
+    assert ok.mean() >= 0.75, ("trajectories with an unverified QP", np.nonzero(hit)[0])
     assert (got["status"][ok] == ref["status"][ok]).all(), (got["status"], ref["status"], hit)
     assert (got["n_qp_solves"][ok] == ref["n_qp_solves"][ok]).all(), (got["n_qp_solves"], ref["n_qp_solves"], hit)
     # final cost within 1e-6 wherever the SQP CONVERGED (north_star); a trajectory that stops at an iteration limit is
@@ -110,6 +123,33 @@ def test_sqp_solve_matches_oracle(oracle, name):
     np.testing.assert_allclose(got["total_cost"][ok], ref["total_cost"][ok], rtol=5e-3)
     # the others still end in a terminal state of the same SQP (not compared step by step)
     assert (got["status"] != capi.OPT_INVALID).all()
+
+
+def test_headline_batch_matches_oracle(oracle):
+    """The bench workload itself: configs[2] at batch 1024 x 30 waypoints solved on the GPU, the first 128 trajectories
+    (converged ones and the ones that stop at an iteration limit alike) compared with the oracle: identical status and
+    QP count, final cost within 1e-6, final joint values within 1e-5."""
+    d = problems.config2(B=1024, T=30)
+    got = api.solve(d)
+    n = 128
+    ref = oracle.solve_batch(d, 0, n)
+    assert (got["status"] != capi.OPT_INVALID).all()
+    assert (got["status"][:n] == ref["status"][:n]).all(), np.nonzero(got["status"][:n] != ref["status"][:n])[0]
+    assert (got["n_qp_solves"][:n] == ref["n_qp_solves"][:n]).all()
+    assert (ref["status"][:n] != capi.OPT_CONVERGED).any()  # the sample holds iteration-limit trajectories too
+    np.testing.assert_allclose(got["total_cost"][:n], ref["total_cost"][:n], atol=COST_ATOL)
+    np.testing.assert_allclose(got["x"][:n], ref["x"][:n], atol=1e-5)
+    assert (got["status"] == capi.OPT_CONVERGED).mean() > 0.85
+
+
+def test_lvs_layout_overflow_is_reported():
+    """A step pair that comes to need more longest-valid-segment sub-segments than the layout sized from the initial
+    trajectory is never truncated: the solve returns TB200_ERR_UNSUPPORTED and the trajectory ends OPT_FAILED."""
+    d0 = problems.config3(B=2, T=8, via_every=4, lvs=0.02)
+    init = d0.init_traj[:, :1] + 1e-3 * np.arange(8)[None, :, None]  # an almost stationary initial trajectory: layout of 4
+    d = capi.ProblemDesc(d0.robot_spec, d0.T, d0.terms, init, fixed_timesteps=[0], cart_targets=d0.cart_targets, obstacles=d0.obstacles)
+    with pytest.raises(RuntimeError, match="sub-segments"):
+        api.solve(d)
 
 
 def test_joint_terms_cfg0(oracle):

@@ -201,4 +201,127 @@ def config_variants(B=8, T=10, seed=SEED + 7, n_obstacles=8):
                        cart_targets=_targets_from_goal(robot, q1, tool), obstacles=obstacles)
 
 
-CONFIGS = {"cfg0": config0, "cfg1": config1, "cfg2": config2, "cfg3": config3, "variants": config_variants}
+def _rotvec(R):
+    """Rotation vector (axis * angle) of a rotation matrix."""
+    c = min(1.0, max(-1.0, (np.trace(R) - 1.0) / 2.0))
+    ang = np.arccos(c)
+    w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    n = np.linalg.norm(w)
+    return np.zeros(3) if n < 1e-14 else w / n * ang
+
+
+def _ik_to_pose(robot, q, link, joints, p_goal, R_goal, iters=200):
+    """Host-side damped least squares IK over `joints` (problem generation only: the synthetic goals of configs[4]
+    must be reachable).  Returns the joint vector or None."""
+    q = q.copy()
+    lo, hi = np.array(robot["lower"]), np.array(robot["upper"])
+    segs = robot["segments"]
+    for _ in range(iters):
+        fr = robots.fk_numpy(robot, q)
+        R, p = fr[link]
+        e = np.concatenate([p_goal - p, _rotvec(R_goal @ R.T)])
+        if np.abs(e).max() < 1e-12:
+            return q
+        J = np.zeros((6, len(joints)))
+        anc, a = set(), link
+        while a >= 0:
+            anc.add(a)
+            a = segs[a].parent
+        for k, j in enumerate(joints):
+            sg = next(i for i, g in enumerate(segs) if g.q_index == j)
+            if sg not in anc:
+                continue
+            Rj, pj = fr[sg]
+            ax = Rj @ np.array(list(segs[sg].axis))
+            J[:3, k], J[3:, k] = np.cross(ax, p - pj), ax
+        dq = J.T @ np.linalg.solve(J @ J.T + 1e-6 * np.eye(6), e)
+        step = np.abs(dq).max()
+        if step > 0.2:
+            dq *= 0.2 / step
+        q[joints] = q[joints] + dq
+        if (q < lo + 1e-3).any() or (q > hi - 1e-3).any():
+            return None
+    return None
+
+
+def config4(B=256, T=40, seed=SEED + 4, n_obstacles=8, trust_box_size=None, trust_shrink_ratio=None,
+            trust_expand_ratio=None):
+    """configs[4]: 14-DOF dual arm (both PR2 arms on torso_lift_link, tree FK), 40 waypoints, the "glass upright"
+    pattern of the reference's README (README.md:57-60): a CartPose constraint with pos_coeffs 0 and rot_coeffs (1,1,0)
+    per gripper on every free waypoint (zero coefficients are dropped by hatch, problem_description.cpp:910-926), a full
+    CartPose constraint per gripper at the last waypoint, discrete collision constraints (14 robot spheres x 8 obstacle
+    spheres) at every free waypoint, JointVel + JointAcc costs, fixed first waypoint, JOINT_INTERPOLATED initial
+    trajectory.  The goal of each gripper lies 0.15-0.30 m from its start position and is rotated about the upright axis
+    (the target frame's z) only, so that start and goal both satisfy the upright constraint; the goal joint state comes
+    from a host-side IK (problem generation), the pose target is FK(q_goal).  The trust-region sweep of SURVEY.md
+    section 8d overrides trust_box_size / trust_shrink_ratio / trust_expand_ratio."""
+    robot = robots.pr2_dual_arm()
+    rng = np.random.default_rng(seed)
+    D = 14
+    lo_q, hi_q = np.array(robot["lower"]), np.array(robot["upper"])
+    w_q = hi_q - lo_q
+    tools = (robot["tool"], robot["tool_left"])
+    arm_joints = (np.arange(0, 7), np.arange(7, 14))
+    q0 = np.zeros((B, D))
+    q1 = np.zeros((B, D))
+    targets = np.zeros((B, 2, 7))
+    radii = np.array([s.radius for s in robot["spheres"]])
+    obstacles = np.zeros((B, n_obstacles, 4))
+    lo, hi = np.array([0.30, -0.75, 0.50]), np.array([0.95, 0.75, 1.30])
+    for b in range(B):
+        while True:  # a start state whose two goals are reachable
+            qs = rng.uniform(lo_q + 0.2 * w_q, hi_q - 0.2 * w_q)
+            fr = robots.fk_numpy(robot, qs)
+            qg = qs.copy()
+            ok = True
+            for a, link in enumerate(tools):
+                R, p = fr[link]
+                v = rng.standard_normal(3)
+                step = v / np.linalg.norm(v) * rng.uniform(0.15, 0.30)
+                th = rng.uniform(-0.6, 0.6)
+                Rz = np.array([[np.cos(th), -np.sin(th), 0.0], [np.sin(th), np.cos(th), 0.0], [0.0, 0.0, 1.0]])
+                sol = _ik_to_pose(robot, qg, link, arm_joints[a], p + step, R @ Rz)
+                if sol is None:
+                    ok = False
+                    break
+                qg = sol
+            if ok:
+                break
+        q0[b], q1[b] = qs, qg
+        frg = robots.fk_numpy(robot, qg)
+        goals = []
+        for a, link in enumerate(tools):
+            R, p = frg[link]
+            targets[b, a, :3] = p
+            targets[b, a, 3:] = robots.rot_to_wxyz(R)
+            goals.append(p)
+        ends = np.concatenate([robots.sphere_centers(robot, qs), robots.sphere_centers(robot, qg)])
+        rr = np.concatenate([radii, radii])
+        k = 0
+        while k < n_obstacles:
+            c = rng.uniform(lo, hi)
+            if np.min(np.linalg.norm(ends - c, axis=1) - rr - 0.10) >= 0.05:
+                obstacles[b, k] = (*c, 0.10)
+                k += 1
+    init = interpolate(q0, q1, T)
+    terms = [joint_term(TERM_JOINT_VEL, ROLE_COST, D, 0, T - 1), joint_term(TERM_JOINT_ACC, ROLE_COST, D, 0, T - 1)]
+    for t in range(1, T - 1):
+        for a, link in enumerate(tools):
+            terms.append(cart_pose_term(ROLE_CNT, t, link, target_slot=a, pos_coeffs=(0, 0, 0), rot_coeffs=(1, 1, 0)))
+    for a, link in enumerate(tools):
+        terms.append(cart_pose_term(ROLE_CNT, T - 1, link, target_slot=a))
+    terms.append(collision_term(ROLE_CNT, 0, T - 1, margin=0.02, coeff=20.0, buffer=0.01, fixed_steps=[0]))
+    sqp = capi.default_sqp_params()
+    if trust_box_size is not None:
+        sqp.trust_box_size = trust_box_size
+    if trust_shrink_ratio is not None:
+        sqp.trust_shrink_ratio = trust_shrink_ratio
+    if trust_expand_ratio is not None:
+        sqp.trust_expand_ratio = trust_expand_ratio
+    return ProblemDesc(robot, T, terms, init, fixed_timesteps=[0], cart_targets=targets, obstacles=obstacles, sqp=sqp)
+
+
+# the trust-region sweep of configs[4] (SURVEY.md section 8d)
+CONFIG4_SWEEP = [(tb, sh, ex) for tb in (0.01, 0.05, 0.1, 0.5) for sh in (0.1, 0.5) for ex in (1.2, 1.5, 2.0)]
+
+CONFIGS = {"cfg0": config0, "cfg1": config1, "cfg2": config2, "cfg3": config3, "cfg4": config4, "variants": config_variants}
