@@ -21,8 +21,6 @@
 #ifndef TRAJOPT_B200_H
 #define TRAJOPT_B200_H
 
-#include <math.h>
-#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -33,8 +31,12 @@ extern "C" {
 #define TB200_VERSION_MINOR 1
 #define TB200_MAX_DOF 16      /* joints per manipulator group (7 single arm, 14 dual arm) */
 #define TB200_MAX_STEPS 64    /* waypoints per trajectory */
-#define TB200_MAX_LVS_LAYOUT 32 /* LVS collision evaluators: upper limit of the sub-segments per step pair that the
-                                   fixed candidate layout of a problem can be sized for (tb200inl_lvs_layout_segments) */
+#define TB200_CAST_ROWS_PER_PAIR 128 /* continuous collision evaluators: active contacts (rows) one step pair can hold.
+                                        The LVS sub-trajectory itself is as long as the reference's (ceil(dist/lvs)
+                                        sub-segments, collision_terms.cpp:1118-1155, unbounded); only contacts inside
+                                        margin + buffer take a row.  A step pair with more active contacts is never
+                                        truncated: its trajectory ends OPT_FAILED and the solve returns
+                                        TB200_ERR_UNSUPPORTED. */
 
 /* ---- return codes ------------------------------------------------------- */
 enum {
@@ -237,37 +239,6 @@ typedef struct tb200_layout {
   int32_t n_vars;           /* T*D */
   int32_t reserved;
 } tb200_layout;
-
-/* Sub-segments per step pair the candidate layout of an LVS collision term is sized for.  The reference's
- * sub-trajectory (CastCollisionEvaluator::CalcCollisions, collision_terms.cpp:1118-1155: cnt = ceil(dist/lvs) + 1
- * states) is unbounded; a fixed layout needs a bound, so it is taken per problem from the description's own initial
- * trajectories: need = max over the batch and the term's step pairs of ceil(||q[t+1] - q[t]|| / lvs), layout =
- * max(4, ceil(1.5 * need) + 1) — the SQP's trust region only moves waypoints a little per step.  A step pair that
- * comes to need MORE during a solve is never truncated: its trajectory ends OPT_FAILED and tb200_solve_batch returns
- * TB200_ERR_UNSUPPORTED.  Returns 0 when the description needs more than TB200_MAX_LVS_LAYOUT (problem_create then
- * fails with TB200_ERR_UNSUPPORTED).  The CPU oracle sizes its dense row output with the same function. */
-static inline int tb200inl_lvs_layout_segments(const tb200_problem_desc* d, const tb200_term* tm) {
-  const int T = d->n_steps, D = d->robot.n_dof;
-  double need = 1.0;
-  if (tm->evaluator_type != TB200_COLL_LVS_CONTINUOUS && tm->evaluator_type != TB200_COLL_LVS_DISCRETE) return 1;
-  if (!(tm->longest_valid_segment_length > 0.0)) return 0;
-  for (int b = 0; b < d->batch; ++b)
-    for (int t = tm->first_step; t < tm->last_step && t + 1 < T; ++t) {
-      const double* q0 = d->init_traj + ((size_t)b * T + (t < 0 ? 0 : t)) * D;
-      double s = 0.0;
-      for (int j = 0; j < D; ++j) s += (q0[D + j] - q0[j]) * (q0[D + j] - q0[j]);
-      s = sqrt(s);
-      if (s > tm->longest_valid_segment_length) {
-        const double n = ceil(s / tm->longest_valid_segment_length);
-        if (n > need) need = n;
-      }
-    }
-  {
-    double lay = ceil(1.5 * need) + 1.0;
-    if (lay < 4.0) lay = 4.0;
-    return lay > (double)TB200_MAX_LVS_LAYOUT ? 0 : (int)lay;
-  }
-}
 
 typedef struct tb200_problem tb200_problem; /* opaque handle; not thread-safe */
 

@@ -423,8 +423,9 @@ struct CollisionEval {
 // obstacle sphere is closed form (closest point of the centre segment, parameter s clamped to [0,1]).
 //   * LVS: ||q1-q0|| > longest_valid_segment_length  =>  ceil(dist/lvs) sub-segments between linearly
 //     interpolated joint states (the reference's LinSpaced sub-trajectory, :1118-1155), unbounded as in the
-//     reference.  Only the DENSE row output (denseRows, the layout the CUDA path is compared in) has a fixed
-//     number of slots per (sphere, obstacle): `layout_sub`, sized by tb200inl_lvs_layout_segments.
+//     reference.  The fixed-layout row output (denseRows, what the CUDA path is compared in) is the step pair's
+//     ACTIVE contacts in canonical order (sphere, obstacle, sub-segment) followed by zero rows up to
+//     TB200_CAST_ROWS_PER_PAIR.
 //     CONTINUOUS (evaluator 3) never subdivides (lvs = max double, problem_description.cpp:1782-1784).
 //   * cc_time of a contact in sub-segment i of n: (i + s)/n  (addInterpolatedCollisionResults [EXT]);
 //     type Time0 iff i == 0 and s == 0, Time1 iff i == n-1 and s == 1, else Between.
@@ -446,7 +447,6 @@ struct CastCollisionEval {
   int t, D;
   double margin, coeff, buffer, lvs;
   bool start_fixed, end_fixed;
-  int layout_sub;  // slots per (sphere, obstacle) of the dense row output
 
   int subSegments(const double* q0, const double* q1) const {
     double d2 = 0;
@@ -558,28 +558,25 @@ struct CastCollisionEval {
       exprs.push_back(cleanupAff(e));
     }
   }
-  // fixed GPU layout: candidate (sphere, obstacle, slot < layout_sub) -> {g0[D], g1[D], dist0, margin, coeff | 0}
+  // fixed GPU layout: the active contacts in canonical order -> {g0[D], g1[D], dist0, margin, coeff}, then zero rows
   void denseRows(const Vec& x, std::vector<Vec>& rows) const {
     std::vector<Cand> cands;
-    const int n = candidates(x, cands);
-    if (n > layout_sub) throw std::runtime_error("oracle: step pair needs more LVS sub-segments than the dense layout holds");
-    const size_t pairs = cands.size() / n;
-    for (size_t pr = 0; pr < pairs; ++pr)
-    for (int slot = 0; slot < layout_sub; ++slot) {
-      const Cand none{};
-      const Cand& cd = (slot < n) ? cands[pr * n + slot] : none;
+    candidates(x, cands);
+    int n_act = 0;
+    for (const Cand& cd : cands) {
+      if (!cd.exists || !cd.active) continue;
+      if (++n_act > TB200_CAST_ROWS_PER_PAIR) throw std::runtime_error("oracle: more active contacts in a step pair than TB200_CAST_ROWS_PER_PAIR");
       Vec row(2 * D + 3, 0.0);
-      if (cd.exists) {
-        for (int j = 0; j < D; ++j) {
-          row[j] = cd.ct.g0[j];
-          row[D + j] = cd.ct.g1[j];
-        }
-        row[2 * D] = cd.ct.dist;
-        row[2 * D + 1] = margin;
-        row[2 * D + 2] = cd.active ? coeff : 0.0;
+      for (int j = 0; j < D; ++j) {
+        row[j] = cd.ct.g0[j];
+        row[D + j] = cd.ct.g1[j];
       }
+      row[2 * D] = cd.ct.dist;
+      row[2 * D + 1] = margin;
+      row[2 * D + 2] = coeff;
       rows.push_back(row);
     }
+    for (; n_act < TB200_CAST_ROWS_PER_PAIR; ++n_act) rows.push_back(Vec(2 * D + 3, 0.0));
   }
   Vec values(const Vec& x) const {
     std::vector<Cand> cands;
@@ -682,22 +679,7 @@ QPSettings qpSettingsFrom(const tb200_qp_settings& q) {
   return s;
 }
 
-int lvsLayout(const tb200_problem_desc& desc) {
-  int lay = 1;
-  for (int k = 0; k < desc.n_terms; ++k) {
-    const tb200_term& tm = desc.terms[k];
-    if (tm.kind != TB200_TERM_COLLISION || tm.evaluator_type == TB200_COLL_DISCRETE) continue;
-    const int l = tb200inl_lvs_layout_segments(&desc, &tm);
-    if (l <= 0) return 0;
-    lay = std::max(lay, l);
-  }
-  return lay;
-}
-
-TrajProblem buildProblem(const tb200_problem_desc& desc, int b, int lvs_layout) {
-  if (lvs_layout < 0) lvs_layout = lvsLayout(desc);
-  // lvs_layout == 0 (beyond TB200_MAX_LVS_LAYOUT): the SQP path below is unbounded like the reference's and still
-  // runs; only the dense row output (denseRows) has no layout then and throws when asked for.
+TrajProblem buildProblem(const tb200_problem_desc& desc, int b) {
   TrajProblem tp;
   tp.robot = std::make_shared<Robot>(desc.robot);
   const int T = desc.n_steps, D = desc.robot.n_dof;
@@ -915,7 +897,7 @@ TrajProblem buildProblem(const tb200_problem_desc& desc, int b, int lvs_layout) 
             }
             // (two adjacent fixed steps fall into the START_FIXED_END_FREE branch: the reference's throw is unreachable)
             CastCollisionEval e{tp.robot, obstacles, t, D, tm.margin, tm.coeff, tm.margin_buffer, lvs, cur_fixed,
-                                !cur_fixed && next_fixed, lvs_layout};
+                                !cur_fixed && next_fixed};
             tp.coll_hooks.push_back([e](const Vec& x, std::vector<Vec>& rows) { e.denseRows(x, rows); });
             if (is_cost) {
               auto c = std::make_shared<CollisionCost>(calcOf(e));

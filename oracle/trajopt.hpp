@@ -61,10 +61,7 @@ struct TrajProblem {
 };
 // One trajectory `b` of the batched description -> the reference's TrajOptProb
 // (ConstructProblem, problem_description.cpp:410-542).
-// lvs_layout: slots per (sphere, obstacle) of the dense continuous-collision row output (lvsLayout(desc); < 0: compute)
-TrajProblem buildProblem(const tb200_problem_desc& desc, int b, int lvs_layout = -1);
-// max over the LVS collision terms of tb200inl_lvs_layout_segments (1 without such a term; 0: beyond the limit)
-int lvsLayout(const tb200_problem_desc& desc);
+TrajProblem buildProblem(const tb200_problem_desc& desc, int b);
 SQPParams sqpParamsFrom(const tb200_sqp_params& p);
 QPSettings qpSettingsFrom(const tb200_qp_settings& s);
 

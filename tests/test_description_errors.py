@@ -79,11 +79,9 @@ def test_full_size_configs_pass_validation():
     assert rc == ok, (rc, msg)
 
 
-def test_lvs_layout_beyond_the_limit_is_refused():
-    """A longest_valid_segment_length that needs more sub-segments per step pair than a layout can hold is refused at
-    problem_create (never truncated, collision_terms.cpp:1118-1155 is unbounded)."""
-    rc, msg = _create(problems.config3(B=1, T=12, via_every=4, lvs=1e-4))
-    assert rc == capi.ERR_UNSUPPORTED and "longest_valid_segment_length" in msg, (rc, msg)
+def test_non_positive_lvs_is_refused():
+    rc, msg = _create(problems.config3(B=1, T=12, via_every=4, lvs=0.0))
+    assert rc == capi.ERR_INVALID and "longest_valid_segment_length" in msg, (rc, msg)
 
 
 def test_null_arrays_with_positive_counts_are_refused():

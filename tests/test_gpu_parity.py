@@ -142,14 +142,20 @@ def test_headline_batch_matches_oracle(oracle):
     assert (got["status"] == capi.OPT_CONVERGED).mean() > 0.85
 
 
-def test_lvs_layout_overflow_is_reported():
-    """A step pair that comes to need more longest-valid-segment sub-segments than the layout sized from the initial
-    trajectory is never truncated: the solve returns TB200_ERR_UNSUPPORTED and the trajectory ends OPT_FAILED."""
-    d0 = problems.config3(B=2, T=8, via_every=4, lvs=0.02)
-    init = d0.init_traj[:, :1] + 1e-3 * np.arange(8)[None, :, None]  # an almost stationary initial trajectory: layout of 4
+def test_long_lvs_sub_trajectories(oracle):
+    """A step pair may need any number of longest-valid-segment sub-segments (collision_terms.cpp:1118-1155 is
+    unbounded): an almost stationary initial trajectory with lvs = 0.02 whose solution has steps of > 1 rad (60+
+    sub-segments) is solved like the oracle solves it."""
+    d0 = problems.config3(B=4, T=8, via_every=4, lvs=0.02)
+    init = d0.init_traj[:, :1] + 1e-3 * np.arange(8)[None, :, None]
     d = capi.ProblemDesc(d0.robot_spec, d0.T, d0.terms, init, fixed_timesteps=[0], cart_targets=d0.cart_targets, obstacles=d0.obstacles)
-    with pytest.raises(RuntimeError, match="sub-segments"):
-        api.solve(d)
+    got, hit = _solve_with_trace(d)
+    ref = oracle.solve_batch(d)
+    assert np.ceil(np.linalg.norm(np.diff(ref["x"], axis=1), axis=2) / 0.02).max() > 32
+    ok = ~hit
+    assert ok.any()
+    assert (got["status"][ok] == ref["status"][ok]).all() and (got["n_qp_solves"][ok] == ref["n_qp_solves"][ok]).all()
+    np.testing.assert_allclose(got["total_cost"][ok], ref["total_cost"][ok], rtol=5e-3)
 
 
 def test_joint_terms_cfg0(oracle):

@@ -310,38 +310,35 @@ def _cast_problem(lvs, T=6, B=3, seed=5):
     return problems.config3(B=B, T=T, seed=seed, via_every=2, lvs=lvs)
 
 
-def _lvs_layout(d, lvs):
-    """tb200inl_lvs_layout_segments (include/trajopt_b200.h): slots per (sphere, obstacle) of a step pair."""
-    step = np.linalg.norm(np.diff(d.init_traj, axis=1), axis=2)
-    need = max(1.0, np.ceil(step[step > lvs] / lvs).max(initial=1.0))
-    return int(max(4.0, np.ceil(1.5 * need) + 1.0))
+CAST_CAP = 128  # TB200_CAST_ROWS_PER_PAIR (include/trajopt_b200.h)
 
 
 def test_cast_collision_layout_and_activity(oracle):
-    lvs = 0.25
+    """Rows of the continuous evaluator: per step pair the ACTIVE contacts first (canonical order), zero rows after them;
+    the LVS sub-trajectory is as long as the reference's (unbounded, collision_terms.cpp:1118-1155)."""
+    lvs = 0.05
     d = _cast_problem(lvs)
     L = oracle.layout(d)
-    MS = _lvs_layout(d, lvs)
-    assert 4 < MS <= 32
     assert L.coll_row_stride == 2 * d.D + 3 and L.cart_jac_stride == 2 * d.D
-    assert L.n_coll_cand == (d.T - 1) * 7 * 8 * MS
+    assert L.n_coll_cand == (d.T - 1) * CAST_CAP
     x = d.init_traj + 0.02 * np.random.default_rng(3).standard_normal(d.init_traj.shape)
+    assert np.ceil(np.linalg.norm(np.diff(x, axis=1), axis=2) / lvs).max() > 16  # far beyond the cap of 4 this used to have
     r = oracle.convexify_batch(d, x)
-    rows = r["coll_rows"].reshape(d.B, d.T - 1, 7 * 8, MS, 2 * d.D + 3)
-    # sub-segments beyond ceil(|dq| / lvs) do not exist: all-zero rows (the count itself is unbounded, as in the
-    # reference: collision_terms.cpp:1118-1155)
-    step = np.linalg.norm(np.diff(x, axis=1), axis=2)
-    nsub = np.where(step > lvs, np.ceil(step / lvs), 1)
-    assert nsub.max() > 4  # more than the cap of 4 this layout used to have
+    rows = r["coll_rows"].reshape(d.B, d.T - 1, CAST_CAP, 2 * d.D + 3)
+    active = rows[..., -1] != 0
+    assert active.any()
     for b in range(d.B):
         for t in range(d.T - 1):
-            assert (rows[b, t, :, int(nsub[b, t]):] == 0).all()
-            assert (rows[b, t, :, :int(nsub[b, t]), 2 * d.D + 1] == 0.02).all()
+            n = int(active[b, t].sum())
+            assert active[b, t, :n].all() and (rows[b, t, n:] == 0).all()  # active rows first, then zero rows
+            assert (rows[b, t, :n, 2 * d.D + 1] == 0.02).all() and (rows[b, t, :n, 2 * d.D + 2] == 20.0).all()
+            assert (rows[b, t, :n, 2 * d.D] <= 0.02 + 0.01).all()  # only contacts inside margin + buffer take a row
     # the first pair starts at the fixed waypoint 0: its timestep-0 gradient block is empty
-    assert (rows[:, 0, :, :, :d.D] == 0).all()
-    # inactive candidates carry no gradient
-    inactive = rows[..., -1] == 0
-    assert (rows[inactive][:, :2 * d.D] == 0).all()
+    assert (rows[:, 0, :, :d.D] == 0).all()
+    # the exact violation of a pair's constraint is the sum of its rows' hinge terms (the collision pairs are the last
+    # T-1 constraint objects)
+    viol = (np.maximum(0.02 - rows[..., 2 * d.D], 0) * rows[..., -1]).sum(axis=2)
+    np.testing.assert_allclose(r["cnt_viols"][:, -(d.T - 1):], viol, atol=1e-12)
 
 
 def test_cast_collision_gradient_is_a_distance_derivative(oracle):
@@ -360,15 +357,17 @@ def test_cast_collision_gradient_is_a_distance_derivative(oracle):
         obst[b, 0, :3] = c + np.array([0.0, 0.0, 0.10 + robot["spheres"][5].radius + 0.015])
     d2 = capi.ProblemDesc(d.robot_spec, d.T, d.terms, x, fixed_timesteps=[0], cart_targets=d.cart_targets, obstacles=obst)
     r = oracle.convexify_batch(d2, x)
-    rows = r["coll_rows"].reshape(d.B, d.T - 1, 7, 8, 4, 2 * d.D + 3)  # (no subdivision: the minimum layout of 4 slots)
-    row = rows[0, 1, 5, 0, 0]  # pair (1,2), sphere 5, obstacle 0, first sub-segment
-    assert row[-1] != 0, "the contact must be active"
+    rows = r["coll_rows"].reshape(d.B, d.T - 1, CAST_CAP, 2 * d.D + 3)
+    act = np.nonzero(rows[0, 1, :, -1] != 0)[0]
+    assert len(act) >= 1, "pair (1,2) must hold the contact of sphere 5 against obstacle 0"
+    pick = lambda rr: rr[act[np.argmin(np.abs(rr[act, 2 * d.D] - 0.015))]]  # the contact built 0.015 away
+    row = pick(rows[0, 1])
     eps = 1e-6
     for k in range(2):
         for j in range(d.D):
             xp = x.copy()
             xp[0, 1 + k, j] += eps
-            rp = oracle.convexify_batch(d2, xp)["coll_rows"].reshape(rows.shape)[0, 1, 5, 0, 0]
+            rp = pick(oracle.convexify_batch(d2, xp)["coll_rows"].reshape(rows.shape)[0, 1])
             fd = (rp[2 * d.D] - row[2 * d.D]) / eps
             assert abs(fd - row[k * d.D + j]) < 2e-2 * max(1.0, abs(fd)), (k, j, fd, row[k * d.D + j])
 

@@ -33,7 +33,6 @@ enum ObjKind {
   OBJ_CART_VEL = 6,        // CartVel per step pair        kinematic_terms.cpp:368-425, problem_description.cpp:1011-1057
   OBJ_COLL_CAST = 7        // continuous (cast) collision per step pair  collision_terms.cpp:262-323, 468-538, 1071-1173
 };
-constexpr int kMaxLvsLayout = 32;  // = TB200_MAX_LVS_LAYOUT (include/trajopt_b200.h): upper limit of the per-problem bound
 struct DevObj {
   int kind;
   int is_cnt;     // 0 cost, 1 constraint
@@ -135,7 +134,7 @@ struct DevProblem {
   double* scratch;             // [B][5*Np]: dx dy stash(x zb yb)
   double* factor_g;            // [grid][3*M*nb*nb]: per-CTA home of a block-cyclic-reduction factor that does not fit
                                // shared memory (14 joints: blocks of 28); stays L2 resident
-  int* lvs_overflow;           // [B] 1: a step pair needed more LVS sub-segments than the candidate layout holds
+  int* lvs_overflow;           // [B] 1: a step pair had more active continuous-collision contacts than its row block holds
   int* qp_done;                // [B] 1: a QP solution is waiting for its evaluation
   int* ws_meta;                // [B][8]: warm-start key (n_aux, rows, nnzA, last status)
   double* ws_rho;              // [B]

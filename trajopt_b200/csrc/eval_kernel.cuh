@@ -21,10 +21,10 @@ struct EvalSmem {
   // offsets in doubles into the dynamic shared buffer
   int x, sph, spo, jax, velp, objv, mask, misc, fr, terms, obst, sphr, segs, sphs, cobj, aobj, wscr, wscr_stride, total;
 };
-// n_vel_objs: CartVel step pairs; cast: the collision objects are step pairs (continuous evaluator) with at most
-// max_sub LVS sub-segments each
+// n_vel_objs: CartVel step pairs; cast: the collision objects are step pairs (continuous evaluator), each holding at
+// most cast_cap active contacts
 __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_coll_objs, int n_mask_words, int S,
-                                                      int n_joint_objs, int n_vel_objs, int cast, int max_sub, int n_objs) {
+                                                      int n_joint_objs, int n_vel_objs, int cast, int cast_cap, int n_objs) {
   EvalSmem s;
   int o = 0;
   s.x = o;      o += T * D;
@@ -43,9 +43,10 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   s.mask = o;   o += n_mask_words;
   s.misc = o;   o += 8;
   o += o & 1;
-  // per-warp scratch of the cast collision objects: one set of frames, the sphere data of the interior
-  // sub-segment states, one joint vector
-  s.wscr_stride = cast ? (S * 12 + (max_sub - 1) * L * 6 + ((D + 1) & ~1)) : 0;
+  // per-warp scratch of the cast collision objects: one set of frames, the sphere centres at the two ends of the
+  // running sub-segment, one joint vector, and the contacts found so far: (s, dist) + key + rank per contact and
+  // their values in canonical order
+  s.wscr_stride = cast ? (S * 12 + 2 * L * 3 + (L & 1) + ((D + 1) & ~1) + 4 * cast_cap) : 0;
   s.wscr = o;   o += 8 * s.wscr_stride;
   // the FK frames are dead once the joint axes / sphere centres are emitted: the term buffer of the later
   // phase reuses their space
@@ -63,8 +64,8 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
 
 struct EvalExtra {
   int n_cart_objs, n_coll_objs, n_joint_objs, n_vel_objs;
-  int cast, max_sub;                 // cast: the collision objects are step pairs (continuous evaluator), each with at
-                                     // most max_sub LVS sub-segments in the candidate layout
+  int cast, cast_cap;                // cast: the collision objects are step pairs (continuous evaluator), each with room
+                                     // for cast_cap active contacts (rows)
   const int* link_chain;             // [S][kMaxSeg + 1]: per segment, the number of segments on its chain from the root,
                                      // then the chain itself (root first, the segment last)
   const DevObj* vel_objs;            // CartVel step pairs
@@ -136,7 +137,7 @@ __device__ inline void warp_fk(const DevProblem& p, const double* q, double* F, 
 }
 
 template <int DD>
-__device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& ex, const int mode, const int b,
+__device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex, const int mode, const int b,
                                           const double* x_in /*EVAL_ONLY*/) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
@@ -149,7 +150,7 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
   if (tid == 0 && !qp_failed) atomicAdd(p.active_count + 1, 1);  // trajectories actually convexified (bench: bytes moved)
   const int n_mask_words = p.n_coll_objs * p.coll_words;
   const EvalSmem S = eval_smem_layout(T, D, L, p.n_coll_objs, n_mask_words, p.S, ex.n_joint_objs, ex.n_vel_objs,
-                                      ex.cast, ex.max_sub, p.n_costs + p.n_cnts);
+                                      ex.cast, ex.cast_cap, p.n_costs + p.n_cnts);
   static_assert(sizeof(DevObj) % 8 == 0 && sizeof(DevSegment) % 8 == 0 && sizeof(DevSphere) % 8 == 0, "tables are copied as doubles");
   const DevObj* cobjs = reinterpret_cast<const DevObj*>(sm + S.cobj);
   const DevObj* aobjs = reinterpret_cast<const DevObj*>(sm + S.aobj);
@@ -473,12 +474,14 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
       } else {
         // ---- continuous ("cast") collision of the step pair (t, t+1): collision_terms.cpp:262-323, 468-538,
         // 1071-1173 with the closed-form swept sphere (capsule) of SURVEY.md section 8d; the same rules as the oracle's
-        // CastCollisionEval.  candidate = (robot sphere, obstacle, sub-segment); row = {g0[D], g1[D], dist, margin,
-        // coeff|0}.  The gradients need one FK per ACTIVE contact (at its own contact-time state), done by the warp.
-        // MS sub-segments fit the candidate layout (sized at tb200_problem_create from the initial trajectories); a
-        // step pair that needs more raises the trajectory's overflow flag and the solve reports it (never truncated
-        // silently: the reference's sub-trajectory is unbounded, collision_terms.cpp:1118-1155).
-        const int MS = ex.max_sub;
+        // CastCollisionEval.  The sub-trajectory is as long as the reference's (nsub = ceil(|q1 - q0| / lvs), unbounded,
+        // :1118-1155).  Pass 1 walks the sub-segments one after the other (one warp FK per interior state, the centres of
+        // the two ends of the running sub-segment in shared memory) and lists the ACTIVE contacts (sphere, obstacle,
+        // sub-segment).  Pass 2 ranks them in the reference's order (link pair, then sub-segment) and writes one row
+        // {g0[D], g1[D], dist, margin, coeff} per contact into slot `rank` of the pair's row block; the mask of the pair
+        // has its low `count` bits set, so the QP step picks the rows up like any other active candidates.  The gradients
+        // need FKs per ACTIVE contact only (both ends of its sub-segment and its contact-time state).
+        const int CAP = ex.cast_cap, CS = 2 * D + 3;
         const bool sfix = co.pad1 & 1, efix = co.pad1 & 2;
         const double* q0 = xs + t * D;
         const double* q1 = q0 + D;
@@ -487,111 +490,166 @@ __device__ __forceinline__ void eval_step(const DevProblem& p, const EvalExtra& 
         for (int j = 0; j < D; ++j) d2 += (q1[j] - q0[j]) * (q1[j] - q0[j]);
         const double qd = sqrt(d2);
         int nsub = 1;
+        bool overflow = false;
         if (qd > co.lvs) {
           const double nn = ceil(qd / co.lvs);
-          if (nn > MS) {
-            if (lane_c == 0) p.lvs_overflow[b] = 1;
-            nsub = MS;
-          } else {
-            nsub = static_cast<int>(nn);
-          }
+          overflow = nn > 32767.0;  // (the contact key holds the sub-segment in 15 bits)
+          nsub = overflow ? 32767 : static_cast<int>(nn);
         }
         double* F = sm + S.wscr + (tid >> 5) * S.wscr_stride;  // frames of one state
-        double* sub = F + p.S * 12;                             // [MS-1][L][6]: centre, centre - link origin
-        double* qv = sub + (MS - 1) * L * 6;
-        for (int i = 1; i < nsub; ++i) {  // interior states of the LinSpaced sub-trajectory
-          if (lane_c < D) qv[lane_c] = q0[lane_c] + (q1[lane_c] - q0[lane_c]) * (static_cast<double>(i) / nsub);
-          __syncwarp();
-          warp_fk(p, qv, F, lane_c);
-          for (int w = lane_c; w < L; w += 32) {
-            const DevSphere sp = p.spheres[w];
-            const double* f = F + sp.segment * 12;
-            double* o6 = sub + ((i - 1) * L + w) * 6;
-            for (int a = 0; a < 3; ++a) {
-              const double off = f[a * 3] * sp.c[0] + f[a * 3 + 1] * sp.c[1] + f[a * 3 + 2] * sp.c[2];
-              o6[a] = off + f[9 + a];
-              o6[3 + a] = off;
+        double* cenA = F + p.S * 12;                            // [L][3] sphere centres at the start of the sub-segment
+        double* cenB = cenA + L * 3;                            // ... and at its end
+        double* qv = cenB + L * 3 + (L & 1);
+        double* csd = qv + ((D + 1) & ~1);                      // [CAP][2]: contact parameter s, distance
+        int* ckey = reinterpret_cast<int*>(csd + 2 * CAP);      // [CAP] (sphere * O + obstacle) << 15 | sub-segment
+        int* crank = ckey + CAP;                                // [CAP]
+        double* cval = csd + 3 * CAP;                           // [CAP] hinge values in canonical order
+        // centres of every sphere at the state `frac` of the way from q0 to q1 (i = 0 / nsub: the waypoints themselves)
+        auto centres_at = [&](int i, double* dstc) {
+          if (i == 0 || i == nsub) {
+            const double* src = sm + S.sph + ((i == 0 ? t : t + 1) * L) * 3;
+            for (int w = lane_c; w < L * 3; w += 32) dstc[w] = src[w];
+          } else {
+            if (lane_c < D) qv[lane_c] = q0[lane_c] + (q1[lane_c] - q0[lane_c]) * (static_cast<double>(i) / nsub);
+            __syncwarp();
+            warp_fk(p, qv, F, lane_c);
+            for (int w = lane_c; w < L; w += 32) {
+              const DevSphere& sp = sphs[w];
+              const double* f = F + sp.segment * 12;
+              for (int a = 0; a < 3; ++a)
+                dstc[w * 3 + a] = f[a * 3] * sp.c[0] + f[a * 3 + 1] * sp.c[1] + f[a * 3 + 2] * sp.c[2] + f[9 + a];
             }
           }
           __syncwarp();
+        };
+        int count = 0;
+        centres_at(0, cenA);
+        for (int i = 0; i < nsub; ++i) {
+          centres_at(i + 1, cenB);
+          for (int c0 = 0; c0 < LO; c0 += 32) {
+            const int pr = c0 + lane_c;
+            const bool in = pr < LO;
+            const int sl = in ? static_cast<int>((static_cast<float>(pr) + 0.5f) * inv_O) : 0, o = in ? pr - sl * O : 0;
+            const double* ca = cenA + sl * 3;
+            const double* cb = cenB + sl * 3;
+            const double4 ob = *reinterpret_cast<const double4*>(obst + o * 4);
+            const double wx = cb[0] - ca[0], wy = cb[1] - ca[1], wz = cb[2] - ca[2];
+            const double ww = wx * wx + wy * wy + wz * wz;
+            const double wd = (ob.x - ca[0]) * wx + (ob.y - ca[1]) * wy + (ob.z - ca[2]) * wz;
+            double sc = (ww > 0.0) ? wd / ww : 0.0;
+            sc = sc < 0.0 ? 0.0 : (sc > 1.0 ? 1.0 : sc);
+            const double dx = ob.x - (ca[0] + sc * wx), dy = ob.y - (ca[1] + sc * wy), dz = ob.z - (ca[2] + sc * wz);
+            const double len = sqrt(dx * dx + dy * dy + dz * dz);
+            const double dist = len - sm[S.sphr + sl] - ob.w;
+            const bool time0 = (i == 0 && sc == 0.0), time1 = (i == nsub - 1 && sc == 1.0);
+            const bool active = in && !(dist > reach) && !(sfix && time0) && !(efix && time1);
+            const unsigned bal = __ballot_sync(0xffffffffu, active);
+            const int pos = count + __popc(bal & ((1u << lane_c) - 1u));
+            if (active && pos < CAP) {
+              csd[2 * pos] = sc;
+              csd[2 * pos + 1] = dist;
+              ckey[pos] = (pr << 15) | i;
+            }
+            count += __popc(bal);
+          }
+          __syncwarp();
+          for (int w = lane_c; w < L * 3; w += 32) cenA[w] = cenB[w];  // the end of this sub-segment starts the next
+          __syncwarp();
         }
-        const int NC = LO * MS, CS = 2 * D + 3;
-        for (int c0 = 0; c0 < NC; c0 += 32) {
-          const int cnd = c0 + lane_c;
-          const bool in = cnd < NC;
-          const int pr = in ? cnd / MS : 0, i = cnd % MS;
-          const int sl = static_cast<int>((static_cast<float>(pr) + 0.5f) * inv_O), o = pr - sl * O;
-          const bool exists = in && i < nsub;
-          const int ia = exists ? i : 0;
-          const double* ca = (ia == 0) ? sm + S.sph + (t * L + sl) * 3 : sub + ((ia - 1) * L + sl) * 6;
-          const double* cb = (ia + 1 >= nsub) ? sm + S.sph + ((t + 1) * L + sl) * 3 : sub + (ia * L + sl) * 6;
-          const double4 ob = *reinterpret_cast<const double4*>(obst + o * 4);
+        if (count > CAP) {
+          overflow = true;
+          count = CAP;
+        }
+        if (overflow && lane_c == 0) p.lvs_overflow[b] = 1;
+        // ranks in the reference's order: link pair (sphere, obstacle) first, then the sub-segment (keys are unique)
+        for (int c = lane_c; c < count; c += 32) {
+          const int key = ckey[c];
+          int r = 0;
+          for (int c2 = 0; c2 < count; ++c2) r += ckey[c2] < key;
+          crank[c] = r;
+          cval[r] = fmax(margin - csd[2 * c + 1], 0.0) * coeff;
+        }
+        __syncwarp();
+        for (int c = 0; c < count; ++c) {  // warp-uniform loop over the active contacts
+          const int key = ckey[c], i_s = key & 32767, pr_s = key >> 15;
+          const int sl_s = static_cast<int>((static_cast<float>(pr_s) + 0.5f) * inv_O), o_s = pr_s - sl_s * O;
+          const double sc = csd[2 * c], dist = csd[2 * c + 1];
+          const DevSphere& sp = sphs[sl_s];
+          // centre and offset (centre - link origin = R_link * c_local) of the sphere at both ends of its sub-segment
+          double ca[3], cb[3], offa[3], offb[3];
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int st = i_s + kk;
+            double* cc3 = kk ? cb : ca;
+            double* of3 = kk ? offb : offa;
+            if (st == 0 || st == nsub) {
+              const int wp = (st == 0) ? t : t + 1;
+#pragma unroll
+              for (int a = 0; a < 3; ++a) {
+                cc3[a] = sm[S.sph + (wp * L + sl_s) * 3 + a];
+                of3[a] = sm[S.spo + (wp * L + sl_s) * 3 + a];
+              }
+            } else {
+              if (lane_c < D) qv[lane_c] = q0[lane_c] + (q1[lane_c] - q0[lane_c]) * (static_cast<double>(st) / nsub);
+              __syncwarp();
+              warp_fk(p, qv, F, lane_c);
+              const double* f = F + sp.segment * 12;
+#pragma unroll
+              for (int a = 0; a < 3; ++a) {
+                const double off = f[a * 3] * sp.c[0] + f[a * 3 + 1] * sp.c[1] + f[a * 3 + 2] * sp.c[2];
+                of3[a] = off;
+                cc3[a] = off + f[9 + a];
+              }
+              __syncwarp();
+            }
+          }
+          const double4 ob = *reinterpret_cast<const double4*>(obst + o_s * 4);
           const double wx = cb[0] - ca[0], wy = cb[1] - ca[1], wz = cb[2] - ca[2];
-          const double ww = wx * wx + wy * wy + wz * wz;
-          const double wd = (ob.x - ca[0]) * wx + (ob.y - ca[1]) * wy + (ob.z - ca[2]) * wz;
-          double sc = (ww > 0.0) ? wd / ww : 0.0;
-          sc = sc < 0.0 ? 0.0 : (sc > 1.0 ? 1.0 : sc);
           const double dx = ob.x - (ca[0] + sc * wx), dy = ob.y - (ca[1] + sc * wy), dz = ob.z - (ca[2] + sc * wz);
           const double len = sqrt(dx * dx + dy * dy + dz * dz);
-          const double dist = len - sm[S.sphr + sl] - ob.w;
-          const double cc = (ia + sc) / nsub;
-          const double nx = dx / len, ny = dy / len, nz = dz / len;
-          const bool time0 = (ia == 0 && sc == 0.0), time1 = (ia == nsub - 1 && sc == 1.0);
-          const bool active = exists && !(dist > reach) && !(sfix && time0) && !(efix && time1);
-          if (in) {
-            double* dstp = rows_out + static_cast<size_t>(co.src_off + cnd) * CS;
+          const double nxs = dx / len, nys = dy / len, nzs = dz / len;
+          const double cc_s = (i_s + sc) / nsub;
+          if (lane_c < D) qv[lane_c] = (cc_s == 1.0) ? q1[lane_c] : q0[lane_c] + (q1[lane_c] - q0[lane_c]) * cc_s;
+          __syncwarp();
+          warp_fk(p, qv, F, lane_c);  // Jacobian at the contact-time state (GetGradient, :276-285)
+          double* rowp = rows_out + static_cast<size_t>(co.src_off + crank[c]) * CS;
+          if (lane_c < D) {
+            const int j = lane_c, sg = ex.joint_seg[j];
+            const DevSegment& g = segs[sg];
+            const double* f = F + sg * 12;
+            const double* pl = F + sp.segment * 12 + 9;
+            const double ax = f[0] * g.axis[0] + f[1] * g.axis[1] + f[2] * g.axis[2];
+            const double ay = f[3] * g.axis[0] + f[4] * g.axis[1] + f[5] * g.axis[2];
+            const double az = f[6] * g.axis[0] + f[7] * g.axis[1] + f[8] * g.axis[2];
+            const bool moves = (ex.sphere_jmask[sl_s] >> j) & 1u, rev = g.joint_type == 1;
 #pragma unroll
-            for (int j = 0; j < 2 * D; ++j) dstp[j] = 0.0;
-            dstp[2 * D] = exists ? dist : 0.0;
-            dstp[2 * D + 1] = exists ? margin : 0.0;
-            dstp[2 * D + 2] = active ? coeff : 0.0;
-          }
-          const unsigned bal = __ballot_sync(0xffffffffu, active);
-          if (lane_c == 0 && bal) atomicOr(&mask[k * p.coll_words + (c0 >> 6)], static_cast<unsigned long long>(bal) << (c0 & 63));
-          const double mine = active ? fmax(margin - dist, 0.0) * coeff : 0.0;
-          unsigned nzb = __ballot_sync(0xffffffffu, mine != 0.0);
-          while (nzb) {
-            vsum += __shfl_sync(0xffffffffu, mine, __ffs(nzb) - 1);
-            nzb &= nzb - 1;
-          }
-          __syncwarp();  // the zero-filled rows are written before the gradients of the active ones
-          unsigned todo = bal;
-          while (todo) {  // warp-uniform loop over the active contacts of this chunk
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int sl_s = __shfl_sync(0xffffffffu, sl, src), i_s = __shfl_sync(0xffffffffu, ia, src);
-            const double cc_s = __shfl_sync(0xffffffffu, cc, src);
-            const double nxs = __shfl_sync(0xffffffffu, nx, src), nys = __shfl_sync(0xffffffffu, ny, src),
-                         nzs = __shfl_sync(0xffffffffu, nz, src);
-            if (lane_c < D) qv[lane_c] = (cc_s == 1.0) ? q1[lane_c] : q0[lane_c] + (q1[lane_c] - q0[lane_c]) * cc_s;
-            __syncwarp();
-            warp_fk(p, qv, F, lane_c);  // Jacobian at the contact-time state (GetGradient, :276-285)
-            if (lane_c < D) {
-              const int j = lane_c, sg = ex.joint_seg[j];
-              const DevSegment& g = p.segs[sg];
-              const double* f = F + sg * 12;
-              const double* pl = F + p.spheres[sl_s].segment * 12 + 9;
-              const double ax = f[0] * g.axis[0] + f[1] * g.axis[1] + f[2] * g.axis[2];
-              const double ay = f[3] * g.axis[0] + f[4] * g.axis[1] + f[5] * g.axis[2];
-              const double az = f[6] * g.axis[0] + f[7] * g.axis[1] + f[8] * g.axis[2];
-              const bool moves = (ex.sphere_jmask[sl_s] >> j) & 1u, rev = g.joint_type == 1;
-              double* rowp = rows_out + static_cast<size_t>(co.src_off + c0 + src) * CS;
-              for (int kk = 0; kk < 2; ++kk) {
-                if ((kk == 0 && sfix) || (kk == 1 && efix)) continue;  // a fixed side contributes nothing
+            for (int kk = 0; kk < 2; ++kk) {
+              double gg = 0.0;
+              if (!((kk == 0 && sfix) || (kk == 1 && efix))) {  // a fixed side contributes nothing
                 // reference point: link origin at the contact-time state + R_link(sub-segment start | end) * c_local
-                const int st = i_s + kk;
-                const double* off = (st == 0) ? sm + S.spo + (t * L + sl_s) * 3
-                                    : (st >= nsub) ? sm + S.spo + ((t + 1) * L + sl_s) * 3 : sub + ((st - 1) * L + sl_s) * 6 + 3;
+                const double* off = kk ? offb : offa;
                 const double rx = pl[0] + off[0] - f[9], ry = pl[1] + off[1] - f[10], rz = pl[2] + off[2] - f[11];
                 const double jx = rev ? ay * rz - az * ry : ax, jy = rev ? az * rx - ax * rz : ay,
                              jz = rev ? ax * ry - ay * rx : az;
-                const double gg = -(nxs * jx + nys * jy + nzs * jz) * (kk == 0 ? 1.0 - cc_s : cc_s);
-                rowp[kk * D + j] = moves ? gg : 0.0;
+                gg = -(nxs * jx + nys * jy + nzs * jz) * (kk == 0 ? 1.0 - cc_s : cc_s);
               }
+              rowp[kk * D + j] = moves ? gg : 0.0;
             }
-            __syncwarp();
           }
+          if (lane_c == 0) {
+            rowp[2 * D] = dist;
+            rowp[2 * D + 1] = margin;
+            rowp[2 * D + 2] = coeff;
+          }
+          __syncwarp();
         }
+        // the pair's mask: its first `count` row slots are active; its exact value: the hinge terms in canonical order
+        for (int w = lane_c; w < p.coll_words; w += 32) {
+          const int lo = w * 64;
+          mask[k * p.coll_words + w] = (count >= lo + 64) ? ~0ull : ((count > lo) ? ((1ull << (count - lo)) - 1ull) : 0ull);
+        }
+        if (lane_c == 0)
+          for (int c = 0; c < count; ++c) vsum += cval[c];
       }
       if (lane_c == 0) sm[S.objv + k] = vsum;
     }

@@ -689,7 +689,7 @@ __device__ __forceinline__ double xbound_weight(const QpCtx& q, const SysW& w, i
 // K = P + sig I + A' W A with the aux variables eliminated, written straight into the block storage
 // (SA: diagonal blocks, SLM: left couplings); one thread per matrix row; then factor.
 template <int NB>
-__device__ inline bool assemble_factor(const QpCtx& q, const SysW& w) {
+__device__ __noinline__ bool assemble_factor(const QpCtx& q, const SysW& w) {
   PROF_T0();
   rows_prepare_weights(q, w);
   constexpr int nb = NB, blk = NB * NB;
@@ -780,6 +780,173 @@ __device__ __forceinline__ void row_backsub(const double* F, double zeta, double
 }
 __device__ __forceinline__ double row_reduce_coef(const double* F, double ra0, double ra1, double zcoef) {
   return zcoef - F[R_WRR] * (F[R_U0] * ra0 * F[R_G1] + F[R_U1] * ra1 * F[R_G0]) * F[R_IDEN];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A block of ADMM iterations (no termination test inside): its own function (not inlined), so that the loop the
+// whole batch time hangs on has its own register allocation and sits in one contiguous piece of code — the rest of
+// the solver (scaling, residuals, certificates, polish, factorisation) cannot spill into it or push it out of the
+// instruction cache.  REG: the thread's rows of the factor live in registers for the whole block (reloaded from the
+// factor in shared memory at entry: ~100 loads per 25 iterations); else the generic solve reads them from memory.
+// Rows are handled by the high thread ids so that they run beside the per-variable work of the low ones.  Every
+// iteration leaves the aux right-hand sides R_RA0/1, the row multiplier R_COEF and the rows' contributions to the
+// right-hand side of the next solve behind; the entry pass (re)builds them because the residual passes, the polish
+// and a refactorisation reuse those fields.  keep_last: the last iteration records its primal / dual steps (dxs, dyb)
+// for the infeasibility certificates.
+template <int NB, int PAIR, bool REG>
+__device__ __noinline__ void admm_block(const QpCtx& q, const double rho_aux, const int n_iter, const int keep_last) {
+  constexpr int CNc = PAIR ? ((NB > 3) ? NB : 3) : ((NB / 2 > 3) ? NB / 2 : 3);
+  constexpr int RNB = REG ? NB : 2;
+  const int N = q.N, tid = q.tid;
+  double* const dxs = q.scratch;
+  double* const dyb = q.scratch + q.Np;
+  SolveRoles roles{};
+  double mF0[RNB], mB0[RNB + RNB / 2], mFU[RNB], mBU[RNB + RNB / 2];
+  if constexpr (REG) {
+    roles = solve_roles<NB>(q);
+    load_fwd_row<NB>(q, 0, tid, mF0);
+    load_bwd_row<NB>(q, 0, tid, mB0);
+    int off = 0;
+    for (int l = 1; l < roles.n_fwd; ++l) {
+      const int cnt = 2 * (q.M >> (l + 1)) * NB;
+      if (roles.fu_level == l) load_fwd_row<NB>(q, l, tid - off, mFU);
+      off += cnt;
+    }
+    off = 0;
+    for (int l = 1; l < roles.n_lvl; ++l) {
+      const int cnt = 2 * ((q.M + (1 << l)) >> (l + 1)) * NB;
+      if (roles.bu_level == l) load_bwd_row<NB>(q, l, tid - off, mBU);
+      off += cnt;
+    }
+  }
+  const bool one_var = REG || q.Np <= kQpThreads;  // one thread per variable: its column range is loop invariant
+  const int my_e0 = (one_var && tid < N) ? q.colptr[tid] : 0, my_e1 = (one_var && tid < N) ? q.colptr[tid + 1] : 0;
+  {  // entry pass: aux right-hand sides, row multipliers and contributions from the current row state
+    PROF_T0();
+    for (int r = kQpThreads - 1 - tid; r < q.nrows; r += kQpThreads) {
+      double* F = q.F(r);
+      const double s = F[R_WRR] * F[R_Z] - F[R_Y];
+      const double ra0 = q.sigma * F[R_XA0] - F[R_QA0] + F[R_U0] * s + F[R_B0] * (rho_aux * F[R_ZA0] - F[R_YA0]);
+      const double ra1 = q.sigma * F[R_XA1] - F[R_QA1] + F[R_U1] * s + F[R_B1] * (rho_aux * F[R_ZA1] - F[R_YA1]);
+      F[R_RA0] = ra0;
+      F[R_RA1] = ra1;
+      const double cf = row_reduce_coef(F, ra0, ra1, s);
+      F[R_COEF] = cf;
+      const double* as = q.R(r) + CNc;
+#pragma unroll
+      for (int k = 0; k < CNc; ++k) F[R_NF + k] = as[k] * cf;
+    }
+    __syncthreads();
+    PROF_ADD(0);
+  }
+  const double inv_rho_aux = 1.0 / rho_aux;
+  const double inv_rho = 1.0 / q.rho, inv_rho_eq = 1.0 / q.rho_eq;
+  for (int it = 0; it < n_iter; ++it) {
+    const bool keep_steps = keep_last && it == n_iter - 1;
+    // right-hand side  sigma x - q + A'(rho z - y)  (one thread per variable; the rows left their terms behind)
+    {
+      PROF_T0();
+      if (one_var) {
+        const int i = tid;
+        double s = 0.0;
+        if (i < N) {
+          const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
+          s = q.sigma * q.x[i] - q.qs[i] + q.beta[i] * (rb * q.zb[i] - q.yb[i]);
+          for (int e = my_e0; e < my_e1; ++e) {
+            const int ent = q.colent[e];
+            s += q.rows[static_cast<size_t>(ent >> 5) * q.RS + (2 * CNc + R_NF) + (ent & 31)];
+          }
+        }
+        if (i < q.Np) q.v1[i] = s;
+      } else {
+        for (int i = tid; i < q.Np; i += kQpThreads) {
+          double s = 0.0;
+          if (i < N) {
+            const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
+            s = q.sigma * q.x[i] - q.qs[i] + q.beta[i] * (rb * q.zb[i] - q.yb[i]);
+            for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
+              const int ent = q.colent[e];
+              s += q.rows[static_cast<size_t>(ent >> 5) * q.RS + (2 * CNc + R_NF) + (ent & 31)];
+            }
+          }
+          q.v1[i] = s;
+        }
+      }
+      PROF_ADD(1);
+    }
+    {
+      PROF_T0();
+      if constexpr (REG) bcr_solve_reg<NB>(q, roles, mF0, mB0, mFU, mBU, q.v1, q.w);
+      else bcr_solve<NB>(q, q.v1, q.w);
+      PROF_ADD(2);
+    }
+    PROF_T0();
+    // rows: back-substitute aux, relax, project, dual update, and the multipliers for the next solve
+    for (int r = kQpThreads - 1 - tid; r < q.nrows; r += kQpThreads) {
+      const double* R = q.R(r);
+      double* F = q.F(r);
+      const double zeta = row_dot<CNc>(q, R, q.I(r), q.w);
+      double a0, a1;
+      row_backsub(F, zeta, a0, a1);
+      const double zt = zeta + F[R_U0] * a0 + F[R_U1] * a1;
+      const double Wr = F[R_WRR];
+      const double zr = q.alpha * zt + (1.0 - q.alpha) * F[R_Z];
+      double zn = zr + F[R_Y] * F[R_IWRR];
+      zn = fmin(fmax(zn, F[R_LO]), F[R_UP]);
+      const double dy = Wr * (zr - zn);
+      const double yn = F[R_Y] + dy;
+      F[R_Z] = zn;
+      F[R_Y] = yn;
+      F[R_DY] = dy;
+      const double s = Wr * zn - yn;
+      double ra[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double at = k ? a1 : a0, bb = F[R_B0 + k];
+        const double xo = F[R_XA0 + k];
+        const double xn = q.alpha * at + (1.0 - q.alpha) * xo;
+        const double zra = q.alpha * (bb * at) + (1.0 - q.alpha) * F[R_ZA0 + k];
+        double z2 = zra + F[R_YA0 + k] * inv_rho_aux;
+        z2 = fmin(fmax(z2, 0.0), kOsqpInf * F[R_EA0 + k]);
+        const double dya = rho_aux * (zra - z2);
+        const double yan = F[R_YA0 + k] + dya;
+        F[R_XA0 + k] = xn;
+        F[R_DXA0 + k] = xn - xo;
+        F[R_ZA0 + k] = z2;
+        F[R_YA0 + k] = yan;
+        F[R_DYA0 + k] = dya;
+        ra[k] = q.sigma * xn - F[R_QA0 + k] + F[R_U0 + k] * s + bb * (rho_aux * z2 - yan);
+      }
+      F[R_RA0] = ra[0];
+      F[R_RA1] = ra[1];
+      const double cf = row_reduce_coef(F, ra[0], ra[1], s);
+      F[R_COEF] = cf;
+#pragma unroll
+      for (int k = 0; k < CNc; ++k) F[R_NF + k] = R[CNc + k] * cf;
+    }
+    // trajectory variables and their bound rows (one thread per variable)
+    for (int i = tid; i < N; i += kQpThreads) {
+      const double beta = q.beta[i];
+      const double lb = q.lbs[i], ub = q.ubs[i];
+      const bool beq = ub - lb < kRhoTol;
+      const double rb = beq ? q.rho_eq : q.rho, irb = beq ? inv_rho_eq : inv_rho;
+      const double xt = q.w[i];
+      const double xn = q.alpha * xt + (1.0 - q.alpha) * q.x[i];
+      const double zr = q.alpha * (beta * xt) + (1.0 - q.alpha) * q.zb[i];
+      double zn = zr + q.yb[i] * irb;
+      zn = fmin(fmax(zn, lb), ub);
+      const double dy = rb * (zr - zn);
+      if (keep_steps) {
+        dxs[i] = xn - q.x[i];
+        dyb[i] = dy;
+      }
+      q.x[i] = xn;
+      q.zb[i] = zn;
+      q.yb[i] += dy;
+    }
+    __syncthreads();
+    PROF_ADD(3);
+  }
 }
 
 // Ruiz equilibration (scale_data of OSQP [EXT]); leaves the scaled view of every row in its record and the
@@ -973,41 +1140,16 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
   SysW sysw{false, st.sigma, rho};
   bool factor_ok = true;
   { PROF_T0(); factor_ok = assemble_factor<NB>(q, sysw); PROF_ADD(6); }
-  // the thread's rows of the ADMM factor, kept in registers between refactorisations (when the roles fit the CTA)
+  // the ADMM loop keeps the thread's rows of the factor in registers when the roles fit the CTA (admm_block<.., true>)
   const bool use_reg = REGOK && solve_roles_fit(q.M, NB);
-  constexpr int RNB = REGOK ? NB : 2;  // (no register rows in instances that never use them)
-  const SolveRoles roles = use_reg ? solve_roles<NB>(q) : SolveRoles{};
-  const bool one_var = q.Np <= kQpThreads;  // one thread per variable: its column range is loop invariant
-  const int my_e0 = (one_var && tid < N) ? q.colptr[tid] : 0, my_e1 = (one_var && tid < N) ? q.colptr[tid + 1] : 0;
-  double mF0[RNB], mB0[RNB + RNB / 2], mFU[RNB], mBU[RNB + RNB / 2];
-  auto solve_sys = [&](double* v, double* w) {  // K w = v with the current factor (v is overwritten)
+  auto run_block = [&](int n, bool keep_last) {
     if constexpr (REGOK) {
       if (use_reg) {
-        bcr_solve_reg<NB>(q, roles, mF0, mB0, mFU, mBU, v, w);
+        admm_block<NB, PAIR, true>(q, sysw.rho_aux, n, keep_last ? 1 : 0);
         return;
       }
     }
-    bcr_solve<NB>(q, v, w);
-  };
-  auto load_factor_regs = [&]() {
-    if constexpr (!REGOK) return;
-    else {
-    if (!use_reg) return;
-    load_fwd_row<NB>(q, 0, tid, mF0);
-    load_bwd_row<NB>(q, 0, tid, mB0);
-    int off = 0;
-    for (int l = 1; l < roles.n_fwd; ++l) {
-      const int cnt = 2 * (q.M >> (l + 1)) * NB;
-      if (roles.fu_level == l) load_fwd_row<NB>(q, l, tid - off, mFU);
-      off += cnt;
-    }
-    off = 0;
-    for (int l = 1; l < roles.n_lvl; ++l) {
-      const int cnt = 2 * ((q.M + (1 << l)) >> (l + 1)) * NB;
-      if (roles.bu_level == l) load_bwd_row<NB>(q, l, tid - off, mBU);
-      off += cnt;
-    }
-    }
+    admm_block<NB, PAIR, false>(q, sysw.rho_aux, n, keep_last ? 1 : 0);
   };
 
   double* dxs = q.scratch;              // [Np] last trajectory step (written on check iterations)
@@ -1184,130 +1326,6 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
     return res;
   };
 
-  // ---------------------------------------------------------------- one ADMM iteration
-  // Rows are handled by the high thread ids so that they run beside the per-variable work of the low ones.
-  // rows_coef: aux right-hand sides R_RA0/1 and the row multiplier R_COEF of the reduced system for the next
-  // solve; the iteration itself refreshes them at its end, so this pass only runs after something else touched
-  // the row state or R_COEF (start, residual pass, refactorisation).
-  auto rows_coef = [&]() {
-    for (int r = kQpThreads - 1 - tid; r < q.nrows; r += kQpThreads) {
-      double* F = q.F(r);
-      const double s = F[R_WRR] * F[R_Z] - F[R_Y];
-      const double ra0 = q.sigma * F[R_XA0] - F[R_QA0] + F[R_U0] * s + F[R_B0] * (sysw.rho_aux * F[R_ZA0] - F[R_YA0]);
-      const double ra1 = q.sigma * F[R_XA1] - F[R_QA1] + F[R_U1] * s + F[R_B1] * (sysw.rho_aux * F[R_ZA1] - F[R_YA1]);
-      F[R_RA0] = ra0;
-      F[R_RA1] = ra1;
-      const double cf = row_reduce_coef(F, ra0, ra1, s);
-      F[R_COEF] = cf;
-      const double* as = q.R(r) + CNc;
-#pragma unroll
-      for (int k = 0; k < CNc; ++k) F[R_NF + k] = as[k] * cf;
-    }
-    __syncthreads();
-  };
-  auto admm_iteration = [&](bool keep_steps) {
-    // right-hand side  sigma x - q + A'(rho z - y)  (one thread per variable)
-    { PROF_T0();
-    if (one_var) {  // one thread per variable: its column range is loop invariant, the rows left their terms behind
-      const int i = tid;
-      double s = 0.0;
-      if (i < N) {
-        const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
-        s = q.sigma * q.x[i] - q.qs[i] + q.beta[i] * (rb * q.zb[i] - q.yb[i]);
-        for (int e = my_e0; e < my_e1; ++e) {
-          const int ent = q.colent[e];
-          s += q.rows[static_cast<size_t>(ent >> 5) * q.RS + (2 * CNc + R_NF) + (ent & 31)];
-        }
-      }
-      if (i < q.Np) q.v1[i] = s;
-    } else {
-      for (int i = tid; i < q.Np; i += kQpThreads) {
-        double s = 0.0;
-        if (i < N) {
-          const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? q.rho_eq : q.rho;
-          s = q.sigma * q.x[i] - q.qs[i] + q.beta[i] * (rb * q.zb[i] - q.yb[i]);
-          for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
-            const int ent = q.colent[e];
-            s += q.rows[static_cast<size_t>(ent >> 5) * q.RS + (2 * CNc + R_NF) + (ent & 31)];
-          }
-        }
-        q.v1[i] = s;
-      }
-    }
-    PROF_ADD(1); }
-    { PROF_T0();
-    solve_sys(q.v1, q.w);
-    PROF_ADD(2); }
-    PROF_T0();
-    // rows: back-substitute aux, relax, project, dual update, and the multipliers for the next solve
-    const double inv_rho_aux = 1.0 / sysw.rho_aux;
-    for (int r = kQpThreads - 1 - tid; r < q.nrows; r += kQpThreads) {
-      const double* R = q.R(r);
-      double* F = q.F(r);
-      const double zeta = row_dot<CNc>(q, R, q.I(r), q.w);
-      double a0, a1;
-      row_backsub(F, zeta, a0, a1);
-      const double zt = zeta + F[R_U0] * a0 + F[R_U1] * a1;
-      const double Wr = F[R_WRR];
-      const double zr = q.alpha * zt + (1.0 - q.alpha) * F[R_Z];
-      double zn = zr + F[R_Y] * F[R_IWRR];
-      zn = fmin(fmax(zn, F[R_LO]), F[R_UP]);
-      const double dy = Wr * (zr - zn);
-      const double yn = F[R_Y] + dy;
-      F[R_Z] = zn;
-      F[R_Y] = yn;
-      F[R_DY] = dy;
-      const double s = Wr * zn - yn;
-      double ra[2];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const double at = k ? a1 : a0, bb = F[R_B0 + k];
-        const double xo = F[R_XA0 + k];
-        const double xn = q.alpha * at + (1.0 - q.alpha) * xo;
-        const double zra = q.alpha * (bb * at) + (1.0 - q.alpha) * F[R_ZA0 + k];
-        double z2 = zra + F[R_YA0 + k] * inv_rho_aux;
-        z2 = fmin(fmax(z2, 0.0), kOsqpInf * F[R_EA0 + k]);
-        const double dya = sysw.rho_aux * (zra - z2);
-        const double yan = F[R_YA0 + k] + dya;
-        F[R_XA0 + k] = xn;
-        F[R_DXA0 + k] = xn - xo;
-        F[R_ZA0 + k] = z2;
-        F[R_YA0 + k] = yan;
-        F[R_DYA0 + k] = dya;
-        ra[k] = q.sigma * xn - F[R_QA0 + k] + F[R_U0 + k] * s + bb * (sysw.rho_aux * z2 - yan);
-      }
-      F[R_RA0] = ra[0];
-      F[R_RA1] = ra[1];
-      const double cf = row_reduce_coef(F, ra[0], ra[1], s);
-      F[R_COEF] = cf;
-#pragma unroll
-      for (int k = 0; k < CNc; ++k) F[R_NF + k] = R[CNc + k] * cf;
-    }
-    // trajectory variables and their bound rows (one thread per variable)
-    const double inv_rho = 1.0 / q.rho, inv_rho_eq = 1.0 / q.rho_eq;
-    for (int i = tid; i < N; i += kQpThreads) {
-      const double beta = q.beta[i];
-      const double lb = q.lbs[i], ub = q.ubs[i];
-      const bool beq = ub - lb < kRhoTol;
-      const double rb = beq ? q.rho_eq : q.rho, irb = beq ? inv_rho_eq : inv_rho;
-      const double xt = q.w[i];
-      const double xn = q.alpha * xt + (1.0 - q.alpha) * q.x[i];
-      const double zr = q.alpha * (beta * xt) + (1.0 - q.alpha) * q.zb[i];
-      double zn = zr + q.yb[i] * irb;
-      zn = fmin(fmax(zn, lb), ub);
-      const double dy = rb * (zr - zn);
-      if (keep_steps) {
-        dxs[i] = xn - q.x[i];
-        dyb[i] = dy;
-      }
-      q.x[i] = xn;
-      q.zb[i] = zn;
-      q.yb[i] += dy;
-    }
-    __syncthreads();
-    PROF_ADD(3);
-  };
-
   // ---------------------------------------------------------------- optimisation O1: when to try the polish early
   // Hash of the active-set guess the polish would start from: an order-independent sum (mod 2^64) of one
   // splitmix64 term per active row, keyed by the row's index in the canonical QP ([rows; trajectory bounds;
@@ -1357,7 +1375,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
   // ADMM iterations, continuing from the current state until a termination test fires or max_iter is reached.
   auto run_admm = [&](auto& polish_fn, auto& restore_fn) {
     status = QPS_UNSOLVED;
-    bool stop = false, need_coef = true, need_regs = true;
+    bool stop = false;
     while (!stop) {
       if (iter >= st.max_iter) {  // max_iter reached without a verdict: approximate test, then MAX_ITER_REACHED
         if (!(st.check_termination > 0 && (iter % st.check_termination == 0))) info_pass();
@@ -1365,20 +1383,19 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
         if (status == QPS_UNSOLVED) status = QPS_MAXITER;
         stop = true;
       } else {
-        ++iter;
+        // the iterations up to the next event (termination test, rho update, max_iter) run as one block
+        int n = st.max_iter - iter;
+        if (st.check_termination > 0) n = min(n, st.check_termination - iter % st.check_termination);
+        if (st.adaptive_rho && st.adaptive_rho_interval > 0) n = min(n, st.adaptive_rho_interval - iter % st.adaptive_rho_interval);
+        iter += n;
         const bool can_check = st.check_termination > 0 && (iter % st.check_termination == 0);
         const bool rho_iter = st.adaptive_rho && st.adaptive_rho_interval > 0 && (iter % st.adaptive_rho_interval == 0);
-        { PROF_T0(); if (need_coef) rows_coef(); PROF_ADD(0); }
-        need_coef = false;
-        if (need_regs) load_factor_regs();
-        need_regs = false;
-        admm_iteration(can_check || iter == st.max_iter);
+        run_block(n, can_check || iter == st.max_iter);
         if (can_check) {
           PROF_T0();
           info_pass();
           status = check_termination(false);
           PROF_ADD(5);
-          need_coef = true;  // the residual passes reuse R_COEF
           if (status != QPS_UNSOLVED) stop = true;
           else if (st.polishing && st.early_polish_every > 0 && iter >= st.early_polish_from &&
                    (iter % st.early_polish_every == 0) && early_guess_settled()) {
@@ -1399,7 +1416,6 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
               have_failed_guess = true;
               restore_fn(false);
               info_pass();  // the polish reuses the vectors of the residual bookkeeping
-              need_regs = true;
               if (!assemble_factor<NB>(q, sysw)) {
                 status = QPS_NONCVX;
                 stop = true;
@@ -1409,7 +1425,6 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
         }
         if (!stop && rho_iter) {
           if (!can_check) info_pass();
-          need_coef = true;
           // compute_rho_estimate on the scaled quantities [EXT]
           const double pn = s_pri / (fmax(s_z, s_ax) + 1e-10);
           const double dn = s_dua / (fmax(s_q, fmax(s_aty, s_px)) + 1e-10);
@@ -1421,7 +1436,6 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
             q.rho_eq = kRhoEqOverIneq * rho;
             sysw.rho_aux = rho;
             out.rho_updates++;
-            need_regs = true;
             if (!assemble_factor<NB>(q, sysw)) {
               status = QPS_NONCVX;
               stop = true;
@@ -1480,7 +1494,6 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
     }
     __syncthreads();
     if (!assemble_factor<NB>(q, pw)) return false;
-    load_factor_regs();  // the polish factor replaces the ADMM factor in the registers until the next reload
     for (int it = 0; it <= st.polish_refine_iter + 1; ++it) {
       const bool last = (it == st.polish_refine_iter + 1);  // final pass: pending dual update + residuals only
       p_matvec<NB>(q, q.x, q.v2);  // v2 <- P xq
@@ -1548,7 +1561,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
         p_dua = mm[1] * q.cinv;
         verified = (mm[2] == 0.0) && (p_pri <= kVerifyTol) && isfinite(p_pri) && isfinite(p_dua);
       } else {
-        solve_sys(q.v1, q.w);
+        bcr_solve<NB>(q, q.v1, q.w);  // (five solves per polish: factor rows read from memory)
         for (int r = tid; r < q.nrows; r += kQpThreads) {
           const double* R = q.R(r);
           double* F = q.F(r);
@@ -1645,7 +1658,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
 // QP assembly (optimizers.cpp:781-799 + osqp_interface.cpp:170-281 in fixed layout) + solve of trajectory b by the
 // calling CTA (256 threads).  DD = degrees of freedom (block size NB = 2*DD); PAIR: rows may span two waypoints.
 template <int DD, int PAIR>
-__device__ __forceinline__ void qp_step(const DevProblem& p, const int b, const double* x_override /*kernel-level API*/,
+__device__ __noinline__ void qp_step(const DevProblem& p, const int b, const double* x_override /*kernel-level API*/,
                                         const double* trust_override, int* admm_iters_out, int* polish_out) {
   constexpr int NB = 2 * DD;
   constexpr bool FG = DD > 8;  // blocks of more than 16: the factor lives in this CTA's region of global memory

@@ -92,7 +92,7 @@ struct tb200_problem {
   DevBuf<unsigned long long> coll_mask;
   DevBuf<int> status, sqp_iter, merit_round, qp_failures, qp_status, cur_buf, n_qp_solves, n_func_evals, n_admm_iters,
       active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish, trace_len, qp_done, lvs_overflow, link_chain;
-  int max_sub = 1;        // LVS sub-segments per step pair the candidate layout holds
+  int cast_cap = TB200_CAST_ROWS_PER_PAIR;  // active contacts (rows) a step pair of the continuous evaluator can hold
   size_t factor_grid = 0;  // CTAs that own a region of factor_g (0: the factor lives in shared memory)
   std::vector<cudaEvent_t> events;
   ~tb200_problem() {
@@ -249,7 +249,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   std::vector<DevJointTerm> jts;
   std::vector<DevCartTerm> cts;
   std::vector<DevObj> costs, eqs, ineqs;
-  int n_cart_rows = 0, n_coll_cand = 0, max_rows = 0, max_sub = 1;
+  int n_cart_rows = 0, n_coll_cand = 0, max_rows = 0;
+  const int cast_cap = TB200_CAST_ROWS_PER_PAIR;
   std::vector<std::pair<int, int>> cart_ref, coll_ref, vel_ref;  // (list id: 0 cost 1 eq 2 ineq, index)
   bool has_vel = false, has_cast = false, has_discrete = false;
   for (int k = 0; k < d->n_terms; ++k) {
@@ -314,13 +315,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
       if (dp.L == 0 || dp.O == 0) return fail(TB200_ERR_INVALID, "collision term needs robot spheres and obstacles");
       if (tm.n_fixed_steps < 0 || tm.n_fixed_steps > 8) return fail(TB200_ERR_INVALID, "collision term: n_fixed_steps outside [0, 8]");
       const bool cast = tm.evaluator_type != TB200_COLL_DISCRETE;
-      if (cast) {
-        const int lay = tb200inl_lvs_layout_segments(d, &tm);
-        if (lay <= 0)
-          return fail(TB200_ERR_UNSUPPORTED, "longest_valid_segment_length needs more than TB200_MAX_LVS_LAYOUT sub-segments per "
-                                             "step pair on the initial trajectories");
-        max_sub = std::max(max_sub, lay);
-      }
+      if (cast && tm.evaluator_type == TB200_COLL_LVS_CONTINUOUS && !(tm.longest_valid_segment_length > 0.0))
+        return fail(TB200_ERR_INVALID, "longest_valid_segment_length must be positive");
       if ((cast && has_discrete) || (!cast && has_cast))
         return fail(TB200_ERR_UNSUPPORTED, "discrete and continuous collision terms in one problem are not supported");
       (cast ? has_cast : has_discrete) = true;
@@ -338,7 +334,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
         c.kind = cast ? OBJ_COLL_CAST : OBJ_COLL;
         c.first = t;
         c.src_off = n_coll_cand;
-        c.n_rows = dp.L * dp.O;  // (continuous: times the layout's sub-segments, set below once every term is seen)
+        c.n_rows = cast ? cast_cap : dp.L * dp.O;  // continuous: room for cast_cap active contacts of the step pair
         c.coeff = tm.coeff; c.margin = tm.margin; c.buffer = tm.margin_buffer;
         // (two adjacent fixed steps take the START_FIXED_END_FREE branch: the reference's throw is unreachable)
         c.pad1 = cast ? ((fixed ? 1 : 0) | ((!fixed && next_fixed) ? 2 : 0)) : 0;
@@ -372,15 +368,12 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
       return fail(TB200_ERR_INVALID, "unknown term kind");
     }
   }
-  // every continuous collision object gets the same number of sub-segment slots
   for (auto* lst : {&costs, &ineqs})
     for (DevObj& o : *lst)
       if (o.kind == OBJ_COLL || o.kind == OBJ_COLL_CAST) {
-        if (o.kind == OBJ_COLL_CAST) o.n_rows *= max_sub;
         n_coll_cand += o.n_rows;
         max_rows += o.n_rows;
       }
-  P->max_sub = max_sub;
   P->cost_objs = costs;
   P->cnt_objs = eqs;
   P->cnt_objs.insert(P->cnt_objs.end(), ineqs.begin(), ineqs.end());
@@ -464,13 +457,13 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.n_fixed = static_cast<int>(fixed.size());
   dp.max_rows = max_rows;
   dp.row_stride = qp_row_stride(CN);
-  dp.coll_words = std::max(1, (dp.L * dp.O * (has_cast ? max_sub : 1) + 63) / 64);
+  dp.coll_words = std::max(1, ((has_cast ? cast_cap : dp.L * dp.O) + 63) / 64);
   dp.n_coll_objs = static_cast<int>(P->coll_objs.size());
   P->ex.n_cart_objs = static_cast<int>(P->cart_objs.size());
   P->ex.n_coll_objs = dp.n_coll_objs;
   P->ex.n_vel_objs = static_cast<int>(P->vel_objs.size());
   P->ex.cast = has_cast ? 1 : 0;
-  P->ex.max_sub = max_sub;
+  P->ex.cast_cap = cast_cap;
   for (int sg = 0; sg < dp.S; ++sg)
     if (segs[sg].q_index >= 0) P->ex.joint_seg[segs[sg].q_index] = sg;
   P->ex.n_joint_objs = 0;
@@ -498,7 +491,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
 
   // ---- kernel resources --------------------------------------------------------------------------------
   const EvalSmem es = eval_smem_layout(T, D, dp.L, dp.n_coll_objs, dp.n_coll_objs * dp.coll_words, dp.S, P->ex.n_joint_objs,
-                                       P->ex.n_vel_objs, P->ex.cast, max_sub, dp.n_costs + dp.n_cnts);
+                                       P->ex.n_vel_objs, P->ex.cast, cast_cap, dp.n_costs + dp.n_cnts);
   P->pair_rows = (CN > std::max(D, 3));
   P->eval_smem = static_cast<size_t>(es.total) * sizeof(double);
   const bool factor_global = D > 8;  // = FG of qp_step: blocks of 2*D > 16 never fit
@@ -757,9 +750,9 @@ int lvsOverflowError(tb200_problem* P) {
   int rc = lvsOverflowCount(P, &n);
   if (rc != TB200_OK) return rc;
   if (n > 0)
-    return fail(TB200_ERR_UNSUPPORTED, std::to_string(n) + " trajectories have a step pair that needs more than " +
-                                           std::to_string(P->max_sub) + " longest-valid-segment sub-segments (the candidate layout "
-                                           "was sized from the initial trajectories); they are reported OPT_FAILED");
+    return fail(TB200_ERR_UNSUPPORTED, std::to_string(n) + " trajectories have a step pair with more than " +
+                                           std::to_string(P->cast_cap) + " active continuous-collision contacts (TB200_CAST_ROWS_PER_PAIR) "
+                                           "or more than 32767 longest-valid-segment sub-segments; they are reported OPT_FAILED");
   return TB200_OK;
 }
 }  // namespace
@@ -815,6 +808,8 @@ int tb200_convexify_batch(tb200_problem* P, const double* x, tb200_convexify_out
   cudaStream_t st = P->stream;
   CK(cudaMemcpyAsync(P->x_tmp.p, x, B * dp.N * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(P->lvs_overflow.p, 0, B * sizeof(int), st));
+  if (P->ex.cast)  // the continuous evaluator writes only its active rows: the rest of the (returned) block reads as zeros
+    CK(cudaMemsetAsync(P->coll_rows.p, 0, B * dp.n_coll_cand * dp.coll_stride * sizeof(double), st));
   cudaEvent_t e0 = getEvent(P, 0), e1 = getEvent(P, 1);
   CK(cudaEventRecord(e0, st));
   eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
