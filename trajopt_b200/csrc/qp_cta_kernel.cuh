@@ -131,6 +131,8 @@ struct QpCtx {
   int* colptr;           // shared [Np+1]
   double *Dz, *v2;       // shared [Np]: variable scalings, scratch of the residual / polish passes
   double* rows;          // shared when the QP has at most row_cap rows, else global
+  double* smbase;        // start of the CTA's dynamic shared memory (generic address), rows_smem: q.rows lives there
+  int rows_smem;
   int* rints;
   const int* colent;     // entries: (row << 5) | k (shared or global, like the rows)
   const double* Pband;   // shared copy of the objective band [N][2D+1]
@@ -949,6 +951,191 @@ __device__ __noinline__ void admm_block(const QpCtx& q, const double rho_aux, co
   }
 }
 
+// The same block of iterations for the common case — factor rows in registers (REG roles fit), QP rows in shared
+// memory — written for the latency of ONE iteration:
+//  * every operand address is an offset into the CTA's dynamic shared memory (LDS / STS, not generic loads), every
+//    solver scalar a register (the QpCtx behind `q` is only read at entry);
+//  * the thread's variable (x, z, y of its bound row, its scaling, bounds, cost) lives in registers for the whole block
+//    and goes back to shared memory at the end: the right-hand side of the next solve is built from registers plus the
+//    rows' contributions, which are fetched through entry addresses preloaded once per block (8 per variable, the
+//    common case; longer columns walk the rest of their list);
+//  * nothing loop invariant is recomputed inside the loop.
+// The arithmetic (operations and their order) is that of admm_block.
+template <int NB, int PAIR>
+__device__ __noinline__ void admm_block_fast(const QpCtx& q, const double rho_aux_in, const int n_iter, const int keep_last) {
+  constexpr int CNc = PAIR ? ((NB > 3) ? NB : 3) : ((NB / 2 > 3) ? NB / 2 : 3);
+  constexpr int kPre = 8;  // column entries whose addresses are kept in registers
+  extern __shared__ double sm[];
+  const int tid = q.tid, N = q.N, Np = q.Np, nrows = q.nrows, RS = q.RS;
+  const double sigma = q.sigma, alpha = q.alpha, oma = 1.0 - q.alpha, rho = q.rho, rho_eq = q.rho_eq, rho_aux = rho_aux_in;
+  const double inv_rho_aux = 1.0 / rho_aux, inv_rho = 1.0 / rho, inv_rho_eq = 1.0 / rho_eq;
+  double* const v1 = sm + (q.v1 - q.smbase);
+  double* const w = sm + (q.w - q.smbase);
+  double* const rows = sm + (q.rows - q.smbase);
+  const int* const rints = reinterpret_cast<const int*>(sm + (reinterpret_cast<const double*>(q.rints) - q.smbase));
+  const int* const colent = reinterpret_cast<const int*>(sm + (reinterpret_cast<const double*>(q.colent) - q.smbase));
+  double* const dxs = q.scratch;
+  double* const dyb = q.scratch + Np;
+  const SolveRoles roles = solve_roles<NB>(q);
+  double mF0[NB], mB0[NB + NB / 2], mFU[NB], mBU[NB + NB / 2];
+  {
+    load_fwd_row<NB>(q, 0, tid, mF0);
+    load_bwd_row<NB>(q, 0, tid, mB0);
+    int off = 0;
+    for (int l = 1; l < roles.n_fwd; ++l) {
+      const int cnt = 2 * (q.M >> (l + 1)) * NB;
+      if (roles.fu_level == l) load_fwd_row<NB>(q, l, tid - off, mFU);
+      off += cnt;
+    }
+    off = 0;
+    for (int l = 1; l < roles.n_lvl; ++l) {
+      const int cnt = 2 * ((q.M + (1 << l)) >> (l + 1)) * NB;
+      if (roles.bu_level == l) load_bwd_row<NB>(q, l, tid - off, mBU);
+      off += cnt;
+    }
+  }
+  // ---- this thread's variable
+  const bool has_var = tid < N;
+  const int vi = has_var ? tid : 0;
+  const double v_beta = q.beta[vi], v_lb = q.lbs[vi], v_ub = q.ubs[vi], v_qs = q.qs[vi];
+  const bool v_eq = v_ub - v_lb < kRhoTol;
+  const double v_rb = v_eq ? rho_eq : rho, v_irb = v_eq ? inv_rho_eq : inv_rho;
+  double v_x = q.x[vi], v_z = q.zb[vi], v_y = q.yb[vi];
+  const int e0 = has_var ? q.colptr[vi] : 0, e1 = has_var ? q.colptr[vi + 1] : 0;
+  // a word that always reads 0.0: the padding coefficient of row 0's contribution block does not exist, so the zero
+  // comes from the (unused) last scalar slot of the factorisation scratch
+  double* const zero_slot = sm + (q.flag - q.smbase) + 7;
+  if (tid == 0) *zero_slot = 0.0;
+  int ea[kPre];
+#pragma unroll
+  for (int k = 0; k < kPre; ++k) {
+    const int e = e0 + k;
+    const int ent = (e < e1) ? colent[e] : -1;
+    ea[k] = (ent >= 0) ? static_cast<int>(rows - sm) + (ent >> 5) * RS + (2 * CNc + R_NF) + (ent & 31)
+                       : static_cast<int>(zero_slot - sm);
+  }
+  // ---- this thread's row (rows are handled by the high thread ids so that they run beside the per-variable work)
+  {  // entry pass: aux right-hand sides, row multipliers and contributions from the current row state
+    PROF_T0();
+    for (int r = kQpThreads - 1 - tid; r < nrows; r += kQpThreads) {
+      double* F = rows + r * RS + 2 * CNc;
+      const double s = F[R_WRR] * F[R_Z] - F[R_Y];
+      const double ra0 = sigma * F[R_XA0] - F[R_QA0] + F[R_U0] * s + F[R_B0] * (rho_aux * F[R_ZA0] - F[R_YA0]);
+      const double ra1 = sigma * F[R_XA1] - F[R_QA1] + F[R_U1] * s + F[R_B1] * (rho_aux * F[R_ZA1] - F[R_YA1]);
+      F[R_RA0] = ra0;
+      F[R_RA1] = ra1;
+      const double cf = row_reduce_coef(F, ra0, ra1, s);
+      F[R_COEF] = cf;
+      const double* as = rows + r * RS + CNc;
+#pragma unroll
+      for (int k = 0; k < CNc; ++k) F[R_NF + k] = as[k] * cf;
+    }
+    __syncthreads();
+    PROF_ADD(0);
+  }
+  for (int it = 0; it < n_iter; ++it) {
+    const bool keep_steps = keep_last && it == n_iter - 1;
+    {
+      PROF_T0();
+      // right-hand side  sigma x - q + A'(rho z - y): the variable's own part from registers, the rows left their terms behind
+      double s = 0.0;
+      if (has_var) {
+        s = sigma * v_x - v_qs + v_beta * (v_rb * v_z - v_y);
+        double c[kPre];
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) c[k] = sm[ea[k]];
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) s += c[k];
+        for (int e = e0 + kPre; e < e1; ++e) {
+          const int ent = colent[e];
+          s += rows[(ent >> 5) * RS + (2 * CNc + R_NF) + (ent & 31)];
+        }
+      }
+      if (tid < Np) v1[tid] = s;
+      PROF_ADD(1);
+    }
+    {
+      PROF_T0();
+      bcr_solve_reg<NB>(q, roles, mF0, mB0, mFU, mBU, v1, w);
+      PROF_ADD(2);
+    }
+    PROF_T0();
+    // rows: back-substitute aux, relax, project, dual update, and the multipliers for the next solve
+    for (int r = kQpThreads - 1 - tid; r < nrows; r += kQpThreads) {
+      const double* R = rows + r * RS;
+      double* F = rows + r * RS + 2 * CNc;
+      const int* I = rints + r * RI_NINTS;
+      double zeta = 0.0;
+      {
+        const int base = I[RI_BASE], stride = I[RI_STRIDE], last = I[RI_CNT] - 1;
+#pragma unroll
+        for (int k = 0; k < CNc; ++k) zeta += R[CNc + k] * w[base + min(k, last) * stride];
+      }
+      double a0, a1;
+      row_backsub(F, zeta, a0, a1);
+      const double zt = zeta + F[R_U0] * a0 + F[R_U1] * a1;
+      const double Wr = F[R_WRR];
+      const double zr = alpha * zt + oma * F[R_Z];
+      double zn = zr + F[R_Y] * F[R_IWRR];
+      zn = fmin(fmax(zn, F[R_LO]), F[R_UP]);
+      const double dy = Wr * (zr - zn);
+      const double yn = F[R_Y] + dy;
+      F[R_Z] = zn;
+      F[R_Y] = yn;
+      F[R_DY] = dy;
+      const double s = Wr * zn - yn;
+      double ra[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double at = k ? a1 : a0, bb = F[R_B0 + k];
+        const double xo = F[R_XA0 + k];
+        const double xn = alpha * at + oma * xo;
+        const double zra = alpha * (bb * at) + oma * F[R_ZA0 + k];
+        double z2 = zra + F[R_YA0 + k] * inv_rho_aux;
+        z2 = fmin(fmax(z2, 0.0), kOsqpInf * F[R_EA0 + k]);
+        const double dya = rho_aux * (zra - z2);
+        const double yan = F[R_YA0 + k] + dya;
+        F[R_XA0 + k] = xn;
+        F[R_DXA0 + k] = xn - xo;
+        F[R_ZA0 + k] = z2;
+        F[R_YA0 + k] = yan;
+        F[R_DYA0 + k] = dya;
+        ra[k] = sigma * xn - F[R_QA0 + k] + F[R_U0 + k] * s + bb * (rho_aux * z2 - yan);
+      }
+      F[R_RA0] = ra[0];
+      F[R_RA1] = ra[1];
+      const double cf = row_reduce_coef(F, ra[0], ra[1], s);
+      F[R_COEF] = cf;
+#pragma unroll
+      for (int k = 0; k < CNc; ++k) F[R_NF + k] = R[CNc + k] * cf;
+    }
+    // the thread's variable and its bound row
+    if (has_var) {
+      const double xt = w[vi];
+      const double xn = alpha * xt + oma * v_x;
+      const double zr = alpha * (v_beta * xt) + oma * v_z;
+      double zn = zr + v_y * v_irb;
+      zn = fmin(fmax(zn, v_lb), v_ub);
+      const double dy = v_rb * (zr - zn);
+      if (keep_steps) {
+        dxs[vi] = xn - v_x;
+        dyb[vi] = dy;
+      }
+      v_x = xn;
+      v_z = zn;
+      v_y += dy;
+    }
+    __syncthreads();
+    PROF_ADD(3);
+  }
+  if (has_var) {
+    q.x[vi] = v_x;
+    q.zb[vi] = v_z;
+    q.yb[vi] = v_y;
+  }
+  __syncthreads();
+}
+
 // Ruiz equilibration (scale_data of OSQP [EXT]); leaves the scaled view of every row in its record and the
 // scaled trajectory cost / bounds in q.qs / q.lbs / q.ubs, Dz (global) / beta (shared).
 __device__ inline void qp_scale(QpCtx& q, const QpSettings& st, int n_aux_total) {
@@ -1145,7 +1332,8 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
   auto run_block = [&](int n, bool keep_last) {
     if constexpr (REGOK) {
       if (use_reg) {
-        admm_block<NB, PAIR, true>(q, sysw.rho_aux, n, keep_last ? 1 : 0);
+        if (q.rows_smem) admm_block_fast<NB, PAIR>(q, sysw.rho_aux, n, keep_last ? 1 : 0);
+        else admm_block<NB, PAIR, true>(q, sysw.rho_aux, n, keep_last ? 1 : 0);
         return;
       }
     }
@@ -1689,6 +1877,8 @@ __device__ __noinline__ void qp_step(const DevProblem& p, const int b, const dou
   double* const rows_g = p.rows + static_cast<size_t>(b) * p.max_rows * p.row_stride;
   int* const rints_g = p.row_ints + static_cast<size_t>(b) * p.max_rows * RI_NINTS;
   q.rows = rows_g;
+  q.smbase = sm;
+  q.rows_smem = 0;
   q.rints = rints_g;
   int* mylist = p.lists + static_cast<size_t>(b) * p.list_stride;
   int* colptr = mylist;                                   // [Np+1] master copy (shared copy in q.colptr)
@@ -1930,6 +2120,7 @@ __device__ __noinline__ void qp_step(const DevProblem& p, const int b, const dou
     for (int t = tid; t < nr * RI_NINTS; t += kQpThreads) rints_s[t] = rints_g[t];
     for (int t = tid; t < q.colptr[q.Np]; t += kQpThreads) colent_s[t] = colent[t];
     q.rows = rows_s;
+    q.rows_smem = 1;
     q.rints = rints_s;
     q.colent = colent_s;
   }
