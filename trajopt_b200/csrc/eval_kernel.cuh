@@ -17,6 +17,12 @@ namespace tb200 {
 constexpr int kEvalThreads = 256;
 enum EvalMode { EVAL_INIT = 0, EVAL_STEP = 1, EVAL_ONLY = 2 };
 
+// Frames of the waypoint FK in shared memory: 13 doubles apart (12 used) and an odd number of doubles per waypoint, so
+// that lanes working on different frames / waypoints hit different banks (12 and S*12 doubles are multiples of the
+// bank period for the access patterns of the chain products: every lane landed on the same banks).
+constexpr int kFrameStride = 13;
+__host__ __device__ inline int eval_job_stride(int S) { return (S * kFrameStride) | 1; }
+
 struct EvalSmem {
   // offsets in doubles into the dynamic shared buffer
   int x, sph, spo, jax, velp, objv, mask, misc, fr, terms, obst, sphr, segs, sphs, cobj, aobj, wscr, wscr_stride, total;
@@ -53,8 +59,8 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   s.fr = o;                                           // frames of every FK job: local, then (in place) world
   s.terms = o;                                        // per-(step, joint) terms of the joint-space objects (later phase)
   // ... and, while the collision rows are written, the per-warp staging tiles of the bulk (TMA) row stores
-  const int a = T * S * 12, b2 = n_joint_objs * 2 * T * D;
-  const int st = (((D + 3) & 1) == 0 && !cast) ? 8 * 32 * (D + 3) : 0;
+  const int a = T * eval_job_stride(S), b2 = n_joint_objs * 2 * T * D;
+  const int st = (((D + 3) & 1) == 0 && !cast) ? 8 * 2 * 32 * (D + 3) : 0;  // two tiles per warp (double buffered)
   const int m = a > b2 ? a : b2;
   o += m > st ? m : st;
   o += o & 1;
@@ -66,6 +72,7 @@ struct EvalExtra {
   int n_cart_objs, n_coll_objs, n_joint_objs, n_vel_objs;
   int cast, cast_cap;                // cast: the collision objects are step pairs (continuous evaluator), each with room
                                      // for cast_cap active contacts (rows)
+  int* work_counter;                 // stand-alone launches: next trajectory to take (reset to 0 before every launch)
   const int* link_chain;             // [S][kMaxSeg + 1]: per segment, the number of segments on its chain from the root,
                                      // then the chain itself (root first, the segment last)
   const DevObj* vel_objs;            // CartVel step pairs
@@ -199,6 +206,8 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
     // so the three lanes of a job never wait for each other, (3) emission of what the row writers need.
     const int n_jobs = T, Sg = p.S;
     double* FR = sm + S.fr;
+    constexpr int FS = kFrameStride;
+    const int JS = eval_job_stride(Sg);
     const DevSegment* segs = reinterpret_cast<const DevSegment*>(sm + S.segs);
     const DevSphere* sphs = reinterpret_cast<const DevSphere*>(sm + S.sphs);
     for (int w = tid; w < n_jobs * Sg; w += kEvalThreads) {
@@ -207,7 +216,7 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
       const double qv = (g.q_index >= 0) ? xs[job * D + g.q_index] : 0.0;
       Frame loc;
       segment_local_q(g, qv, loc);
-      double* f = FR + static_cast<size_t>(w) * 12;
+      double* f = FR + job * JS + sg * FS;
       for (int i = 0; i < 9; ++i) f[i] = loc.R[i];
       for (int i = 0; i < 3; ++i) f[9 + i] = loc.p[i];
     }
@@ -220,26 +229,26 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
       // in-place overwrite of a local frame behind its readers.
       const bool act = w < n_jobs * 4 && (w & 3) < 3;
       const int job = (w < n_jobs * 4) ? w / 4 : 0, i = (w & 3) % 3;
-      double* F = FR + static_cast<size_t>(job) * Sg * 12;
+      double* F = FR + job * JS;
       double r0 = 0.0, r1 = 0.0, r2 = 0.0, rp = 0.0;
       for (int sg = 0; sg < Sg; ++sg) {
         const int parent = segs[sg].parent;
         double l[12];
-        for (int k = 0; k < 12; ++k) l[k] = F[sg * 12 + k];
+        for (int k = 0; k < 12; ++k) l[k] = F[sg * FS + k];
         __syncwarp();
         if (parent >= 0) {
           if (parent != sg - 1) {
-            const double* P = F + parent * 12;
+            const double* P = F + parent * FS;
             r0 = P[i * 3]; r1 = P[i * 3 + 1]; r2 = P[i * 3 + 2]; rp = P[9 + i];
           }
           const double n0 = r0 * l[0] + r1 * l[3] + r2 * l[6], n1 = r0 * l[1] + r1 * l[4] + r2 * l[7],
                        n2 = r0 * l[2] + r1 * l[5] + r2 * l[8], np = r0 * l[9] + r1 * l[10] + r2 * l[11] + rp;
           r0 = n0; r1 = n1; r2 = n2; rp = np;
           if (act) {
-            F[sg * 12 + i * 3 + 0] = r0;
-            F[sg * 12 + i * 3 + 1] = r1;
-            F[sg * 12 + i * 3 + 2] = r2;
-            F[sg * 12 + 9 + i] = rp;
+            F[sg * FS + i * 3 + 0] = r0;
+            F[sg * FS + i * 3 + 1] = r1;
+            F[sg * FS + i * 3 + 2] = r2;
+            F[sg * FS + 9 + i] = rp;
           }
         } else {  // a root segment: its world frame is its local frame
           r0 = (i == 0) ? l[0] : ((i == 1) ? l[3] : l[6]);  // (selects, not l[3 * i]: the frame stays in registers)
@@ -259,7 +268,7 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
       const int t = w / Sg, sg = w % Sg;
       const DevSegment& g = segs[sg];
       if (g.q_index < 0) continue;
-      const double* f = FR + static_cast<size_t>(w) * 12;
+      const double* f = FR + t * JS + sg * FS;
       double* ab = sm + S.jax + (t * D + g.q_index) * 6;
       double a[3];
       for (int i = 0; i < 3; ++i) a[i] = f[i * 3] * g.axis[0] + f[i * 3 + 1] * g.axis[1] + f[i * 3 + 2] * g.axis[2];
@@ -275,7 +284,7 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
     for (int w = tid; w < T * L; w += kEvalThreads) {
       const int t = w / L, sl = w % L;
       const DevSphere& sp = sphs[sl];
-      const double* f = FR + (static_cast<size_t>(t) * Sg + sp.segment) * 12;
+      const double* f = FR + t * JS + sp.segment * FS;
       double* sph = sm + S.sph + w * 3;
       for (int i = 0; i < 3; ++i) {
         const double off = f[i * 3] * sp.c[0] + f[i * 3 + 1] * sp.c[1] + f[i * 3 + 2] * sp.c[2];
@@ -286,7 +295,7 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
     for (int w = tid; w < ex.n_vel_objs * 6; w += kEvalThreads) {  // link position at both ends of a CartVel pair
       const int c = w / 6, k = (w % 6) / 3, i = w % 3;
       const DevObj& o = ex.vel_objs[c];
-      sm[S.velp + w] = FR[(static_cast<size_t>(o.first + k) * Sg + o.link) * 12 + 9 + i];
+      sm[S.velp + w] = FR[(o.first + k) * JS + o.link * FS + 9 + i];
     }
     __syncthreads();
     EVAL_PROF(4);
@@ -389,6 +398,7 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
     const double* obst = sm + S.obst;
     double* rows_out = p.coll_rows + slot * static_cast<size_t>(p.n_coll_cand) * p.coll_stride;
     const float inv_O = 1.0f / static_cast<float>(O);
+    int tile_sel = 0;
     for (;;) {
       int k = 0;
       if (lane_c == 0) k = atomicAdd(&misc[2], 1);  // next collision object: warps take them as they get free
@@ -400,8 +410,12 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
       double vsum = 0.0;  // exact value of the object: its terms added in candidate order (warp-uniform)
       if (co.kind == OBJ_COLL) {
         const double* AB = sm + S.jax + t * D * 6;
-        double* stage = sm + S.fr + (tid >> 5) * (32 * (D + 3));  // this warp's tile (the FK frames are dead by now)
+        // this warp's two staging tiles (the FK frames are dead by now): a chunk is staged in one while the bulk store of
+        // the previous chunk still reads the other
+        double* const stage0 = sm + S.fr + (tid >> 5) * (2 * 32 * (D + 3));
         for (int c0 = 0; c0 < LO; c0 += 32) {
+          double* stage = stage0 + (tile_sel ? 32 * (D + 3) : 0);
+          tile_sel ^= 1;
           const int cnd = c0 + lane_c;
           const bool in = cnd < LO;
           const int sl = in ? static_cast<int>((static_cast<float>(cnd) + 0.5f) * inv_O) : 0, o = in ? cnd - sl * O : 0;
@@ -439,6 +453,9 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
             // rows are 16-byte aligned (D + 3 even, 256-byte aligned buffers): the 32 rows of the chunk are staged in
             // shared memory and leave as ONE asynchronous bulk store (cp.async.bulk, 2.5 KB contiguous in HBM).
             // Measured (scripts/probes/store_probe.cu): lane-per-row 16-byte stores reach 2.7 TB/s, this 5.2 TB/s.
+            // the store issued from this tile two chunks ago has read it (at most one group, the last one, is pending)
+            if (lane_c == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
             if (in) {
               double2* d2 = reinterpret_cast<double2*>(stage + lane_c * (D + 3));
 #pragma unroll
@@ -454,9 +471,7 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
                            "r"(nrows * (D + 3) * 8)
                            : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile may be refilled
             }
-            __syncwarp();
           } else if (in) {
             double* dstp = rows_out + static_cast<size_t>(co.src_off + cnd) * (D + 3);
 #pragma unroll
@@ -871,14 +886,25 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
 }
 
 #ifndef TB200_EVAL_MIN_BLOCKS
-#define TB200_EVAL_MIN_BLOCKS 4
+#define TB200_EVAL_MIN_BLOCKS 3
 #endif
 // Stand-alone launch, one CTA per trajectory: the initial evaluation of a solve (EVAL_INIT) and the kernel-level
 // convexify entry point (EVAL_ONLY).  Inside a solve the same code runs as a step of solve_kernel.cuh.
 template <int DD>
 __global__ void __launch_bounds__(kEvalThreads, (DD <= 8) ? TB200_EVAL_MIN_BLOCKS : 2)
 eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double* x_in /*EVAL_ONLY*/) {
-  eval_step<DD>(p, ex, mode, blockIdx.x, x_in);
+  // persistent CTAs: the grid fills the SMs once and every CTA takes the next trajectory when it is done with one
+  // (1024 trajectories over 148 SMs x 3-4 resident CTAs: no tail wave of half-empty SMs)
+  __shared__ int s_next;
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(ex.work_counter, 1);
+    __syncthreads();
+    const int b = s_next;
+    __syncthreads();
+    if (b >= p.B) return;
+    eval_step<DD>(p, ex, mode, b, x_in);
+    __syncthreads();
+  }
 }
 
 }  // namespace tb200

@@ -91,7 +91,8 @@ struct tb200_problem {
   DevBuf<int> sched_state;
   DevBuf<unsigned long long> coll_mask;
   DevBuf<int> status, sqp_iter, merit_round, qp_failures, qp_status, cur_buf, n_qp_solves, n_func_evals, n_admm_iters,
-      active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish, trace_len, qp_done, lvs_overflow, link_chain;
+      active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish, trace_len, qp_done, lvs_overflow, link_chain, work_counter;
+  int eval_grid = 1;  // CTAs of a stand-alone evaluation launch: what fits the device at once (persistent CTAs)
   int cast_cap = TB200_CAST_ROWS_PER_PAIR;  // active contacts (rows) a step pair of the continuous evaluator can hold
   size_t factor_grid = 0;  // CTAs that own a region of factor_g (0: the factor lives in shared memory)
   std::vector<cudaEvent_t> events;
@@ -104,7 +105,7 @@ struct tb200_problem {
     x.release(); new_x.release(); trust.release(); merit_coeffs.release(); cost_vals.release(); cnt_viols.release();
     new_cost_vals.release(); new_cnt_viols.release(); model_cost_vals.release(); model_cnt_viols.release();
     cart_err.release(); cart_jac.release(); coll_rows.release(); rows.release(); ws_x.release(); ws_yb.release();
-    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); factor_g.release(); lvs_overflow.release(); link_chain.release(); qp_done.release(); sched_state.release(); sched_timers.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
+    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); factor_g.release(); lvs_overflow.release(); link_chain.release(); work_counter.release(); qp_done.release(); sched_state.release(); sched_timers.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
     sqp_iter.release(); merit_round.release(); qp_failures.release(); qp_status.release(); cur_buf.release();
     n_qp_solves.release(); n_func_evals.release(); n_admm_iters.release(); active_count.release(); row_ints.release();
     lists.release(); ws_meta.release(); tmp_iters.release(); tmp_polish.release();
@@ -557,6 +558,12 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   ALLOC(lists, Bs * dp.list_stride);
   ALLOC(ws_x, Bs * N); ALLOC(ws_yb, Bs * N); ALLOC(scratch, Bs * 5 * Np); ALLOC(qp_done, Bs); ALLOC(ws_rho, Bs); ALLOC(ws_meta, Bs * 8);
   ALLOC(lvs_overflow, Bs);
+  ALLOC(work_counter, 1);
+  {
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eval_kernel_for(D), kEvalThreads, P->eval_smem));
+    P->eval_grid = std::max(1, std::min(B, std::max(1, per_sm) * P->n_sm));
+  }
   // a factor that does not fit shared memory lives in a per-CTA region (the kernel-level QP entry point launches B CTAs)
   P->factor_grid = (factor_global || !qs.factor_smem) ? std::max<size_t>(Bs, static_cast<size_t>(P->n_sm)) : 0;
   ALLOC(factor_g, P->factor_grid * qp_factor_doubles(N, 2 * D));
@@ -594,6 +601,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.scratch = P->scratch.p; dp.ws_meta = P->ws_meta.p; dp.ws_rho = P->ws_rho.p; dp.dbg = P->dbg.p; dp.sched_state = P->sched_state.p; dp.sched_timers = P->sched_timers.p; dp.trace_len = P->trace_len.p; dp.trace = nullptr; dp.trace_cap = 0;
   dp.factor_g = P->factor_g.p; dp.lvs_overflow = P->lvs_overflow.p; dp.qp_done = P->qp_done.p;
   P->ex.link_chain = P->link_chain.p;
+  P->ex.work_counter = P->work_counter.p;
   P->ex.cart_objs = P->d_cart_objs.p;
   P->ex.coll_objs = P->d_coll_objs.p;
   P->ex.vel_objs = P->d_vel_objs.p;
@@ -696,7 +704,8 @@ int tb200_solve_batch_resident(tb200_problem* P) {
   reset_state_kernel<<<(dp.B + 127) / 128, 128, 0, st>>>(dp);
   // the initial evaluation + convexification of every trajectory: one CTA per trajectory (optimizers.cpp:761-783)
   CK(cudaEventRecord(e_init0, st));
-  eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_INIT, nullptr);
+  CK(cudaMemsetAsync(P->work_counter.p, 0, sizeof(int), st));
+  eval_kernel_for(P->D)<<<P->eval_grid, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_INIT, nullptr);
   CK(cudaEventRecord(e_init1, st));
   // everything else: one persistent CTA per SM (solve_kernel.cuh); no host round trips until every trajectory is done
   SolveCtl ctl{};
@@ -810,9 +819,10 @@ int tb200_convexify_batch(tb200_problem* P, const double* x, tb200_convexify_out
   CK(cudaMemsetAsync(P->lvs_overflow.p, 0, B * sizeof(int), st));
   if (P->ex.cast)  // the continuous evaluator writes only its active rows: the rest of the (returned) block reads as zeros
     CK(cudaMemsetAsync(P->coll_rows.p, 0, B * dp.n_coll_cand * dp.coll_stride * sizeof(double), st));
+  CK(cudaMemsetAsync(P->work_counter.p, 0, sizeof(int), st));
   cudaEvent_t e0 = getEvent(P, 0), e1 = getEvent(P, 1);
   CK(cudaEventRecord(e0, st));
-  eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
+  eval_kernel_for(P->D)<<<P->eval_grid, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
   CK(cudaEventRecord(e1, st));
   CK(cudaGetLastError());
   auto pull = [&](void* dst, const void* src, size_t n) {
@@ -850,7 +860,8 @@ int tb200_qp_solve_batch(tb200_problem* P, const double* x, const double* trust,
   if (dp.n_cnts > 0) CK(cudaMemcpyAsync(P->merit_coeffs.p, merit_coeffs, B * dp.n_cnts * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(P->ws_meta.p, 0, B * 8 * sizeof(int), st));
   CK(cudaMemsetAsync(P->lvs_overflow.p, 0, B * sizeof(int), st));
-  eval_kernel_for(P->D)<<<dp.B, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
+  CK(cudaMemsetAsync(P->work_counter.p, 0, sizeof(int), st));
+  eval_kernel_for(P->D)<<<P->eval_grid, kEvalThreads, P->eval_smem, st>>>(dp, P->ex, EVAL_ONLY, P->x_tmp.p);
   SolveCtl ctl{};
   ctl.mode = SOLVE_QP_ONLY;  // one QP step per trajectory (one CTA each), no evaluation / decision
   ctl.quantum = 1;
