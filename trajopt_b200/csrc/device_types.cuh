@@ -81,7 +81,8 @@ struct DevProblem {
   int S, L, O, obstacles_per_traj;
   int n_costs, n_cnts, n_cart_rows, cart_stride, n_coll_cand, coll_stride;
   int n_cart_targets, n_fixed, max_rows, row_stride, coll_words;  // coll_words: 64-bit mask words per collision object
-  int n_sparse_lists, pad;
+  int n_sparse_lists, n_band;  // n_band: band offsets k with a structurally non-zero P(i, i-k)
+  int band_offs[32];           // those offsets, ascending (joint costs: 0, D, 2D)
   const DevSegment* segs;
   const DevSphere* spheres;
   const double* lower;

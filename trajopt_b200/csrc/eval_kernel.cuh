@@ -25,7 +25,7 @@ __host__ __device__ inline int eval_job_stride(int S) { return (S * kFrameStride
 
 struct EvalSmem {
   // offsets in doubles into the dynamic shared buffer
-  int x, sph, spo, jax, velp, objv, mask, misc, fr, terms, obst, sphr, segs, sphs, cobj, aobj, wscr, wscr_stride, total;
+  int x, sph, spo, jax, velp, objv, mask, misc, fr, terms, obst, sphr, segs, sphs, cobj, aobj, wscr, wscr_stride, cfk, total;
 };
 // n_vel_objs: CartVel step pairs; cast: the collision objects are step pairs (continuous evaluator), each holding at
 // most cast_cap active contacts
@@ -54,6 +54,8 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   // their values in canonical order
   s.wscr_stride = cast ? (S * 12 + 2 * L * 3 + (L & 1) + ((D + 1) & ~1) + 4 * cast_cap) : 0;
   s.wscr = o;   o += 8 * s.wscr_stride;
+  s.cfk = o;    o += 8 * (1 + D) * kFrameStride;    // running frames of the CartPose chain FK: one per lane and warp
+  o += o & 1;
   // the FK frames are dead once the joint axes / sphere centres are emitted: the term buffer of the later
   // phase reuses their space
   s.fr = o;                                           // frames of every FK job: local, then (in place) world
@@ -312,26 +314,44 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
       const DevObj& o = ex.cart_objs[c];
       const DevCartTerm& ct = p.cart_terms[o.term];
       Frame tgt, off, lf, src, e1;
-      quat_to_frame(o.target_slot >= 0 ? p.cart_targets + (static_cast<size_t>(b) * p.n_cart_targets + o.target_slot) * 7 : ct.tgt, tgt);
-      for (int i = 0; i < 9; ++i) off.R[i] = ct.src_R[i];
-      for (int i = 0; i < 3; ++i) off.p[i] = ct.src_p[i];
       {
+        // the running frame lives in shared memory (one 13-double slot per lane), the segment's local frame in
+        // registers: row i of (frame * local) needs only row i of the frame, so the product is formed in place
         const int* chain = ex.link_chain + o.link * (kMaxSeg + 1);
         const int clen = chain[0], pj = work ? col - 1 : -1;
         const double* qw = xs + o.first * D;
+        double* cur = sm + S.cfk + ((tid >> 5) * (1 + D) + (work ? col : 0)) * kFrameStride;
         for (int k = 0; k < clen; ++k) {
           const DevSegment& g = segs[chain[1 + k]];
           const double qv = (g.q_index >= 0) ? qw[g.q_index] + (g.q_index == pj ? 1e-5 : 0.0) : 0.0;
           Frame loc;
           segment_local_q(g, qv, loc);
-          if (k == 0) lf = loc;
-          else {
-            Frame nx;
-            frame_mul(lf, loc, nx);
-            lf = nx;
+          if (work) {
+            if (k == 0) {
+#pragma unroll
+              for (int i = 0; i < 9; ++i) cur[i] = loc.R[i];
+#pragma unroll
+              for (int i = 0; i < 3; ++i) cur[9 + i] = loc.p[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                const double r0 = cur[i * 3], r1 = cur[i * 3 + 1], r2 = cur[i * 3 + 2], rp = cur[9 + i];
+                cur[i * 3 + 0] = r0 * loc.R[0] + r1 * loc.R[3] + r2 * loc.R[6];
+                cur[i * 3 + 1] = r0 * loc.R[1] + r1 * loc.R[4] + r2 * loc.R[7];
+                cur[i * 3 + 2] = r0 * loc.R[2] + r1 * loc.R[5] + r2 * loc.R[8];
+                cur[9 + i] = r0 * loc.p[0] + r1 * loc.p[1] + r2 * loc.p[2] + rp;
+              }
+            }
           }
         }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) lf.R[i] = cur[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) lf.p[i] = cur[9 + i];
       }
+      quat_to_frame(o.target_slot >= 0 ? p.cart_targets + (static_cast<size_t>(b) * p.n_cart_targets + o.target_slot) * 7 : ct.tgt, tgt);
+      for (int i = 0; i < 9; ++i) off.R[i] = ct.src_R[i];
+      for (int i = 0; i < 3; ++i) off.p[i] = ct.src_p[i];
       frame_mul(lf, off, src);
       rel_pose(tgt, src, e1);
       double a1[3], g1;

@@ -136,6 +136,8 @@ struct QpCtx {
   int* rints;
   const int* colent;     // entries: (row << 5) | k (shared or global, like the rows)
   const double* Pband;   // shared copy of the objective band [N][2D+1]
+  const int* band_offs;  // the band offsets k with a structurally non-zero P(i, i-k), ascending; n_band of them
+  int n_band;
   double* scratch;
   double c, cinv, rho, rho_eq, sigma, alpha;
   __device__ __forceinline__ double* R(int r) const { return rows + static_cast<size_t>(r) * RS; }
@@ -454,6 +456,9 @@ struct SolveRoles {
   int fu_level, fu_vec, fu_dst, bu_level, bu_y, bu_wl, bu_dst;
   bool f0_valid, f0_store, b0_store, b0_hasl, b0_hasr, b0_yw;
   bool fu_valid, fu_store, bu_store, bu_hasl, bu_hasr, bu_yw;  // *_yw: the NB-long operand is read from w, not v
+  // upper-level rows read from the factor in shared memory (bcr_solve_hyb): offsets in doubles from the start of the
+  // dynamic shared memory, valid when the factor lives there
+  int fu_mat, bu_X, bu_Um;
 };
 template <int NB>
 __device__ inline SolveRoles solve_roles(const QpCtx& q) {
@@ -465,6 +470,8 @@ __device__ inline SolveRoles solve_roles(const QpCtx& q) {
   while ((1 << nl) - 1 < M) ++nl;
   R.n_fwd = nf;
   R.n_lvl = nl;
+  constexpr int BLK = NB * NB;
+  const int oSA = static_cast<int>(q.SA - q.smbase), oSLM = static_cast<int>(q.SLM - q.smbase), oSU = static_cast<int>(q.SU - q.smbase);
   auto fwd_role = [&](int l, int u, int& vec, int& dst, bool& valid, bool& store) {
     const int s = 1 << l, sh = l + 1, nS = M >> sh;
     const int task = u >> 1, side = u & 1, e = task / NB, r = task % NB;
@@ -475,6 +482,7 @@ __device__ inline SolveRoles solve_roles(const QpCtx& q) {
     vec = (valid ? pb : j - s) * NB;
     dst = j * NB + r;
     store = act && side == 0;
+    if (l > 0) R.fu_mat = (side ? oSLM : oSU) + (valid ? pb : j - s) * BLK + r * NB;
   };
   auto bwd_role = [&](int l, int u, int& y, int& wl, int& dst, bool& store, bool& hasl, bool& hasr, bool& yw) {
     const int s = 1 << l, first = s - 1, sh = l + 1, nE = (M + s) >> sh;
@@ -488,6 +496,10 @@ __device__ inline SolveRoles solve_roles(const QpCtx& q) {
     wl = (hasl ? p - s : 0) * NB + (side ? NB / 2 : 0);
     dst = p * NB + r;
     store = act && side == 0;
+    if (l > 0) {
+      R.bu_X = (side ? oSU : oSA) + p * BLK + r;
+      R.bu_Um = oSLM + p * BLK + (side ? (NB / 2) * NB : 0) + r;
+    }
   };
   // level 0: thread = (task, side)
   fwd_role(0, tid, R.f0_vec, R.f0_dst, R.f0_valid, R.f0_store);
@@ -625,6 +637,65 @@ __device__ __forceinline__ void bcr_solve_reg(const QpCtx& q, const SolveRoles& 
   __syncthreads();
 }
 
+// Hybrid solve for the ADMM block: level 0 (every thread has a role there) applies factor rows held in registers, the
+// upper levels (a few warps each) read their rows from the factor in shared memory.  Half the registers of
+// bcr_solve_reg: nothing of the thread's loop state spills.
+template <int NB>
+__device__ __forceinline__ void bcr_solve_hyb(const int tid, const SolveRoles& R, const double (&mF0)[NB],
+                                              const double (&mB0)[NB + NB / 2], const double* sm_base, double* v, double* w) {
+  const int wbase = tid & ~31;
+  const bool side = tid & 1;
+  __syncthreads();
+  // ---- down
+  if (wbase < R.f0_warps) {
+    double a = fwd_dot<NB>(mF0, v + R.f0_vec);
+    a = R.f0_valid ? a : 0.0;
+    const double o = __shfl_xor_sync(0xffffffffu, a, 1);
+    if (R.f0_store) v[R.f0_dst] -= a + o;
+  }
+  __syncthreads();
+  for (int l = 1; l < R.n_fwd; ++l) {
+    const bool mine = R.fu_level == l;
+    if (__any_sync(0xffffffffu, mine)) {
+      double a = dot_row<NB>(sm_base + (mine ? R.fu_mat : 0), v + (mine ? R.fu_vec : 0));
+      a = (mine && R.fu_valid) ? a : 0.0;
+      const double o = __shfl_xor_sync(0xffffffffu, a, 1);
+      if (mine && R.fu_store) v[R.fu_dst] -= a + o;
+    }
+    __syncthreads();
+  }
+  // ---- up
+  for (int l = R.n_lvl - 1; l >= 1; --l) {
+    const bool mine = R.bu_level == l;
+    if (__any_sync(0xffffffffu, mine)) {
+      const double* y = (R.bu_yw ? w : v) + (mine ? R.bu_y : 0);
+      const double* wl = w + (mine ? R.bu_wl : 0);
+      const double* X = sm_base + (mine ? R.bu_X : 0);
+      const double* Um = sm_base + (mine ? R.bu_Um : 0);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < NB; k += 2) {
+        a0 += X[k * NB] * y[k];
+        a1 += X[(k + 1) * NB] * y[k + 1];
+      }
+#pragma unroll
+      for (int k = 0; k < NB / 2; ++k) a2 += Um[k * NB] * wl[k];
+      const double dx = a0 + a1;
+      double acc = (R.bu_yw ? (R.bu_hasr ? -dx : 0.0) : dx) - (R.bu_hasl ? a2 : 0.0);
+      acc = mine ? acc : 0.0;
+      const double o = __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (mine && R.bu_store) w[R.bu_dst] = acc + o;
+    }
+    __syncthreads();
+  }
+  if (wbase < R.b0_warps) {
+    const double acc = bwd_dot<NB>(mB0, (side ? w : v) + R.b0_y, w + R.b0_wl, side, R.b0_hasl, R.b0_hasr);
+    const double o = __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (R.b0_store) w[R.b0_dst] = acc + o;
+  }
+  __syncthreads();
+}
+
 // scaled P (band) times a vector: out = c * Dz .* (P (Dz .* in)); in: shared or global, out: global/shared.
 // The band loads are independent and fully unrolled, so the pass costs one memory round trip, not 2*HB+1.
 template <int NB>
@@ -634,25 +705,16 @@ __device__ inline void p_matvec(const QpCtx& q, const double* in, double* out) {
   for (int i = q.tid; i < q.Np; i += kQpThreads) {
     double s = 0.0;
     if (i < N) {
-      double pl[W], pu[HB], xl[W], xu[HB];  // (P * Dz) and x, multiplied in the reference's order
-#pragma unroll
-      for (int k = 0; k <= HB; ++k) {
-        const bool on = k <= i;
-        const int j = on ? i - k : i;
-        pl[k] = (on ? q.Pband[i * W + k] : 0.0) * q.Dz[j];
-        xl[k] = in[j];
+      // (P * Dz) and x, multiplied and added in the reference's order: the lower part of row i (k = 0..HB), then the
+      // upper part; only the structurally non-zero offsets are visited (a zero entry adds an exact zero)
+      for (int t = 0; t < q.n_band; ++t) {
+        const int k = q.band_offs[t];
+        if (k <= i) s += (q.Pband[i * W + k] * q.Dz[i - k]) * in[i - k];
       }
-#pragma unroll
-      for (int k = 1; k <= HB; ++k) {
-        const bool on = i + k < N;
-        const int j = on ? i + k : i;
-        pu[k - 1] = (on ? q.Pband[j * W + k] : 0.0) * q.Dz[j];
-        xu[k - 1] = in[j];
+      for (int t = 0; t < q.n_band; ++t) {
+        const int k = q.band_offs[t];
+        if (k >= 1 && i + k < N) s += (q.Pband[(i + k) * W + k] * q.Dz[i + k]) * in[i + k];
       }
-#pragma unroll
-      for (int k = 0; k <= HB; ++k) s += pl[k] * xl[k];
-#pragma unroll
-      for (int k = 0; k < HB; ++k) s += pu[k] * xu[k];
       s *= q.c * q.Dz[i];
     }
     out[i] = s;
@@ -714,7 +776,10 @@ __device__ __noinline__ bool assemble_factor(const QpCtx& q, const SysW& w) {
       if (k <= r) Arow[r - k] += val;
       else Lrow[nb + r - k] += val;
     };
-    for (int k = 0; k <= HB && k <= i; ++k) add(k, q.c * q.Dz[i] * q.Pband[i * PW + k] * q.Dz[i - k]);
+    for (int t = 0; t < q.n_band; ++t) {
+      const int k = q.band_offs[t];
+      if (k <= i) add(k, q.c * q.Dz[i] * q.Pband[i * PW + k] * q.Dz[i - k]);
+    }
     add(0, w.sig + xbound_weight(q, w, i) * q.beta[i] * q.beta[i]);
     for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
       const int ent = q.colent[e], rw = ent >> 5, k = ent & 31;
@@ -977,23 +1042,9 @@ __device__ __noinline__ void admm_block_fast(const QpCtx& q, const double rho_au
   double* const dxs = q.scratch;
   double* const dyb = q.scratch + Np;
   const SolveRoles roles = solve_roles<NB>(q);
-  double mF0[NB], mB0[NB + NB / 2], mFU[NB], mBU[NB + NB / 2];
-  {
-    load_fwd_row<NB>(q, 0, tid, mF0);
-    load_bwd_row<NB>(q, 0, tid, mB0);
-    int off = 0;
-    for (int l = 1; l < roles.n_fwd; ++l) {
-      const int cnt = 2 * (q.M >> (l + 1)) * NB;
-      if (roles.fu_level == l) load_fwd_row<NB>(q, l, tid - off, mFU);
-      off += cnt;
-    }
-    off = 0;
-    for (int l = 1; l < roles.n_lvl; ++l) {
-      const int cnt = 2 * ((q.M + (1 << l)) >> (l + 1)) * NB;
-      if (roles.bu_level == l) load_bwd_row<NB>(q, l, tid - off, mBU);
-      off += cnt;
-    }
-  }
+  double mF0[NB], mB0[NB + NB / 2];  // level-0 rows of the factor; the upper levels read theirs from shared memory
+  load_fwd_row<NB>(q, 0, tid, mF0);
+  load_bwd_row<NB>(q, 0, tid, mB0);
   // ---- this thread's variable
   const bool has_var = tid < N;
   const int vi = has_var ? tid : 0;
@@ -1044,8 +1095,8 @@ __device__ __noinline__ void admm_block_fast(const QpCtx& q, const double rho_au
         double c[kPre];
 #pragma unroll
         for (int k = 0; k < kPre; ++k) c[k] = sm[ea[k]];
-#pragma unroll
-        for (int k = 0; k < kPre; ++k) s += c[k];
+        // (a fixed pairwise order: the eight loads are in flight together instead of one load per dependent add)
+        s += ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
         for (int e = e0 + kPre; e < e1; ++e) {
           const int ent = colent[e];
           s += rows[(ent >> 5) * RS + (2 * CNc + R_NF) + (ent & 31)];
@@ -1056,7 +1107,7 @@ __device__ __noinline__ void admm_block_fast(const QpCtx& q, const double rho_au
     }
     {
       PROF_T0();
-      bcr_solve_reg<NB>(q, roles, mF0, mB0, mFU, mBU, v1, w);
+      bcr_solve_hyb<NB>(tid, roles, mF0, mB0, sm, v1, w);
       PROF_ADD(2);
     }
     PROF_T0();
@@ -1186,8 +1237,11 @@ __device__ inline void qp_scale(QpCtx& q, const QpSettings& st, int n_aux_total)
     // column norms of [P A'; A 0] restricted to the trajectory variables (one thread per variable)
     for (int i = tid; i < N; i += kQpThreads) {
       double m = 0.0;
-      for (int k = 0; k <= HB && k <= i; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[i * W + k] * q.Dz[i - k]));
-      for (int k = 1; k <= HB && i + k < N; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[(i + k) * W + k] * q.Dz[i + k]));
+      for (int t = 0; t < q.n_band; ++t) {  // (structurally zero band entries cannot raise a norm)
+        const int k = q.band_offs[t];
+        if (k <= i) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[i * W + k] * q.Dz[i - k]));
+        if (k >= 1 && i + k < N) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[(i + k) * W + k] * q.Dz[i + k]));
+      }
       const double bn = fabs(Eb[i] * q.Dz[i]);
       m = fmax(m, bn);
       for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
@@ -1209,8 +1263,11 @@ __device__ inline void qp_scale(QpCtx& q, const QpSettings& st, int n_aux_total)
     double csum = 0.0, qn = 0.0;
     for (int i = tid; i < N; i += kQpThreads) {
       double m = 0.0;
-      for (int k = 0; k <= HB && k <= i; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[i * W + k] * q.Dz[i - k]));
-      for (int k = 1; k <= HB && i + k < N; ++k) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[(i + k) * W + k] * q.Dz[i + k]));
+      for (int t = 0; t < q.n_band; ++t) {  // (structurally zero band entries cannot raise a norm)
+        const int k = q.band_offs[t];
+        if (k <= i) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[i * W + k] * q.Dz[i - k]));
+        if (k >= 1 && i + k < N) m = fmax(m, fabs(q.c * q.Dz[i] * q.Pband[(i + k) * W + k] * q.Dz[i + k]));
+      }
       csum += m;
       qn = fmax(qn, fabs(q.c * q.Dz[i] * qs[i]));
     }
@@ -1885,6 +1942,8 @@ __device__ __noinline__ void qp_step(const DevProblem& p, const int b, const dou
   int* colent = mylist + q.Np + 1;                        // [max_rows*CN]
   int* obj_start = colent + static_cast<size_t>(p.max_rows) * q.CN;  // [n_objs+1]
   q.colent = colent;
+  q.band_offs = p.band_offs;
+  q.n_band = p.n_band;
   if (S.pband_smem) {
     q.Pband = sm + S.Pb;
     for (int t = tid; t < N * (NB + 1); t += kQpThreads) sm[S.Pb + t] = p.Pband[t];

@@ -447,6 +447,14 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
         }
   }
 
+  {  // the structurally non-zero offsets of the band (the kernels visit only these)
+    dp.n_band = 0;
+    for (int k = 0; k < W; ++k) {
+      bool nz = false;
+      for (int i = k; i < N && !nz; ++i) nz = Pband[static_cast<size_t>(i) * W + k] != 0.0;
+      if (nz) dp.band_offs[dp.n_band++] = k;
+    }
+  }
   // ---- layout ---------------------------------------------------------------------------------------
   dp.n_costs = static_cast<int>(P->cost_objs.size());
   dp.n_cnts = static_cast<int>(P->cnt_objs.size());
