@@ -145,8 +145,18 @@ struct QpCtx {
   __device__ __forceinline__ const int* I(int r) const { return rints + static_cast<size_t>(r) * RI_NINTS; }
 };
 
-// ---- block reductions: xor butterfly inside each warp, then 8 partials through shared memory ---------------
-// vals[k] -> max, or (bit k of sum_mask set) the sum; fixed order, every thread gets the result.
+// ---- block reductions: inside each warp, then 8 partials through shared memory ------------------------------
+// vals[k] -> max, or (bit k of sum_mask set) the sum; fixed order, every thread gets the result.  Every quantity that
+// is max-reduced here is a norm (>= 0, built from fabs): non-negative doubles order like their bit patterns, so the
+// warp maximum is two 32-bit redux instructions (high word, then the low words of the lanes that hold it) instead of
+// five 64-bit shuffle steps.  NaNs are ignored, as fmax ignores them.
+__device__ __forceinline__ double warp_max_norm(double v) {
+  v = (v != v) ? 0.0 : v;
+  const unsigned hi = static_cast<unsigned>(__double2hiint(v)) & 0x7fffffffu, lo = static_cast<unsigned>(__double2loint(v));
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return __hiloint2double(static_cast<int>(mh), static_cast<int>(ml));
+}
 template <int NQ>
 __device__ inline void block_reduce(const QpCtx& q, double (&vals)[NQ], unsigned sum_mask) {
   static_assert(NQ <= 16, "red area too small");
@@ -156,10 +166,11 @@ __device__ inline void block_reduce(const QpCtx& q, double (&vals)[NQ], unsigned
   for (int k = 0; k < NQ; ++k) {
     double v = vals[k];
     const bool sum = (sum_mask >> k) & 1u;
+    if (sum) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double o = __shfl_xor_sync(0xffffffffu, v, off);
-      v = sum ? v + o : fmax(v, o);
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    } else {
+      v = warp_max_norm(v);
     }
     if (lane == 0) q.red[k * 8 + wid] = v;
   }
@@ -167,10 +178,14 @@ __device__ inline void block_reduce(const QpCtx& q, double (&vals)[NQ], unsigned
 #pragma unroll
   for (int k = 0; k < NQ; ++k) {
     const bool sum = (sum_mask >> k) & 1u;
-    double acc = q.red[k * 8];
+    if (sum) {
+      double acc = q.red[k * 8];
 #pragma unroll
-    for (int w = 1; w < kQpThreads / 32; ++w) acc = sum ? acc + q.red[k * 8 + w] : fmax(acc, q.red[k * 8 + w]);
-    vals[k] = acc;
+      for (int w = 1; w < kQpThreads / 32; ++w) acc += q.red[k * 8 + w];
+      vals[k] = acc;
+    } else {
+      vals[k] = warp_max_norm(q.red[k * 8 + (lane & 7)]);  // every warp reduces the 8 partials again
+    }
   }
   __syncthreads();
 }
@@ -458,7 +473,7 @@ struct SolveRoles {
   bool fu_valid, fu_store, bu_store, bu_hasl, bu_hasr, bu_yw;  // *_yw: the NB-long operand is read from w, not v
   // upper-level rows read from the factor in shared memory (bcr_solve_hyb): offsets in doubles from the start of the
   // dynamic shared memory, valid when the factor lives there
-  int fu_mat, bu_X, bu_Um;
+  int fu_mat, bu_X, bu_Um, f0_mat, b0_X, b0_Um;
 };
 template <int NB>
 __device__ inline SolveRoles solve_roles(const QpCtx& q) {
@@ -482,7 +497,7 @@ __device__ inline SolveRoles solve_roles(const QpCtx& q) {
     vec = (valid ? pb : j - s) * NB;
     dst = j * NB + r;
     store = act && side == 0;
-    if (l > 0) R.fu_mat = (side ? oSLM : oSU) + (valid ? pb : j - s) * BLK + r * NB;
+    (l > 0 ? R.fu_mat : R.f0_mat) = (side ? oSLM : oSU) + (valid ? pb : j - s) * BLK + r * NB;
   };
   auto bwd_role = [&](int l, int u, int& y, int& wl, int& dst, bool& store, bool& hasl, bool& hasr, bool& yw) {
     const int s = 1 << l, first = s - 1, sh = l + 1, nE = (M + s) >> sh;
@@ -496,10 +511,8 @@ __device__ inline SolveRoles solve_roles(const QpCtx& q) {
     wl = (hasl ? p - s : 0) * NB + (side ? NB / 2 : 0);
     dst = p * NB + r;
     store = act && side == 0;
-    if (l > 0) {
-      R.bu_X = (side ? oSU : oSA) + p * BLK + r;
-      R.bu_Um = oSLM + p * BLK + (side ? (NB / 2) * NB : 0) + r;
-    }
+    (l > 0 ? R.bu_X : R.b0_X) = (side ? oSU : oSA) + p * BLK + r;
+    (l > 0 ? R.bu_Um : R.b0_Um) = oSLM + p * BLK + (side ? (NB / 2) * NB : 0) + r;
   };
   // level 0: thread = (task, side)
   fwd_role(0, tid, R.f0_vec, R.f0_dst, R.f0_valid, R.f0_store);
@@ -637,18 +650,75 @@ __device__ __forceinline__ void bcr_solve_reg(const QpCtx& q, const SolveRoles& 
   __syncthreads();
 }
 
-// Hybrid solve for the ADMM block: level 0 (every thread has a role there) applies factor rows held in registers, the
-// upper levels (a few warps each) read their rows from the factor in shared memory.  Half the registers of
-// bcr_solve_reg: nothing of the thread's loop state spills.
+// Shared-memory loads that stay where they are written: every level of the solve is a short dependent chain (loads ->
+// 14 multiply-adds -> shuffle -> store -> barrier), and a schedule that interleaves one load with the two multiply-adds
+// that consume it exposes the load latency seven times per level instead of once.
+__device__ __forceinline__ double2 lds_v2(const double* p) {
+  double2 v;
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(const double* p) {
+  double v;
+  const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+// Solve for the ADMM block with every level reading its factor rows from shared memory through fixed per-thread
+// roles (offsets computed once per block).  No matrix row is kept in a register: the block's register budget goes to
+// having all the loads of a level in flight at once.
 template <int NB>
-__device__ __forceinline__ void bcr_solve_hyb(const int tid, const SolveRoles& R, const double (&mF0)[NB],
-                                              const double (&mB0)[NB + NB / 2], const double* sm_base, double* v, double* w) {
+__device__ __forceinline__ double bcr_fwd_task(const double* mrow, const double* yv) {
+  constexpr int H = NB / 2;
+  double2 mm[H], yy[H];
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    mm[k] = lds_v2(mrow + 2 * k);
+    yy[k] = lds_v2(yv + 2 * k);
+  }
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    a0 += mm[k].x * yy[k].x;
+    a1 += mm[k].y * yy[k].y;
+  }
+  return a0 + a1;
+}
+template <int NB>
+__device__ __forceinline__ double bcr_bwd_task(const double* X, const double* Um, const double* y, const double* wl,
+                                               bool side, bool hasl, bool hasr) {
+  constexpr int H = NB / 2;
+  double2 yy[H];
+  double xx[NB], um[H], ww[H];
+#pragma unroll
+  for (int k = 0; k < H; ++k) yy[k] = lds_v2(y + 2 * k);
+#pragma unroll
+  for (int k = 0; k < NB; ++k) xx[k] = lds_f64(X + k * NB);
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    um[k] = lds_f64(Um + k * NB);
+    ww[k] = lds_f64(wl + k);
+  }
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    a0 += xx[2 * k] * yy[k].x;
+    a1 += xx[2 * k + 1] * yy[k].y;
+  }
+#pragma unroll
+  for (int k = 0; k < H; ++k) a2 += um[k] * ww[k];
+  const double dx = a0 + a1;
+  return (side ? (hasr ? -dx : 0.0) : dx) - (hasl ? a2 : 0.0);
+}
+template <int NB>
+__device__ __forceinline__ void bcr_solve_sm(const int tid, const SolveRoles& R, const double* sm_base, double* v, double* w) {
   const int wbase = tid & ~31;
   const bool side = tid & 1;
   __syncthreads();
   // ---- down
   if (wbase < R.f0_warps) {
-    double a = fwd_dot<NB>(mF0, v + R.f0_vec);
+    double a = bcr_fwd_task<NB>(sm_base + R.f0_mat, v + R.f0_vec);
     a = R.f0_valid ? a : 0.0;
     const double o = __shfl_xor_sync(0xffffffffu, a, 1);
     if (R.f0_store) v[R.f0_dst] -= a + o;
@@ -657,7 +727,7 @@ __device__ __forceinline__ void bcr_solve_hyb(const int tid, const SolveRoles& R
   for (int l = 1; l < R.n_fwd; ++l) {
     const bool mine = R.fu_level == l;
     if (__any_sync(0xffffffffu, mine)) {
-      double a = dot_row<NB>(sm_base + (mine ? R.fu_mat : 0), v + (mine ? R.fu_vec : 0));
+      double a = bcr_fwd_task<NB>(sm_base + (mine ? R.fu_mat : 0), v + (mine ? R.fu_vec : 0));
       a = (mine && R.fu_valid) ? a : 0.0;
       const double o = __shfl_xor_sync(0xffffffffu, a, 1);
       if (mine && R.fu_store) v[R.fu_dst] -= a + o;
@@ -668,20 +738,9 @@ __device__ __forceinline__ void bcr_solve_hyb(const int tid, const SolveRoles& R
   for (int l = R.n_lvl - 1; l >= 1; --l) {
     const bool mine = R.bu_level == l;
     if (__any_sync(0xffffffffu, mine)) {
-      const double* y = (R.bu_yw ? w : v) + (mine ? R.bu_y : 0);
-      const double* wl = w + (mine ? R.bu_wl : 0);
-      const double* X = sm_base + (mine ? R.bu_X : 0);
-      const double* Um = sm_base + (mine ? R.bu_Um : 0);
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-#pragma unroll
-      for (int k = 0; k < NB; k += 2) {
-        a0 += X[k * NB] * y[k];
-        a1 += X[(k + 1) * NB] * y[k + 1];
-      }
-#pragma unroll
-      for (int k = 0; k < NB / 2; ++k) a2 += Um[k * NB] * wl[k];
-      const double dx = a0 + a1;
-      double acc = (R.bu_yw ? (R.bu_hasr ? -dx : 0.0) : dx) - (R.bu_hasl ? a2 : 0.0);
+      double acc = bcr_bwd_task<NB>(sm_base + (mine ? R.bu_X : 0), sm_base + (mine ? R.bu_Um : 0),
+                                    (R.bu_yw ? w : v) + (mine ? R.bu_y : 0), w + (mine ? R.bu_wl : 0), R.bu_yw, R.bu_hasl,
+                                    R.bu_hasr);
       acc = mine ? acc : 0.0;
       const double o = __shfl_xor_sync(0xffffffffu, acc, 1);
       if (mine && R.bu_store) w[R.bu_dst] = acc + o;
@@ -689,7 +748,8 @@ __device__ __forceinline__ void bcr_solve_hyb(const int tid, const SolveRoles& R
     __syncthreads();
   }
   if (wbase < R.b0_warps) {
-    const double acc = bwd_dot<NB>(mB0, (side ? w : v) + R.b0_y, w + R.b0_wl, side, R.b0_hasl, R.b0_hasr);
+    const double acc = bcr_bwd_task<NB>(sm_base + R.b0_X, sm_base + R.b0_Um, (side ? w : v) + R.b0_y, w + R.b0_wl, side,
+                                        R.b0_hasl, R.b0_hasr);
     const double o = __shfl_xor_sync(0xffffffffu, acc, 1);
     if (R.b0_store) w[R.b0_dst] = acc + o;
   }
@@ -1042,9 +1102,6 @@ __device__ __noinline__ void admm_block_fast(const QpCtx& q, const double rho_au
   double* const dxs = q.scratch;
   double* const dyb = q.scratch + Np;
   const SolveRoles roles = solve_roles<NB>(q);
-  double mF0[NB], mB0[NB + NB / 2];  // level-0 rows of the factor; the upper levels read theirs from shared memory
-  load_fwd_row<NB>(q, 0, tid, mF0);
-  load_bwd_row<NB>(q, 0, tid, mB0);
   // ---- this thread's variable
   const bool has_var = tid < N;
   const int vi = has_var ? tid : 0;
@@ -1107,7 +1164,7 @@ __device__ __noinline__ void admm_block_fast(const QpCtx& q, const double rho_au
     }
     {
       PROF_T0();
-      bcr_solve_hyb<NB>(tid, roles, mF0, mB0, sm, v1, w);
+      bcr_solve_sm<NB>(tid, roles, sm, v1, w);
       PROF_ADD(2);
     }
     PROF_T0();
@@ -1383,19 +1440,32 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
   }
   SysW sysw{false, st.sigma, rho};
   bool factor_ok = true;
-  { PROF_T0(); factor_ok = assemble_factor<NB>(q, sysw); PROF_ADD(6); }
+
   // the ADMM loop keeps the thread's rows of the factor in registers when the roles fit the CTA (admm_block<.., true>)
   const bool use_reg = REGOK && solve_roles_fit(q.M, NB);
+  using BlockFn = void (*)(const QpCtx&, double, int, int);
   auto run_block = [&](int n, bool keep_last) {
     if constexpr (REGOK) {
       if (use_reg) {
-        if (q.rows_smem) admm_block_fast<NB, PAIR>(q, sysw.rho_aux, n, keep_last ? 1 : 0);
-        else admm_block<NB, PAIR, true>(q, sysw.rho_aux, n, keep_last ? 1 : 0);
+        // (called through pointers: an indirect call follows the standard calling convention, so the block gets the
+        // whole register file — saving what it uses of the callee-saved registers at entry — instead of the registers
+        // this solver's own state leaves free.  Measured: with a direct call the caller's register allocation squeezes
+        // the loop and every level of its solve is scheduled one shared-memory load at a time.)
+        BlockFn volatile fn = q.rows_smem ? &admm_block_fast<NB, PAIR> : &admm_block<NB, PAIR, true>;
+        fn(q, sysw.rho_aux, n, keep_last ? 1 : 0);
         return;
       }
     }
-    admm_block<NB, PAIR, false>(q, sysw.rho_aux, n, keep_last ? 1 : 0);
+    BlockFn volatile fn = &admm_block<NB, PAIR, false>;
+    fn(q, sysw.rho_aux, n, keep_last ? 1 : 0);
   };
+  // the same for the factorisation (a few calls per QP, tens of thousands of cycles each)
+  using FactorFn = bool (*)(const QpCtx&, const SysW&);
+  auto factorize = [&](const SysW& wts) -> bool {
+    FactorFn volatile fn = &assemble_factor<NB>;
+    return fn(q, wts);
+  };
+  { PROF_T0(); factor_ok = factorize(sysw); PROF_ADD(6); }
 
   double* dxs = q.scratch;              // [Np] last trajectory step (written on check iterations)
   double* dyb = q.scratch + q.Np;       // [Np] last dual step of the variable-bound rows
@@ -1661,7 +1731,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
               have_failed_guess = true;
               restore_fn(false);
               info_pass();  // the polish reuses the vectors of the residual bookkeeping
-              if (!assemble_factor<NB>(q, sysw)) {
+              if (!factorize(sysw)) {
                 status = QPS_NONCVX;
                 stop = true;
               }
@@ -1681,7 +1751,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
             q.rho_eq = kRhoEqOverIneq * rho;
             sysw.rho_aux = rho;
             out.rho_updates++;
-            if (!assemble_factor<NB>(q, sysw)) {
+            if (!factorize(sysw)) {
               status = QPS_NONCVX;
               stop = true;
             }
@@ -1738,7 +1808,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
       }
     }
     __syncthreads();
-    if (!assemble_factor<NB>(q, pw)) return false;
+    if (!factorize(pw)) return false;
     for (int it = 0; it <= st.polish_refine_iter + 1; ++it) {
       const bool last = (it == st.polish_refine_iter + 1);  // final pass: pending dual update + residuals only
       p_matvec<NB>(q, q.x, q.v2);  // v2 <- P xq
@@ -1874,7 +1944,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
         ++round;
         eps_scale *= 0.1;
         restore_admm_state(false);
-        if (!assemble_factor<NB>(q, sysw)) {  // back to the ADMM factor
+        if (!factorize(sysw)) {  // back to the ADMM factor
           status = QPS_NONCVX;
           done = true;
         }

@@ -520,6 +520,12 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
     return fail(TB200_ERR_NO_DEVICE, "no CUDA device: trajopt_b200 has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(TB200_ERR_INVALID, "bad device ordinal");
   CK(cudaSetDevice(device));
+  {  // the QP step calls its hot functions through pointers (standard calling convention): make sure the per-thread stack
+     // covers the deepest chain (ptxas reports < 3 KB for the chains it can follow)
+    size_t cur = 0;
+    CK(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
+    if (cur < 6144) CK(cudaDeviceSetLimit(cudaLimitStackSize, 6144));
+  }
   CK(cudaFuncSetAttribute(eval_kernel_for(D), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->eval_smem)));
   P->solve_smem = std::max(P->qp_smem, P->eval_smem);  // the QP step and the evaluation step share one buffer
   CK(cudaFuncSetAttribute(solve_kernel_for(D, P->pair_rows), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P->solve_smem)));
