@@ -16,4 +16,6 @@ print(f"B={B} wall {dt:.2f}s, total ADMM iters {tot_iters}, qp solves {got['n_qp
 for i, n in enumerate(names[:9]):
     print(f"  {n:22s} {prof[i]/1e6:10.1f} Mcycles  per-iter {prof[i]/max(tot_iters,1):9.0f} cycles")
 nq = got['n_qp_solves'].sum()
+for slot, n in ((4, "solve: wait for the rhs barrier"), (14, "solve: level 0 down"), (15, "solve: upper levels down"), (9, "solve: upper levels up"),):
+    print(f"  {n:32s} {prof[slot]/1e6:10.1f} Mcycles  per-iter {prof[slot]/max(tot_iters,1):9.0f} cycles")
 print(f"  assemble (all calls) {prof[10]/1e6:10.1f} Mcycles, bcr_factor (all calls) {prof[11]/1e6:10.1f} Mcycles, polish passes {prof[12]/1e6:10.1f} Mcycles in {prof[13]} polishes ({prof[13]/nq:.2f} per QP)")

@@ -715,10 +715,160 @@ template <int NB>
 __device__ __forceinline__ void bcr_solve_sm(const int tid, const SolveRoles& R, const double* sm_base, double* v, double* w) {
   const int wbase = tid & ~31;
   const bool side = tid & 1;
+#ifdef TB200_PROFILE
+  long long pt_ = clock64();
+#define PROF_LVL(slot) do { const long long n_ = clock64(); if (tid == 0) atomicAdd(&g_prof[slot], (unsigned long long)(n_ - pt_)); pt_ = n_; } while (0)
+#else
+#define PROF_LVL(slot)
+#endif
   __syncthreads();
+  PROF_LVL(4);   // wait for the right-hand side
   // ---- down
   if (wbase < R.f0_warps) {
     double a = bcr_fwd_task<NB>(sm_base + R.f0_mat, v + R.f0_vec);
+    a = R.f0_valid ? a : 0.0;
+    const double o = __shfl_xor_sync(0xffffffffu, a, 1);
+    if (R.f0_store) v[R.f0_dst] -= a + o;
+  }
+  __syncthreads();
+  PROF_LVL(14);  // level 0 down
+  for (int l = 1; l < R.n_fwd; ++l) {
+    const bool mine = R.fu_level == l;
+    if (__any_sync(0xffffffffu, mine)) {
+      double a = bcr_fwd_task<NB>(sm_base + (mine ? R.fu_mat : 0), v + (mine ? R.fu_vec : 0));
+      a = (mine && R.fu_valid) ? a : 0.0;
+      const double o = __shfl_xor_sync(0xffffffffu, a, 1);
+      if (mine && R.fu_store) v[R.fu_dst] -= a + o;
+    }
+    __syncthreads();
+  }
+  PROF_LVL(15);  // upper levels down
+  // ---- up
+  for (int l = R.n_lvl - 1; l >= 1; --l) {
+    const bool mine = R.bu_level == l;
+    if (__any_sync(0xffffffffu, mine)) {
+      double acc = bcr_bwd_task<NB>(sm_base + (mine ? R.bu_X : 0), sm_base + (mine ? R.bu_Um : 0),
+                                    (R.bu_yw ? w : v) + (mine ? R.bu_y : 0), w + (mine ? R.bu_wl : 0), R.bu_yw, R.bu_hasl,
+                                    R.bu_hasr);
+      acc = mine ? acc : 0.0;
+      const double o = __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (mine && R.bu_store) w[R.bu_dst] = acc + o;
+    }
+    __syncthreads();
+  }
+  PROF_LVL(9);   // upper levels up (slot 9 is otherwise the QP-step counter: read before it is used as such)
+  if (wbase < R.b0_warps) {
+    const double acc = bcr_bwd_task<NB>(sm_base + R.b0_X, sm_base + R.b0_Um, (side ? w : v) + R.b0_y, w + R.b0_wl, side,
+                                        R.b0_hasl, R.b0_hasr);
+    const double o = __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (R.b0_store) w[R.b0_dst] = acc + o;
+  }
+  __syncthreads();
+}
+
+// Register-resident solve for the ADMM block (called with the whole register file at its disposal): every thread
+// applies the same few factor rows in every solve, so they live in registers (level 0: one forward and one backward
+// row; upper levels: one each for the threads that have a role there) and a level only reads the right-hand side —
+// a few distinct 16-byte words per warp — from shared memory.  Measured with the rows read from shared memory instead:
+// level 0 alone moves 44 KB (down) and 75 KB (up) per solve through the 128 B/clock shared-memory port, 210 KB per
+// solve in all = 1640 cycles of pure bandwidth.  The loads of a level are issued before its multiply-adds.
+template <int NB>
+__device__ __forceinline__ double reg_fwd_task(const double (&m)[NB], const double* yv) {
+  constexpr int H = NB / 2;
+  double2 yy[H];
+#pragma unroll
+  for (int k = 0; k < H; ++k) yy[k] = lds_v2(yv + 2 * k);
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    a0 += m[2 * k] * yy[k].x;
+    a1 += m[2 * k + 1] * yy[k].y;
+  }
+  return a0 + a1;
+}
+template <int NB>
+__device__ __forceinline__ double reg_bwd_task(const double (&m)[NB + NB / 2], const double* y, const double* wl, bool side,
+                                               bool hasl, bool hasr) {
+  constexpr int H = NB / 2;
+  double2 yy[H];
+  double ww[H];
+#pragma unroll
+  for (int k = 0; k < H; ++k) yy[k] = lds_v2(y + 2 * k);
+#pragma unroll
+  for (int k = 0; k < H; ++k) ww[k] = lds_f64(wl + k);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    a0 += m[2 * k] * yy[k].x;
+    a1 += m[2 * k + 1] * yy[k].y;
+  }
+#pragma unroll
+  for (int k = 0; k < H; ++k) a2 += m[NB + k] * ww[k];
+  const double dx = a0 + a1;
+  return (side ? (hasr ? -dx : 0.0) : dx) - (hasl ? a2 : 0.0);
+}
+template <int NB>
+__device__ __forceinline__ void bcr_solve_regs(const int tid, const SolveRoles& R, const double (&mF0)[NB],
+                                               const double (&mB0)[NB + NB / 2], const double (&mFU)[NB],
+                                               const double (&mBU)[NB + NB / 2], double* v, double* w) {
+  const int wbase = tid & ~31;
+  const bool side = tid & 1;
+  __syncthreads();
+  // ---- down
+  if (wbase < R.f0_warps) {
+    double a = reg_fwd_task<NB>(mF0, v + R.f0_vec);
+    a = R.f0_valid ? a : 0.0;
+    const double o = __shfl_xor_sync(0xffffffffu, a, 1);
+    if (R.f0_store) v[R.f0_dst] -= a + o;
+  }
+  __syncthreads();
+  for (int l = 1; l < R.n_fwd; ++l) {
+    const bool mine = R.fu_level == l;
+    if (__any_sync(0xffffffffu, mine)) {
+      double a = reg_fwd_task<NB>(mFU, v + (mine ? R.fu_vec : 0));
+      a = (mine && R.fu_valid) ? a : 0.0;
+      const double o = __shfl_xor_sync(0xffffffffu, a, 1);
+      if (mine && R.fu_store) v[R.fu_dst] -= a + o;
+    }
+    __syncthreads();
+  }
+  // ---- up
+  for (int l = R.n_lvl - 1; l >= 1; --l) {
+    const bool mine = R.bu_level == l;
+    if (__any_sync(0xffffffffu, mine)) {
+      double acc = reg_bwd_task<NB>(mBU, (R.bu_yw ? w : v) + (mine ? R.bu_y : 0), w + (mine ? R.bu_wl : 0), R.bu_yw,
+                                    R.bu_hasl, R.bu_hasr);
+      acc = mine ? acc : 0.0;
+      const double o = __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (mine && R.bu_store) w[R.bu_dst] = acc + o;
+    }
+    __syncthreads();
+  }
+  if (wbase < R.b0_warps) {
+    const double acc = reg_bwd_task<NB>(mB0, (side ? w : v) + R.b0_y, w + R.b0_wl, side, R.b0_hasl, R.b0_hasr);
+    const double o = __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (R.b0_store) w[R.b0_dst] = acc + o;
+  }
+  __syncthreads();
+}
+
+// The solve of the ADMM block: level 0 (every thread has a role there: 44 KB + 75 KB of factor rows per solve if they
+// were read from shared memory) applies rows held in registers; the upper levels (a few warps each, 91 KB per solve in
+// all) read theirs from shared memory.  All four row sets in registers (140 registers) do not fit beside the loop's own
+// state even with the whole register file.
+template <int NB>
+__device__ __forceinline__ void bcr_solve_hyb(const int tid, const SolveRoles& R, const double (&mF0)[NB],
+                                              const double (&mB0)[NB + NB / 2], const double* sm_base, double* v, double* w) {
+  const int wbase = tid & ~31;
+  const bool side = tid & 1;
+  __syncthreads();
+  // ---- down
+  if (wbase < R.f0_warps) {
+#ifndef TB200_HYB_F0_REGS  // (default: the level-0 forward rows come from shared memory, only the backward rows are register resident)
+    double a = bcr_fwd_task<NB>(sm_base + R.f0_mat, v + R.f0_vec);
+#else
+    double a = reg_fwd_task<NB>(mF0, v + R.f0_vec);
+#endif
     a = R.f0_valid ? a : 0.0;
     const double o = __shfl_xor_sync(0xffffffffu, a, 1);
     if (R.f0_store) v[R.f0_dst] -= a + o;
@@ -748,8 +898,7 @@ __device__ __forceinline__ void bcr_solve_sm(const int tid, const SolveRoles& R,
     __syncthreads();
   }
   if (wbase < R.b0_warps) {
-    const double acc = bcr_bwd_task<NB>(sm_base + R.b0_X, sm_base + R.b0_Um, (side ? w : v) + R.b0_y, w + R.b0_wl, side,
-                                        R.b0_hasl, R.b0_hasr);
+    const double acc = reg_bwd_task<NB>(mB0, (side ? w : v) + R.b0_y, w + R.b0_wl, side, R.b0_hasl, R.b0_hasr);
     const double o = __shfl_xor_sync(0xffffffffu, acc, 1);
     if (R.b0_store) w[R.b0_dst] = acc + o;
   }
@@ -1102,6 +1251,9 @@ __device__ __noinline__ void admm_block_fast(const QpCtx& q, const double rho_au
   double* const dxs = q.scratch;
   double* const dyb = q.scratch + Np;
   const SolveRoles roles = solve_roles<NB>(q);
+  double mF0[NB], mB0[NB + NB / 2];  // the thread's level-0 rows of the factor
+  load_fwd_row<NB>(q, 0, tid, mF0);
+  load_bwd_row<NB>(q, 0, tid, mB0);
   // ---- this thread's variable
   const bool has_var = tid < N;
   const int vi = has_var ? tid : 0;
@@ -1153,7 +1305,8 @@ __device__ __noinline__ void admm_block_fast(const QpCtx& q, const double rho_au
 #pragma unroll
         for (int k = 0; k < kPre; ++k) c[k] = sm[ea[k]];
         // (a fixed pairwise order: the eight loads are in flight together instead of one load per dependent add)
-        s += ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+        if constexpr (kPre == 8) s += ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+        else s += (c[0] + c[1]) + (c[2] + c[3]);
         for (int e = e0 + kPre; e < e1; ++e) {
           const int ent = colent[e];
           s += rows[(ent >> 5) * RS + (2 * CNc + R_NF) + (ent & 31)];
@@ -1164,7 +1317,7 @@ __device__ __noinline__ void admm_block_fast(const QpCtx& q, const double rho_au
     }
     {
       PROF_T0();
-      bcr_solve_sm<NB>(tid, roles, sm, v1, w);
+      bcr_solve_hyb<NB>(tid, roles, mF0, mB0, sm, v1, w);
       PROF_ADD(2);
     }
     PROF_T0();
