@@ -62,7 +62,7 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   s.terms = o;                                        // per-(step, joint) terms of the joint-space objects (later phase)
   // ... and, while the collision rows are written, the per-warp staging tiles of the bulk (TMA) row stores
   const int a = T * eval_job_stride(S), b2 = n_joint_objs * 2 * T * D;
-  const int st = (((D + 3) & 1) == 0 && !cast) ? 8 * 2 * 32 * (D + 3) : 0;  // two tiles per warp (double buffered)
+  const int st = (((D + 3) & 1) == 0 && !cast) ? 8 * 32 * (D + 3) : 0;  // one staging tile per warp
   const int m = a > b2 ? a : b2;
   o += m > st ? m : st;
   o += o & 1;
@@ -146,8 +146,8 @@ __device__ inline void warp_fk(const DevProblem& p, const double* q, double* F, 
 }
 
 template <int DD>
-__device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex, const int mode, const int b,
-                                          const double* x_in /*EVAL_ONLY*/) {
+__device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalExtra& ex, const int mode, const int b,
+                                               const double* x_in /*EVAL_ONLY*/) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
   constexpr int D = DD;
@@ -366,8 +366,12 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
       double* err_out = p.cart_err + slot * p.n_cart_rows + o.src_off;
       double* jac_out = p.cart_jac + (slot * p.n_cart_rows + o.src_off) * p.cart_stride;
       if (col == 0) {
-        const double e[6] = {e1.p[0], e1.p[1], e1.p[2], a1[0] * g1, a1[1] * g1, a1[2] * g1};
-        for (int r = 0; r < ct.n_idx; ++r) err_out[r] = e[ct.idx[r]] * ct.coeff[r];
+        const double e0 = e1.p[0], e1v = e1.p[1], e2 = e1.p[2], e3 = a1[0] * g1, e4 = a1[1] * g1, e5 = a1[2] * g1;
+        for (int r = 0; r < ct.n_idx; ++r) {  // (a select chain: a dynamically indexed array would live in local memory)
+          const int ix = ct.idx[r];
+          const double ev = ix == 0 ? e0 : (ix == 1 ? e1v : (ix == 2 ? e2 : (ix == 3 ? e3 : (ix == 4 ? e4 : e5))));
+          err_out[r] = ev * ct.coeff[r];
+        }
       } else if (work) {
         if (a1[0] * a0[0] + a1[1] * a0[1] + a1[2] * a0[2] < 0) {
           a1[0] = -a1[0]; a1[1] = -a1[1]; a1[2] = -a1[2];
@@ -376,9 +380,13 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
         const double diff = g1 - g0, pi = 3.14159265358979323846;
         if (diff > pi) g1 -= 2.0 * pi;
         else if (diff < -pi) g1 += 2.0 * pi;
-        const double dlt[6] = {e1.p[0] - e0p[0], e1.p[1] - e0p[1], e1.p[2] - e0p[2],
-                               a1[0] * g1 - a0[0] * g0, a1[1] * g1 - a0[1] * g0, a1[2] * g1 - a0[2] * g0};
-        for (int r = 0; r < ct.n_idx; ++r) jac_out[r * p.cart_stride + (col - 1)] = dlt[ct.idx[r]] / 1e-5 * ct.coeff[r];
+        const double d0 = e1.p[0] - e0p[0], d1 = e1.p[1] - e0p[1], d2 = e1.p[2] - e0p[2], d3 = a1[0] * g1 - a0[0] * g0,
+                     d4 = a1[1] * g1 - a0[1] * g0, d5 = a1[2] * g1 - a0[2] * g0;
+        for (int r = 0; r < ct.n_idx; ++r) {
+          const int ix = ct.idx[r];
+          const double dv = ix == 0 ? d0 : (ix == 1 ? d1 : (ix == 2 ? d2 : (ix == 3 ? d3 : (ix == 4 ? d4 : d5))));
+          jac_out[r * p.cart_stride + (col - 1)] = dv / 1e-5 * ct.coeff[r];
+        }
       }
     }
 
@@ -418,7 +426,6 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
     const double* obst = sm + S.obst;
     double* rows_out = p.coll_rows + slot * static_cast<size_t>(p.n_coll_cand) * p.coll_stride;
     const float inv_O = 1.0f / static_cast<float>(O);
-    int tile_sel = 0;
     for (;;) {
       int k = 0;
       if (lane_c == 0) k = atomicAdd(&misc[2], 1);  // next collision object: warps take them as they get free
@@ -430,12 +437,8 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
       double vsum = 0.0;  // exact value of the object: its terms added in candidate order (warp-uniform)
       if (co.kind == OBJ_COLL) {
         const double* AB = sm + S.jax + t * D * 6;
-        // this warp's two staging tiles (the FK frames are dead by now): a chunk is staged in one while the bulk store of
-        // the previous chunk still reads the other
-        double* const stage0 = sm + S.fr + (tid >> 5) * (2 * 32 * (D + 3));
+        double* const stage = sm + S.fr + (tid >> 5) * (32 * (D + 3));  // this warp's staging tile (the FK frames are dead by now)
         for (int c0 = 0; c0 < LO; c0 += 32) {
-          double* stage = stage0 + (tile_sel ? 32 * (D + 3) : 0);
-          tile_sel ^= 1;
           const int cnd = c0 + lane_c;
           const bool in = cnd < LO;
           const int sl = in ? static_cast<int>((static_cast<float>(cnd) + 0.5f) * inv_O) : 0, o = in ? cnd - sl * O : 0;
@@ -471,27 +474,28 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
           row[D + 2] = active ? coeff : 0.0;
           if constexpr (((D + 3) & 1) == 0) {
             // rows are 16-byte aligned (D + 3 even, 256-byte aligned buffers): the 32 rows of the chunk are staged in
-            // shared memory and leave as ONE asynchronous bulk store (cp.async.bulk, 2.5 KB contiguous in HBM).
-            // Measured (scripts/probes/store_probe.cu): lane-per-row 16-byte stores reach 2.7 TB/s, this 5.2 TB/s.
-            // the store issued from this tile two chunks ago has read it (at most one group, the last one, is pending)
-            if (lane_c == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncwarp();
+            // shared memory and leave as warp-contiguous 16-byte stores (512 contiguous bytes per store instruction,
+            // 2.5 KB contiguous per chunk).  (A cp.async.bulk store of the tile moves the same bytes, but the tile can
+            // only be refilled once the bulk engine has read it — microseconds with 24 warps per SM queueing their
+            // stores — and the row phase of a CTA took 32k cycles; plain stores are fire and forget.)
             if (in) {
               double2* d2 = reinterpret_cast<double2*>(stage + lane_c * (D + 3));
 #pragma unroll
               for (int i = 0; i < (D + 3) / 2; ++i) d2[i] = make_double2(row[2 * i], row[2 * i + 1]);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane_c == 0) {
+            {
               const int nrows = (LO - c0 < 32) ? LO - c0 : 32;
-              const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(stage));
-              double* dstp = rows_out + static_cast<size_t>(co.src_off + c0) * (D + 3);
-              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstp), "r"(saddr),
-                           "r"(nrows * (D + 3) * 8)
-                           : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              const double2* src2 = reinterpret_cast<const double2*>(stage);
+              double2* dst2 = reinterpret_cast<double2*>(rows_out + static_cast<size_t>(co.src_off + c0) * (D + 3));
+              const int n2 = nrows * ((D + 3) / 2);
+#pragma unroll
+              for (int i = 0; i < (D + 3) / 2; ++i) {
+                const int e = i * 32 + lane_c;
+                if (e < n2) dst2[e] = src2[e];
+              }
             }
+            __syncwarp();  // the tile may be refilled
           } else if (in) {
             double* dstp = rows_out + static_cast<size_t>(co.src_off + cnd) * (D + 3);
 #pragma unroll
@@ -688,7 +692,6 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
       }
       if (lane_c == 0) sm[S.objv + k] = vsum;
     }
-    if (lane_c == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's row stores have landed
     __syncthreads();
     EVAL_PROF(5);
     for (int i = tid; i < n_mask_words; i += kEvalThreads) p.coll_mask[slot * n_mask_words + i] = mask[i];
@@ -905,14 +908,23 @@ __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex,
   }
 }
 
+// The evaluation step as a function of its own (the persistent SQP kernel calls it beside its QP step; the stand-alone
+// kernel below inlines the implementation).
+template <int DD>
+__device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex, const int mode, const int b,
+                                       const double* x_in /*EVAL_ONLY*/) {
+  eval_step_impl<DD>(p, ex, mode, b, x_in);
+}
+
 #ifndef TB200_EVAL_MIN_BLOCKS
-#define TB200_EVAL_MIN_BLOCKS 3
+#define TB200_EVAL_MIN_BLOCKS 2
 #endif
 // Stand-alone launch, one CTA per trajectory: the initial evaluation of a solve (EVAL_INIT) and the kernel-level
 // convexify entry point (EVAL_ONLY).  Inside a solve the same code runs as a step of solve_kernel.cuh.
 template <int DD>
 __global__ void __launch_bounds__(kEvalThreads, (DD <= 8) ? TB200_EVAL_MIN_BLOCKS : 2)
-eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double* x_in /*EVAL_ONLY*/) {
+eval_convexify_decide_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ EvalExtra ex, int mode,
+                             const double* x_in /*EVAL_ONLY*/) {
   // persistent CTAs: the grid fills the SMs once and every CTA takes the next trajectory when it is done with one
   // (1024 trajectories over 148 SMs x 3-4 resident CTAs: no tail wave of half-empty SMs)
   __shared__ int s_next;
@@ -922,7 +934,7 @@ eval_convexify_decide_kernel(DevProblem p, EvalExtra ex, int mode, const double*
     const int b = s_next;
     __syncthreads();
     if (b >= p.B) return;
-    eval_step<DD>(p, ex, mode, b, x_in);
+    eval_step_impl<DD>(p, ex, mode, b, x_in);
     __syncthreads();
   }
 }

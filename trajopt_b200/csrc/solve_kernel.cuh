@@ -85,7 +85,8 @@ __device__ inline int claim_trajectory(const DevProblem& p, int* state, int tid)
 }
 
 template <int DD, int PAIR>
-__global__ void __launch_bounds__(kQpThreads, 1) solve_kernel(DevProblem p, EvalExtra ex, SolveCtl ctl) {
+__global__ void __launch_bounds__(kQpThreads, 1)
+solve_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ EvalExtra ex, const __grid_constant__ SolveCtl ctl) {
   const int tid = threadIdx.x;
   const bool qp_only = ctl.mode == SOLVE_QP_ONLY;  // kernel-level entry point: grid = B, one QP step each, no scheduler
   for (bool first = true;; first = false) {
