@@ -280,6 +280,34 @@ int tb200_qp_solve_batch(tb200_problem* p, const double* x, const double* trust,
                          double* new_x, int32_t* qp_status, double* model_cost_vals, double* model_cnt_viols,
                          int32_t* admm_iters);
 
+/* ---- general QP (the sco::Model plugin surface, include/trajopt_b200_sco.hpp) ----------------------------
+ * OSQP's canonical form as OSQPModel builds it (trajopt_sco/src/osqp_interface.cpp:170-281):
+ *     min 1/2 x'Px + q'x   s.t.  l <= A x <= u        (variable bounds are identity rows of A)
+ * with dense, row-major inputs; `batch` problems of the same size back to back.  Replaces
+ * OSQPModel::optimize() -> osqp_setup / osqp_solve (osqp_interface.cpp:283-370, 440-615) for one
+ * sco::Model::optimize() call at a time; the batched trajectory path does not go through it. */
+typedef struct tb200_qp_general {
+  int32_t n;                /* variables */
+  int32_t m;                /* rows of A */
+  int32_t batch;            /* problems (>= 1) */
+  int32_t reserved;
+  const double* P;          /* [batch][n][n] symmetric; the upper triangle is read */
+  const double* q;          /* [batch][n] */
+  const double* A;          /* [batch][m][n] */
+  const double* l;          /* [batch][m]  (<= -1e30: none) */
+  const double* u;          /* [batch][m]  (>=  1e30: none) */
+} tb200_qp_general;
+/* OSQP status values (osqp_api_constants.h): 1 solved, 2 solved inaccurate, 3/4 primal infeasible (/inaccurate),
+ * 5/6 dual infeasible (/inaccurate), 7 max iterations, 8 non convex */
+int tb200_qp_solve_general(const tb200_qp_general* qp, const tb200_qp_settings* settings /* NULL: defaults */, int device,
+                           double* x /* [batch][n] */, double* y /* [batch][m] or NULL */, int32_t* status /* [batch] */,
+                           int32_t* iters /* [batch] or NULL */, int32_t* polish /* [batch] or NULL */);
+const char* tb200_qp_general_last_error(void);
+
+/* OSQP's own order of operations: the polish runs only after ADMM has met its tolerances
+ * (tb200_default_qp_settings also tries the VERIFIED polish early, DESIGN.md optimisation O1). */
+void tb200_osqp_order_qp_settings(tb200_qp_settings* s);
+
 /* Polish outcome (1 accepted, -1 rejected, 0 not attempted) of the last tb200_qp_solve_batch call, [B]. */
 int tb200_last_qp_polish(tb200_problem* p, int32_t* polish);
 

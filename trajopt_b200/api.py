@@ -129,3 +129,26 @@ def solve(desc, device=0):
         return p.solve()
     finally:
         p.close()
+
+
+def qp_solve_general(P, q, A, l, u, settings=None, device=0):
+    """One sco::Model::optimize() worth of QP on the GPU: min 1/2 x'Px + q'x s.t. l <= Ax <= u (dense inputs; a leading
+    batch dimension is allowed).  Returns dict(x, y, status, iters, polish) with OSQP's status values."""
+    lib = capi.load_library()
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    batched = P.ndim == 3
+    if not batched:
+        P, q, A, l, u = (np.asarray(a, dtype=np.float64)[None] for a in (P, q, A, l, u))
+    P, q, A, l, u = (np.ascontiguousarray(a, dtype=np.float64) for a in (P, q, A, l, u))
+    B, n = q.shape
+    m = l.shape[1]
+    g = capi.QpGeneral(n, m, B, 0, _dp(P), _dp(q), _dp(A) if m else None, _dp(l) if m else None, _dp(u) if m else None)
+    x, y = np.zeros((B, n)), np.zeros((B, max(m, 1)))
+    status, iters, polish = np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
+    rc = lib.tb200_qp_solve_general(C.byref(g), C.byref(settings) if settings is not None else None, device, _dp(x), _dp(y),
+                                    _ip(status), _ip(iters), _ip(polish))
+    if rc != 0:
+        lib.tb200_qp_general_last_error.restype = C.c_char_p
+        raise RuntimeError(f"tb200_qp_solve_general failed ({rc}): {lib.tb200_qp_general_last_error().decode()}")
+    out = dict(x=x, y=y[:, :m], status=status, iters=iters, polish=polish)
+    return out if batched else {k: v[0] for k, v in out.items()}

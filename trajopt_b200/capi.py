@@ -80,6 +80,12 @@ class ProblemDescC(C.Structure):
                 ("obstacles_per_traj", C.c_int32), ("obstacles", _dbl_p), ("sqp", SqpParams), ("qp", QpSettings)]
 
 
+class QpGeneral(C.Structure):
+    """tb200_qp_general: dense QP(s) in OSQP's canonical form (include/trajopt_b200.h)."""
+    _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("batch", C.c_int32), ("reserved", C.c_int32), ("P", _dbl_p),
+                ("q", _dbl_p), ("A", _dbl_p), ("l", _dbl_p), ("u", _dbl_p)]
+
+
 class Results(C.Structure):
     _fields_ = [("x", _dbl_p), ("status", _i32_p), ("total_cost", _dbl_p), ("cost_vals", _dbl_p),
                 ("cnt_viols", _dbl_p), ("n_qp_solves", _i32_p), ("n_func_evals", _i32_p), ("n_admm_iters", _i32_p)]
@@ -263,4 +269,5 @@ EXPORTED_SYMBOLS = [
     "tb200_problem_create", "tb200_problem_destroy", "tb200_problem_layout", "tb200_problem_set_inputs",
     "tb200_solve_batch", "tb200_solve_batch_resident", "tb200_fetch_results", "tb200_convexify_batch",
     "tb200_qp_solve_batch", "tb200_last_qp_polish", "tb200_last_timing",
+    "tb200_qp_solve_general", "tb200_qp_general_last_error", "tb200_osqp_order_qp_settings",
 ]
