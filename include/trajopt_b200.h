@@ -21,6 +21,8 @@
 #ifndef TRAJOPT_B200_H
 #define TRAJOPT_B200_H
 
+#include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -31,12 +33,8 @@ extern "C" {
 #define TB200_VERSION_MINOR 1
 #define TB200_MAX_DOF 16      /* joints per manipulator group (7 single arm, 14 dual arm) */
 #define TB200_MAX_STEPS 64    /* waypoints per trajectory */
-#define TB200_CAST_ROWS_PER_PAIR 128 /* continuous collision evaluators: active contacts (rows) one step pair can hold.
-                                        The LVS sub-trajectory itself is as long as the reference's (ceil(dist/lvs)
-                                        sub-segments, collision_terms.cpp:1118-1155, unbounded); only contacts inside
-                                        margin + buffer take a row.  A step pair with more active contacts is never
-                                        truncated: its trajectory ends OPT_FAILED and the solve returns
-                                        TB200_ERR_UNSUPPORTED. */
+#define TB200_MIN_CAST_ROWS_PER_PAIR 128  /* continuous collision evaluators: lower / upper limit of the active contacts */
+#define TB200_MAX_CAST_ROWS_PER_PAIR 4096 /* (rows) one step pair can hold; see tb200inl_cast_rows_per_pair */
 
 /* ---- return codes ------------------------------------------------------- */
 enum {
@@ -240,6 +238,42 @@ typedef struct tb200_layout {
   int32_t reserved;
 } tb200_layout;
 
+/* Rows (active contacts) one step pair of a continuous collision term can hold.  The LVS sub-trajectory itself is as
+ * long as the reference's (ceil(dist / lvs) sub-segments, collision_terms.cpp:1118-1155, unbounded) and only contacts
+ * inside margin + buffer take a row, but the row block of a pair has a fixed size: room for EVERY candidate (robot
+ * sphere x obstacle x sub-segment) of the longest step pair of the description's initial trajectories, rounded up to 64,
+ * within [TB200_MIN_CAST_ROWS_PER_PAIR, TB200_MAX_CAST_ROWS_PER_PAIR].  (The reference's JSON default of
+ * collision_margin_buffer is 0.5 m: nearly every candidate near an obstacle is an active contact then.)  A step pair that
+ * comes to hold more during a solve is never truncated: its trajectory ends OPT_FAILED and the solve returns
+ * TB200_ERR_UNSUPPORTED.  The CPU oracle sizes its row output with the same function. */
+static inline int tb200inl_cast_rows_per_pair(const tb200_problem_desc* d) {
+  const int T = d->n_steps, D = d->robot.n_dof;
+  double need = 1.0;
+  for (int k = 0; k < d->n_terms; ++k) {
+    const tb200_term* tm = d->terms + k;
+    if (tm->kind != TB200_TERM_COLLISION || tm->evaluator_type != TB200_COLL_LVS_CONTINUOUS) continue;
+    if (!(tm->longest_valid_segment_length > 0.0)) continue;
+    for (int b = 0; b < d->batch; ++b)
+      for (int t = tm->first_step < 0 ? 0 : tm->first_step; t < tm->last_step && t + 1 < T; ++t) {
+        const double* q0 = d->init_traj + ((size_t)b * T + t) * D;
+        double s = 0.0;
+        for (int j = 0; j < D; ++j) s += (q0[D + j] - q0[j]) * (q0[D + j] - q0[j]);
+        s = sqrt(s);
+        if (s > tm->longest_valid_segment_length) {
+          const double n = ceil(s / tm->longest_valid_segment_length);
+          if (n > need) need = n;
+        }
+      }
+  }
+  {
+    double cand = need * (double)d->robot.n_spheres * (double)d->n_obstacles;
+    cand = ceil(cand / 64.0) * 64.0;
+    if (cand < TB200_MIN_CAST_ROWS_PER_PAIR) cand = TB200_MIN_CAST_ROWS_PER_PAIR;
+    if (cand > TB200_MAX_CAST_ROWS_PER_PAIR) cand = TB200_MAX_CAST_ROWS_PER_PAIR;
+    return (int)cand;
+  }
+}
+
 typedef struct tb200_problem tb200_problem; /* opaque handle; not thread-safe */
 
 const char* tb200_version(void);
@@ -253,6 +287,10 @@ void tb200_default_qp_settings(tb200_qp_settings* s);
 int tb200_problem_create(const tb200_problem_desc* desc, int device, tb200_problem** out);
 void tb200_problem_destroy(tb200_problem* p);
 int tb200_problem_layout(const tb200_problem* p, tb200_layout* out);
+
+/* Replace the optimizer parameters of an existing problem (what `opt.getParameters() = ...` does on a
+ * sco::BasicTrustRegionSQP, optimizers.hpp:92-135, 365-366).  Takes effect at the next solve. */
+int tb200_problem_set_sqp_params(tb200_problem* p, const tb200_sqp_params* params);
 
 /* Replace the per-trajectory inputs without rebuilding (same shapes). Host pointers. */
 int tb200_problem_set_inputs(tb200_problem* p, const double* init_traj, const double* cart_targets,

@@ -376,6 +376,12 @@ inline std::shared_ptr<FlatProblem> FlattenProblem(const ProblemConstructionInfo
   }
   fp->terms = flat.terms;
   fp->cart_targets = flat.cart_targets;
+  {
+    const size_t want = static_cast<size_t>(pci.obstacles_per_problem ? B : 1) * static_cast<size_t>(pci.n_obstacles) * 4;
+    if (pci.obstacles.size() != want)
+      throw std::runtime_error("obstacles has " + std::to_string(pci.obstacles.size()) + " values, expected " + std::to_string(want) +
+                               " ([B or 1][n_obstacles][4])");
+  }
   fp->obstacles = pci.obstacles;
   fp->fixed_timesteps.assign(pci.basic_info.fixed_timesteps.begin(), pci.basic_info.fixed_timesteps.end());
   fp->fixed_dofs.assign(pci.basic_info.fixed_dofs.begin(), pci.basic_info.fixed_dofs.end());
@@ -435,6 +441,7 @@ public:
   int GetNumDOF() const { return flat_->desc.robot.n_dof; }
   int GetBatch() const { return flat_->desc.batch; }
   const DblVec& GetInitTraj() const { return flat_->init_traj; }
+  const tb200_sqp_params& sqpParams() const { return flat_->desc.sqp; }  // = pci.opt_info
   int getNumCosts() const { return layout_.n_costs; }
   int getNumConstraints() const { return layout_.n_cnts; }
   tb200_problem* handle() const { return handle_; }
@@ -450,9 +457,11 @@ inline TrajOptProb::Ptr ConstructProblem(const ProblemConstructionInfo& pci, int
   return std::make_shared<TrajOptProb>(FlattenProblem(pci), device);
 }
 
-// BasicTrustRegionSQP::optimize() for every problem of the batch (optimizers.cpp:699-991): what
-// `sco::BasicTrustRegionSQP opt(prob); opt.initialize(...); opt.optimize(); opt.results()` returns, per problem.
-inline std::vector<sco::OptResults> OptimizeProblem(TrajOptProb& prob) {
+// BasicTrustRegionSQP::optimize() for every problem of the batch (optimizers.cpp:699-991) with the given parameters: what
+// `sco::BasicTrustRegionSQP opt(prob); opt.getParameters() = params; opt.initialize(...); opt.optimize(); opt.results()`
+// returns, per problem.
+inline std::vector<sco::OptResults> OptimizeWithParams(TrajOptProb& prob, const tb200_sqp_params& params) {
+  if (tb200_problem_set_sqp_params(prob.handle(), &params) != TB200_OK) throw std::runtime_error(tb200_last_error());
   const size_t B = prob.GetBatch(), N = static_cast<size_t>(prob.GetNumSteps()) * prob.GetNumDOF();
   const size_t nc = prob.getNumCosts(), nk = prob.getNumConstraints();
   DblVec x(B * N), total(B), cv(B * (nc ? nc : 1)), kv(B * (nk ? nk : 1));
@@ -473,6 +482,23 @@ inline std::vector<sco::OptResults> OptimizeProblem(TrajOptProb& prob) {
     out[b].n_func_evals = nfe[b];
   }
   return out;
+}
+// ... with the problem description's own parameters (pci.opt_info)
+inline std::vector<sco::OptResults> OptimizeWithParams(TrajOptProb& prob) { return OptimizeWithParams(prob, prob.sqpParams()); }
+
+// trajopt::OptimizeProblem(prob) (problem_description.hpp:665, problem_description.cpp:392-408).  The reference's function
+// does NOT run with pci.opt_info: it builds a fresh BasicTrustRegionSQP and overrides four parameters (max_iter 40,
+// min_approx_improve_frac 1e-3, improve_ratio_threshold 0.2, initial_merit_error_coeff 20) on top of the optimizer's
+// DEFAULTS.  Reproduced here, so that the same description gives the same iterates; OptimizeWithParams is the entry point
+// that honours pci.opt_info.
+inline std::vector<sco::OptResults> OptimizeProblem(TrajOptProb& prob) {
+  tb200_sqp_params p;
+  tb200_default_sqp_params(&p);
+  p.max_iter = 40;
+  p.min_approx_improve_frac = .001;
+  p.improve_ratio_threshold = .2;
+  p.initial_merit_error_coeff = 20;
+  return OptimizeWithParams(prob, p);
 }
 
 }  // namespace trajopt

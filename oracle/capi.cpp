@@ -32,7 +32,7 @@ Layout layoutOf(const tb200_problem_desc& d, const TrajProblem& tp) {
       has_vel = true;
     } else if (t.kind == TB200_TERM_COLLISION) {
       if (t.evaluator_type != TB200_COLL_DISCRETE) {  // one object per step pair, dense over sub-segments
-        L.n_coll_cand += (t.last_step - t.first_step) * TB200_CAST_ROWS_PER_PAIR;
+        L.n_coll_cand += (t.last_step - t.first_step) * tb200inl_cast_rows_per_pair(&d);
         has_cast = true;
         continue;
       }
@@ -79,6 +79,7 @@ int oracle_solve_batch(const tb200_problem_desc* desc, int b0, int b1, int n_thr
                        double* seconds, int trace_b, double* trace_out, int trace_cap, int* trace_len) {
   const int T = desc->n_steps, D = desc->robot.n_dof;
   int err = 0;
+  const int cast_cap = tb200inl_cast_rows_per_pair(desc);
   const auto t0 = std::chrono::steady_clock::now();
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);
@@ -86,7 +87,7 @@ int oracle_solve_batch(const tb200_problem_desc* desc, int b0, int b1, int n_thr
 #pragma omp parallel for schedule(dynamic)
   for (int b = b0; b < b1; ++b) {
     try {
-      TrajProblem tp = buildProblem(*desc, b);
+      TrajProblem tp = buildProblem(*desc, b, cast_cap);
       BasicTrustRegionSQP opt(tp.prob);
       opt.params() = sqpParamsFrom(desc->sqp);
       opt.initialize(tp.init);
@@ -131,9 +132,10 @@ int oracle_solve_batch(const tb200_problem_desc* desc, int b0, int b1, int n_thr
 // fixed dense layout of tb200_convexify_out.
 int oracle_convexify_batch(const tb200_problem_desc* desc, int b0, int b1, const double* x, tb200_convexify_out* out) {
   const int T = desc->n_steps, D = desc->robot.n_dof;
+  const int cast_cap = tb200inl_cast_rows_per_pair(desc);
   try {
     for (int b = b0; b < b1; ++b) {
-      TrajProblem tp = buildProblem(*desc, b);
+      TrajProblem tp = buildProblem(*desc, b, cast_cap);
       const Layout L = layoutOf(*desc, tp);
       Vec xv(x + static_cast<size_t>(b) * T * D, x + static_cast<size_t>(b + 1) * T * D);
       if (out->cart_err || out->cart_jac) {
@@ -178,9 +180,10 @@ int oracle_qp_solve_batch(const tb200_problem_desc* desc, int b0, int b1, const 
                           double* model_cnt_viols, int32_t* admm_iters, double* kkt /*[B][3]*/,
                           int32_t* polish /*[B]*/) {
   const int T = desc->n_steps, D = desc->robot.n_dof, N = T * D;
+  const int cast_cap = tb200inl_cast_rows_per_pair(desc);
   try {
     for (int b = b0; b < b1; ++b) {
-      TrajProblem tp = buildProblem(*desc, b);
+      TrajProblem tp = buildProblem(*desc, b, cast_cap);
       Model* model = tp.prob->model();
       const auto& costs = tp.prob->getCosts();
       const auto cnts = tp.prob->getConstraints();

@@ -425,7 +425,7 @@ struct CollisionEval {
 //     interpolated joint states (the reference's LinSpaced sub-trajectory, :1118-1155), unbounded as in the
 //     reference.  The fixed-layout row output (denseRows, what the CUDA path is compared in) is the step pair's
 //     ACTIVE contacts in canonical order (sphere, obstacle, sub-segment) followed by zero rows up to
-//     TB200_CAST_ROWS_PER_PAIR.
+//     the pair's row block (tb200inl_cast_rows_per_pair).
 //     CONTINUOUS (evaluator 3) never subdivides (lvs = max double, problem_description.cpp:1782-1784).
 //   * cc_time of a contact in sub-segment i of n: (i + s)/n  (addInterpolatedCollisionResults [EXT]);
 //     type Time0 iff i == 0 and s == 0, Time1 iff i == n-1 and s == 1, else Between.
@@ -447,6 +447,7 @@ struct CastCollisionEval {
   int t, D;
   double margin, coeff, buffer, lvs;
   bool start_fixed, end_fixed;
+  int row_cap;  // rows of a step pair in the fixed-layout output (tb200inl_cast_rows_per_pair)
 
   int subSegments(const double* q0, const double* q1) const {
     double d2 = 0;
@@ -565,7 +566,7 @@ struct CastCollisionEval {
     int n_act = 0;
     for (const Cand& cd : cands) {
       if (!cd.exists || !cd.active) continue;
-      if (++n_act > TB200_CAST_ROWS_PER_PAIR) throw std::runtime_error("oracle: more active contacts in a step pair than TB200_CAST_ROWS_PER_PAIR");
+      if (++n_act > row_cap) throw std::runtime_error("oracle: more active contacts in a step pair than its row block holds");
       Vec row(2 * D + 3, 0.0);
       for (int j = 0; j < D; ++j) {
         row[j] = cd.ct.g0[j];
@@ -576,7 +577,7 @@ struct CastCollisionEval {
       row[2 * D + 2] = coeff;
       rows.push_back(row);
     }
-    for (; n_act < TB200_CAST_ROWS_PER_PAIR; ++n_act) rows.push_back(Vec(2 * D + 3, 0.0));
+    for (; n_act < row_cap; ++n_act) rows.push_back(Vec(2 * D + 3, 0.0));
   }
   Vec values(const Vec& x) const {
     std::vector<Cand> cands;
@@ -679,7 +680,8 @@ QPSettings qpSettingsFrom(const tb200_qp_settings& q) {
   return s;
 }
 
-TrajProblem buildProblem(const tb200_problem_desc& desc, int b) {
+TrajProblem buildProblem(const tb200_problem_desc& desc, int b, int cast_cap) {
+  if (cast_cap < 0) cast_cap = tb200inl_cast_rows_per_pair(&desc);
   TrajProblem tp;
   tp.robot = std::make_shared<Robot>(desc.robot);
   const int T = desc.n_steps, D = desc.robot.n_dof;
@@ -897,7 +899,7 @@ TrajProblem buildProblem(const tb200_problem_desc& desc, int b) {
             }
             // (two adjacent fixed steps fall into the START_FIXED_END_FREE branch: the reference's throw is unreachable)
             CastCollisionEval e{tp.robot, obstacles, t, D, tm.margin, tm.coeff, tm.margin_buffer, lvs, cur_fixed,
-                                !cur_fixed && next_fixed};
+                                !cur_fixed && next_fixed, cast_cap};
             tp.coll_hooks.push_back([e](const Vec& x, std::vector<Vec>& rows) { e.denseRows(x, rows); });
             if (is_cost) {
               auto c = std::make_shared<CollisionCost>(calcOf(e));

@@ -61,7 +61,9 @@ struct TrajProblem {
 };
 // One trajectory `b` of the batched description -> the reference's TrajOptProb
 // (ConstructProblem, problem_description.cpp:410-542).
-TrajProblem buildProblem(const tb200_problem_desc& desc, int b);
+// cast_cap: rows per step pair of the continuous collision evaluator's fixed-layout output (< 0: compute it,
+// tb200inl_cast_rows_per_pair)
+TrajProblem buildProblem(const tb200_problem_desc& desc, int b, int cast_cap = -1);
 SQPParams sqpParamsFrom(const tb200_sqp_params& p);
 QPSettings qpSettingsFrom(const tb200_qp_settings& s);
 

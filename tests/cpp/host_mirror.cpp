@@ -124,7 +124,9 @@ int main(int argc, char** argv) {
       return 0;
     }
     TrajOptProb::Ptr prob = ConstructProblem(pci);
-    std::vector<tb::sco::OptResults> res = OptimizeProblem(*prob);
+    // "solve": with the description's own parameters (pci.opt_info); "solve_ref": trajopt::OptimizeProblem, which
+    // overrides four of them on top of the optimizer's defaults (problem_description.cpp:394-408)
+    std::vector<tb::sco::OptResults> res = (mode == "solve_ref") ? OptimizeProblem(*prob) : OptimizeWithParams(*prob);
     for (const auto& r : res) {
       std::printf("result %d %.17g %d %d", static_cast<int>(r.status), r.total_cost, r.n_qp_solves, r.n_func_evals);
       for (double v : r.x) std::printf(" %.17g", v);

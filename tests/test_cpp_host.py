@@ -172,9 +172,17 @@ def test_json_front_end_rejects_what_the_reference_rejects(host_bin, tmp_path, b
 
 
 @pytest.mark.gpu
-def test_cpp_host_solves_like_the_python_path(host_bin, tmp_path):
+@pytest.mark.parametrize("mode", ["solve", "solve_ref"])
+def test_cpp_host_solves_like_the_python_path(host_bin, tmp_path, mode):
+    """OptimizeWithParams runs with pci.opt_info; OptimizeProblem reproduces the reference's hard-coded overrides
+    (max_iter 40, min_approx_improve_frac 1e-3, improve_ratio_threshold 0.2, initial_merit_error_coeff 20 on top of the
+    optimizer defaults, problem_description.cpp:394-408)."""
     d, path = _case(tmp_path)
-    out = subprocess.run([host_bin, path, "solve"], check=True, capture_output=True, text=True).stdout.splitlines()
+    out = subprocess.run([host_bin, path, mode], check=True, capture_output=True, text=True).stdout.splitlines()
+    if mode == "solve_ref":
+        d.c.sqp = capi.default_sqp_params()
+        d.c.sqp.max_iter, d.c.sqp.min_approx_improve_frac = 40, 1e-3
+        d.c.sqp.improve_ratio_threshold, d.c.sqp.initial_merit_error_coeff = 0.2, 20.0
     ref = api.solve(d)
     assert len(out) == d.B
     for b, line in enumerate(out):

@@ -310,7 +310,12 @@ def _cast_problem(lvs, T=6, B=3, seed=5):
     return problems.config3(B=B, T=T, seed=seed, via_every=2, lvs=lvs)
 
 
-CAST_CAP = 128  # TB200_CAST_ROWS_PER_PAIR (include/trajopt_b200.h)
+def _cast_cap(d, lvs, L=7, O=8):
+    """tb200inl_cast_rows_per_pair (include/trajopt_b200.h): rows of a step pair = every candidate of the longest step
+    pair of the initial trajectories, rounded up to 64, within [128, 4096]."""
+    step = np.linalg.norm(np.diff(d.init_traj, axis=1), axis=2)
+    need = max(1.0, np.ceil(step[step > lvs] / lvs).max(initial=1.0))
+    return int(min(4096, max(128, np.ceil(need * L * O / 64.0) * 64)))
 
 
 def test_cast_collision_layout_and_activity(oracle):
@@ -319,6 +324,8 @@ def test_cast_collision_layout_and_activity(oracle):
     lvs = 0.05
     d = _cast_problem(lvs)
     L = oracle.layout(d)
+    CAST_CAP = _cast_cap(d, lvs)
+    assert CAST_CAP > 128
     assert L.coll_row_stride == 2 * d.D + 3 and L.cart_jac_stride == 2 * d.D
     assert L.n_coll_cand == (d.T - 1) * CAST_CAP
     x = d.init_traj + 0.02 * np.random.default_rng(3).standard_normal(d.init_traj.shape)
@@ -357,6 +364,7 @@ def test_cast_collision_gradient_is_a_distance_derivative(oracle):
         obst[b, 0, :3] = c + np.array([0.0, 0.0, 0.10 + robot["spheres"][5].radius + 0.015])
     d2 = capi.ProblemDesc(d.robot_spec, d.T, d.terms, x, fixed_timesteps=[0], cart_targets=d.cart_targets, obstacles=obst)
     r = oracle.convexify_batch(d2, x)
+    CAST_CAP = _cast_cap(d2, 10.0)
     rows = r["coll_rows"].reshape(d.B, d.T - 1, CAST_CAP, 2 * d.D + 3)
     act = np.nonzero(rows[0, 1, :, -1] != 0)[0]
     assert len(act) >= 1, "pair (1,2) must hold the contact of sphere 5 against obstacle 0"

@@ -269,5 +269,5 @@ EXPORTED_SYMBOLS = [
     "tb200_problem_create", "tb200_problem_destroy", "tb200_problem_layout", "tb200_problem_set_inputs",
     "tb200_solve_batch", "tb200_solve_batch_resident", "tb200_fetch_results", "tb200_convexify_batch",
     "tb200_qp_solve_batch", "tb200_last_qp_polish", "tb200_last_timing",
-    "tb200_qp_solve_general", "tb200_qp_general_last_error", "tb200_osqp_order_qp_settings",
+    "tb200_qp_solve_general", "tb200_qp_general_last_error", "tb200_osqp_order_qp_settings", "tb200_problem_set_sqp_params",
 ]

@@ -50,9 +50,10 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   s.misc = o;   o += 8;
   o += o & 1;
   // per-warp scratch of the cast collision objects: one set of frames, the sphere centres at the two ends of the
-  // running sub-segment, one joint vector, and the contacts found so far: (s, dist) + key + rank per contact and
-  // their values in canonical order
-  s.wscr_stride = cast ? (S * 12 + 2 * L * 3 + (L & 1) + ((D + 1) & ~1) + 4 * cast_cap) : 0;
+  // running sub-segment, one joint vector (the contacts found so far live in a per-warp block of global memory:
+  // EvalExtra::cast_scratch)
+  (void)cast_cap;
+  s.wscr_stride = cast ? (S * 12 + 2 * L * 3 + (L & 1) + ((D + 1) & ~1)) : 0;
   s.wscr = o;   o += 8 * s.wscr_stride;
   s.cfk = o;    o += 8 * (1 + D) * kFrameStride;    // running frames of the CartPose chain FK: one per lane and warp
   o += o & 1;
@@ -74,6 +75,7 @@ struct EvalExtra {
   int n_cart_objs, n_coll_objs, n_joint_objs, n_vel_objs;
   int cast, cast_cap;                // cast: the collision objects are step pairs (continuous evaluator), each with room
                                      // for cast_cap active contacts (rows)
+  double* cast_scratch;              // [gridDim * 8 warps][4 * cast_cap]: per contact (s, dist), key + rank, value in canonical order
   int* work_counter;                 // stand-alone launches: next trajectory to take (reset to 0 before every launch)
   const int* link_chain;             // [S][kMaxSeg + 1]: per segment, the number of segments on its chain from the root,
                                      // then the chain itself (root first, the segment last)
@@ -539,10 +541,11 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
         double* cenA = F + p.S * 12;                            // [L][3] sphere centres at the start of the sub-segment
         double* cenB = cenA + L * 3;                            // ... and at its end
         double* qv = cenB + L * 3 + (L & 1);
-        double* csd = qv + ((D + 1) & ~1);                      // [CAP][2]: contact parameter s, distance
-        int* ckey = reinterpret_cast<int*>(csd + 2 * CAP);      // [CAP] (sphere * O + obstacle) << 15 | sub-segment
-        int* crank = ckey + CAP;                                // [CAP]
-        double* cval = csd + 3 * CAP;                           // [CAP] hinge values in canonical order
+        // the contacts of this pair (written and read by this warp only; volatile: no stale L1 lines, no reordering)
+        volatile double* csd = ex.cast_scratch + (static_cast<size_t>(blockIdx.x) * (kEvalThreads / 32) + (tid >> 5)) * 4 * CAP;  // [CAP][2]: s, distance
+        volatile int* ckey = reinterpret_cast<volatile int*>(csd + 2 * CAP);  // [CAP] (sphere * O + obstacle) << 15 | sub-segment
+        volatile int* crank = ckey + CAP;                                     // [CAP]
+        volatile double* cval = csd + 3 * CAP;                                // [CAP] hinge values in canonical order
         // centres of every sphere at the state `frac` of the way from q0 to q1 (i = 0 / nsub: the waypoints themselves)
         auto centres_at = [&](int i, double* dstc) {
           if (i == 0 || i == nsub) {

@@ -86,14 +86,14 @@ struct tb200_problem {
   DevBuf<DevCartTerm> cart_terms;
   DevBuf<int> fixed_vars;
   DevBuf<double> x, new_x, trust, merit_coeffs, cost_vals, cnt_viols, new_cost_vals, new_cnt_viols, model_cost_vals,
-      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace, factor_g;
+      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace, factor_g, cast_scratch;
   DevBuf<unsigned long long> sched_timers;
   DevBuf<int> sched_state;
   DevBuf<unsigned long long> coll_mask;
   DevBuf<int> status, sqp_iter, merit_round, qp_failures, qp_status, cur_buf, n_qp_solves, n_func_evals, n_admm_iters,
       active_count, row_ints, lists, ws_meta, tmp_iters, tmp_polish, trace_len, qp_done, lvs_overflow, link_chain, work_counter;
   int eval_grid = 1;  // CTAs of a stand-alone evaluation launch: what fits the device at once (persistent CTAs)
-  int cast_cap = TB200_CAST_ROWS_PER_PAIR;  // active contacts (rows) a step pair of the continuous evaluator can hold
+  int cast_cap = TB200_MIN_CAST_ROWS_PER_PAIR;  // active contacts (rows) a step pair of the continuous evaluator can hold
   size_t factor_grid = 0;  // CTAs that own a region of factor_g (0: the factor lives in shared memory)
   std::vector<cudaEvent_t> events;
   ~tb200_problem() {
@@ -105,7 +105,7 @@ struct tb200_problem {
     x.release(); new_x.release(); trust.release(); merit_coeffs.release(); cost_vals.release(); cnt_viols.release();
     new_cost_vals.release(); new_cnt_viols.release(); model_cost_vals.release(); model_cnt_viols.release();
     cart_err.release(); cart_jac.release(); coll_rows.release(); rows.release(); ws_x.release(); ws_yb.release();
-    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); factor_g.release(); lvs_overflow.release(); link_chain.release(); work_counter.release(); qp_done.release(); sched_state.release(); sched_timers.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
+    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); factor_g.release(); cast_scratch.release(); lvs_overflow.release(); link_chain.release(); work_counter.release(); qp_done.release(); sched_state.release(); sched_timers.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
     sqp_iter.release(); merit_round.release(); qp_failures.release(); qp_status.release(); cur_buf.release();
     n_qp_solves.release(); n_func_evals.release(); n_admm_iters.release(); active_count.release(); row_ints.release();
     lists.release(); ws_meta.release(); tmp_iters.release(); tmp_polish.release();
@@ -260,7 +260,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   std::vector<DevCartTerm> cts;
   std::vector<DevObj> costs, eqs, ineqs;
   int n_cart_rows = 0, n_coll_cand = 0, max_rows = 0;
-  const int cast_cap = TB200_CAST_ROWS_PER_PAIR;
+  const int cast_cap = tb200inl_cast_rows_per_pair(d);
+  P->cast_cap = cast_cap;
   std::vector<std::pair<int, int>> cart_ref, coll_ref, vel_ref;  // (list id: 0 cost 1 eq 2 ineq, index)
   bool has_vel = false, has_cast = false, has_discrete = false;
   for (int k = 0; k < d->n_terms; ++k) {
@@ -587,6 +588,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eval_kernel_for(D), kEvalThreads, P->eval_smem));
     P->eval_grid = std::max(1, std::min(B, std::max(1, per_sm) * P->n_sm));
   }
+  // contact lists of the continuous collision evaluator: one per resident warp of the largest launch (4 doubles a contact)
+  ALLOC(cast_scratch, has_cast ? static_cast<size_t>(std::max(P->eval_grid, std::min(B, P->n_sm))) * (kEvalThreads / 32) * 4 * cast_cap : 0);
   // a factor that does not fit shared memory lives in a per-CTA region (the kernel-level QP entry point launches B CTAs)
   P->factor_grid = (factor_global || !qs.factor_smem) ? std::max<size_t>(Bs, static_cast<size_t>(P->n_sm)) : 0;
   ALLOC(factor_g, P->factor_grid * qp_factor_doubles(N, 2 * D));
@@ -625,6 +628,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.factor_g = P->factor_g.p; dp.lvs_overflow = P->lvs_overflow.p; dp.qp_done = P->qp_done.p;
   P->ex.link_chain = P->link_chain.p;
   P->ex.work_counter = P->work_counter.p;
+  P->ex.cast_scratch = P->cast_scratch.p;
   P->ex.cart_objs = P->d_cart_objs.p;
   P->ex.coll_objs = P->d_coll_objs.p;
   P->ex.vel_objs = P->d_vel_objs.p;
@@ -650,6 +654,15 @@ void tb200_problem_destroy(tb200_problem* p) { delete p; }
 int tb200_problem_layout(const tb200_problem* p, tb200_layout* out) {
   if (!p || !out) return fail(TB200_ERR_INVALID, "null argument");
   *out = p->layout;
+  return TB200_OK;
+}
+
+int tb200_problem_set_sqp_params(tb200_problem* P, const tb200_sqp_params* s) {
+  if (!P || !s) return fail(TB200_ERR_INVALID, "null argument");
+  P->dp.sqp = SqpParams{s->improve_ratio_threshold, s->min_trust_box_size, s->min_approx_improve, s->min_approx_improve_frac,
+                        s->trust_shrink_ratio, s->trust_expand_ratio, s->cnt_tolerance, s->max_merit_coeff_increases,
+                        s->merit_coeff_increase_ratio, s->initial_merit_error_coeff, s->trust_box_size, s->max_iter,
+                        s->max_qp_solver_failures, s->inflate_constraints_individually, 0};
   return TB200_OK;
 }
 
@@ -783,8 +796,9 @@ int lvsOverflowError(tb200_problem* P) {
   if (rc != TB200_OK) return rc;
   if (n > 0)
     return fail(TB200_ERR_UNSUPPORTED, std::to_string(n) + " trajectories have a step pair with more than " +
-                                           std::to_string(P->cast_cap) + " active continuous-collision contacts (TB200_CAST_ROWS_PER_PAIR) "
-                                           "or more than 32767 longest-valid-segment sub-segments; they are reported OPT_FAILED");
+                                           std::to_string(P->cast_cap) + " active continuous-collision contacts (the row block of a pair, "
+                                           "tb200inl_cast_rows_per_pair) or more than 32767 longest-valid-segment sub-segments; they are "
+                                           "reported OPT_FAILED");
   return TB200_OK;
 }
 }  // namespace

@@ -86,16 +86,18 @@ def _term(v, role, T, D, link_of, root_frame, targets):
 
 def from_json(doc, robot, start_states, link_names=None, root_frame="base_footprint", obstacles=None):
     """doc: JSON text or parsed dict.  robot: robots.* dict.  start_states: [B][D] (the environment's current joint values
-    of every problem).  link_names: names of the robot's segments (default "link<i>")."""
+    of every problem).  link_names: names of the robot's segments (default: the robot's own "link_names", else "link<i>")."""
     v = json.loads(doc) if isinstance(doc, str) else doc
     start = np.atleast_2d(np.asarray(start_states, float))
     B, D = start.shape
-    names = link_names or [f"link{i}" for i in range(len(robot["segments"]))]
+    names = link_names or robot.get("link_names") or [f"link{i}" for i in range(len(robot["segments"]))]
 
     def link_of(name):
-        if name not in names:
-            raise ValueError(f'link "{name}" is not part of the manipulator model')
-        return names.index(name)
+        if name in names:
+            return names.index(name)
+        if name.startswith("link") and name[4:].isdigit() and int(name[4:]) < len(robot["segments"]):
+            return int(name[4:])  # "link<i>": the i-th segment, whatever the robot calls it
+        raise ValueError(f'link "{name}" is not part of the manipulator model')
 
     basic = _req(v, "basic_info")
     T = _req(basic, "n_steps")
