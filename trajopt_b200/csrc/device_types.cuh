@@ -133,6 +133,8 @@ struct DevProblem {
   double* ws_x;                // [B][N]  warm start: previous QP solution (trajectory part, unscaled)
   double* ws_yb;               // [B][N]  warm start: duals of the variable-bound rows (unscaled)
   double* scratch;             // [B][5*Np]: dx dy stash(x zb yb)
+  double* soa;                 // [grid][soa_stride]: column-major copy of a QP's rows while an ADMM block runs on rows that do
+  size_t soa_stride;           //                     not fit shared memory (qp_soa_doubles)
   double* factor_g;            // [grid][3*M*nb*nb]: per-CTA home of a block-cyclic-reduction factor that does not fit
                                // shared memory (14 joints: blocks of 28); stays L2 resident
   int* lvs_overflow;           // [B] 1: a step pair had more active continuous-collision contacts than its row block holds

@@ -131,6 +131,7 @@ struct QpCtx {
   int* colptr;           // shared [Np+1]
   double *Dz, *v2;       // shared [Np]: variable scalings, scratch of the residual / polish passes
   double* rows;          // shared when the QP has at most row_cap rows, else global
+  double* soa;           // this CTA's block of global memory for the column-major copy of the rows (admm_block_soa)
   double* smbase;        // start of the CTA's dynamic shared memory (generic address), rows_smem: q.rows lives there
   int rows_smem;
   int* rints;
@@ -1397,6 +1398,166 @@ __device__ __noinline__ void admm_block_fast(const QpCtx& q, const double rho_au
   __syncthreads();
 }
 
+// The block of iterations for QPs whose rows do not fit shared memory (configs[3] at 50 waypoints: ~370 rows of 14
+// coefficients; configs[4]).  Their row records live in global memory, 98 doubles apart: a warp that works on 32 rows
+// touches 32 different sectors with every field it loads (4x the bytes it uses), and the right-hand side gathers the rows'
+// contributions through two dependent loads per entry.  So for the duration of a block the fields the loop needs are
+// copied into a COLUMN-MAJOR block of this CTA (field f of row r at soa[f * RSd + r]: a warp's load of a field is one
+// contiguous 256 bytes, all loads of a row independent), the contributions go to ct[e] in column-entry order (the
+// right-hand side of variable i adds ct[colptr[i] .. colptr[i+1]) - contiguous, addresses known up front), and the row
+// state goes back to the records at the end.  Same arithmetic, operation for operation, as admm_block.
+enum SoaF { S_U0 = 0, S_U1, S_B0, S_B1, S_LO, S_UP, S_QA0, S_QA1, S_WRR, S_IWRR, S_G0, S_G1, S_IDEN, S_UPA0, S_UPA1,
+            S_Z, S_Y, S_XA0, S_XA1, S_ZA0, S_ZA1, S_YA0, S_YA1, S_RA0, S_RA1, S_AS };  // S_AS: CN scaled coefficients follow
+__host__ __device__ inline size_t qp_soa_doubles(int max_rows, int CN) {
+  const size_t rsd = (static_cast<size_t>(max_rows) + 31) & ~static_cast<size_t>(31);
+  return rsd * (S_AS + CN) + (rsd * (3 + CN) + 1) / 2 + static_cast<size_t>(max_rows) * CN + 8;
+}
+template <int NB, int PAIR>
+__device__ __noinline__ void admm_block_soa(const QpCtx& q, const double rho_aux_in, const int n_iter, const int keep_last) {
+  constexpr int CNc = PAIR ? ((NB > 3) ? NB : 3) : ((NB / 2 > 3) ? NB / 2 : 3);
+  const int N = q.N, Np = q.Np, tid = q.tid, nrows = q.nrows;
+  const double sigma = q.sigma, alpha = q.alpha, oma = 1.0 - q.alpha, rho = q.rho, rho_eq = q.rho_eq, rho_aux = rho_aux_in;
+  const double inv_rho_aux = 1.0 / rho_aux, inv_rho = 1.0 / rho, inv_rho_eq = 1.0 / rho_eq;
+  double* const dxs = q.scratch;
+  double* const dyb = q.scratch + Np;
+  const int RSd = (nrows + 31) & ~31;
+  double* const sd = q.soa;                                                      // [S_AS + CNc][RSd]
+  int* const si = reinterpret_cast<int*>(sd + static_cast<size_t>(RSd) * (S_AS + CNc));  // [3 + CNc][RSd]: base, stride, last, entry of k
+  double* const ct = sd + static_cast<size_t>(RSd) * (S_AS + CNc) + (static_cast<size_t>(RSd) * (3 + CNc) + 1) / 2 + 1;
+  const int nnz = q.colptr[Np];
+  // ---- entry: entry index of every (row, coefficient); fields of every row; contributions of the current state
+  for (int i = tid; i < N; i += kQpThreads)
+    for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
+      const int ent = q.colent[e];
+      si[(3 + (ent & 31)) * RSd + (ent >> 5)] = e;
+    }
+  for (int e = tid; e < nnz; e += kQpThreads) ct[e] = 0.0;
+  __syncthreads();
+  for (int r = tid; r < nrows; r += kQpThreads) {
+    const double* R = q.R(r);
+    const double* F = q.F(r);
+    const int* I = q.I(r);
+    const int cnt = I[RI_CNT];
+    si[r] = I[RI_BASE];
+    si[RSd + r] = I[RI_STRIDE];
+    si[2 * RSd + r] = cnt - 1;
+    sd[S_U0 * RSd + r] = F[R_U0]; sd[S_U1 * RSd + r] = F[R_U1]; sd[S_B0 * RSd + r] = F[R_B0]; sd[S_B1 * RSd + r] = F[R_B1];
+    sd[S_LO * RSd + r] = F[R_LO]; sd[S_UP * RSd + r] = F[R_UP]; sd[S_QA0 * RSd + r] = F[R_QA0]; sd[S_QA1 * RSd + r] = F[R_QA1];
+    sd[S_WRR * RSd + r] = F[R_WRR]; sd[S_IWRR * RSd + r] = F[R_IWRR]; sd[S_G0 * RSd + r] = F[R_G0]; sd[S_G1 * RSd + r] = F[R_G1];
+    sd[S_IDEN * RSd + r] = F[R_IDEN];
+    sd[S_UPA0 * RSd + r] = kOsqpInf * F[R_EA0]; sd[S_UPA1 * RSd + r] = kOsqpInf * F[R_EA1];
+    sd[S_Z * RSd + r] = F[R_Z]; sd[S_Y * RSd + r] = F[R_Y]; sd[S_XA0 * RSd + r] = F[R_XA0]; sd[S_XA1 * RSd + r] = F[R_XA1];
+    sd[S_ZA0 * RSd + r] = F[R_ZA0]; sd[S_ZA1 * RSd + r] = F[R_ZA1]; sd[S_YA0 * RSd + r] = F[R_YA0]; sd[S_YA1 * RSd + r] = F[R_YA1];
+    const double s0 = F[R_WRR] * F[R_Z] - F[R_Y];
+    const double ra0 = sigma * F[R_XA0] - F[R_QA0] + F[R_U0] * s0 + F[R_B0] * (rho_aux * F[R_ZA0] - F[R_YA0]);
+    const double ra1 = sigma * F[R_XA1] - F[R_QA1] + F[R_U1] * s0 + F[R_B1] * (rho_aux * F[R_ZA1] - F[R_YA1]);
+    sd[S_RA0 * RSd + r] = ra0;
+    sd[S_RA1 * RSd + r] = ra1;
+    const double cf = row_reduce_coef(F, ra0, ra1, s0);
+#pragma unroll
+    for (int k = 0; k < CNc; ++k) {
+      const double a = R[CNc + k];
+      sd[(S_AS + k) * RSd + r] = a;
+      if (k < cnt) ct[si[(3 + k) * RSd + r]] = a * cf;
+    }
+  }
+  __syncthreads();
+  for (int it = 0; it < n_iter; ++it) {
+    const bool keep_steps = keep_last && it == n_iter - 1;
+    // right-hand side  sigma x - q + A'(rho z - y)
+    for (int i = tid; i < Np; i += kQpThreads) {
+      double s = 0.0;
+      if (i < N) {
+        const double rb = (q.ubs[i] - q.lbs[i] < kRhoTol) ? rho_eq : rho;
+        s = sigma * q.x[i] - q.qs[i] + q.beta[i] * (rb * q.zb[i] - q.yb[i]);
+        const int e1 = q.colptr[i + 1];
+        for (int e = q.colptr[i]; e < e1; ++e) s += ct[e];
+      }
+      q.v1[i] = s;
+    }
+    bcr_solve<NB>(q, q.v1, q.w);
+    // rows
+    for (int r = tid; r < nrows; r += kQpThreads) {
+      const int base = si[r], stride = si[RSd + r], last = si[2 * RSd + r];
+      double as[CNc];
+#pragma unroll
+      for (int k = 0; k < CNc; ++k) as[k] = sd[(S_AS + k) * RSd + r];
+      const double U0 = sd[S_U0 * RSd + r], U1 = sd[S_U1 * RSd + r], B0 = sd[S_B0 * RSd + r], B1 = sd[S_B1 * RSd + r];
+      const double LO = sd[S_LO * RSd + r], UP = sd[S_UP * RSd + r], QA0 = sd[S_QA0 * RSd + r], QA1 = sd[S_QA1 * RSd + r];
+      const double Wr = sd[S_WRR * RSd + r], IWRR = sd[S_IWRR * RSd + r], G0 = sd[S_G0 * RSd + r], G1 = sd[S_G1 * RSd + r];
+      const double iden = sd[S_IDEN * RSd + r], UPA0 = sd[S_UPA0 * RSd + r], UPA1 = sd[S_UPA1 * RSd + r];
+      const double Z = sd[S_Z * RSd + r], Y = sd[S_Y * RSd + r], XA0 = sd[S_XA0 * RSd + r], XA1 = sd[S_XA1 * RSd + r];
+      const double ZA0 = sd[S_ZA0 * RSd + r], ZA1 = sd[S_ZA1 * RSd + r], YA0 = sd[S_YA0 * RSd + r], YA1 = sd[S_YA1 * RSd + r];
+      const double ra0o = sd[S_RA0 * RSd + r], ra1o = sd[S_RA1 * RSd + r];
+      double zeta = 0.0;
+#pragma unroll
+      for (int k = 0; k < CNc; ++k) zeta += as[k] * q.w[base + min(k, last) * stride];
+      // row_backsub
+      const double a0 = (G1 * (ra0o - Wr * U0 * zeta) + Wr * U1 * (U1 * ra0o - U0 * ra1o)) * iden;
+      const double a1 = (G0 * (ra1o - Wr * U1 * zeta) + Wr * U0 * (U0 * ra1o - U1 * ra0o)) * iden;
+      const double zt = zeta + U0 * a0 + U1 * a1;
+      const double zr = alpha * zt + oma * Z;
+      double zn = zr + Y * IWRR;
+      zn = fmin(fmax(zn, LO), UP);
+      const double dy = Wr * (zr - zn);
+      const double yn = Y + dy;
+      const double s = Wr * zn - yn;
+      // aux 0
+      const double xn0 = alpha * a0 + oma * XA0;
+      const double zra0 = alpha * (B0 * a0) + oma * ZA0;
+      double z20 = zra0 + YA0 * inv_rho_aux;
+      z20 = fmin(fmax(z20, 0.0), UPA0);
+      const double dya0 = rho_aux * (zra0 - z20);
+      const double yan0 = YA0 + dya0;
+      const double ra0 = sigma * xn0 - QA0 + U0 * s + B0 * (rho_aux * z20 - yan0);
+      // aux 1
+      const double xn1 = alpha * a1 + oma * XA1;
+      const double zra1 = alpha * (B1 * a1) + oma * ZA1;
+      double z21 = zra1 + YA1 * inv_rho_aux;
+      z21 = fmin(fmax(z21, 0.0), UPA1);
+      const double dya1 = rho_aux * (zra1 - z21);
+      const double yan1 = YA1 + dya1;
+      const double ra1 = sigma * xn1 - QA1 + U1 * s + B1 * (rho_aux * z21 - yan1);
+      // row_reduce_coef
+      const double cf = s - Wr * (U0 * ra0 * G1 + U1 * ra1 * G0) * iden;
+      sd[S_Z * RSd + r] = zn; sd[S_Y * RSd + r] = yn; sd[S_XA0 * RSd + r] = xn0; sd[S_XA1 * RSd + r] = xn1;
+      sd[S_ZA0 * RSd + r] = z20; sd[S_ZA1 * RSd + r] = z21; sd[S_YA0 * RSd + r] = yan0; sd[S_YA1 * RSd + r] = yan1;
+      sd[S_RA0 * RSd + r] = ra0; sd[S_RA1 * RSd + r] = ra1;
+#pragma unroll
+      for (int k = 0; k < CNc; ++k)
+        if (k <= last) ct[si[(3 + k) * RSd + r]] = as[k] * cf;
+      if (it == n_iter - 1) {  // the state (and, for the certificates, the last steps) go back to the row record
+        double* F = q.F(r);
+        F[R_Z] = zn; F[R_Y] = yn; F[R_DY] = dy;
+        F[R_XA0] = xn0; F[R_XA1] = xn1; F[R_DXA0] = xn0 - XA0; F[R_DXA1] = xn1 - XA1;
+        F[R_ZA0] = z20; F[R_ZA1] = z21; F[R_YA0] = yan0; F[R_YA1] = yan1; F[R_DYA0] = dya0; F[R_DYA1] = dya1;
+        F[R_RA0] = ra0; F[R_RA1] = ra1; F[R_COEF] = cf;
+      }
+    }
+    // trajectory variables and their bound rows
+    for (int i = tid; i < N; i += kQpThreads) {
+      const double beta = q.beta[i];
+      const double lb = q.lbs[i], ub = q.ubs[i];
+      const bool beq = ub - lb < kRhoTol;
+      const double rb = beq ? rho_eq : rho, irb = beq ? inv_rho_eq : inv_rho;
+      const double xt = q.w[i];
+      const double xn = alpha * xt + oma * q.x[i];
+      const double zr = alpha * (beta * xt) + oma * q.zb[i];
+      double zn = zr + q.yb[i] * irb;
+      zn = fmin(fmax(zn, lb), ub);
+      const double dy = rb * (zr - zn);
+      if (keep_steps) {
+        dxs[i] = xn - q.x[i];
+        dyb[i] = dy;
+      }
+      q.x[i] = xn;
+      q.zb[i] = zn;
+      q.yb[i] += dy;
+    }
+    __syncthreads();
+  }
+}
+
 // Ruiz equilibration (scale_data of OSQP [EXT]); leaves the scaled view of every row in its record and the
 // scaled trajectory cost / bounds in q.qs / q.lbs / q.ubs, Dz (global) / beta (shared).
 __device__ inline void qp_scale(QpCtx& q, const QpSettings& st, int n_aux_total) {
@@ -1604,12 +1765,13 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
         // whole register file — saving what it uses of the callee-saved registers at entry — instead of the registers
         // this solver's own state leaves free.  Measured: with a direct call the caller's register allocation squeezes
         // the loop and every level of its solve is scheduled one shared-memory load at a time.)
-        BlockFn volatile fn = q.rows_smem ? &admm_block_fast<NB, PAIR> : &admm_block<NB, PAIR, true>;
+        BlockFn volatile fn = q.rows_smem ? &admm_block_fast<NB, PAIR> : &admm_block_soa<NB, PAIR>;
         fn(q, sysw.rho_aux, n, keep_last ? 1 : 0);
         return;
       }
     }
-    BlockFn volatile fn = &admm_block<NB, PAIR, false>;
+    // long trajectories / wide blocks: rows in shared memory -> the plain block; rows in global memory -> column-major copy
+    BlockFn volatile fn = q.rows_smem ? &admm_block<NB, PAIR, false> : &admm_block_soa<NB, PAIR>;
     fn(q, sysw.rho_aux, n, keep_last ? 1 : 0);
   };
   // the same for the factorisation (a few calls per QP, tens of thousands of cycles each)
@@ -2157,6 +2319,7 @@ __device__ __noinline__ void qp_step(const DevProblem& p, const int b, const dou
   double* const rows_g = p.rows + static_cast<size_t>(b) * p.max_rows * p.row_stride;
   int* const rints_g = p.row_ints + static_cast<size_t>(b) * p.max_rows * RI_NINTS;
   q.rows = rows_g;
+  q.soa = p.soa + static_cast<size_t>(blockIdx.x) * p.soa_stride;
   q.smbase = sm;
   q.rows_smem = 0;
   q.rints = rints_g;

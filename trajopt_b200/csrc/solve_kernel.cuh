@@ -88,9 +88,10 @@ template <int DD, int PAIR>
 __global__ void __launch_bounds__(kQpThreads, 1)
 solve_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ EvalExtra ex, const __grid_constant__ SolveCtl ctl) {
   const int tid = threadIdx.x;
-  const bool qp_only = ctl.mode == SOLVE_QP_ONLY;  // kernel-level entry point: grid = B, one QP step each, no scheduler
-  for (bool first = true;; first = false) {
-    const int b = qp_only ? (first ? static_cast<int>(blockIdx.x) : -1) : claim_trajectory(p, ctl.sched_state, tid);
+  const bool qp_only = ctl.mode == SOLVE_QP_ONLY;  // kernel-level entry point: one QP step per trajectory, no scheduler
+  for (int round = 0;; ++round) {
+    const int bq = static_cast<int>(blockIdx.x) + round * static_cast<int>(gridDim.x);
+    const int b = qp_only ? (bq < p.B ? bq : -1) : claim_trajectory(p, ctl.sched_state, tid);
     if (b < 0) return;
     unsigned long long t_qp = 0ull, t_ev = 0ull, n_ev = 0ull;
     bool finished = false;
@@ -98,7 +99,7 @@ solve_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ EvalE
       const unsigned long long t0 = global_ns();
       // (a single call site: the QP solve stays inlined in the kernel, as tuned)
       qp_step<DD, PAIR>(p, b, ctl.x_override, ctl.trust_override, ctl.admm_iters_out, ctl.polish_out);
-      if (qp_only) return;
+      if (qp_only) break;
       __syncthreads();
       const unsigned long long t1 = global_ns();
       eval_step<DD>(p, ex, EVAL_STEP, b, nullptr);
@@ -108,6 +109,10 @@ solve_kernel(const __grid_constant__ DevProblem p, const __grid_constant__ EvalE
       t_ev += t2 - t1;
       n_ev += 1ull;
       finished = p.status[b] != 5;
+    }
+    if (qp_only) {
+      __syncthreads();
+      continue;
     }
     if (tid == 0) {
       if (!qp_only) {  // diagnostics of the schedule (scripts/sched_report.py)

@@ -86,7 +86,7 @@ struct tb200_problem {
   DevBuf<DevCartTerm> cart_terms;
   DevBuf<int> fixed_vars;
   DevBuf<double> x, new_x, trust, merit_coeffs, cost_vals, cnt_viols, new_cost_vals, new_cnt_viols, model_cost_vals,
-      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace, factor_g, cast_scratch;
+      model_cnt_viols, cart_err, cart_jac, coll_rows, rows, ws_x, ws_yb, scratch, ws_rho, x_tmp, trust_tmp, dbg, trace, factor_g, cast_scratch, soa;
   DevBuf<unsigned long long> sched_timers;
   DevBuf<int> sched_state;
   DevBuf<unsigned long long> coll_mask;
@@ -105,7 +105,7 @@ struct tb200_problem {
     x.release(); new_x.release(); trust.release(); merit_coeffs.release(); cost_vals.release(); cnt_viols.release();
     new_cost_vals.release(); new_cnt_viols.release(); model_cost_vals.release(); model_cnt_viols.release();
     cart_err.release(); cart_jac.release(); coll_rows.release(); rows.release(); ws_x.release(); ws_yb.release();
-    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); factor_g.release(); cast_scratch.release(); lvs_overflow.release(); link_chain.release(); work_counter.release(); qp_done.release(); sched_state.release(); sched_timers.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
+    scratch.release(); ws_rho.release(); dbg.release(); trace.release(); trace_len.release(); factor_g.release(); cast_scratch.release(); soa.release(); lvs_overflow.release(); link_chain.release(); work_counter.release(); qp_done.release(); sched_state.release(); sched_timers.release(); x_tmp.release(); trust_tmp.release(); coll_mask.release(); status.release();
     sqp_iter.release(); merit_round.release(); qp_failures.release(); qp_status.release(); cur_buf.release();
     n_qp_solves.release(); n_func_evals.release(); n_admm_iters.release(); active_count.release(); row_ints.release();
     lists.release(); ws_meta.release(); tmp_iters.release(); tmp_polish.release();
@@ -590,9 +590,12 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   }
   // contact lists of the continuous collision evaluator: one per resident warp of the largest launch (4 doubles a contact)
   ALLOC(cast_scratch, has_cast ? static_cast<size_t>(std::max(P->eval_grid, std::min(B, P->n_sm))) * (kEvalThreads / 32) * 4 * cast_cap : 0);
-  // a factor that does not fit shared memory lives in a per-CTA region (the kernel-level QP entry point launches B CTAs)
-  P->factor_grid = (factor_global || !qs.factor_smem) ? std::max<size_t>(Bs, static_cast<size_t>(P->n_sm)) : 0;
+  // per-CTA regions (the persistent kernel and the kernel-level QP entry point both launch at most one CTA per SM):
+  // a factor that does not fit shared memory, and the column-major copy of rows that do not
+  P->factor_grid = (factor_global || !qs.factor_smem) ? static_cast<size_t>(P->n_sm) : 0;
   ALLOC(factor_g, P->factor_grid * qp_factor_doubles(N, 2 * D));
+  dp.soa_stride = (max_rows > qs.row_cap) ? qp_soa_doubles(max_rows, CN) : 0;
+  ALLOC(soa, static_cast<size_t>(P->n_sm) * dp.soa_stride);
   {
     std::vector<int> chain(static_cast<size_t>(dp.S) * (kMaxSeg + 1), 0);
     for (int sg = 0; sg < dp.S; ++sg) {
@@ -625,6 +628,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   dp.cart_err = P->cart_err.p; dp.cart_jac = P->cart_jac.p; dp.coll_rows = P->coll_rows.p; dp.coll_mask = P->coll_mask.p;
   dp.rows = P->rows.p; dp.row_ints = P->row_ints.p; dp.lists = P->lists.p; dp.ws_x = P->ws_x.p; dp.ws_yb = P->ws_yb.p;
   dp.scratch = P->scratch.p; dp.ws_meta = P->ws_meta.p; dp.ws_rho = P->ws_rho.p; dp.dbg = P->dbg.p; dp.sched_state = P->sched_state.p; dp.sched_timers = P->sched_timers.p; dp.trace_len = P->trace_len.p; dp.trace = nullptr; dp.trace_cap = 0;
+  dp.soa = P->soa.p;
   dp.factor_g = P->factor_g.p; dp.lvs_overflow = P->lvs_overflow.p; dp.qp_done = P->qp_done.p;
   P->ex.link_chain = P->link_chain.p;
   P->ex.work_counter = P->work_counter.p;
@@ -904,7 +908,7 @@ int tb200_qp_solve_batch(tb200_problem* P, const double* x, const double* trust,
   ctl.quantum = 1;
   ctl.x_override = P->x_tmp.p; ctl.trust_override = P->trust_tmp.p;
   ctl.admm_iters_out = P->tmp_iters.p; ctl.polish_out = P->tmp_polish.p;
-  solve_kernel_for(P->D, P->pair_rows)<<<dp.B, kQpThreads, P->solve_smem, st>>>(dp, P->ex, ctl);
+  solve_kernel_for(P->D, P->pair_rows)<<<std::min(dp.B, P->n_sm), kQpThreads, P->solve_smem, st>>>(dp, P->ex, ctl);
   CK(cudaGetLastError());
   auto pull = [&](void* dst, const void* src, size_t n) {
     if (!dst || n == 0) return cudaSuccess;
