@@ -4,7 +4,8 @@ import numpy as np
 # needs a build of solve_kernels.cu with -DTB200_PROFILE, selected with TB200_LIB=<path to that .so>
 from trajopt_b200 import api, problems
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-d = {"cfg1": problems.config1, "cfg2": problems.config2}[sys.argv[2] if len(sys.argv) > 2 else "cfg2"](B=B, T=30)
+cfg = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
+d = problems.CONFIGS[cfg](B=B, T={"cfg3": 50, "cfg4": 40}.get(cfg, 30))
 p = api.Problem(d)
 p.lib.tb200_debug_prof(None, 1)
 t0 = time.time(); got = p.solve(); dt = time.time() - t0

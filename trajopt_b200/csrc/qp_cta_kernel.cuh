@@ -88,10 +88,16 @@ __host__ __device__ inline QpSmem qp_smem_layout(int N, int nb, int row_stride, 
   s.red = o;  o += 16 * 8;                            // block reductions: 16 quantities x 8 warps
   s.colptr = o; o += qp_even((Np + 2) / 2 + 1);
   // the factor (SA, SLM, SU contiguous) when it fits, then the objective's band P(i, i-k), then rows with what is left
-  s.factor_smem = (!factor_global && o + 3 * qp_even(M * blk) <= kQpSmemBudget) ? 1 : 0;
-  s.SA = o;   o += s.factor_smem ? qp_even(M * blk) : 0;
-  s.SLM = o;  o += s.factor_smem ? qp_even(M * blk) : 0;
-  s.SU = o;   o += s.factor_smem ? qp_even(M * blk) : 0;
+  // (bank layout: the solve reads SA and SU side by side in its backward tasks and SU and SLM side by side in its
+  // forward tasks, even lanes one matrix, odd lanes the other: SLM starts a multiple of 16 doubles after SA and SU
+  // 8 doubles (16 banks) off that grid, so the two halves of a warp's access land on disjoint banks.  Measured before:
+  // 1.5 G bank conflicts in a 344 ms launch.)
+  const int fA = (M * blk + 15) & ~15, fL = fA + 8, fU = qp_even(M * blk);
+  s.factor_smem = (!factor_global && o + fA + fL + fU <= kQpSmemBudget) ? 1 : 0;
+  o = s.factor_smem ? ((o + 15) & ~15) : o;
+  s.SA = o;   o += s.factor_smem ? fA : 0;
+  s.SLM = o;  o += s.factor_smem ? fL : 0;
+  s.SU = o;   o += s.factor_smem ? fU : 0;
   s.pband_smem = (o + qp_even(N * (nb + 1)) <= kQpSmemBudget) ? 1 : 0;
   s.Pb = o;   o += s.pband_smem ? qp_even(N * (nb + 1)) : 0;
   const int per_row2 = 2 * row_stride + CN + RI_NINTS;  // in half doubles: record + column entries + row ints
@@ -1425,6 +1431,7 @@ __device__ __noinline__ void admm_block_soa(const QpCtx& q, const double rho_aux
   int* const si = reinterpret_cast<int*>(sd + static_cast<size_t>(RSd) * (S_AS + CNc));  // [3 + CNc][RSd]: base, stride, last, entry of k
   double* const ct = sd + static_cast<size_t>(RSd) * (S_AS + CNc) + (static_cast<size_t>(RSd) * (3 + CNc) + 1) / 2 + 1;
   const int nnz = q.colptr[Np];
+  PROF_T0();
   // ---- entry: entry index of every (row, coefficient); fields of every row; contributions of the current state
   for (int i = tid; i < N; i += kQpThreads)
     for (int e = q.colptr[i]; e < q.colptr[i + 1]; ++e) {
@@ -1462,9 +1469,17 @@ __device__ __noinline__ void admm_block_soa(const QpCtx& q, const double rho_aux
     }
   }
   __syncthreads();
+  PROF_ADD(0);
   for (int it = 0; it < n_iter; ++it) {
     const bool keep_steps = keep_last && it == n_iter - 1;
     // right-hand side  sigma x - q + A'(rho z - y)
+    long long pt_ = 0;
+#ifdef TB200_PROFILE
+    pt_ = clock64();
+#define PROF_SOA(slot) do { const long long n_ = clock64(); if (tid == 0) atomicAdd(&g_prof[slot], (unsigned long long)(n_ - pt_)); pt_ = n_; } while (0)
+#else
+#define PROF_SOA(slot) (void)pt_
+#endif
     for (int i = tid; i < Np; i += kQpThreads) {
       double s = 0.0;
       if (i < N) {
@@ -1475,7 +1490,9 @@ __device__ __noinline__ void admm_block_soa(const QpCtx& q, const double rho_aux
       }
       q.v1[i] = s;
     }
+    PROF_SOA(1);
     bcr_solve<NB>(q, q.v1, q.w);
+    PROF_SOA(2);
     // rows
     for (int r = tid; r < nrows; r += kQpThreads) {
       const int base = si[r], stride = si[RSd + r], last = si[2 * RSd + r];
@@ -1555,6 +1572,7 @@ __device__ __noinline__ void admm_block_soa(const QpCtx& q, const double rho_aux
       q.yb[i] += dy;
     }
     __syncthreads();
+    PROF_SOA(3);
   }
 }
 
