@@ -388,3 +388,25 @@ def test_cast_collision_sqp_clears_the_swept_volume(oracle):
     conv = r["status"] == capi.OPT_CONVERGED
     assert conv.any()
     assert (r["cnt_viols"][conv] < 1e-4).all()
+
+
+# ---------------------------------------------------------------- default QP settings vs OSQP's order of operations
+@pytest.mark.parametrize("name,B", [("config1", 12), ("config2", 12)])
+def test_early_polish_default_keeps_the_sqp_outcome(oracle, name, B):
+    """tb200_default_qp_settings tries the VERIFIED polish before ADMM has met its tolerances (DESIGN.md O1);
+    tb200_osqp_order_qp_settings (early_polish_every = 0) is OSQP's own order (osqp_interface.cpp:78-90 settings,
+    OSQP 0.6 osqp_solve).  An accepted polish is the exact KKT point of the QP whichever iteration it starts
+    from, so the outer SQP must land on the same trajectories; it may not do so bit for bit because a QP that
+    ends on the ADMM iterate ends on a different one."""
+    d1 = getattr(problems, name)(B=B, T=12)
+    d0 = getattr(problems, name)(B=B, T=12)
+    d0.c.qp.early_polish_every = 0
+    d0.c.qp.early_polish_from = 0
+    r1, r0 = oracle.solve_batch(d1), oracle.solve_batch(d0)
+    assert (r1["status"] == r0["status"]).mean() >= 0.9
+    same = r1["status"] == r0["status"]
+    rel = np.abs(r1["total_cost"] - r0["total_cost"]) / np.maximum(1.0, np.abs(r0["total_cost"]))
+    assert (rel[same] < 1e-5).mean() >= 0.8, rel
+    assert np.abs(r1["cnt_viols"][same]).max() < 1e-3 or np.abs(r0["cnt_viols"][same]).max() >= 1e-3
+    # the early polish must pay for itself: fewer ADMM iterations in total
+    assert r1["n_admm_iters"].sum() <= r0["n_admm_iters"].sum()
