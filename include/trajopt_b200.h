@@ -251,7 +251,9 @@ static inline int tb200inl_cast_rows_per_pair(const tb200_problem_desc* d) {
   double need = 1.0;
   for (int k = 0; k < d->n_terms; ++k) {
     const tb200_term* tm = d->terms + k;
-    if (tm->kind != TB200_TERM_COLLISION || tm->evaluator_type != TB200_COLL_LVS_CONTINUOUS) continue;
+    if (tm->kind != TB200_TERM_COLLISION) continue;
+    if (tm->evaluator_type == TB200_COLL_LVS_DISCRETE && need < 2.0) need = 2.0; /* both waypoints are tested */
+    if (tm->evaluator_type != TB200_COLL_LVS_CONTINUOUS && tm->evaluator_type != TB200_COLL_LVS_DISCRETE) continue;
     if (!(tm->longest_valid_segment_length > 0.0)) continue;
     for (int b = 0; b < d->batch; ++b)
       for (int t = tm->first_step < 0 ? 0 : tm->first_step; t < tm->last_step && t + 1 < T; ++t) {
@@ -260,7 +262,8 @@ static inline int tb200inl_cast_rows_per_pair(const tb200_problem_desc* d) {
         for (int j = 0; j < D; ++j) s += (q0[D + j] - q0[j]) * (q0[D + j] - q0[j]);
         s = sqrt(s);
         if (s > tm->longest_valid_segment_length) {
-          const double n = ceil(s / tm->longest_valid_segment_length);
+          /* sub-segments (continuous) | states (LVS_DISCRETE: one more) of this step pair */
+          const double n = ceil(s / tm->longest_valid_segment_length) + (tm->evaluator_type == TB200_COLL_LVS_DISCRETE ? 1.0 : 0.0);
           if (n > need) need = n;
         }
       }

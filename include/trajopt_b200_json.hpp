@@ -7,7 +7,7 @@
 // One JSON document describes ONE problem; a batch repeats it for pci.batch problems, whose per-problem start states
 // (and, if wanted, endpoints / targets / obstacles) the caller fills in afterwards.
 // Not on the device path (std::runtime_error, as an unregistered type is in the reference): joint_jerk, total_time,
-// dynamic_cart_pose, use_time terms, collision "pairs" overrides and LVS_DISCRETE.
+// dynamic_cart_pose, use_time terms and collision "pairs" overrides.
 #pragma once
 #include <cctype>
 #include <cstdlib>

@@ -448,6 +448,12 @@ struct CastCollisionEval {
   double margin, coeff, buffer, lvs;
   bool start_fixed, end_fixed;
   int row_cap;  // rows of a step pair in the fixed-layout output (tb200inl_cast_rows_per_pair)
+  // LVS_DISCRETE (DiscreteCollisionEvaluator, collision_terms.cpp:744-893): a discrete contact test at EVERY state of
+  // the sub-trajectory (both waypoints included: cnt = ceil(dist/lvs) + 1 states, 2 when the step is short) instead of
+  // a swept test per sub-segment.  cc_time of a contact at state i is i / (cnt - 1), type Time0 | Time1 at the two
+  // waypoints, transform == cc_transform == the link frame at that state (addInterpolatedCollisionResults with
+  // discrete = true [EXT]); filter, gradient and rows as for the swept evaluator.
+  bool discrete_states = false;
 
   int subSegments(const double* q0, const double* q1) const {
     double d2 = 0;
@@ -479,19 +485,21 @@ struct CastCollisionEval {
       for (int j = 0; j < D; ++j) u[j] = (i == n) ? q1[j] : q0[j] + (q1[j] - q0[j]) * (static_cast<double>(i) / n);
       robot->fk(u.data(), fr[i]);
     }
-    out.assign(static_cast<size_t>(L) * O * n, Cand{});
+    const int n_slots = discrete_states ? n + 1 : n;  // states | sub-segments
+    out.assign(static_cast<size_t>(L) * O * n_slots, Cand{});
     std::vector<Pose> frt;
     std::vector<Vec> J;
     for (int s = 0; s < L; ++s) {
       const tb200_sphere& sp = robot->spheres[s];
       for (int o = 0; o < O; ++o) {
         const double* ob = &obstacles[o * 4];
-        for (int i = 0; i < n; ++i) {
-          Cand& cd = out[(static_cast<size_t>(s) * O + o) * n + i];
+        for (int i = 0; i < n_slots; ++i) {
+          Cand& cd = out[(static_cast<size_t>(s) * O + o) * n_slots + i];
           cd.exists = true;
+          const int i_end = discrete_states ? i : i + 1;  // a state is a sub-segment of zero length
           double ca[3], cb[3], w[3], ww = 0, wd = 0;
           sphereCentre(fr[i], s, ca);
-          sphereCentre(fr[i + 1], s, cb);
+          sphereCentre(fr[i_end], s, cb);
           for (int k = 0; k < 3; ++k) {
             w[k] = cb[k] - ca[k];
             ww += w[k] * w[k];
@@ -510,7 +518,7 @@ struct CastCollisionEval {
           ct.dist = len - sp.radius - ob[3];
           ct.cc_time = (i + sc) / n;
           for (int k = 0; k < 3; ++k) ct.normal[k] = d[k] / len;
-          const bool time0 = (i == 0 && sc == 0.0), time1 = (i == n - 1 && sc == 1.0);
+          const bool time0 = (i == 0 && sc == 0.0), time1 = discrete_states ? (i == n) : (i == n - 1 && sc == 1.0);
           cd.active = !(ct.dist > margin + buffer) && !(start_fixed && time0) && !(end_fixed && time1);
           ct.g0.assign(D, 0.0);
           ct.g1.assign(D, 0.0);
@@ -522,7 +530,7 @@ struct CastCollisionEval {
           const Pose& lt = frt[sp.segment];
           for (int k = 0; k < 2; ++k) {
             if ((k == 0 && start_fixed) || (k == 1 && end_fixed)) continue;
-            const Pose& lk = fr[i + k][sp.segment];
+            const Pose& lk = fr[discrete_states ? i : i + k][sp.segment];
             double pt[3];
             for (int a = 0; a < 3; ++a)
               pt[a] = lk.R[a * 3] * sp.center[0] + lk.R[a * 3 + 1] * sp.center[1] + lk.R[a * 3 + 2] * sp.center[2] + lt.p[a];
@@ -535,7 +543,7 @@ struct CastCollisionEval {
         }
       }
     }
-    return n;
+    return n_slots;
   }
   void distExpressions(const Vec& x, std::vector<AffExpr>& exprs) const {
     std::vector<Cand> cands;
@@ -884,8 +892,6 @@ TrajProblem buildProblem(const tb200_problem_desc& desc, int b, int cast_cap) {
         break;
       }
       case TB200_TERM_COLLISION: {
-        if (tm.evaluator_type == TB200_COLL_LVS_DISCRETE)
-          throw std::runtime_error("oracle: the LVS_DISCRETE collision evaluator is not restated");
         if (tm.evaluator_type != TB200_COLL_DISCRETE) {
           // CollisionTermInfo::hatch continuous branch (problem_description.cpp:1776-1819 / cost: 1714-1760):
           // one object per step pair [first, last), expression type from the fixed steps
@@ -899,7 +905,7 @@ TrajProblem buildProblem(const tb200_problem_desc& desc, int b, int cast_cap) {
             }
             // (two adjacent fixed steps fall into the START_FIXED_END_FREE branch: the reference's throw is unreachable)
             CastCollisionEval e{tp.robot, obstacles, t, D, tm.margin, tm.coeff, tm.margin_buffer, lvs, cur_fixed,
-                                !cur_fixed && next_fixed, cast_cap};
+                                !cur_fixed && next_fixed, cast_cap, tm.evaluator_type == TB200_COLL_LVS_DISCRETE};
             tp.coll_hooks.push_back([e](const Vec& x, std::vector<Vec>& rows) { e.denseRows(x, rows); });
             if (is_cost) {
               auto c = std::make_shared<CollisionCost>(calcOf(e));

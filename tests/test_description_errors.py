@@ -48,7 +48,8 @@ def _set_term(d, k, **kw):
     (lambda d: setattr(d.c, "batch", 0), capi.ERR_INVALID, "batch must be >= 1"),
     (lambda d: _set_term(d, 2, link=99), capi.ERR_INVALID, "cart_pose link out of range"),
     (lambda d: _set_term(d, 2, first_step=77), capi.ERR_INVALID, "cart_pose timestep outside the trajectory"),
-    (lambda d: _set_term(d, 3, evaluator_type=capi.COLL_LVS_DISCRETE), capi.ERR_UNSUPPORTED, "LVS_DISCRETE"),
+    (lambda d: _set_term(d, 3, evaluator_type=capi.COLL_LVS_DISCRETE, longest_valid_segment_length=0.0), capi.ERR_INVALID,
+     "longest_valid_segment_length must be positive"),
     (lambda d: _set_term(d, 3, evaluator_type=9), capi.ERR_INVALID, "unknown collision evaluator type"),
     (lambda d: _set_term(d, 0, role=7), capi.ERR_INVALID, "term role must be COST or CNT"),
     (lambda d: _set_term(d, 0, kind=42), capi.ERR_INVALID, "unknown term kind"),

@@ -17,6 +17,8 @@ _MAKERS = {"cfg1": lambda: problems.config1(B=16, T=12), "cfg2": lambda: problem
            # configs[3] terms (CartVel + LVS_CONTINUOUS collision + via-point CartPose) at the lengths the QP kernel holds
            "cfg3": lambda: problems.config3(B=16, T=12, via_every=4), "cfg3_T30": lambda: problems.config3(B=4, T=30),
            "cfg3_no_lvs": lambda: problems.config3(B=8, T=12, via_every=4, lvs=10.0),
+           # the same terms with LVS_DISCRETE: discrete tests at the interpolated states instead of the swept test
+           "cfg3_lvs_discrete": lambda: problems.config3(B=8, T=12, via_every=4, evaluator=capi.COLL_LVS_DISCRETE),
            # configs[3] at its stated length (50 waypoints: 25 factor blocks) and configs[4] (14-DOF dual arm, upright
            # constraints on every waypoint, 40 waypoints: factor blocks of 28 in global memory) with three points of its
            # trust-region sweep (trust_box_size, trust_shrink_ratio, trust_expand_ratio)
@@ -44,7 +46,7 @@ def _cfgs():
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg2_full_T", "cfg3", "cfg3_T30", "cfg3_no_lvs", "variants", "cfg3_T50",
-                                  "cfg4", "cfg4_short"])
+                                  "cfg4", "cfg4_short", "cfg3_lvs_discrete"])
 def test_convexify_rows_match_oracle(oracle, name):
     d = _cfgs()[name]
     rng = np.random.default_rng(7)
@@ -62,7 +64,7 @@ def test_convexify_rows_match_oracle(oracle, name):
         assert ((got["coll_rows"][..., -1] != 0) == (ref["coll_rows"][..., -1] != 0)).all()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "variants", "cfg3_T50", "cfg4", "cfg4_short"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "variants", "cfg3_T50", "cfg4", "cfg4_short", "cfg3_lvs_discrete"])
 @pytest.mark.parametrize("trust", [0.1, 0.01])
 def test_qp_solve_matches_oracle(oracle, name, trust):
     d = _cfgs()[name]
@@ -102,7 +104,7 @@ def _solve_with_trace(d, cap=600):
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg1_full_T", "cfg2_full_T", "cfg3", "cfg3_T30", "variants", "cfg3_T50",
-                                  "cfg4", "cfg4_short", "cfg4_sweep_a", "cfg4_sweep_b", "cfg4_sweep_c"])
+                                  "cfg4", "cfg4_short", "cfg4_sweep_a", "cfg4_sweep_b", "cfg4_sweep_c", "cfg3_lvs_discrete"])
 def test_sqp_solve_matches_oracle(oracle, name):
     d = _cfgs()[name]
     got, hit = _solve_with_trace(d)

@@ -390,6 +390,55 @@ def test_cast_collision_sqp_clears_the_swept_volume(oracle):
     assert (r["cnt_viols"][conv] < 1e-4).all()
 
 
+
+def test_lvs_discrete_rows_are_discrete_rows_at_the_interpolated_states(oracle):
+    """LVS_DISCRETE (DiscreteCollisionEvaluator, collision_terms.cpp:744-893): a discrete contact test at each of the
+    ceil(dist/lvs) + 1 states of the sub-trajectory (both waypoints included); a contact at state i has cc_time =
+    i / (cnt - 1) and its gradient (the DISCRETE evaluator's at that state, GetGradient :262-323 with transform ==
+    cc_transform) enters the row scaled (1 - cc_time) over q_t and cc_time over q_t+1; a fixed start drops the contacts
+    of state 0 and the q_t half."""
+    from trajopt_b200 import problems, robots
+    from trajopt_b200.problems import collision_term
+    lvs = 0.05
+    d = problems.config3(B=2, T=4, seed=21, via_every=2, lvs=lvs, evaluator=capi.COLL_LVS_DISCRETE)
+    D, LO = d.D, 7 * 8
+    x = d.init_traj + 0.03 * np.random.default_rng(4).standard_normal(d.init_traj.shape)
+    x[:, 0] = d.init_traj[:, 0]
+    cap = oracle.layout(d).n_coll_cand // (d.T - 1)
+    rows = oracle.convexify_batch(d, x)["coll_rows"].reshape(d.B, d.T - 1, cap, 2 * D + 3)
+    robot = robots.pr2_arm("r", with_spheres=True)
+    seen = 0
+    for b in range(d.B):
+        for t in range(d.T - 1):
+            q0, q1 = x[b, t], x[b, t + 1]
+            dist = np.linalg.norm(q1 - q0)
+            n = int(np.ceil(dist / lvs)) if dist > lvs else 1
+            states = np.array([q1 if i == n else q0 + (q1 - q0) * (i / n) for i in range(n + 1)])
+            # the DISCRETE evaluator at those states (its own pins: simple_collision_unit.cpp + the FD test above)
+            dd = capi.ProblemDesc(robot, n + 1, [collision_term(capi.ROLE_CNT, 0, n, margin=0.02, coeff=20.0, buffer=0.01)],
+                                  states[None], fixed_timesteps=[], obstacles=d.obstacles[b:b + 1])
+            disc = oracle.convexify_batch(dd, states[None])["coll_rows"].reshape(n + 1, LO, D + 3)
+            want = []
+            for pr in range(LO):  # canonical order: link pair, then state
+                for i in range(n + 1):
+                    if disc[i, pr, -1] == 0 or (t == 0 and i == 0):  # filtered | Time0 contact of the fixed start
+                        continue
+                    cc = i / n
+                    g = disc[i, pr, :D]
+                    want.append(np.concatenate([np.zeros(D) if t == 0 else (1 - cc) * g, cc * g, disc[i, pr, D:]]))
+            got = rows[b, t]
+            assert (got[len(want):] == 0).all()
+            if want:
+                np.testing.assert_allclose(got[:len(want)], np.array(want), rtol=1e-9, atol=1e-12)
+            seen += len(want)
+    assert seen >= 4, "the test world must produce contacts"
+    # and the SQP with this evaluator ends collision free
+    d2 = problems.config3(B=4, T=8, seed=9, via_every=2, lvs=lvs, evaluator=capi.COLL_LVS_DISCRETE)
+    r = oracle.solve_batch(d2)
+    conv = r["status"] == capi.OPT_CONVERGED
+    assert conv.any() and (r["cnt_viols"][conv] < 1e-4).all()
+
+
 # ---------------------------------------------------------------- default QP settings vs OSQP's order of operations
 @pytest.mark.parametrize("name,B", [("config1", 12), ("config2", 12)])
 def test_early_polish_default_keeps_the_sqp_outcome(oracle, name, B):

@@ -45,7 +45,7 @@ struct DevObj {
   int link;       // cart: segment
   int target_slot;
   int pad0;       // index of the object in its own list (cost / cnt)
-  int pad1;       // cart_vel: joints moving the link (bit mask); cast collision: bit 0 start fixed, bit 1 end fixed
+  int pad1;       // cart_vel: joints moving the link (bit mask); cast collision: bit 0 start fixed, bit 1 end fixed, bit 2 LVS_DISCRETE
   double coeff, margin, buffer;
   double lvs;     // cast collision: longest valid segment length (max double: never subdivide); cart_vel: max_displacement
 };

@@ -523,7 +523,10 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
         // has its low `count` bits set, so the QP step picks the rows up like any other active candidates.  The gradients
         // need FKs per ACTIVE contact only (both ends of its sub-segment and its contact-time state).
         const int CAP = ex.cast_cap, CS = 2 * D + 3;
-        const bool sfix = co.pad1 & 1, efix = co.pad1 & 2;
+        // LVS_DISCRETE (DiscreteCollisionEvaluator, collision_terms.cpp:744-893): the same machinery with a discrete test
+        // at each of the nsub + 1 STATES of the sub-trajectory (a sub-segment of zero length: s = 0, cc_time = i / nsub,
+        // Time0 | Time1 at the waypoints, one link frame for both reference points).
+        const bool sfix = co.pad1 & 1, efix = co.pad1 & 2, disc = co.pad1 & 4;
         const double* q0 = xs + t * D;
         const double* q1 = q0 + D;
         double d2 = 0.0;
@@ -566,14 +569,16 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
         };
         int count = 0;
         centres_at(0, cenA);
-        for (int i = 0; i < nsub; ++i) {
-          centres_at(i + 1, cenB);
+        const int n_slots = disc ? nsub + 1 : nsub;
+        for (int i = 0; i < n_slots; ++i) {
+          if (!disc) centres_at(i + 1, cenB);
+          else if (i > 0) centres_at(i, cenA);
           for (int c0 = 0; c0 < LO; c0 += 32) {
             const int pr = c0 + lane_c;
             const bool in = pr < LO;
             const int sl = in ? static_cast<int>((static_cast<float>(pr) + 0.5f) * inv_O) : 0, o = in ? pr - sl * O : 0;
             const double* ca = cenA + sl * 3;
-            const double* cb = cenB + sl * 3;
+            const double* cb = (disc ? cenA : cenB) + sl * 3;
             const double4 ob = *reinterpret_cast<const double4*>(obst + o * 4);
             const double wx = cb[0] - ca[0], wy = cb[1] - ca[1], wz = cb[2] - ca[2];
             const double ww = wx * wx + wy * wy + wz * wz;
@@ -583,7 +588,7 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
             const double dx = ob.x - (ca[0] + sc * wx), dy = ob.y - (ca[1] + sc * wy), dz = ob.z - (ca[2] + sc * wz);
             const double len = sqrt(dx * dx + dy * dy + dz * dz);
             const double dist = len - sm[S.sphr + sl] - ob.w;
-            const bool time0 = (i == 0 && sc == 0.0), time1 = (i == nsub - 1 && sc == 1.0);
+            const bool time0 = (i == 0 && sc == 0.0), time1 = disc ? (i == nsub) : (i == nsub - 1 && sc == 1.0);
             const bool active = in && !(dist > reach) && !(sfix && time0) && !(efix && time1);
             const unsigned bal = __ballot_sync(0xffffffffu, active);
             const int pos = count + __popc(bal & ((1u << lane_c) - 1u));
@@ -595,7 +600,8 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
             count += __popc(bal);
           }
           __syncwarp();
-          for (int w = lane_c; w < L * 3; w += 32) cenA[w] = cenB[w];  // the end of this sub-segment starts the next
+          if (!disc)
+            for (int w = lane_c; w < L * 3; w += 32) cenA[w] = cenB[w];  // the end of this sub-segment starts the next
           __syncwarp();
         }
         if (count > CAP) {
@@ -621,7 +627,7 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
           double ca[3], cb[3], offa[3], offb[3];
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
-            const int st = i_s + kk;
+            const int st = disc ? i_s : i_s + kk;
             double* cc3 = kk ? cb : ca;
             double* of3 = kk ? offb : offa;
             if (st == 0 || st == nsub) {

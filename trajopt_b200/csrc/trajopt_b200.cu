@@ -319,14 +319,12 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
       if (is_cnt) { cart_ref.push_back({1, static_cast<int>(eqs.size())}); eqs.push_back(o); }
       else { cart_ref.push_back({0, static_cast<int>(costs.size())}); costs.push_back(o); }
     } else if (tm.kind == TB200_TERM_COLLISION) {
-      if (tm.evaluator_type == TB200_COLL_LVS_DISCRETE)
-        return fail(TB200_ERR_UNSUPPORTED, "the LVS_DISCRETE collision evaluator is not implemented");
       if (tm.evaluator_type < TB200_COLL_DISCRETE || tm.evaluator_type > TB200_COLL_LVS_CONTINUOUS)
         return fail(TB200_ERR_INVALID, "unknown collision evaluator type");
       if (dp.L == 0 || dp.O == 0) return fail(TB200_ERR_INVALID, "collision term needs robot spheres and obstacles");
       if (tm.n_fixed_steps < 0 || tm.n_fixed_steps > 8) return fail(TB200_ERR_INVALID, "collision term: n_fixed_steps outside [0, 8]");
       const bool cast = tm.evaluator_type != TB200_COLL_DISCRETE;
-      if (cast && tm.evaluator_type == TB200_COLL_LVS_CONTINUOUS && !(tm.longest_valid_segment_length > 0.0))
+      if (cast && tm.evaluator_type != TB200_COLL_CONTINUOUS && !(tm.longest_valid_segment_length > 0.0))
         return fail(TB200_ERR_INVALID, "longest_valid_segment_length must be positive");
       if ((cast && has_discrete) || (!cast && has_cast))
         return fail(TB200_ERR_UNSUPPORTED, "discrete and continuous collision terms in one problem are not supported");
@@ -348,7 +346,8 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
         c.n_rows = cast ? cast_cap : dp.L * dp.O;  // continuous: room for cast_cap active contacts of the step pair
         c.coeff = tm.coeff; c.margin = tm.margin; c.buffer = tm.margin_buffer;
         // (two adjacent fixed steps take the START_FIXED_END_FREE branch: the reference's throw is unreachable)
-        c.pad1 = cast ? ((fixed ? 1 : 0) | ((!fixed && next_fixed) ? 2 : 0)) : 0;
+        // bit 2: LVS_DISCRETE = a discrete test at every state of the sub-trajectory instead of a swept one per sub-segment
+        c.pad1 = cast ? ((fixed ? 1 : 0) | ((!fixed && next_fixed) ? 2 : 0) | (tm.evaluator_type == TB200_COLL_LVS_DISCRETE ? 4 : 0)) : 0;
         c.lvs = (tm.evaluator_type == TB200_COLL_CONTINUOUS) ? std::numeric_limits<double>::max() : tm.longest_valid_segment_length;
         if (is_cnt) { coll_ref.push_back({2, static_cast<int>(ineqs.size())}); ineqs.push_back(c); }
         else { coll_ref.push_back({0, static_cast<int>(costs.size())}); costs.push_back(c); }

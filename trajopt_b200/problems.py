@@ -150,11 +150,12 @@ def _sample_obstacles(rng, robot, q0, q1, n_obstacles):
     return obstacles
 
 
-def config3(B=4096, T=50, seed=SEED + 3, n_obstacles=8, via_every=10, lvs=0.05):
+def config3(B=4096, T=50, seed=SEED + 3, n_obstacles=8, via_every=10, lvs=0.05, evaluator=COLL_LVS_CONTINUOUS):
     """configs[3]: the configs[2] world with LVS_CONTINUOUS collision (longest_valid_segment_length 0.05) between
     consecutive waypoints, position-only CartPose constraints on every 10th waypoint along the straight Cartesian
     line start -> goal, the full CartPose constraint at the last waypoint, and a CartVel INEQ constraint
-    (max_displacement 0.05) on every step pair."""
+    (max_displacement 0.05) on every step pair.  `evaluator=COLL_LVS_DISCRETE` swaps the swept test
+    for discrete tests at the interpolated states (DiscreteCollisionEvaluator, collision_terms.cpp:744-893)."""
     robot = robots.pr2_arm("r", with_spheres=True)
     rng = np.random.default_rng(seed)
     D = 7
@@ -176,7 +177,7 @@ def config3(B=4096, T=50, seed=SEED + 3, n_obstacles=8, via_every=10, lvs=0.05):
     terms.append(cart_pose_term(ROLE_CNT, T - 1, tool, target_slot=len(vias)))
     terms.append(cart_vel_term(ROLE_CNT, 0, T - 2, tool, 0.05))
     terms.append(collision_term(ROLE_CNT, 0, T - 1, margin=0.02, coeff=20.0, buffer=0.01, fixed_steps=[0],
-                                evaluator=COLL_LVS_CONTINUOUS, lvs=lvs))
+                                evaluator=evaluator, lvs=lvs))
     return ProblemDesc(robot, T, terms, init, fixed_timesteps=[0], cart_targets=targets, obstacles=obstacles)
 
 
