@@ -45,7 +45,7 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   s.cobj = o;   o += n_coll_objs * static_cast<int>(sizeof(DevObj) / 8);   // the collision objects in kernel order
   s.aobj = o;   o += n_objs * static_cast<int>(sizeof(DevObj) / 8);        // every object: costs, then constraints
   s.velp = o;   o += n_vel_objs * 6;                  // link position at both waypoints of a CartVel pair
-  s.objv = o;   o += n_coll_objs;                     // exact value of every collision object (in-order sums)
+  s.objv = o;   o += n_coll_objs + n_joint_objs;      // exact value of every collision / joint-space object (in-order sums)
   s.mask = o;   o += n_mask_words;
   s.misc = o;   o += 8;
   o += o & 1;
@@ -57,15 +57,14 @@ __host__ __device__ inline EvalSmem eval_smem_layout(int T, int D, int L, int n_
   s.wscr = o;   o += 8 * s.wscr_stride;
   s.cfk = o;    o += 8 * (1 + D) * kFrameStride;    // running frames of the CartPose chain FK: one per lane and warp
   o += o & 1;
-  // the FK frames are dead once the joint axes / sphere centres are emitted: the term buffer of the later
-  // phase reuses their space
+  s.terms = o;  o += n_joint_objs * 2 * T * D;        // per-(step, joint) terms of the joint-space objects
+  o += o & 1;
+  // the FK frames are dead once the joint axes / sphere centres are emitted: while the collision rows are written
+  // their space holds the per-warp staging tiles of the row stores
   s.fr = o;                                           // frames of every FK job: local, then (in place) world
-  s.terms = o;                                        // per-(step, joint) terms of the joint-space objects (later phase)
-  // ... and, while the collision rows are written, the per-warp staging tiles of the bulk (TMA) row stores
-  const int a = T * eval_job_stride(S), b2 = n_joint_objs * 2 * T * D;
-  const int st = (((D + 3) & 1) == 0 && !cast) ? 8 * 32 * (D + 3) : 0;  // one staging tile per warp
-  const int m = a > b2 ? a : b2;
-  o += m > st ? m : st;
+  const int a = T * eval_job_stride(S);
+  const int st = (((D + 3) & 1) == 0 && !cast) ? 8 * 32 * (D + 3) : 0;  // one staging tile (32 rows) per warp
+  o += a > st ? a : st;
   o += o & 1;
   s.total = o;
   return s;
@@ -147,9 +146,17 @@ __device__ inline void warp_fk(const DevProblem& p, const double* q, double* F, 
   }
 }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS): the copies of one phase are all in flight together instead of
+// each loop's store waiting for its own load
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int DD>
 __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalExtra& ex, const int mode, const int b,
-                                               const double* x_in /*EVAL_ONLY*/) {
+                                               const double* x_in /*EVAL_ONLY*/, bool& tables_ready) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
   constexpr int D = DD;
@@ -178,29 +185,31 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
     // ---- load the iterate (coalesced) -------------------------------------------------------
     const double* src = (mode == EVAL_ONLY) ? x_in + static_cast<size_t>(b) * N
                                             : (mode == EVAL_INIT ? p.init_traj : p.new_x) + static_cast<size_t>(b) * N;
-    for (int i = tid; i < N; i += kEvalThreads) {
-      double v = src[i];
-      if (mode == EVAL_INIT) v = fmin(p.upper[i % D] - 1e-3, v);  // getClosestFeasiblePoint quirk, modeling.cpp:267-268
-      xs[i] = v;
-    }
+    for (int i = tid; i < N; i += kEvalThreads) cp_async8(xs + i, src + i);
     for (int i = tid; i < n_mask_words; i += kEvalThreads) mask[i] = 0ull;
     if (tid == 0) misc[2] = 0;  // work counter of the collision phase
     {
       const double* og = p.obstacles + (p.obstacles_per_traj ? static_cast<size_t>(b) * O * 4 : 0);
-      for (int i = tid; i < O * 4; i += kEvalThreads) sm[S.obst + i] = og[i];
-      for (int i = tid; i < L; i += kEvalThreads) sm[S.sphr + i] = p.spheres[i].r;
+      for (int i = tid; i < O * 4; i += kEvalThreads) cp_async8(sm + S.obst + i, og + i);
+    }
+    if (!tables_ready) {  // the same for every trajectory: a persistent CTA of the stand-alone kernel copies them once
+      tables_ready = true;
+      for (int i = tid; i < L; i += kEvalThreads) cp_async8(sm + S.sphr + i, &p.spheres[i].r);
       const double* sg_g = reinterpret_cast<const double*>(p.segs);
-      for (int i = tid; i < p.S * static_cast<int>(sizeof(DevSegment) / 8); i += kEvalThreads) sm[S.segs + i] = sg_g[i];
+      for (int i = tid; i < p.S * static_cast<int>(sizeof(DevSegment) / 8); i += kEvalThreads) cp_async8(sm + S.segs + i, sg_g + i);
       const double* sp_g = reinterpret_cast<const double*>(p.spheres);
-      for (int i = tid; i < L * static_cast<int>(sizeof(DevSphere) / 8); i += kEvalThreads) sm[S.sphs + i] = sp_g[i];
+      for (int i = tid; i < L * static_cast<int>(sizeof(DevSphere) / 8); i += kEvalThreads) cp_async8(sm + S.sphs + i, sp_g + i);
       constexpr int OD = static_cast<int>(sizeof(DevObj) / 8);
       const double* co_g = reinterpret_cast<const double*>(ex.coll_objs);
-      for (int i = tid; i < p.n_coll_objs * OD; i += kEvalThreads) sm[S.cobj + i] = co_g[i];
+      for (int i = tid; i < p.n_coll_objs * OD; i += kEvalThreads) cp_async8(sm + S.cobj + i, co_g + i);
       const double* cs_g = reinterpret_cast<const double*>(p.cost_objs);
-      for (int i = tid; i < p.n_costs * OD; i += kEvalThreads) sm[S.aobj + i] = cs_g[i];
+      for (int i = tid; i < p.n_costs * OD; i += kEvalThreads) cp_async8(sm + S.aobj + i, cs_g + i);
       const double* cn_g = reinterpret_cast<const double*>(p.cnt_objs);
-      for (int i = tid; i < p.n_cnts * OD; i += kEvalThreads) sm[S.aobj + p.n_costs * OD + i] = cn_g[i];
+      for (int i = tid; i < p.n_cnts * OD; i += kEvalThreads) cp_async8(sm + S.aobj + p.n_costs * OD + i, cn_g + i);
     }
+    cp_async_wait_all();
+    if (mode == EVAL_INIT)  // getClosestFeasiblePoint quirk, modeling.cpp:267-268 (a thread clamps what it copied itself)
+      for (int i = tid; i < N; i += kEvalThreads) xs[i] = fmin(p.upper[i % D] - 1e-3, xs[i]);
     __syncthreads();
     EVAL_PROF(1);
 
@@ -223,6 +232,29 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
       double* f = FR + job * JS + sg * FS;
       for (int i = 0; i < 9; ++i) f[i] = loc.R[i];
       for (int i = 0; i < 3; ++i) f[9 + i] = loc.p[i];
+    }
+    // joint-space terms (they need the iterate only): slot j of the term buffer belongs to the j-th joint-space object in
+    // (costs, cnts) order; their in-order sums are work items of the row phase below
+    double* const terms = sm + S.terms;
+    for (int slot_j = 0; slot_j < ex.n_joint_objs; ++slot_j) {
+      const int i = ex.joint_obj_idx[slot_j];
+      const DevObj& o = aobjs[i];
+      const DevJointTerm& jt = p.joint_terms[o.term];
+      double* tb = terms + static_cast<size_t>(slot_j) * 2 * T * D;
+      const int kind = o.kind, order = o.order, first = o.first;
+      for (int w = tid; w < o.n_steps * D; w += kEvalThreads) {
+        const int t = first + w / D, d = w % D;
+        const double e = joint_err(xs, D, order, t, d, jt.targets[d]);
+        double v0, v1 = 0.0;
+        if (kind == OBJ_JOINT_EQ_COST) v0 = e * e * jt.coeffs[d];
+        else if (kind == OBJ_JOINT_EQ_CNT) v0 = fabs(e * e * jt.coeffs[d]);  // value() is c*e^2 while the row is c*e (trajectory_costs.cpp:160 vs 173)
+        else {
+          v0 = fmax((e - jt.upper[d]) * jt.coeffs[d], 0.0);
+          v1 = fmax((jt.lower[d] - e) * jt.coeffs[d], 0.0);
+        }
+        tb[2 * w] = v0;
+        tb[2 * w + 1] = v1;
+      }
     }
     __syncthreads();
     EVAL_PROF(2);
@@ -430,9 +462,24 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
     const float inv_O = 1.0f / static_cast<float>(O);
     for (;;) {
       int k = 0;
-      if (lane_c == 0) k = atomicAdd(&misc[2], 1);  // next collision object: warps take them as they get free
+      if (lane_c == 0) k = atomicAdd(&misc[2], 1);  // next work item: warps take them as they get free
       k = __shfl_sync(0xffffffffu, k, 0);
-      if (k >= p.n_coll_objs) break;
+      if (k >= ex.n_joint_objs + p.n_coll_objs) break;
+      if (k < ex.n_joint_objs) {
+        // the value of a joint-space object: the SEQUENTIAL sum of its terms in the reference's order (one lane; a chain
+        // of ~T*D dependent additions that runs beside the row writers instead of after them)
+        if (lane_c == 0) {
+          const DevObj& o = aobjs[ex.joint_obj_idx[k]];
+          const double* tb = terms + static_cast<size_t>(k) * 2 * T * D;
+          const bool two = o.kind == OBJ_JOINT_INEQ_COST || o.kind == OBJ_JOINT_INEQ_CNT;
+          double v = 0.0;
+          if (two) for (int w = 0; w < 2 * o.n_steps * D; ++w) v += tb[w];
+          else for (int w = 0; w < o.n_steps * D; ++w) v += tb[2 * w];
+          sm[S.objv + p.n_coll_objs + k] = v;
+        }
+        continue;
+      }
+      k -= ex.n_joint_objs;  // the other items: the collision objects
       const DevObj& co = cobjs[k];
       const int t = co.first;
       const double margin = co.margin, reach = co.margin + co.buffer, coeff = co.coeff;
@@ -440,76 +487,98 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
       if (co.kind == OBJ_COLL) {
         const double* AB = sm + S.jax + t * D * 6;
         double* const stage = sm + S.fr + (tid >> 5) * (32 * (D + 3));  // this warp's staging tile (the FK frames are dead by now)
-        for (int c0 = 0; c0 < LO; c0 += 32) {
-          const int cnd = c0 + lane_c;
-          const bool in = cnd < LO;
-          const int sl = in ? static_cast<int>((static_cast<float>(cnd) + 0.5f) * inv_O) : 0, o = in ? cnd - sl * O : 0;
-          const double* c = sm + S.sph + (t * L + sl) * 3;
-          const double cx = c[0], cy = c[1], cz = c[2];
-          const double4 ob = *reinterpret_cast<const double4*>(obst + o * 4);
-          const double dx = ob.x - cx, dy = ob.y - cy, dz = ob.z - cz;
-          const double len = sqrt(dx * dx + dy * dy + dz * dz);
-          const double dist = len - sm[S.sphr + sl] - ob.w;
-          const bool active = in && !(dist > reach);
-          double row[D + 3 + ((D + 3) & 1)];
+        for (int c00 = 0; c00 < LO; c00 += 64) {
+          // Two chunks of 32 candidates per pass: the distance chains (loads, fp64 square root) of the two are independent
+          // and overlap; the rest of a chunk (row, staging, stores) follows one chunk after the other on one tile.
+          int sl2[2];
+          double cx2[2], cy2[2], cz2[2], dx2[2], dy2[2], dz2[2], len2[2], dist2[2];
+          bool in2[2], act2[2];
 #pragma unroll
-          for (int j = 0; j < D; ++j) row[j] = 0.0;
-          // The gradient exists only for contacts inside margin + buffer (the reference never builds an expression
-          // for a filtered contact, collision_terms.cpp:655-691): the other candidates keep a zero gradient.
-          if (active) {
-            const double inv = 1.0 / len;
-            const double nx = dx * inv, ny = dy * inv, nz = dz * inv;  // from the robot sphere towards the obstacle
-            const double mx = cy * nz - cz * ny, my = cz * nx - cx * nz, mz = cx * ny - cy * nx;  // c x n
-            const unsigned jm = ex.sphere_jmask[sl];
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-              const double2 a01 = *reinterpret_cast<const double2*>(AB + j * 6);
-              const double2 a2b0 = *reinterpret_cast<const double2*>(AB + j * 6 + 2);
-              const double2 b12 = *reinterpret_cast<const double2*>(AB + j * 6 + 4);
-              // d(dist)/dq_j = -n . d(c)/dq_j = B_j . n - A_j . (c x n)
-              const double g = (a2b0.y * nx + b12.x * ny + b12.y * nz) - (a01.x * mx + a01.y * my + a2b0.x * mz);
-              row[j] = ((jm >> j) & 1u) ? g : 0.0;
-            }
+          for (int h = 0; h < 2; ++h) {
+            const int cnd = c00 + h * 32 + lane_c;
+            const bool in = cnd < LO;
+            const int sl = in ? static_cast<int>((static_cast<float>(cnd) + 0.5f) * inv_O) : 0, o = in ? cnd - sl * O : 0;
+            const double* c = sm + S.sph + (t * L + sl) * 3;
+            const double cx = c[0], cy = c[1], cz = c[2];
+            const double4 ob = *reinterpret_cast<const double4*>(obst + o * 4);
+            const double dx = ob.x - cx, dy = ob.y - cy, dz = ob.z - cz;
+            const double len = sqrt(dx * dx + dy * dy + dz * dz);
+            const double dist = len - sm[S.sphr + sl] - ob.w;
+            sl2[h] = sl; in2[h] = in;
+            cx2[h] = cx; cy2[h] = cy; cz2[h] = cz;
+            dx2[h] = dx; dy2[h] = dy; dz2[h] = dz;
+            len2[h] = len; dist2[h] = dist;
+            act2[h] = in && !(dist > reach);
           }
-          row[D] = dist;
-          row[D + 1] = margin;
-          row[D + 2] = active ? coeff : 0.0;
-          if constexpr (((D + 3) & 1) == 0) {
-            // rows are 16-byte aligned (D + 3 even, 256-byte aligned buffers): the 32 rows of the chunk are staged in
-            // shared memory and leave as warp-contiguous 16-byte stores (512 contiguous bytes per store instruction,
-            // 2.5 KB contiguous per chunk).  (A cp.async.bulk store of the tile moves the same bytes, but the tile can
-            // only be refilled once the bulk engine has read it — microseconds with 24 warps per SM queueing their
-            // stores — and the row phase of a CTA took 32k cycles; plain stores are fire and forget.)
-            if (in) {
-              double2* d2 = reinterpret_cast<double2*>(stage + lane_c * (D + 3));
 #pragma unroll
-              for (int i = 0; i < (D + 3) / 2; ++i) d2[i] = make_double2(row[2 * i], row[2 * i + 1]);
-            }
-            __syncwarp();
-            {
-              const int nrows = (LO - c0 < 32) ? LO - c0 : 32;
-              const double2* src2 = reinterpret_cast<const double2*>(stage);
-              double2* dst2 = reinterpret_cast<double2*>(rows_out + static_cast<size_t>(co.src_off + c0) * (D + 3));
-              const int n2 = nrows * ((D + 3) / 2);
+          for (int h = 0; h < 2; ++h) {
+            const int c0 = c00 + h * 32;
+            if (c0 < LO) {  // (warp-uniform)
+            const int cnd = c0 + lane_c, sl = sl2[h];
+            const bool in = in2[h], active = act2[h];
+            const double dist = dist2[h];
+            double row[D + 3 + ((D + 3) & 1)];
 #pragma unroll
-              for (int i = 0; i < (D + 3) / 2; ++i) {
-                const int e = i * 32 + lane_c;
-                if (e < n2) dst2[e] = src2[e];
+            for (int j = 0; j < D; ++j) row[j] = 0.0;
+            // The gradient exists only for contacts inside margin + buffer (the reference never builds an expression
+            // for a filtered contact, collision_terms.cpp:655-691): the other candidates keep a zero gradient.
+            if (active) {
+              const double cx = cx2[h], cy = cy2[h], cz = cz2[h];
+              const double inv = 1.0 / len2[h];
+              const double nx = dx2[h] * inv, ny = dy2[h] * inv, nz = dz2[h] * inv;  // from the robot sphere towards the obstacle
+              const double mx = cy * nz - cz * ny, my = cz * nx - cx * nz, mz = cx * ny - cy * nx;  // c x n
+              const unsigned jm = ex.sphere_jmask[sl];
+#pragma unroll
+              for (int j = 0; j < D; ++j) {
+                const double2 a01 = *reinterpret_cast<const double2*>(AB + j * 6);
+                const double2 a2b0 = *reinterpret_cast<const double2*>(AB + j * 6 + 2);
+                const double2 b12 = *reinterpret_cast<const double2*>(AB + j * 6 + 4);
+                // d(dist)/dq_j = -n . d(c)/dq_j = B_j . n - A_j . (c x n)
+                const double g = (a2b0.y * nx + b12.x * ny + b12.y * nz) - (a01.x * mx + a01.y * my + a2b0.x * mz);
+                row[j] = ((jm >> j) & 1u) ? g : 0.0;
               }
             }
-            __syncwarp();  // the tile may be refilled
-          } else if (in) {
-            double* dstp = rows_out + static_cast<size_t>(co.src_off + cnd) * (D + 3);
+            row[D] = dist;
+            row[D + 1] = margin;
+            row[D + 2] = active ? coeff : 0.0;
+            if constexpr (((D + 3) & 1) == 0) {
+              // rows are 16-byte aligned (D + 3 even, 256-byte aligned buffers): the 32 rows of the chunk are staged in
+              // shared memory and leave as warp-contiguous 16-byte stores (512 contiguous bytes per store instruction,
+              // 2.5 KB contiguous per chunk).  (A cp.async.bulk store of the tile moves the same bytes, but the tile can
+              // only be refilled once the bulk engine has read it — microseconds with 24 warps per SM queueing their
+              // stores — and the row phase of a CTA took 32k cycles; plain stores are fire and forget.)
+              if (in) {
+                double2* d2 = reinterpret_cast<double2*>(stage + lane_c * (D + 3));
 #pragma unroll
-            for (int i = 0; i < D + 3; ++i) dstp[i] = row[i];
-          }
-          const unsigned bal = __ballot_sync(0xffffffffu, active);
-          if (lane_c == 0 && bal) atomicOr(&mask[k * p.coll_words + (c0 >> 6)], static_cast<unsigned long long>(bal) << (c0 & 63));
-          const double mine = active ? fmax(margin - dist, 0.0) * coeff : 0.0;
-          unsigned nzb = __ballot_sync(0xffffffffu, mine != 0.0);
-          while (nzb) {  // warp-uniform: the non-zero terms in candidate order (zeros do not change the sum)
-            vsum += __shfl_sync(0xffffffffu, mine, __ffs(nzb) - 1);
-            nzb &= nzb - 1;
+                for (int i = 0; i < (D + 3) / 2; ++i) d2[i] = make_double2(row[2 * i], row[2 * i + 1]);
+              }
+              __syncwarp();
+              {
+                const int nrows = (LO - c0 < 32) ? LO - c0 : 32;
+                const double2* src2 = reinterpret_cast<const double2*>(stage);
+                double2* dst2 = reinterpret_cast<double2*>(rows_out + static_cast<size_t>(co.src_off + c0) * (D + 3));
+                const int n2 = nrows * ((D + 3) / 2);
+#pragma unroll
+                for (int i = 0; i < (D + 3) / 2; ++i) {
+                  const int e = i * 32 + lane_c;
+                  if (e < n2) dst2[e] = src2[e];
+                }
+              }
+              __syncwarp();  // the tile may be refilled
+            } else if (in) {
+              double* dstp = rows_out + static_cast<size_t>(co.src_off + cnd) * (D + 3);
+#pragma unroll
+              for (int i = 0; i < D + 3; ++i) dstp[i] = row[i];
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, active);
+            if (lane_c == 0 && bal) atomicOr(&mask[k * p.coll_words + (c0 >> 6)], static_cast<unsigned long long>(bal) << (c0 & 63));
+            const double mine = active ? fmax(margin - dist, 0.0) * coeff : 0.0;
+            unsigned nzb = __ballot_sync(0xffffffffu, mine != 0.0);
+            while (nzb) {  // warp-uniform: the non-zero terms in candidate order (zeros do not change the sum)
+              vsum += __shfl_sync(0xffffffffu, mine, __ffs(nzb) - 1);
+              nzb &= nzb - 1;
+            }
+            }
           }
         }
       } else {
@@ -715,62 +784,29 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
   double* out_viol = (mode == EVAL_ONLY) ? p.cnt_viols + static_cast<size_t>(b) * p.n_cnts
                                          : (mode == EVAL_INIT ? p.cnt_viols : p.new_cnt_viols) + static_cast<size_t>(b) * p.n_cnts;
   if (!qp_failed) {
+    // (the barrier after the row phase covers everything read here: the in-order sums in shared memory and the
+    // cart_err rows this CTA wrote to global memory)
     const int n_obj = p.n_costs + p.n_cnts;
-    double* terms = sm + S.terms;
-    // joint-space terms: slot j of the term buffer belongs to the j-th joint-space object in (costs, cnts) order
-    for (int slot_j = 0; slot_j < ex.n_joint_objs; ++slot_j) {
-      const int i = ex.joint_obj_idx[slot_j];
-      const DevObj& o = aobjs[i];
-      const DevJointTerm& jt = p.joint_terms[o.term];
-      double* tb = terms + static_cast<size_t>(slot_j) * 2 * T * D;
-      const int kind = o.kind, order = o.order, first = o.first;
-      for (int w = tid; w < o.n_steps * D; w += kEvalThreads) {
-        const int t = first + w / D, d = w % D;
-        const double e = joint_err(xs, D, order, t, d, jt.targets[d]);
-        double v0, v1 = 0.0;
-        if (kind == OBJ_JOINT_EQ_COST) v0 = e * e * jt.coeffs[d];
-        else if (kind == OBJ_JOINT_EQ_CNT) v0 = fabs(e * e * jt.coeffs[d]);  // value() is c*e^2 while the row is c*e (trajectory_costs.cpp:160 vs 173)
-        else {
-          v0 = fmax((e - jt.upper[d]) * jt.coeffs[d], 0.0);
-          v1 = fmax((jt.lower[d] - e) * jt.coeffs[d], 0.0);
-        }
-        tb[2 * w] = v0;
-        tb[2 * w + 1] = v1;
-      }
-    }
-    __syncthreads();  // terms, collision violations (shared) and cart_err rows (global, this CTA) are complete
     EVAL_PROF(6);
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int i = wid; i < n_obj; i += kEvalThreads / 32) {  // one warp per object
+    for (int i = tid; i < n_obj; i += kEvalThreads) {  // one thread per object
       const bool is_cnt = i >= p.n_costs;
       const DevObj& o = aobjs[i];
       double v = 0.0;
       if (o.kind <= OBJ_JOINT_INEQ_CNT) {
         int slot_j = 0;
         for (int k = 0; k < ex.n_joint_objs; ++k) slot_j = (ex.joint_obj_idx[k] == i) ? k : slot_j;
-        const double* tb = terms + static_cast<size_t>(slot_j) * 2 * T * D;
-        const bool two = o.kind == OBJ_JOINT_INEQ_COST || o.kind == OBJ_JOINT_INEQ_CNT;
-        if (lane == 0) {
-          if (two) for (int w = 0; w < 2 * o.n_steps * D; ++w) v += tb[w];
-          else for (int w = 0; w < o.n_steps * D; ++w) v += tb[2 * w];
-        }
+        v = sm[S.objv + p.n_coll_objs + slot_j];  // summed in order by a warp of the row phase
       } else if (o.kind == OBJ_CART_POSE) {
-        if (lane == 0) {
-          const double* e = p.cart_err + slot * p.n_cart_rows + o.src_off;
-          for (int r = 0; r < o.n_rows; ++r) v += fabs(e[r]);
-        }
+        const double* e = p.cart_err + slot * p.n_cart_rows + o.src_off;
+        for (int r = 0; r < o.n_rows; ++r) v += fabs(e[r]);
       } else if (o.kind == OBJ_CART_VEL) {
-        if (lane == 0) {
-          const double* e = p.cart_err + slot * p.n_cart_rows + o.src_off;
-          for (int r = 0; r < 6; ++r) v += is_cnt ? fmax(e[r], 0.0) : fabs(e[r]);  // INEQ violation | ABS cost
-        }
+        const double* e = p.cart_err + slot * p.n_cart_rows + o.src_off;
+        for (int r = 0; r < 6; ++r) v += is_cnt ? fmax(e[r], 0.0) : fabs(e[r]);  // INEQ violation | ABS cost
       } else {
-        if (lane == 0) v = sm[S.objv + o.target_slot];  // collision object: summed by the warp that built its rows
+        v = sm[S.objv + o.target_slot];  // collision object: summed by the warp that built its rows
       }
-      if (lane == 0) {
-        if (is_cnt) out_viol[i - p.n_costs] = v;
-        else out_cost[i] = v;
-      }
+      if (is_cnt) out_viol[i - p.n_costs] = v;
+      else out_cost[i] = v;
     }
   }
   EVAL_PROF(7);
@@ -922,7 +958,8 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
 template <int DD>
 __device__ __noinline__ void eval_step(const DevProblem& p, const EvalExtra& ex, const int mode, const int b,
                                        const double* x_in /*EVAL_ONLY*/) {
-  eval_step_impl<DD>(p, ex, mode, b, x_in);
+  bool tables_ready = false;  // (the QP step used the same shared memory in between)
+  eval_step_impl<DD>(p, ex, mode, b, x_in, tables_ready);
 }
 
 #ifndef TB200_EVAL_MIN_BLOCKS
@@ -937,13 +974,14 @@ eval_convexify_decide_kernel(const __grid_constant__ DevProblem p, const __grid_
   // persistent CTAs: the grid fills the SMs once and every CTA takes the next trajectory when it is done with one
   // (1024 trajectories over 148 SMs x 3-4 resident CTAs: no tail wave of half-empty SMs)
   __shared__ int s_next;
+  bool tables_ready = false;  // the robot / object tables stay in shared memory from one trajectory to the next
   for (;;) {
     if (threadIdx.x == 0) s_next = atomicAdd(ex.work_counter, 1);
     __syncthreads();
     const int b = s_next;
     __syncthreads();
     if (b >= p.B) return;
-    eval_step_impl<DD>(p, ex, mode, b, x_in);
+    eval_step_impl<DD>(p, ex, mode, b, x_in, tables_ready);
     __syncthreads();
   }
 }
