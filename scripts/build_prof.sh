@@ -5,7 +5,7 @@
 set -e
 cd "$(dirname "$0")/../trajopt_b200/csrc"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -ccbin /usr/bin/g++"
-nvcc $FLAGS -DTB200_PROFILE -c -o solve_inst_7_0.prof.o solve_inst_7_0.cu &
+nvcc $FLAGS -DTB200_PROFILE $PROF_EXTRA -c -o solve_inst_7_0.prof.o solve_inst_7_0.cu &
 nvcc $FLAGS -DTB200_PROFILE -c -o solve_inst_7_1.prof.o solve_inst_7_1.cu &
 nvcc $FLAGS -DTB200_EVAL_PROFILE -c -o eval_kernels.prof.o eval_kernels.cu &
 wait

@@ -42,6 +42,14 @@ static __device__ unsigned long long g_prof[16];
 #define PROF_T0()
 #define PROF_ADD(slot)
 #endif
+// -DTB200_PROFILE_CHECK: the per-level slots of the solve (4, 14, 15, 9) count the parts of a termination check instead
+#if defined(TB200_PROFILE) && defined(TB200_PROFILE_CHECK)
+#define PROF_CHK_T0() long long pc_ = clock64()
+#define PROF_CHK(slot) do { const long long n_ = clock64(); if (q.tid == 0) atomicAdd(&g_prof[slot], (unsigned long long)(n_ - pc_)); pc_ = n_; } while (0)
+#else
+#define PROF_CHK_T0()
+#define PROF_CHK(slot)
+#endif
 
 constexpr int kQpThreads = 256;
 constexpr int kQpThreadsC = 256;  // (usable in __host__ __device__ constant expressions)
@@ -131,11 +139,30 @@ enum RowF {
 // row to the right-hand side of the next ADMM solve
 __host__ __device__ inline int qp_row_stride(int CN) { return 3 * CN + R_NF; }
 
+// A vector of the CTA's dynamic shared memory, kept as its offset: q.x[i] is sm[off + i], which the compiler can prove
+// to be a shared-memory access (ld.shared / st.shared, and no aliasing with the global-memory stores around it), while a
+// plain double* member read back from the context is a generic pointer.  Converts to double* where one is asked for.
+struct SmVec {
+  int off;
+  __device__ __forceinline__ double* ptr() const {
+    extern __shared__ double sm[];
+    return sm + off;
+  }
+  __device__ __forceinline__ double& operator[](int i) const { return ptr()[i]; }
+  __device__ __forceinline__ operator double*() const { return ptr(); }
+  __device__ __forceinline__ SmVec& operator=(double* p) {
+    extern __shared__ double sm[];
+    off = static_cast<int>(p - sm);
+    return *this;
+  }
+};
+
 struct QpCtx {
   int N, Np, nb, M, T, D, CN, RS, tid, nrows;
-  double *SA, *SLM, *SU, *beta, *x, *zb, *yb, *v1, *w, *qs, *lbs, *ubs, *tmp, *red, *flag;   // shared (flag: 8 scalars)
+  double *SA, *SLM, *SU;                                                 // the factor: shared, or global (wide blocks)
+  SmVec beta, x, zb, yb, v1, w, qs, lbs, ubs, tmp, red, flag;            // shared (flag: 8 scalars)
   int* colptr;           // shared [Np+1]
-  double *Dz, *v2;       // shared [Np]: variable scalings, scratch of the residual / polish passes
+  SmVec Dz, v2;          // shared [Np]: variable scalings, scratch of the residual / polish passes
   double* rows;          // shared when the QP has at most row_cap rows, else global
   double* soa;           // this CTA's block of global memory for the column-major copy of the rows (admm_block_soa)
   double* smbase;        // start of the CTA's dynamic shared memory (generic address), rows_smem: q.rows lives there
@@ -164,34 +191,40 @@ __device__ __forceinline__ double warp_max_norm(double v) {
   const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
   return __hiloint2double(static_cast<int>(mh), static_cast<int>(ml));
 }
-template <int NQ>
-__device__ inline void block_reduce(const QpCtx& q, double (&vals)[NQ], unsigned sum_mask) {
+template <int NQ, unsigned SUM_MASK>
+__device__ __forceinline__ void block_reduce(const QpCtx& q, double (&vals)[NQ]) {
   static_assert(NQ <= 16, "red area too small");
+  // (forced inline with compile-time roles: the values stay in registers; the partials go through shared-memory
+  // offsets, not generic pointers)
+  extern __shared__ double sm[];
+  double* const red = sm + (q.red - q.smbase);
   const int lane = q.tid & 31, wid = q.tid >> 5;
   __syncwarp();
 #pragma unroll
   for (int k = 0; k < NQ; ++k) {
     double v = vals[k];
-    const bool sum = (sum_mask >> k) & 1u;
-    if (sum) {
+    if ((SUM_MASK >> k) & 1u) {  // (a constant once the loop is unrolled)
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     } else {
       v = warp_max_norm(v);
     }
-    if (lane == 0) q.red[k * 8 + wid] = v;
+    vals[k] = v;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) red[k * 8 + wid] = vals[k];
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < NQ; ++k) {
-    const bool sum = (sum_mask >> k) & 1u;
-    if (sum) {
-      double acc = q.red[k * 8];
+    if ((SUM_MASK >> k) & 1u) {  // (a constant once the loop is unrolled)
+      double acc = red[k * 8];
 #pragma unroll
-      for (int w = 1; w < kQpThreads / 32; ++w) acc += q.red[k * 8 + w];
+      for (int w = 1; w < kQpThreads / 32; ++w) acc += red[k * 8 + w];
       vals[k] = acc;
     } else {
-      vals[k] = warp_max_norm(q.red[k * 8 + (lane & 7)]);  // every warp reduces the 8 partials again
+      vals[k] = warp_max_norm(red[k * 8 + (lane & 7)]);  // every warp reduces the 8 partials again
     }
   }
   __syncthreads();
@@ -722,7 +755,7 @@ template <int NB>
 __device__ __forceinline__ void bcr_solve_sm(const int tid, const SolveRoles& R, const double* sm_base, double* v, double* w) {
   const int wbase = tid & ~31;
   const bool side = tid & 1;
-#ifdef TB200_PROFILE
+#if defined(TB200_PROFILE) && !defined(TB200_PROFILE_CHECK)
   long long pt_ = clock64();
 #define PROF_LVL(slot) do { const long long n_ = clock64(); if (tid == 0) atomicAdd(&g_prof[slot], (unsigned long long)(n_ - pt_)); pt_ = n_; } while (0)
 #else
@@ -915,25 +948,44 @@ __device__ __forceinline__ void bcr_solve_hyb(const int tid, const SolveRoles& R
 // scaled P (band) times a vector: out = c * Dz .* (P (Dz .* in)); in: shared or global, out: global/shared.
 // The band loads are independent and fully unrolled, so the pass costs one memory round trip, not 2*HB+1.
 template <int NB>
-__device__ inline void p_matvec(const QpCtx& q, const double* in, double* out) {
+__device__ __forceinline__ void p_matvec(const QpCtx& q, const double* in, double* out) {
+  // in, out and the scalings are vectors of the CTA's shared memory: addressed as offsets (ld.shared); everything the
+  // loop needs is copied to locals first, and the band offsets are visited four at a time with their loads side by side
+  extern __shared__ double sm[];
   constexpr int HB = NB, W = HB + 1;
-  const int N = q.N;
-  for (int i = q.tid; i < q.Np; i += kQpThreads) {
+  const int N = q.N, Np = q.Np, nbo = q.n_band;
+  const double* const Pb = q.Pband;  // shared or global
+  const double* const Dz = sm + (q.Dz - q.smbase);
+  const double* const vin = sm + (in - q.smbase);
+  double* const vout = sm + (out - q.smbase);
+  const int* const offs = q.band_offs;
+  const double cc = q.c;
+  for (int i = q.tid; i < Np; i += kQpThreads) {
     double s = 0.0;
     if (i < N) {
-      // (P * Dz) and x, multiplied and added in the reference's order: the lower part of row i (k = 0..HB), then the
-      // upper part; only the structurally non-zero offsets are visited (a zero entry adds an exact zero)
-      for (int t = 0; t < q.n_band; ++t) {
-        const int k = q.band_offs[t];
-        if (k <= i) s += (q.Pband[i * W + k] * q.Dz[i - k]) * in[i - k];
+      // (P * Dz) and x, multiplied and added in the reference's order: the lower part of row i (k ascending), then the
+      // upper part; only the structurally non-zero offsets are visited (a skipped entry adds an exact zero)
+      for (int t0 = 0; t0 < nbo; t0 += 4) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = (t0 + u < nbo) ? offs[t0 + u] : -1;
+          v[u] = (k >= 0 && k <= i) ? (Pb[i * W + k] * Dz[i - k]) * vin[i - k] : 0.0;
+        }
+        s += v[0]; s += v[1]; s += v[2]; s += v[3];
       }
-      for (int t = 0; t < q.n_band; ++t) {
-        const int k = q.band_offs[t];
-        if (k >= 1 && i + k < N) s += (q.Pband[(i + k) * W + k] * q.Dz[i + k]) * in[i + k];
+      for (int t0 = 0; t0 < nbo; t0 += 4) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = (t0 + u < nbo) ? offs[t0 + u] : -1;
+          v[u] = (k >= 1 && i + k < N) ? (Pb[(i + k) * W + k] * Dz[i + k]) * vin[i + k] : 0.0;
+        }
+        s += v[0]; s += v[1]; s += v[2]; s += v[3];
       }
-      s *= q.c * q.Dz[i];
+      s *= cc * Dz[i];
     }
-    out[i] = s;
+    vout[i] = s;
   }
   __syncthreads();
 }
@@ -1667,7 +1719,7 @@ __device__ inline void qp_scale(QpCtx& q, const QpSettings& st, int n_aux_total)
       if (aux == 2) qn = fmax(qn, fabs(q.c * F[R_DA1] * F[R_W]));
     }
     double red2[2] = {csum, qn};
-    block_reduce<2>(q, red2, 0x1u);
+    block_reduce<2, 0x1u>(q, red2);
     const double mean = limit_scaling(red2[0] / static_cast<double>(N + n_aux_total));
     q.c *= 1.0 / fmax(mean, limit_scaling(red2[1]));
   }
@@ -1813,8 +1865,11 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
   double n_z = 0, n_ax = 0, n_q = 0, n_aty = 0, n_px = 0, s_pri = 0, s_dua = 0, s_z = 0, s_ax = 0, s_q = 0, s_aty = 0, s_px = 0;
 
   // ---------------------------------------------------------------- update_info(): residuals and norms
-  auto info_pass = [&]() {
+  // `scaled`: also the norms of the scaled quantities (only the rho estimate reads them)
+  auto info_pass = [&](const bool scaled) {
+    PROF_CHK_T0();
     p_matvec<NB>(q, q.x, q.v2);  // v2 <- P x
+    PROF_CHK(4);
     double m[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     // 0 pri 1 z 2 ax 3 dua 4 aty 5 q 6 px | 7..13 the same on the scaled quantities
     for (int r = tid; r < q.nrows; r += kQpThreads) {
@@ -1832,18 +1887,19 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
       for (int k = 0; k < 2; ++k) {  // absent aux slots contribute exact zeros
         const double u = F[R_U0 + k], bb = F[R_B0 + k], qa = F[R_QA0 + k];
         const double xa = F[R_XA0 + k], za = F[R_ZA0 + k], ya = F[R_YA0 + k];
-        const double da = F[R_DA0 + k], ea = F[R_EA0 + k];
+        // Einv / Dinv of the aux row and column: one reciprocal each, multiplied like the Einv[r] * (...) of the oracle
+        const double iea = 1.0 / F[R_EA0 + k], ida = 1.0 / F[R_DA0 + k];
         const double axb = bb * xa;
-        m[0] = fmax(m[0], fabs((axb - za) / ea));
-        m[1] = fmax(m[1], fabs(za / ea));
-        m[2] = fmax(m[2], fabs(axb / ea));
+        m[0] = fmax(m[0], fabs(iea * (axb - za)));
+        m[1] = fmax(m[1], fabs(iea * za));
+        m[2] = fmax(m[2], fabs(iea * axb));
         m[7] = fmax(m[7], fabs(axb - za));
         m[8] = fmax(m[8], fabs(za));
         m[9] = fmax(m[9], fabs(axb));
         const double aty = u * F[R_Y] + bb * ya;
-        m[3] = fmax(m[3], fabs((qa + aty) / da));
-        m[4] = fmax(m[4], fabs(aty / da));
-        m[5] = fmax(m[5], fabs(qa / da));
+        m[3] = fmax(m[3], fabs(ida * (qa + aty)));
+        m[4] = fmax(m[4], fabs(ida * aty));
+        m[5] = fmax(m[5], fabs(ida * qa));
         m[10] = fmax(m[10], fabs(qa + aty));
         m[11] = fmax(m[11], fabs(aty));
         m[12] = fmax(m[12], fabs(qa));
@@ -1851,6 +1907,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
       F[R_COEF] = F[R_Y];
     }
     __syncthreads();
+    PROF_CHK(14);
     scatter_columns<CNc>(q, [&](int i) { return q.beta[i] * q.yb[i]; });  // v1 <- A'y (trajectory part)
     for (int i = tid; i < N; i += kQpThreads) {
       const double dz = q.Dz[i], beta = q.beta[i];
@@ -1872,11 +1929,19 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
       m[12] = fmax(m[12], fabs(qv));
       m[13] = fmax(m[13], fabs(px));
     }
-    block_reduce<14>(q, m, 0u);
+    if (scaled) {  // (block-uniform)
+      block_reduce<14, 0u>(q, m);
+      s_pri = m[7]; s_z = m[8]; s_ax = m[9]; s_dua = m[10]; s_aty = m[11]; s_q = m[12]; s_px = m[13];
+    } else {
+      double m7[7] = {m[0], m[1], m[2], m[3], m[4], m[5], m[6]};
+      block_reduce<7, 0u>(q, m7);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) m[k] = m7[k];
+    }
+    PROF_CHK(15);
     pri_res = m[0];
     dua_res = m[3] * q.cinv;
     n_z = m[1]; n_ax = m[2]; n_aty = m[4]; n_q = m[5]; n_px = m[6];
-    s_pri = m[7]; s_z = m[8]; s_ax = m[9]; s_dua = m[10]; s_aty = m[11]; s_q = m[12]; s_px = m[13];
   };
 
   auto primal_infeasible = [&](double eps) -> bool {  // is_primal_infeasible [EXT]
@@ -1901,12 +1966,12 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
       a[0] = fmax(a[0], fabs(q.beta[i] / q.Dz[i] * d));
       a[1] += q.ubs[i] * fmax(d, 0.0) + q.lbs[i] * fmin(d, 0.0);
     }
-    block_reduce<3>(q, a, 0x2u);
+    block_reduce<3, 0x2u>(q, a);
     if (!((a[0] > eps) && (a[1] < -eps * a[0]))) return false;  // block-uniform: the A'dy test cannot rescue it
     scatter_columns<CNc>(q, [&](int i) { return q.beta[i] * dyb[i]; });
     double mm[1] = {a[2]};
     for (int i = tid; i < N; i += kQpThreads) mm[0] = fmax(mm[0], fabs(q.v1[i] / q.Dz[i]));
-    block_reduce<1>(q, mm, 0u);
+    block_reduce<1, 0u>(q, mm);
     return (a[0] > eps) && (a[1] < -eps * a[0]) && (mm[0] < eps * a[0]);
   };
   auto dual_infeasible = [&](double eps) -> bool {  // is_dual_infeasible [EXT]
@@ -1927,7 +1992,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
         a[1] += F[R_QA0 + k] * F[R_DXA0 + k];
       }
     }
-    block_reduce<2>(q, a, 0x2u);
+    block_reduce<2, 0x2u>(q, a);
     const double ndx = a[0], qdx = a[1];
     if (!((ndx > eps) && (qdx < -q.c * eps * ndx))) return false;  // block-uniform: skip the P dx / A dx tests
     p_matvec<NB>(q, q.v1, q.v2);  // v2 <- P dx
@@ -1951,7 +2016,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
         b2[1] += (k < naux && va < -eps * ndx) ? 1.0 : 0.0;               // aux rows: l = 0 finite, u infinite
       }
     }
-    block_reduce<2>(q, b2, 0x2u);
+    block_reduce<2, 0x2u>(q, b2);
     return (ndx > eps) && (qdx < -q.c * eps * ndx) && (b2[0] < q.c * eps * ndx) && (b2[1] == 0.0);
   };
   auto check_termination = [&](bool approximate) -> int {
@@ -2007,7 +2072,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
     // block sum (wraps): butterfly inside the warp, then the 8 partials through shared memory
     __syncwarp();
     for (int off = 16; off > 0; off >>= 1) h += __shfl_xor_sync(0xffffffffu, h, off);
-    unsigned long long* red = reinterpret_cast<unsigned long long*>(q.red);
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(q.red.ptr());
     if ((tid & 31) == 0) red[tid >> 5] = h;
     __syncthreads();
     h = 0ull;
@@ -2026,7 +2091,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
     bool stop = false;
     while (!stop) {
       if (iter >= st.max_iter) {  // max_iter reached without a verdict: approximate test, then MAX_ITER_REACHED
-        if (!(st.check_termination > 0 && (iter % st.check_termination == 0))) info_pass();
+        if (!(st.check_termination > 0 && (iter % st.check_termination == 0))) info_pass(false);
         status = check_termination(true);
         if (status == QPS_UNSOLVED) status = QPS_MAXITER;
         stop = true;
@@ -2041,8 +2106,10 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
         run_block(n, can_check || iter == st.max_iter);
         if (can_check) {
           PROF_T0();
-          info_pass();
+          info_pass(rho_iter);
+          PROF_CHK_T0();
           status = check_termination(false);
+          PROF_CHK(9);
           PROF_ADD(5);
           if (status != QPS_UNSOLVED) stop = true;
           else if (st.polishing && st.early_polish_every > 0 && iter >= st.early_polish_from &&
@@ -2063,7 +2130,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
               failed_guess = pending_guess;
               have_failed_guess = true;
               restore_fn(false);
-              info_pass();  // the polish reuses the vectors of the residual bookkeeping
+              info_pass(rho_iter);  // the polish reuses the vectors of the residual bookkeeping
               if (!factorize(sysw)) {
                 status = QPS_NONCVX;
                 stop = true;
@@ -2072,7 +2139,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
           }
         }
         if (!stop && rho_iter) {
-          if (!can_check) info_pass();
+          if (!can_check) info_pass(true);
           // compute_rho_estimate on the scaled quantities [EXT]
           const double pn = s_pri / (fmax(s_z, s_ax) + 1e-10);
           const double dn = s_dua / (fmax(s_q, fmax(s_aty, s_px)) + 1e-10);
@@ -2204,7 +2271,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
         if (last) mm[1] = fmax(mm[1], fabs(q.v1[i] / q.Dz[i]));
       }
       if (last) {
-        block_reduce<3>(q, mm, 0x4u);
+        block_reduce<3, 0x4u>(q, mm);
         p_pri = mm[0];
         p_dua = mm[1] * q.cinv;
         verified = (mm[2] == 0.0) && (p_pri <= kVerifyTol) && isfinite(p_pri) && isfinite(p_dua);
