@@ -72,7 +72,52 @@ __device__ __forceinline__ double limit_scaling(double v) {
 struct QpSmem {
   int SA, SLM, SU, beta, x, zb, yb, v1, w, qs, lbs, ubs, Dz, v2, Pb, tmp, red, colptr, colent, rints, rows, total, row_cap;
   int factor_smem, pband_smem;  // 1: lives in shared memory; 0: in global memory (factor: per-CTA region, band: the shared table)
+  int pinv;                     // 1: the factor region also holds the partition-inverse form of the ADMM system (PinvPlan)
 };
+
+// ---- partition-inverse form of the block-tridiagonal system (the ADMM system of short trajectories) --------------------
+// Blocks 3, 7, 11, ... are SEPARATORS, the runs of <= 3 blocks between them PARTITIONS (independent once the separators are
+// known).  With A_pp the partitions, C their coupling to the separators, S = A_ss - C' inv(A_pp) C:
+//   factor:  PI = inv(A_pp) (dense, <= 3 NB square per partition);  W = PI C (2 NB columns per partition: its left and its
+//            right separator);  Sinv;  Z = [-Sinv W' | Sinv] = the separator rows of the inverse of the whole matrix
+//   solve:   step A   y = PI b_p (one thread per partition row, its row of PI in REGISTERS for a whole block of iterations)
+//                     x_s = Z b  (two threads per separator row, Z in shared memory)          -- independent of each other
+//            step B   x_p = y - W [x_left; x_right]
+// Two dependent steps instead of the 2 log2(M) + 1 of the cyclic reduction (7 at 15 blocks), and 8.8 k instead of 26 k
+// doubles read from shared memory per solve.  scripts/probes/pinv_proto.py checks the algebra against a dense solve.
+// Thread roles: tid < PR owns partition row tid (partition tid / 3NB); PR <= tid < PR + 2 nS: separator row (tid - PR) / 2,
+// half (tid - PR) & 1 of its columns.
+struct PinvPlan {
+  int ok;          // the system fits this path (roles <= 256 threads, <= 3 separators)
+  int Ns, nS;      // separator blocks, their rows Ns * NB
+  int PR;          // partition rows (M - Ns) * NB
+  int ZS, HO;      // row stride of Z (>= Np, = 4 mod 16: the 8 lanes of a quarter warp hit 8 different 16-byte bank groups),
+                   // first column of the second half of a separator row (= 2 mod 16, same reason)
+  int WS;          // row stride of W (2 NB + 2: consecutive rows 16 bytes apart modulo 128)
+  int SS;          // row stride of S / Sinv
+  int zo, wo, so;  // offsets (doubles from the start of the factor region) of Z, W, S
+  int total;       // doubles of the factor region this path needs
+};
+__host__ __device__ inline PinvPlan pinv_plan(int M, int nb) {
+  PinvPlan pl;
+  pl.Ns = M / 4;
+  pl.nS = pl.Ns * nb;
+  pl.PR = (M - pl.Ns) * nb;
+  const int Np = M * nb, blk = nb * nb;
+  pl.ok = (nb % 2 == 0) && nb <= 14 && pl.Ns <= 3 && pl.PR + 2 * pl.nS <= 256;
+  pl.ZS = Np + ((4 - Np % 16) + 16) % 16;
+  pl.HO = ((Np / 2 + 6) / 16) * 16 + 2;
+  if (pl.HO > Np) pl.HO = Np;
+  pl.WS = 2 * nb + 2;
+  pl.SS = pl.nS + (pl.nS & 1);
+  const int fA = (M * blk + 15) & ~15, fL = fA + 8;
+  const int zn = pl.nS * pl.ZS;
+  pl.zo = 0;
+  pl.wo = ((zn > fA + fL ? zn : fA + fL) + 15) & ~15;  // W is written while SA / SLM are still read; Z replaces them at the end
+  pl.so = pl.wo + ((pl.PR * pl.WS + 1) & ~1);
+  pl.total = pl.so + pl.nS * pl.SS;
+  return pl;
+}
 constexpr int kQpSmemBudget = 28800;  // doubles per CTA (225 KB of the 227 KB a CTA may use): one CTA per SM
 __host__ __device__ inline int qp_block_count(int N, int nb) { return (N + nb - 1) / nb; }
 __host__ __device__ inline int qp_even(int v) { return (v + 1) & ~1; }
@@ -92,7 +137,7 @@ __host__ __device__ inline QpSmem qp_smem_layout(int N, int nb, int row_stride, 
   s.ubs = o;  o += qp_even(Np);
   s.Dz = o;   o += qp_even(Np);
   s.v2 = o;   o += qp_even(Np);
-  s.tmp = o;  o += 2 * kQpThreadsC + 8;               // Gauss-Jordan pivot rows of one task chunk, 8 scalars at the end
+  s.tmp = o;  o += 2 * kQpThreadsC + 64 + 8;          // Gauss-Jordan pivot rows (and column scales), 8 scalars at the end
   s.red = o;  o += 16 * 8;                            // block reductions: 16 quantities x 8 warps
   s.colptr = o; o += qp_even((Np + 2) / 2 + 1);
   // the factor (SA, SLM, SU contiguous) when it fits, then the objective's band P(i, i-k), then rows with what is left
@@ -103,12 +148,22 @@ __host__ __device__ inline QpSmem qp_smem_layout(int N, int nb, int row_stride, 
   const int fA = (M * blk + 15) & ~15, fL = fA + 8, fU = qp_even(M * blk);
   s.factor_smem = (!factor_global && o + fA + fL + fU <= kQpSmemBudget) ? 1 : 0;
   o = s.factor_smem ? ((o + 15) & ~15) : o;
+  const int per_row2 = 2 * row_stride + CN + RI_NINTS;  // in half doubles: record + column entries + row ints
+  // the partition-inverse form needs a larger region (Z, W, S): taken when the band still fits and at least 64 rows
+  // (or every row the problem can have) stay on chip
+  const PinvPlan pl = pinv_plan(M, nb);
+  {
+    const int region = qp_even(pl.total > fA + fL + fU ? pl.total : fA + fL + fU);
+    const int o2 = o + region + qp_even(N * (nb + 1));
+    const int cap2 = (o2 < kQpSmemBudget) ? 2 * (kQpSmemBudget - o2) / per_row2 - 1 : 0;
+    s.pinv = (s.factor_smem && pl.ok && cap2 >= (max_rows < 64 ? max_rows : 64)) ? 1 : 0;
+  }
   s.SA = o;   o += s.factor_smem ? fA : 0;
   s.SLM = o;  o += s.factor_smem ? fL : 0;
   s.SU = o;   o += s.factor_smem ? fU : 0;
+  if (s.pinv && s.SA + pl.total > o) o = s.SA + qp_even(pl.total);
   s.pband_smem = (o + qp_even(N * (nb + 1)) <= kQpSmemBudget) ? 1 : 0;
   s.Pb = o;   o += s.pband_smem ? qp_even(N * (nb + 1)) : 0;
-  const int per_row2 = 2 * row_stride + CN + RI_NINTS;  // in half doubles: record + column entries + row ints
   int cap = (o < kQpSmemBudget) ? 2 * (kQpSmemBudget - o) / per_row2 - 1 : 0;
   cap = cap > max_rows ? max_rows : cap;
   cap = cap > 1023 ? 1023 : cap;
@@ -173,6 +228,9 @@ struct QpCtx {
   const int* band_offs;  // the band offsets k with a structurally non-zero P(i, i-k), ascending; n_band of them
   int n_band;
   double* scratch;
+  int pinv;              // the ADMM system is factored in its partition-inverse form (pl)
+  PinvPlan pl;
+  double* pi_g;          // this CTA's block of global memory for the rows of the partition inverses [PR][3 NB]
   double c, cinv, rho, rho_eq, sigma, alpha;
   __device__ __forceinline__ double* R(int r) const { return rows + static_cast<size_t>(r) * RS; }
   __device__ __forceinline__ double* F(int r) const { return rows + static_cast<size_t>(r) * RS + 2 * CN; }
@@ -699,6 +757,13 @@ __device__ __forceinline__ double2 lds_v2(const double* p) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
   return v;
 }
+// ... from a 32-bit shared-memory address computed once (base + constant folds into the load's immediate offset)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ double2 lds_v2_at(const unsigned a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ double lds_f64(const double* p) {
   double v;
   const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
@@ -1020,7 +1085,242 @@ __device__ __forceinline__ double xbound_weight(const QpCtx& q, const SysW& w, i
 
 // K = P + sig I + A' W A with the aux variables eliminated, written straight into the block storage
 // (SA: diagonal blocks, SLM: left couplings); one thread per matrix row; then factor.
+// ---- partition-inverse factorisation (PinvPlan) -----------------------------------------------------------------------
+// In-place Gauss-Jordan inverse of independent SPD matrices, one thread per row with the row in registers (a[QN],
+// zeros beyond the matrix size n).  Register arrays cannot be indexed by the (run-time) step number, and unrolling the
+// steps (6 k instructions) ran at the speed of the instruction fetch, rotating the row (2 QN register moves per step)
+// at the speed of instruction issue, and anything the pivot thread does to its own row sits on the critical path of the
+// step (its warp runs both sides of the branch).  So the columns stay put, every step is the same generic update
+// a[j] -= g' t[j] over ALL columns with compile-time indices, and what depends on the step is carried as scales:
+//  * the thread's entry f of the pivot column comes from the published pivot row: the working matrix is symmetric in
+//    the rows still to be eliminated and antisymmetric across the eliminated ones;
+//  * the finished column k (true value -f / pivot in the other rows) is not written: the pivot thread publishes 0 in
+//    place of its pivot entry, the column keeps f and carries the scale -1 / pivot from then on (one per column and
+//    matrix, in shared memory);
+//  * the pivot row is not scaled either: it carries the row scale 1 / pivot (a register), and its later updates use
+//    g / scale = g * pivot;
+//  * the diagonal entry of an eliminated row does not fit either scale: it lives in a register of its own (as the
+//    not-yet-eliminated rows' diagonal entries do, together with their reciprocal, ready for the row's own pivot step).
+// One pass at the end applies the scales.  scripts/probes/pinv_proto.py holds the same algorithm in numpy (error 1e-15
+// at condition 1e16; a shortcut that published pivot + 1 to get -g by cancellation lost eps * pivot).
+// tmp: [2][nmat][QN + 2] then [nmat][QN] column scales.  Every thread of the CTA calls it (one block barrier per step,
+// n_max steps); returns true when this thread met a non-positive pivot.
+// 1 / x for the pivots: hardware seed (about 20 bits) and three Newton steps, straight-line code (the library division
+// keeps a slow-path CALL, and a call inside the elimination loop spills the row around it)
+__device__ __forceinline__ double pivot_rcp(const double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+template <int QN>
+__device__ __forceinline__ bool gj_rows(double (&a)[QN], double diag, const bool active, const int mat, const int row,
+                                        const int n, const int n_max, double* tmp, const int nmat) {
+  constexpr int BS = QN + 2;  // row + reciprocal (+ pad)
+  double* const csv = tmp + 2 * nmat * BS + mat * QN;  // this matrix's column scales
+  bool bad = false;
+  // diag: the row's diagonal entry (true value; after the row's own step: of the inverse being built)
+  double pv_mine = pivot_rcp(diag), my_cs = 1.0, rs = 1.0, inv_rs = 1.0;
+#pragma unroll 1
+  for (int k = 0; k < n_max; ++k) {
+    double* buf = tmp + ((k & 1) * nmat + mat) * BS;
+    const bool piv = active && row == k;  // (k < n follows from row < n)
+    if (piv) {
+      bad |= !(diag > 0.0);
+#pragma unroll
+      for (int j = 0; j < QN; j += 2) *reinterpret_cast<double2*>(buf + j) = make_double2(a[j], a[j + 1]);
+      buf[k] = 0.0;
+      buf[QN] = pv_mine;
+      my_cs = -pv_mine;
+      csv[k] = my_cs;
+      rs = pv_mine;
+      inv_rs = diag;
+      diag = pv_mine;
+    }
+    __syncthreads();
+    if (active && k < n && !piv) {
+      const double tr = buf[row];
+      const bool ahead = row > k;  // this row is still to be eliminated
+      const double f = ahead ? tr : -tr * my_cs;
+      const double g = f * buf[QN];
+      diag = ahead ? diag - g * f : diag + g * f;
+      const double gs = g * inv_rs;
+#pragma unroll
+      for (int j = 0; j < QN; j += 2) {
+        const double2 t = *reinterpret_cast<const double2*>(buf + j);
+        a[j] -= gs * t.x;
+        a[j + 1] -= gs * t.y;
+      }
+      if (ahead) pv_mine = pivot_rcp(diag);
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < QN; ++j) a[j] = (j == row) ? diag : ((j < n) ? a[j] * (rs * csv[j]) : 0.0);
+  }
+  return bad;
+}
+
+// From the assembled blocks (SA: diagonal blocks, SLM: K(block p, block p-1)) to PI (global, read back into registers
+// by admm_block_pinv), W, Z (shared).  Called by every thread of the CTA.  false: a pivot was not positive.
 template <int NB>
+__device__ inline bool pinv_factor(const QpCtx& q) {
+  constexpr int QN = 3 * NB, blk = NB * NB;
+  static_assert(QN % 2 == 0, "pivot rows move as double2");
+  extern __shared__ double sm[];
+  const int tid = q.tid, M = q.M, Np = q.Np;
+  const int PR = q.pl.PR, nS = q.pl.nS, Ns = q.pl.Ns, ZS = q.pl.ZS, WS = q.pl.WS, SS = q.pl.SS;
+  double* const fbase = sm + (q.SA - q.smbase);
+  const double* const SA = fbase;
+  const double* const SLM = sm + (q.SLM - q.smbase);
+  double* const Z = fbase + q.pl.zo;
+  double* const W = fbase + q.pl.wo;
+  double* const S = fbase + q.pl.so;
+  double* const tmp = q.tmp.ptr();
+  const int nparts = (M + 3) / 4;
+  bool bad = false;
+#ifdef TB200_PROFILE
+  long long pf_ = clock64();
+#define PROF_PF(slot) do { const long long n_ = clock64(); if (tid == 0) atomicAdd(&g_prof[slot], (unsigned long long)(n_ - pf_)); pf_ = n_; } while (0)
+#else
+#define PROF_PF(slot)
+#endif
+  {
+    // ---- 1. inverse of every partition (the tridiagonal run of <= 3 blocks starting at block 4 p)
+    const bool prow = tid < PR;
+    const int p = prow ? tid / QN : 0, lr = prow ? tid % QN : 0;
+    const int npb = (M - 4 * p) < 3 ? (M - 4 * p) : 3;
+    const int kb = lr / NB, r = lr % NB, gb = 4 * p + kb;  // local block, row inside it, global block
+    double a[QN];
+#pragma unroll
+    for (int j = 0; j < QN; ++j) {
+      const int cb = j / NB, c = j % NB;  // (compile-time)
+      double v = 0.0;
+      if (prow && cb < npb) {
+        if (cb == kb) v = SA[gb * blk + r * NB + c];
+        else if (cb == kb - 1) v = SLM[gb * blk + r * NB + c];            // K(gb, gb - 1)
+        else if (cb == kb + 1) v = SLM[(gb + 1) * blk + c * NB + r];      // K(gb, gb + 1) = K(gb + 1, gb)'
+      }
+      a[j] = v;
+    }
+    PROF_PF(0);
+    const double dg = prow ? SA[gb * blk + r * NB + r] : 1.0;  // the row's diagonal entry
+    bad |= gj_rows<QN>(a, dg, prow, p, lr, npb * NB, (M < 3 ? M : 3) * NB, tmp, nparts);
+    PROF_PF(4);
+    if (prow) {
+#pragma unroll
+      for (int j = 0; j < QN; ++j) q.pi_g[tid * QN + j] = a[j];
+      // ---- 2. W = PI C: the left separator couples to the partition's first block (C = SLM[4p]), the right one to its
+      // last block (C = SLM[4p + 3]'); a partition that has a right separator is always full (3 blocks)
+      const bool has_l = p > 0, has_r = 4 * p + 3 < M;
+#pragma unroll 2
+      for (int j = 0; j < NB; ++j) {
+        double wl = 0.0, wr = 0.0;
+        if (has_l) {
+#pragma unroll
+          for (int c = 0; c < NB; ++c) wl += a[c] * SLM[(4 * p) * blk + c * NB + j];
+        }
+        if (has_r) {
+#pragma unroll
+          for (int c = 0; c < NB; ++c) wr += a[2 * NB + c] * SLM[(4 * p + 3) * blk + j * NB + c];
+        }
+        W[tid * WS + j] = wl;
+        W[tid * WS + NB + j] = wr;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 3. Schur complement on the separators: S = A_ss - C' W (block tridiagonal in the separators).  One entry per
+  // thread and pass; the dot products are unrolled with two partial sums each (a dependent chain of 28 multiply-adds
+  // with its loads in between took 1.3 k cycles per entry)
+  for (int e = tid; e < nS * nS; e += kQpThreads) {
+    const int ra = e / nS, ca = e % nS, sa = ra / NB, i = ra % NB, sb = ca / NB, j = ca % NB;
+    double v = 0.0;
+    if (sa == sb || sb == sa + 1 || sb == sa - 1) {
+      // left partition of separator sa (its last block couples through SLM[4 sa + 3](i, :)), right partition (its first
+      // block couples through SLM[4 sa + 4](:, i)); the W columns: the partition's own left (0) or right (NB) separator
+      const bool use_l = sb <= sa, use_r = sb >= sa && 4 * sa + 4 < M;
+      const double* cl = SLM + (4 * sa + 3) * blk + i * NB;                       // stride 1 over rr
+      const double* wl = W + (sa * QN + 2 * NB) * WS + (sb == sa ? NB : 0) + j;   // stride WS over rr
+      const double* cr = SLM + (4 * sa + 4) * blk + i;                            // stride NB over rr
+      const double* wr = W + ((sa + 1) * QN) * WS + (sb == sa ? 0 : NB) + j;      // stride WS over rr
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      if (use_l) {
+#pragma unroll
+        for (int rr = 0; rr < NB; rr += 2) {
+          s0 += cl[rr] * wl[rr * WS];
+          s1 += cl[rr + 1] * wl[(rr + 1) * WS];
+        }
+      }
+      if (use_r) {
+#pragma unroll
+        for (int rr = 0; rr < NB; rr += 2) {
+          s2 += cr[rr * NB] * wr[rr * WS];
+          s3 += cr[(rr + 1) * NB] * wr[(rr + 1) * WS];
+        }
+      }
+      v = ((sa == sb) ? SA[(4 * sa + 3) * blk + i * NB + j] : 0.0) - ((s0 + s1) + (s2 + s3));
+    }
+    S[ra * SS + ca] = v;
+  }
+  __syncthreads();
+  PROF_PF(14);
+  {
+    // ---- 4. its inverse (one matrix of nS <= 3 NB rows)
+    const bool srow = tid < nS;
+    double a[QN];
+#pragma unroll
+    for (int j = 0; j < QN; ++j) a[j] = (srow && j < nS) ? S[tid * SS + j] : 0.0;
+    const double dg = srow ? S[tid * SS + tid] : 1.0;
+    bad |= gj_rows<QN>(a, dg, srow, 0, tid, nS, nS, tmp, 1);
+    if (srow) {
+#pragma unroll
+      for (int j = 0; j < QN; ++j)
+        if (j < nS) S[tid * SS + j] = a[j];
+    }
+  }
+  __syncthreads();
+  PROF_PF(15);
+  // ---- 5. Z = [-Sinv W' | Sinv]: the separator rows of the inverse of the whole matrix (over the dead SA / SLM).
+  // One thread per COLUMN with its row of W in registers; per separator row 2 NB multiply-adds against a row segment of
+  // Sinv that every thread of the partition reads at the same address; the stores of a warp are contiguous.
+  if (tid < Np) {
+    const int col = tid, cb = col / NB, c = col % NB, p = cb / 4;
+    if (cb % 4 == 3) {
+      for (int sr = 0; sr < nS; ++sr) Z[sr * ZS + col] = S[sr * SS + p * NB + c];
+    } else {
+      const bool has_l = p > 0, has_r = 4 * p + 3 < M;
+      const double* wrow = W + (p * QN + (cb % 4) * NB + c) * WS;
+      double wv[2 * NB];
+#pragma unroll
+      for (int t = 0; t < 2 * NB; ++t) wv[t] = wrow[t];
+      const double* sl = S + (has_l ? (p - 1) * NB : 0);  // (W is zero where a separator is absent)
+      const double* sr_ = S + (has_r ? p * NB : 0);
+#pragma unroll 2
+      for (int sr = 0; sr < nS; ++sr) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int t = 0; t < NB; t += 2) {
+          s0 += sl[sr * SS + t] * wv[t];
+          s1 += sl[sr * SS + t + 1] * wv[t + 1];
+          s2 += sr_[sr * SS + t] * wv[NB + t];
+          s3 += sr_[sr * SS + t + 1] * wv[NB + t + 1];
+        }
+        Z[sr * ZS + col] = -((s0 + s1) + (s2 + s3));
+      }
+    }
+  }
+  (void)Ns;
+  const bool ok = !__syncthreads_or(bad ? 1 : 0);
+  PROF_PF(9);
+  return ok;
+}
+
+template <int NB, bool PINV>
 __device__ __noinline__ bool assemble_factor(const QpCtx& q, const SysW& w) {
   PROF_T0();
   rows_prepare_weights(q, w);
@@ -1069,7 +1369,12 @@ __device__ __noinline__ bool assemble_factor(const QpCtx& q, const SysW& w) {
   __syncthreads();
   PROF_ADD(10);
   bool ok;
-  { PROF_T0(); ok = bcr_factor<NB>(q); PROF_ADD(11); }
+  {
+    PROF_T0();
+    if constexpr (PINV) ok = pinv_factor<NB>(q);
+    else ok = bcr_factor<NB>(q);
+    PROF_ADD(11);
+  }
   return ok;
 }
 
@@ -1456,6 +1761,264 @@ __device__ __noinline__ void admm_block_fast(const QpCtx& q, const double rho_au
   __syncthreads();
 }
 
+// The block of iterations for systems factored in their partition-inverse form (PinvPlan: short trajectories, QP rows in
+// shared memory).  As admm_block_fast — shared-memory offsets, scalars in locals, the thread's variable in registers for
+// the whole block, preloaded contribution addresses — with the two-step solve, and WARP SPECIALISED: warps 0-5 own the
+// partition rows (each thread its row of PI, 3 NB doubles, in registers), warps 6-7 own the QP rows; both take part in the
+// separator rows of step A and own their variables.  The two paths never hold each other's state, so neither spills:
+// with the 227 KB shared-memory carve-out L1 is a few KB and every spilled register costs an L2 round trip per
+// iteration (measured: the single-path version of this block ran slower than the cyclic reduction).  The paths meet at
+// `bar.sync 0` (four per iteration), which counts arrivals and does not care where they come from.
+template <int NB, int PAIR>
+__device__ __noinline__ void admm_block_pinv(const QpCtx& q, const double rho_aux_in, const int n_iter, const int keep_last) {
+  constexpr int CNc = PAIR ? ((NB > 3) ? NB : 3) : ((NB / 2 > 3) ? NB / 2 : 3);
+  constexpr int kPre = 8;  // column entries whose addresses are kept in registers
+  constexpr int QN = 3 * NB;
+  constexpr int kRowThreads = 64;  // warps 6-7
+  extern __shared__ double sm[];
+  const int tid = q.tid, N = q.N, Np = q.Np, nrows = q.nrows, RS = q.RS;
+  const double sigma = q.sigma, alpha = q.alpha, oma = 1.0 - q.alpha, rho = q.rho, rho_eq = q.rho_eq, rho_aux = rho_aux_in;
+  const double inv_rho_aux = 1.0 / rho_aux, inv_rho = 1.0 / rho, inv_rho_eq = 1.0 / rho_eq;
+  double* const v1 = sm + (q.v1 - q.smbase);
+  double* const w = sm + (q.w - q.smbase);
+  double* const rows = sm + (q.rows - q.smbase);
+  const int* const rints = reinterpret_cast<const int*>(sm + (reinterpret_cast<const double*>(q.rints) - q.smbase));
+  const int* const colent = reinterpret_cast<const int*>(sm + (reinterpret_cast<const double*>(q.colent) - q.smbase));
+  double* const dxs = q.scratch;
+  double* const dyb = q.scratch + Np;
+  // ---- roles in the solve
+  const int M = q.M, PR = q.pl.PR, nS = q.pl.nS, ZS = q.pl.ZS, HO = q.pl.HO, WS = q.pl.WS;
+  const double* const fbase = sm + (q.SA - q.smbase);
+  const bool upper = tid >= kQpThreads - kRowThreads;      // warps 6-7: the QP rows
+  const bool prow = tid < PR;                              // a partition row (PR <= 192: always in warps 0-5)
+  const int pp = prow ? tid / QN : 0, plr = prow ? tid % QN : 0;
+  const int pb0 = pp * 4 * NB, pvar = pb0 + plr;           // first variable of the partition, the variable of this row
+  const int pn = ((M - 4 * pp) < 3 ? (M - 4 * pp) : 3) * NB;
+  const int xl_off = (pp > 0) ? (4 * pp - 1) * NB : 0;     // solutions of the left / right separator in w (absent: W is 0)
+  const int xr_off = (4 * pp + 3 < M) ? (4 * pp + 3) * NB : 0;
+  const unsigned a_wrow = smem_u32(fbase + q.pl.wo + (prow ? tid : 0) * WS);
+  const unsigned a_b = smem_u32(v1 + pb0), a_xl = smem_u32(w + xl_off), a_xr = smem_u32(w + xr_off);
+  const bool swork = tid >= PR && tid < PR + 2 * nS;       // half of a separator row of Z
+  const int sw = swork ? tid - PR : 0, srow = sw >> 1, half = sw & 1;
+  const int svar = (4 * (srow / NB) + 3) * NB + srow % NB;
+  const int c0 = half ? HO : 0, c1 = half ? Np : HO;
+  const unsigned a_z = smem_u32(fbase + q.pl.zo + srow * ZS), a_v1 = smem_u32(v1);
+  // ---- this thread's variable
+  const bool has_var = tid < N;
+  const int vi = has_var ? tid : 0;
+  const double v_beta = q.beta[vi], v_lb = q.lbs[vi], v_ub = q.ubs[vi], v_qs = q.qs[vi];
+  const bool v_eq = v_ub - v_lb < kRhoTol;
+  const double v_rb = v_eq ? rho_eq : rho, v_irb = v_eq ? inv_rho_eq : inv_rho;
+  double v_x = q.x[vi], v_z = q.zb[vi], v_y = q.yb[vi];
+  const int e0 = has_var ? q.colptr[vi] : 0, e1 = has_var ? q.colptr[vi + 1] : 0;
+  // a word that always reads 0.0 (the unused last scalar slot of the factorisation scratch)
+  double* const zero_slot = sm + (q.flag - q.smbase) + 7;
+  if (tid == 0) *zero_slot = 0.0;
+  int ea[kPre];
+#pragma unroll
+  for (int k = 0; k < kPre; ++k) {
+    const int e = e0 + k;
+    const int ent = (e < e1) ? colent[e] : -1;
+    ea[k] = (ent >= 0) ? static_cast<int>(rows - sm) + (ent >> 5) * RS + (2 * CNc + R_NF) + (ent & 31)
+                       : static_cast<int>(zero_slot - sm);
+  }
+  auto bar = []() { asm volatile("bar.sync 0;" ::: "memory"); };
+  // right-hand side  sigma x - q + A'(rho z - y): the variable's own part from registers, the rows left their terms behind
+  auto build_rhs = [&]() {
+    double s = 0.0;
+    if (has_var) {
+      s = sigma * v_x - v_qs + v_beta * (v_rb * v_z - v_y);
+      double c[kPre];
+#pragma unroll
+      for (int k = 0; k < kPre; ++k) c[k] = sm[ea[k]];
+      // (a fixed pairwise order: the eight loads are in flight together instead of one load per dependent add)
+      s += ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+      for (int e = e0 + kPre; e < e1; ++e) {
+        const int ent = colent[e];
+        s += rows[(ent >> 5) * RS + (2 * CNc + R_NF) + (ent & 31)];
+      }
+    }
+    if (tid < Np) v1[tid] = s;
+  };
+  // step A for a separator worker: its half of x_s = Z b; the two halves of a row sit in neighbouring lanes
+  auto sep_half = [&]() {
+    double zs = 0.0;
+    if (swork) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int c = c0;
+      unsigned az = a_z + c0 * 8, ab = a_v1 + c0 * 8;
+#pragma unroll 2
+      for (; c + 8 <= c1; c += 8, az += 64, ab += 64) {
+        const double2 z0 = lds_v2_at(az), z1 = lds_v2_at(az + 16), z2 = lds_v2_at(az + 32), z3 = lds_v2_at(az + 48);
+        const double2 b0 = lds_v2_at(ab), b1 = lds_v2_at(ab + 16), b2 = lds_v2_at(ab + 32), b3 = lds_v2_at(ab + 48);
+        s0 += z0.x * b0.x; s1 += z0.y * b0.y; s2 += z1.x * b1.x; s3 += z1.y * b1.y;
+        s0 += z2.x * b2.x; s1 += z2.y * b2.y; s2 += z3.x * b3.x; s3 += z3.y * b3.y;
+      }
+      for (; c < c1; c += 2, az += 16, ab += 16) {
+        const double2 z0 = lds_v2_at(az), b0 = lds_v2_at(ab);
+        s0 += z0.x * b0.x; s1 += z0.y * b0.y;
+      }
+      zs = (s0 + s1) + (s2 + s3);
+    }
+    zs += __shfl_xor_sync(0xffffffffu, zs, 1);
+    if (swork && half == 0) w[svar] = zs;
+  };
+  // the thread's variable and its bound row after the solve
+  auto var_update = [&](const bool keep_steps) {
+    if (has_var) {
+      const double xt = w[vi];
+      const double xn = alpha * xt + oma * v_x;
+      const double zr = alpha * (v_beta * xt) + oma * v_z;
+      double zn = zr + v_y * v_irb;
+      zn = fmin(fmax(zn, v_lb), v_ub);
+      const double dy = v_rb * (zr - zn);
+      if (keep_steps) {
+        dxs[vi] = xn - v_x;
+        dyb[vi] = dy;
+      }
+      v_x = xn;
+      v_z = zn;
+      v_y += dy;
+    }
+  };
+
+  if (!upper) {
+    // ================= warps 0-5: partition rows (PI row in registers), separator halves, variables
+    double pi[QN];
+#pragma unroll
+    for (int j = 0; j < QN; ++j) pi[j] = prow ? q.pi_g[tid * QN + j] : 0.0;
+    bar();  // (the entry pass of the row warps)
+    for (int it = 0; it < n_iter; ++it) {
+      const bool keep_steps = keep_last && it == n_iter - 1;
+      { PROF_T0(); build_rhs(); PROF_ADD(1); }
+      {
+        PROF_T0();
+        PROF_CHK_T0();
+        bar();  // the right-hand side is complete
+        PROF_CHK(4);
+        double y = 0.0;
+        if (prow) {  // step A: y = PI b_p
+          double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < QN; j += 2) {
+            double2 bb = make_double2(0.0, 0.0);
+            if (j < pn) bb = lds_v2_at(a_b + j * 8);
+            y0 += pi[j] * bb.x;
+            y1 += pi[j + 1] * bb.y;
+          }
+          y = y0 + y1;
+        }
+        sep_half();
+        PROF_CHK(14);
+        bar();
+        PROF_CHK(15);
+        if (prow) {  // step B: x_p = y - W [x_left; x_right]
+          double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+          for (int t = 0; t < NB; t += 2) {
+            const double2 wl = lds_v2_at(a_wrow + t * 8), wr = lds_v2_at(a_wrow + (NB + t) * 8);
+            const double2 xl = lds_v2_at(a_xl + t * 8), xr = lds_v2_at(a_xr + t * 8);
+            t0 += wl.x * xl.x + wr.x * xr.x;
+            t1 += wl.y * xl.y + wr.y * xr.y;
+          }
+          w[pvar] = y - (t0 + t1);
+        }
+        bar();
+        PROF_CHK(9);
+        PROF_ADD(2);
+      }
+      {
+        PROF_T0();
+        var_update(keep_steps);
+        bar();
+        PROF_ADD(3);
+      }
+    }
+  } else {
+    // ================= warps 6-7: the QP rows, separator halves, variables
+    // entry pass: aux right-hand sides, row multipliers and contributions from the current row state
+    for (int r = kQpThreads - 1 - tid; r < nrows; r += kRowThreads) {
+      double* F = rows + r * RS + 2 * CNc;
+      const double s = F[R_WRR] * F[R_Z] - F[R_Y];
+      const double ra0 = sigma * F[R_XA0] - F[R_QA0] + F[R_U0] * s + F[R_B0] * (rho_aux * F[R_ZA0] - F[R_YA0]);
+      const double ra1 = sigma * F[R_XA1] - F[R_QA1] + F[R_U1] * s + F[R_B1] * (rho_aux * F[R_ZA1] - F[R_YA1]);
+      F[R_RA0] = ra0;
+      F[R_RA1] = ra1;
+      const double cf = row_reduce_coef(F, ra0, ra1, s);
+      F[R_COEF] = cf;
+      const double* as = rows + r * RS + CNc;
+#pragma unroll
+      for (int k = 0; k < CNc; ++k) F[R_NF + k] = as[k] * cf;
+    }
+    bar();
+    for (int it = 0; it < n_iter; ++it) {
+      const bool keep_steps = keep_last && it == n_iter - 1;
+      build_rhs();
+      bar();
+      sep_half();
+      bar();
+      bar();  // (step B of the partition warps)
+      // rows: back-substitute aux, relax, project, dual update, and the multipliers for the next solve
+      for (int r = kQpThreads - 1 - tid; r < nrows; r += kRowThreads) {
+        const double* R = rows + r * RS;
+        double* F = rows + r * RS + 2 * CNc;
+        const int* I = rints + r * RI_NINTS;
+        double zeta = 0.0;
+        {
+          const int base = I[RI_BASE], stride = I[RI_STRIDE], last = I[RI_CNT] - 1;
+#pragma unroll
+          for (int k = 0; k < CNc; ++k) zeta += R[CNc + k] * w[base + min(k, last) * stride];
+        }
+        double a0, a1;
+        row_backsub(F, zeta, a0, a1);
+        const double zt = zeta + F[R_U0] * a0 + F[R_U1] * a1;
+        const double Wr = F[R_WRR];
+        const double zr = alpha * zt + oma * F[R_Z];
+        double zn = zr + F[R_Y] * F[R_IWRR];
+        zn = fmin(fmax(zn, F[R_LO]), F[R_UP]);
+        const double dy = Wr * (zr - zn);
+        const double yn = F[R_Y] + dy;
+        F[R_Z] = zn;
+        F[R_Y] = yn;
+        F[R_DY] = dy;
+        const double s = Wr * zn - yn;
+        double ra[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const double at = k ? a1 : a0, bb = F[R_B0 + k];
+          const double xo = F[R_XA0 + k];
+          const double xn = alpha * at + oma * xo;
+          const double zra = alpha * (bb * at) + oma * F[R_ZA0 + k];
+          double z2 = zra + F[R_YA0 + k] * inv_rho_aux;
+          z2 = fmin(fmax(z2, 0.0), kOsqpInf * F[R_EA0 + k]);
+          const double dya = rho_aux * (zra - z2);
+          const double yan = F[R_YA0 + k] + dya;
+          F[R_XA0 + k] = xn;
+          F[R_DXA0 + k] = xn - xo;
+          F[R_ZA0 + k] = z2;
+          F[R_YA0 + k] = yan;
+          F[R_DYA0 + k] = dya;
+          ra[k] = sigma * xn - F[R_QA0 + k] + F[R_U0 + k] * s + bb * (rho_aux * z2 - yan);
+        }
+        F[R_RA0] = ra[0];
+        F[R_RA1] = ra[1];
+        const double cf = row_reduce_coef(F, ra[0], ra[1], s);
+        F[R_COEF] = cf;
+#pragma unroll
+        for (int k = 0; k < CNc; ++k) F[R_NF + k] = R[CNc + k] * cf;
+      }
+      var_update(keep_steps);
+      bar();
+    }
+  }
+  if (has_var) {
+    q.x[vi] = v_x;
+    q.zb[vi] = v_z;
+    q.yb[vi] = v_y;
+  }
+  __syncthreads();
+}
+
 // The block of iterations for QPs whose rows do not fit shared memory (configs[3] at 50 waypoints: ~370 rows of 14
 // coefficients; configs[4]).  Their row records live in global memory, 98 doubles apart: a warp that works on 32 rows
 // touches 32 different sectors with every field it loads (4x the bytes it uses), and the right-hand side gathers the rows'
@@ -1827,15 +2390,18 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
 
   // the ADMM loop keeps the thread's rows of the factor in registers when the roles fit the CTA (admm_block<.., true>)
   const bool use_reg = REGOK && solve_roles_fit(q.M, NB);
+  // ... and short trajectories with their rows on chip use the partition-inverse form of the system (PinvPlan)
+  const bool use_pinv = REGOK && q.pinv && q.rows_smem;
   using BlockFn = void (*)(const QpCtx&, double, int, int);
   auto run_block = [&](int n, bool keep_last) {
     if constexpr (REGOK) {
-      if (use_reg) {
+      if (use_pinv || use_reg) {
         // (called through pointers: an indirect call follows the standard calling convention, so the block gets the
         // whole register file — saving what it uses of the callee-saved registers at entry — instead of the registers
         // this solver's own state leaves free.  Measured: with a direct call the caller's register allocation squeezes
         // the loop and every level of its solve is scheduled one shared-memory load at a time.)
-        BlockFn volatile fn = q.rows_smem ? &admm_block_fast<NB, PAIR> : &admm_block_soa<NB, PAIR>;
+        BlockFn volatile fn = use_pinv ? &admm_block_pinv<NB, PAIR>
+                                       : (q.rows_smem ? &admm_block_fast<NB, PAIR> : &admm_block_soa<NB, PAIR>);
         fn(q, sysw.rho_aux, n, keep_last ? 1 : 0);
         return;
       }
@@ -1844,10 +2410,17 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
     BlockFn volatile fn = q.rows_smem ? &admm_block<NB, PAIR, false> : &admm_block_soa<NB, PAIR>;
     fn(q, sysw.rho_aux, n, keep_last ? 1 : 0);
   };
-  // the same for the factorisation (a few calls per QP, tens of thousands of cycles each)
+  // the same for the factorisation (a few calls per QP, tens of thousands of cycles each); the polish system always
+  // takes the cyclic reduction (its solves are the generic ones)
   using FactorFn = bool (*)(const QpCtx&, const SysW&);
   auto factorize = [&](const SysW& wts) -> bool {
-    FactorFn volatile fn = &assemble_factor<NB>;
+    if constexpr (REGOK) {
+      if (use_pinv && !wts.polish) {
+        FactorFn volatile fn = &assemble_factor<NB, true>;
+        return fn(q, wts);
+      }
+    }
+    FactorFn volatile fn = &assemble_factor<NB, false>;
     return fn(q, wts);
   };
   { PROF_T0(); factor_ok = factorize(sysw); PROF_ADD(6); }
@@ -2406,6 +2979,9 @@ __device__ __noinline__ void qp_step(const DevProblem& p, const int b, const dou
   q.rows = rows_g;
   q.soa = p.soa + static_cast<size_t>(blockIdx.x) * p.soa_stride;
   q.smbase = sm;
+  q.pinv = S.pinv;
+  q.pl = pinv_plan(q.M, NB);
+  q.pi_g = p.factor_g + static_cast<size_t>(blockIdx.x) * qp_factor_doubles(N, NB);
   q.rows_smem = 0;
   q.rints = rints_g;
   int* mylist = p.lists + static_cast<size_t>(b) * p.list_stride;
