@@ -360,6 +360,9 @@ def main():
     conv_total = reduce(float(sum(conv)), SUM)
     e2e_total_s = reduce(e2e_s, MAX)
     e2e_conv_total = reduce(float(e2e_conv), SUM)
+    # the batches of every rank, step by step: a batch is as slow as its longest trajectory (tens of thousands of
+    # dependent ADMM iterations), so its time varies with the draw — the spread is part of the measurement
+    step_ms_min, step_ms_max = reduce(-min(dev_ms), MAX), reduce(max(dev_ms), MAX)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -393,6 +396,9 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_total_s / args.steps},
             # per solve: reset_state_kernel, eval_convexify_decide_kernel (initial evaluation), solve_kernel (persistent);
             # plus the stand-alone convexify launch the roofline is quoted on (resident leg only)
+            "ms_per_step_rank0": [round(x, 1) for x in dev_ms],
+            "ms_per_step_spread": {"min_over_ranks_and_steps": round(-step_ms_min, 1), "max_over_ranks_and_steps": round(step_ms_max, 1),
+                                   "note": "a batch is bound by its longest trajectory: the time of a fresh batch varies with the draw"},
             "gpu_launches": 4 * len(tms) + 3 * args.steps,
             "roofline": roofline,
             "qp_steps": {"share_of_step": qp_ms / sum(dev_ms), "qp_solves": int(sum(t["qp_launches"] for t in tms)),

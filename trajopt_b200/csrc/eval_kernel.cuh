@@ -187,7 +187,10 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
                                             : (mode == EVAL_INIT ? p.init_traj : p.new_x) + static_cast<size_t>(b) * N;
     for (int i = tid; i < N; i += kEvalThreads) cp_async8(xs + i, src + i);
     for (int i = tid; i < n_mask_words; i += kEvalThreads) mask[i] = 0ull;
-    if (tid == 0) misc[2] = 0;  // work counter of the collision phase
+    if (tid == 0) {
+      misc[2] = 0;  // work counter of the row phase
+      misc[3] = 0;  // ... of the CartPose objects
+    }
     {
       const double* og = p.obstacles + (p.obstacles_per_traj ? static_cast<size_t>(b) * O * 4 : 0);
       for (int i = tid; i < O * 4; i += kEvalThreads) cp_async8(sm + S.obst + i, og + i);
@@ -217,13 +220,26 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
     // (1) local frames of every (job, segment) in parallel (this is where the sincos are), (2) the chain
     // products, one lane per (job, frame row): row i of a world frame depends only on row i of the parent's,
     // so the three lanes of a job never wait for each other, (3) emission of what the row writers need.
+    // Head start: the CartPose objects need the iterate only, and one of them is a long dependent chain (chain FK of eight
+    // states, pose error, atan2) that used to set the length of the row phase.  So when the problem has any, warp 7 starts
+    // on them right away while warps 0-6 run the three FK phases among themselves (named barrier 1, 224 threads); warp 7
+    // waits for the end of the emission (barrier 2: 224 arrive, 32 wait) before it touches anything the FK produced.
+    const bool head = ex.n_cart_objs > 0;
+    const int nthr = head ? kEvalThreads - 32 : kEvalThreads;
+    const bool fk_thread = tid < nthr;
+    auto fk_sync = [&]() {
+      if (head) asm volatile("bar.sync 1, 224;" ::: "memory");
+      else __syncthreads();
+    };
     const int n_jobs = T, Sg = p.S;
     double* FR = sm + S.fr;
     constexpr int FS = kFrameStride;
     const int JS = eval_job_stride(Sg);
     const DevSegment* segs = reinterpret_cast<const DevSegment*>(sm + S.segs);
     const DevSphere* sphs = reinterpret_cast<const DevSphere*>(sm + S.sphs);
-    for (int w = tid; w < n_jobs * Sg; w += kEvalThreads) {
+    double* const terms = sm + S.terms;
+    if (fk_thread) {
+    for (int w = tid; w < n_jobs * Sg; w += nthr) {
       const int job = w / Sg, sg = w % Sg;
       const DevSegment& g = segs[sg];
       const double qv = (g.q_index >= 0) ? xs[job * D + g.q_index] : 0.0;
@@ -235,14 +251,13 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
     }
     // joint-space terms (they need the iterate only): slot j of the term buffer belongs to the j-th joint-space object in
     // (costs, cnts) order; their in-order sums are work items of the row phase below
-    double* const terms = sm + S.terms;
     for (int slot_j = 0; slot_j < ex.n_joint_objs; ++slot_j) {
       const int i = ex.joint_obj_idx[slot_j];
       const DevObj& o = aobjs[i];
       const DevJointTerm& jt = p.joint_terms[o.term];
       double* tb = terms + static_cast<size_t>(slot_j) * 2 * T * D;
       const int kind = o.kind, order = o.order, first = o.first;
-      for (int w = tid; w < o.n_steps * D; w += kEvalThreads) {
+      for (int w = tid; w < o.n_steps * D; w += nthr) {
         const int t = first + w / D, d = w % D;
         const double e = joint_err(xs, D, order, t, d, jt.targets[d]);
         double v0, v1 = 0.0;
@@ -256,9 +271,11 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
         tb[2 * w + 1] = v1;
       }
     }
-    __syncthreads();
+    }
+    if (fk_thread) fk_sync();
     EVAL_PROF(2);
-    for (int w = tid; w < ((n_jobs * 4 + 31) & ~31); w += kEvalThreads) {  // whole warps: __syncwarp below
+    if (fk_thread) {
+    for (int w = tid; w < ((n_jobs * 4 + 31) & ~31); w += nthr) {  // whole warps: __syncwarp below
       // four lanes per job (three rows + one idle) so that the rows of a job always sit in the same warp.  A lane
       // only ever needs ITS row of the parent frame: along a chain (parent == previous segment) it is still in
       // registers, at a branch point it reads back what it wrote itself.  The one barrier per step keeps the
@@ -294,13 +311,15 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
         }
       }
     }
-    __syncthreads();
+    }
+    if (fk_thread) fk_sync();
     EVAL_PROF(3);
+    if (fk_thread) {
     // per (waypoint, joint) the two vectors the gradient of a point on the chain needs: for a point c and a unit
     // direction n,  n . d(c)/dq_j = n . (a_j x (c - o_j)) = A_j . (c x n) - B_j . n  with A_j = a_j, B_j = a_j x o_j
     // (revolute; a_j axis, o_j origin of the joint in the scene root) and A_j = 0, B_j = -a_j (prismatic).
     // Six doubles per (waypoint, joint), 16-byte aligned: the row writers read them as broadcasts.
-    for (int w = tid; w < T * Sg; w += kEvalThreads) {
+    for (int w = tid; w < T * Sg; w += nthr) {
       const int t = w / Sg, sg = w % Sg;
       const DevSegment& g = segs[sg];
       if (g.q_index < 0) continue;
@@ -317,7 +336,7 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
         ab[3] = -a[0]; ab[4] = -a[1]; ab[5] = -a[2];
       }
     }
-    for (int w = tid; w < T * L; w += kEvalThreads) {
+    for (int w = tid; w < T * L; w += nthr) {
       const int t = w / L, sl = w % L;
       const DevSphere& sp = sphs[sl];
       const double* f = FR + t * JS + sp.segment * FS;
@@ -328,12 +347,16 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
         if (ex.cast) sm[S.spo + w * 3 + i] = off;
       }
     }
-    for (int w = tid; w < ex.n_vel_objs * 6; w += kEvalThreads) {  // link position at both ends of a CartVel pair
+    for (int w = tid; w < ex.n_vel_objs * 6; w += nthr) {  // link position at both ends of a CartVel pair
       const int c = w / 6, k = (w % 6) / 3, i = w % 3;
       const DevObj& o = ex.vel_objs[c];
       sm[S.velp + w] = FR[(o.first + k) * JS + o.link * FS + 9 + i];
     }
-    __syncthreads();
+    }
+    if (fk_thread) {
+      fk_sync();
+      if (head) asm volatile("bar.arrive 2, 256;" ::: "memory");
+    }
     EVAL_PROF(4);
 
     // ---- CartPose rows: error + forward-difference Jacobian (kinematic_terms.cpp:250-263, 348-366) ----
@@ -342,7 +365,7 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
     // in the same order as the waypoint FK above) and then the pose-error pipeline ONCE (a long dependent chain of fp64
     // divisions, square roots and an atan2); the base error reaches the difference quotients by shuffle.  No shared
     // memory per object, so a problem may carry any number of them (configs[4]: two per waypoint).
-    for (int c = tid >> 5; c < ex.n_cart_objs; c += kEvalThreads / 32) {
+    auto cart_object = [&](const int c) {
       const int col = tid & 31;  // col 0 = error, col 1+i = Jacobian column i
       const bool work = col < 1 + D;
       const DevObj& o = ex.cart_objs[c];
@@ -422,6 +445,22 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
           jac_out[r * p.cart_stride + (col - 1)] = dv / 1e-5 * ct.coeff[r];
         }
       }
+    };
+    // the objects are handed out one at a time (a counter in shared memory): warp 7 takes them from the start, the others
+    // join once the FK is done
+    auto cart_objects = [&]() {
+      for (;;) {
+        int c = 0;
+        if ((tid & 31) == 0) c = atomicAdd(&misc[3], 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= ex.n_cart_objs) break;
+        cart_object(c);
+      }
+    };
+    // (one copy of the code: warp 7 runs the loop twice — before and after it has waited for the emission of warps 0-6)
+    for (int pass = (head && !fk_thread) ? 0 : 1; pass < 2; ++pass) {
+      cart_objects();
+      if (pass == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
     }
 
     // ---- CartVel rows (kinematic_terms.cpp:376-425): err = [p1 - p0 - lim; p0 - p1 - lim], rows over (q_t, q_t+1)
