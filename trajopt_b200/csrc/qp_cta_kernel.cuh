@@ -110,10 +110,13 @@ __host__ __device__ inline PinvPlan pinv_plan(int M, int nb) {
   if (pl.HO > Np) pl.HO = Np;
   pl.WS = 2 * nb + 2;
   pl.SS = pl.nS + (pl.nS & 1);
-  const int fA = (M * blk + 15) & ~15, fL = fA + 8;
+  const int fA = (M * blk + 15) & ~15, fL = fA + 8, fU = (M * blk + 1) & ~1;
   const int zn = pl.nS * pl.ZS;
   pl.zo = 0;
-  pl.wo = ((zn > fA + fL ? zn : fA + fL) + 15) & ~15;  // W is written while SA / SLM are still read; Z replaces them at the end
+  // W is written while SA / SLM are still read (Z replaces them at the end), and it sits beyond the whole cyclic-reduction
+  // layout: a polish factors its own system there, and a polish that fails hands the ADMM system back without a new
+  // factorisation (Z comes back from a copy in global memory, W and the rows of PI were never touched)
+  pl.wo = ((zn > fA + fL + fU ? zn : fA + fL + fU) + 15) & ~15;
   pl.so = pl.wo + ((pl.PR * pl.WS + 1) & ~1);
   pl.total = pl.so + pl.nS * pl.SS;
   return pl;
@@ -122,6 +125,12 @@ constexpr int kQpSmemBudget = 28800;  // doubles per CTA (225 KB of the 227 KB a
 __host__ __device__ inline int qp_block_count(int N, int nb) { return (N + nb - 1) / nb; }
 __host__ __device__ inline int qp_even(int v) { return (v + 1) & ~1; }
 __host__ __device__ inline int qp_factor_doubles(int N, int nb) { return 3 * qp_even(qp_block_count(N, nb) * nb * nb); }
+// per resident CTA in global memory: the factor of wide blocks or the rows of the partition inverses, then the copy of Z
+// that survives a polish
+__host__ __device__ inline size_t qp_cta_global_doubles(int N, int nb) {
+  const PinvPlan pl = pinv_plan(qp_block_count(N, nb), nb);
+  return static_cast<size_t>(qp_factor_doubles(N, nb)) + static_cast<size_t>(pl.nS) * pl.ZS;
+}
 __host__ __device__ inline QpSmem qp_smem_layout(int N, int nb, int row_stride, int CN, int max_rows, bool factor_global) {
   const int M = qp_block_count(N, nb), Np = M * nb, blk = nb * nb;
   QpSmem s;
@@ -231,6 +240,7 @@ struct QpCtx {
   int pinv;              // the ADMM system is factored in its partition-inverse form (pl)
   PinvPlan pl;
   double* pi_g;          // this CTA's block of global memory for the rows of the partition inverses [PR][3 NB]
+  double* z_stash;       // ... and for the copy of Z taken before a polish
   double c, cinv, rho, rho_eq, sigma, alpha;
   __device__ __forceinline__ double* R(int r) const { return rows + static_cast<size_t>(r) * RS; }
   __device__ __forceinline__ double* F(int r) const { return rows + static_cast<size_t>(r) * RS + 2 * CN; }
@@ -2423,6 +2433,20 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
     FactorFn volatile fn = &assemble_factor<NB, false>;
     return fn(q, wts);
   };
+  // A polish factors its own system over Z (the rest of the partition-inverse form lies beyond the cyclic-reduction
+  // layout): Z is copied to global memory before and, when the polish fails, copied back — the same bytes a new
+  // factorisation of the unchanged ADMM system would produce, at a hundredth of its cost.
+  auto stash_z = [&](const bool restore) {
+    extern __shared__ double sm[];
+    double2* zs = reinterpret_cast<double2*>(sm + (q.SA - q.smbase) + q.pl.zo);
+    double2* zg = reinterpret_cast<double2*>(q.z_stash);
+    const int n2 = q.pl.nS * q.pl.ZS / 2;
+    if (restore) for (int i = tid; i < n2; i += kQpThreads) zs[i] = zg[i];
+    else for (int i = tid; i < n2; i += kQpThreads) zg[i] = zs[i];
+    __syncthreads();
+    // (the polish left its own weights in the rows' per-solve fields; a factorisation would have rebuilt them)
+    if (restore) rows_prepare_weights(q, sysw);
+  };
   { PROF_T0(); factor_ok = factorize(sysw); PROF_ADD(6); }
 
   double* dxs = q.scratch;              // [Np] last trajectory step (written on check iterations)
@@ -2691,6 +2715,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
             // is the exact minimiser no matter how rough the iterate that produced the active-set guess was
             bool verified = false;
             double p_pri = 0.0, p_dua = 0.0;
+            if (use_pinv) stash_z(false);
             const bool factored = polish_fn(verified, p_pri, p_dua);
             if (factored && verified) {
               early_verified = true;
@@ -2704,7 +2729,9 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
               have_failed_guess = true;
               restore_fn(false);
               info_pass(rho_iter);  // the polish reuses the vectors of the residual bookkeeping
-              if (!factorize(sysw)) {
+              if (use_pinv) {
+                stash_z(true);
+              } else if (!factorize(sysw)) {
                 status = QPS_NONCVX;
                 stop = true;
               }
@@ -2900,6 +2927,7 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
     } else {
       bool verified = false;
       double p_pri = 0.0, p_dua = 0.0;
+      if (use_pinv) stash_z(false);
       const bool factored = polish_once(verified, p_pri, p_dua);
       out.pol_factor_ok = factored ? 1 : 0;
       out.pol_pri = p_pri;
@@ -2917,7 +2945,9 @@ __device__ inline QpOut qp_solve_block(QpCtx& q, const QpSettings& st, bool warm
         ++round;
         eps_scale *= 0.1;
         restore_admm_state(false);
-        if (!factorize(sysw)) {  // back to the ADMM factor
+        if (use_pinv) {  // back to the ADMM factor
+          stash_z(true);
+        } else if (!factorize(sysw)) {
           status = QPS_NONCVX;
           done = true;
         }
@@ -2963,7 +2993,7 @@ __device__ __noinline__ void qp_step(const DevProblem& p, const int b, const dou
   q.RS = p.row_stride;
   const QpSmem S = qp_smem_layout(N, NB, q.RS, q.CN, p.max_rows, FG);
   if (FG || !S.factor_smem) {  // (a factor of <= 16-wide blocks that does not fit shared memory goes the same way)
-    double* fg = p.factor_g + static_cast<size_t>(blockIdx.x) * qp_factor_doubles(N, NB);
+    double* fg = p.factor_g + static_cast<size_t>(blockIdx.x) * qp_cta_global_doubles(N, NB);
     const int fb = qp_even(q.M * NB * NB);
     q.SA = fg; q.SLM = fg + fb; q.SU = fg + 2 * fb;
   } else {
@@ -2981,7 +3011,8 @@ __device__ __noinline__ void qp_step(const DevProblem& p, const int b, const dou
   q.smbase = sm;
   q.pinv = S.pinv;
   q.pl = pinv_plan(q.M, NB);
-  q.pi_g = p.factor_g + static_cast<size_t>(blockIdx.x) * qp_factor_doubles(N, NB);
+  q.pi_g = p.factor_g + static_cast<size_t>(blockIdx.x) * qp_cta_global_doubles(N, NB);
+  q.z_stash = q.pi_g + qp_factor_doubles(N, NB);
   q.rows_smem = 0;
   q.rints = rints_g;
   int* mylist = p.lists + static_cast<size_t>(b) * p.list_stride;

@@ -592,7 +592,7 @@ int tb200_problem_create(const tb200_problem_desc* d, int device, tb200_problem*
   // per-CTA regions (the persistent kernel and the kernel-level QP entry point both launch at most one CTA per SM):
   // a factor that does not fit shared memory, and the column-major copy of rows that do not
   P->factor_grid = static_cast<size_t>(P->n_sm);  // per resident CTA: the factor of wide blocks, or the rows of the partition inverses
-  ALLOC(factor_g, P->factor_grid * qp_factor_doubles(N, 2 * D));
+  ALLOC(factor_g, P->factor_grid * qp_cta_global_doubles(N, 2 * D));
   dp.soa_stride = (max_rows > qs.row_cap) ? qp_soa_doubles(max_rows, CN) : 0;
   ALLOC(soa, static_cast<size_t>(P->n_sm) * dp.soa_stride);
   {
