@@ -13,4 +13,5 @@ if [ -f trajopt_b200/csrc/libtb200_prof.so ]; then
 ( TB200_LIB=$PWD/trajopt_b200/csrc/libtb200_prof.so timeout 200 python scripts/prof_phases.py 148 cfg2 ) > gpurun_out/r02_prof_phases.log 2>&1
 fi
 ( timeout 200 python scripts/time_full.py cfg2 1024 64 ) > gpurun_out/r02_time_full.log 2>&1
-tail -3 gpurun_out/r02_pytest_gpu.log; cat gpurun_out/r02_bench.json; tail -3 gpurun_out/r02_bench.err; tail -2 gpurun_out/r02_ncu_eval.log gpurun_out/r02_ncu_solve.log; tail -5 gpurun_out/r02_time_full.log
+( timeout 300 python scripts/time_cfg.py cfg3 64 50; timeout 200 python scripts/time_cfg.py cfg4 64 40 ) > gpurun_out/r02_time_cfg34.log 2>&1
+tail -3 gpurun_out/r02_pytest_gpu.log; cat gpurun_out/r02_bench.json; tail -3 gpurun_out/r02_bench.err; tail -n 2 gpurun_out/r02_ncu_eval.log; tail -n 2 gpurun_out/r02_ncu_solve.log; cat gpurun_out/r02_time_cfg34.log; tail -5 gpurun_out/r02_time_full.log
