@@ -163,7 +163,7 @@ __device__ __forceinline__ void eval_step_impl(const DevProblem& p, const EvalEx
   EVAL_PROF_BEGIN();
   const int T = p.T, N = p.N, L = p.L, O = p.O;
   if (mode != EVAL_ONLY && p.status[b] != 5 /*running == INVALID*/) return;
-  if (mode == EVAL_STEP && p.qp_done[b] == 0) return;  // its QP is still being solved (time-sliced)
+  if (mode == EVAL_STEP && p.qp_done[b] == 0) return;  // (defensive: the QP step of this trajectory has not finished)
   const bool qp_failed = (mode == EVAL_STEP) && (p.qp_status[b] != 0);
   if (tid == 0 && !qp_failed) atomicAdd(p.active_count + 1, 1);  // trajectories actually convexified (bench: bytes moved)
   const int n_mask_words = p.n_coll_objs * p.coll_words;

@@ -22,10 +22,14 @@
 // The hinge / abs auxiliary variables of the l1 penalty are eliminated per row in closed form (cancellation
 // free), exactly as in DESIGN.md §4.2.
 //
+// Short trajectories (M <= 15 blocks of 14, rows on chip: the headline case) keep their ADMM system in another form,
+// the partition inverse (PinvPlan below): a solve is two dependent steps instead of seven; the cyclic reduction stays
+// for their polish system and for everything larger.
+//
 // Sizes.  The level loops of the factorisation and of the generic solve run over task chunks, so the number of
-// blocks M is not tied to the CTA size (configs[3]: 50 waypoints = 25 blocks of 14).  The register-resident solve of
-// the ADMM loop is used whenever its roles fit the 256 threads (M <= 15 at 7 joints), the generic solve (factor rows
-// read from memory) otherwise.  With 14 joints (blocks of 28, configs[4]) the factor (3*M*28*28 doubles = 376 KB at
+// blocks M is not tied to the CTA size (configs[3]: 50 waypoints = 25 blocks of 14).  Without the partition form the
+// register-resident solve of the ADMM loop is used whenever its roles fit the 256 threads (M <= 15 at 7 joints), the
+// generic solve (factor rows read from memory) otherwise.  With 14 joints (blocks of 28, configs[4]) the factor (3*M*28*28 doubles = 376 KB at
 // 40 waypoints) does not fit shared memory: it lives in a per-CTA region of global memory that stays L2 resident
 // (template flag FG), everything else is unchanged.
 #pragma once
