@@ -862,7 +862,7 @@ CvxStatus Model::optimize() {
     // the POLISHED duals when polish succeeded.  On degenerate active sets (linearly dependent bounds + rows,
     // common at trust-box corners) those are non-unique and only fixed by the 1e-6 regularisation, i.e. not
     // reproducible across linear-algebra back ends.  Primal x from polish, duals from the last ADMM iterate.
-    ws.y = last_.y_admm;
+    ws.y = settings_.warm_polished_duals ? last_.y : last_.y_admm;
     ws.rho = last_.rho;
   }
   last_ = qp_solve(qp, settings_, ws.valid ? &ws : nullptr);

@@ -105,6 +105,7 @@ struct QPSettings {
   int early_polish_every = 0;  // >0: also try the (verified) polish every this many iterations (optimisation O1)
   int early_polish_from = 50;
   int early_polish_stable = 1; // only try when the active-set guess is unchanged since the previous test and has not failed yet
+  int warm_polished_duals = 0; // 1: warm start the next QP from the POLISHED duals as OSQP / the reference do (deviation D1 off)
 };
 enum QPStatus {
   QP_SOLVED = 1,

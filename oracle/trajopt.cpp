@@ -683,6 +683,15 @@ QPSettings qpSettingsFrom(const tb200_qp_settings& q) {
   s.adaptive_rho = q.adaptive_rho; s.adaptive_rho_interval = q.adaptive_rho_interval;
   s.polishing = q.polishing; s.polish_refine_iter = q.polish_refine_iter; s.warm_starting = q.warm_starting;
   s.early_polish_every = q.early_polish_every; s.early_polish_from = q.early_polish_from;
+  // ORACLE_PLAIN_OSQP=1 (tests only): OSQP's own behaviour - no early polish (O1), the polish accepted by OSQP's rule
+  // without verification rounds (D2), the next QP warm started from the polished duals (D1)
+  if (const char* e = getenv("ORACLE_PLAIN_OSQP")) {
+    if (atoi(e)) {
+      s.early_polish_every = 0;
+      s.verify_rounds = 0;
+      s.warm_polished_duals = 1;
+    }
+  }
   if (const char* e = getenv("ORACLE_EARLY_STABLE")) s.early_polish_stable = atoi(e);
   if (const char* e = getenv("ORACLE_EARLY_EVERY")) s.early_polish_every = atoi(e);
   return s;

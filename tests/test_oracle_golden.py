@@ -459,3 +459,27 @@ def test_early_polish_default_keeps_the_sqp_outcome(oracle, name, B):
     assert np.abs(r1["cnt_viols"][same]).max() < 1e-3 or np.abs(r0["cnt_viols"][same]).max() >= 1e-3
     # the early polish must pay for itself: fewer ADMM iterations in total
     assert r1["n_admm_iters"].sum() <= r0["n_admm_iters"].sum()
+
+
+@pytest.mark.parametrize("name", ["config1", "config2"])
+def test_plain_osqp_mode_of_the_oracle(oracle, name, monkeypatch):
+    """ORACLE_PLAIN_OSQP=1 switches the three QP-level deviations off together: no early polish
+    (O1), OSQP's own polish acceptance without verification rounds (D2), warm start from the polished duals (D1) — the
+    restated OSQP as the reference drives it.  What holds between the two modes, and what does not: the SQP ends in the
+    same status for nearly every trajectory and both end feasible, but the final costs differ for about half of them (by
+    up to ~10 %): an unverified QP solution is an eps-accurate point, and the accept / converge tests of the SQP react to
+    it (some trajectories stop after 2 QPs in plain mode where the exact QP solutions keep improving for 60).  GPU parity
+    is claimed against the oracle WITH the deviations; this test pins the size of the gap to plain OSQP."""
+    d1 = getattr(problems, name)(B=16, T=12)
+    r1 = oracle.solve_batch(d1)
+    monkeypatch.setenv("ORACLE_PLAIN_OSQP", "1")
+    d0 = getattr(problems, name)(B=16, T=12)
+    r0 = oracle.solve_batch(d0)
+    assert (r1["status"] == r0["status"]).mean() >= 0.85
+    conv = (r1["status"] == capi.OPT_CONVERGED) & (r0["status"] == capi.OPT_CONVERGED)
+    assert conv.sum() >= 8
+    assert r1["cnt_viols"][conv].max() < 1e-3 and r0["cnt_viols"][conv].max() < 1e-3
+    rel = np.abs(r1["total_cost"] - r0["total_cost"]) / np.maximum(1.0, np.abs(r0["total_cost"]))
+    assert rel[conv].max() < 0.15
+    # the exact QP solutions never do worse on a converged trajectory than the eps-accurate ones by more than noise
+    assert (r1["total_cost"][conv] <= r0["total_cost"][conv] * (1 + 1e-3) + 1e-6).mean() >= 0.9

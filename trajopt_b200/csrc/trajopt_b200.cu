@@ -139,10 +139,11 @@ void tb200_osqp_order_qp_settings(tb200_qp_settings* s) {
   s->early_polish_every = 0;  // polish only after ADMM converged, as OSQP does
   s->early_polish_from = 0;
 }
-// The reference's OSQPSettings (osqp_interface.cpp:78-90 over osqp_set_default_settings) plus three choices that are NOT
-// OSQP's: a fixed adaptive_rho_interval (OSQP's default is wall-clock based), and the early
+// The reference's OSQPSettings (osqp_interface.cpp:78-90 over osqp_set_default_settings) plus two choices that are NOT
+// OSQP's: a fixed adaptive_rho_interval (D0: OSQP's default is wall-clock based), and the early
 // VERIFIED polish (O1: early_polish_every / early_polish_from = 25) - same minimiser, ~40 % fewer ADMM iterations;
-// tb200_osqp_order_qp_settings turns it off.
+// tb200_osqp_order_qp_settings turns it off.  Two more deviations are not settings but how the QP step works: the warm
+// start from the ADMM duals (D1) and the verified polish (D2).
 void tb200_default_qp_settings(tb200_qp_settings* s) {
   s->rho = 0.1; s->sigma = 1e-6; s->alpha = 1.6;
   s->eps_abs = 1e-4; s->eps_rel = 1e-6;
